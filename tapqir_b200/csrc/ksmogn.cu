@@ -1,0 +1,271 @@
+// K1: fused spot render + offset-marginalised Gamma image likelihood, forward and reverse mode,
+// one warp per (AOI, frame, channel) patch.
+//
+// Replaces distributions/util.py:15-64 (gaussian_spots), distributions/ksmogn.py:146-169 and
+// ksmogn.py:187-238 (KSMOGN.log_prob; KeOps Genred LogSumExp or the torch branch) and their
+// autograd backward.  The reference materialises (2^K, nb, fb, C, K, P, P, 2) temporaries; here a
+// patch's pixels are read once from HBM (392 B as uint16 at P=14), everything else lives in
+// registers / a 448 B per-warp row-column table, and the reverse pass is computed in the same
+// sweep because its upstream weights are known before the sweep starts.
+#include "common.cuh"
+#include "ksmogn_core.cuh"
+
+namespace tq {
+
+template <typename T> struct KsmognArgs {
+    tq_patch_view v;
+    const T* height; const T* width; const T* x; const T* y; const T* background;
+    const T* gain; const T* mcfg; const T* W;
+    T* logp; T* g_height; T* g_width; T* g_x; T* g_y; T* g_background; T* g_rate;
+    int64_t U;
+};
+
+template <typename PIX> __device__ __forceinline__ float load_pixel_f(const PIX* p) { return (float)*p; }
+
+constexpr int kWarpsPerBlock = 4;
+
+// smem layout: [off_s (O)] [off_w (O)] [per warp: gx (K*kMaxP), gy (K*kMaxP)]
+template <typename T, typename PIX, int NM, bool BWD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ksmogn_kernel(const KsmognArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* off_s = reinterpret_cast<T*>(smem_raw);
+    T* off_w = off_s + a.v.O;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* gx = off_w + a.v.O + warp * (2 * kK * kMaxP);
+    T* gy = gx + kK * kMaxP;
+
+    for (int j = threadIdx.x; j < a.v.O; j += blockDim.x) {
+        off_s[j] = static_cast<const T*>(a.v.offset_samples)[j];
+        off_w[j] = static_cast<const T*>(a.v.offset_logits)[j];
+    }
+    T mcfg[NM][kK];
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int k = 0; k < kK; ++k) mcfg[m][k] = a.mcfg[m * kK + k];
+    const T gain = a.gain[0];
+    const T rate = T(1) / gain;
+    const T log_rate = Real<T>::log(rate);
+    __syncthreads();
+
+    const int P = a.v.P, PP = P * P;
+    const PIX* pixels = static_cast<const PIX*>(a.v.pixels);
+    const T* xy = static_cast<const T*>(a.v.xy);
+
+    for (int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp; u < a.U;
+         u += (int64_t)gridDim.x * kWarpsPerBlock) {
+        const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        PatchSpots<T> s;
+        const T tx = xy[ui.patch * 2 + 0], ty = xy[ui.patch * 2 + 1];
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            s.h[k] = a.height[k * a.U + u];
+            s.w[k] = a.width[k * a.U + u];
+            s.cx[k] = a.x[k * a.U + u] + tx;
+            s.cy[k] = a.y[k * a.U + u] + ty;
+        }
+        s.b = a.background[u];
+        T W[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) W[m] = BWD ? a.W[m * a.U + u] : T(0);
+
+        // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
+        __syncwarp();
+        for (int idx = lane; idx < 2 * kK * P; idx += 32) {
+            const int axis = idx / (kK * P), rem = idx - axis * (kK * P);
+            const int k = rem / P, i = rem - k * P;
+            if (axis == 0) gx[k * kMaxP + i] = axis_factor<T>(i, s.cx[k], s.w[k]);
+            else           gy[k * kMaxP + i] = axis_factor<T>(i, s.cy[k], s.w[k]);
+        }
+        __syncwarp();
+
+        PatchOut<T, NM> out;
+        out.zero();
+        const PIX* pix = pixels + ui.patch * PP;
+        for (int p = lane; p < PP; p += 32) {
+            const int row = p / P, col = p - row * P;
+            T gxk[kK], gyk[kK];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                gxk[k] = gx[k * kMaxP + col];
+                gyk[k] = gy[k * kMaxP + row];
+            }
+            pixel_accumulate<T, NM, BWD>(T(pix[p]), gxk, gyk, col, row, s, mcfg, rate, log_rate,
+                                         a.v.O, off_s, off_w, W, out);
+        }
+#pragma unroll
+        for (int m = 0; m < NM; ++m) out.logp[m] = warp_sum(out.logp[m]);
+        if (BWD) {
+            out.g_b = warp_sum(out.g_b);
+            out.g_rate = warp_sum(out.g_rate);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                out.g_h[k] = warp_sum(out.g_h[k]);
+                out.g_w[k] = warp_sum(out.g_w[k]);
+                out.g_x[k] = warp_sum(out.g_x[k]);
+                out.g_y[k] = warp_sum(out.g_y[k]);
+            }
+        }
+        if (lane == 0) {
+            if (a.logp) {
+#pragma unroll
+                for (int m = 0; m < NM; ++m) a.logp[m * a.U + u] = out.logp[m];
+            }
+            if (BWD) {
+                a.g_background[u] = out.g_b;
+                a.g_rate[u] = out.g_rate;
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    a.g_height[k * a.U + u] = out.g_h[k];
+                    a.g_width[k * a.U + u] = out.g_w[k];
+                    a.g_x[k * a.U + u] = out.g_x[k];
+                    a.g_y[k * a.U + u] = out.g_y[k];
+                }
+            }
+        }
+    }
+}
+
+template <typename T, typename PIX, int NM, bool BWD>
+static int launch_ksmogn(const KsmognArgs<T>& a, cudaStream_t st) {
+    if (a.U == 0) return TQ_OK;
+    const size_t smem = sizeof(T) * (2 * (size_t)a.v.O + kWarpsPerBlock * 2 * kK * kMaxP);
+    auto kern = ksmogn_kernel<T, PIX, NM, BWD>;
+    if (smem > 48 * 1024) {
+        int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                              "cudaFuncSetAttribute(ksmogn)");
+        if (st2 != TQ_OK) return st2;
+    }
+    const int64_t blocks_needed = (a.U + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = (int64_t)sm_count() * 16;  // 16 x 4 warps = full residency per SM
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
+    TQ_LAUNCH_CHECK("ksmogn_kernel launch");
+    return TQ_OK;
+}
+
+template <typename T, int NM, bool BWD>
+static int dispatch_pix(const KsmognArgs<T>& a, cudaStream_t st) {
+    switch (a.v.pixtype) {
+        case TQ_PIX_U16: return launch_ksmogn<T, uint16_t, NM, BWD>(a, st);
+        case TQ_PIX_F32: return launch_ksmogn<T, float, NM, BWD>(a, st);
+        case TQ_PIX_F64: return launch_ksmogn<T, double, NM, BWD>(a, st);
+    }
+    set_error("ksmogn: unknown pixtype %d", a.v.pixtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T, bool BWD>
+static int run_ksmogn(const tq_patch_view* view, const void* height, const void* width, const void* x,
+                      const void* y, const void* background, const void* gain, const void* mcfg, int NM,
+                      const void* W, void* logp, void* g_height, void* g_width, void* g_x, void* g_y,
+                      void* g_background, void* g_rate, void* stream) {
+    KsmognArgs<T> a;
+    a.v = *view;
+    a.height = (const T*)height; a.width = (const T*)width; a.x = (const T*)x; a.y = (const T*)y;
+    a.background = (const T*)background; a.gain = (const T*)gain; a.mcfg = (const T*)mcfg;
+    a.W = (const T*)W; a.logp = (T*)logp;
+    a.g_height = (T*)g_height; a.g_width = (T*)g_width; a.g_x = (T*)g_x; a.g_y = (T*)g_y;
+    a.g_background = (T*)g_background; a.g_rate = (T*)g_rate;
+    a.U = (int64_t)view->nb * view->fb * view->C;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (NM == 1) return dispatch_pix<T, 1, BWD>(a, st);
+    if (NM == kM) return dispatch_pix<T, kM, BWD>(a, st);
+    set_error("ksmogn: NM must be 1 or %d, got %d", kM, NM);
+    return TQ_ERR_UNSUPPORTED;
+}
+
+static int check_view(const tq_patch_view* v) {
+    TQ_CHECK_ARG(v != nullptr, "view is NULL");
+    TQ_CHECK_ARG(v->nb >= 0 && v->fb >= 0 && v->C >= 1, "bad minibatch shape");
+    TQ_CHECK_ARG(v->P >= 2 && v->P <= kMaxP, "P must be in [2, 32]");
+    TQ_CHECK_ARG(v->O >= 1, "need at least one offset bin");
+    TQ_CHECK_ARG(v->pixels && v->xy && v->offset_samples && v->offset_logits, "NULL dataset pointer");
+    return TQ_OK;
+}
+
+// ---- gaussian_spots -----------------------------------------------------------------------------
+template <typename T>
+__global__ void gaussian_spots_kernel(int64_t U, int P, const T* __restrict__ height,
+                                      const T* __restrict__ width, const T* __restrict__ x,
+                                      const T* __restrict__ y, const T* __restrict__ target,
+                                      const T* __restrict__ m, T* __restrict__ out) {
+    const int64_t total = U * kK * P * P;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % P);
+        const int row = (int)((i / P) % P);
+        const int k = (int)((i / ((int64_t)P * P)) % kK);
+        const int64_t u = i / ((int64_t)P * P * kK);
+        const T w = width[k * U + u];
+        T h = height[k * U + u];
+        if (m) h *= m[k * U + u];
+        const T cx = x[k * U + u] + target[u * 2 + 0];
+        const T cy = y[k * U + u] + target[u * 2 + 1];
+        out[i] = h * axis_factor<T>(col, cx, w) * axis_factor<T>(row, cy, w)
+                 / (T(6.283185307179586476925) * w * w);
+    }
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_gaussian_spots(int dtype, int64_t U, int P, const void* height, const void* width,
+                                 const void* x, const void* y, const void* target_xy, const void* m,
+                                 void* out, void* stream) {
+    TQ_CHECK_ARG(U >= 0 && P >= 1, "bad shape");
+    if (U == 0) return TQ_OK;
+    TQ_CHECK_ARG(height && width && x && y && target_xy && out, "NULL pointer");
+    const int64_t total = U * kK * P * P;
+    const int block = 256;
+    int64_t grid = (total + block - 1) / block;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32)
+        gaussian_spots_kernel<float><<<(int)grid, block, 0, st>>>(U, P, (const float*)height, (const float*)width,
+            (const float*)x, (const float*)y, (const float*)target_xy, (const float*)m, (float*)out);
+    else if (dtype == TQ_F64)
+        gaussian_spots_kernel<double><<<(int)grid, block, 0, st>>>(U, P, (const double*)height, (const double*)width,
+            (const double*)x, (const double*)y, (const double*)target_xy, (const double*)m, (double*)out);
+    else { set_error("tq_gaussian_spots: bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("gaussian_spots_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_ksmogn_fwd(int dtype, const tq_patch_view* view, const void* height, const void* width,
+                             const void* x, const void* y, const void* background, const void* gain,
+                             const void* mcfg, int NM, void* logp, void* stream) {
+    int st = check_view(view);
+    if (st != TQ_OK) return st;
+    TQ_CHECK_ARG(height && width && x && y && background && gain && mcfg && logp, "NULL pointer");
+    if (dtype == TQ_F32)
+        return run_ksmogn<float, false>(view, height, width, x, y, background, gain, mcfg, NM, nullptr, logp,
+                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    if (dtype == TQ_F64)
+        return run_ksmogn<double, false>(view, height, width, x, y, background, gain, mcfg, NM, nullptr, logp,
+                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    set_error("tq_ksmogn_fwd: bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+extern "C" int tq_ksmogn_fwd_bwd(int dtype, const tq_patch_view* view, const void* height, const void* width,
+                                 const void* x, const void* y, const void* background, const void* gain,
+                                 const void* mcfg, int NM, const void* W, void* logp, void* g_height,
+                                 void* g_width, void* g_x, void* g_y, void* g_background, void* g_rate,
+                                 void* stream) {
+    int st = check_view(view);
+    if (st != TQ_OK) return st;
+    TQ_CHECK_ARG(height && width && x && y && background && gain && mcfg && W, "NULL input pointer");
+    TQ_CHECK_ARG(g_height && g_width && g_x && g_y && g_background && g_rate, "NULL gradient pointer");
+    if (dtype == TQ_F32)
+        return run_ksmogn<float, true>(view, height, width, x, y, background, gain, mcfg, NM, W, logp,
+                                       g_height, g_width, g_x, g_y, g_background, g_rate, stream);
+    if (dtype == TQ_F64)
+        return run_ksmogn<double, true>(view, height, width, x, y, background, gain, mcfg, NM, W, logp,
+                                        g_height, g_width, g_x, g_y, g_background, g_rate, stream);
+    set_error("tq_ksmogn_fwd_bwd: bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}

@@ -1,0 +1,333 @@
+// Device math shared by the cosmos kernels (sm_100a).
+//
+// * Real<T>: thin wrappers so every kernel is written once and instantiated for float (the
+//   production path) and double (the CLI's dtype, main.py:428; also the exact-parity check).
+// * digamma / lgamma: closed forms used by the likelihood and by the log-densities.
+// * std_gamma_grad / beta_grad: the implicit reparameterisation gradients.  The reference gets
+//   these from torch (ATen ``_standard_gamma_grad`` / ``_dirichlet_grad``, reached through
+//   ``Gamma.rsample`` / ``Beta.rsample`` in models/cosmos.py:342-368,408-462).  ATen's versions are
+//   piecewise *approximations* (Taylor / Rice saddle point / fitted rationals), so gradient parity
+//   with the reference requires the same published algorithm and coefficient tables
+//   (torch 2.x, ATen/native/Distributions.h, BSD-3); they are restated here.
+// * Philox4x32-10 + Marsaglia-Tsang: in-kernel sampling for the production (non-replay) path.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace tq {
+
+constexpr int kK = 2;          // spots per image (cosmos K, BASELINE configs use 2)
+constexpr int kM = 1 << kK;    // enumerated spot-presence configurations
+constexpr int kTheta = kK + 1; // theta states
+constexpr int kZ = 2;          // z states (S = 1)
+
+#ifdef __CUDACC__
+#define TQ_DEV __device__ __forceinline__
+#define TQ_HD __host__ __device__ __forceinline__
+#else
+#define TQ_DEV inline
+#define TQ_HD inline
+#endif
+
+template <typename T> struct Real;
+template <> struct Real<float> {
+    static TQ_HD float log(float x) { return logf(x); }
+    static TQ_HD float exp(float x) { return expf(x); }
+    static TQ_HD float log1p(float x) { return log1pf(x); }
+    static TQ_HD float lgamma(float x) { return lgammaf(x); }
+    static TQ_HD float sqrt(float x) { return sqrtf(x); }
+    static TQ_HD float pow(float x, float y) { return powf(x, y); }
+    static TQ_HD float floor(float x) { return floorf(x); }
+    static TQ_HD float max(float a, float b) { return fmaxf(a, b); }
+    static TQ_HD float min(float a, float b) { return fminf(a, b); }
+    static TQ_HD float abs(float a) { return fabsf(a); }
+    static TQ_HD float inf() { return INFINITY; }
+    static TQ_HD float eps() { return 1.1920928955078125e-07f; }
+    static TQ_HD float tiny() { return 1.17549435e-38f; }
+};
+template <> struct Real<double> {
+    static TQ_HD double log(double x) { return ::log(x); }
+    static TQ_HD double exp(double x) { return ::exp(x); }
+    static TQ_HD double log1p(double x) { return ::log1p(x); }
+    static TQ_HD double lgamma(double x) { return ::lgamma(x); }
+    static TQ_HD double sqrt(double x) { return ::sqrt(x); }
+    static TQ_HD double pow(double x, double y) { return ::pow(x, y); }
+    static TQ_HD double floor(double x) { return ::floor(x); }
+    static TQ_HD double max(double a, double b) { return fmax(a, b); }
+    static TQ_HD double min(double a, double b) { return fmin(a, b); }
+    static TQ_HD double abs(double a) { return fabs(a); }
+    static TQ_HD double inf() { return (double)INFINITY; }
+    static TQ_HD double eps() { return 2.220446049250313e-16; }
+    static TQ_HD double tiny() { return 2.2250738585072014e-308; }
+};
+
+// ---- warp helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+// ---- digamma --------------------------------------------------------------------------------
+// psi(x) for x > 0: recurrence up to x >= 10, then the asymptotic series (same construction as
+// ATen's digamma_one, Cephes-derived, so the reparameterisation gradients below agree with torch).
+template <typename T> TQ_HD T digamma(T x) {
+    if (x == T(0)) return Real<T>::inf();
+    T acc = T(0);
+    while (x < T(10)) {
+        acc -= T(1) / x;
+        x += T(1);
+    }
+    if (x == T(10)) return acc + T(2.25175258906672110764);
+    T z = T(1) / (x * x);
+    // z * (A0 z^6 .. A6) evaluated by Horner
+    T poly = T(8.33333333333333333333E-2);
+    poly = poly * z + T(-2.10927960927960927961E-2);
+    poly = poly * z + T(7.57575757575757575758E-3);
+    poly = poly * z + T(-4.16666666666666666667E-3);
+    poly = poly * z + T(3.96825396825396825397E-3);
+    poly = poly * z + T(-8.33333333333333333333E-3);
+    poly = poly * z + T(8.33333333333333333333E-2);
+    return acc + Real<T>::log(x) - T(0.5) / x - z * poly;
+}
+
+// ---- reparameterisation gradient of a standard Gamma(alpha) draw x: d x / d alpha ------------
+template <typename T> TQ_HD T std_gamma_grad(T alpha, T x) {
+    using R = Real<T>;
+    if (x < T(0.8)) {
+        // Taylor series of the lower incomplete gamma function around x = 0
+        T numer = T(1), denom = alpha;
+        T s1 = numer / denom, s2 = numer / (denom * denom);
+#pragma unroll
+        for (int i = 1; i <= 5; ++i) {
+            numer *= -x / T(i);
+            denom += T(1);
+            s1 += numer / denom;
+            s2 += numer / (denom * denom);
+        }
+        const T pow_x_alpha = R::pow(x, alpha);
+        const T pdf = R::pow(x, alpha - T(1)) * R::exp(-x);
+        const T cdf = pow_x_alpha * s1;
+        const T cdf_alpha = (R::log(x) - digamma(alpha)) * cdf - pow_x_alpha * s2;
+        const T res = -cdf_alpha / pdf;
+        return (res != res) ? T(0) : res;
+    }
+    if (alpha > T(8)) {
+        // Rice saddle-point expansion; a Taylor patch removes the singularity at x = alpha
+        if (T(0.9) * alpha <= x && x <= T(1.1) * alpha) {
+            const T n1 = T(1) + T(24) * alpha * (T(1) + T(12) * alpha);
+            const T n2 = T(1440) * (alpha * alpha) + T(6) * x * (T(53) - T(120) * x)
+                         - T(65) * x * x / alpha + alpha * (T(107) + T(3600) * x);
+            const T den = T(1244160) * (alpha * alpha) * (alpha * alpha);
+            return n1 * n2 / den;
+        }
+        const T den = R::sqrt(T(8) * alpha);
+        const T t2 = den / (alpha - x);
+        const T t3 = R::pow(x - alpha - alpha * R::log(x / alpha), T(-1.5));
+        const T t23 = (x < alpha) ? t2 - t3 : t2 + t3;
+        const T t1 = R::log(x / alpha) * t23 - R::sqrt(T(2) / alpha) * (alpha + x) / ((alpha - x) * (alpha - x));
+        const T stirling = T(1) + T(1) / (T(12) * alpha) * (T(1) + T(1) / (T(24) * alpha));
+        return -stirling * (x * t1) / den;
+    }
+    // bivariate rational fit in (log(x/alpha), log alpha)
+    const T u = R::log(x / alpha);
+    const T v = R::log(alpha);
+    const T c[3][8] = {
+        {T(0.16009398), T(-0.094634809), T(0.025146376), T(-0.0030648343), T(1), T(0.32668115), T(0.10406089), T(0.0014179084)},
+        {T(0.53487893), T(0.1298071), T(0.065735949), T(-0.0015649758), T(0.16639465), T(0.020070113), T(-0.0035938915), T(-0.00058392623)},
+        {T(0.040121004), T(-0.0065914022), T(-0.0026286047), T(-0.0013441777), T(0.017050642), T(-0.0021309326), T(0.00085092367), T(-1.5247877e-07)},
+    };
+    T cv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cv[i] = c[0][i] + u * (c[1][i] + u * c[2][i]);
+    const T p = cv[0] + v * (cv[1] + v * (cv[2] + v * cv[3]));
+    const T q = cv[4] + v * (cv[5] + v * (cv[6] + v * cv[7]));
+    return R::exp(p / q);
+}
+
+// ---- scaled reparameterisation gradient of a Beta(alpha, total-alpha) draw x wrt alpha --------
+//   -(d/dalpha cdf) / pdf / (1 - x); total is passed so that the 2-Dirichlet form
+//   dx/dc1 = (1-x) g(x, c1, tot),  dx/dc0 = -x g(1-x, c0, tot)   follows (torch dirichlet.py backward).
+template <typename T> TQ_HD T beta_grad_alpha_small(T x, T alpha, T beta) {
+    using R = Real<T>;
+    const T factor = digamma(alpha) - digamma(alpha + beta) - R::log(x);
+    T numer = T(1);
+    T series = numer / alpha * (factor + T(1) / alpha);
+#pragma unroll
+    for (int i = 1; i <= 10; ++i) {
+        numer *= (T(i) - beta) * x / T(i);
+        const T denom = alpha + T(i);
+        series += numer / denom * (factor + T(1) / denom);
+    }
+    const T res = x * R::pow(T(1) - x, -beta) * series;
+    return (res != res) ? T(0) : res;
+}
+
+template <typename T> TQ_HD T beta_grad_beta_small(T x, T alpha, T beta) {
+    using R = Real<T>;
+    const T factor = digamma(alpha + beta) - digamma(beta);
+    T numer = T(1), betas = T(1), dbetas = T(0), series = factor / alpha;
+#pragma unroll
+    for (int i = 1; i <= 8; ++i) {
+        numer *= -x / T(i);
+        dbetas = dbetas * (beta - T(i)) + betas;
+        betas = betas * (beta - T(i));
+        series += numer / (alpha + T(i)) * (dbetas + factor * betas);
+    }
+    const T res = -R::pow(T(1) - x, T(1) - beta) * series;
+    return (res != res) ? T(0) : res;
+}
+
+template <typename T> TQ_HD T beta_grad_alpha_mid(T x, T alpha, T beta) {
+    using R = Real<T>;
+    const T total = alpha + beta;
+    const T mean = alpha / total;
+    const T sd = R::sqrt(alpha * beta / (total + T(1))) / total;
+    if (mean - T(0.1) * sd <= x && x <= mean + T(0.1) * sd) {
+        const T b2 = beta * beta;
+        const T poly = T(47) * x * b2 * b2 + alpha * (
+                           (T(43) + T(20) * (T(16) + T(27) * beta) * x) * b2 * beta + alpha * (
+                           T(3) * (T(59) + T(180) * beta - T(90) * x) * b2 + alpha * (
+                           (T(453) + T(1620) * beta * (T(1) - x) - T(455) * x) * beta + alpha * (
+                           T(8) * (T(1) - x) * (T(135) * beta - T(11))))));
+        const T pn = (T(1) + T(12) * alpha) * (T(1) + T(12) * beta) / (total * total);
+        const T pd = T(12960) * alpha * alpha * alpha * b2 * (T(1) + T(12) * total);
+        return pn / (T(1) - x) * poly / pd;
+    }
+    const T prefactor = -x / R::sqrt(T(2) * alpha * beta / total);
+    const T stirling = (T(1) + T(1) / (T(12) * alpha) + T(1) / (T(288) * alpha * alpha))
+                     * (T(1) + T(1) / (T(12) * beta) + T(1) / (T(288) * beta * beta))
+                     / (T(1) + T(1) / (T(12) * total) + T(1) / (T(288) * total * total));
+    const T t1n = T(2) * (alpha * alpha) * (x - T(1)) + alpha * beta * (x - T(1)) - x * (beta * beta);
+    const T axbx = alpha * (x - T(1)) + beta * x;
+    const T t1d = R::sqrt(T(2) * alpha / beta) * R::pow(total, T(1.5)) * axbx * axbx;
+    const T t1 = t1n / t1d;
+    const T t2 = T(0.5) * R::log(alpha / (total * x));
+    const T t3 = R::sqrt(T(8) * alpha * beta / total) / (beta * x + alpha * (x - T(1)));
+    const T t4b = beta * R::log(beta / (total * (T(1) - x))) + alpha * R::log(alpha / (total * x));
+    const T t4 = R::pow(t4b, T(-1.5));
+    return stirling * prefactor * (t1 + t2 * (t3 + (x < mean ? t4 : -t4)));
+}
+
+template <typename T> TQ_HD T beta_grad(T x, T alpha, T total) {
+    using R = Real<T>;
+    const T beta = total - alpha;
+    const T boundary = total * x * (T(1) - x);
+    if (x <= T(0.5) && boundary < T(2.5)) return beta_grad_alpha_small(x, alpha, beta);
+    if (x >= T(0.5) && boundary < T(0.75)) return -beta_grad_beta_small(T(1) - x, beta, alpha);
+    if (alpha > T(6) && beta > T(6)) return beta_grad_alpha_mid(x, alpha, beta);
+    // rational correction to an analytic approximation (coefficients: torch Distributions.h)
+    const T c[2][3][3][4] = {
+        {{{T(1.003668233), T(-0.01061107488), T(-0.0657888334), T(0.01201642863)},
+          {T(0.6336835991), T(-0.3557432599), T(0.05486251648), T(-0.001465281033)},
+          {T(-0.03276231906), T(0.004474107445), T(0.002429354597), T(-0.0001557569013)}},
+         {{T(0.221950385), T(-0.3187676331), T(0.01799915743), T(0.01074823814)},
+          {T(-0.2951249643), T(0.06219954479), T(0.01535556598), T(0.001550077057)},
+          {T(0.02155310298), T(0.004170831599), T(0.001292462449), T(6.976601077e-05)}},
+         {{T(-0.05980841433), T(0.008441916499), T(0.01085618172), T(0.002319392565)},
+          {T(0.02911413504), T(0.01400243777), T(-0.002721828457), T(0.000751041181)},
+          {T(0.005900514878), T(-0.001936558688), T(-9.495446725e-06), T(5.385558597e-05)}}},
+        {{{T(1), T(-0.02924021934), T(-0.04438342661), T(0.007285809825)},
+          {T(0.6357567472), T(-0.3473456711), T(0.05454656494), T(-0.002407477521)},
+          {T(-0.03301322327), T(0.004845219414), T(0.00231480583), T(-0.0002307248149)}},
+         {{T(0.5925320577), T(-0.1757678135), T(0.01505928619), T(0.000564515273)},
+          {T(0.1014815858), T(-0.06589186703), T(0.01272886114), T(-0.0007316646956)},
+          {T(-0.007258481865), T(0.001096195486), T(0.0003934994223), T(-4.12701925e-05)}},
+         {{T(0.06469649321), T(-0.0236701437), T(0.002902096474), T(-5.896963079e-05)},
+          {T(0.001925008108), T(-0.002869809258), T(0.0008000589141), T(-6.063713228e-05)},
+          {T(-0.0003477407336), T(6.959756487e-05), T(1.097287507e-05), T(-1.650964693e-06)}}},
+    };
+    const T u = R::log(x);
+    const T a = R::log(alpha) - u;
+    const T b = R::log(total) - a;
+    const T pu[3] = {T(1), u, u * u};
+    const T pa[3] = {T(1), a, a * a};
+    T p = T(0), q = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const T ua = pu[i] * pa[j];
+            p += ua * (c[0][i][j][0] + b * (c[0][i][j][1] + b * (c[0][i][j][2] + b * c[0][i][j][3])));
+            q += ua * (c[1][i][j][0] + b * (c[1][i][j][1] + b * (c[1][i][j][2] + b * c[1][i][j][3])));
+        }
+    const T approx = x * (digamma(total) - digamma(alpha)) / beta;
+    return p / q * approx;
+}
+
+// ---- Philox4x32-10 counter RNG -----------------------------------------------------------------
+struct Philox {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t out[4];
+    int have;
+    TQ_HD Philox(uint64_t seed, uint64_t stream, uint64_t offset) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = (uint32_t)offset; ctr[1] = (uint32_t)(offset >> 32);
+        ctr[2] = (uint32_t)stream; ctr[3] = (uint32_t)(stream >> 32);
+        have = 0;
+    }
+    TQ_HD void round(uint32_t (&c)[4], const uint32_t (&k)[2]) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    TQ_HD void refill() {
+        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+        uint32_t k[2] = {key[0], key[1]};
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, k);
+            k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+        if (++ctr[0] == 0) ++ctr[1];
+        have = 4;
+    }
+    TQ_HD uint32_t next() {
+        if (have == 0) refill();
+        return out[--have];
+    }
+    // uniform in (0, 1]
+    TQ_HD float uniform() { return ((float)(next() >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+    TQ_HD double uniform_d() {
+        const uint64_t hi = next(), lo = next();
+        return ((double)(((hi << 32) | lo) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    }
+    TQ_HD float normal() {  // Box-Muller, one value per call (the partner is discarded)
+        const float u1 = uniform(), u2 = uniform();
+        return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+    }
+};
+
+// Marsaglia & Tsang (2000) standard gamma sampler (doi:10.1145/358407.358414), alpha > 0.
+template <typename T> TQ_HD T sample_std_gamma(Philox& rng, T alpha) {
+    using R = Real<T>;
+    T scale = T(1);
+    if (alpha < T(1)) {
+        scale = R::pow(T(rng.uniform_d()), T(1) / alpha);
+        alpha += T(1);
+    }
+    const T d = alpha - T(1) / T(3);
+    const T c = T(1) / R::sqrt(T(9) * d);
+    for (int it = 0; it < 64; ++it) {
+        T xn, yv;
+        do {
+            xn = T(rng.normal());
+            yv = T(1) + c * xn;
+        } while (yv <= T(0));
+        const T v = yv * yv * yv;
+        const T u = T(rng.uniform());
+        const T xx = xn * xn;
+        if (u < T(1) - T(0.0331) * xx * xx) return scale * d * v;
+        if (R::log(u) < T(0.5) * xx + d * (T(1) - v + R::log(v))) return scale * d * v;
+    }
+    return scale * d;  // unreachable in practice (acceptance > 95 % per trial)
+}
+
+}  // namespace tq
