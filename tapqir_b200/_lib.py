@@ -42,6 +42,20 @@ SIGNATURES = {
     "tq_ksmogn_fwd": (c_int, [c_int, POINTER(PatchView), _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_int, _VP, _VP]),
     "tq_ksmogn_fwd_bwd": (c_int, [c_int, POINTER(PatchView), _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_int, _VP,
                                    _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    # ---- SVI step (csrc/cosmos_step.cu) ----
+    "tq_sizeof_tables": (c_int, []),
+    "tq_sizeof_gstate": (c_int, []),
+    "tq_sizeof_model_const": (c_int, []),
+    "tq_local_post_blocks": (c_int, [c_int64]),
+    "tq_cosmos_globals_sample": (c_int, [c_int, c_int, _VP, _VP, _VP, c_uint64, _VP, _VP, _VP, _VP, _VP]),
+    "tq_cosmos_local_pre": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, c_int64, c_uint64, _VP, _VP,
+                                     _VP, _VP, _VP]),
+    "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double,
+                                      c_double, _VP, _VP, _VP, _VP, _VP]),
+    "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP]),
+    "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
+    "tq_step_advance": (c_int, [_VP, _VP]),
+    "tq_subsample": (c_int, [c_int, c_int, c_uint64, _VP, c_uint64, _VP, _VP, _VP]),
 }
 
 _lib = None

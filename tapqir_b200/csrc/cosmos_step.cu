@@ -1,0 +1,445 @@
+// Kernels of one cosmos SVI step around the likelihood kernel (ksmogn.cu):
+//
+//   globals_sample -> local_pre -> [tq_ksmogn_fwd_bwd] -> local_post -> reduce -> [allreduce]
+//   -> globals_grad -> adam
+//
+// Replaces, for this path, what Pyro's SVI.step does around models/cosmos.py:82-462 (guide/model
+// execution, TraceEnum_ELBO contraction, autograd backward; models/model.py:212) -- SURVEY.md
+// App. A.  The arithmetic is in cosmos_local.cuh / cosmos_globals.cuh (also compiled for the CPU by
+// tests/hostcheck); this file is gather/scatter, reductions and launch plumbing.
+#include "common.cuh"
+#include "cosmos_globals.cuh"
+
+namespace tq {
+
+using Acc = double;  // arithmetic type of the per-unit local terms ("precision")
+
+// flat local-parameter buffer (tapqir_b200/models/layout.py LocalLayout)
+struct LocalOffsets {
+    int64_t Nt, F, C;
+    __host__ __device__ int64_t tensor_off(int t) const {
+        const int64_t aoi = Nt * C, unit = Nt * F * C;
+        if (t < 2) return t * aoi;
+        if (t < 4) return 2 * aoi + (t - 2) * unit;
+        return 2 * aoi + 2 * unit + (int64_t)(t - 4) * kK * unit;
+    }
+    __host__ __device__ int64_t index(int i, int64_t n, int64_t f, int64_t c) const {
+        if (i < 2) return tensor_off(i) + n * C + c;
+        if (i < 4) return tensor_off(i) + (n * F + f) * C + c;
+        const int t = 4 + (i - 4) / kK, k = (i - 4) % kK;
+        return tensor_off(t) + ((k * Nt + n) * F + f) * C + c;
+    }
+    __host__ __device__ int64_t numel() const { return tensor_off(12); }
+};
+
+// per-step state kept on the device so that a captured CUDA graph can be replayed unchanged
+struct StepState {
+    unsigned long long step;  // SVI iteration counter: Philox stream + Adam bias correction
+};
+
+constexpr int kLocalBlock = 128;
+
+template <typename T>
+__device__ __forceinline__ void load_unit_params(const T* __restrict__ lparams, const LocalOffsets& lo,
+                                                 int64_t n, int64_t f, int c, const ModelConst& mc,
+                                                 UnitParams<Acc>& up) {
+    Acc u[NLOCAL];
+#pragma unroll
+    for (int i = 0; i < NLOCAL; ++i) u[i] = (Acc)lparams[lo.index(i, n, f, c)];
+    transform_unit<Acc>(u, mc, up);
+}
+
+// ---- globals: sample + tables ------------------------------------------------------------------------
+template <typename T>
+__global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+                                      const double* __restrict__ noise_in, unsigned long long seed,
+                                      const StepState* __restrict__ state, double* __restrict__ gstate,
+                                      GlobalTables<double>* __restrict__ tables, T* __restrict__ gain_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    GlobalLayout gl{Q};
+    double u[kMaxGlobals], variate[kMaxGlobalNoise], sample[kMaxGlobalNoise];
+    for (int i = 0; i < gl.count(); ++i) u[i] = (double)gparams[i];
+    const bool use_rng = noise_in == nullptr;
+    Philox rng(seed, state->step, 0ull);
+    if (!use_rng)
+        for (int i = 0; i < gl.n_count(); ++i) variate[i] = noise_in[i];
+    GlobalTables<double> gt;
+    globals_pre(u, gl, mc, use_rng, &rng, variate, sample, gt);
+    for (int i = 0; i < gl.n_count(); ++i) {
+        gstate[i] = variate[i];
+        gstate[kMaxGlobalNoise + i] = sample[i];
+    }
+    *tables = gt;
+    gain_out[0] = (T)gt.gain;
+}
+
+// ---- local_pre: thread per unit -------------------------------------------------------------------------
+template <typename T> struct LocalArgs {
+    tq_patch_view v;
+    LocalOffsets lo;
+    ModelConst mc;
+    const T* lparams;
+    const GlobalTables<double>* tables;
+    int64_t U;
+    int64_t aoi_offset;          // global index of this rank's AOI 0 (RNG stream identity)
+    unsigned long long seed;
+    const StepState* state;
+    // pre
+    const T* noise_in;           // (NSAMP, U) base variates or NULL -> Philox
+    T* samples;                  // (NSAMP, U)
+    T* qm;                       // (kM, U)
+    // post
+    const T* L;                  // (kM, U)
+    const T* gs[NSAMP];          // d/d sample from the likelihood kernel, in S_* order
+    const T* g_rate;             // (U,)
+    double sN, sF;
+    T* lgrads;                   // flat, LocalOffsets layout
+    double* aoi_partial;         // (2, U): per-unit contributions to d/d(bm, bs)
+    double* block_partial;       // (gridDim.x, C, NACC)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) local_pre_kernel(const LocalArgs<T> a) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= a.U) return;
+    const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
+    UnitParams<Acc> up;
+    load_unit_params(a.lparams, a.lo, ui.aoi, f, ui.c, a.mc, up);
+    Acc variate[NSAMP], sample[NSAMP], qm[kM];
+    const bool use_rng = a.noise_in == nullptr;
+    const unsigned long long gid = (((unsigned long long)(a.aoi_offset + ui.aoi)) * a.v.F + f) * a.v.C + ui.c;
+    Philox rng(a.seed, a.state->step, (gid + 1ull) << 12);
+    if (!use_rng) {
+#pragma unroll
+        for (int i = 0; i < NSAMP; ++i) variate[i] = (Acc)a.noise_in[i * a.U + u];
+    }
+    local_pre<Acc>(up, a.mc, use_rng, &rng, variate, sample, qm);
+#pragma unroll
+    for (int i = 0; i < NSAMP; ++i) a.samples[i * a.U + u] = (T)sample[i];
+#pragma unroll
+    for (int m = 0; m < kM; ++m) a.qm[m * a.U + u] = (T)qm[m];
+}
+
+// ---- local_post: thread per unit + deterministic block reduction of the channel accumulators -------------
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) local_post_kernel(const LocalArgs<T> a) {
+    __shared__ double red[kLocalBlock / 32][NACC];
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = u < a.U;
+    UnitGrads<Acc> ug;
+    int my_c = -1;
+    double mu = 0.0;
+    if (live) {
+        const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
+        my_c = ui.c;
+        mu = a.v.mask[ui.aoi] ? 1.0 : 0.0;
+        UnitParams<Acc> up;
+        load_unit_params(a.lparams, a.lo, ui.aoi, f, ui.c, a.mc, up);
+        Acc sample[NSAMP], gs[NSAMP], L[kM];
+#pragma unroll
+        for (int i = 0; i < NSAMP; ++i) {
+            sample[i] = (Acc)a.samples[i * a.U + u];
+            gs[i] = (Acc)a.gs[i][u];
+        }
+#pragma unroll
+        for (int m = 0; m < kM; ++m) L[m] = (Acc)a.L[m * a.U + u];
+        GlobalTables<Acc> gt = *a.tables;
+        local_post<Acc>(up, a.mc, gt, ui.c, a.v.is_ontarget[ui.aoi] != 0, ui.fi == 0, sample, L, gs,
+                        (Acc)a.g_rate[u], ug);
+        const double s = -a.sN * a.sF * mu;  // loss = -ELBO
+#pragma unroll
+        for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, ui.aoi, f, ui.c)] = (T)(s * ug.g[i]);
+        a.aoi_partial[u] = mu * ug.g[LP_BM];
+        a.aoi_partial[a.U + u] = mu * ug.g[LP_BS];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = 0; c < a.v.C; ++c) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+            double v = (live && my_c == c) ? mu * ug.acc[i] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) red[warp][i] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < NACC) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kLocalBlock / 32; ++w) v += red[w][threadIdx.x];
+            a.block_partial[((int64_t)blockIdx.x * a.v.C + c) * NACC + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- reductions (fixed order => run-to-run deterministic) ---------------------------------------------------
+// acc[c][i] = sum over blocks; one warp per (c, i)
+__global__ void reduce_acc_kernel(const double* __restrict__ block_partial, int nblocks, int C,
+                                  double* __restrict__ acc) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C * NACC) return;
+    const int c = warp / NACC, i = warp - c * NACC;
+    double v = 0.0;
+    for (int b = lane; b < nblocks; b += 32) v += block_partial[((int64_t)b * C + c) * NACC + i];
+    v = warp_sum(v);
+    if (lane == 0) acc[c * NACC + i] = v;
+}
+
+// d loss / d (background_mean_loc, background_std_loc)[n, 0, c]: sum over the minibatch frames of the
+// per-unit contributions + the AOI-level prior; one warp per (ni, c)
+template <typename T>
+__global__ void reduce_aoi_kernel(const LocalArgs<T> a) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nb = a.v.nb, fb = a.v.fb, C = a.v.C;
+    if (warp >= (int64_t)nb * C) return;
+    const int ni = (int)(warp / C), c = (int)(warp - (int64_t)ni * C);
+    double sbm = 0.0, sbs = 0.0;
+    for (int fi = lane; fi < fb; fi += 32) {
+        const int64_t u = ((int64_t)ni * fb + fi) * C + c;
+        sbm += a.aoi_partial[u];
+        sbs += a.aoi_partial[a.U + u];
+    }
+    sbm = warp_sum(sbm);
+    sbs = warp_sum(sbs);
+    if (lane == 0) {
+        const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
+        const double mu = a.v.mask[n] ? 1.0 : 0.0;
+        const int64_t ibm = a.lo.index(LP_BM, n, 0, c), ibs = a.lo.index(LP_BS, n, 0, c);
+        const Transformed<double> bm = t_positive<double>((double)a.lparams[ibm]);
+        const Transformed<double> bs = t_positive<double>((double)a.lparams[ibs]);
+        const double s1 = a.mc.bg_mean_std, s2 = a.mc.bg_std_std;
+        const double pbm = -bm.v / (s1 * s1) * bm.d, pbs = -bs.v / (s2 * s2) * bs.d;
+        a.lgrads[ibm] = (T)(-(a.sN * a.sF * sbm + a.sN * mu * pbm));
+        a.lgrads[ibs] = (T)(-(a.sN * a.sF * sbs + a.sN * mu * pbs));
+    }
+}
+
+// ---- globals: reverse mode ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void globals_grad_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+                                    const double* __restrict__ gstate, const double* __restrict__ acc,
+                                    double sN, double sF, T* __restrict__ ggrads, double* __restrict__ loss) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    GlobalLayout gl{Q};
+    double u[kMaxGlobals], grad[kMaxGlobals];
+    for (int i = 0; i < gl.count(); ++i) u[i] = (double)gparams[i];
+    const double elbo = globals_post(u, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, grad);
+    for (int i = 0; i < gl.count(); ++i) ggrads[i] = (T)grad[i];
+    loss[0] = -elbo;
+}
+
+// ---- dense Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) --------------------------------------
+// models/model.py:168-171: pyro.optim.Adam({"lr", "betas": [0.9, 0.999]}) on every unconstrained tensor,
+// dense over the whole tensor.  `state->step` is the number of completed steps.
+template <typename T>
+__global__ void adam_kernel(int64_t n, T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
+                            T* __restrict__ v, double lr, double b1, double b2, double eps,
+                            const StepState* __restrict__ state) {
+    const double t = (double)(state->step + 1ull);
+    const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+    const T step_size = (T)(lr / bc1);
+    const T inv_sqrt_bc2 = (T)(1.0 / sqrt(bc2));
+    const T tb1 = (T)b1, tb2 = (T)b2, teps = (T)eps;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T gi = g[i];
+        const T mi = m[i] + (gi - m[i]) * (T(1) - tb1);          // exp_avg.lerp_(grad, 1 - beta1)
+        const T vi = v[i] * tb2 + (T(1) - tb2) * gi * gi;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        m[i] = mi;
+        v[i] = vi;
+        const T denom = Real<T>::sqrt(vi) * inv_sqrt_bc2 + teps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+
+__global__ void step_advance_kernel(StepState* state) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) state->step += 1ull;
+}
+
+static int local_blocks(int64_t U) { return (int)((U + kLocalBlock - 1) / kLocalBlock); }
+
+template <typename T>
+static void fill_common(LocalArgs<T>& a, const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams,
+                        const void* tables, int64_t aoi_offset, unsigned long long seed, const void* state) {
+    a.v = *view;
+    a.lo = LocalOffsets{Nt, (int64_t)view->F, (int64_t)view->C};
+    a.mc = *mc;
+    a.lparams = (const T*)lparams;
+    a.tables = (const GlobalTables<double>*)tables;
+    a.U = (int64_t)view->nb * view->fb * view->C;
+    a.aoi_offset = aoi_offset;
+    a.seed = seed;
+    a.state = (const StepState*)state;
+}
+
+}  // namespace tq
+
+using namespace tq;
+
+extern "C" int tq_sizeof_tables(void) { return (int)sizeof(GlobalTables<double>); }
+extern "C" int tq_sizeof_gstate(void) { return (int)(2 * kMaxGlobalNoise * sizeof(double)); }
+extern "C" int tq_sizeof_model_const(void) { return (int)sizeof(ModelConst); }
+extern "C" int tq_local_post_blocks(int64_t U) { return local_blocks(U); }
+
+extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
+                                        uint64_t seed, const void* state, double* gstate, void* tables,
+                                        void* gain_out, void* stream) {
+    TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
+    TQ_CHECK_ARG(gparams && mc && state && gstate && tables && gain_out, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ModelConst m = *(const ModelConst*)mc;
+    if (dtype == TQ_F32)
+        globals_sample_kernel<float><<<1, 32, 0, st>>>((const float*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+                                                      gstate, (GlobalTables<double>*)tables, (float*)gain_out);
+    else if (dtype == TQ_F64)
+        globals_sample_kernel<double><<<1, 32, 0, st>>>((const double*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+                                                       gstate, (GlobalTables<double>*)tables, (double*)gain_out);
+    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("globals_sample_kernel launch");
+    return TQ_OK;
+}
+
+template <typename T>
+static int run_local_pre(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                         int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in, void* samples,
+                         void* qm, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, aoi_offset, seed, state);
+    a.noise_in = (const T*)noise_in;
+    a.samples = (T*)samples;
+    a.qm = (T*)qm;
+    if (a.U == 0) return TQ_OK;
+    local_pre_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a);
+    TQ_LAUNCH_CHECK("local_pre_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_cosmos_local_pre(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                   const void* tables, int64_t aoi_offset, uint64_t seed, const void* state,
+                                   const void* noise_in, void* samples, void* qm, void* stream) {
+    TQ_CHECK_ARG(view && mc && lparams && tables && state && samples && qm, "NULL pointer");
+    TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_local_pre<float>(view, Nt, (const ModelConst*)mc, lparams, tables, aoi_offset, seed, state, noise_in, samples, qm, st);
+    if (dtype == TQ_F64) return run_local_pre<double>(view, Nt, (const ModelConst*)mc, lparams, tables, aoi_offset, seed, state, noise_in, samples, qm, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T>
+static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                          const void* samples, const void* L, const void* gs, const void* g_rate, double sN, double sF,
+                          void* lgrads, double* aoi_partial, double* block_partial, double* acc, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
+    a.samples = (T*)samples;
+    a.L = (const T*)L;
+    // gs: (NSAMP, U) record in S_* order: background, height_k, width_k, x_k, y_k
+    for (int i = 0; i < NSAMP; ++i) a.gs[i] = (const T*)gs + (int64_t)i * a.U;
+    a.g_rate = (const T*)g_rate;
+    a.sN = sN; a.sF = sF;
+    a.lgrads = (T*)lgrads;
+    a.aoi_partial = aoi_partial;
+    a.block_partial = block_partial;
+    const int nblocks = local_blocks(a.U);
+    if (a.U > 0) {
+        local_post_kernel<T><<<nblocks, kLocalBlock, 0, st>>>(a);
+        TQ_LAUNCH_CHECK("local_post_kernel launch");
+        const int64_t warps = (int64_t)view->nb * view->C;
+        reduce_aoi_kernel<T><<<(int)((warps * 32 + 127) / 128), 128, 0, st>>>(a);
+        TQ_LAUNCH_CHECK("reduce_aoi_kernel launch");
+    }
+    const int rw = view->C * NACC;
+    reduce_acc_kernel<<<(rw * 32 + 127) / 128, 128, 0, st>>>(block_partial, a.U > 0 ? nblocks : 0, view->C, acc);
+    TQ_LAUNCH_CHECK("reduce_acc_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                    const void* tables, const void* samples, const void* L, const void* gs,
+                                    const void* g_rate, double sN, double sF, void* lgrads, double* aoi_partial,
+                                    double* block_partial, double* acc, void* stream) {
+    TQ_CHECK_ARG(view && mc && lparams && tables && samples && L && gs && g_rate, "NULL input pointer");
+    TQ_CHECK_ARG(lgrads && aoi_partial && block_partial && acc, "NULL output pointer");
+    TQ_CHECK_ARG(view->mask && view->is_ontarget, "view needs mask and is_ontarget");
+    TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_local_post<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
+    if (dtype == TQ_F64) return run_local_post<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+extern "C" int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
+                                      const double* acc, double sN, double sF, void* ggrads, double* loss, void* stream) {
+    TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
+    TQ_CHECK_ARG(gparams && mc && gstate && acc && ggrads && loss, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ModelConst m = *(const ModelConst*)mc;
+    if (dtype == TQ_F32)
+        globals_grad_kernel<float><<<1, 32, 0, st>>>((const float*)gparams, Q, m, gstate, acc, sN, sF, (float*)ggrads, loss);
+    else if (dtype == TQ_F64)
+        globals_grad_kernel<double><<<1, 32, 0, st>>>((const double*)gparams, Q, m, gstate, acc, sN, sF, (double*)ggrads, loss);
+    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("globals_grad_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_adam_dense(int dtype, int64_t n, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
+                             double lr, double beta1, double beta2, double eps, const void* state, void* stream) {
+    TQ_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return TQ_OK;
+    TQ_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 256;
+    int64_t grid = (n + block - 1) / block;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    if (dtype == TQ_F32)
+        adam_kernel<float><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+    else if (dtype == TQ_F64)
+        adam_kernel<double><<<(int)grid, block, 0, st>>>(n, (double*)params, (const double*)grads, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("adam_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_step_advance(void* state, void* stream) {
+    TQ_CHECK_ARG(state != nullptr, "NULL pointer");
+    step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((StepState*)state);
+    TQ_LAUNCH_CHECK("step_advance_kernel launch");
+    return TQ_OK;
+}
+
+// ---- minibatch subsampling (pyro.plate(subsample_size=...) [third party]: randperm(size)[:n]) -----------
+// Partial Fisher-Yates on a persistent permutation: after n_pick swaps the first n_pick entries are
+// a uniform sample without replacement whatever permutation the array held before.
+namespace tq {
+__global__ void subsample_kernel(int n_total, int n_pick, unsigned long long seed, const StepState* state,
+                                 unsigned long long stream_id, int32_t* __restrict__ perm, int32_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Philox rng(seed ^ (0x9E3779B97F4A7C15ull * (stream_id + 1ull)), state->step, 0ull);
+    for (int i = 0; i < n_pick; ++i) {
+        const unsigned int span = (unsigned int)(n_total - i);
+        const unsigned int j = i + (unsigned int)(((unsigned long long)rng.next() * span) >> 32);
+        const int32_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+        out[i] = perm[i];
+    }
+}
+}  // namespace tq
+
+// perm: (n_total,) int32 scratch holding a permutation of 0..n_total-1 (initialise to arange once);
+// out: (n_pick,) int32.  stream_id separates independent draws (AOIs vs frames, ranks).
+extern "C" int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* state, uint64_t stream_id, void* perm,
+                            void* out, void* stream) {
+    TQ_CHECK_ARG(n_total >= 1 && n_pick >= 0 && n_pick <= n_total, "bad sizes");
+    TQ_CHECK_ARG(state && perm && out, "NULL pointer");
+    if (n_pick == 0) return TQ_OK;
+    tq::subsample_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_total, n_pick, seed, (const tq::StepState*)state, stream_id,
+                                                          (int32_t*)perm, (int32_t*)out);
+    TQ_LAUNCH_CHECK("subsample_kernel launch");
+    return TQ_OK;
+}

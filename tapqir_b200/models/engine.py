@@ -1,0 +1,161 @@
+"""
+Step engine: owns the device buffers of one rank's AOI shard and enqueues the kernels of one
+cosmos SVI step through the C ABI (include/tapqir_b200.h).
+
+One step (what ``svi.step()`` does in models/model.py:212):
+
+    subsample -> globals_sample -> local_pre -> ksmogn_fwd_bwd -> local_post (+ reductions)
+    -> [all-reduce of the (C, NACC) accumulators across ranks] -> globals_grad -> Adam (local, global)
+
+Everything runs on torch's current stream; no host synchronisation inside a step (the loss stays on
+the device until someone reads it).  There is no CPU path: constructing an engine without the
+sm_100a library or without a CUDA device raises.
+"""
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from tapqir_b200 import _lib
+from tapqir_b200.models import layout as L
+
+
+class CosmosEngine:
+    def __init__(self, store, Nt_local, F, C, P, priors, dtype=torch.float32, lr=0.005, betas=(0.9, 0.999),
+                 adam_eps=1e-8, nbatch_size=None, fbatch_size=None, seed=0, ref_dtype=torch.float64,
+                 Nt_total=None, aoi_offset=0, rank=0, world_size=1, process_group=None):
+        self.lib = _lib.load()
+        self.store = store
+        self.device = store.pixels.device
+        if self.device.type != "cuda":
+            raise ValueError("CosmosEngine needs a CUDA device store (no CPU path)")
+        self.dtype = dtype
+        self.code = _lib.dtype_code(dtype)
+        self.Nt, self.F, self.C, self.P = int(Nt_local), int(F), int(C), int(P)
+        self.Nt_total = int(Nt_total if Nt_total is not None else Nt_local)
+        self.aoi_offset, self.rank, self.world_size, self.pg = int(aoi_offset), int(rank), int(world_size), process_group
+        self.lr, self.betas, self.adam_eps = float(lr), (float(betas[0]), float(betas[1])), float(adam_eps)
+        self.seed = int(seed)
+        self.mc = L.ModelConst.make(priors, P, ref_dtype)
+        assert self.lib.tq_sizeof_model_const() == ctypes.sizeof(self.mc), "ModelConst ABI mismatch"
+        self.ll = L.LocalLayout(self.Nt, self.F, self.C)
+        self.gl = L.GlobalLayout(self.C)
+        dev, f64 = self.device, torch.float64
+        z = lambda n, dt=dtype: torch.zeros(n, dtype=dt, device=dev)
+        # parameters, gradients, Adam moments (flat; see layout.py)
+        self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
+        self.gparams, self.ggrads, self.gm, self.gv = z(self.gl.numel), z(self.gl.numel), z(self.gl.numel), z(self.gl.numel)
+        # small device-resident state
+        self.state = torch.zeros(1, dtype=torch.int64, device=dev)          # StepState.step
+        self.tables = torch.zeros(self.lib.tq_sizeof_tables(), dtype=torch.uint8, device=dev)
+        self.gstate = torch.zeros(self.lib.tq_sizeof_gstate() // 8, dtype=f64, device=dev)
+        self.gain = z(1)
+        self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
+        self.loss = torch.zeros(1, dtype=f64, device=dev)
+        self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
+        self.set_batch(nbatch_size or self.Nt, fbatch_size or self.F)
+
+    # ---- buffers that depend on the minibatch shape ---------------------------------------------------
+    def set_batch(self, nbatch_size, fbatch_size):
+        self.nb, self.fb = min(int(nbatch_size), self.Nt), min(int(fbatch_size), self.F)
+        dev, dtype = self.device, self.dtype
+        U = self.U = self.nb * self.fb * self.C
+        self.full_n, self.full_f = self.nb == self.Nt, self.fb == self.F
+        self.ndx = None if self.full_n else torch.zeros(self.nb, dtype=torch.int32, device=dev)
+        self.fdx = None if self.full_f else torch.zeros(self.fb, dtype=torch.int32, device=dev)
+        self.perm_n = torch.arange(self.Nt, dtype=torch.int32, device=dev)
+        self.perm_f = torch.arange(self.F, dtype=torch.int32, device=dev)
+        e = lambda *s, dt=dtype: torch.empty(*s, dtype=dt, device=dev)
+        self.samples, self.gs = e(L.NSAMP, U), e(L.NSAMP, U)
+        self.qm, self.Lm, self.g_rate = e(4, U), e(4, U), e(U)
+        self.aoi_partial = e(2, U, dt=torch.float64)
+        self.nblocks = self.lib.tq_local_post_blocks(U)
+        self.block_partial = e(max(self.nblocks, 1) * self.C * L.NACC, dt=torch.float64)
+        # scale factors of the subsampled plates (cosmos.py:194-208): all ranks together draw
+        # nb * world_size of Nt_total AOIs (stratified by shard)
+        self.sN = self.Nt_total / (self.nb * self.world_size)
+        self.sF = self.F / self.fb
+
+    def _view(self, ndx, fdx):
+        s = self.store
+        return _lib.make_view(s.pixels, s.xy, s.offset_samples, s.offset_logits, nb=self.nb, fb=self.fb, C=self.C,
+                              F=self.F, P=self.P, ndx=ndx, fdx=fdx, is_ontarget=s.is_ontarget, mask=s.mask)
+
+    # ---- parameter access -------------------------------------------------------------------------------
+    def named_unconstrained(self):
+        out = OrderedDict(self.ll.views(self.lparams))
+        out.update(self.gl.views(self.gparams))
+        return out
+
+    def named_grads(self):
+        out = OrderedDict(self.ll.views(self.lgrads))
+        out.update(self.gl.views(self.ggrads))
+        return out
+
+    def load_unconstrained(self, tensors):
+        views = self.named_unconstrained()
+        for k, v in views.items():
+            v.copy_(tensors[k].to(device=self.device, dtype=self.dtype).reshape(v.shape))
+
+    # ---- one step ------------------------------------------------------------------------------------------
+    def step(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True):
+        """
+        Enqueue one SVI step.  ``ndx``/``fdx`` (int32 CUDA tensors of local AOI / frame indices) and
+        the base variates (``local_noise`` (NSAMP, U) in ``dtype``; ``global_noise`` float64 in
+        GlobalLayout noise order) put the step in *replay* mode for parity tests; by default indices
+        and variates are drawn on the device with Philox keyed by (seed, step).
+        With ``update=False`` parameters are left untouched (gradients only).
+        Returns the device tensor holding the loss (-ELBO).
+        """
+        lib, st, code = self.lib, _lib.stream_ptr(self.device), self.code
+        p = _lib.ptr
+        mc = ctypes.byref(self.mc)
+        with torch.cuda.device(self.device):
+            if ndx is None and not self.full_n:
+                _lib.check(lib.tq_subsample(self.Nt, self.nb, self.seed, p(self.state), 2 + self.rank, p(self.perm_n),
+                                            p(self.ndx), st), "tq_subsample")
+                ndx = self.ndx
+            if fdx is None and not self.full_f:
+                # same frame subset on every rank: stream id does not depend on the rank
+                _lib.check(lib.tq_subsample(self.F, self.fb, self.seed, p(self.state), 1, p(self.perm_f), p(self.fdx), st),
+                           "tq_subsample")
+                fdx = self.fdx
+            view = self._view(ndx, fdx)
+            if not (self.full_n and self.full_f):
+                self.lgrads.zero_()  # dense zero-filled gradient outside the minibatch
+            _lib.check(lib.tq_cosmos_globals_sample(code, self.C, p(self.gparams), mc, p(global_noise), self.seed,
+                                                    p(self.state), p(self.gstate), p(self.tables), p(self.gain), st),
+                       "tq_cosmos_globals_sample")
+            _lib.check(lib.tq_cosmos_local_pre(code, view, self.Nt, mc, p(self.lparams), p(self.tables), self.aoi_offset,
+                                               self.seed, p(self.state), p(local_noise), p(self.samples), p(self.qm), st),
+                       "tq_cosmos_local_pre")
+            S, G, K = self.samples, self.gs, L.K
+            _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
+                                             p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg), 4, p(self.qm),
+                                             p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
+                                             p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
+            _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
+                                                p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
+                                                p(self.aoi_partial), p(self.block_partial), p(self.acc), st),
+                       "tq_cosmos_local_post")
+            if self.world_size > 1:
+                torch.distributed.all_reduce(self.acc, group=self.pg)
+            _lib.check(lib.tq_cosmos_globals_grad(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.acc),
+                                                  self.sN, self.sF, p(self.ggrads), p(self.loss), st),
+                       "tq_cosmos_globals_grad")
+            if update:
+                b1, b2 = self.betas
+                _lib.check(lib.tq_adam_dense(code, self.ll.numel, p(self.lparams), p(self.lgrads), p(self.lm), p(self.lv),
+                                             self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
+                _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm), p(self.gv),
+                                             self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
+                _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
+        return self.loss
+
+    @property
+    def iteration(self):
+        return int(self.state.item())
+
+    def set_iteration(self, it):
+        self.state.fill_(int(it))

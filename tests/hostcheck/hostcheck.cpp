@@ -65,3 +65,135 @@ void hc_sample_gamma_f64(uint64_t seed, uint64_t stream, double alpha, int n, do
     for (int i = 0; i < n; ++i) { Philox rng(seed, stream, (uint64_t)i * 64); out[i] = sample_std_gamma<double>(rng, alpha); }
 }
 }
+
+// ---- whole-step emulation: the same sequence of device functions the kernels run -------------------
+#include "cosmos_globals.cuh"
+
+namespace {
+
+struct LocalOffsets {
+    int64_t Nt, F, C;
+    int64_t tensor_off(int t) const {
+        const int64_t aoi = Nt * C, unit = Nt * F * C;
+        if (t < 2) return t * aoi;
+        if (t < 4) return 2 * aoi + (t - 2) * unit;
+        return 2 * aoi + 2 * unit + (int64_t)(t - 4) * kK * unit;
+    }
+    // flat index of local record entry i for (aoi n, frame f, channel c)
+    int64_t index(int i, int64_t n, int64_t f, int64_t c) const {
+        if (i < 2) return tensor_off(i) + n * C + c;
+        if (i < 4) return tensor_off(i) + (n * F + f) * C + c;
+        const int t = 4 + (i - 4) / kK, k = (i - 4) % kK;
+        return tensor_off(t) + ((k * Nt + n) * F + f) * C + c;
+    }
+};
+
+// T: storage + pixel arithmetic type; A: arithmetic type of the per-unit (local) terms
+template <typename T, typename A>
+double cosmos_step_host(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
+                        const T* pixels, const T* xy, const uint8_t* ontarget, const uint8_t* mask, const T* off_s,
+                        const T* off_w, const ModelConst* mcp, double sN, double sF, const T* lparams, const double* gparams,
+                        const T* lnoise, const double* gnoise, T* lgrads, double* ggrads, double* acc_out, T* samples_out) {
+    const ModelConst& mc = *mcp;
+    GlobalLayout gl{C};
+    GlobalTables<double> gtd;
+    double gvar[kMaxGlobalNoise], gsamp[kMaxGlobalNoise];
+    for (int i = 0; i < gl.n_count(); ++i) gvar[i] = gnoise[i];
+    globals_pre(gparams, gl, mc, false, nullptr, gvar, gsamp, gtd);
+    // tables in the local compute type
+    GlobalTables<A> gt;
+    gt.gain = (A)gtd.gain; gt.rate = (A)gtd.rate; gt.log_rate = (A)gtd.log_rate; gt.size1 = (A)gtd.size1;
+    gt.lnorm1 = (A)gtd.lnorm1; gt.dlnorm1 = (A)gtd.dlnorm1;
+    for (int q = 0; q < C; ++q) {
+        for (int a = 0; a < 2; ++a) for (int z = 0; z < kZ; ++z) gt.ch[q].logpz[a][z] = (A)gtd.ch[q].logpz[a][z];
+        for (int a = 0; a < 2; ++a) for (int t = 0; t < kTheta; ++t) gt.ch[q].logptheta[a][t] = (A)gtd.ch[q].logptheta[a][t];
+        for (int t = 0; t < kTheta; ++t) for (int k = 0; k < kK; ++k) for (int m = 0; m < 2; ++m) gt.ch[q].logpm[t][k][m] = (A)gtd.ch[q].logpm[t][k][m];
+    }
+    LocalOffsets lo{Nt, F, C};
+    const int64_t U = (int64_t)nb * fb * C;
+    std::vector<double> acc((size_t)C * NACC, 0.0);
+    const int64_t total = lo.tensor_off(12);
+    for (int64_t i = 0; i < total; ++i) lgrads[i] = T(0);
+    const double s = sN * sF;
+    T mcfg[kM][kK];
+    for (int m = 0; m < kM; ++m) for (int k = 0; k < kK; ++k) mcfg[m][k] = T((m >> k) & 1);
+    for (int64_t u = 0; u < U; ++u) {
+        const int c = (int)(u % C), fi = (int)((u / C) % fb), ni = (int)(u / ((int64_t)C * fb));
+        const int64_t n = ndx ? ndx[ni] : ni, f = fdx ? fdx[fi] : fi;
+        A uu[NLOCAL];
+        for (int i = 0; i < NLOCAL; ++i) uu[i] = (A)lparams[lo.index(i, n, f, c)];
+        UnitParams<A> up;
+        transform_unit<A>(uu, mc, up);
+        A variate[NSAMP], sampleA[NSAMP], qmA[kM];
+        for (int i = 0; i < NSAMP; ++i) variate[i] = (A)lnoise[i * U + u];
+        local_pre<A>(up, mc, false, nullptr, variate, sampleA, qmA);
+        // samples and weights cross to the likelihood kernel in storage precision
+        T sample[NSAMP], qm[kM];
+        for (int i = 0; i < NSAMP; ++i) { sample[i] = (T)sampleA[i]; sampleA[i] = (A)sample[i]; }
+        for (int m = 0; m < kM; ++m) qm[m] = (T)qmA[m];
+        if (samples_out) for (int i = 0; i < NSAMP; ++i) samples_out[i * U + u] = sample[i];
+        // likelihood with W = q(m)
+        const int64_t patch = (n * F + f) * C + c;
+        PatchSpots<T> sp;
+        for (int k = 0; k < kK; ++k) {
+            sp.h[k] = sample[S_H + k]; sp.w[k] = sample[S_W + k];
+            sp.cx[k] = sample[S_X + k] + xy[patch * 2]; sp.cy[k] = sample[S_Y + k] + xy[patch * 2 + 1];
+        }
+        sp.b = sample[S_B];
+        PatchOut<T, kM> po; po.zero();
+        for (int row = 0; row < P; ++row)
+            for (int col = 0; col < P; ++col) {
+                T gxk[kK], gyk[kK];
+                for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<T>(col, sp.cx[k], sp.w[k]); gyk[k] = axis_factor<T>(row, sp.cy[k], sp.w[k]); }
+                pixel_accumulate<T, kM, true>(pixels[(patch * P + row) * P + col], gxk, gyk, col, row, sp, mcfg, (T)gtd.rate, (T)gtd.log_rate, O, off_s, off_w, qm, po);
+            }
+        A gs[NSAMP], LA[kM];
+        gs[S_B] = (A)po.g_b;
+        for (int k = 0; k < kK; ++k) { gs[S_H + k] = (A)po.g_h[k]; gs[S_W + k] = (A)po.g_w[k]; gs[S_X + k] = (A)po.g_x[k]; gs[S_Y + k] = (A)po.g_y[k]; }
+        for (int m = 0; m < kM; ++m) LA[m] = (A)po.logp[m];
+        UnitGrads<A> ug;
+        local_post<A>(up, mc, gt, c, ontarget[n] != 0, fi == 0, sampleA, LA, gs, (A)po.g_rate, ug);
+        const double mu = mask[n] ? 1.0 : 0.0;
+        for (int i = 0; i < NACC; ++i) acc[(size_t)c * NACC + i] += mu * (double)ug.acc[i];
+        for (int i = 0; i < NLOCAL; ++i) lgrads[lo.index(i, n, f, c)] += (T)(-s * mu * (double)ug.g[i]);
+        if (fi == 0) {
+            A gbm, gbs;
+            aoi_prior_grad<A>(up, mc, gbm, gbs);
+            lgrads[lo.index(LP_BM, n, f, c)] += (T)(-sN * mu * (double)gbm);
+            lgrads[lo.index(LP_BS, n, f, c)] += (T)(-sN * mu * (double)gbs);
+        }
+    }
+    for (size_t i = 0; i < acc.size(); ++i) acc_out[i] = acc[i];
+    const double elbo = globals_post(gparams, gl, mc, gsamp, acc.data(), sN, sF, ggrads);
+    return -elbo;
+}
+
+}  // namespace
+
+extern "C" {
+double hc_cosmos_step_f64(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
+                          const double* pixels, const double* xy, const uint8_t* ontarget, const uint8_t* mask,
+                          const double* off_s, const double* off_w, const ModelConst* mc, double sN, double sF,
+                          const double* lparams, const double* gparams, const double* lnoise, const double* gnoise,
+                          double* lgrads, double* ggrads, double* acc_out, double* samples_out) {
+    return cosmos_step_host<double, double>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
+                                    lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
+}
+double hc_cosmos_step_f32(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
+                          const float* pixels, const float* xy, const uint8_t* ontarget, const uint8_t* mask,
+                          const float* off_s, const float* off_w, const ModelConst* mc, double sN, double sF,
+                          const float* lparams, const double* gparams, const float* lnoise, const double* gnoise,
+                          float* lgrads, double* ggrads, double* acc_out, float* samples_out) {
+    return cosmos_step_host<float, double>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
+                                   lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
+}
+double hc_cosmos_step_f32_localf32(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
+                          const float* pixels, const float* xy, const uint8_t* ontarget, const uint8_t* mask,
+                          const float* off_s, const float* off_w, const ModelConst* mc, double sN, double sF,
+                          const float* lparams, const double* gparams, const float* lnoise, const double* gnoise,
+                          float* lgrads, double* ggrads, double* acc_out, float* samples_out) {
+    return cosmos_step_host<float, float>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
+                                          lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
+}
+int hc_sizeof_model_const() { return (int)sizeof(ModelConst); }
+}

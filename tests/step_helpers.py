@@ -1,0 +1,78 @@
+"""Shared by the step parity tests: builds a small simulated problem, oracle params/noise, and the
+flat buffers the kernels (or the host emulation) take."""
+
+import ctypes
+
+import torch
+
+from oracle import cosmos_oracle as O
+from tapqir_b200.models import layout as L
+from tapqir_b200.utils.simulate import simulate
+
+
+def make_problem(N=4, F=6, C=1, nb=3, fb=4, seed=0, perturb=True, offsets="sim", dtype=torch.float64):
+    kw = {}
+    if offsets == "hist":
+        s = torch.arange(80.0, 96.0)
+        w = torch.exp(-0.5 * ((s - 90) / 3) ** 2) + 1e-3
+        kw = dict(offset_samples=s, offset_weights=w / w.sum())
+    ds = simulate(N, F, C=C, seed=seed, **kw)
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights, dtype=dtype)
+    g = torch.Generator().manual_seed(seed + 100)
+    params = O.to_unconstrained(O.init_constrained(data), data.P, data.dtype)
+    if perturb:  # move away from the symmetric initial point so every gradient path is exercised
+        for k, v in params.items():
+            v.add_(0.3 * torch.randn(v.shape, generator=g, dtype=v.dtype))
+    ndx = torch.randperm(N, generator=g)[:nb]
+    fdx = torch.randperm(F, generator=g)[:fb]
+    noise = O.draw_noise(params, data, ndx, fdx, g)
+    return ds, data, params, ndx, fdx, noise
+
+
+def flat_inputs(data, params, noise, dtype):
+    ll, gl = L.LocalLayout(data.Nt, data.F, data.C), L.GlobalLayout(data.C)
+    lparams = ll.pack({k: params[k] for k in L.LOCAL_NAMES}, dtype=dtype)
+    gparams = gl.pack({k: params[k] for k in L.GLOBAL_NAMES}, dtype=torch.float64)
+    lnoise = L.pack_local_noise(noise, dtype, "cpu")
+    gnoise = gl.pack_noise(noise)
+    return ll, gl, lparams, gparams, lnoise, gnoise
+
+
+def host_step(hc, data, params, ndx, fdx, noise, dtype=torch.float64, priors=O.DEFAULT_PRIORS, ref_dtype=torch.float64):
+    """Run tests/hostcheck's CPU emulation of the kernel pipeline; returns loss and named grads."""
+    ll, gl, lparams, gparams, lnoise, gnoise = flat_inputs(data, params, noise, dtype)
+    mc = L.ModelConst.make(priors, data.P, ref_dtype)
+    assert hc.hc_sizeof_model_const() == ctypes.sizeof(mc)
+    nb, fb = len(ndx), len(fdx)
+    U = nb * fb * data.C
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    ndx32, fdx32 = ndx.to(torch.int32).contiguous(), fdx.to(torch.int32).contiguous()
+    pixels = data.images.to(dtype).contiguous()
+    xy = data.xy.to(dtype).contiguous()
+    ont, mask = data.is_ontarget.to(torch.uint8).contiguous(), data.mask.to(torch.uint8).contiguous()
+    off_s, off_w = data.offset_samples.to(dtype).contiguous(), data.offset_logits.to(dtype).contiguous()
+    lgrads = torch.empty_like(lparams)
+    ggrads = torch.empty(gl.numel, dtype=torch.float64)
+    acc = torch.empty(data.C * L.NACC, dtype=torch.float64)
+    samples = torch.empty(L.NSAMP, U, dtype=dtype)
+    fn = hc.hc_cosmos_step_f64 if dtype == torch.float64 else hc.hc_cosmos_step_f32
+    fn.restype = ctypes.c_double
+    loss = fn(nb, fb, data.Nt, data.F, data.C, data.P, off_s.numel(), p(ndx32), p(fdx32), p(pixels), p(xy), p(ont), p(mask),
+              p(off_s), p(off_w), ctypes.byref(mc), ctypes.c_double(data.Nt / nb), ctypes.c_double(data.F / fb),
+              p(lparams), p(gparams), p(lnoise), p(gnoise), p(lgrads), p(ggrads), p(acc), p(samples))
+    grads = dict(ll.views(lgrads))
+    grads.update(gl.views(ggrads))
+    return loss, grads, samples
+
+
+def compare_grads(ours, ref, tol, names=None):
+    """max |ours - ref| / max |ref| per parameter; returns the worst offenders for the message."""
+    bad = {}
+    for k in names or ref.keys():
+        r = ref[k].double()
+        denom = r.abs().max().item()
+        err = (ours[k].double().cpu().reshape(r.shape) - r).abs().max().item()
+        rel = err / denom if denom > 0 else err
+        if not rel < tol:
+            bad[k] = rel
+    return bad
