@@ -52,8 +52,8 @@ def simulate(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0,
     f64 = dict(dtype=torch.float64, device=dev)
 
     if offset_samples is None:
-        offset_samples = torch.full((3,), float(prm["offset"]))
-        offset_weights = torch.ones(3) / 3
+        offset_samples = torch.full((3,), float(prm["offset"]), dtype=torch.float64)
+        offset_weights = torch.ones(3, dtype=torch.float64) / 3
     off_s = offset_samples.to(**f64)
     off_cdf = torch.cumsum(offset_weights.to(**f64), 0)
     off_cdf[-1] = 1.0
@@ -105,11 +105,11 @@ def simulate(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0,
     labels["z"] = z_all[:n_on].numpy()
     return CosmosDataset(
         images,
-        torch.full((N, F, C, 2), centre, dtype=torch.float32),
+        torch.full((N, F, C, 2), centre, dtype=torch.float64),
         is_ontarget,
         labels=labels,
-        offset_samples=offset_samples.clone().float(),
-        offset_weights=offset_weights.clone().float(),
+        offset_samples=offset_samples.clone().double(),  # the reference simulates under default dtype double
+        offset_weights=offset_weights.clone().double(),
         device="cpu",
         name=f"simulated_N{N}_F{F}_C{C}_seed{seed}",
     )

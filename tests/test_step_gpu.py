@@ -26,8 +26,8 @@ def make_engine(ds, data, params, nb, fb, dtype, **kw):
 
 def replay_args(eng, data, params, ndx, fdx, noise, dtype):
     _, gl, _, _, lnoise, gnoise = flat_inputs(data, params, noise, dtype)
-    n = None if eng.full_n else ndx.to(torch.int32).cuda()
-    f = None if eng.full_f else fdx.to(torch.int32).cuda()
+    # explicit indices even for a full batch: the oracle's minibatch order is a permutation
+    n, f = ndx.to(torch.int32).cuda(), fdx.to(torch.int32).cuda()
     return dict(ndx=n, fdx=f, local_noise=lnoise.cuda(), global_noise=gnoise.cuda())
 
 
