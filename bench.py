@@ -1,0 +1,335 @@
+"""
+Benchmark of the cosmos SVI hot path (ELBO forward + backward + dense Adam), AOI-frames/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c3|c2mb]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full SVI step over one minibatch of synthetic (tapqir-simulated) data.
+Default workload = BASELINE.json configs[1]: N=100 AOIs x F=1000 frames, P=14, K=2, C=1, O=3 offset
+bins, full local batch, per GPU (weak scaling: every rank holds its own 100-AOI shard; only the
+(C, 18) accumulator vector is all-reduced).  Prints ONE JSON line (rank 0).
+
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) before
+each timed step outside the event pair, max over ranks; clocks sampled with nvidia-smi during the
+timed region.  `--impl reference` times the reference's CPU path restated by oracle/ (Pyro cannot be
+installed here) on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (AOIs per GPU, frames, nb, fb, description)
+    "c2": (100, 1000, 100, 1000, "cosmos C2: simulated N=100 AOIs x F=1000 frames per GPU, P=14, K=2, C=1, O=3, full local batch"),
+    "c2mb": (100, 1000, 10, 512, "cosmos C2 with the reference-default minibatch 10 AOIs x 512 frames (main.py:1428-1431)"),
+    "c3": (1000, 5000, 1000, 5000, "cosmos C3: simulated N=1000 AOIs x F=5000 frames on this GPU, full batch"),
+    "c1": (5, 100, 5, 100, "cosmos C1: simulated N=5 AOIs x F=100 frames, full batch"),
+}
+O_BINS = 3
+# algorithmic work per unit, forward + backward
+MUFU_PER_UNIT = 980 * O_BINS + 3276
+FLOP_PER_UNIT = 8232 * O_BINS + 63220
+HBM_BYTES_PER_UNIT = 604 + 504
+KSMOGN_HBM_BYTES_PER_UNIT = 392 + 8 + 4 * 9 + 4 * 4 + 4 * 4 + 4 * 10  # pixels, xy, samples, W in; L, grads out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def measure_peaks(lib, _lib, device):
+    """FP32 FMA and MUFU issue peaks of this GPU (ops/s), best of 5 launches."""
+    import ctypes
+
+    scratch = torch.zeros(16, device=device)
+    out = {}
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    for name, fn in (("fma", lib.tq_peak_fma), ("mufu", lib.tq_peak_mufu)):
+        ops = ctypes.c_double()
+        best = 0.0
+        for it in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(sms * 8, 4096, _lib.ptr(scratch), ctypes.byref(ops), _lib.stream_ptr(device)))
+            e1.record()
+            torch.cuda.synchronize(device)
+            if it:
+                best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+        out[name] = best
+    return out
+
+
+def make_shard(workload, rank, device):
+    from tapqir_b200.utils.simulate import simulate
+
+    n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
+    ds = simulate(n_aoi, n_frames, C=1, P=14, seed=rank, device=device, aoi_chunk=50)
+    return ds, nb, fb, desc
+
+
+def run_native(args):
+    from oracle import cosmos_oracle as O
+    from tapqir_b200 import _lib
+    from tapqir_b200.models.cosmos import cosmos
+
+    rank, world, local = dist_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    lib = _lib.load()  # raises if the sm_100a library is missing: no fallback
+
+    ds, nb, fb, desc = make_shard(args.workload, rank, device)
+    model = cosmos(device=str(device), dtype="float")
+    model.data = ds
+    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world)
+    eng = model.engine
+    units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step (C = 1)
+    launches_per_step = model.launches_per_step
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        model.step()
+    barrier()
+
+    # ---- device-resident timing ("value") ----------------------------------------------------------
+    evs = []
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)  # evict the 126 MB L2 (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.step()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    value = units_per_step * world / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (roofline) -------------------------------------------------------------
+    k_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.step(time_likelihood=(e0, e1))
+        torch.cuda.synchronize(device)
+        k_ms.append(e0.elapsed_time(e1))
+    k_ms_avg = sum(k_ms) / len(k_ms)
+    peaks = measure_peaks(lib, _lib, device)
+    measured = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm_peak = measured.get("hbm_gbs", 6650.0)
+    hbm_src = "measured" if "hbm_gbs" in measured else "fallback"
+    mufu_ach = MUFU_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
+    flop_ach = FLOP_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
+    hbm_ach = KSMOGN_HBM_BYTES_PER_UNIT * units_per_step / (k_ms_avg * 1e-3) / 1e9
+    t_mufu, t_fp32 = MUFU_PER_UNIT / peaks["mufu"], FLOP_PER_UNIT / (2 * peaks["fma"])
+    t_hbm = KSMOGN_HBM_BYTES_PER_UNIT / (hbm_peak * 1e9)
+    bound = max((t_mufu, "mufu"), (t_fp32, "fp32"), (t_hbm, "hbm"))
+    roof_units_per_s = 1.0 / bound[0]
+    roofline = {
+        "kernel": "ksmogn_kernel<float,uint16,4,true> (fused render + offset-LSE likelihood fwd+bwd)",
+        "bound": bound[1],
+        "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
+        "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
+        "unit": "Top/s (MUFU)" if bound[1] == "mufu" else ("TFLOP/s" if bound[1] == "fp32" else "GB/s"),
+        "frac": (units_per_step / (k_ms_avg * 1e-3)) / roof_units_per_s,
+        "traffic": None,
+        "kernel_ms": k_ms_avg,
+        "kernel_share_of_step": k_ms_avg / ms_per_step,
+        "algorithmic_per_unit": {"mufu_ops": MUFU_PER_UNIT, "fp32_flop": FLOP_PER_UNIT, "hbm_bytes": KSMOGN_HBM_BYTES_PER_UNIT},
+        "peaks_measured_here": {"mufu_Tops": peaks["mufu"] / 1e12, "fp32_TFLOPs": 2 * peaks["fma"] / 1e12,
+                                "hbm_GBs": hbm_peak, "hbm_source": hbm_src + " (MEASURED_PEAKS.json)"},
+        "hbm_view": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak},
+        "step_roofline_frac": value / world / roof_units_per_s,
+    }
+
+    # ---- end to end through the public API with host buffers --------------------------------------------
+    host_pix = ds.device_store(device).pixels.cpu().pin_memory()
+    host_xy = eng.store.xy.cpu().pin_memory()
+    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        model.step_from_host(host_pix, host_xy, loss_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model.step_from_host(host_pix, host_xy, loss_host)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = units_per_step * world * args.steps / (e2e_ms.item() * 1e-3)
+    e2e = {"value": e2e_value, "unit": "AOI-frames/s",
+           "h2d_bytes_per_step": host_pix.numel() * host_pix.element_size() + host_xy.numel() * host_xy.element_size(),
+           "d2h_bytes_per_step": 8}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_sample(args, budget_s=20.0)
+
+    if rank == 0:
+        line = {
+            "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value, "unit": "AOI-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
+                       "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
+                       "local_terms_dtype": "f64", "likelihood_dtype": "f32"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
+            "wall_s_timed_region": t_wall, "final_loss": float(eng.loss.item()),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_cpu_sample(args, budget_s=20.0):
+    """The oracle (CPU, fp64, all host threads) on the reference-default 10 x 512 minibatch of the
+    same kind of data; returns the cpu_baseline object."""
+    from oracle import cosmos_oracle as O
+    from tapqir_b200.utils.simulate import simulate
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_aoi, n_frames = 20, 600
+    nb, fb = 10, 512
+    ds = simulate(n_aoi, n_frames, seed=0)
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    svi = O.OracleSVI(data, nbatch_size=nb, fbatch_size=fb, seed=0)
+    svi.step()
+    times, t_start = [], time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 40):
+        t0 = time.perf_counter()
+        svi.step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": nb * fb / med, "unit": "AOI-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} steps of the fp64 torch oracle, minibatch {nb} AOIs x {fb} frames drawn from a "
+                      f"simulated {n_aoi} x {n_frames} dataset (O=3), median step {med * 1e3:.0f} ms"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation cannot be imported (pyro-ppl, funsor,
+    pykeops are not installable here), so this times its restatement in oracle/ on the host cores."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    n_aoi, n_frames, _, _, desc = WORKLOADS[args.workload]
+    from oracle import cosmos_oracle as O
+    from tapqir_b200.utils.simulate import simulate
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    nb, fb = 10, 512
+    ds = simulate(20, 600, seed=0)
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    svi = O.OracleSVI(data, nbatch_size=nb, fbatch_size=fb, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        svi.step()
+    steps = min(args.steps, 30)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        svi.step()
+    dt = (time.perf_counter() - t0) / steps
+    value = nb * fb / dt
+    sample = (f"fp64 torch oracle (port of the reference step, Pyro not installable), {steps} steps of the "
+              f"reference-default minibatch {nb} AOIs x {fb} frames from a simulated 20 x 600 dataset, O=3")
+    print(json.dumps({
+        "impl": "reference", "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value,
+        "unit": "AOI-frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "AOI-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "AOI-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,8 @@ SIGNATURES = {
     "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),
+    "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
+    "tq_peak_mufu": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
     "tq_subsample": (c_int, [c_int, c_int, c_uint64, _VP, c_uint64, _VP, _VP, _VP]),
 }
 

@@ -1,0 +1,8 @@
+"""Model registry with the reference's keys (tapqir/models/__init__.py:17-21)."""
+
+from tapqir_b200.models.cosmos import cosmos
+from tapqir_b200.models.model import Model
+
+__all__ = ["models", "Model", "cosmos"]
+
+models = {cosmos.name: cosmos}

@@ -1,0 +1,193 @@
+"""
+cosmos -- multi-colour time-independent colocalization model, B200-native SVI path.
+
+Same class name, registry key, constructor, variational-parameter names / shapes / constraints and
+checkpoint layout as the reference (tapqir/models/cosmos.py:28-80, 464-598).  The generative
+model and guide of cosmos.py:82-462 are not re-expressed in an effect DSL: their ELBO (SURVEY.md
+App. A.3) and its gradient are evaluated by the kernels in ``csrc/`` through
+:class:`tapqir_b200.models.engine.CosmosEngine`.
+"""
+
+import math
+from collections import OrderedDict
+
+import torch
+import torch.distributions.constraints as constraints
+from torch.distributions import transform_to
+
+from tapqir_b200.models import layout as L
+from tapqir_b200.models.model import Model
+
+DEFAULT_PRIORS = {  # cosmos.py:55-64
+    "background_mean_std": 1000.0,
+    "background_std_std": 100.0,
+    "lamda_rate": 1.0,
+    "height_std": 10000.0,
+    "width_min": 0.75,
+    "width_max": 2.25,
+    "proximity_rate": 1.0,
+    "gain_std": 50.0,
+}
+
+
+class cosmos(Model):
+    r"""
+    **Multi-Color Time-Independent Colocalization Model**
+
+    Ordabayev YA, Friedman LJ, Gelles J, Theobald DL. *Bayesian machine learning analysis of
+    single-molecule fluorescence colocalization images.* eLife 2022, doi:10.7554/eLife.73860.
+
+    :param K: Maximum number of spots that can be present in a single image (kernels: K = 2).
+    :param device: Computation device.
+    :param dtype: "float" or "double".
+    :param use_pykeops: accepted for signature compatibility; the offset marginalisation always runs
+        in the fused CUDA kernel.
+    :param priors: Dictionary of parameters of prior distributions.
+    :param ref_dtype: dtype whose ``eps``/``tiny`` the clamping conventions follow; the reference CLI
+        always runs in double (main.py:428), so that is the default whatever ``dtype`` is.
+    """
+
+    name = "cosmos"
+
+    def __init__(self, S: int = 1, K: int = 2, Q: int = None, device: str = "cuda", dtype: str = "float",
+                 use_pykeops: bool = True, priors: dict = None, ref_dtype: str = "double"):
+        super().__init__(S=S, K=K, Q=Q, device=device, dtype=dtype, priors=dict(priors or DEFAULT_PRIORS))
+        if K != L.K or S != L.S:
+            raise NotImplementedError(f"the sm_100a kernels are built for K={L.K}, S={L.S}")
+        self._global_params = ["gain", "proximity", "lamda", "pi"]
+        self.use_pykeops = use_pykeops
+        self.ref_dtype = getattr(torch, ref_dtype)
+        self.conv_params = ["-ELBO", "proximity_loc", "gain_loc", "lamda_loc"]
+        self.ci_params = ["gain", "pi", "lamda", "proximity", "background", "height", "width", "x", "y"]
+
+    # ---- the Pyro-facing hooks of the reference have no counterpart here ------------------------------
+    def model(self):
+        raise NotImplementedError("evaluated by csrc/cosmos_local.cuh + ksmogn_core.cuh, see DESIGN.md")
+
+    def guide(self):
+        raise NotImplementedError("evaluated by csrc/cosmos_local.cuh, see DESIGN.md")
+
+    def TraceELBO(self, jit=False):
+        raise NotImplementedError("the enumerated ELBO is assembled in csrc/cosmos_local.cuh::local_post")
+
+    # ---- variational parameters --------------------------------------------------------------------------
+    def constraints(self):
+        """name -> torch constraint, in the reference's creation order (cosmos.py:471-598)."""
+        eps = torch.finfo(self.ref_dtype).eps
+        P = self.data.P
+        half = (P + 1) / 2
+        return OrderedDict([
+            ("pi_mean", constraints.simplex),
+            ("pi_size", constraints.positive),
+            ("m_probs", constraints.unit_interval),
+            ("proximity_loc", constraints.interval(0, (P + 1) / math.sqrt(12) - eps)),
+            ("proximity_size", constraints.greater_than(2.0)),
+            ("lamda_loc", constraints.positive),
+            ("lamda_beta", constraints.positive),
+            ("gain_loc", constraints.positive),
+            ("gain_beta", constraints.positive),
+            ("background_mean_loc", constraints.positive),
+            ("background_std_loc", constraints.positive),
+            ("b_loc", constraints.positive),
+            ("b_beta", constraints.positive),
+            ("h_loc", constraints.positive),
+            ("h_beta", constraints.positive),
+            ("w_mean", constraints.interval(0.75 + eps, 2.25 - eps)),
+            ("w_size", constraints.greater_than(2.0)),
+            ("x_mean", constraints.interval(-half + eps, half - eps)),
+            ("y_mean", constraints.interval(-half + eps, half - eps)),
+            ("size", constraints.greater_than(2.0)),
+        ])
+
+    def _shard(self):
+        """Contiguous AOI block of this rank."""
+        Nt, w, r = self.data.Nt, self.world_size, self.rank
+        per = (Nt + w - 1) // w
+        lo, hi = min(r * per, Nt), min((r + 1) * per, Nt)
+        return slice(lo, hi)
+
+    def build_engine(self, seed=0):
+        from tapqir_b200.models.engine import CosmosEngine
+
+        if self.device.type != "cuda":
+            raise RuntimeError("tapqir_b200 has no CPU execution path: construct the model with device='cuda'")
+        sl = self._shard()
+        store = self.data.device_store(self.device, self.dtype, sl)
+        self.engine = CosmosEngine(
+            store, sl.stop - sl.start, self.data.F, self.data.C, self.data.P, self.priors, dtype=self.dtype,
+            lr=self.lr, betas=self.optim_args["betas"], nbatch_size=self.nbatch_size, fbatch_size=self.fbatch_size,
+            seed=seed, ref_dtype=self.ref_dtype, Nt_total=self.data.Nt, aoi_offset=sl.start, rank=self.rank,
+            world_size=self.world_size, process_group=self.process_group)
+        self.nbatch_size, self.fbatch_size = self.engine.nb, self.engine.fb
+        return self.engine
+
+    def init_parameters(self):
+        """Initial values of cosmos.py:471-598, stored unconstrained (``transform_to(c).inv``)."""
+        eng, data = self.engine, self.data
+        dev, dt = self.device, torch.float64
+        K, Q, C, F = self.K, self.Q, data.C, data.F
+        Nt = eng.Nt
+        bg = (data.median.to(dev, dt) - data.offset.mean)
+        full = lambda shape, v: torch.full(shape, float(v), dtype=dt, device=dev)
+        init = {
+            "pi_mean": torch.ones(Q, self.S + 1, dtype=dt, device=dev),
+            "pi_size": full((Q, 1), 2),
+            "m_probs": full((K, Nt, F, Q), 0.5),
+            "proximity_loc": full((), 0.5),
+            "proximity_size": full((), 100),
+            "lamda_loc": full((Q,), 0.5),
+            "lamda_beta": full((Q,), 100),
+            "gain_loc": full((), 5),
+            "gain_beta": full((), 100),
+            "background_mean_loc": bg.expand(Nt, 1, C),
+            "background_std_loc": full((Nt, 1, C), 1),
+            "b_loc": bg.expand(Nt, F, C),
+            "b_beta": full((Nt, F, C), 1),
+            "h_loc": full((K, Nt, F, Q), 2000),
+            "h_beta": full((K, Nt, F, Q), 0.001),
+            "w_mean": full((K, Nt, F, Q), 1.5),
+            "w_size": full((K, Nt, F, Q), 100),
+            "x_mean": full((K, Nt, F, Q), 0),
+            "y_mean": full((K, Nt, F, Q), 0),
+            "size": full((K, Nt, F, Q), 200),
+        }
+        cons = self.constraints()
+        views = eng.named_unconstrained()
+        for name, value in init.items():
+            if name == "pi_mean":
+                u = value.log()  # SoftmaxTransform.inv
+            else:
+                u = transform_to(cons[name]).inv(value)
+            views[name].copy_(u.to(eng.dtype).reshape(views[name].shape))
+        for buf in (eng.lm, eng.lv, eng.gm, eng.gv, eng.lgrads, eng.ggrads):
+            buf.zero_()
+        eng.set_iteration(0)
+
+    # ---- stepping ---------------------------------------------------------------------------------------------
+    @property
+    def launches_per_step(self):
+        """Kernels of this library launched by one default step (for bench.py's gpu_launches)."""
+        eng = self.engine
+        n = 10  # globals_sample, local_pre, ksmogn, local_post, reduce_aoi, reduce_acc, globals_grad, adam x2, advance
+        n += (0 if eng.full_n else 1) + (0 if eng.full_f else 1)
+        return n
+
+    def step_from_host(self, host_pixels, host_xy, loss_host):
+        """
+        One step fed from HOST buffers, the way the reference feeds every step
+        (utils/dataset.py:140-151: gather on the CPU, ``.to(device)``): pinned host pixels + target
+        locations are copied to the device store, the step runs, the loss is copied back.
+        """
+        eng = self.engine
+        eng.store.pixels.copy_(host_pixels, non_blocking=True)
+        eng.store.xy.copy_(host_xy, non_blocking=True)
+        loss = self.step()
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(loss_host.item())
+
+    # ---- posterior summaries -----------------------------------------------------------------------------------
+    @property
+    def m_probs(self) -> torch.Tensor:
+        r"""Posterior spot presence probability :math:`q(m=1)` (cosmos.py:688-693)."""
+        return self.param("m_probs").detach()

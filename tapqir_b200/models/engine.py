@@ -99,13 +99,14 @@ class CosmosEngine:
             v.copy_(tensors[k].to(device=self.device, dtype=self.dtype).reshape(v.shape))
 
     # ---- one step ------------------------------------------------------------------------------------------
-    def step(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True):
+    def step(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
         """
         Enqueue one SVI step.  ``ndx``/``fdx`` (int32 CUDA tensors of local AOI / frame indices) and
         the base variates (``local_noise`` (NSAMP, U) in ``dtype``; ``global_noise`` float64 in
         GlobalLayout noise order) put the step in *replay* mode for parity tests; by default indices
         and variates are drawn on the device with Philox keyed by (seed, step).
         With ``update=False`` parameters are left untouched (gradients only).
+        ``time_likelihood=(start_event, end_event)`` records CUDA events around the likelihood kernel.
         Returns the device tensor holding the loss (-ELBO).
         """
         lib, st, code = self.lib, _lib.stream_ptr(self.device), self.code
@@ -131,10 +132,14 @@ class CosmosEngine:
                                                self.seed, p(self.state), p(local_noise), p(self.samples), p(self.qm), st),
                        "tq_cosmos_local_pre")
             S, G, K = self.samples, self.gs, L.K
+            if time_likelihood is not None:
+                time_likelihood[0].record()
             _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
                                              p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg), 4, p(self.qm),
                                              p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
                                              p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
+            if time_likelihood is not None:
+                time_likelihood[1].record()
             _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
                                                 p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
                                                 p(self.aoi_partial), p(self.block_partial), p(self.acc), st),
