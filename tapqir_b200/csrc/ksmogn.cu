@@ -9,6 +9,7 @@
 // sweep because its upstream weights are known before the sweep starts.
 #include "common.cuh"
 #include "ksmogn_core.cuh"
+#include "ksmogn_fast.cuh"
 
 namespace tq {
 
@@ -43,7 +44,7 @@ ksmogn_kernel(const KsmognArgs<T> a) {
 #pragma unroll
     for (int m = 0; m < NM; ++m)
 #pragma unroll
-        for (int k = 0; k < kK; ++k) mcfg[m][k] = a.mcfg[m * kK + k];
+        for (int k = 0; k < kK; ++k) mcfg[m][k] = a.mcfg ? a.mcfg[m * kK + k] : T((m >> k) & 1);
     const T gain = a.gain[0];
     const T rate = T(1) / gain;
     const T log_rate = Real<T>::log(rate);
@@ -127,6 +128,153 @@ ksmogn_kernel(const KsmognArgs<T> a) {
     }
 }
 
+
+// ---- fp32 production kernel (ksmogn_fast.cuh): enumerated table, offsets cached in registers ---------
+template <typename PIX, int OC, bool P14, bool BWD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ksmogn_fast_kernel(const KsmognArgs<float> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* off_s = reinterpret_cast<float*>(smem_raw);
+    float* off_w2 = off_s + a.v.O;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* gx = off_w2 + a.v.O + warp * (2 * kK * kMaxP);
+    float* gy = gx + kK * kMaxP;
+    for (int j = threadIdx.x; j < a.v.O; j += blockDim.x) {
+        off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
+        off_w2[j] = static_cast<const float*>(a.v.offset_logits)[j] * kLog2e;
+    }
+    FastConst fc;
+    fc.gain = a.gain[0];
+    fc.rate = 1.0f / fc.gain;
+    fc.rate2 = fc.rate * kLog2e;
+    fc.log_rate = logf(fc.rate);
+    __syncthreads();
+
+    const int P = P14 ? 14 : a.v.P, PP = P * P;
+    const PIX* pixels = static_cast<const PIX*>(a.v.pixels);
+    const float* xy = static_cast<const float*>(a.v.xy);
+
+    for (int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp; u < a.U;
+         u += (int64_t)gridDim.x * kWarpsPerBlock) {
+        const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        PatchSpots<float> s;
+        float norm[kK];
+        const float tx = xy[ui.patch * 2 + 0], ty = xy[ui.patch * 2 + 1];
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            s.h[k] = a.height[k * a.U + u];
+            s.w[k] = a.width[k * a.U + u];
+            s.cx[k] = a.x[k * a.U + u] + tx;
+            s.cy[k] = a.y[k * a.U + u] + ty;
+            norm[k] = 1.0f / (6.283185307179586f * s.w[k] * s.w[k]);
+        }
+        s.b = a.background[u];
+        float Wr[kM];
+#pragma unroll
+        for (int m = 0; m < kM; ++m) Wr[m] = BWD ? a.W[m * a.U + u] * fc.rate : 0.0f;
+
+        __syncwarp();
+        for (int idx = lane; idx < 2 * kK * P; idx += 32) {
+            const int axis = idx / (kK * P), rem = idx - axis * (kK * P);
+            const int k = rem / P, i = rem - k * P;
+            const float c = axis == 0 ? s.cx[k] : s.cy[k];
+            const float d = float(i) - c;
+            const float g = __expf(-(d * d) * 0.5f * (norm[k] * 6.283185307179586f));
+            (axis == 0 ? gx : gy)[k * kMaxP + i] = g;
+        }
+        __syncwarp();
+
+        PatchOut<float, kM> out;
+        out.zero();
+        const PIX* pix = pixels + ui.patch * PP;
+#pragma unroll 1
+        for (int p = lane; p < PP; p += 32) {
+            const int row = p / P, col = p - row * P;
+            float gxk[kK], gyk[kK];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                gxk[k] = gx[k * kMaxP + col];
+                gyk[k] = gy[k * kMaxP + row];
+            }
+            pixel_accumulate_fast<kM, OC, BWD>(float(pix[p]), gxk, gyk, col, row, s, norm, fc, a.v.O, off_s,
+                                               off_w2, Wr, out);
+        }
+#pragma unroll
+        for (int m = 0; m < kM; ++m) out.logp[m] = warp_sum(out.logp[m]);
+        if (BWD) {
+            out.g_b = warp_sum(out.g_b);
+            out.g_rate = warp_sum(out.g_rate);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                out.g_h[k] = warp_sum(out.g_h[k]);
+                out.g_w[k] = warp_sum(out.g_w[k]);
+                out.g_x[k] = warp_sum(out.g_x[k]);
+                out.g_y[k] = warp_sum(out.g_y[k]);
+            }
+        }
+        if (lane == 0) {
+            if (a.logp) {
+#pragma unroll
+                for (int m = 0; m < kM; ++m) a.logp[m * a.U + u] = out.logp[m];
+            }
+            if (BWD) {
+                a.g_background[u] = out.g_b;
+                a.g_rate[u] = out.g_rate;
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    a.g_height[k * a.U + u] = out.g_h[k];
+                    a.g_width[k * a.U + u] = out.g_w[k];
+                    a.g_x[k * a.U + u] = out.g_x[k];
+                    a.g_y[k * a.U + u] = out.g_y[k];
+                }
+            }
+        }
+    }
+}
+
+template <typename PIX, int OC, bool P14, bool BWD>
+static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (2 * (size_t)a.v.O + kWarpsPerBlock * 2 * kK * kMaxP);
+    auto kern = ksmogn_fast_kernel<PIX, OC, P14, BWD>;
+    if (smem > 48 * 1024) {
+        int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                              "cudaFuncSetAttribute(ksmogn_fast)");
+        if (st2 != TQ_OK) return st2;
+    }
+    const int64_t blocks_needed = (a.U + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
+    TQ_LAUNCH_CHECK("ksmogn_fast_kernel launch");
+    return TQ_OK;
+}
+
+template <typename PIX, bool BWD>
+static int dispatch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
+    const bool p14 = a.v.P == 14;
+    switch (a.v.O <= 4 ? a.v.O : 0) {
+        case 1: return p14 ? launch_fast<PIX, 1, true, BWD>(a, st) : launch_fast<PIX, 1, false, BWD>(a, st);
+        case 2: return p14 ? launch_fast<PIX, 2, true, BWD>(a, st) : launch_fast<PIX, 2, false, BWD>(a, st);
+        case 3: return p14 ? launch_fast<PIX, 3, true, BWD>(a, st) : launch_fast<PIX, 3, false, BWD>(a, st);
+        case 4: return p14 ? launch_fast<PIX, 4, true, BWD>(a, st) : launch_fast<PIX, 4, false, BWD>(a, st);
+        default: return p14 ? launch_fast<PIX, 0, true, BWD>(a, st) : launch_fast<PIX, 0, false, BWD>(a, st);
+    }
+}
+
+// float + enumerated table (mcfg == NULL): production kernel; everything else: exact generic kernel
+template <bool BWD>
+static int try_fast(const KsmognArgs<float>& a, int NM, cudaStream_t st, bool& handled) {
+    handled = false;
+    if (NM != kM || a.mcfg != nullptr || a.U == 0) return TQ_OK;
+    handled = true;
+    switch (a.v.pixtype) {
+        case TQ_PIX_U16: return dispatch_fast<uint16_t, BWD>(a, st);
+        case TQ_PIX_F32: return dispatch_fast<float, BWD>(a, st);
+        default: handled = false; return TQ_OK;
+    }
+}
+template <bool BWD> static int try_fast(const KsmognArgs<double>&, int, cudaStream_t, bool& handled) { handled = false; return TQ_OK; }
+
 template <typename T, typename PIX, int NM, bool BWD>
 static int launch_ksmogn(const KsmognArgs<T>& a, cudaStream_t st) {
     if (a.U == 0) return TQ_OK;
@@ -170,6 +318,9 @@ static int run_ksmogn(const tq_patch_view* view, const void* height, const void*
     a.g_background = (T*)g_background; a.g_rate = (T*)g_rate;
     a.U = (int64_t)view->nb * view->fb * view->C;
     cudaStream_t st = (cudaStream_t)stream;
+    bool handled = false;
+    const int fst = try_fast<BWD>(a, NM, st, handled);
+    if (handled) return fst;
     if (NM == 1) return dispatch_pix<T, 1, BWD>(a, st);
     if (NM == kM) return dispatch_pix<T, kM, BWD>(a, st);
     set_error("ksmogn: NM must be 1 or %d, got %d", kM, NM);
@@ -240,7 +391,8 @@ extern "C" int tq_ksmogn_fwd(int dtype, const tq_patch_view* view, const void* h
                              const void* mcfg, int NM, void* logp, void* stream) {
     int st = check_view(view);
     if (st != TQ_OK) return st;
-    TQ_CHECK_ARG(height && width && x && y && background && gain && mcfg && logp, "NULL pointer");
+    TQ_CHECK_ARG(height && width && x && y && background && gain && logp, "NULL pointer");
+    TQ_CHECK_ARG(mcfg || NM == kM, "mcfg == NULL selects the enumerated 2^K table and needs NM == 4");
     if (dtype == TQ_F32)
         return run_ksmogn<float, false>(view, height, width, x, y, background, gain, mcfg, NM, nullptr, logp,
                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
@@ -258,7 +410,8 @@ extern "C" int tq_ksmogn_fwd_bwd(int dtype, const tq_patch_view* view, const voi
                                  void* stream) {
     int st = check_view(view);
     if (st != TQ_OK) return st;
-    TQ_CHECK_ARG(height && width && x && y && background && gain && mcfg && W, "NULL input pointer");
+    TQ_CHECK_ARG(height && width && x && y && background && gain && W, "NULL input pointer");
+    TQ_CHECK_ARG(mcfg || NM == kM, "mcfg == NULL selects the enumerated 2^K table and needs NM == 4");
     TQ_CHECK_ARG(g_height && g_width && g_x && g_y && g_background && g_rate, "NULL gradient pointer");
     if (dtype == TQ_F32)
         return run_ksmogn<float, true>(view, height, width, x, y, background, gain, mcfg, NM, W, logp,

@@ -1,0 +1,172 @@
+// fp32 production form of the per-pixel likelihood arithmetic (same quantities as
+// ksmogn_core.cuh::pixel_accumulate, which stays the fp64 / exact-parity form).
+//
+// The kernel is bound by instruction issue and by the MUFU pipe (16 lanes/SM/clk), so this form
+//   * works in base 2: lg2.approx / ex2.approx are single MUFU ops, the ln2 factors are folded into
+//     per-patch constants;
+//   * caches the per-offset terms of a pixel in registers (OC <= 4 offset bins, one pass) instead
+//     of two passes over the offsets;
+//   * evaluates lgamma(a) and digamma(a) from ONE lg2(a) and ONE reciprocal through their Stirling
+//     series (a = image/gain >= 4 directly, recurrence shift below that), SURVEY.md App. C.3;
+//   * gets 1/a and 1/sum_exp from one rcp of their product;
+//   * specialises the spot-presence table to the enumerated {0,1}^K one (no multiplies by m).
+// Accuracy is pinned by tests/test_ksmogn_gpu.py and tests/test_step_gpu.py at the north-star
+// tolerance (1e-5 of the fp64 oracle).
+#pragma once
+#include "ksmogn_core.cuh"
+
+namespace tq {
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+inline float f_lg2(float x) { return log2f(x); }
+inline float f_ex2(float x) { return exp2f(x); }
+inline float f_rcp(float x) { return 1.0f / x; }
+#endif
+
+constexpr float kLn2 = 0.69314718055994530942f;
+constexpr float kLog2e = 1.44269504088896340736f;
+constexpr float kHalfLn2Pi = 0.91893853320467274178f;
+constexpr float kNegInf = -3.0e38f;  // finite stand-in for -inf: keeps (v - max) free of NaNs
+
+// per-patch constants of the fast form
+struct FastConst {
+    float rate;       // 1 / gain
+    float rate2;      // rate * log2(e)
+    float log_rate;   // log(rate)
+    float gain;       // 1 / rate
+};
+
+// Stirling pieces for a >= 4:  lgamma(a) = (a - 1/2) ln a - a + ln(2 pi)/2 + r(a);  psi(a) = ln a - q(a)
+TQ_HD void stirling(float ia, float& r, float& q) {
+    const float ia2 = ia * ia;
+    r = ia * (0.0833333333f - ia2 * (0.00277777778f - ia2 * 0.000793650794f));
+    q = ia * (0.5f + ia * (0.0833333333f - ia2 * (0.00833333333f - ia2 * 0.00396825397f)));
+}
+
+// OC > 0: exactly OC offset bins cached in registers.  OC == 0: any O, two passes.
+template <int NM, int OC, bool BWD>
+TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&gyk)[kK], int col, int row,
+                                 const PatchSpots<float>& s, const float (&norm)[kK], const FastConst& fc,
+                                 int O, const float* __restrict__ off_s, const float* __restrict__ off_w2,
+                                 const float (&Wr)[NM], PatchOut<float, NM>& out) {
+    static_assert(NM == kM, "fast path is written for the enumerated 2^K table");
+    float shape[kK], mu[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        shape[k] = gxk[k] * gyk[k] * norm[k];
+        mu[k] = s.h[k] * shape[k];
+    }
+    float img[NM];
+    img[0] = s.b;
+    img[1] = s.b + mu[0];
+    img[2] = s.b + mu[1];
+    img[3] = img[1] + mu[1];
+
+    constexpr int NC = OC > 0 ? OC : 1;
+    float y[NC], l2[NC], b2[NC];
+    if (OC > 0) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const float yy = D - off_s[j];
+            const bool ok = yy > 0.0f;
+            y[j] = ok ? yy : 1.0f;
+            l2[j] = f_lg2(y[j]);
+            b2[j] = ok ? fmaf(-fc.rate2, yy, off_w2[j]) - l2[j] : kNegInf;
+        }
+    }
+    float gi[NM];
+    float g_img_sum = 0.0f;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+        const float a = img[m] * fc.rate;
+        float mx = kNegInf, se = 0.0f, sl = 0.0f, sy = 0.0f;
+        if (OC > 0) {
+            float v[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                v[j] = fmaf(a, l2[j], b2[j]);
+                mx = fmaxf(mx, v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const float e = f_ex2(v[j] - mx);
+                se += e;
+                if (BWD) {
+                    sl = fmaf(e, l2[j], sl);
+                    sy = fmaf(e, y[j], sy);
+                }
+            }
+        } else {
+            for (int j = 0; j < O; ++j) {
+                const float yy = D - off_s[j];
+                if (yy > 0.0f) {
+                    const float l = f_lg2(yy);
+                    mx = fmaxf(mx, fmaf(a, l, fmaf(-fc.rate2, yy, off_w2[j]) - l));
+                }
+            }
+            for (int j = 0; j < O; ++j) {
+                const float yy = D - off_s[j];
+                if (yy > 0.0f) {
+                    const float l = f_lg2(yy);
+                    const float e = f_ex2(fmaf(a, l, fmaf(-fc.rate2, yy, off_w2[j]) - l) - mx);
+                    se += e;
+                    if (BWD) {
+                        sl = fmaf(e, l, sl);
+                        sy = fmaf(e, yy, sy);
+                    }
+                }
+            }
+        }
+        if (mx <= kNegInf) {  // pixel at or below every offset: log-probability -inf (ksmogn.py:225-236)
+            out.logp[m] = -INFINITY;
+            gi[m] = 0.0f;
+            continue;
+        }
+        // lgamma / digamma of a through Stirling; shift by 4 when a is small
+        float as = a, shift_log = 0.0f, shift_psi = 0.0f;
+        if (a < 4.0f) {
+            const float p01 = a * (a + 1.0f), p23 = (a + 2.0f) * (a + 3.0f);
+            shift_log = kLn2 * f_lg2(p01 * p23);
+            // 1/a + 1/(a+1) + 1/(a+2) + 1/(a+3)
+            shift_psi = (2.0f * a + 1.0f) * f_rcp(p01) + (2.0f * a + 5.0f) * f_rcp(p23);
+            as = a + 4.0f;
+        }
+        const float inv = f_rcp(as * se);   // one reciprocal for 1/a and 1/se
+        const float ia = inv * se, ise = inv * as;
+        const float la = kLn2 * f_lg2(as);
+        float r, q;
+        stirling(ia, r, q);
+        // a log(rate) - lgamma(a) = a log(rate) - [(as - 1/2) la - as + ln(2pi)/2 + r] + shift_log
+        const float neg_lgamma = fmaf(0.5f - as, la, as) - kHalfLn2Pi - r + shift_log;
+        const float lse = kLn2 * (mx + f_lg2(se));
+        out.logp[m] += fmaf(a, fc.log_rate, neg_lgamma) + lse;
+        if (BWD) {
+            const float psi = la - q - shift_psi;
+            const float dLda = fc.log_rate - psi + kLn2 * sl * ise;
+            gi[m] = Wr[m] * dLda;   // Wr = W * rate
+            out.g_rate += Wr[m] * fc.gain * fmaf(img[m], dLda + 1.0f, -sy * ise);
+            g_img_sum += gi[m];
+        }
+    }
+    if (BWD) {
+        out.g_b += g_img_sum;
+        const float S[kK] = {gi[1] + gi[3], gi[2] + gi[3]};
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            const float iw = f_rcp(s.w[k]);
+            const float iw2 = iw * iw;
+            const float dx = float(col) - s.cx[k], dy = float(row) - s.cy[k];
+            const float t = S[k] * mu[k];
+            out.g_h[k] = fmaf(S[k], shape[k], out.g_h[k]);
+            out.g_x[k] = fmaf(t * iw2, dx, out.g_x[k]);
+            out.g_y[k] = fmaf(t * iw2, dy, out.g_y[k]);
+            out.g_w[k] = fmaf(t * iw, fmaf(dx, dx, dy * dy) * iw2 - 2.0f, out.g_w[k]);
+        }
+    }
+}
+
+}  // namespace tq

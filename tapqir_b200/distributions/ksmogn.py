@@ -22,6 +22,10 @@ from tapqir_b200 import _lib
 from tapqir_b200.distributions.util import gaussian_spots
 
 
+def _enumerated_table(dtype, device):
+    return torch.tensor([[(m >> k) & 1 for k in range(_lib.K)] for m in range(_lib.M)], dtype=dtype, device=device)
+
+
 class _KsmognLogProb(torch.autograd.Function):
     """log p for NM configurations of U patches; inputs already flattened to kernel layout."""
 
@@ -32,11 +36,13 @@ class _KsmognLogProb(torch.autograd.Function):
         view = _lib.make_view(value, target, off_s, off_w, nb=U, fb=1, C=1, F=1, P=P)
         logp = torch.empty((NM, U), dtype=dtype, device=dev)
         lib = _lib.load()
+        # the enumerated {0,1}^K table selects the specialised kernel (mcfg = NULL in the C ABI)
+        ctx.enumerated = NM == _lib.M and bool(torch.equal(mcfg, _enumerated_table(dtype, dev)))
         with torch.cuda.device(dev):
             _lib.check(lib.tq_ksmogn_fwd(_lib.dtype_code(dtype), view, _lib.ptr(height), _lib.ptr(width),
                                          _lib.ptr(x), _lib.ptr(y), _lib.ptr(background), _lib.ptr(gain),
-                                         _lib.ptr(mcfg), NM, _lib.ptr(logp), _lib.stream_ptr(dev)),
-                       "tq_ksmogn_fwd")
+                                         None if ctx.enumerated else _lib.ptr(mcfg), NM, _lib.ptr(logp),
+                                         _lib.stream_ptr(dev)), "tq_ksmogn_fwd")
         ctx.save_for_backward(height, width, x, y, background, gain, target, value, off_s, off_w, mcfg)
         ctx.P = P
         return logp
@@ -54,7 +60,7 @@ class _KsmognLogProb(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.tq_ksmogn_fwd_bwd(_lib.dtype_code(dtype), view, _lib.ptr(height), _lib.ptr(width),
                                              _lib.ptr(x), _lib.ptr(y), _lib.ptr(background), _lib.ptr(gain),
-                                             _lib.ptr(mcfg), NM, _lib.ptr(W), None, _lib.ptr(g_h), _lib.ptr(g_w),
+                                             None if ctx.enumerated else _lib.ptr(mcfg), NM, _lib.ptr(W), None, _lib.ptr(g_h), _lib.ptr(g_w),
                                              _lib.ptr(g_x), _lib.ptr(g_y), _lib.ptr(g_b), _lib.ptr(g_rate),
                                              _lib.stream_ptr(dev)), "tq_ksmogn_fwd_bwd")
         g_gain = (-(g_rate.sum()) / (gain * gain)).reshape(gain.shape)

@@ -54,6 +54,7 @@ class CosmosEngine:
         self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
+        self.mcfg_arg = None  # NULL = built-in enumerated table -> fp32 production kernel; set to self.mcfg for the generic one
         self.set_batch(nbatch_size or self.Nt, fbatch_size or self.F)
 
     # ---- buffers that depend on the minibatch shape ---------------------------------------------------
@@ -135,7 +136,7 @@ class CosmosEngine:
             if time_likelihood is not None:
                 time_likelihood[0].record()
             _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
-                                             p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg), 4, p(self.qm),
+                                             p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg_arg), 4, p(self.qm),
                                              p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
                                              p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
             if time_likelihood is not None:

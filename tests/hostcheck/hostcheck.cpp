@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ksmogn_core.cuh"
+#include "ksmogn_fast.cuh"
 
 using namespace tq;
 
@@ -50,6 +51,39 @@ void hc_ksmogn_f32(int64_t U, int P, int O, int NM, const float* height, const f
                    const float* background, float gain, const float* mcfg, const float* W, const float* value, const float* target,
                    const float* off_s, const float* off_w, float* logp, float* g_h, float* g_w, float* g_x, float* g_y, float* g_b, float* g_rate) {
     ksmogn_host<float>(U, P, O, NM, height, width, x, y, background, gain, mcfg, W, value, target, off_s, off_w, logp, g_h, g_w, g_x, g_y, g_b, g_rate);
+}
+// fp32 production form (ksmogn_fast.cuh) with libm standing in for the MUFU approximations
+void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, const float* width, const float* x, const float* y,
+                        const float* background, float gain, const float* W, const float* value, const float* target,
+                        const float* off_s, const float* off_w, float* logp, float* g_h, float* g_w, float* g_x, float* g_y, float* g_b, float* g_rate) {
+    FastConst fc; fc.gain = gain; fc.rate = 1.0f / gain; fc.rate2 = fc.rate * kLog2e; fc.log_rate = logf(fc.rate);
+    std::vector<float> w2(O);
+    for (int j = 0; j < O; ++j) w2[j] = off_w[j] * kLog2e;
+    for (int64_t u = 0; u < U; ++u) {
+        PatchSpots<float> s; float norm[kK], Wr[kM];
+        for (int k = 0; k < kK; ++k) {
+            s.h[k] = height[k * U + u]; s.w[k] = width[k * U + u];
+            s.cx[k] = x[k * U + u] + target[u * 2]; s.cy[k] = y[k * U + u] + target[u * 2 + 1];
+            norm[k] = 1.0f / (6.283185307179586f * s.w[k] * s.w[k]);
+        }
+        s.b = background[u];
+        for (int m = 0; m < kM; ++m) Wr[m] = W[m * U + u] * fc.rate;
+        PatchOut<float, kM> out; out.zero();
+        for (int row = 0; row < P; ++row)
+            for (int col = 0; col < P; ++col) {
+                float gxk[kK], gyk[kK];
+                for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<float>(col, s.cx[k], s.w[k]); gyk[k] = axis_factor<float>(row, s.cy[k], s.w[k]); }
+                const float D = value[(u * P + row) * P + col];
+                switch (OC) {
+                    case 3: pixel_accumulate_fast<kM, 3, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
+                    case 4: pixel_accumulate_fast<kM, 4, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
+                    default: pixel_accumulate_fast<kM, 0, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
+                }
+            }
+        for (int m = 0; m < kM; ++m) logp[m * U + u] = out.logp[m];
+        g_b[u] = out.g_b; g_rate[u] = out.g_rate;
+        for (int k = 0; k < kK; ++k) { g_h[k * U + u] = out.g_h[k]; g_w[k * U + u] = out.g_w[k]; g_x[k * U + u] = out.g_x[k]; g_y[k * U + u] = out.g_y[k]; }
+    }
 }
 double hc_digamma_f64(double x) { return digamma<double>(x); }
 float hc_digamma_f32(float x) { return digamma<float>(x); }

@@ -17,7 +17,7 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def run_host_ksmogn(case, dtype):
+def run_host_ksmogn(case, dtype, fast_oc=None):
     hc = hostcheck.load()
     i = case["inputs"]
     K, P = 2, i["P"]
@@ -37,10 +37,15 @@ def run_host_ksmogn(case, dtype):
     logp = torch.empty(NM, U, dtype=tdt)
     g_h, g_w, g_x, g_y = (torch.empty(K, U, dtype=tdt) for _ in range(4))
     g_b, g_rate = torch.empty(U, dtype=tdt), torch.empty(U, dtype=tdt)
-    fn = getattr(hc, f"hc_ksmogn_{dtype}")
     cf = ctypes.c_double if dtype == "f64" else ctypes.c_float
-    fn(ctypes.c_int64(U), P, off_s.numel(), NM, _p(h), _p(w), _p(x), _p(y), _p(b), cf(i["gain"].item()), _p(mcfg),
-       _p(W), _p(val), _p(tgt), _p(off_s), _p(off_w), _p(logp), _p(g_h), _p(g_w), _p(g_x), _p(g_y), _p(g_b), _p(g_rate))
+    if fast_oc is not None:
+        hc.hc_ksmogn_fast_f32(ctypes.c_int64(U), P, off_s.numel(), fast_oc, _p(h), _p(w), _p(x), _p(y), _p(b),
+                              cf(i["gain"].item()), _p(W), _p(val), _p(tgt), _p(off_s), _p(off_w), _p(logp), _p(g_h),
+                              _p(g_w), _p(g_x), _p(g_y), _p(g_b), _p(g_rate))
+    else:
+        fn = getattr(hc, f"hc_ksmogn_{dtype}")
+        fn(ctypes.c_int64(U), P, off_s.numel(), NM, _p(h), _p(w), _p(x), _p(y), _p(b), cf(i["gain"].item()), _p(mcfg),
+           _p(W), _p(val), _p(tgt), _p(off_s), _p(off_w), _p(logp), _p(g_h), _p(g_w), _p(g_x), _p(g_y), _p(g_b), _p(g_rate))
     back = lambda t: t.t().reshape(batch + (K,)).double()
     gain = i["gain"].item()
     return dict(log_prob=logp.reshape((NM,) + batch).double(), height=back(g_h), width=back(g_w), x=back(g_x), y=back(g_y),
@@ -66,6 +71,16 @@ def test_pixel_math_f32_within_tolerance(golden, name):
     # largest entry of each tensor)
     case = golden["ksmogn"][name]
     out = run_host_ksmogn(case, "f32")
+    assert relerr(out["log_prob"], case["log_prob"]) < 1e-5
+    for k in ("height", "width", "x", "y", "background", "gain"):
+        assert relerr(out[k], case["grads"][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name,oc", [("sim_O3", 3), ("sim_O3", 0), ("hist_O16_C2", 0), ("small_P6", 0)])
+def test_fast_fp32_form_within_tolerance(golden, name, oc):
+    """ksmogn_fast.cuh (Stirling lgamma/digamma, base-2 log-sum-exp, cached offsets) vs the reference."""
+    case = golden["ksmogn"][name]
+    out = run_host_ksmogn(case, "f32", fast_oc=oc)
     assert relerr(out["log_prob"], case["log_prob"]) < 1e-5
     for k in ("height", "width", "x", "y", "background", "gain"):
         assert relerr(out[k], case["grads"][k]) < 1e-5, k
