@@ -48,10 +48,11 @@ SIGNATURES = {
     "tq_sizeof_model_const": (c_int, []),
     "tq_local_post_blocks": (c_int, [c_int64]),
     "tq_cosmos_globals_sample": (c_int, [c_int, c_int, _VP, _VP, _VP, c_uint64, _VP, _VP, _VP, _VP, _VP]),
-    "tq_cosmos_local_pre": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, c_int64, c_uint64, _VP, _VP,
-                                     _VP, _VP, _VP]),
-    "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double,
-                                      c_double, _VP, _VP, _VP, _VP, _VP]),
+    "tq_site_record_rows": (c_int, []),
+    "tq_cosmos_sites": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,
+                                 _VP, _VP]),
+    "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
+                                      c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),

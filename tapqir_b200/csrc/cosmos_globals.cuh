@@ -96,8 +96,13 @@ TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst
     gt.log_rate = log(gt.rate);
     const double r = (mc.P + 1) / (2.0 * prox);
     gt.size1 = r * r - 1.0;                                                            // cosmos.py:185-191
-    gt.lnorm1 = lgamma(gt.size1) - 2.0 * lgamma(0.5 * gt.size1);
-    gt.dlnorm1 = digamma<double>(gt.size1) - digamma<double>(0.5 * gt.size1);
+    {
+        const double ln2 = 0.69314718055994530942, lP1 = log((double)(mc.P + 1));
+        const double lnorm1 = lgamma(gt.size1) - 2.0 * lgamma(0.5 * gt.size1);
+        gt.cxy1 = 2.0 * lnorm1 - 4.0 * (0.5 * gt.size1 - 1.0) * ln2 - 2.0 * lP1;
+        gt.dcxy1 = 2.0 * (digamma<double>(gt.size1) - digamma<double>(0.5 * gt.size1)) - 2.0 * ln2;
+        gt.lxy0 = -2.0 * lP1;
+    }
     const double le = log(mc.eps), l1e = log(1.0 - mc.eps);
     for (int q = 0; q < gl.Q; ++q) {
         ChannelTables<double>& ct = gt.ch[q];

@@ -1,12 +1,20 @@
 // Per-unit ("local") part of the cosmos ELBO: everything models/cosmos.py:216-327 (model) and
 // :393-462 (guide) do for one (AOI, frame, channel) patch except the pixel likelihood itself,
-// written out with its analytic reverse mode.  SURVEY.md App. A.3 gives the ELBO, this file is its
+// written out with its analytic reverse mode.  SURVEY.md App. A.3 gives the ELBO; this file is its
 // per-unit summand and the chain rule down to the unconstrained variational parameters.
 //
-//   local_pre   : unconstrained params -> constrained -> guide samples (replayed variates or
-//                 in-kernel Philox) -> q(m) weights for the likelihood kernel
-//   local_post  : priors, guide log-densities, the (z, theta) log-sum-exp T(m), ELBO summand,
-//                 d/d(samples) (+ likelihood part from K1) -> reparameterisation -> d/d(unconstrained)
+// Two stages around the likelihood kernel:
+//
+//   site_eval  one call per (guide site, unit); 9 sites per unit at K = 2: background, and height,
+//              width, x, y of each spot.  unconstrained params -> constrained -> guide sample (replayed
+//              variate or in-kernel Philox) -> log q, d log q / d sample, and the LINEAR map that turns
+//              the total derivative G = dELBO/dsample into the gradients of the site's two
+//              variational parameters:   grad_p = G * A_p - w * B_p   (w = q(m_k = 1), 1 for background).
+//              Always evaluated in double: ATen's implicit reparameterisation gradients and the
+//              Beta/Gamma log-normalisers cancel catastrophically in fp32 ("precision").
+//   unit_post  one call per unit, cheap (F = float in production): priors, the (z, theta)
+//              log-sum-exp T(m), q(m)-weighted ELBO summand, d/d m_probs, G for every sample, parameter
+//              gradients through the site maps, and the per-channel accumulators for the globals.
 //
 // Host+device: tests/hostcheck runs the same code on the CPU against the oracle.
 #pragma once
@@ -32,17 +40,30 @@ template <typename A> struct ChannelTables {
 };
 template <typename A> struct GlobalTables {
     A gain, rate, log_rate;
-    A size1;        // AffineBeta sample size of the target-specific spot: ((P+1)/(2 proximity))^2 - 1
-    A lnorm1;       // lgamma(size1) - 2 lgamma(size1/2)      (Beta normaliser, per axis)
-    A dlnorm1;      // d lnorm1 / d size1 = psi(size1) - psi(size1/2)
+    A size1;   // AffineBeta sample size of the target-specific spot: ((P+1)/(2 proximity))^2 - 1
+    // log AffineBeta(x; 0, size1) + log AffineBeta(y; 0, size1)
+    //    = (size1/2 - 1) [log1p(-tx^2) + log1p(-ty^2)] + cxy1,   tx = 2 x / (P+1)
+    A cxy1;    // 2 [lgamma(size1) - 2 lgamma(size1/2)] - 4 (size1/2 - 1) ln 2 - 2 ln(P+1)
+    A dcxy1;   // d cxy1-part / d size1 at fixed x, y: 2 [psi(size1) - psi(size1/2)] - 2 ln 2
+    A lxy0;    // uniform (size 2) prior on x and y: -2 ln(P+1)
     ChannelTables<A> ch[kMaxC];
+    template <typename B> TQ_HD void convert_from(const GlobalTables<B>& o) {
+        gain = (A)o.gain; rate = (A)o.rate; log_rate = (A)o.log_rate; size1 = (A)o.size1;
+        cxy1 = (A)o.cxy1; dcxy1 = (A)o.dcxy1; lxy0 = (A)o.lxy0;
+        for (int q = 0; q < kMaxC; ++q) {
+            for (int a = 0; a < 2; ++a) for (int z = 0; z < kZ; ++z) ch[q].logpz[a][z] = (A)o.ch[q].logpz[a][z];
+            for (int a = 0; a < 2; ++a) for (int t = 0; t < kTheta; ++t) ch[q].logptheta[a][t] = (A)o.ch[q].logptheta[a][t];
+            for (int t = 0; t < kTheta; ++t) for (int k = 0; k < kK; ++k) for (int m = 0; m < 2; ++m)
+                ch[q].logpm[t][k][m] = (A)o.ch[q].logpm[t][k][m];
+        }
+    }
 };
 
 // indices into the per-channel accumulator vector reduced over units
 enum {
     ACC_ELBO_FRAME = 0,   // sum mu_n * (frame-level ELBO summand), unscaled
     ACC_ELBO_AOI = 1,     // sum mu_n * (AOI-level prior terms), once per (AOI, channel)
-    ACC_LOGPZ = 2,        // [kZ]           d/d logpz[ontarget=1][z]
+    ACC_LOGPZ = 2,        // [kZ]            d/d logpz[ontarget=1][z]
     ACC_LOGPM = 4,        // [kTheta][kK][2] d/d logpm
     ACC_SIZE1 = 16,       // d/d size1
     ACC_RATE = 17,        // d/d (1/gain) from the likelihood
@@ -66,13 +87,9 @@ template <typename A> TQ_HD Transformed<A> t_interval(A u, A lo, A hi, const Mod
     const A s = sigmoid_clamped(u, mc, act);
     return {lo + (hi - lo) * s, act ? (hi - lo) * s * (A(1) - s) : A(0)};
 }
-template <typename A> TQ_HD Transformed<A> t_unit_interval(A u, const ModelConst& mc) {
-    bool act;
-    const A s = sigmoid_clamped(u, mc, act);
-    return {s, act ? s * (A(1) - s) : A(0)};
-}
 
-// The 18 AOI-local variational parameters of one unit.  Order = order of the flat gradient record.
+// The AOI-local variational parameters of one unit.  Order = order of the flat gradient record and
+// of the tensors in the flat parameter buffer (tapqir_b200/models/layout.py).
 enum {
     LP_BM = 0, LP_BS, LP_B_LOC, LP_B_BETA,
     LP_M_PROBS,                 // + k
@@ -86,30 +103,31 @@ enum {
     NLOCAL = LP_SIZE + kK       // 20 at K = 2
 };
 
-template <typename A> struct UnitParams { Transformed<A> p[NLOCAL]; };
-
-// unconstrained -> constrained for one unit (constraints: models/cosmos.py:481-485, 530-598)
-template <typename A> TQ_HD void transform_unit(const A (&u)[NLOCAL], const ModelConst& mc, UnitParams<A>& out) {
-    const A half = A(mc.P + 1) / A(2), eps = A(mc.eps);
-    out.p[LP_BM] = t_positive(u[LP_BM]);
-    out.p[LP_BS] = t_positive(u[LP_BS]);
-    out.p[LP_B_LOC] = t_positive(u[LP_B_LOC]);
-    out.p[LP_B_BETA] = t_positive(u[LP_B_BETA]);
-#pragma unroll
-    for (int k = 0; k < kK; ++k) {
-        out.p[LP_M_PROBS + k] = t_unit_interval(u[LP_M_PROBS + k], mc);
-        out.p[LP_H_LOC + k] = t_positive(u[LP_H_LOC + k]);
-        out.p[LP_H_BETA + k] = t_positive(u[LP_H_BETA + k]);
-        out.p[LP_W_MEAN + k] = t_interval(u[LP_W_MEAN + k], A(mc.width_min) + eps, A(mc.width_max) - eps, mc);
-        out.p[LP_W_SIZE + k] = t_greater_than(u[LP_W_SIZE + k], A(2));
-        out.p[LP_X_MEAN + k] = t_interval(u[LP_X_MEAN + k], -half + eps, half - eps, mc);
-        out.p[LP_Y_MEAN + k] = t_interval(u[LP_Y_MEAN + k], -half + eps, half - eps, mc);
-        out.p[LP_SIZE + k] = t_greater_than(u[LP_SIZE + k], A(2));
-    }
-}
-
-// Guide samples of one unit: background, and per spot height, width, x, y.  Order of the record.
+// Guide sites of one unit = samples of one unit: background, then height, width, x, y per spot.
 enum { S_B = 0, S_H = 1, S_W = S_H + kK, S_X = S_W + kK, S_Y = S_X + kK, NSAMP = S_Y + kK };  // 9 at K=2
+
+// Per-site record written by site_eval (SoA rows of the (NREC, U) buffer)
+enum { SO_LQ = 0, SO_DQ, SO_A0, SO_B0, SO_A1, SO_B1, NSO };
+// extra rows of the background site: its model prior Gamma((bm/bs)^2, bm/bs^2)
+enum { EX_LP = 0, EX_DP, EX_GBM, EX_GBS, NEX };
+constexpr int NREC = NSAMP * NSO + NEX;  // 58 at K = 2
+
+// which two local parameters parameterise site s, and which family it is
+TQ_HD int site_param0(int s) {
+    if (s == S_B) return LP_B_LOC;
+    if (s < S_W) return LP_H_LOC + (s - S_H);
+    if (s < S_X) return LP_W_MEAN + (s - S_W);
+    if (s < S_Y) return LP_X_MEAN + (s - S_X);
+    return LP_Y_MEAN + (s - S_Y);
+}
+TQ_HD int site_param1(int s) {
+    if (s == S_B) return LP_B_BETA;
+    if (s < S_W) return LP_H_BETA + (s - S_H);
+    if (s < S_X) return LP_W_SIZE + (s - S_W);
+    if (s < S_Y) return LP_SIZE + (s - S_X);
+    return LP_SIZE + (s - S_Y);
+}
+TQ_HD bool site_is_gamma(int s) { return s < S_W; }
 
 // Beta on [low, low+scale] in mean / sample-size form (affine_beta.py:33-49)
 template <typename A> struct AffBeta {
@@ -126,58 +144,6 @@ template <typename A> TQ_HD A beta01_from_gammas(A g1, A g2, const ModelConst& m
     A v = g1 / (g1 + g2);
     v = Real<A>::max(v, A(mc.tiny));
     return Real<A>::min(v, A(1) - A(mc.eps));
-}
-
-// ---- local_pre ---------------------------------------------------------------------------------
-// variates: standard-gamma draws for S_B, S_H+k; (0,1) Beta draws for S_W.., S_X.., S_Y.. (replay),
-// or nullptr-equivalent `use_rng` to draw them here.
-template <typename A>
-TQ_HD void local_pre(const UnitParams<A>& up, const ModelConst& mc, bool use_rng, Philox* rng,
-                     A (&variate)[NSAMP], A (&sample)[NSAMP], A (&qm)[kM]) {
-    const A half = A(mc.P + 1) / A(2);
-    const A tiny = A(mc.tiny);
-    // background ~ Gamma(b_loc * b_beta, b_beta)                                    cosmos.py:408-415
-    {
-        const A conc = up.p[LP_B_LOC].v * up.p[LP_B_BETA].v;
-        if (use_rng) variate[S_B] = Real<A>::max(sample_std_gamma<A>(*rng, conc), tiny);
-        sample[S_B] = Real<A>::max(variate[S_B] / up.p[LP_B_BETA].v, tiny);
-    }
-#pragma unroll
-    for (int k = 0; k < kK; ++k) {
-        // height ~ Gamma(h_loc * h_beta, h_beta)                                     cosmos.py:428-435
-        const A conc = up.p[LP_H_LOC + k].v * up.p[LP_H_BETA + k].v;
-        if (use_rng) variate[S_H + k] = Real<A>::max(sample_std_gamma<A>(*rng, conc), tiny);
-        sample[S_H + k] = Real<A>::max(variate[S_H + k] / up.p[LP_H_BETA + k].v, tiny);
-        // width, x, y ~ AffineBeta                                                   cosmos.py:436-462
-        const AffBeta<A> dw(up.p[LP_W_MEAN + k].v, up.p[LP_W_SIZE + k].v, A(mc.width_min), A(mc.width_max));
-        const AffBeta<A> dx(up.p[LP_X_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-        const AffBeta<A> dy(up.p[LP_Y_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-        if (use_rng) {
-            A g1 = sample_std_gamma<A>(*rng, dw.c1), g2 = sample_std_gamma<A>(*rng, dw.c0);
-            variate[S_W + k] = beta01_from_gammas(g1, g2, mc);
-            g1 = sample_std_gamma<A>(*rng, dx.c1); g2 = sample_std_gamma<A>(*rng, dx.c0);
-            variate[S_X + k] = beta01_from_gammas(g1, g2, mc);
-            g1 = sample_std_gamma<A>(*rng, dy.c1); g2 = sample_std_gamma<A>(*rng, dy.c0);
-            variate[S_Y + k] = beta01_from_gammas(g1, g2, mc);
-        }
-        sample[S_W + k] = dw.clamp(dw.low + dw.scale * variate[S_W + k], mc);
-        sample[S_X + k] = dx.clamp(dx.low + dx.scale * variate[S_X + k], mc);
-        sample[S_Y + k] = dy.clamp(dy.low + dy.scale * variate[S_Y + k], mc);
-    }
-    // q(m) = prod_k Bernoulli(m_k; m_probs_k) with torch's eps clamp                   cosmos.py:419-425
-    A q1[kK];
-#pragma unroll
-    for (int k = 0; k < kK; ++k) {
-        const A p = up.p[LP_M_PROBS + k].v;
-        q1[k] = Real<A>::min(Real<A>::max(p, A(mc.eps)), A(1) - A(mc.eps));
-    }
-#pragma unroll
-    for (int m = 0; m < kM; ++m) {
-        A q = A(1);
-#pragma unroll
-        for (int k = 0; k < kK; ++k) q *= ((m >> k) & 1) ? q1[k] : (A(1) - q1[k]);
-        qm[m] = q;
-    }
 }
 
 // ---- densities and their partials ----------------------------------------------------------------
@@ -209,133 +175,194 @@ template <typename A> struct BetaSite {
     }
 };
 
-// Outputs of local_post for one unit.
-template <typename A> struct UnitGrads {
-    A g[NLOCAL];   // d ELBO_unit / d unconstrained (unit-level, unscaled, before the mask)
-    A acc[NACC];   // contributions to the per-channel accumulators (unscaled, before the mask)
+// ---- site_eval -----------------------------------------------------------------------------------------
+//   s         site index (S_B, S_H + k, S_W + k, S_X + k, S_Y + k)
+//   u0, u1    unconstrained values of the site's two parameters (site_param0/1)
+//   ubm, ubs  unconstrained background_mean_loc / background_std_loc (read only for s == S_B)
+//   variate   base draw: standard gamma (Gamma sites) or (0,1) Beta draw; filled here when use_rng
+//   rec[NSO]  site record;  extra[NEX] background-prior record (s == S_B only)
+// Returns the guide sample.
+TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, const ModelConst& mc, bool use_rng,
+                       Philox* rng, double& variate, double* rec, double* extra) {
+    using A = double;
+    const A tiny = mc.tiny;
+    if (site_is_gamma(s)) {
+        // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
+        const A loc = exp(u0), beta = exp(u1);
+        const A conc = loc * beta;
+        if (use_rng) variate = fmax(sample_std_gamma<A>(*rng, conc), tiny);
+        const A v = fmax(variate / beta, tiny);
+        const GammaSite<A> q(v, conc, beta);
+        const A sgg = std_gamma_grad<A>(conc, v * beta);
+        rec[SO_LQ] = q.lp;
+        rec[SO_DQ] = q.d_v;
+        // v = variate / beta:  dv/du_loc = sgg * loc,  dv/du_beta = sgg * loc - v
+        rec[SO_A0] = sgg * loc;
+        rec[SO_A1] = sgg * loc - v;
+        rec[SO_B0] = q.d_conc * conc;
+        rec[SO_B1] = q.d_conc * conc + q.d_rate * beta;
+        if (s == S_B) {
+            // model prior Gamma((bm/bs)^2, bm/bs^2)                                       cosmos.py:233-239
+            const A bm = exp(ubm), bs = exp(ubs);
+            const A pc = (bm / bs) * (bm / bs), pr = bm / (bs * bs);
+            const GammaSite<A> p(v, pc, pr);
+            extra[EX_LP] = p.lp;
+            extra[EX_DP] = p.d_v;
+            // d/d u_bm, d/d u_bs (exp transforms: times bm, bs)
+            extra[EX_GBM] = (p.d_conc * (A(2) * bm / (bs * bs)) + p.d_rate / (bs * bs)) * bm;
+            extra[EX_GBS] = (p.d_conc * (-A(2) * bm * bm / (bs * bs * bs)) + p.d_rate * (-A(2) * bm / (bs * bs * bs))) * bs;
+        }
+        return v;
+    }
+    // AffineBeta(mean, size, lo, hi): width cosmos.py:436-444, x :445-453, y :454-462
+    const A half = A(mc.P + 1) / A(2), eps = mc.eps;
+    A lo, hi;
+    if (s < S_X) { lo = mc.width_min; hi = mc.width_max; } else { lo = -half; hi = half; }
+    const Transformed<A> mean = t_interval<A>(u0, lo + eps, hi - eps, mc);
+    const Transformed<A> size = t_greater_than<A>(u1, A(2));
+    const AffBeta<A> d(mean.v, size.v, lo, hi);
+    if (use_rng) {
+        const A g1 = sample_std_gamma<A>(*rng, d.c1), g2 = sample_std_gamma<A>(*rng, d.c0);
+        variate = beta01_from_gammas(g1, g2, mc);
+    }
+    const A v = d.clamp(d.low + d.scale * variate, mc);
+    const BetaSite<A> q(v, d);
+    A bg1, bg0;
+    beta_grad_pair<A>(q.x01, d.c1, d.c0, bg1, bg0);
+    const A dv_dc1 = d.scale * (A(1) - q.x01) * bg1;
+    const A dv_dc0 = -d.scale * q.x01 * bg0;
+    const A km = size.v / d.scale * mean.d;                  // d c1 / d u_mean = - d c0 / d u_mean
+    const A k1 = (mean.v - d.low) / d.scale * size.d;        // d c1 / d u_size
+    const A k0 = (d.low + d.scale - mean.v) / d.scale * size.d;
+    rec[SO_LQ] = q.lp;
+    rec[SO_DQ] = q.d_v;
+    rec[SO_A0] = (dv_dc1 - dv_dc0) * km;
+    rec[SO_B0] = (q.d_c1 - q.d_c0) * km;
+    rec[SO_A1] = dv_dc1 * k1 + dv_dc0 * k0;
+    rec[SO_B1] = q.d_c1 * k1 + q.d_c0 * k0;
+    return v;
+}
+
+// q(m_k = 1), q(m_k = 0), their logs and d q1 / d u for Bernoulli(sigmoid(u)) with the reference's
+// clamps (unit_interval transform clamp + Bernoulli probs clamp to [eps, 1 - eps]), evaluated on the
+// logit so that fp32 never produces an exact 0 or 1.                                  cosmos.py:419-425, 481-485
+template <typename F> struct SpotPresence {
+    F q1, q0, lq1, lq0, dq1;
+    TQ_HD SpotPresence(F u, const ModelConst& mc) {
+        using R = Real<F>;
+        const F lim = F(log((1.0 - mc.eps) / mc.eps));
+        const bool inside = (u >= -lim) && (u <= lim);
+        const F uc = R::min(R::max(u, -lim), lim);
+        const F e = R::exp(-R::abs(uc));
+        const F sp = R::log1p(e);                 // softplus(-|uc|)
+        const F big = F(1) / (F(1) + e), small = e / (F(1) + e);
+        if (uc >= F(0)) { q1 = big; q0 = small; lq1 = -sp; lq0 = -uc - sp; }
+        else            { q1 = small; q0 = big; lq1 = uc - sp; lq0 = -sp; }
+        dq1 = inside ? q1 * q0 : F(0);
+    }
 };
 
-// ---- local_post --------------------------------------------------------------------------------
-//   sample     guide samples (same values the likelihood kernel used)
+template <typename F> TQ_HD void presence_weights(const F (&q1)[kK], const F (&q0)[kK], F (&qm)[kM]) {
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        F q = F(1);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) q *= ((m >> k) & 1) ? q1[k] : q0[k];
+        qm[m] = q;
+    }
+}
+
+// Outputs of unit_post for one unit.
+template <typename F> struct UnitGrads {
+    F g[NLOCAL];   // d ELBO_unit / d unconstrained (unit-level, unscaled, before the mask)
+    F acc[NACC];   // contributions to the per-channel accumulators (unscaled, before the mask)
+};
+
+// ---- unit_post -------------------------------------------------------------------------------------------
+//   rec        (NREC) site records of this unit (rows s * NSO + SO_*, then the NEX extra rows)
+//   sample     guide samples (the values the likelihood kernel used)
 //   L          log-likelihood of the 4 configurations from K1
 //   gs         d (sum_m q(m) L(m)) / d sample from K1 (weights W(m) = q(m))
 //   g_rate     d (sum_m q(m) L(m)) / d (1/gain) from K1
+//   u_mp       unconstrained m_probs of the K spots; u_bm/u_bs unconstrained AOI-level parameters
 //   first_frame  this unit carries the AOI-level prior terms of its (AOI, channel)
-template <typename A>
-TQ_HD void local_post(const UnitParams<A>& up, const ModelConst& mc, const GlobalTables<A>& gt, int c,
-                      bool ontarget, bool first_frame, const A (&sample)[NSAMP], const A (&L)[kM],
-                      const A (&gs)[NSAMP], A g_rate, UnitGrads<A>& out) {
-    using R = Real<A>;
-    const ChannelTables<A>& ct = gt.ch[c];
-    const A half = A(mc.P + 1) / A(2);
+template <typename F>
+TQ_HD void unit_post(const F (&rec)[NREC], const F (&sample)[NSAMP], const F (&L)[kM], const F (&gs)[NSAMP],
+                     F g_rate, const F (&u_mp)[kK], F u_bm, F u_bs, const ModelConst& mc,
+                     const GlobalTables<F>& gt, int c, bool ontarget, bool first_frame, UnitGrads<F>& out) {
+    using R = Real<F>;
+    const ChannelTables<F>& ct = gt.ch[c];
+    const F half = F(mc.P + 1) / F(2);
 #pragma unroll
-    for (int i = 0; i < NLOCAL; ++i) out.g[i] = A(0);
+    for (int i = 0; i < NLOCAL; ++i) out.g[i] = F(0);
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) out.acc[i] = A(0);
+    for (int i = 0; i < NACC; ++i) out.acc[i] = F(0);
+    auto R_ = [&](int s, int j) -> F { return rec[s * NSO + j]; };
 
-    // q(m_k), log q(m_k)
-    A q1[kK], lq1[kK], lq0[kK];
+    F q1[kK], q0[kK], lq1[kK], lq0[kK], dq1[kK];
 #pragma unroll
     for (int k = 0; k < kK; ++k) {
-        q1[k] = R::min(R::max(up.p[LP_M_PROBS + k].v, A(mc.eps)), A(1) - A(mc.eps));
-        lq1[k] = R::log(q1[k]);
-        lq0[k] = R::log1p(-q1[k]);
+        const SpotPresence<F> sp(u_mp[k], mc);
+        q1[k] = sp.q1; q0[k] = sp.q0; lq1[k] = sp.lq1; lq0[k] = sp.lq0; dq1[k] = sp.dq1;
     }
 
-    // ---- background: model Gamma((bm/bs)^2, bm/bs^2), guide Gamma(b_loc b_beta, b_beta)  :233-239, 408-415
-    const A bm = up.p[LP_BM].v, bs = up.p[LP_BS].v;
-    const A b = sample[S_B];
-    const A pc = (bm / bs) * (bm / bs), pr = bm / (bs * bs);
-    const GammaSite<A> pb(b, pc, pr);
-    const A qc = up.p[LP_B_LOC].v * up.p[LP_B_BETA].v, qr = up.p[LP_B_BETA].v;
-    const GammaSite<A> qb(b, qc, qr);
-    A elbo = pb.lp - qb.lp;
-    // total derivative w.r.t. the sample b, then through the reparameterisation
-    const A Gb = pb.d_v - qb.d_v + gs[S_B];
+    // ---- background ------------------------------------------------------------------------------------------
+    const F* ex = rec + NSAMP * NSO;
+    F elbo = ex[EX_LP] - R_(S_B, SO_LQ);
     {
-        const A variate = b * qr;
-        const A db_dconc = std_gamma_grad<A>(qc, variate) / qr;
-        const A db_drate = -b / qr;
-        const A g_conc = Gb * db_dconc - qb.d_conc;
-        const A g_rate_q = Gb * db_drate - qb.d_rate;
-        // conc = loc * beta, rate = beta
-        out.g[LP_B_LOC] = g_conc * up.p[LP_B_BETA].v * up.p[LP_B_LOC].d;
-        out.g[LP_B_BETA] = (g_conc * up.p[LP_B_LOC].v + g_rate_q) * up.p[LP_B_BETA].d;
-        // prior parameters: conc_p = (bm/bs)^2, rate_p = bm/bs^2
-        const A g_bm = pb.d_conc * (A(2) * bm / (bs * bs)) + pb.d_rate / (bs * bs);
-        const A g_bs = pb.d_conc * (-A(2) * bm * bm / (bs * bs * bs)) + pb.d_rate * (-A(2) * bm / (bs * bs * bs));
-        out.g[LP_BM] = g_bm * up.p[LP_BM].d;
-        out.g[LP_BS] = g_bs * up.p[LP_BS].d;
+        const F G = ex[EX_DP] - R_(S_B, SO_DQ) + gs[S_B];
+        out.g[LP_B_LOC] = G * R_(S_B, SO_A0) - R_(S_B, SO_B0);
+        out.g[LP_B_BETA] = G * R_(S_B, SO_A1) - R_(S_B, SO_B1);
+        out.g[LP_BM] = ex[EX_GBM];
+        out.g[LP_BS] = ex[EX_GBS];
     }
 
-    // ---- per-spot continuous sites ------------------------------------------------------------------
-    A spot_term[kK];           // log p - log q of (h, w, x, y)_k excluding the theta-dependent x,y prior
-    A lxy1[kK], dlxy1_dx[kK], dlxy1_dy[kK], dlxy1_dsize[kK];  // target-specific x,y prior and partials
-    const A lxy0 = -A(2) * R::log(A(2) * half);  // size 2 => Beta(1,1): uniform on the patch      :283-300
-    A Gh[kK], Gw[kK], Gx[kK], Gy[kK];            // running d/d sample
-    // guide sites kept for the chain rule
-    A h_dconc[kK], h_drate[kK], w_dc1[kK], w_dc0[kK], x_dc1[kK], x_dc0[kK], y_dc1[kK], y_dc0[kK];
+    // ---- per-spot terms that do not depend on (z, theta) ------------------------------------------------------
+    F spot_term[kK], lxy1[kK], dlxy1_dx[kK], dlxy1_dy[kK], dlxy1_dsize[kK];
+    const F cs1 = gt.size1 * F(0.5) - F(1);
+    const F hs = F(mc.height_std);
+    const F lp_w = -R::log(F(mc.width_max) - F(mc.width_min));   // AffineBeta(1.5, 2, ..) = uniform  :274-282
+    const F c_hn = -R::log(hs) + F(0.5) * R::log(F(2) / F(3.14159265358979323846));
 #pragma unroll
     for (int k = 0; k < kK; ++k) {
-        const A h = sample[S_H + k], w = sample[S_W + k], x = sample[S_X + k], y = sample[S_Y + k];
-        const A hs = A(mc.height_std);
-        // HalfNormal(h; height_std)                                                            :270-273
-        const A lp_h = -h * h / (A(2) * hs * hs) - R::log(hs) + A(0.5) * R::log(A(2) / A(3.14159265358979323846));
-        // AffineBeta(1.5, 2, wmin, wmax) is Beta(1,1): uniform                                  :274-282
-        const A lp_w = -R::log(A(mc.width_max) - A(mc.width_min));
-        const GammaSite<A> qh(h, up.p[LP_H_LOC + k].v * up.p[LP_H_BETA + k].v, up.p[LP_H_BETA + k].v);
-        const AffBeta<A> dw(up.p[LP_W_MEAN + k].v, up.p[LP_W_SIZE + k].v, A(mc.width_min), A(mc.width_max));
-        const AffBeta<A> dx(up.p[LP_X_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-        const AffBeta<A> dy(up.p[LP_Y_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-        const BetaSite<A> qw(w, dw), qx(x, dx), qy(y, dy);
-        spot_term[k] = lp_h + lp_w - qh.lp - qw.lp - qx.lp - qy.lp;
-        // d spot_term / d sample (weighted by q(m_k = 1) below)
-        Gh[k] = -h / (hs * hs) - qh.d_v;
-        Gw[k] = -qw.d_v;
-        Gx[k] = -qx.d_v;
-        Gy[k] = -qy.d_v;
-        h_dconc[k] = qh.d_conc; h_drate[k] = qh.d_rate;
-        w_dc1[k] = qw.d_c1; w_dc0[k] = qw.d_c0;
-        x_dc1[k] = qx.d_c1; x_dc0[k] = qx.d_c0;
-        y_dc1[k] = qy.d_c1; y_dc0[k] = qy.d_c0;
-        // target-specific prior AffineBeta(0, size1, -half, half) on x and y                   :283-300
-        const A cs = gt.size1 / A(2);
-        const A Lx = R::log(qx.x01) + R::log(A(1) - qx.x01);
-        const A Ly = R::log(qy.x01) + R::log(A(1) - qy.x01);
-        lxy1[k] = (cs - A(1)) * (Lx + Ly) + A(2) * gt.lnorm1 + lxy0;
-        dlxy1_dx[k] = (cs - A(1)) * (A(1) / qx.x01 - A(1) / (A(1) - qx.x01)) / (A(2) * half);
-        dlxy1_dy[k] = (cs - A(1)) * (A(1) / qy.x01 - A(1) / (A(1) - qy.x01)) / (A(2) * half);
-        dlxy1_dsize[k] = A(0.5) * (Lx + Ly) + A(2) * gt.dlnorm1;
+        const F h = sample[S_H + k], x = sample[S_X + k], y = sample[S_Y + k];
+        const F lp_h = -h * h / (F(2) * hs * hs) + c_hn;          // HalfNormal(height_std)           :270-273
+        spot_term[k] = lp_h + lp_w - R_(S_H + k, SO_LQ) - R_(S_W + k, SO_LQ) - R_(S_X + k, SO_LQ) - R_(S_Y + k, SO_LQ);
+        // target-specific prior AffineBeta(0, size1, -half, half) on x and y                 :283-300
+        const F tx = x / half, ty = y / half;
+        const F ox = F(1) - tx * tx, oy = F(1) - ty * ty;
+        const F lsum = R::log1p(-tx * tx) + R::log1p(-ty * ty);
+        lxy1[k] = cs1 * lsum + gt.cxy1;
+        dlxy1_dx[k] = cs1 * (-F(2) * tx / ox) / half;
+        dlxy1_dy[k] = cs1 * (-F(2) * ty / oy) / half;
+        dlxy1_dsize[k] = F(0.5) * lsum + gt.dcxy1;
     }
 
-    // ---- enumerated part: T(m) = logsumexp over (z, theta), weighted by q(m)   ----
-    A sum_qC = A(0);
-    A gmp[kK];  // d / d (clamped m_probs_k)
+    // ---- enumerated part: T(m) = logsumexp over (z, theta), weighted by q(m)   ---------------
+    F sum_qC = F(0);
+    F gmp[kK], wk_x[kK];
 #pragma unroll
-    for (int k = 0; k < kK; ++k) gmp[k] = A(0);
-    A wk_x[kK], wk_s[kK];  // sum_m q(m) m_k R_k(m): weight of the target-specific prior derivative
-#pragma unroll
-    for (int k = 0; k < kK; ++k) wk_x[k] = wk_s[k] = A(0);
+    for (int k = 0; k < kK; ++k) gmp[k] = wk_x[k] = F(0);
     const int ot = ontarget ? 1 : 0;
 #pragma unroll
     for (int m = 0; m < kM; ++m) {
-        A lj[kZ][kTheta];
-        A mx = -R::inf();
+        F lj[kZ][kTheta];
+        F mx = -R::inf();
 #pragma unroll
         for (int z = 0; z < kZ; ++z)
 #pragma unroll
             for (int th = 0; th < kTheta; ++th) {
-                A v = ct.logpz[ot][z] + ct.logptheta[z][th];
+                F v = ct.logpz[ot][z] + ct.logptheta[z][th];
 #pragma unroll
                 for (int k = 0; k < kK; ++k) {
                     const int mk = (m >> k) & 1;
                     v += ct.logpm[th][k][mk];
-                    if (mk) v += (th == k + 1) ? lxy1[k] : lxy0;
+                    if (mk) v += (th == k + 1) ? lxy1[k] : gt.lxy0;
                 }
                 lj[z][th] = v;
                 mx = R::max(mx, v);
             }
-        A se = A(0);
+        F se = F(0);
 #pragma unroll
         for (int z = 0; z < kZ; ++z)
 #pragma unroll
@@ -343,30 +370,30 @@ TQ_HD void local_post(const UnitParams<A>& up, const ModelConst& mc, const Globa
                 lj[z][th] = R::exp(lj[z][th] - mx);
                 se += lj[z][th];
             }
-        const A T = mx + R::log(se);
-        A q = A(1), lq = A(0), Cm = T + L[m];
+        const F T = mx + R::log(se);
+        F q = F(1), lq = F(0), Cm = T + L[m];
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
             const int mk = (m >> k) & 1;
-            q *= mk ? q1[k] : (A(1) - q1[k]);
+            q *= mk ? q1[k] : q0[k];
             lq += mk ? lq1[k] : lq0[k];
             if (mk) Cm += spot_term[k];
         }
         Cm -= lq;
         sum_qC += q * Cm;
-        // d / d m_probs_k: q(m) * dlog q(m_k)/dp * (C(m) - 1)
+        // d / d u_mprobs_k: q(m) (m_k - q1_k) (C(m) - 1)   [= q(m) dlog q(m_k)/dp * dp/du * (C - 1)]
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
             const int mk = (m >> k) & 1;
-            gmp[k] += q * (mk ? A(1) / q1[k] : -A(1) / (A(1) - q1[k])) * (Cm - A(1));
+            gmp[k] += q * (mk ? q0[k] : -q1[k]) * (Cm - F(1));
         }
         // posterior responsibilities r(z, theta | m) drive the table gradients
-        const A qi = q / se;
+        const F qi = q / se;
 #pragma unroll
         for (int z = 0; z < kZ; ++z)
 #pragma unroll
             for (int th = 0; th < kTheta; ++th) {
-                const A r = qi * lj[z][th];
+                const F r = qi * lj[z][th];
                 if (ontarget) out.acc[ACC_LOGPZ + z] += r;
 #pragma unroll
                 for (int k = 0; k < kK; ++k) {
@@ -382,80 +409,40 @@ TQ_HD void local_post(const UnitParams<A>& up, const ModelConst& mc, const Globa
 #pragma unroll
     for (int k = 0; k < kK; ++k) out.acc[ACC_SIZE1] += wk_x[k] * dlxy1_dsize[k];
 
-    // ---- chain rule for the spot sites ---------------------------------------------------------------
+    // ---- parameter gradients through the site maps ------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < kK; ++k) {
-        // m_probs: clamp (identity inside) -> sigmoid
-        const A p = up.p[LP_M_PROBS + k].v;
-        const bool inside = (p >= A(mc.eps)) && (p <= A(1) - A(mc.eps));
-        out.g[LP_M_PROBS + k] = inside ? gmp[k] * up.p[LP_M_PROBS + k].d : A(0);
-
-        const A qk = q1[k];  // sum_m q(m) m_k
-        // height
-        {
-            const A h = sample[S_H + k];
-            const A conc = up.p[LP_H_LOC + k].v * up.p[LP_H_BETA + k].v, rate = up.p[LP_H_BETA + k].v;
-            const A G = qk * Gh[k] + gs[S_H + k];
-            const A dv_dconc = std_gamma_grad<A>(conc, h * rate) / rate;
-            const A g_conc = G * dv_dconc - qk * h_dconc[k];
-            const A g_rt = G * (-h / rate) - qk * h_drate[k];
-            out.g[LP_H_LOC + k] = g_conc * rate * up.p[LP_H_LOC + k].d;
-            out.g[LP_H_BETA + k] = (g_conc * up.p[LP_H_LOC + k].v + g_rt) * up.p[LP_H_BETA + k].d;
-        }
-        // width / x / y share the AffineBeta chain
-        A g_size = A(0);
-        auto beta_chain = [&](A G, A v, const AffBeta<A>& d, A dq_c1, A dq_c0, A mean, A size, A& g_mean, A& g_sz) {
-            const A x01 = (v - d.low) / d.scale;
-            const A tot = d.c1 + d.c0;
-            const A dv_dc1 = d.scale * (A(1) - x01) * beta_grad<A>(x01, d.c1, tot);
-            const A dv_dc0 = -d.scale * x01 * beta_grad<A>(A(1) - x01, d.c0, tot);
-            const A g_c1 = G * dv_dc1 - qk * dq_c1;
-            const A g_c0 = G * dv_dc0 - qk * dq_c0;
-            g_mean = (g_c1 - g_c0) * size / d.scale;
-            g_sz = g_c1 * (mean - d.low) / d.scale + g_c0 * (d.low + d.scale - mean) / d.scale;
-        };
-        {
-            const AffBeta<A> dw(up.p[LP_W_MEAN + k].v, up.p[LP_W_SIZE + k].v, A(mc.width_min), A(mc.width_max));
-            A gm, gsz;
-            beta_chain(qk * Gw[k] + gs[S_W + k], sample[S_W + k], dw, w_dc1[k], w_dc0[k], up.p[LP_W_MEAN + k].v,
-                       up.p[LP_W_SIZE + k].v, gm, gsz);
-            out.g[LP_W_MEAN + k] = gm * up.p[LP_W_MEAN + k].d;
-            out.g[LP_W_SIZE + k] = gsz * up.p[LP_W_SIZE + k].d;
-        }
-        {
-            const AffBeta<A> dx(up.p[LP_X_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-            A gm, gsz;
-            beta_chain(qk * Gx[k] + gs[S_X + k] + wk_x[k] * dlxy1_dx[k], sample[S_X + k], dx, x_dc1[k], x_dc0[k],
-                       up.p[LP_X_MEAN + k].v, up.p[LP_SIZE + k].v, gm, gsz);
-            out.g[LP_X_MEAN + k] = gm * up.p[LP_X_MEAN + k].d;
-            g_size += gsz;
-        }
-        {
-            const AffBeta<A> dy(up.p[LP_Y_MEAN + k].v, up.p[LP_SIZE + k].v, -half, half);
-            A gm, gsz;
-            beta_chain(qk * Gy[k] + gs[S_Y + k] + wk_x[k] * dlxy1_dy[k], sample[S_Y + k], dy, y_dc1[k], y_dc0[k],
-                       up.p[LP_Y_MEAN + k].v, up.p[LP_SIZE + k].v, gm, gsz);
-            out.g[LP_Y_MEAN + k] = gm * up.p[LP_Y_MEAN + k].d;
-            g_size += gsz;
-        }
-        out.g[LP_SIZE + k] = g_size * up.p[LP_SIZE + k].d;
+        out.g[LP_M_PROBS + k] = dq1[k] > F(0) ? gmp[k] : F(0);
+        const F qk = q1[k];  // sum_m q(m) m_k
+        const F Gh = qk * (-sample[S_H + k] / (hs * hs) - R_(S_H + k, SO_DQ)) + gs[S_H + k];
+        const F Gw = -qk * R_(S_W + k, SO_DQ) + gs[S_W + k];
+        const F Gx = -qk * R_(S_X + k, SO_DQ) + gs[S_X + k] + wk_x[k] * dlxy1_dx[k];
+        const F Gy = -qk * R_(S_Y + k, SO_DQ) + gs[S_Y + k] + wk_x[k] * dlxy1_dy[k];
+        out.g[LP_H_LOC + k] = Gh * R_(S_H + k, SO_A0) - qk * R_(S_H + k, SO_B0);
+        out.g[LP_H_BETA + k] = Gh * R_(S_H + k, SO_A1) - qk * R_(S_H + k, SO_B1);
+        out.g[LP_W_MEAN + k] = Gw * R_(S_W + k, SO_A0) - qk * R_(S_W + k, SO_B0);
+        out.g[LP_W_SIZE + k] = Gw * R_(S_W + k, SO_A1) - qk * R_(S_W + k, SO_B1);
+        out.g[LP_X_MEAN + k] = Gx * R_(S_X + k, SO_A0) - qk * R_(S_X + k, SO_B0);
+        out.g[LP_Y_MEAN + k] = Gy * R_(S_Y + k, SO_A0) - qk * R_(S_Y + k, SO_B0);
+        out.g[LP_SIZE + k] = (Gx * R_(S_X + k, SO_A1) - qk * R_(S_X + k, SO_B1))
+                           + (Gy * R_(S_Y + k, SO_A1) - qk * R_(S_Y + k, SO_B1));
     }
-    (void)wk_s;
 
-    // ---- AOI-level prior terms, carried by the first minibatch frame of each (AOI, channel) ---------
+    // ---- AOI-level prior terms, carried by the first minibatch frame of each (AOI, channel) ---------------------
     // HalfNormal(bm; bg_mean_std) + HalfNormal(bs; bg_std_std), Delta guide                    :221-227, 397-404
     if (first_frame) {
-        const A s1 = A(mc.bg_mean_std), s2 = A(mc.bg_std_std);
-        const A c0 = A(0.5) * R::log(A(2) / A(3.14159265358979323846));
-        out.acc[ACC_ELBO_AOI] = (-bm * bm / (A(2) * s1 * s1) - R::log(s1) + c0) + (-bs * bs / (A(2) * s2 * s2) - R::log(s2) + c0);
+        const F bm = R::exp(u_bm), bs = R::exp(u_bs);
+        const F s1 = F(mc.bg_mean_std), s2 = F(mc.bg_std_std);
+        const F c0 = F(0.5) * R::log(F(2) / F(3.14159265358979323846));
+        out.acc[ACC_ELBO_AOI] = (-bm * bm / (F(2) * s1 * s1) - R::log(s1) + c0) + (-bs * bs / (F(2) * s2 * s2) - R::log(s2) + c0);
     }
 }
 
 // gradient of the AOI-level prior terms w.r.t. the unconstrained (bm, bs); scaled by s_N (not s_N s_F)
-template <typename A> TQ_HD void aoi_prior_grad(const UnitParams<A>& up, const ModelConst& mc, A& g_bm, A& g_bs) {
-    const A s1 = A(mc.bg_mean_std), s2 = A(mc.bg_std_std);
-    g_bm = -up.p[LP_BM].v / (s1 * s1) * up.p[LP_BM].d;
-    g_bs = -up.p[LP_BS].v / (s2 * s2) * up.p[LP_BS].d;
+TQ_HD void aoi_prior_grad(double u_bm, double u_bs, const ModelConst& mc, double& g_bm, double& g_bs) {
+    const double bm = exp(u_bm), bs = exp(u_bs);
+    g_bm = -bm / (mc.bg_mean_std * mc.bg_mean_std) * bm;
+    g_bs = -bs / (mc.bg_std_std * mc.bg_std_std) * bs;
 }
 
 }  // namespace tq

@@ -39,16 +39,6 @@ struct StepState {
 
 constexpr int kLocalBlock = 128;
 
-template <typename T>
-__device__ __forceinline__ void load_unit_params(const T* __restrict__ lparams, const LocalOffsets& lo,
-                                                 int64_t n, int64_t f, int c, const ModelConst& mc,
-                                                 UnitParams<Acc>& up) {
-    Acc u[NLOCAL];
-#pragma unroll
-    for (int i = 0; i < NLOCAL; ++i) u[i] = (Acc)lparams[lo.index(i, n, f, c)];
-    transform_unit<Acc>(u, mc, up);
-}
-
 // ---- globals: sample + tables ------------------------------------------------------------------------
 template <typename T>
 __global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
@@ -73,7 +63,6 @@ __global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, Mode
     gain_out[0] = (T)gt.gain;
 }
 
-// ---- local_pre: thread per unit -------------------------------------------------------------------------
 template <typename T> struct LocalArgs {
     tq_patch_view v;
     LocalOffsets lo;
@@ -84,13 +73,14 @@ template <typename T> struct LocalArgs {
     int64_t aoi_offset;          // global index of this rank's AOI 0 (RNG stream identity)
     unsigned long long seed;
     const StepState* state;
-    // pre
+    // sites
     const T* noise_in;           // (NSAMP, U) base variates or NULL -> Philox
     T* samples;                  // (NSAMP, U)
     T* qm;                       // (kM, U)
+    T* rec;                      // (NREC, U) site records
     // post
     const T* L;                  // (kM, U)
-    const T* gs[NSAMP];          // d/d sample from the likelihood kernel, in S_* order
+    const T* gs;                 // (NSAMP, U) d/d sample from the likelihood kernel, S_* order
     const T* g_rate;             // (U,)
     double sN, sF;
     T* lgrads;                   // flat, LocalOffsets layout
@@ -98,36 +88,57 @@ template <typename T> struct LocalArgs {
     double* block_partial;       // (gridDim.x, C, NACC)
 };
 
+// ---- sites: one thread per (site, unit), site-major so that a warp evaluates one family ------------------
 template <typename T>
-__global__ void __launch_bounds__(kLocalBlock) local_pre_kernel(const LocalArgs<T> a) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= a.U) return;
+__global__ void __launch_bounds__(kLocalBlock) site_kernel(const LocalArgs<T> a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.U * NSAMP) return;
+    const int s = (int)(t / a.U);
+    const int64_t u = t - (int64_t)s * a.U;
     const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
     const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
-    UnitParams<Acc> up;
-    load_unit_params(a.lparams, a.lo, ui.aoi, f, ui.c, a.mc, up);
-    Acc variate[NSAMP], sample[NSAMP], qm[kM];
+    const double u0 = (double)a.lparams[a.lo.index(site_param0(s), ui.aoi, f, ui.c)];
+    const double u1 = (double)a.lparams[a.lo.index(site_param1(s), ui.aoi, f, ui.c)];
+    double ubm = 0.0, ubs = 0.0;
+    if (s == S_B) {
+        ubm = (double)a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)];
+        ubs = (double)a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
+    }
     const bool use_rng = a.noise_in == nullptr;
     const unsigned long long gid = (((unsigned long long)(a.aoi_offset + ui.aoi)) * a.v.F + f) * a.v.C + ui.c;
-    Philox rng(a.seed, a.state->step, (gid + 1ull) << 12);
-    if (!use_rng) {
+    Philox rng(a.seed, a.state->step, ((gid + 1ull) << 12) + ((unsigned long long)s << 8));
+    double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u];
+    double rec[NSO], extra[NEX];
+    const double v = site_eval(s, u0, u1, ubm, ubs, a.mc, use_rng, &rng, variate, rec, extra);
+    a.samples[(int64_t)s * a.U + u] = (T)v;
 #pragma unroll
-        for (int i = 0; i < NSAMP; ++i) variate[i] = (Acc)a.noise_in[i * a.U + u];
+    for (int j = 0; j < NSO; ++j) a.rec[((int64_t)s * NSO + j) * a.U + u] = (T)rec[j];
+    if (s == S_B) {
+#pragma unroll
+        for (int j = 0; j < NEX; ++j) a.rec[((int64_t)NSAMP * NSO + j) * a.U + u] = (T)extra[j];
+        // weights of the likelihood kernel: q(m) from the unconstrained m_probs
+        T q1[kK], q0[kK], qm[kM];
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            const SpotPresence<T> sp((T)a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, f, ui.c)], a.mc);
+            q1[k] = sp.q1; q0[k] = sp.q0;
+        }
+        presence_weights<T>(q1, q0, qm);
+#pragma unroll
+        for (int m = 0; m < kM; ++m) a.qm[m * a.U + u] = qm[m];
     }
-    local_pre<Acc>(up, a.mc, use_rng, &rng, variate, sample, qm);
-#pragma unroll
-    for (int i = 0; i < NSAMP; ++i) a.samples[i * a.U + u] = (T)sample[i];
-#pragma unroll
-    for (int m = 0; m < kM; ++m) a.qm[m * a.U + u] = (T)qm[m];
 }
 
-// ---- local_post: thread per unit + deterministic block reduction of the channel accumulators -------------
+// ---- post: thread per unit (cheap) + deterministic block reduction of the channel accumulators -----------
 template <typename T>
 __global__ void __launch_bounds__(kLocalBlock) local_post_kernel(const LocalArgs<T> a) {
     __shared__ double red[kLocalBlock / 32][NACC];
+    __shared__ GlobalTables<T> gt;
+    if (threadIdx.x == 0) gt.convert_from(*a.tables);
+    __syncthreads();
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = u < a.U;
-    UnitGrads<Acc> ug;
+    UnitGrads<T> ug;
     int my_c = -1;
     double mu = 0.0;
     if (live) {
@@ -135,30 +146,32 @@ __global__ void __launch_bounds__(kLocalBlock) local_post_kernel(const LocalArgs
         const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
         my_c = ui.c;
         mu = a.v.mask[ui.aoi] ? 1.0 : 0.0;
-        UnitParams<Acc> up;
-        load_unit_params(a.lparams, a.lo, ui.aoi, f, ui.c, a.mc, up);
-        Acc sample[NSAMP], gs[NSAMP], L[kM];
+        T rec[NREC], sample[NSAMP], gs[NSAMP], L[kM], u_mp[kK];
+#pragma unroll
+        for (int i = 0; i < NREC; ++i) rec[i] = a.rec[(int64_t)i * a.U + u];
 #pragma unroll
         for (int i = 0; i < NSAMP; ++i) {
-            sample[i] = (Acc)a.samples[i * a.U + u];
-            gs[i] = (Acc)a.gs[i][u];
+            sample[i] = a.samples[(int64_t)i * a.U + u];
+            gs[i] = a.gs[(int64_t)i * a.U + u];
         }
 #pragma unroll
-        for (int m = 0; m < kM; ++m) L[m] = (Acc)a.L[m * a.U + u];
-        GlobalTables<Acc> gt = *a.tables;
-        local_post<Acc>(up, a.mc, gt, ui.c, a.v.is_ontarget[ui.aoi] != 0, ui.fi == 0, sample, L, gs,
-                        (Acc)a.g_rate[u], ug);
-        const double s = -a.sN * a.sF * mu;  // loss = -ELBO
+        for (int m = 0; m < kM; ++m) L[m] = a.L[m * a.U + u];
 #pragma unroll
-        for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, ui.aoi, f, ui.c)] = (T)(s * ug.g[i]);
-        a.aoi_partial[u] = mu * ug.g[LP_BM];
-        a.aoi_partial[a.U + u] = mu * ug.g[LP_BS];
+        for (int k = 0; k < kK; ++k) u_mp[k] = a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, f, ui.c)];
+        const T u_bm = a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)], u_bs = a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
+        unit_post<T>(rec, sample, L, gs, a.g_rate[u], u_mp, u_bm, u_bs, a.mc, gt, ui.c,
+                     a.v.is_ontarget[ui.aoi] != 0, ui.fi == 0, ug);
+        const T s = (T)(-a.sN * a.sF * mu);  // loss = -ELBO
+#pragma unroll
+        for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, ui.aoi, f, ui.c)] = s * ug.g[i];
+        a.aoi_partial[u] = mu * (double)ug.g[LP_BM];
+        a.aoi_partial[a.U + u] = mu * (double)ug.g[LP_BS];
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = 0; c < a.v.C; ++c) {
 #pragma unroll
         for (int i = 0; i < NACC; ++i) {
-            double v = (live && my_c == c) ? mu * ug.acc[i] : 0.0;
+            double v = (live && my_c == c) ? mu * (double)ug.acc[i] : 0.0;
             v = warp_sum(v);
             if (lane == 0) red[warp][i] = v;
         }
@@ -281,6 +294,7 @@ extern "C" int tq_sizeof_tables(void) { return (int)sizeof(GlobalTables<double>)
 extern "C" int tq_sizeof_gstate(void) { return (int)(2 * kMaxGlobalNoise * sizeof(double)); }
 extern "C" int tq_sizeof_model_const(void) { return (int)sizeof(ModelConst); }
 extern "C" int tq_local_post_blocks(int64_t U) { return local_blocks(U); }
+extern "C" int tq_site_record_rows(void) { return NREC; }
 
 extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
                                         uint64_t seed, const void* state, double* gstate, void* tables,
@@ -301,42 +315,43 @@ extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, c
 }
 
 template <typename T>
-static int run_local_pre(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
-                         int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in, void* samples,
-                         void* qm, cudaStream_t st) {
+static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams,
+                     int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in, void* samples,
+                     void* qm, void* rec, cudaStream_t st) {
     LocalArgs<T> a{};
-    fill_common(a, view, Nt, mc, lparams, tables, aoi_offset, seed, state);
+    fill_common(a, view, Nt, mc, lparams, nullptr, aoi_offset, seed, state);
     a.noise_in = (const T*)noise_in;
     a.samples = (T*)samples;
     a.qm = (T*)qm;
+    a.rec = (T*)rec;
     if (a.U == 0) return TQ_OK;
-    local_pre_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a);
-    TQ_LAUNCH_CHECK("local_pre_kernel launch");
+    site_kernel<T><<<local_blocks(a.U * NSAMP), kLocalBlock, 0, st>>>(a);
+    TQ_LAUNCH_CHECK("site_kernel launch");
     return TQ_OK;
 }
 
-extern "C" int tq_cosmos_local_pre(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
-                                   const void* tables, int64_t aoi_offset, uint64_t seed, const void* state,
-                                   const void* noise_in, void* samples, void* qm, void* stream) {
-    TQ_CHECK_ARG(view && mc && lparams && tables && state && samples && qm, "NULL pointer");
+extern "C" int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                               int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
+                               void* samples, void* qm, void* rec, void* stream) {
+    TQ_CHECK_ARG(view && mc && lparams && state && samples && qm && rec, "NULL pointer");
     TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_local_pre<float>(view, Nt, (const ModelConst*)mc, lparams, tables, aoi_offset, seed, state, noise_in, samples, qm, st);
-    if (dtype == TQ_F64) return run_local_pre<double>(view, Nt, (const ModelConst*)mc, lparams, tables, aoi_offset, seed, state, noise_in, samples, qm, st);
+    if (dtype == TQ_F32) return run_sites<float>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, st);
+    if (dtype == TQ_F64) return run_sites<double>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }
 
 template <typename T>
 static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
-                          const void* samples, const void* L, const void* gs, const void* g_rate, double sN, double sF,
+                          const void* samples, const void* rec, const void* L, const void* gs, const void* g_rate, double sN, double sF,
                           void* lgrads, double* aoi_partial, double* block_partial, double* acc, cudaStream_t st) {
     LocalArgs<T> a{};
     fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
     a.samples = (T*)samples;
+    a.rec = (T*)rec;
     a.L = (const T*)L;
-    // gs: (NSAMP, U) record in S_* order: background, height_k, width_k, x_k, y_k
-    for (int i = 0; i < NSAMP; ++i) a.gs[i] = (const T*)gs + (int64_t)i * a.U;
+    a.gs = (const T*)gs;  // (NSAMP, U) in S_* order: background, height_k, width_k, x_k, y_k
     a.g_rate = (const T*)g_rate;
     a.sN = sN; a.sF = sF;
     a.lgrads = (T*)lgrads;
@@ -357,16 +372,16 @@ static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelCons
 }
 
 extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
-                                    const void* tables, const void* samples, const void* L, const void* gs,
+                                    const void* tables, const void* samples, const void* rec, const void* L, const void* gs,
                                     const void* g_rate, double sN, double sF, void* lgrads, double* aoi_partial,
                                     double* block_partial, double* acc, void* stream) {
-    TQ_CHECK_ARG(view && mc && lparams && tables && samples && L && gs && g_rate, "NULL input pointer");
+    TQ_CHECK_ARG(view && mc && lparams && tables && samples && rec && L && gs && g_rate, "NULL input pointer");
     TQ_CHECK_ARG(lgrads && aoi_partial && block_partial && acc, "NULL output pointer");
     TQ_CHECK_ARG(view->mask && view->is_ontarget, "view needs mask and is_ontarget");
     TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_local_post<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
-    if (dtype == TQ_F64) return run_local_post<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
+    if (dtype == TQ_F32) return run_local_post<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
+    if (dtype == TQ_F64) return run_local_post<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }

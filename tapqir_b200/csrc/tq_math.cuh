@@ -25,10 +25,32 @@ constexpr int kZ = 2;          // z states (S = 1)
 #ifdef __CUDACC__
 #define TQ_DEV __device__ __forceinline__
 #define TQ_HD __host__ __device__ __forceinline__
+#define TQ_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define TQ_DEV inline
 #define TQ_HD inline
+#define TQ_HD_NOINLINE inline
 #endif
+
+// log Gamma(x) for x > 0 in double: recurrence up to x >= 10 then the Stirling series (relative
+// error ~1e-15); several times cheaper on the device than the general-purpose ::lgamma.
+TQ_HD double lgamma_pos(double x) {
+    double prod = 1.0;
+    while (x < 10.0) {
+        prod *= x;
+        x += 1.0;
+    }
+    const double ix = 1.0 / x, z = ix * ix;
+    double r = 6.41025641025641025641e-3;                    // 1/156
+    r = 1.91752691752691752692e-3 - z * r;                   // 691/360360
+    r = 8.41750841750841750842e-4 - z * r;                   // 1/1188
+    r = 5.95238095238095238095e-4 - z * r;                   // 1/1680
+    r = 7.93650793650793650794e-4 - z * r;                   // 1/1260
+    r = 2.77777777777777777778e-3 - z * r;                   // 1/360
+    r = 8.33333333333333333333e-2 - z * r;                   // 1/12
+    const double lg = (x - 0.5) * ::log(x) - x + 0.91893853320467274178 + ix * r;
+    return prod == 1.0 ? lg : lg - ::log(prod);
+}
 
 template <typename T> struct Real;
 template <> struct Real<float> {
@@ -50,7 +72,7 @@ template <> struct Real<double> {
     static TQ_HD double log(double x) { return ::log(x); }
     static TQ_HD double exp(double x) { return ::exp(x); }
     static TQ_HD double log1p(double x) { return ::log1p(x); }
-    static TQ_HD double lgamma(double x) { return ::lgamma(x); }
+    static TQ_HD double lgamma(double x) { return lgamma_pos(x); }
     static TQ_HD double sqrt(double x) { return ::sqrt(x); }
     static TQ_HD double pow(double x, double y) { return ::pow(x, y); }
     static TQ_HD double floor(double x) { return ::floor(x); }
@@ -74,7 +96,7 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 // ---- digamma --------------------------------------------------------------------------------
 // psi(x) for x > 0: recurrence up to x >= 10, then the asymptotic series (same construction as
 // ATen's digamma_one, Cephes-derived, so the reparameterisation gradients below agree with torch).
-template <typename T> TQ_HD T digamma(T x) {
+template <typename T> TQ_HD_NOINLINE T digamma(T x) {
     if (x == T(0)) return Real<T>::inf();
     T acc = T(0);
     while (x < T(10)) {
@@ -95,7 +117,7 @@ template <typename T> TQ_HD T digamma(T x) {
 }
 
 // ---- reparameterisation gradient of a standard Gamma(alpha) draw x: d x / d alpha ------------
-template <typename T> TQ_HD T std_gamma_grad(T alpha, T x) {
+template <typename T> TQ_HD_NOINLINE T std_gamma_grad(T alpha, T x) {
     using R = Real<T>;
     if (x < T(0.8)) {
         // Taylor series of the lower incomplete gamma function around x = 0
@@ -126,7 +148,8 @@ template <typename T> TQ_HD T std_gamma_grad(T alpha, T x) {
         }
         const T den = R::sqrt(T(8) * alpha);
         const T t2 = den / (alpha - x);
-        const T t3 = R::pow(x - alpha - alpha * R::log(x / alpha), T(-1.5));
+        const T t3b = x - alpha - alpha * R::log(x / alpha);
+        const T t3 = T(1) / (t3b * R::sqrt(t3b));   // t3b^(-3/2)
         const T t23 = (x < alpha) ? t2 - t3 : t2 + t3;
         const T t1 = R::log(x / alpha) * t23 - R::sqrt(T(2) / alpha) * (alpha + x) / ((alpha - x) * (alpha - x));
         const T stirling = T(1) + T(1) / (T(12) * alpha) * (T(1) + T(1) / (T(24) * alpha));
@@ -151,7 +174,7 @@ template <typename T> TQ_HD T std_gamma_grad(T alpha, T x) {
 // ---- scaled reparameterisation gradient of a Beta(alpha, total-alpha) draw x wrt alpha --------
 //   -(d/dalpha cdf) / pdf / (1 - x); total is passed so that the 2-Dirichlet form
 //   dx/dc1 = (1-x) g(x, c1, tot),  dx/dc0 = -x g(1-x, c0, tot)   follows (torch dirichlet.py backward).
-template <typename T> TQ_HD T beta_grad_alpha_small(T x, T alpha, T beta) {
+template <typename T> TQ_HD_NOINLINE T beta_grad_alpha_small(T x, T alpha, T beta) {
     using R = Real<T>;
     const T factor = digamma(alpha) - digamma(alpha + beta) - R::log(x);
     T numer = T(1);
@@ -166,7 +189,7 @@ template <typename T> TQ_HD T beta_grad_alpha_small(T x, T alpha, T beta) {
     return (res != res) ? T(0) : res;
 }
 
-template <typename T> TQ_HD T beta_grad_beta_small(T x, T alpha, T beta) {
+template <typename T> TQ_HD_NOINLINE T beta_grad_beta_small(T x, T alpha, T beta) {
     using R = Real<T>;
     const T factor = digamma(alpha + beta) - digamma(beta);
     T numer = T(1), betas = T(1), dbetas = T(0), series = factor / alpha;
@@ -181,7 +204,7 @@ template <typename T> TQ_HD T beta_grad_beta_small(T x, T alpha, T beta) {
     return (res != res) ? T(0) : res;
 }
 
-template <typename T> TQ_HD T beta_grad_alpha_mid(T x, T alpha, T beta) {
+template <typename T> TQ_HD_NOINLINE T beta_grad_alpha_mid(T x, T alpha, T beta) {
     using R = Real<T>;
     const T total = alpha + beta;
     const T mean = alpha / total;
@@ -203,16 +226,16 @@ template <typename T> TQ_HD T beta_grad_alpha_mid(T x, T alpha, T beta) {
                      / (T(1) + T(1) / (T(12) * total) + T(1) / (T(288) * total * total));
     const T t1n = T(2) * (alpha * alpha) * (x - T(1)) + alpha * beta * (x - T(1)) - x * (beta * beta);
     const T axbx = alpha * (x - T(1)) + beta * x;
-    const T t1d = R::sqrt(T(2) * alpha / beta) * R::pow(total, T(1.5)) * axbx * axbx;
+    const T t1d = R::sqrt(T(2) * alpha / beta) * (total * R::sqrt(total)) * axbx * axbx;
     const T t1 = t1n / t1d;
     const T t2 = T(0.5) * R::log(alpha / (total * x));
     const T t3 = R::sqrt(T(8) * alpha * beta / total) / (beta * x + alpha * (x - T(1)));
     const T t4b = beta * R::log(beta / (total * (T(1) - x))) + alpha * R::log(alpha / (total * x));
-    const T t4 = R::pow(t4b, T(-1.5));
+    const T t4 = T(1) / (t4b * R::sqrt(t4b));   // t4b^(-3/2)
     return stirling * prefactor * (t1 + t2 * (t3 + (x < mean ? t4 : -t4)));
 }
 
-template <typename T> TQ_HD T beta_grad(T x, T alpha, T total) {
+template <typename T> TQ_HD_NOINLINE T beta_grad(T x, T alpha, T total) {
     using R = Real<T>;
     const T beta = total - alpha;
     const T boundary = total * x * (T(1) - x);
@@ -256,6 +279,50 @@ template <typename T> TQ_HD T beta_grad(T x, T alpha, T total) {
         }
     const T approx = x * (digamma(total) - digamma(alpha)) / beta;
     return p / q * approx;
+}
+
+// Both reparameterisation gradients of a Beta(c1, c0) draw x at once:
+//   g1 = beta_grad(x, c1, c1 + c0),  g0 = beta_grad(1 - x, c0, c1 + c0)
+// In the "both concentrations large" regime (the usual one for the cosmos guide: sizes of 100-1000)
+// the two Rice expansions share their logarithms and square roots.
+template <typename T> TQ_HD_NOINLINE void beta_grad_pair(T x, T c1, T c0, T& g1, T& g0) {
+    using R = Real<T>;
+    const T total = c1 + c0;
+    const T boundary = total * x * (T(1) - x);
+    const bool mid = (c1 > T(6)) && (c0 > T(6)) && !(boundary < T(2.5)) ;
+    const T mean = c1 / total;
+    const T sd = R::sqrt(c1 * c0 / (total + T(1))) / total;
+    const bool patch = (mean - T(0.1) * sd <= x) && (x <= mean + T(0.1) * sd);
+    if (!mid || patch) {
+        g1 = beta_grad<T>(x, c1, total);
+        g0 = beta_grad<T>(T(1) - x, c0, total);
+        return;
+    }
+    const T y = T(1) - x;
+    const T sab = R::sqrt(c1 * c0 / total);                 // sqrt(alpha beta / total)
+    const T stirling = (T(1) + T(1) / (T(12) * c1) + T(1) / (T(288) * c1 * c1))
+                     * (T(1) + T(1) / (T(12) * c0) + T(1) / (T(288) * c0 * c0))
+                     / (T(1) + T(1) / (T(12) * total) + T(1) / (T(288) * total * total));
+    const T axbx = c0 * x - c1 * y;                        // alpha (x - 1) + beta x   (call 1); call 2 has the opposite sign
+    const T t15 = total * R::sqrt(total) * axbx * axbx;
+    const T rab = R::sqrt(c1 / c0);                         // sqrt(alpha / beta)
+    const T L1 = R::log(c1 / (total * x)), L0 = R::log(c0 / (total * y));
+    const T t4b = c0 * L0 + c1 * L1;
+    const T t4 = T(1) / (t4b * R::sqrt(t4b));
+    const T s8 = T(2.8284271247461900976) * sab;           // sqrt(8 alpha beta / total)
+    const T r2 = T(1.4142135623730950488);
+    // call 1: (x, alpha = c1, beta = c0)
+    {
+        const T t1 = (-T(2) * c1 * c1 * y - c1 * c0 * y - x * c0 * c0) / (r2 * rab * t15);
+        const T t3 = s8 / axbx;
+        g1 = stirling * (-x / (r2 * sab)) * (t1 + T(0.5) * L1 * (t3 + (x < mean ? t4 : -t4)));
+    }
+    // call 2: (1 - x, alpha = c0, beta = c1)
+    {
+        const T t1 = (-T(2) * c0 * c0 * x - c1 * c0 * x - y * c1 * c1) / (r2 / rab * t15);
+        const T t3 = -s8 / axbx;
+        g0 = stirling * (-y / (r2 * sab)) * (t1 + T(0.5) * L0 * (t3 + (y < c0 / total ? t4 : -t4)));
+    }
 }
 
 // ---- Philox4x32-10 counter RNG -----------------------------------------------------------------
@@ -306,7 +373,7 @@ struct Philox {
 };
 
 // Marsaglia & Tsang (2000) standard gamma sampler (doi:10.1145/358407.358414), alpha > 0.
-template <typename T> TQ_HD T sample_std_gamma(Philox& rng, T alpha) {
+template <typename T> TQ_HD_NOINLINE T sample_std_gamma(Philox& rng, T alpha) {
     using R = Real<T>;
     T scale = T(1);
     if (alpha < T(1)) {

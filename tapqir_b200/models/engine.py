@@ -4,7 +4,7 @@ cosmos SVI step through the C ABI (include/tapqir_b200.h).
 
 One step (what ``svi.step()`` does in models/model.py:212):
 
-    subsample -> globals_sample -> local_pre -> ksmogn_fwd_bwd -> local_post (+ reductions)
+    subsample -> globals_sample -> sites -> ksmogn_fwd_bwd -> local_post (+ reductions)
     -> [all-reduce of the (C, NACC) accumulators across ranks] -> globals_grad -> Adam (local, global)
 
 Everything runs on torch's current stream; no host synchronisation inside a step (the loss stays on
@@ -24,7 +24,7 @@ from tapqir_b200.models import layout as L
 class CosmosEngine:
     def __init__(self, store, Nt_local, F, C, P, priors, dtype=torch.float32, lr=0.005, betas=(0.9, 0.999),
                  adam_eps=1e-8, nbatch_size=None, fbatch_size=None, seed=0, ref_dtype=torch.float64,
-                 Nt_total=None, aoi_offset=0, rank=0, world_size=1, process_group=None):
+                 Nt_total=None, aoi_offset=0, rank=0, world_size=1, process_group=None, use_graph=True):
         self.lib = _lib.load()
         self.store = store
         self.device = store.pixels.device
@@ -54,11 +54,14 @@ class CosmosEngine:
         self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
+        self.use_graph = use_graph
+        self._graph, self._eager_default_steps = None, 0
         self.mcfg_arg = None  # NULL = built-in enumerated table -> fp32 production kernel; set to self.mcfg for the generic one
         self.set_batch(nbatch_size or self.Nt, fbatch_size or self.F)
 
     # ---- buffers that depend on the minibatch shape ---------------------------------------------------
     def set_batch(self, nbatch_size, fbatch_size):
+        self._graph, self._eager_default_steps = None, 0  # buffers below are re-allocated: drop any captured graph
         self.nb, self.fb = min(int(nbatch_size), self.Nt), min(int(fbatch_size), self.F)
         dev, dtype = self.device, self.dtype
         U = self.U = self.nb * self.fb * self.C
@@ -70,6 +73,7 @@ class CosmosEngine:
         e = lambda *s, dt=dtype: torch.empty(*s, dtype=dt, device=dev)
         self.samples, self.gs = e(L.NSAMP, U), e(L.NSAMP, U)
         self.qm, self.Lm, self.g_rate = e(4, U), e(4, U), e(U)
+        self.rec = e(self.lib.tq_site_record_rows(), U)   # per-site records (csrc/cosmos_local.cuh SO_*/EX_*)
         self.aoi_partial = e(2, U, dt=torch.float64)
         self.nblocks = self.lib.tq_local_post_blocks(U)
         self.block_partial = e(max(self.nblocks, 1) * self.C * L.NACC, dt=torch.float64)
@@ -102,6 +106,32 @@ class CosmosEngine:
     # ---- one step ------------------------------------------------------------------------------------------
     def step(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
         """
+        One SVI step.  The default call (device-drawn minibatch and variates, parameter update) is
+        captured into a CUDA graph the second time it runs and replayed from then on: every
+        step-varying quantity (iteration counter for Philox and Adam, minibatch indices) lives in
+        device memory, so the captured launches never change.  Any explicit argument (replay-mode
+        tests, kernel timing) takes the eager path :meth:`_enqueue`.
+        """
+        default = (ndx is None and fdx is None and local_noise is None and global_noise is None and update
+                   and time_likelihood is None)
+        if not (default and self.use_graph):
+            return self._enqueue(ndx, fdx, local_noise, global_noise, update, time_likelihood)
+        if self._graph is not None:
+            self._graph.replay()
+            return self.loss
+        self._eager_default_steps += 1
+        if self._eager_default_steps < 2:
+            return self._enqueue(None, None, None, None, True, None)  # first call: lazy CUDA/NCCL init outside capture
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._enqueue(None, None, None, None, True, None)
+        self._graph = graph
+        graph.replay()
+        return self.loss
+
+    def _enqueue(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
+        """
         Enqueue one SVI step.  ``ndx``/``fdx`` (int32 CUDA tensors of local AOI / frame indices) and
         the base variates (``local_noise`` (NSAMP, U) in ``dtype``; ``global_noise`` float64 in
         GlobalLayout noise order) put the step in *replay* mode for parity tests; by default indices
@@ -129,9 +159,9 @@ class CosmosEngine:
             _lib.check(lib.tq_cosmos_globals_sample(code, self.C, p(self.gparams), mc, p(global_noise), self.seed,
                                                     p(self.state), p(self.gstate), p(self.tables), p(self.gain), st),
                        "tq_cosmos_globals_sample")
-            _lib.check(lib.tq_cosmos_local_pre(code, view, self.Nt, mc, p(self.lparams), p(self.tables), self.aoi_offset,
-                                               self.seed, p(self.state), p(local_noise), p(self.samples), p(self.qm), st),
-                       "tq_cosmos_local_pre")
+            _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                           p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
+                       "tq_cosmos_sites")
             S, G, K = self.samples, self.gs, L.K
             if time_likelihood is not None:
                 time_likelihood[0].record()
@@ -142,7 +172,7 @@ class CosmosEngine:
             if time_likelihood is not None:
                 time_likelihood[1].record()
             _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
-                                                p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
+                                                p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
                                                 p(self.aoi_partial), p(self.block_partial), p(self.acc), st),
                        "tq_cosmos_local_post")
             if self.world_size > 1:

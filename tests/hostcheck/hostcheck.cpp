@@ -91,6 +91,8 @@ double hc_std_gamma_grad_f64(double alpha, double x) { return std_gamma_grad<dou
 float hc_std_gamma_grad_f32(float alpha, float x) { return std_gamma_grad<float>(alpha, x); }
 double hc_beta_grad_f64(double x, double alpha, double total) { return beta_grad<double>(x, alpha, total); }
 float hc_beta_grad_f32(float x, float alpha, float total) { return beta_grad<float>(x, alpha, total); }
+void hc_beta_grad_pair_f64(double x, double c1, double c0, double* g1, double* g0) { beta_grad_pair<double>(x, c1, c0, *g1, *g0); }
+double hc_lgamma_pos(double x) { return lgamma_pos(x); }
 void hc_philox(uint64_t seed, uint64_t stream, uint64_t offset, int n, uint32_t* out) {
     Philox rng(seed, stream, offset);
     for (int i = 0; i < n; ++i) out[i] = rng.next();
@@ -122,9 +124,9 @@ struct LocalOffsets {
     }
 };
 
-// T: storage + pixel arithmetic type; A: arithmetic type of the per-unit (local) terms
-template <typename T, typename A>
-double cosmos_step_host(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
+// T: storage + pixel arithmetic type; F: arithmetic type of unit_post (site_eval is always double)
+template <typename T, typename F>
+double cosmos_step_host(int nb, int fb, int Nt, int F_, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
                         const T* pixels, const T* xy, const uint8_t* ontarget, const uint8_t* mask, const T* off_s,
                         const T* off_w, const ModelConst* mcp, double sN, double sF, const T* lparams, const double* gparams,
                         const T* lnoise, const double* gnoise, T* lgrads, double* ggrads, double* acc_out, T* samples_out) {
@@ -134,16 +136,9 @@ double cosmos_step_host(int nb, int fb, int Nt, int F, int C, int P, int O, cons
     double gvar[kMaxGlobalNoise], gsamp[kMaxGlobalNoise];
     for (int i = 0; i < gl.n_count(); ++i) gvar[i] = gnoise[i];
     globals_pre(gparams, gl, mc, false, nullptr, gvar, gsamp, gtd);
-    // tables in the local compute type
-    GlobalTables<A> gt;
-    gt.gain = (A)gtd.gain; gt.rate = (A)gtd.rate; gt.log_rate = (A)gtd.log_rate; gt.size1 = (A)gtd.size1;
-    gt.lnorm1 = (A)gtd.lnorm1; gt.dlnorm1 = (A)gtd.dlnorm1;
-    for (int q = 0; q < C; ++q) {
-        for (int a = 0; a < 2; ++a) for (int z = 0; z < kZ; ++z) gt.ch[q].logpz[a][z] = (A)gtd.ch[q].logpz[a][z];
-        for (int a = 0; a < 2; ++a) for (int t = 0; t < kTheta; ++t) gt.ch[q].logptheta[a][t] = (A)gtd.ch[q].logptheta[a][t];
-        for (int t = 0; t < kTheta; ++t) for (int k = 0; k < kK; ++k) for (int m = 0; m < 2; ++m) gt.ch[q].logpm[t][k][m] = (A)gtd.ch[q].logpm[t][k][m];
-    }
-    LocalOffsets lo{Nt, F, C};
+    GlobalTables<F> gt;
+    gt.convert_from(gtd);
+    LocalOffsets lo{Nt, F_, C};
     const int64_t U = (int64_t)nb * fb * C;
     std::vector<double> acc((size_t)C * NACC, 0.0);
     const int64_t total = lo.tensor_off(12);
@@ -154,20 +149,31 @@ double cosmos_step_host(int nb, int fb, int Nt, int F, int C, int P, int O, cons
     for (int64_t u = 0; u < U; ++u) {
         const int c = (int)(u % C), fi = (int)((u / C) % fb), ni = (int)(u / ((int64_t)C * fb));
         const int64_t n = ndx ? ndx[ni] : ni, f = fdx ? fdx[fi] : fi;
-        A uu[NLOCAL];
-        for (int i = 0; i < NLOCAL; ++i) uu[i] = (A)lparams[lo.index(i, n, f, c)];
-        UnitParams<A> up;
-        transform_unit<A>(uu, mc, up);
-        A variate[NSAMP], sampleA[NSAMP], qmA[kM];
-        for (int i = 0; i < NSAMP; ++i) variate[i] = (A)lnoise[i * U + u];
-        local_pre<A>(up, mc, false, nullptr, variate, sampleA, qmA);
-        // samples and weights cross to the likelihood kernel in storage precision
-        T sample[NSAMP], qm[kM];
-        for (int i = 0; i < NSAMP; ++i) { sample[i] = (T)sampleA[i]; sampleA[i] = (A)sample[i]; }
-        for (int m = 0; m < kM; ++m) qm[m] = (T)qmA[m];
+        // sites (double), results stored in T like the (NREC, U) device buffer
+        T rec[NREC], sample[NSAMP], qm[kM], u_mp[kK];
+        const double ubm = (double)lparams[lo.index(LP_BM, n, f, c)], ubs = (double)lparams[lo.index(LP_BS, n, f, c)];
+        for (int st = 0; st < NSAMP; ++st) {
+            double r[NSO], ex[NEX];
+            double variate = (double)lnoise[st * U + u];
+            const double v = site_eval(st, (double)lparams[lo.index(site_param0(st), n, f, c)],
+                                       (double)lparams[lo.index(site_param1(st), n, f, c)], ubm, ubs, mc, false, nullptr,
+                                       variate, r, ex);
+            sample[st] = (T)v;
+            for (int j2 = 0; j2 < NSO; ++j2) rec[st * NSO + j2] = (T)r[j2];
+            if (st == S_B) for (int j2 = 0; j2 < NEX; ++j2) rec[NSAMP * NSO + j2] = (T)ex[j2];
+        }
+        {
+            T q1[kK], q0[kK];
+            for (int k = 0; k < kK; ++k) {
+                u_mp[k] = lparams[lo.index(LP_M_PROBS + k, n, f, c)];
+                const SpotPresence<T> sp(u_mp[k], mc);
+                q1[k] = sp.q1; q0[k] = sp.q0;
+            }
+            presence_weights<T>(q1, q0, qm);
+        }
         if (samples_out) for (int i = 0; i < NSAMP; ++i) samples_out[i * U + u] = sample[i];
         // likelihood with W = q(m)
-        const int64_t patch = (n * F + f) * C + c;
+        const int64_t patch = (n * F_ + f) * C + c;
         PatchSpots<T> sp;
         for (int k = 0; k < kK; ++k) {
             sp.h[k] = sample[S_H + k]; sp.w[k] = sample[S_W + k];
@@ -181,20 +187,24 @@ double cosmos_step_host(int nb, int fb, int Nt, int F, int C, int P, int O, cons
                 for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<T>(col, sp.cx[k], sp.w[k]); gyk[k] = axis_factor<T>(row, sp.cy[k], sp.w[k]); }
                 pixel_accumulate<T, kM, true>(pixels[(patch * P + row) * P + col], gxk, gyk, col, row, sp, mcfg, (T)gtd.rate, (T)gtd.log_rate, O, off_s, off_w, qm, po);
             }
-        A gs[NSAMP], LA[kM];
-        gs[S_B] = (A)po.g_b;
-        for (int k = 0; k < kK; ++k) { gs[S_H + k] = (A)po.g_h[k]; gs[S_W + k] = (A)po.g_w[k]; gs[S_X + k] = (A)po.g_x[k]; gs[S_Y + k] = (A)po.g_y[k]; }
-        for (int m = 0; m < kM; ++m) LA[m] = (A)po.logp[m];
-        UnitGrads<A> ug;
-        local_post<A>(up, mc, gt, c, ontarget[n] != 0, fi == 0, sampleA, LA, gs, (A)po.g_rate, ug);
+        // post in F
+        F recF[NREC], sampleF[NSAMP], gsF[NSAMP], LF[kM], umpF[kK];
+        for (int i = 0; i < NREC; ++i) recF[i] = (F)rec[i];
+        for (int i = 0; i < NSAMP; ++i) sampleF[i] = (F)sample[i];
+        gsF[S_B] = (F)po.g_b;
+        for (int k = 0; k < kK; ++k) { gsF[S_H + k] = (F)po.g_h[k]; gsF[S_W + k] = (F)po.g_w[k]; gsF[S_X + k] = (F)po.g_x[k]; gsF[S_Y + k] = (F)po.g_y[k]; }
+        for (int m = 0; m < kM; ++m) LF[m] = (F)po.logp[m];
+        for (int k = 0; k < kK; ++k) umpF[k] = (F)u_mp[k];
+        UnitGrads<F> ug;
+        unit_post<F>(recF, sampleF, LF, gsF, (F)po.g_rate, umpF, (F)ubm, (F)ubs, mc, gt, c, ontarget[n] != 0, fi == 0, ug);
         const double mu = mask[n] ? 1.0 : 0.0;
         for (int i = 0; i < NACC; ++i) acc[(size_t)c * NACC + i] += mu * (double)ug.acc[i];
         for (int i = 0; i < NLOCAL; ++i) lgrads[lo.index(i, n, f, c)] += (T)(-s * mu * (double)ug.g[i]);
         if (fi == 0) {
-            A gbm, gbs;
-            aoi_prior_grad<A>(up, mc, gbm, gbs);
-            lgrads[lo.index(LP_BM, n, f, c)] += (T)(-sN * mu * (double)gbm);
-            lgrads[lo.index(LP_BS, n, f, c)] += (T)(-sN * mu * (double)gbs);
+            double gbm, gbs;
+            aoi_prior_grad(ubm, ubs, mc, gbm, gbs);
+            lgrads[lo.index(LP_BM, n, f, c)] += (T)(-sN * mu * gbm);
+            lgrads[lo.index(LP_BS, n, f, c)] += (T)(-sN * mu * gbs);
         }
     }
     for (size_t i = 0; i < acc.size(); ++i) acc_out[i] = acc[i];
@@ -218,16 +228,8 @@ double hc_cosmos_step_f32(int nb, int fb, int Nt, int F, int C, int P, int O, co
                           const float* off_s, const float* off_w, const ModelConst* mc, double sN, double sF,
                           const float* lparams, const double* gparams, const float* lnoise, const double* gnoise,
                           float* lgrads, double* ggrads, double* acc_out, float* samples_out) {
-    return cosmos_step_host<float, double>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
-                                   lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
-}
-double hc_cosmos_step_f32_localf32(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
-                          const float* pixels, const float* xy, const uint8_t* ontarget, const uint8_t* mask,
-                          const float* off_s, const float* off_w, const ModelConst* mc, double sN, double sF,
-                          const float* lparams, const double* gparams, const float* lnoise, const double* gnoise,
-                          float* lgrads, double* ggrads, double* acc_out, float* samples_out) {
     return cosmos_step_host<float, float>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
-                                          lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
+                                   lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
 }
 int hc_sizeof_model_const() { return (int)sizeof(ModelConst); }
 }

@@ -131,6 +131,38 @@ def test_beta_grad_matches_aten():
     np.testing.assert_allclose(ours1, ref[:, 1], rtol=1e-10, atol=1e-14)
 
 
+def test_beta_grad_pair_matches_aten():
+    """The shared-subexpression pair used by site_eval == two ATen _dirichlet_grad evaluations."""
+    hc = hostcheck.load()
+    rng = np.random.default_rng(2)
+    a = np.concatenate([rng.uniform(6, 1500, 500), rng.uniform(0.3, 6, 100)])
+    b = np.concatenate([rng.uniform(6, 1500, 500), rng.uniform(0.3, 900, 100)])
+    x = np.clip(rng.beta(a, b), 1e-6, 1 - 1e-6)
+    a, b, x = np.concatenate([a, [50.0, 700.0]]), np.concatenate([b, [50.0, 700.0]]), np.concatenate([x, [0.5, 0.5003]])
+    conc = torch.tensor(np.stack([a, b], -1))
+    xv = torch.tensor(np.stack([x, 1 - x], -1))
+    ref = torch._dirichlet_grad(xv, conc, conc.sum(-1, True).expand_as(conc)).numpy()
+    g1, g0 = ctypes.c_double(), ctypes.c_double()
+    ours = []
+    for xi, ai, bi in zip(x, a, b):
+        hc.hc_beta_grad_pair_f64(ctypes.c_double(xi), ctypes.c_double(ai), ctypes.c_double(bi), ctypes.byref(g1), ctypes.byref(g0))
+        ours.append((g1.value, g0.value))
+    # mathematically identical to ATen; the expansion is ill-conditioned near x = mean, so a different
+    # evaluation order moves the result at the 1e-9 level
+    np.testing.assert_allclose(np.array(ours), ref, rtol=1e-7, atol=1e-14)
+
+
+def test_lgamma_pos_matches_scipy():
+    from scipy.special import gammaln
+
+    hc = hostcheck.load()
+    hc.hc_lgamma_pos.restype = ctypes.c_double
+    hc.hc_lgamma_pos.argtypes = [ctypes.c_double]
+    xs = np.concatenate([np.geomspace(1e-3, 1e5, 400), [1.0, 2.0, 10.0, 0.5]])
+    ours = np.array([hc.hc_lgamma_pos(float(v)) for v in xs])
+    np.testing.assert_allclose(ours, gammaln(xs), rtol=1e-13, atol=2e-14)
+
+
 def test_gamma_sampler_moments():
     hc = hostcheck.load()
     n = 20000

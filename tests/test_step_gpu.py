@@ -41,7 +41,9 @@ CONFIGS = [
 
 
 @pytest.mark.parametrize("cfg", CONFIGS)
-@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-9), (torch.float32, 1e-6, 1e-5)])
+# fp64 gradients: 1e-8 (the paired Rice expansion of the Beta reparameterisation gradient is
+# ill-conditioned near x = mean, evaluation order moves it at the 1e-9 level; see test_hostcheck_math)
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
 def test_step_loss_and_grads_match_oracle(cfg, dtype, ltol, gtol):
     ds, data, params, ndx, fdx, noise = make_problem(**cfg)
     if dtype == torch.float32:  # both sides see the same fp32-rounded parameters and variates
