@@ -48,11 +48,14 @@ TQ_HD void stirling(float ia, float& r, float& q) {
 }
 
 // OC > 0: exactly OC offset bins cached in registers.  OC == 0: any O, two passes.
-template <int NM, int OC, bool BWD>
+// SMALL: some configuration of this patch may have a = image/gain < 4 (needs the recurrence shift);
+// a is smallest for the all-absent configuration, so the caller tests background/gain once per patch.
+template <int NM, int OC, bool BWD, bool SMALL>
 TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&gyk)[kK], int col, int row,
-                                 const PatchSpots<float>& s, const float (&norm)[kK], const FastConst& fc,
-                                 int O, const float* __restrict__ off_s, const float* __restrict__ off_w2,
-                                 const float (&Wr)[NM], PatchOut<float, NM>& out) {
+                                 const PatchSpots<float>& s, const float (&norm)[kK], const float (&iw)[kK],
+                                 const FastConst& fc, int O, const float* __restrict__ off_s,
+                                 const float* __restrict__ off_w2, const float (&W)[NM], const float (&Wr)[NM],
+                                 PatchOut<float, NM>& out) {
     static_assert(NM == kM, "fast path is written for the enumerated 2^K table");
     float shape[kK], mu[kK];
 #pragma unroll
@@ -68,15 +71,24 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
 
     constexpr int NC = OC > 0 ? OC : 1;
     float y[NC], l2[NC], b2[NC];
+    bool any_ok = false;
     if (OC > 0) {
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
             const float yy = D - off_s[j];
             const bool ok = yy > 0.0f;
+            any_ok |= ok;
             y[j] = ok ? yy : 1.0f;
             l2[j] = f_lg2(y[j]);
             b2[j] = ok ? fmaf(-fc.rate2, yy, off_w2[j]) - l2[j] : kNegInf;
         }
+    } else {
+        for (int j = 0; j < O; ++j) any_ok |= (D - off_s[j]) > 0.0f;
+    }
+    if (!any_ok) {  // pixel at or below every offset: log-probability -inf (ksmogn.py:225-236)
+#pragma unroll
+        for (int m = 0; m < NM; ++m) out.logp[m] = -INFINITY;
+        return;
     }
     float gi[NM];
     float g_img_sum = 0.0f;
@@ -121,19 +133,16 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
                 }
             }
         }
-        if (mx <= kNegInf) {  // pixel at or below every offset: log-probability -inf (ksmogn.py:225-236)
-            out.logp[m] = -INFINITY;
-            gi[m] = 0.0f;
-            continue;
-        }
         // lgamma / digamma of a through Stirling; shift by 4 when a is small
         float as = a, shift_log = 0.0f, shift_psi = 0.0f;
-        if (a < 4.0f) {
-            const float p01 = a * (a + 1.0f), p23 = (a + 2.0f) * (a + 3.0f);
-            shift_log = kLn2 * f_lg2(p01 * p23);
-            // 1/a + 1/(a+1) + 1/(a+2) + 1/(a+3)
-            shift_psi = (2.0f * a + 1.0f) * f_rcp(p01) + (2.0f * a + 5.0f) * f_rcp(p23);
-            as = a + 4.0f;
+        if (SMALL) {
+            if (a < 4.0f) {
+                const float p01 = a * (a + 1.0f), p23 = (a + 2.0f) * (a + 3.0f);
+                shift_log = kLn2 * f_lg2(p01 * p23);
+                // 1/a + 1/(a+1) + 1/(a+2) + 1/(a+3)
+                shift_psi = (2.0f * a + 1.0f) * f_rcp(p01) + (2.0f * a + 5.0f) * f_rcp(p23);
+                as = a + 4.0f;
+            }
         }
         const float inv = f_rcp(as * se);   // one reciprocal for 1/a and 1/se
         const float ia = inv * se, ise = inv * as;
@@ -148,7 +157,7 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
             const float psi = la - q - shift_psi;
             const float dLda = fc.log_rate - psi + kLn2 * sl * ise;
             gi[m] = Wr[m] * dLda;   // Wr = W * rate
-            out.g_rate += Wr[m] * fc.gain * fmaf(img[m], dLda + 1.0f, -sy * ise);
+            out.g_rate = fmaf(W[m], fmaf(img[m], dLda + 1.0f, -sy * ise), out.g_rate);
             g_img_sum += gi[m];
         }
     }
@@ -157,14 +166,13 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
         const float S[kK] = {gi[1] + gi[3], gi[2] + gi[3]};
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
-            const float iw = f_rcp(s.w[k]);
-            const float iw2 = iw * iw;
+            const float iw2 = iw[k] * iw[k];
             const float dx = float(col) - s.cx[k], dy = float(row) - s.cy[k];
             const float t = S[k] * mu[k];
             out.g_h[k] = fmaf(S[k], shape[k], out.g_h[k]);
             out.g_x[k] = fmaf(t * iw2, dx, out.g_x[k]);
             out.g_y[k] = fmaf(t * iw2, dy, out.g_y[k]);
-            out.g_w[k] = fmaf(t * iw, fmaf(dx, dx, dy * dy) * iw2 - 2.0f, out.g_w[k]);
+            out.g_w[k] = fmaf(t * iw[k], fmaf(dx, dx, dy * dy) * iw2 - 2.0f, out.g_w[k]);
         }
     }
 }

@@ -60,14 +60,15 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
     std::vector<float> w2(O);
     for (int j = 0; j < O; ++j) w2[j] = off_w[j] * kLog2e;
     for (int64_t u = 0; u < U; ++u) {
-        PatchSpots<float> s; float norm[kK], Wr[kM];
+        PatchSpots<float> s; float norm[kK], iw[kK], Wr[kM], Wm[kM];
         for (int k = 0; k < kK; ++k) {
             s.h[k] = height[k * U + u]; s.w[k] = width[k * U + u];
             s.cx[k] = x[k * U + u] + target[u * 2]; s.cy[k] = y[k * U + u] + target[u * 2 + 1];
-            norm[k] = 1.0f / (6.283185307179586f * s.w[k] * s.w[k]);
+            norm[k] = 1.0f / (6.283185307179586f * s.w[k] * s.w[k]); iw[k] = 1.0f / s.w[k];
         }
         s.b = background[u];
-        for (int m = 0; m < kM; ++m) Wr[m] = W[m * U + u] * fc.rate;
+        for (int m = 0; m < kM; ++m) { Wm[m] = W[m * U + u]; Wr[m] = Wm[m] * fc.rate; }
+        const bool small = s.b * fc.rate < 4.0f;
         PatchOut<float, kM> out; out.zero();
         for (int row = 0; row < P; ++row)
             for (int col = 0; col < P; ++col) {
@@ -75,9 +76,9 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
                 for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<float>(col, s.cx[k], s.w[k]); gyk[k] = axis_factor<float>(row, s.cy[k], s.w[k]); }
                 const float D = value[(u * P + row) * P + col];
                 switch (OC) {
-                    case 3: pixel_accumulate_fast<kM, 3, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
-                    case 4: pixel_accumulate_fast<kM, 4, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
-                    default: pixel_accumulate_fast<kM, 0, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wr, out); break;
+                    case 3: if (small) pixel_accumulate_fast<kM, 3, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 3, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
+                    case 4: if (small) pixel_accumulate_fast<kM, 4, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 4, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
+                    default: if (small) pixel_accumulate_fast<kM, 0, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 0, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
                 }
             }
         for (int m = 0; m < kM; ++m) logp[m * U + u] = out.logp[m];
