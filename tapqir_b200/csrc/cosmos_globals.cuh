@@ -45,21 +45,33 @@ TQ_HD void probs_m_k2(double lam, double& p0, double& dp0, double& p1, double& d
     dp1 = e;
 }
 
+// The global sites are independent of each other, so both directions are written per site and the
+// kernels give each site its own lane (a serial single-thread version cost 80 us per step at C2
+// scale, as much as a third of the likelihood kernel).  Site ids: 0 gain, 1 proximity, 2+q pi_q,
+// 2+Q+q lamda_q.
+TQ_HD int global_site_count(int Q) { return 2 + 2 * Q; }
+
 // ---- forward: variates -> samples -> tables --------------------------------------------------------
 // u: unconstrained global params; variate: base draws (replay) or filled here from `rng`;
-// sample: gain, proximity, pi, lamda in the GlobalLayout::n_* order.
-TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst& mc, bool use_rng, Philox* rng,
-                       double* variate, double* sample, GlobalTables<double>& gt) {
+// sample: gain, proximity, pi, lamda in the GlobalLayout::n_* order.  Writes only the entries of
+// `variate`, `sample` and `gt` that belong to `site`.
+TQ_HD void globals_pre_site(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc, bool use_rng,
+                            Philox* rng, double* variate, double* sample, GlobalTables<double>& gt) {
     static_assert(kK == 2, "probs_m closed form below is written for K = 2");
     const double hi = (mc.P + 1) / sqrt(12.0);
-    // gain ~ Gamma(gain_loc * gain_beta, gain_beta)                                     cosmos.py:342-348
-    {
+    if (site == 0) {
+        // gain ~ Gamma(gain_loc * gain_beta, gain_beta)                                 cosmos.py:342-348
         const double loc = exp(u[gl.gain_loc()]), beta = exp(u[gl.gain_beta()]);
         if (use_rng) variate[gl.n_gain()] = fmax(sample_std_gamma<double>(*rng, loc * beta), mc.tiny);
-        sample[gl.n_gain()] = fmax(variate[gl.n_gain()] / beta, mc.tiny);
+        const double gain = fmax(variate[gl.n_gain()] / beta, mc.tiny);
+        sample[gl.n_gain()] = gain;
+        gt.gain = gain;
+        gt.rate = 1.0 / gain;
+        gt.log_rate = log(gt.rate);
+        return;
     }
-    // proximity ~ AffineBeta(loc, size, 0, (P+1)/sqrt(12))                              cosmos.py:360-368
-    {
+    if (site == 1) {
+        // proximity ~ AffineBeta(loc, size, 0, (P+1)/sqrt(12))                          cosmos.py:360-368
         const Transformed<double> loc = t_interval<double>(u[gl.prox_loc()], 0.0, hi - mc.eps, mc);
         const Transformed<double> size = t_greater_than<double>(u[gl.prox_size()], 2.0);
         const AffBeta<double> d(loc.v, size.v, 0.0, hi);
@@ -67,9 +79,22 @@ TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst
             const double g1 = sample_std_gamma<double>(*rng, d.c1), g2 = sample_std_gamma<double>(*rng, d.c0);
             variate[gl.n_prox()] = beta01_from_gammas(g1, g2, mc);
         }
-        sample[gl.n_prox()] = d.clamp(d.low + d.scale * variate[gl.n_prox()], mc);
+        const double prox = d.clamp(d.low + d.scale * variate[gl.n_prox()], mc);
+        sample[gl.n_prox()] = prox;
+        const double r = (mc.P + 1) / (2.0 * prox);
+        gt.size1 = r * r - 1.0;                                                        // cosmos.py:185-191
+        const double ln2 = 0.69314718055994530942, lP1 = log((double)(mc.P + 1));
+        double lg1, ps1, lgh, psh;
+        lgamma_digamma(gt.size1, lg1, ps1);
+        lgamma_digamma(0.5 * gt.size1, lgh, psh);
+        gt.cxy1 = 2.0 * (lg1 - 2.0 * lgh) - 4.0 * (0.5 * gt.size1 - 1.0) * ln2 - 2.0 * lP1;
+        gt.dcxy1 = 2.0 * (ps1 - psh) - 2.0 * ln2;
+        gt.lxy0 = -2.0 * lP1;
+        return;
     }
-    for (int q = 0; q < gl.Q; ++q) {
+    const double le = log(mc.eps), l1e = log(1.0 - mc.eps);
+    if (site < 2 + gl.Q) {
+        const int q = site - 2;
         // pi_q ~ Dirichlet(pi_mean * pi_size)                                             cosmos.py:349-352
         const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
         const double mxu = fmax(u0, u1);
@@ -81,33 +106,11 @@ TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst
             variate[gl.n_pi(q, 0)] = fmin(fmax(g0 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
             variate[gl.n_pi(q, 1)] = fmin(fmax(g1 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
         }
-        sample[gl.n_pi(q, 0)] = variate[gl.n_pi(q, 0)];
-        sample[gl.n_pi(q, 1)] = variate[gl.n_pi(q, 1)];
-        // lamda_q ~ Gamma(lamda_loc * lamda_beta, lamda_beta)                              cosmos.py:353-359
-        const double lloc = exp(u[gl.lamda_loc(q)]), lbeta = exp(u[gl.lamda_beta(q)]);
-        if (use_rng) variate[gl.n_lamda(q)] = fmax(sample_std_gamma<double>(*rng, lloc * lbeta), mc.tiny);
-        sample[gl.n_lamda(q)] = fmax(variate[gl.n_lamda(q)] / lbeta, mc.tiny);
-    }
-
-    // ---- tables ---------------------------------------------------------------------------------
-    const double gain = sample[gl.n_gain()], prox = sample[gl.n_prox()];
-    gt.gain = gain;
-    gt.rate = 1.0 / gain;
-    gt.log_rate = log(gt.rate);
-    const double r = (mc.P + 1) / (2.0 * prox);
-    gt.size1 = r * r - 1.0;                                                            // cosmos.py:185-191
-    {
-        const double ln2 = 0.69314718055994530942, lP1 = log((double)(mc.P + 1));
-        const double lnorm1 = lgamma(gt.size1) - 2.0 * lgamma(0.5 * gt.size1);
-        gt.cxy1 = 2.0 * lnorm1 - 4.0 * (0.5 * gt.size1 - 1.0) * ln2 - 2.0 * lP1;
-        gt.dcxy1 = 2.0 * (digamma<double>(gt.size1) - digamma<double>(0.5 * gt.size1)) - 2.0 * ln2;
-        gt.lxy0 = -2.0 * lP1;
-    }
-    const double le = log(mc.eps), l1e = log(1.0 - mc.eps);
-    for (int q = 0; q < gl.Q; ++q) {
+        const double p0 = variate[gl.n_pi(q, 0)], p1 = variate[gl.n_pi(q, 1)];
+        sample[gl.n_pi(q, 0)] = p0;
+        sample[gl.n_pi(q, 1)] = p1;
         ChannelTables<double>& ct = gt.ch[q];
         // Categorical(probs).logits = log(clamp(probs / sum))                           cosmos.py:242-246
-        const double p0 = sample[gl.n_pi(q, 0)], p1 = sample[gl.n_pi(q, 1)];
         ct.logpz[0][0] = l1e;  // off-target: [1, 0]                                       util.py:133-151
         ct.logpz[0][1] = le;
         ct.logpz[1][0] = log(clamp_prob(p0 / (p0 + p1), mc));
@@ -117,8 +120,18 @@ TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst
             ct.logptheta[0][th] = (th == 0) ? l1e : le;
             ct.logptheta[1][th] = (th == 0) ? le : log(clamp_prob(1.0 / kK, mc));
         }
+        return;
+    }
+    {
+        const int q = site - 2 - gl.Q;
+        // lamda_q ~ Gamma(lamda_loc * lamda_beta, lamda_beta)                              cosmos.py:353-359
+        const double lloc = exp(u[gl.lamda_loc(q)]), lbeta = exp(u[gl.lamda_beta(q)]);
+        if (use_rng) variate[gl.n_lamda(q)] = fmax(sample_std_gamma<double>(*rng, lloc * lbeta), mc.tiny);
+        const double lam = fmax(variate[gl.n_lamda(q)] / lbeta, mc.tiny);
+        sample[gl.n_lamda(q)] = lam;
+        ChannelTables<double>& ct = gt.ch[q];
         double pm0, d0, pm1, d1;
-        probs_m_k2(sample[gl.n_lamda(q)], pm0, d0, pm1, d1);
+        probs_m_k2(lam, pm0, d0, pm1, d1);
         for (int th = 0; th < kTheta; ++th)
             for (int k = 0; k < kK; ++k) {
                 const double p = clamp_prob(th == 0 ? pm0 : (th == k + 1 ? 1.0 : pm1), mc);
@@ -130,24 +143,20 @@ TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst
 
 // ---- reverse: accumulators -> loss and d loss / d unconstrained globals ------------------------------
 // acc: [Q][NACC] sums over all units of all ranks (unscaled, masked); sN = Nt/nb, sF = F/fb.
-// Returns the ELBO (loss = -ELBO); grad[i] = d loss / d u[i].
-TQ_HD double globals_post(const double* u, const GlobalLayout& gl, const ModelConst& mc, const double* sample,
-                          const double* acc, double sN, double sF, double* grad) {
+// Returns this site's part of the ELBO (site 0 also carries the data terms); writes grad[i] =
+// d loss / d u[i] for the parameters of `site` only.
+TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc,
+                               const double* sample, const double* acc, double sN, double sF, double* grad) {
     const double s = sN * sF;
     const double hi = (mc.P + 1) / sqrt(12.0);
     double elbo = 0.0;
-    for (int i = 0; i < gl.count(); ++i) grad[i] = 0.0;
-
-    double rate_grad = 0.0, size1_grad = 0.0;
-    for (int q = 0; q < gl.Q; ++q) {
-        const double* a = acc + q * NACC;
-        elbo += s * a[ACC_ELBO_FRAME] + sN * a[ACC_ELBO_AOI];
-        rate_grad += s * a[ACC_RATE];
-        size1_grad += s * a[ACC_SIZE1];
-    }
-
-    // ---- gain ----------------------------------------------------------------------------------------
-    {
+    if (site == 0) {
+        double rate_grad = 0.0;
+        for (int q = 0; q < gl.Q; ++q) {
+            const double* a = acc + q * NACC;
+            elbo += s * a[ACC_ELBO_FRAME] + sN * a[ACC_ELBO_AOI];
+            rate_grad += s * a[ACC_RATE];
+        }
         const double loc = exp(u[gl.gain_loc()]), beta = exp(u[gl.gain_beta()]);
         const double conc = loc * beta;
         const double g = sample[gl.n_gain()];
@@ -161,9 +170,11 @@ TQ_HD double globals_post(const double* u, const GlobalLayout& gl, const ModelCo
         const double g_rate = G * (-g / beta) - qg.d_rate;
         grad[gl.gain_loc()] = -(g_conc * beta * loc);
         grad[gl.gain_beta()] = -((g_conc * loc + g_rate) * beta);
+        return elbo;
     }
-    // ---- proximity --------------------------------------------------------------------------------------
-    {
+    if (site == 1) {
+        double size1_grad = 0.0;
+        for (int q = 0; q < gl.Q; ++q) size1_grad += s * acc[q * NACC + ACC_SIZE1];
         const Transformed<double> loc = t_interval<double>(u[gl.prox_loc()], 0.0, hi - mc.eps, mc);
         const Transformed<double> size = t_greater_than<double>(u[gl.prox_size()], 2.0);
         const AffBeta<double> d(loc.v, size.v, 0.0, hi);
@@ -173,83 +184,99 @@ TQ_HD double globals_post(const double* u, const GlobalLayout& gl, const ModelCo
         const double half = 0.5 * (mc.P + 1);
         const double dsize1 = -2.0 * half * half / (v * v * v);
         const double G = size1_grad * dsize1 - mc.proximity_rate - qs.d_v;
-        const double tot = d.c1 + d.c0;
-        const double dv_dc1 = d.scale * (1.0 - qs.x01) * beta_grad<double>(qs.x01, d.c1, tot);
-        const double dv_dc0 = -d.scale * qs.x01 * beta_grad<double>(1.0 - qs.x01, d.c0, tot);
+        double bg1, bg0;
+        beta_grad_pair<double>(qs.x01, d.c1, d.c0, bg1, bg0);
+        const double dv_dc1 = d.scale * (1.0 - qs.x01) * bg1;
+        const double dv_dc0 = -d.scale * qs.x01 * bg0;
         const double g_c1 = G * dv_dc1 - qs.d_c1, g_c0 = G * dv_dc0 - qs.d_c0;
         grad[gl.prox_loc()] = -((g_c1 - g_c0) * size.v / d.scale * loc.d);
         grad[gl.prox_size()] = -((g_c1 * (loc.v - d.low) / d.scale + g_c0 * (d.low + d.scale - loc.v) / d.scale) * size.d);
+        return elbo;
     }
-    for (int q = 0; q < gl.Q; ++q) {
+    if (site < 2 + gl.Q) {
+        const int q = site - 2;
         const double* a = acc + q * NACC;
-        // ---- pi_q ----------------------------------------------------------------------------------------
-        {
-            const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
-            const double mxu = fmax(u0, u1);
-            const double e0 = exp(u0 - mxu), e1 = exp(u1 - mxu);
-            const double mean[2] = {e0 / (e0 + e1), e1 / (e0 + e1)};
-            const double size = exp(u[gl.pi_size(q)]);
-            const double conc[2] = {mean[0] * size, mean[1] * size};
-            const double x[2] = {sample[gl.n_pi(q, 0)], sample[gl.n_pi(q, 1)]};
-            const double tot = conc[0] + conc[1], sx = x[0] + x[1];
-            const double prior_c = 1.0 / kZ;  // Dirichlet(1/(S+1))                               cosmos.py:171-174
-            double lp = lgamma(prior_c * kZ), lq = lgamma(tot);
-            double gx[2];
-            for (int z = 0; z < kZ; ++z) {
-                lp += (prior_c - 1.0) * log(x[z]) - lgamma(prior_c);
-                lq += (conc[z] - 1.0) * log(x[z]) - lgamma(conc[z]);
-                // table path: logpz[1][z] = log(clamp(x_z / sum x))
-                const double pz = x[z] / sx;
-                const bool inside = pz >= mc.eps && pz <= 1.0 - mc.eps;
-                gx[z] = (prior_c - 1.0) / x[z] - (conc[z] - 1.0) / x[z];
-                if (inside) gx[z] += s * a[ACC_LOGPZ + z] / x[z];
-            }
-            for (int z = 0; z < kZ; ++z) {
-                const double pz = x[z] / sx;
-                if (pz >= mc.eps && pz <= 1.0 - mc.eps) {
-                    gx[0] -= s * a[ACC_LOGPZ + z] / sx;
-                    gx[1] -= s * a[ACC_LOGPZ + z] / sx;
-                }
-            }
-            elbo += lp - lq;
-            // Dirichlet reparameterisation (torch dirichlet.py _Dirichlet_backward) + direct -dlogq/dconc
-            const double dot = x[0] * gx[0] + x[1] * gx[1];
-            const double pt = digamma<double>(tot);
-            double g_conc[2];
-            for (int z = 0; z < kZ; ++z)
-                g_conc[z] = beta_grad<double>(x[z], conc[z], tot) * (gx[z] - dot) - (log(x[z]) + pt - digamma<double>(conc[z]));
-            // conc = softmax(u_mean) * exp(u_size)
-            const double gm[2] = {g_conc[0] * size, g_conc[1] * size};
-            const double gmdot = mean[0] * gm[0] + mean[1] * gm[1];
-            grad[gl.pi_mean(q, 0)] = -(mean[0] * (gm[0] - gmdot));
-            grad[gl.pi_mean(q, 1)] = -(mean[1] * (gm[1] - gmdot));
-            grad[gl.pi_size(q)] = -((g_conc[0] * mean[0] + g_conc[1] * mean[1]) * size);
+        const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
+        const double mxu = fmax(u0, u1);
+        const double e0 = exp(u0 - mxu), e1 = exp(u1 - mxu);
+        const double mean[2] = {e0 / (e0 + e1), e1 / (e0 + e1)};
+        const double size = exp(u[gl.pi_size(q)]);
+        const double conc[2] = {mean[0] * size, mean[1] * size};
+        const double x[2] = {sample[gl.n_pi(q, 0)], sample[gl.n_pi(q, 1)]};
+        const double tot = conc[0] + conc[1], sx = x[0] + x[1];
+        const double prior_c = 1.0 / kZ;  // Dirichlet(1/(S+1))                               cosmos.py:171-174
+        double lp = lgamma_pos(prior_c * kZ), lq = lgamma_pos(tot);
+        double gx[2];
+        for (int z = 0; z < kZ; ++z) {
+            lp += (prior_c - 1.0) * log(x[z]) - lgamma_pos(prior_c);
+            lq += (conc[z] - 1.0) * log(x[z]) - lgamma_pos(conc[z]);
+            // table path: logpz[1][z] = log(clamp(x_z / sum x))
+            const double pz = x[z] / sx;
+            const bool inside = pz >= mc.eps && pz <= 1.0 - mc.eps;
+            gx[z] = (prior_c - 1.0) / x[z] - (conc[z] - 1.0) / x[z];
+            if (inside) gx[z] += s * a[ACC_LOGPZ + z] / x[z];
         }
-        // ---- lamda_q ---------------------------------------------------------------------------------------
-        {
-            const double loc = exp(u[gl.lamda_loc(q)]), beta = exp(u[gl.lamda_beta(q)]);
-            const double conc = loc * beta;
-            const double lam = sample[gl.n_lamda(q)];
-            const GammaSite<double> ql(lam, conc, beta);
-            elbo += (log(mc.lamda_rate) - mc.lamda_rate * lam) - ql.lp;  // Exponential prior :176-181
-            double pm0, d0, pm1, d1;
-            probs_m_k2(lam, pm0, d0, pm1, d1);
-            double G = -mc.lamda_rate - ql.d_v;
-            for (int th = 0; th < kTheta; ++th)
-                for (int k = 0; k < kK; ++k) {
-                    if (th == k + 1) continue;  // certain spot: probability 1, no lamda dependence
-                    const double p = th == 0 ? pm0 : pm1, dp = th == 0 ? d0 : d1;
-                    if (p < mc.eps || p > 1.0 - mc.eps) continue;
-                    const double* t = a + ACC_LOGPM + (th * kK + k) * 2;
-                    G += s * (t[1] / p - t[0] / (1.0 - p)) * dp;
-                }
-            const double dv_dconc = std_gamma_grad<double>(conc, lam * beta) / beta;
-            const double g_conc = G * dv_dconc - ql.d_conc;
-            const double g_rate = G * (-lam / beta) - ql.d_rate;
-            grad[gl.lamda_loc(q)] = -(g_conc * beta * loc);
-            grad[gl.lamda_beta(q)] = -((g_conc * loc + g_rate) * beta);
+        for (int z = 0; z < kZ; ++z) {
+            const double pz = x[z] / sx;
+            if (pz >= mc.eps && pz <= 1.0 - mc.eps) {
+                gx[0] -= s * a[ACC_LOGPZ + z] / sx;
+                gx[1] -= s * a[ACC_LOGPZ + z] / sx;
+            }
         }
+        elbo += lp - lq;
+        // Dirichlet reparameterisation (torch dirichlet.py _Dirichlet_backward) + direct -dlogq/dconc
+        const double dot = x[0] * gx[0] + x[1] * gx[1];
+        const double pt = digamma<double>(tot);
+        double g_conc[2];
+        for (int z = 0; z < kZ; ++z)
+            g_conc[z] = beta_grad<double>(x[z], conc[z], tot) * (gx[z] - dot) - (log(x[z]) + pt - digamma<double>(conc[z]));
+        // conc = softmax(u_mean) * exp(u_size)
+        const double gm[2] = {g_conc[0] * size, g_conc[1] * size};
+        const double gmdot = mean[0] * gm[0] + mean[1] * gm[1];
+        grad[gl.pi_mean(q, 0)] = -(mean[0] * (gm[0] - gmdot));
+        grad[gl.pi_mean(q, 1)] = -(mean[1] * (gm[1] - gmdot));
+        grad[gl.pi_size(q)] = -((g_conc[0] * mean[0] + g_conc[1] * mean[1]) * size);
+        return elbo;
     }
+    {
+        const int q = site - 2 - gl.Q;
+        const double* a = acc + q * NACC;
+        const double loc = exp(u[gl.lamda_loc(q)]), beta = exp(u[gl.lamda_beta(q)]);
+        const double conc = loc * beta;
+        const double lam = sample[gl.n_lamda(q)];
+        const GammaSite<double> ql(lam, conc, beta);
+        elbo += (log(mc.lamda_rate) - mc.lamda_rate * lam) - ql.lp;  // Exponential prior :176-181
+        double pm0, d0, pm1, d1;
+        probs_m_k2(lam, pm0, d0, pm1, d1);
+        double G = -mc.lamda_rate - ql.d_v;
+        for (int th = 0; th < kTheta; ++th)
+            for (int k = 0; k < kK; ++k) {
+                if (th == k + 1) continue;  // certain spot: probability 1, no lamda dependence
+                const double p = th == 0 ? pm0 : pm1, dp = th == 0 ? d0 : d1;
+                if (p < mc.eps || p > 1.0 - mc.eps) continue;
+                const double* t = a + ACC_LOGPM + (th * kK + k) * 2;
+                G += s * (t[1] / p - t[0] / (1.0 - p)) * dp;
+            }
+        const double dv_dconc = std_gamma_grad<double>(conc, lam * beta) / beta;
+        const double g_conc = G * dv_dconc - ql.d_conc;
+        const double g_rate = G * (-lam / beta) - ql.d_rate;
+        grad[gl.lamda_loc(q)] = -(g_conc * beta * loc);
+        grad[gl.lamda_beta(q)] = -((g_conc * loc + g_rate) * beta);
+        return elbo;
+    }
+}
+
+// serial forms (host check, tests)
+TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst& mc, bool use_rng, Philox* rng,
+                       double* variate, double* sample, GlobalTables<double>& gt) {
+    for (int site = 0; site < global_site_count(gl.Q); ++site)
+        globals_pre_site(site, u, gl, mc, use_rng, rng, variate, sample, gt);
+}
+TQ_HD double globals_post(const double* u, const GlobalLayout& gl, const ModelConst& mc, const double* sample,
+                          const double* acc, double sN, double sF, double* grad) {
+    double elbo = 0.0;
+    for (int site = 0; site < global_site_count(gl.Q); ++site)
+        elbo += globals_post_site(site, u, gl, mc, sample, acc, sN, sF, grad);
     return elbo;
 }
 

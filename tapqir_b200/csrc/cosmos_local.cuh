@@ -147,15 +147,19 @@ template <typename A> TQ_HD A beta01_from_gammas(A g1, A g2, const ModelConst& m
 }
 
 // ---- densities and their partials ----------------------------------------------------------------
+TQ_HD void special(double x, double& lg, double& psi) { lgamma_digamma(x, lg, psi); }
+TQ_HD void special(float x, float& lg, float& psi) { lg = lgammaf(x); psi = digamma<float>(x); }
 template <typename A> struct GammaSite {
     // value v ~ Gamma(conc, rate): log-density and partials
     A lp, d_v, d_conc, d_rate;
     TQ_HD GammaSite(A v, A conc, A rate) {
         using R = Real<A>;
         const A lv = R::log(v), lr = R::log(rate);
-        lp = conc * lr + (conc - A(1)) * lv - rate * v - R::lgamma(conc);
+        A lg, psi;
+        special(conc, lg, psi);
+        lp = conc * lr + (conc - A(1)) * lv - rate * v - lg;
         d_v = (conc - A(1)) / v - rate;
-        d_conc = lr + lv - digamma(conc);
+        d_conc = lr + lv - psi;
         d_rate = conc / rate - v;
     }
 };
@@ -167,11 +171,14 @@ template <typename A> struct BetaSite {
         x01 = (v - d.low) / d.scale;
         const A l1 = R::log(x01), l0 = R::log(A(1) - x01);
         const A tot = d.c1 + d.c0;
-        const A pt = digamma(tot);
-        lp = (d.c1 - A(1)) * l1 + (d.c0 - A(1)) * l0 + R::lgamma(tot) - R::lgamma(d.c1) - R::lgamma(d.c0) - R::log(d.scale);
+        A lgt, pt, lg1, p1, lg0, p0;
+        special(tot, lgt, pt);
+        special(d.c1, lg1, p1);
+        special(d.c0, lg0, p0);
+        lp = (d.c1 - A(1)) * l1 + (d.c0 - A(1)) * l0 + lgt - lg1 - lg0 - R::log(d.scale);
         d_v = ((d.c1 - A(1)) / x01 - (d.c0 - A(1)) / (A(1) - x01)) / d.scale;
-        d_c1 = l1 + pt - digamma(d.c1);
-        d_c0 = l0 + pt - digamma(d.c0);
+        d_c1 = l1 + pt - p1;
+        d_c0 = l0 + pt - p0;
     }
 };
 
@@ -190,7 +197,7 @@ TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, cons
         // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
         const A loc = exp(u0), beta = exp(u1);
         const A conc = loc * beta;
-        if (use_rng) variate = fmax(sample_std_gamma<A>(*rng, conc), tiny);
+        if (use_rng) variate = fmax((A)sample_std_gamma<float>(*rng, (float)conc), tiny);
         const A v = fmax(variate / beta, tiny);
         const GammaSite<A> q(v, conc, beta);
         const A sgg = std_gamma_grad<A>(conc, v * beta);
@@ -222,7 +229,8 @@ TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, cons
     const Transformed<A> size = t_greater_than<A>(u1, A(2));
     const AffBeta<A> d(mean.v, size.v, lo, hi);
     if (use_rng) {
-        const A g1 = sample_std_gamma<A>(*rng, d.c1), g2 = sample_std_gamma<A>(*rng, d.c0);
+        // the base draws are made in fp32 (their value is random); everything done with them is double
+        const A g1 = (A)sample_std_gamma<float>(*rng, (float)d.c1), g2 = (A)sample_std_gamma<float>(*rng, (float)d.c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
     const A v = d.clamp(d.low + d.scale * variate, mc);

@@ -39,28 +39,31 @@ struct StepState {
 
 constexpr int kLocalBlock = 128;
 
-// ---- globals: sample + tables ------------------------------------------------------------------------
+// ---- globals: sample + tables; one block per global site --------------------------------------------------
 template <typename T>
 __global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
                                       const double* __restrict__ noise_in, unsigned long long seed,
                                       const StepState* __restrict__ state, double* __restrict__ gstate,
                                       GlobalTables<double>* __restrict__ tables, T* __restrict__ gain_out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // one BLOCK per site: lanes of one warp would serialise the divergent per-site code paths
+    const int site = blockIdx.x;
+    if (threadIdx.x != 0 || site >= global_site_count(Q)) return;
     GlobalLayout gl{Q};
-    double u[kMaxGlobals], variate[kMaxGlobalNoise], sample[kMaxGlobalNoise];
+    double u[kMaxGlobals];
     for (int i = 0; i < gl.count(); ++i) u[i] = (double)gparams[i];
     const bool use_rng = noise_in == nullptr;
-    Philox rng(seed, state->step, 0ull);
-    if (!use_rng)
-        for (int i = 0; i < gl.n_count(); ++i) variate[i] = noise_in[i];
-    GlobalTables<double> gt;
-    globals_pre(u, gl, mc, use_rng, &rng, variate, sample, gt);
-    for (int i = 0; i < gl.n_count(); ++i) {
-        gstate[i] = variate[i];
-        gstate[kMaxGlobalNoise + i] = sample[i];
+    Philox rng(seed, state->step, (unsigned long long)site << 8);
+    // every lane works on the shared device buffers directly: the entries of different sites are disjoint
+    double* variate = gstate;
+    double* sample = gstate + kMaxGlobalNoise;
+    if (!use_rng) {
+        if (site == 0) variate[gl.n_gain()] = noise_in[gl.n_gain()];
+        else if (site == 1) variate[gl.n_prox()] = noise_in[gl.n_prox()];
+        else if (site < 2 + Q) { for (int z = 0; z < kZ; ++z) variate[gl.n_pi(site - 2, z)] = noise_in[gl.n_pi(site - 2, z)]; }
+        else variate[gl.n_lamda(site - 2 - Q)] = noise_in[gl.n_lamda(site - 2 - Q)];
     }
-    *tables = gt;
-    gain_out[0] = (T)gt.gain;
+    globals_pre_site(site, u, gl, mc, use_rng, &rng, variate, sample, *tables);
+    if (site == 0) gain_out[0] = (T)tables->gain;
 }
 
 template <typename T> struct LocalArgs {
@@ -229,18 +232,37 @@ __global__ void reduce_aoi_kernel(const LocalArgs<T> a) {
     }
 }
 
-// ---- globals: reverse mode ------------------------------------------------------------------------------------
+// ---- globals: reverse mode; one block per global site, then a fixed-order sum of the ELBO parts -----------------
 template <typename T>
 __global__ void globals_grad_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
                                     const double* __restrict__ gstate, const double* __restrict__ acc,
-                                    double sN, double sF, T* __restrict__ ggrads, double* __restrict__ loss) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+                                    double sN, double sF, T* __restrict__ ggrads, double* __restrict__ elbo_parts) {
+    const int site = blockIdx.x;
+    if (threadIdx.x != 0 || site >= global_site_count(Q)) return;
     GlobalLayout gl{Q};
     double u[kMaxGlobals], grad[kMaxGlobals];
-    for (int i = 0; i < gl.count(); ++i) u[i] = (double)gparams[i];
-    const double elbo = globals_post(u, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, grad);
-    for (int i = 0; i < gl.count(); ++i) ggrads[i] = (T)grad[i];
-    loss[0] = -elbo;
+    for (int i = 0; i < gl.count(); ++i) { u[i] = (double)gparams[i]; grad[i] = 0.0; }
+    elbo_parts[site] = globals_post_site(site, u, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, grad);
+    // each site owns its parameters' gradient entries
+    if (site == 0) { ggrads[gl.gain_loc()] = (T)grad[gl.gain_loc()]; ggrads[gl.gain_beta()] = (T)grad[gl.gain_beta()]; }
+    else if (site == 1) { ggrads[gl.prox_loc()] = (T)grad[gl.prox_loc()]; ggrads[gl.prox_size()] = (T)grad[gl.prox_size()]; }
+    else if (site < 2 + Q) {
+        const int q = site - 2;
+        ggrads[gl.pi_mean(q, 0)] = (T)grad[gl.pi_mean(q, 0)];
+        ggrads[gl.pi_mean(q, 1)] = (T)grad[gl.pi_mean(q, 1)];
+        ggrads[gl.pi_size(q)] = (T)grad[gl.pi_size(q)];
+    } else {
+        const int q = site - 2 - Q;
+        ggrads[gl.lamda_loc(q)] = (T)grad[gl.lamda_loc(q)];
+        ggrads[gl.lamda_beta(q)] = (T)grad[gl.lamda_beta(q)];
+    }
+}
+
+__global__ void finalize_loss_kernel(const double* __restrict__ elbo_parts, int n, double* __restrict__ loss) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double e = 0.0;
+    for (int i = 0; i < n; ++i) e += elbo_parts[i];
+    loss[0] = -e;
 }
 
 // ---- dense Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) --------------------------------------
@@ -304,10 +326,10 @@ extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, c
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
     if (dtype == TQ_F32)
-        globals_sample_kernel<float><<<1, 32, 0, st>>>((const float*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+        globals_sample_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, noise_in, seed, (const StepState*)state,
                                                       gstate, (GlobalTables<double>*)tables, (float*)gain_out);
     else if (dtype == TQ_F64)
-        globals_sample_kernel<double><<<1, 32, 0, st>>>((const double*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+        globals_sample_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, noise_in, seed, (const StepState*)state,
                                                        gstate, (GlobalTables<double>*)tables, (double*)gain_out);
     else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("globals_sample_kernel launch");
@@ -387,17 +409,20 @@ extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_
 }
 
 extern "C" int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
-                                      const double* acc, double sN, double sF, void* ggrads, double* loss, void* stream) {
+                                      const double* acc, double sN, double sF, void* ggrads, double* elbo_parts,
+                                      double* loss, void* stream) {
     TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
-    TQ_CHECK_ARG(gparams && mc && gstate && acc && ggrads && loss, "NULL pointer");
+    TQ_CHECK_ARG(gparams && mc && gstate && acc && ggrads && elbo_parts && loss, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
     if (dtype == TQ_F32)
-        globals_grad_kernel<float><<<1, 32, 0, st>>>((const float*)gparams, Q, m, gstate, acc, sN, sF, (float*)ggrads, loss);
+        globals_grad_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, gstate, acc, sN, sF, (float*)ggrads, elbo_parts);
     else if (dtype == TQ_F64)
-        globals_grad_kernel<double><<<1, 32, 0, st>>>((const double*)gparams, Q, m, gstate, acc, sN, sF, (double*)ggrads, loss);
+        globals_grad_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, gstate, acc, sN, sF, (double*)ggrads, elbo_parts);
     else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("globals_grad_kernel launch");
+    finalize_loss_kernel<<<1, 32, 0, st>>>(elbo_parts, global_site_count(Q), loss);
+    TQ_LAUNCH_CHECK("finalize_loss_kernel launch");
     return TQ_OK;
 }
 

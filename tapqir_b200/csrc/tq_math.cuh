@@ -98,10 +98,19 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 // ATen's digamma_one, Cephes-derived, so the reparameterisation gradients below agree with torch).
 template <typename T> TQ_HD_NOINLINE T digamma(T x) {
     if (x == T(0)) return Real<T>::inf();
+    // recurrence psi(x) = psi(x + n) - sum_{i<n} 1/(x + i) up to x + n >= 10; written as a fixed-trip
+    // predicated loop so that the (independent) reciprocals pipeline instead of forming a serial chain
     T acc = T(0);
-    while (x < T(10)) {
-        acc -= T(1) / x;
-        x += T(1);
+    if (x < T(10)) {
+        const T x0 = x;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const T xi = x0 + T(i);
+            if (xi < T(10)) {
+                acc -= T(1) / xi;
+                x = xi + T(1);
+            }
+        }
     }
     if (x == T(10)) return acc + T(2.25175258906672110764);
     T z = T(1) / (x * x);
@@ -114,6 +123,33 @@ template <typename T> TQ_HD_NOINLINE T digamma(T x) {
     poly = poly * z + T(-8.33333333333333333333E-3);
     poly = poly * z + T(8.33333333333333333333E-2);
     return acc + Real<T>::log(x) - T(0.5) / x - z * poly;
+}
+
+// lgamma(x) and digamma(x) together for x >= 10 from one log and one reciprocal (Stirling series,
+// relative error ~1e-15); the guide's Beta/Gamma concentrations are in this range almost always.
+TQ_HD void lgamma_digamma_large(double x, double& lg, double& psi) {
+    const double lx = ::log(x), ix = 1.0 / x, z = ix * ix;
+    double r = 6.41025641025641025641e-3;
+    r = 1.91752691752691752692e-3 - z * r;
+    r = 8.41750841750841750842e-4 - z * r;
+    r = 5.95238095238095238095e-4 - z * r;
+    r = 7.93650793650793650794e-4 - z * r;
+    r = 2.77777777777777777778e-3 - z * r;
+    r = 8.33333333333333333333e-2 - z * r;
+    lg = (x - 0.5) * lx - x + 0.91893853320467274178 + ix * r;
+    double p = 8.33333333333333333333E-2;
+    p = p * z + -2.10927960927960927961E-2;
+    p = p * z + 7.57575757575757575758E-3;
+    p = p * z + -4.16666666666666666667E-3;
+    p = p * z + 3.96825396825396825397E-3;
+    p = p * z + -8.33333333333333333333E-3;
+    p = p * z + 8.33333333333333333333E-2;
+    psi = lx - 0.5 * ix - z * p;
+}
+TQ_HD void lgamma_digamma(double x, double& lg, double& psi) {
+    if (x > 10.0) { lgamma_digamma_large(x, lg, psi); return; }
+    lg = lgamma_pos(x);
+    psi = digamma<double>(x);
 }
 
 // ---- reparameterisation gradient of a standard Gamma(alpha) draw x: d x / d alpha ------------
@@ -358,7 +394,10 @@ struct Philox {
     }
     TQ_HD uint32_t next() {
         if (have == 0) refill();
-        return out[--have];
+        const uint32_t r = out[0];   // shift instead of out[--have]: keeps the state in registers
+        out[0] = out[1]; out[1] = out[2]; out[2] = out[3];
+        --have;
+        return r;
     }
     // uniform in (0, 1]
     TQ_HD float uniform() { return ((float)(next() >> 8) + 1.0f) * (1.0f / 16777216.0f); }

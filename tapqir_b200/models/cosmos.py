@@ -168,7 +168,7 @@ class cosmos(Model):
     def launches_per_step(self):
         """Kernels of this library launched by one default step (for bench.py's gpu_launches)."""
         eng = self.engine
-        n = 10  # globals_sample, local_pre, ksmogn, local_post, reduce_aoi, reduce_acc, globals_grad, adam x2, advance
+        n = 11  # globals_sample, sites, ksmogn, local_post, reduce_aoi, reduce_acc, globals_grad, finalize_loss, adam x2, advance
         n += (0 if eng.full_n else 1) + (0 if eng.full_f else 1)
         return n
 

@@ -53,8 +53,12 @@ class CosmosEngine:
         self.gain = z(1)
         self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
+        self.elbo_parts = torch.zeros(2 + 2 * 4, dtype=f64, device=dev)   # per-global-site ELBO terms
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
         self.use_graph = use_graph
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork0, self._ev_join0 = torch.cuda.Event(), torch.cuda.Event()
         self._graph, self._eager_default_steps = None, 0
         self.mcfg_arg = None  # NULL = built-in enumerated table -> fp32 production kernel; set to self.mcfg for the generic one
         self.set_batch(nbatch_size or self.Nt, fbatch_size or self.F)
@@ -156,12 +160,20 @@ class CosmosEngine:
             view = self._view(ndx, fdx)
             if not (self.full_n and self.full_f):
                 self.lgrads.zero_()  # dense zero-filled gradient outside the minibatch
-            _lib.check(lib.tq_cosmos_globals_sample(code, self.C, p(self.gparams), mc, p(global_noise), self.seed,
-                                                    p(self.state), p(self.gstate), p(self.tables), p(self.gain), st),
-                       "tq_cosmos_globals_sample")
+            # sampling the globals (one warp, latency-bound) and evaluating the guide sites (independent
+            # of the globals) run concurrently; the likelihood kernel needs both
+            main = torch.cuda.current_stream(self.device)
+            self._ev_fork0.record(main)
+            self._side.wait_event(self._ev_fork0)
+            with torch.cuda.stream(self._side):
+                _lib.check(lib.tq_cosmos_globals_sample(code, self.C, p(self.gparams), mc, p(global_noise), self.seed,
+                                                        p(self.state), p(self.gstate), p(self.tables), p(self.gain),
+                                                        _lib.stream_ptr(self.device)), "tq_cosmos_globals_sample")
+                self._ev_join0.record(self._side)
             _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
                                            p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
                        "tq_cosmos_sites")
+            main.wait_event(self._ev_join0)
             S, G, K = self.samples, self.gs, L.K
             if time_likelihood is not None:
                 time_likelihood[0].record()
@@ -177,15 +189,27 @@ class CosmosEngine:
                        "tq_cosmos_local_post")
             if self.world_size > 1:
                 torch.distributed.all_reduce(self.acc, group=self.pg)
-            _lib.check(lib.tq_cosmos_globals_grad(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.acc),
-                                                  self.sN, self.sF, p(self.ggrads), p(self.loss), st),
-                       "tq_cosmos_globals_grad")
+            # the global reverse pass is a latency-bound single-warp kernel; the dense Adam over the
+            # AOI-local buffer does not depend on it, so the two run on forked streams
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                sst = _lib.stream_ptr(self.device)
+                _lib.check(lib.tq_cosmos_globals_grad(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.acc),
+                                                      self.sN, self.sF, p(self.ggrads), p(self.elbo_parts), p(self.loss), sst),
+                           "tq_cosmos_globals_grad")
+                if update:
+                    b1, b2 = self.betas
+                    _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
+                                                 p(self.gv), self.lr, b1, b2, self.adam_eps, p(self.state), sst),
+                               "tq_adam_dense")
+                self._ev_join.record(self._side)
             if update:
                 b1, b2 = self.betas
                 _lib.check(lib.tq_adam_dense(code, self.ll.numel, p(self.lparams), p(self.lgrads), p(self.lm), p(self.lv),
                                              self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
-                _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm), p(self.gv),
-                                             self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
+            main.wait_event(self._ev_join)
+            if update:
                 _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
         return self.loss
 
