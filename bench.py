@@ -45,6 +45,11 @@ HBM_BYTES_PER_UNIT = 604 + 504
 KSMOGN_HBM_BYTES_PER_UNIT = 392 + 8 + 4 * 9 + 4 * 4 + 4 * 4 + 4 * 10  # pixels, xy, samples, W in; L, grads out
 
 
+def dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', 0)} +{time.perf_counter():.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -137,7 +142,7 @@ def run_native(args):
     ds, nb, fb, desc = make_shard(args.workload, rank, device)
     model = cosmos(device=str(device), dtype="float")
     model.data = ds
-    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world)
+    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world, presharded=True)
     eng = model.engine
     units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step (C = 1)
     launches_per_step = model.launches_per_step
@@ -149,9 +154,11 @@ def run_native(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(device)
 
+    dbg('model ready')
     for _ in range(max(args.warmup, 3)):
         model.step()
     barrier()
+    dbg('warm-up done')
 
     # ---- device-resident timing ("value") ----------------------------------------------------------
     evs = []
@@ -167,6 +174,7 @@ def run_native(args):
             evs.append((e0, e1))
         barrier()
         t_wall = time.perf_counter() - t_wall
+    dbg('timed region done')
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
     if world > 1:
@@ -183,6 +191,7 @@ def run_native(args):
         torch.cuda.synchronize(device)
         k_ms.append(e0.elapsed_time(e1))
     k_ms_avg = sum(k_ms) / len(k_ms)
+    dbg('kernel timing done')
     peaks = measure_peaks(lib, _lib, device)
     measured = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = measured.get("hbm_gbs", 6650.0)
@@ -215,15 +224,18 @@ def run_native(args):
     host_pix = ds.device_store(device).pixels.cpu().pin_memory()
     host_xy = eng.store.xy.cpu().pin_memory()
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    dbg('e2e buffers ready')
     for _ in range(2):
         model.step_from_host(host_pix, host_xy, loss_host)
     barrier()
+    dbg('e2e warm-up done')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         model.step_from_host(host_pix, host_xy, loss_host)
     e1.record()
     barrier()
+    dbg('e2e done')
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
@@ -251,7 +263,14 @@ def run_native(args):
         }
         print(json.dumps(line))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # Tear-down: the captured CUDA graphs hold NCCL work; drop them, drain the device, and leave
+        # without destroy_process_group() (it can block behind graph-captured collectives).
+        barrier()
+        model.engine.release_graph()
+        torch.cuda.synchronize(device)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_cpu_sample(args, budget_s=20.0):

@@ -102,6 +102,8 @@ class cosmos(Model):
     def _shard(self):
         """Contiguous AOI block of this rank."""
         Nt, w, r = self.data.Nt, self.world_size, self.rank
+        if getattr(self, "presharded", False):
+            return slice(0, Nt)
         per = (Nt + w - 1) // w
         lo, hi = min(r * per, Nt), min((r + 1) * per, Nt)
         return slice(lo, hi)
@@ -116,7 +118,9 @@ class cosmos(Model):
         self.engine = CosmosEngine(
             store, sl.stop - sl.start, self.data.F, self.data.C, self.data.P, self.priors, dtype=self.dtype,
             lr=self.lr, betas=self.optim_args["betas"], nbatch_size=self.nbatch_size, fbatch_size=self.fbatch_size,
-            seed=seed, ref_dtype=self.ref_dtype, Nt_total=self.data.Nt, aoi_offset=sl.start, rank=self.rank,
+            seed=seed, ref_dtype=self.ref_dtype,
+            Nt_total=self.data.Nt * (self.world_size if getattr(self, "presharded", False) else 1),
+            aoi_offset=self.rank * self.data.Nt if getattr(self, "presharded", False) else sl.start, rank=self.rank,
             world_size=self.world_size, process_group=self.process_group)
         self.nbatch_size, self.fbatch_size = self.engine.nb, self.engine.fb
         return self.engine

@@ -213,6 +213,10 @@ class CosmosEngine:
                 _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
         return self.loss
 
+    def release_graph(self):
+        """Drop the captured CUDA graph (it keeps references to NCCL work when world_size > 1)."""
+        self._graph, self._eager_default_steps = None, 0
+
     @property
     def iteration(self):
         return int(self.state.item())

@@ -97,17 +97,19 @@ class Model:
 
     # ---- SVI ------------------------------------------------------------------------------------------------
     def init(self, lr: float = 0.005, nbatch_size: int = 5, fbatch_size: int = 512, jit: bool = False,
-             rank: int = 0, world_size: int = 1, process_group=None, seed: int = 0) -> None:
+             rank: int = 0, world_size: int = 1, process_group=None, seed: int = 0, presharded: bool = False) -> None:
         """
         Initialize the SVI state (reference: model.py:153-186): Adam(lr, betas (0.9, 0.999)); resume from
         ``.tapqir/<name>_model.tpqr`` if present, else initialise the variational parameters.
 
         ``rank/world_size/process_group``: AOI-sharded data parallelism -- this process owns the
-        contiguous AOI block ``rank`` of ``world_size``.  ``jit`` is accepted and ignored.
+        contiguous AOI block ``rank`` of ``world_size`` (``presharded=True``: ``self.data`` already IS
+        that block, every rank holding the same number of AOIs).  ``jit`` is accepted and ignored.
         """
         self.lr = lr
         self.optim_args = {"lr": lr, "betas": [0.9, 0.999]}
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        self.presharded = presharded
         self.nbatch_size = min(nbatch_size, self.data.Nt)
         self.fbatch_size = min(fbatch_size, self.data.F)
         self.seed = seed
@@ -166,7 +168,8 @@ class Model:
                     # NaN/Inf found at checkpoint time: go back to the last checkpoint with a new seed
                     new_seed = random.randint(0, 100)
                     self.init(lr=self.lr, nbatch_size=self.nbatch_size, fbatch_size=self.fbatch_size, rank=self.rank,
-                              world_size=self.world_size, process_group=self.process_group, seed=new_seed)
+                              world_size=self.world_size, process_group=self.process_group, seed=new_seed,
+                              presharded=self.presharded)
                     logger.warning(f"Iteration #{self.iter} restarting with a new seed: {new_seed}.")
                 except RuntimeError as err:
                     if str(err.args[0]).startswith("CUDA out of memory") or "out of memory" in str(err):
