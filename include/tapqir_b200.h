@@ -73,7 +73,8 @@ int tq_gaussian_spots(int dtype, int64_t U, int P, const void* height, const voi
 
 /* KSMOGN.log_prob (distributions/ksmogn.py:187-238) for NM spot-presence configurations.
  * height,width,x,y: (K, U); background: (U,); gain: device scalar; mcfg: (NM, K) device table
- * (NM in {1, 4}); logp out: (NM, U). */
+ * (NM in {1, 4}); logp out: (NM, U).  mcfg == NULL (with NM == 4) selects the built-in enumerated
+ * {0,1}^K table of cosmos.py:419-425 and, for TQ_F32, the production kernel (csrc/ksmogn_fast.cuh). */
 int tq_ksmogn_fwd(int dtype, const tq_patch_view* view, const void* height, const void* width,
                   const void* x, const void* y, const void* background, const void* gain,
                   const void* mcfg, int NM, void* logp, void* stream);
@@ -86,6 +87,94 @@ int tq_ksmogn_fwd_bwd(int dtype, const tq_patch_view* view, const void* height, 
                       const void* mcfg, int NM, const void* W, void* logp, void* g_height,
                       void* g_width, void* g_x, void* g_y, void* g_background, void* g_rate,
                       void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * One cosmos SVI step = what `svi.step()` does in models/model.py:212 around the model/guide of
+ * models/cosmos.py:82-462.  Call order on one stream:
+ *
+ *   tq_subsample (x2, optional) -> tq_cosmos_globals_sample -> tq_cosmos_sites -> tq_ksmogn_fwd_bwd
+ *   -> tq_cosmos_local_post -> [all-reduce of `acc` across ranks] -> tq_cosmos_globals_grad
+ *   -> tq_adam_dense (local buffer, global buffer) -> tq_step_advance
+ *
+ * Parameter buffers (unconstrained values, what pyro's param store holds; models/cosmos.py:471-598):
+ *   local  flat (Nt = AOIs of this rank): background_mean_loc (Nt,1,C) | background_std_loc (Nt,1,C)
+ *          | b_loc (Nt,F,C) | b_beta (Nt,F,C) | m_probs | h_loc | h_beta | w_mean | w_size | x_mean
+ *          | y_mean | size, each (K,Nt,F,C)
+ *   global flat: gain_loc | gain_beta | proximity_loc | proximity_size | pi_mean (Q,2) | pi_size (Q)
+ *          | lamda_loc (Q) | lamda_beta (Q)        (Q = C channels, <= 4)
+ * `mc` points to a host `tq_model_const`; `state` to a device uint64 iteration counter (Philox
+ * stream id and Adam bias correction), so a captured CUDA graph can be replayed unchanged.
+ * --------------------------------------------------------------------------------------------- */
+
+/* Prior hyper-parameters (models/cosmos.py:55-64) + eps/tiny of the reference dtype (clamps of
+ * torch's Categorical/Bernoulli/sigmoid and pyro's AffineBeta follow finfo(dtype)). */
+typedef struct {
+    double bg_mean_std, bg_std_std, lamda_rate, height_std, width_min, width_max, proximity_rate, gain_std;
+    double eps, tiny;
+    int32_t P;
+} tq_model_const;
+
+int tq_sizeof_model_const(void);   /* sizeof(tq_model_const) as compiled */
+int tq_sizeof_tables(void);        /* bytes of the device-side global tables blob */
+int tq_sizeof_gstate(void);        /* bytes of the device-side global variates+samples blob */
+int tq_site_record_rows(void);     /* rows NREC of the per-site record buffer (NREC, U) */
+int tq_local_post_blocks(int64_t U); /* thread blocks tq_cosmos_local_post launches for U units */
+
+/* pyro.plate(subsample_size=n) [third party: randperm(size)[:n]]: uniform sample without
+ * replacement by a partial Fisher-Yates on the persistent permutation `perm` (n_total int32,
+ * initialise to arange once).  out: (n_pick,) int32.  stream_id separates independent draws. */
+int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* state, uint64_t stream_id,
+                 void* perm, void* out, void* stream);
+
+/* Guide samples of the four global sites (cosmos.py:342-368) and the prior tables derived from
+ * them (distributions/util.py:67-173).  gparams: global flat buffer (dtype).  noise_in: base
+ * variates (double; gain, proximity, pi (Q,2), lamda (Q)) for replay, or NULL to draw them with
+ * Philox(seed, *state).  Outputs: gstate blob, tables blob, gain_out (1 value, dtype). */
+int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc,
+                             const double* noise_in, uint64_t seed, const void* state,
+                             double* gstate, void* tables, void* gain_out, void* stream);
+
+/* Guide sites of every unit (cosmos.py:397-462): background, height/width/x/y per spot.
+ * noise_in: (9, U) base variates (standard-gamma draws / (0,1) Beta draws) for replay, or NULL.
+ * Outputs: samples (9, U); qm (4, U) = q(m) weights of the enumerated spot-presence configs;
+ * rec (NREC, U) per-site log q, d log q/d sample and the linear maps of the reparameterised
+ * gradient (csrc/cosmos_local.cuh).  Nt: AOIs held by this rank; aoi_offset: global index of AOI 0. */
+int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                    const void* lparams, int64_t aoi_offset, uint64_t seed, const void* state,
+                    const void* noise_in, void* samples, void* qm, void* rec, void* stream);
+
+/* Priors, (z, theta) log-sum-exp, q(m)-weighted ELBO summand and its reverse mode per unit
+ * (TraceEnum_ELBO [third party] on cosmos.py:216-327).  Inputs: the buffers above plus L (4, U),
+ * gs (9, U) and g_rate (U,) from tq_ksmogn_fwd_bwd with W = qm.  sN = Nt_total / nb_total and
+ * sF = F / fb are the plate scales.  Outputs: lgrads (local flat layout; entries of the minibatch
+ * units and of their AOIs), acc (C, 18) per-channel sums for the globals (double);
+ * aoi_partial (2, U) and block_partial (tq_local_post_blocks(U), C, 18) are scratch (double). */
+int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                         const void* lparams, const void* tables, const void* samples,
+                         const void* rec, const void* L, const void* gs, const void* g_rate,
+                         double sN, double sF, void* lgrads, double* aoi_partial,
+                         double* block_partial, double* acc, void* stream);
+
+/* Global sites: ELBO terms and reverse mode from `acc` (summed over ranks) to the global flat
+ * gradient.  elbo_parts: (2 + 2Q,) scratch; loss: 1 double = -ELBO of the step. */
+int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, const void* mc,
+                           const double* gstate, const double* acc, double sN, double sF,
+                           void* ggrads, double* elbo_parts, double* loss, void* stream);
+
+/* torch.optim.Adam step (pyro.optim.Adam({"lr", "betas"}), models/model.py:168-171), dense over
+ * the whole buffer; *state = number of completed steps. */
+int tq_adam_dense(int dtype, int64_t n, void* params, const void* grads, void* exp_avg,
+                  void* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                  const void* state, void* stream);
+
+/* *state += 1 */
+int tq_step_advance(void* state, void* stream);
+
+/* Measured-peak helpers for the roofline (register-resident FMA / MUFU loops); *ops receives the
+ * operations issued by the launch (host pointer). */
+int tq_peak_fma(int blocks, int iters, void* scratch, double* ops, void* stream);
+int tq_peak_mufu(int blocks, int iters, void* scratch, double* ops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -232,5 +232,15 @@ double hc_cosmos_step_f32(int nb, int fb, int Nt, int F, int C, int P, int O, co
     return cosmos_step_host<float, float>(nb, fb, Nt, F, C, P, O, ndx, fdx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, sF,
                                    lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc_out, samples_out);
 }
+// globals only: (replayed) sample -> reverse mode from the given accumulators; returns the loss
+double hc_globals_post(int C, const ModelConst* mc, const double* gparams, const double* gnoise, const double* acc,
+                       double sN, double sF, double* ggrads) {
+    GlobalLayout gl{C};
+    GlobalTables<double> gt;
+    double gvar[kMaxGlobalNoise], gsamp[kMaxGlobalNoise];
+    for (int i = 0; i < gl.n_count(); ++i) gvar[i] = gnoise[i];
+    globals_pre(gparams, gl, *mc, false, nullptr, gvar, gsamp, gt);
+    return -globals_post(gparams, gl, *mc, gsamp, acc, sN, sF, ggrads);
+}
 int hc_sizeof_model_const() { return (int)sizeof(ModelConst); }
 }

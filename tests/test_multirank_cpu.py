@@ -1,0 +1,120 @@
+"""
+CPU, world_size 2 over gloo: the N>1 host logic of the AOI-sharded step.
+
+Each rank evaluates ITS contiguous AOI block (the kernels' arithmetic compiled for the host,
+tests/hostcheck), the (C, 18) accumulator vector is all-reduced -- the only exchange of the path,
+SURVEY.md 8(e) -- and the replicated global reverse pass then yields the same loss and global
+gradients as the single-process oracle on the whole minibatch; local gradients equal the oracle's
+slices for the rank's AOIs.
+"""
+
+import ctypes
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cosmos_oracle as O
+from tapqir_b200.models import layout as L
+from tests.step_helpers import compare_grads, make_problem
+
+
+def _worker(rank, world, port, cfg, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import hostcheck
+        from tests.step_helpers import host_step
+
+        hc = hostcheck.load()
+        ds, data, params, ndx, fdx, noise = make_problem(**cfg)
+        Nt, per = data.Nt, data.Nt // world
+        lo, hi = rank * per, (rank + 1) * per
+        # this rank's shard: AOIs [lo, hi) and the minibatch AOIs that fall inside it
+        sel = (ndx >= lo) & (ndx < hi)
+        shard = O.OracleData(data.images[lo:hi], data.xy[lo:hi], data.is_ontarget[lo:hi], data.mask[lo:hi],
+                             data.offset_samples, data.offset_weights)
+        sparams = {k: (v[:, lo:hi] if v.dim() == 4 else (v[lo:hi] if v.dim() == 3 else v)) for k, v in params.items()}
+        snoise = {k: v for k, v in noise.items()}
+        for k in ("background",):
+            snoise[k] = noise[k][sel]
+        for k in ("height", "width", "x", "y"):
+            snoise[k] = noise[k][:, sel]
+        sndx = ndx[sel] - lo
+        nb_total = len(ndx)
+        # host_step derives sN from the shard; override with the global plate scale
+        import tests.step_helpers as SH
+
+        ll, gl, lparams, gparams, lnoise, gnoise = SH.flat_inputs(shard, sparams, snoise, torch.float64)
+        mc = L.ModelConst.make(O.DEFAULT_PRIORS, shard.P, torch.float64)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        nb, fb = len(sndx), len(fdx)
+        U = nb * fb * shard.C
+        lgrads = torch.empty_like(lparams)
+        ggrads = torch.empty(gl.numel, dtype=torch.float64)
+        acc = torch.zeros(shard.C * L.NACC, dtype=torch.float64)
+        samples = torch.empty(L.NSAMP, U, dtype=torch.float64)
+        sN, sF = Nt / nb_total, data.F / fb
+        hc.hc_cosmos_step_f64.restype = ctypes.c_double
+        n32, f32 = sndx.to(torch.int32).contiguous(), fdx.to(torch.int32).contiguous()
+        pix, xy = shard.images.contiguous(), shard.xy.contiguous()
+        ont, mask = shard.is_ontarget.to(torch.uint8).contiguous(), shard.mask.to(torch.uint8).contiguous()
+        off_s, off_w = shard.offset_samples.contiguous(), shard.offset_logits.contiguous()
+        hc.hc_cosmos_step_f64(nb, fb, shard.Nt, shard.F, shard.C, shard.P, off_s.numel(), p(n32), p(f32), p(pix), p(xy), p(ont),
+                              p(mask), p(off_s), p(off_w), ctypes.byref(mc), ctypes.c_double(sN), ctypes.c_double(sF),
+                              p(lparams), p(gparams), p(lnoise), p(gnoise), p(lgrads), p(ggrads), p(acc), p(samples))
+        dist.all_reduce(acc)   # the one collective of the path
+        hc.hc_globals_post.restype = ctypes.c_double
+        loss = hc.hc_globals_post(shard.C, ctypes.byref(mc), p(gparams), p(gnoise), p(acc), ctypes.c_double(sN),
+                                  ctypes.c_double(sF), p(ggrads))
+        # numpy copies: torch tensors travel through mp queues as shared-memory handles that die with the worker
+        grads = {k: v.numpy().copy() for k, v in ll.views(lgrads).items()}
+        grads.update({k: v.numpy().copy() for k, v in gl.views(ggrads).items()})
+        out_q.put((rank, loss, grads, lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [dict(N=4, F=6, C=1, nb=4, fb=4, seed=0), dict(N=6, F=5, C=2, nb=4, fb=3, seed=1)])
+def test_two_rank_sharded_step_equals_single_process_oracle(cfg):
+    world = 2
+    ds, data, params, ndx, fdx, noise = make_problem(**cfg)
+    ref_loss, ref_grads = O.loss_and_grads(params, data, ndx, fdx, noise)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, loss, grads, lo, hi in results:
+        grads = {k: torch.from_numpy(v) for k, v in grads.items()}
+        assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)          # identical on every rank
+        assert not compare_grads(grads, ref_grads, 1e-8, names=L.GLOBAL_NAMES)
+        for k in L.LOCAL_NAMES:
+            ref = ref_grads[k][:, lo:hi] if ref_grads[k].dim() == 4 else ref_grads[k][lo:hi]
+            err = (grads[k] - ref).abs().max().item()
+            assert err <= 1e-8 * max(ref_grads[k].abs().max().item(), 1e-30), (k, err)
+
+
+def test_aoi_sharding_covers_every_aoi_once():
+    """cosmos._shard: contiguous blocks, disjoint, complete (also when Nt is not divisible)."""
+    from tapqir_b200.models.cosmos import cosmos
+
+    class FakeData:
+        def __init__(self, Nt):
+            self.Nt = Nt
+
+    for Nt, world in [(100, 8), (7, 2), (5, 4), (1000, 8), (3, 4)]:
+        seen = []
+        for r in range(world):
+            m = cosmos.__new__(cosmos)
+            m.data, m.world_size, m.rank, m.presharded = FakeData(Nt), world, r, False
+            sl = m._shard()
+            seen += list(range(sl.start, sl.stop))
+        assert seen == list(range(Nt))
