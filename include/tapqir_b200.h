@@ -156,6 +156,14 @@ int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const
                          double sN, double sF, void* lgrads, double* aoi_partial,
                          double* block_partial, double* acc, void* stream);
 
+/* Posterior of the enumerated latents for one guide draw (cosmos.compute_probs, cosmos.py:609-672):
+ * z_probs (nb, fb, C, 2) += weight * p(z | ...), theta_probs (K, nb, fb, C) += weight * p(theta = k+1 | ...),
+ * from the samples of tq_cosmos_sites and the tables of tq_cosmos_globals_sample (data term hidden,
+ * average over m with q(m)).  Call once per particle with weight = 1 / particles. */
+int tq_cosmos_zprobs(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                     const void* lparams, const void* tables, const void* samples, double weight,
+                     void* z_probs, void* theta_probs, void* stream);
+
 /* Global sites: ELBO terms and reverse mode from `acc` (summed over ranks) to the global flat
  * gradient.  elbo_parts: (2 + 2Q,) scratch; loss: 1 double = -ELBO of the step. */
 int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, const void* mc,

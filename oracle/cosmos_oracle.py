@@ -564,3 +564,59 @@ class OracleSVI:
             opt.step()
         self.iter += 1
         return loss.item()
+
+
+# ------------------------------------------------------------------------------------------------
+# posterior of z / theta (models/cosmos.py:609-672), "next" row N1
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def compute_probs(unconstrained, data: OracleData, ndx, fdx, noises, priors=DEFAULT_PRIORS, K=2, S=1):
+    """
+    z_probs (nb,fb,Q,1+S) and theta_probs (K,nb,fb,Q) for a minibatch, averaged over the given
+    list of guide draws (the reference uses 50 particles, cosmos.py:630-667): for every draw,
+    log p(z, theta, m, x, y) from the model with the data site hidden (:634-648), normalised over
+    (z, theta) (:650), weighted by the guide's q(m) (:651-657), marginalised (:659-667).
+    """
+    dt, P = data.dtype, data.P
+    Q = C = data.C
+    nb, fb = len(ndx), len(fdx)
+    half = (P + 1) / 2
+    t = lambda v: torch.as_tensor(v, dtype=dt)
+    p = to_constrained(unconstrained, P, dt)
+    loc = _gather_local(p, ndx, fdx)
+    g = guide_dists(p, loc, P, priors)
+    mcfg = m_configs(K, dt)
+    M = mcfg.shape[0]
+    qm = D.Bernoulli(probs=loc["m_probs"], validate_args=False)
+    logq_mk = torch.stack([qm.log_prob(torch.zeros((), dtype=dt)), qm.log_prob(torch.ones((), dtype=dt))])
+    logq_m = sum(logq_mk[mcfg[:, k].long(), k] for k in range(K))  # (M,nb,fb,C)
+    ont = data.is_ontarget[ndx]
+    z_acc = torch.zeros(nb, fb, C, S + 1, dtype=dt)
+    th_acc = torch.zeros(K, nb, fb, C, dtype=dt)
+    for noise in noises:
+        pi = noise["pi"].to(dt)
+        lamda = rsample_gamma(*g["lamda"], noise["lamda"])
+        proximity = rsample_affine_beta(g["proximity"], noise["proximity"])
+        size = torch.stack([torch.full_like(proximity, 2.0), ((P + 1) / (2 * proximity)) ** 2 - 1], -1)
+        x = rsample_affine_beta(g["x"], noise["x"])
+        y = rsample_affine_beta(g["y"], noise["y"])
+        pz = expand_offtarget(pi)[:, :, ont.long()].permute(2, 0, 1)[:, None]
+        logp_z = D.Categorical(probs=pz, validate_args=False).logits
+        logp_theta = D.Categorical(probs=probs_theta(K, dt), validate_args=False).logits
+        bern = D.Bernoulli(probs=probs_m(lamda, K), validate_args=False)
+        logp_mk = torch.stack([bern.log_prob(torch.zeros((), dtype=dt)), bern.log_prob(torch.ones((), dtype=dt))])
+        xy_prior = [AffineBeta(t(0.0), size[s], -half, half) for s in range(2)]
+        logp_xy = torch.stack([d.log_prob(x) + d.log_prob(y) for d in xy_prior])
+        joint = torch.empty(S + 1, K + 1, M, nb, fb, C, dtype=dt)
+        for z in range(S + 1):
+            for th in range(K + 1):
+                term = (logp_z[..., z].expand(nb, fb, C) + logp_theta[min(z, 1), th])[None].expand(M, nb, fb, C)
+                for k in range(K):
+                    mk = mcfg[:, k]
+                    term = term + logp_mk[mk.long(), :, th, k][:, None, None, :] + mk[:, None, None, None] * logp_xy[int(th == k + 1), k]
+                joint[z, th] = term
+        post = joint - torch.logsumexp(joint.reshape(-1, M, nb, fb, C), 0)  # normalise over (z, theta)
+        result = torch.logsumexp(post + logq_m, 2)  # average over m -> (Z, TH, nb, fb, C)
+        z_acc += torch.logsumexp(result, 1).exp().permute(1, 2, 3, 0)
+        th_acc += torch.logsumexp(result, 0).exp()[1:]
+    return z_acc / len(noises), th_acc / len(noises)

@@ -53,6 +53,7 @@ SIGNATURES = {
                                  _VP, _VP]),
     "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                       c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
+    "tq_cosmos_zprobs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP]),
     "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),

@@ -446,6 +446,70 @@ TQ_HD void unit_post(const F (&rec)[NREC], const F (&sample)[NSAMP], const F (&L
     }
 }
 
+// ---- posterior of (z, theta) for one guide draw (models/cosmos.py:609-672, "next" row N1) -------------------
+// p(z, theta | m, x, y, globals) from the model's m/x/y/z/theta log-probs (data hidden), averaged
+// over m with the guide weights q(m):  pz[z] = sum_theta,  pth[k] = sum_z at theta = k + 1.
+template <typename F>
+TQ_HD void unit_ztheta_posterior(F x_[kK], F y_[kK], const F (&u_mp)[kK], const ModelConst& mc,
+                                 const GlobalTables<F>& gt, int c, bool ontarget, F (&pz)[kZ], F (&pth)[kK]) {
+    using R = Real<F>;
+    const ChannelTables<F>& ct = gt.ch[c];
+    const F half = F(mc.P + 1) / F(2);
+    const F cs1 = gt.size1 * F(0.5) - F(1);
+    F q1[kK], q0[kK], lxy1[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const SpotPresence<F> sp(u_mp[k], mc);
+        q1[k] = sp.q1; q0[k] = sp.q0;
+        const F tx = x_[k] / half, ty = y_[k] / half;
+        lxy1[k] = cs1 * (R::log1p(-tx * tx) + R::log1p(-ty * ty)) + gt.cxy1;
+    }
+#pragma unroll
+    for (int z = 0; z < kZ; ++z) pz[z] = F(0);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) pth[k] = F(0);
+    const int ot = ontarget ? 1 : 0;
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        F lj[kZ][kTheta];
+        F mx = -R::inf();
+#pragma unroll
+        for (int z = 0; z < kZ; ++z)
+#pragma unroll
+            for (int th = 0; th < kTheta; ++th) {
+                F v = ct.logpz[ot][z] + ct.logptheta[z][th];
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    const int mk = (m >> k) & 1;
+                    v += ct.logpm[th][k][mk];
+                    if (mk) v += (th == k + 1) ? lxy1[k] : gt.lxy0;
+                }
+                lj[z][th] = v;
+                mx = R::max(mx, v);
+            }
+        F se = F(0);
+#pragma unroll
+        for (int z = 0; z < kZ; ++z)
+#pragma unroll
+            for (int th = 0; th < kTheta; ++th) {
+                lj[z][th] = R::exp(lj[z][th] - mx);
+                se += lj[z][th];
+            }
+        F q = F(1);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) q *= ((m >> k) & 1) ? q1[k] : q0[k];
+        const F qi = q / se;
+#pragma unroll
+        for (int z = 0; z < kZ; ++z)
+#pragma unroll
+            for (int th = 0; th < kTheta; ++th) {
+                const F r = qi * lj[z][th];
+                pz[z] += r;
+                if (th > 0) pth[th - 1] += r;
+            }
+    }
+}
+
 // gradient of the AOI-level prior terms w.r.t. the unconstrained (bm, bs); scaled by s_N (not s_N s_F)
 TQ_HD void aoi_prior_grad(double u_bm, double u_bs, const ModelConst& mc, double& g_bm, double& g_bs) {
     const double bm = exp(u_bm), bs = exp(u_bs);

@@ -189,6 +189,31 @@ __global__ void __launch_bounds__(kLocalBlock) local_post_kernel(const LocalArgs
     }
 }
 
+// ---- z / theta posterior of one particle, accumulated into the running means (row N1) ---------------------
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) zprobs_kernel(const LocalArgs<T> a, T weight, T* __restrict__ z_probs,
+                                                            T* __restrict__ theta_probs) {
+    __shared__ GlobalTables<T> gt;
+    if (threadIdx.x == 0) gt.convert_from(*a.tables);
+    __syncthreads();
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= a.U) return;
+    const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
+    T x[kK], y[kK], u_mp[kK], pz[kZ], pth[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        x[k] = a.samples[(int64_t)(S_X + k) * a.U + u];
+        y[k] = a.samples[(int64_t)(S_Y + k) * a.U + u];
+        u_mp[k] = a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, f, ui.c)];
+    }
+    unit_ztheta_posterior<T>(x, y, u_mp, a.mc, gt, ui.c, a.v.is_ontarget[ui.aoi] != 0, pz, pth);
+#pragma unroll
+    for (int z = 0; z < kZ; ++z) z_probs[u * kZ + z] += weight * pz[z];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) theta_probs[(int64_t)k * a.U + u] += weight * pth[k];
+}
+
 // ---- reductions (fixed order => run-to-run deterministic) ---------------------------------------------------
 // acc[c][i] = sum over blocks; one warp per (c, i)
 __global__ void reduce_acc_kernel(const double* __restrict__ block_partial, int nblocks, int C,
@@ -404,6 +429,31 @@ extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TQ_F32) return run_local_post<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
     if (dtype == TQ_F64) return run_local_post<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, sN, sF, lgrads, aoi_partial, block_partial, acc, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T>
+static int run_zprobs(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                      const void* samples, double weight, void* z_probs, void* theta_probs, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
+    a.samples = (T*)samples;
+    if (a.U == 0) return TQ_OK;
+    zprobs_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a, (T)weight, (T*)z_probs, (T*)theta_probs);
+    TQ_LAUNCH_CHECK("zprobs_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_cosmos_zprobs(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                const void* tables, const void* samples, double weight, void* z_probs,
+                                void* theta_probs, void* stream) {
+    TQ_CHECK_ARG(view && mc && lparams && tables && samples && z_probs && theta_probs, "NULL pointer");
+    TQ_CHECK_ARG(view->is_ontarget, "view needs is_ontarget");
+    TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_zprobs<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, weight, z_probs, theta_probs, st);
+    if (dtype == TQ_F64) return run_zprobs<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, weight, z_probs, theta_probs, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }

@@ -192,6 +192,45 @@ class cosmos(Model):
 
     # ---- posterior summaries -----------------------------------------------------------------------------------
     @property
+    def compute_probs(self):
+        """
+        ``(z_probs (Nt,F,Q,1+S), theta_probs (K,Nt,F,Q))`` from 50 guide particles for the on-target AOIs;
+        off-target AOIs stay 0 (reference: cosmos.py:609-672).  Cached; this rank's AOI block only.
+        """
+        if getattr(self, "_probs", None) is None:
+            eng, data = self.engine, self.data
+            sl = self._shard()
+            ont = data.is_ontarget[sl]
+            n_on = int(ont.sum().item())
+            assert bool(ont[:n_on].all()), "on-target AOIs must come first (as written by glimpse/simulate)"
+            z_probs = torch.zeros(eng.Nt, data.F, self.Q, 1 + self.S, dtype=eng.dtype)
+            theta_probs = torch.zeros(self.K, eng.Nt, data.F, self.Q, dtype=eng.dtype)
+            if n_on:
+                z, th = eng.compute_probs(aoi_count=n_on, particles=50)
+                z_probs[:n_on] = z.cpu()
+                theta_probs[:, :n_on] = th.cpu()
+            self._probs = (z_probs, theta_probs)
+        return self._probs
+
+    @property
+    def z_probs(self) -> torch.Tensor:
+        r"""Probability of there being a target-specific spot :math:`p(z=1)` (cosmos.py:674-679)."""
+        return self.compute_probs[0]
+
+    @property
+    def theta_probs(self) -> torch.Tensor:
+        r"""Posterior target-specific spot probability :math:`q(\theta = k)`, k = 1..K (cosmos.py:681-686)."""
+        return self.compute_probs[1]
+
+    @property
+    def pspecific(self) -> torch.Tensor:
+        return self.z_probs
+
+    @property
+    def z_map(self) -> torch.Tensor:
+        return torch.argmax(self.z_probs, dim=-1)
+
+    @property
     def m_probs(self) -> torch.Tensor:
         r"""Posterior spot presence probability :math:`q(m=1)` (cosmos.py:688-693)."""
         return self.param("m_probs").detach()

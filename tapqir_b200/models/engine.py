@@ -213,6 +213,57 @@ class CosmosEngine:
                 _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
         return self.loss
 
+    # ---- posterior of the enumerated latents (cosmos.compute_probs, row N1) --------------------------------
+    @torch.no_grad()
+    def compute_probs(self, aoi_count=None, particles=50, aoi_chunk=None, local_noise=None, global_noise=None,
+                      ndx=None, fdx=None, seed_offset=1 << 40):
+        """
+        z_probs (n, F, C, 2) and theta_probs (K, n, F, C) for local AOIs [0, aoi_count) and all frames
+        (reference: cosmos.py:609-672, 50 guide particles).  For every particle the guide is sampled
+        (tq_cosmos_globals_sample + tq_cosmos_sites) and tq_cosmos_zprobs accumulates the posterior of
+        (z, theta) given that draw.  ``local_noise`` / ``global_noise`` (lists, one per particle) and
+        explicit ``ndx`` / ``fdx`` replay given draws for the parity test.
+        """
+        lib, code, p = self.lib, self.code, _lib.ptr
+        mc = ctypes.byref(self.mc)
+        dev, dtype = self.device, self.dtype
+        n = self.Nt if aoi_count is None else int(aoi_count)
+        if ndx is not None:
+            chunks = [ndx.to(torch.int32)]
+        else:
+            step = aoi_chunk or max(1, min(n, (1 << 22) // max(self.F * self.C, 1)))
+            chunks = [torch.arange(lo, min(lo + step, n), dtype=torch.int32, device=dev) for lo in range(0, n, step)]
+        fb = self.F if fdx is None else len(fdx)
+        z_out, th_out = [], []
+        rows = lib.tq_site_record_rows()
+        for chunk in chunks:
+            nbc = len(chunk)
+            U = nbc * fb * self.C
+            s = self.store
+            view = _lib.make_view(s.pixels, s.xy, s.offset_samples, s.offset_logits, nb=nbc, fb=fb, C=self.C, F=self.F,
+                                  P=self.P, ndx=chunk, fdx=fdx, is_ontarget=s.is_ontarget, mask=s.mask)
+            samples = torch.empty(L.NSAMP, U, dtype=dtype, device=dev)
+            qm = torch.empty(4, U, dtype=dtype, device=dev)
+            rec = torch.empty(rows, U, dtype=dtype, device=dev)
+            z_probs = torch.zeros(nbc, fb, self.C, 2, dtype=dtype, device=dev)
+            theta_probs = torch.zeros(L.K, nbc, fb, self.C, dtype=dtype, device=dev)
+            with torch.cuda.device(dev):
+                st = _lib.stream_ptr(dev)
+                for i in range(particles):
+                    pstate = torch.tensor([seed_offset + i], dtype=torch.int64, device=dev)
+                    gn = None if global_noise is None else global_noise[i]
+                    ln = None if local_noise is None else local_noise[i]
+                    _lib.check(lib.tq_cosmos_globals_sample(code, self.C, p(self.gparams), mc, p(gn), self.seed, p(pstate),
+                                                            p(self.gstate), p(self.tables), p(self.gain), st),
+                               "tq_cosmos_globals_sample")
+                    _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                                   p(pstate), p(ln), p(samples), p(qm), p(rec), st), "tq_cosmos_sites")
+                    _lib.check(lib.tq_cosmos_zprobs(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(samples),
+                                                    1.0 / particles, p(z_probs), p(theta_probs), st), "tq_cosmos_zprobs")
+            z_out.append(z_probs)
+            th_out.append(theta_probs)
+        return torch.cat(z_out, 0), torch.cat(th_out, 1)
+
     def release_graph(self):
         """Drop the captured CUDA graph (it keeps references to NCCL work when world_size > 1)."""
         self._graph, self._eager_default_steps = None, 0

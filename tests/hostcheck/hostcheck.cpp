@@ -242,5 +242,16 @@ double hc_globals_post(int C, const ModelConst* mc, const double* gparams, const
     globals_pre(gparams, gl, *mc, false, nullptr, gvar, gsamp, gt);
     return -globals_post(gparams, gl, *mc, gsamp, acc, sN, sF, ggrads);
 }
+// RNG-mode guide draws of one site type: n samples of site `s` with unconstrained params (u0, u1)
+void hc_site_draws(int s, double u0, double u1, const ModelConst* mc, uint64_t seed, int n, double* out) {
+    for (int i = 0; i < n; ++i) {
+        Philox rng(seed, 7ull, ((uint64_t)(i + 1) << 12) + ((uint64_t)s << 8));
+        double variate = 0.0, rec[NSO], ex[NEX];
+        out[i] = site_eval(s, u0, u1, 0.0, 0.0, *mc, true, &rng, variate, rec, ex);
+    }
+}
+void hc_gamma_draws_f32(float alpha, uint64_t seed, int n, float* out) {
+    for (int i = 0; i < n; ++i) { Philox rng(seed, 3ull, (uint64_t)i << 8); out[i] = sample_std_gamma<float>(rng, alpha); }
+}
 int hc_sizeof_model_const() { return (int)sizeof(ModelConst); }
 }
