@@ -203,6 +203,13 @@ def run_native(args):
     t_hbm = KSMOGN_HBM_BYTES_PER_UNIT / (hbm_peak * 1e9)
     bound = max((t_mufu, "mufu"), (t_fp32, "fp32"), (t_hbm, "hbm"))
     roof_units_per_s = 1.0 / bound[0]
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text()).get("ksmogn_fast_kernel", {})
+        if t.get("workload") == args.workload and t.get("units_per_launch") == units_per_step:
+            traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
+                       "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * units_per_step, "source": t["source"]}
     roofline = {
         "kernel": "ksmogn_kernel<float,uint16,4,true> (fused render + offset-LSE likelihood fwd+bwd)",
         "bound": bound[1],
@@ -210,7 +217,7 @@ def run_native(args):
         "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
         "unit": "Top/s (MUFU)" if bound[1] == "mufu" else ("TFLOP/s" if bound[1] == "fp32" else "GB/s"),
         "frac": (units_per_step / (k_ms_avg * 1e-3)) / roof_units_per_s,
-        "traffic": None,
+        "traffic": traffic,
         "kernel_ms": k_ms_avg,
         "kernel_share_of_step": k_ms_avg / ms_per_step,
         "algorithmic_per_unit": {"mufu_ops": MUFU_PER_UNIT, "fp32_flop": FLOP_PER_UNIT, "hbm_bytes": KSMOGN_HBM_BYTES_PER_UNIT},
