@@ -1,0 +1,104 @@
+"""
+The reference's own smoke contract (test/test_tapqir.py:53-93: simulate N=2, F=5, P=14; `fit` one
+iteration; exit code 0) re-expressed against the new `cosmos` class, plus the on-disk state formats.
+"""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def dataset_path(tmp_path):
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    data = simulate(2, 5, C=1, P=14, seed=0)   # constants of test_tapqir.py:25-40 are simulate()'s defaults
+    save(data, tmp_path)
+    return tmp_path
+
+
+@pytest.mark.parametrize("dtype", ["float", "double"])
+def test_fit_one_iteration_and_checkpoint(dataset_path, dtype):
+    from tapqir_b200.models import models
+
+    model = models["cosmos"](device="cuda", dtype=dtype)
+    model.load(dataset_path)
+    assert (model.data.Nt, model.data.F, model.data.C, model.data.P) == (2, 5, 1, 14)
+    model.init(lr=0.005, nbatch_size=2, fbatch_size=5)
+    model.run(1, progress_bar=lambda it: it)
+    assert model.iter == 1 and model.iter_loss == model.iter_loss  # finite, not NaN
+    ckpt_file = dataset_path / ".tapqir" / "cosmos_model.tpqr"
+    assert ckpt_file.exists()
+    ckpt = torch.load(ckpt_file, weights_only=False)
+    # layout of models/model.py:273-282
+    assert set(ckpt) == {"iter", "params", "optimizer", "rolling", "convergence_status"}
+    assert set(ckpt["params"]) == {"params", "constraints"}
+    names = set(ckpt["params"]["params"])
+    assert names == {"pi_mean", "pi_size", "m_probs", "proximity_loc", "proximity_size", "lamda_loc", "lamda_beta",
+                     "gain_loc", "gain_beta", "background_mean_loc", "background_std_loc", "b_loc", "b_beta", "h_loc",
+                     "h_beta", "w_mean", "w_size", "x_mean", "y_mean", "size"}
+    assert ckpt["params"]["params"]["h_loc"].shape == (2, 2, 5, 1)
+    assert ckpt["params"]["params"]["background_mean_loc"].shape == (2, 1, 1)
+    assert ckpt["params"]["params"]["pi_mean"].shape == (1, 2)
+    st = ckpt["optimizer"]["h_loc"]
+    assert set(st) == {"state", "param_groups"} and set(st["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert "-ELBO" in ckpt["rolling"]
+    assert (dataset_path / ".tapqir" / "logs" / "cosmos").exists()   # tensorboard directory (model.py:209)
+
+    # resume: a fresh model picks the checkpoint up in init() (model.py:173-180)
+    again = models["cosmos"](device="cuda", dtype=dtype)
+    again.load(dataset_path)
+    again.init(lr=0.005, nbatch_size=2, fbatch_size=5)
+    assert again.iter == ckpt["iter"]
+    a, b = model.engine.named_unconstrained(), again.engine.named_unconstrained()
+    # checkpoint was written at iteration 0 (before the counter increments): parameters after 1 step
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(model.engine.lm, again.engine.lm)
+    again.run(2, progress_bar=lambda it: it)
+    assert again.iter == ckpt["iter"] + 2
+
+
+def test_missing_data_raises_reference_exception(tmp_path):
+    from tapqir_b200.exceptions import TapqirFileNotFoundError
+    from tapqir_b200.models import models
+
+    model = models["cosmos"](device="cuda")
+    with pytest.raises(TapqirFileNotFoundError) as err:
+        model.load(tmp_path)
+    assert err.value.name == "data"
+
+
+def test_nan_parameters_raise_value_error_at_checkpoint(dataset_path):
+    """model.py:246-250: NaN/Inf in any parameter -> ValueError at checkpoint time."""
+    from tapqir_b200.models import models
+
+    model = models["cosmos"](device="cuda")
+    model.load(dataset_path)
+    model.init(nbatch_size=2, fbatch_size=5)
+    model.step()
+    model.engine.named_unconstrained()["gain_loc"].fill_(float("nan"))
+    with pytest.raises(ValueError, match="gain_loc"):
+        model.save_checkpoint()
+
+
+def test_minibatch_run_with_device_subsampling(dataset_path):
+    """nbatch/fbatch smaller than the data: indices drawn on the device each step, dense Adam."""
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    save(simulate(6, 40, seed=1), dataset_path)
+    model = models["cosmos"](device="cuda")
+    model.load(dataset_path)
+    model.init(nbatch_size=3, fbatch_size=16)
+    before = model.engine.lparams.clone()
+    losses = [model.step().item() for _ in range(30)]
+    assert all(l == l for l in losses)
+    ndx = model.engine.ndx.cpu()
+    assert len(set(ndx.tolist())) == 3 and ndx.min() >= 0 and ndx.max() < 6
+    fdx = model.engine.fdx.cpu()
+    assert len(set(fdx.tolist())) == 16 and fdx.max() < 40
+    assert (model.engine.lparams != before).float().mean().item() > 0.9   # dense update: (almost) every entry moved
