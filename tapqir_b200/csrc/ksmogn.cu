@@ -142,8 +142,8 @@ template <typename T> __device__ __forceinline__ T sub_sum(T v) {
     return v;
 }
 
-template <typename PIX, int OC, bool P14, bool BWD, bool SMALL>
-__device__ __forceinline__ void sweep_patch(const PIX* __restrict__ pix, int P, int PP, int sub, const float* gx,
+template <int OC, bool P14, bool BWD, bool SMALL>
+__device__ __forceinline__ void sweep_patch(const float* __restrict__ pix, int P, int PP, int sub, const float* gx,
                                             const float* gy, const PatchSpots<float>& s, const float (&norm)[kK],
                                             const float (&iw)[kK], const FastConst& fc, int O, const float* off_s,
                                             const float* off_w2, const float (&W)[kM], const float (&Wr)[kM],
@@ -157,13 +157,13 @@ __device__ __forceinline__ void sweep_patch(const PIX* __restrict__ pix, int P, 
             gxk[k] = gx[k * kMaxP + col];
             gyk[k] = gy[k * kMaxP + row];
         }
-        pixel_accumulate_fast<kM, OC, BWD, SMALL>(float(pix[p]), gxk, gyk, col, row, s, norm, iw, fc, O, off_s, off_w2,
+        pixel_accumulate_fast<kM, OC, BWD, SMALL>(pix[p], gxk, gyk, col, row, s, norm, iw, fc, O, off_s, off_w2,
                                                   W, Wr, out);
     }
 }
 
 template <typename PIX, int OC, bool P14, bool BWD>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
 ksmogn_fast_kernel(const KsmognArgs<float> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* off_s = reinterpret_cast<float*>(smem_raw);
@@ -171,6 +171,10 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
     const int slot = threadIdx.x / kSub, sub = threadIdx.x % kSub;
     float* gx = off_w2 + a.v.O + slot * (2 * kK * kMaxP);
     float* gy = gx + kK * kMaxP;
+    const int PPs = (P14 ? 14 * 14 : a.v.P * a.v.P);
+    // staged pixels of this slot's patch: all global loads of a patch are issued back to back up
+    // front instead of one dependent load per sweep (long-scoreboard stalls dominated before)
+    float* spx = off_w2 + a.v.O + kUnitsPerBlock * (2 * kK * kMaxP) + slot * PPs;
     for (int j = threadIdx.x; j < a.v.O; j += blockDim.x) {
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
         off_w2[j] = static_cast<const float*>(a.v.offset_logits)[j] * kLog2e;
@@ -214,6 +218,26 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
 
         // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
         __syncwarp();
+        {
+            const PIX* src = pixels + ui.patch * PP;
+            if (P14 && sizeof(PIX) == 2) {
+                // 196 uint16 = 49 x 8 bytes, 8-byte aligned (392 B per patch)
+                const uint2* v = reinterpret_cast<const uint2*>(src);
+#pragma unroll
+                for (int t = 0; t < 7; ++t) {
+                    const int i = sub + t * kSub;
+                    if (i < 49) {
+                        const uint2 q = __ldg(v + i);
+                        spx[4 * i + 0] = float(q.x & 0xffffu);
+                        spx[4 * i + 1] = float(q.x >> 16);
+                        spx[4 * i + 2] = float(q.y & 0xffffu);
+                        spx[4 * i + 3] = float(q.y >> 16);
+                    }
+                }
+            } else {
+                for (int p = sub; p < PP; p += kSub) spx[p] = float(src[p]);
+            }
+        }
         for (int idx = sub; idx < 2 * kK * P; idx += kSub) {
             const int axis = idx / (kK * P), rem = idx - axis * (kK * P);
             const int k = rem / P, i = rem - k * P;
@@ -229,9 +253,9 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
         // a = image/gain is smallest without spots: one test per patch selects the Stirling variant
         const bool small = s.b * fc.rate < 4.0f;
         if (__any_sync(0xffffffffu, small))
-            sweep_patch<PIX, OC, P14, BWD, true>(pix, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
+            sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
         else
-            sweep_patch<PIX, OC, P14, BWD, false>(pix, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
+            sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
 
 #pragma unroll
         for (int m = 0; m < kM; ++m) out.logp[m] = sub_sum(out.logp[m]);
@@ -268,15 +292,17 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
 
 template <typename PIX, int OC, bool P14, bool BWD>
 static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (2 * (size_t)a.v.O + kUnitsPerBlock * 2 * kK * kMaxP);
+    const size_t smem = sizeof(float) * (2 * (size_t)a.v.O + kUnitsPerBlock * (2 * kK * kMaxP + (size_t)a.v.P * a.v.P));
     auto kern = ksmogn_fast_kernel<PIX, OC, P14, BWD>;
     if (smem > 48 * 1024) {
         int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                               "cudaFuncSetAttribute(ksmogn_fast)");
         if (st2 != TQ_OK) return st2;
     }
+    // one block per 16 patches, no persistence: equal-cost blocks + the hardware block scheduler balance
+    // better than a capped grid (2.64 static iterations per block left the last wave 64 % full)
     const int64_t blocks_needed = (a.U + kUnitsPerBlock - 1) / kUnitsPerBlock;
-    const int64_t cap = (int64_t)sm_count() * 16;
+    const int64_t cap = 0x7fffffff;
     const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
     kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
     TQ_LAUNCH_CHECK("ksmogn_fast_kernel launch");
