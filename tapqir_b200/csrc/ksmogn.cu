@@ -145,7 +145,7 @@ template <typename T> __device__ __forceinline__ T sub_sum(T v) {
 template <int OC, bool P14, bool BWD, bool SMALL>
 __device__ __forceinline__ void sweep_patch(const float* __restrict__ pix, int P, int PP, int sub, const float* gx,
                                             const float* gy, const PatchSpots<float>& s, const float (&norm)[kK],
-                                            const float (&iw)[kK], const FastConst& fc, int O, const float* off_s,
+                                            const FastConst& fc, int O, const float* off_s,
                                             const float* off_w2, const float (&W)[kM], const float (&Wr)[kM],
                                             PatchOut<float, kM>& out) {
 #pragma unroll 1
@@ -157,7 +157,7 @@ __device__ __forceinline__ void sweep_patch(const float* __restrict__ pix, int P
             gxk[k] = gx[k * kMaxP + col];
             gyk[k] = gy[k * kMaxP + row];
         }
-        pixel_accumulate_fast<kM, OC, BWD, SMALL>(pix[p], gxk, gyk, col, row, s, norm, iw, fc, O, off_s, off_w2,
+        pixel_accumulate_fast<kM, OC, BWD, SMALL>(pix[p], gxk, gyk, col, row, s, norm, fc, O, off_s, off_w2,
                                                   W, Wr, out);
     }
 }
@@ -253,9 +253,9 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
         // a = image/gain is smallest without spots: one test per patch selects the Stirling variant
         const bool small = s.b * fc.rate < 4.0f;
         if (__any_sync(0xffffffffu, small))
-            sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
+            sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);
         else
-            sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, iw, fc, a.v.O, off_s, off_w2, W, Wr, out);
+            sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);
 
 #pragma unroll
         for (int m = 0; m < kM; ++m) out.logp[m] = sub_sum(out.logp[m]);
@@ -269,6 +269,7 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
                 out.g_x[k] = sub_sum(out.g_x[k]);
                 out.g_y[k] = sub_sum(out.g_y[k]);
             }
+            finish_spot_moments(s, out);
         }
         if (live && sub == 0) {
             if (a.logp) {

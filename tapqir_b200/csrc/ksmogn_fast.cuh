@@ -52,7 +52,7 @@ TQ_HD void stirling(float ia, float& r, float& q) {
 // a is smallest for the all-absent configuration, so the caller tests background/gain once per patch.
 template <int NM, int OC, bool BWD, bool SMALL>
 TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&gyk)[kK], int col, int row,
-                                 const PatchSpots<float>& s, const float (&norm)[kK], const float (&iw)[kK],
+                                 const PatchSpots<float>& s, const float (&norm)[kK],
                                  const FastConst& fc, int O, const float* __restrict__ off_s,
                                  const float* __restrict__ off_w2, const float (&W)[NM], const float (&Wr)[NM],
                                  PatchOut<float, NM>& out) {
@@ -163,17 +163,34 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
     }
     if (BWD) {
         out.g_b += g_img_sum;
+        // spot gradients as moments of t = S_k mu_k about the spot centre; the 1/w^2, 1/w^3, 1/h
+        // factors are applied once per patch (finish_spot_moments).  (Moments about the patch centre
+        // would save three more ops but cancel for off-centre spots: 1e-5 errors measured.)
         const float S[kK] = {gi[1] + gi[3], gi[2] + gi[3]};
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
-            const float iw2 = iw[k] * iw[k];
             const float dx = float(col) - s.cx[k], dy = float(row) - s.cy[k];
             const float t = S[k] * mu[k];
-            out.g_h[k] = fmaf(S[k], shape[k], out.g_h[k]);
-            out.g_x[k] = fmaf(t * iw2, dx, out.g_x[k]);
-            out.g_y[k] = fmaf(t * iw2, dy, out.g_y[k]);
-            out.g_w[k] = fmaf(t * iw[k], fmaf(dx, dx, dy * dy) * iw2 - 2.0f, out.g_w[k]);
+            out.g_h[k] += t;
+            out.g_x[k] = fmaf(t, dx, out.g_x[k]);
+            out.g_y[k] = fmaf(t, dy, out.g_y[k]);
+            out.g_w[k] = fmaf(t, fmaf(dx, dx, dy * dy), out.g_w[k]);
         }
+    }
+}
+
+// Per-patch conversion of the accumulated moments (after the cross-lane reduction):
+//   A0 = sum t, A1 = sum t dx, A2 = sum t dy, A3 = sum t (dx^2 + dy^2)
+//   d/dh = A0 / h,  d/dx = A1 / w^2,  d/dy = A2 / w^2,  d/dw = A3 / w^3 - 2 A0 / w
+TQ_HD void finish_spot_moments(const PatchSpots<float>& s, PatchOut<float, kM>& out) {
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const float A0 = out.g_h[k], A3 = out.g_w[k];
+        const float iw = 1.0f / s.w[k], iw2 = iw * iw;
+        out.g_h[k] = A0 / s.h[k];
+        out.g_x[k] *= iw2;
+        out.g_y[k] *= iw2;
+        out.g_w[k] = iw * (iw2 * A3 - 2.0f * A0);
     }
 }
 

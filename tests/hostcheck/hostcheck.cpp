@@ -76,11 +76,12 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
                 for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<float>(col, s.cx[k], s.w[k]); gyk[k] = axis_factor<float>(row, s.cy[k], s.w[k]); }
                 const float D = value[(u * P + row) * P + col];
                 switch (OC) {
-                    case 3: if (small) pixel_accumulate_fast<kM, 3, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 3, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
-                    case 4: if (small) pixel_accumulate_fast<kM, 4, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 4, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
-                    default: if (small) pixel_accumulate_fast<kM, 0, true, true>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 0, true, false>(D, gxk, gyk, col, row, s, norm, iw, fc, O, off_s, w2.data(), Wm, Wr, out); break;
+                    case 3: if (small) pixel_accumulate_fast<kM, 3, true, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 3, true, false>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); break;
+                    case 4: if (small) pixel_accumulate_fast<kM, 4, true, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 4, true, false>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); break;
+                    default: if (small) pixel_accumulate_fast<kM, 0, true, true>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); else pixel_accumulate_fast<kM, 0, true, false>(D, gxk, gyk, col, row, s, norm, fc, O, off_s, w2.data(), Wm, Wr, out); break;
                 }
             }
+        finish_spot_moments(s, out);
         for (int m = 0; m < kM; ++m) logp[m * U + u] = out.logp[m];
         g_b[u] = out.g_b; g_rate[u] = out.g_rate;
         for (int k = 0; k < kK; ++k) { g_h[k * U + u] = out.g_h[k]; g_w[k * U + u] = out.g_w[k]; g_x[k * U + u] = out.g_x[k]; g_y[k * U + u] = out.g_y[k]; }
