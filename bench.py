@@ -58,41 +58,56 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons of one GPU while the timed region runs."""
-
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, polled through NVML (nvidia_ml_py) every ~2 ms on a
+    background thread while the timed region runs (nvidia-smi -lms is too coarse for a 10 ms region)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                "hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap,
+            }
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.reasons.update(n for n, bit in names.items() if mask & bit)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+        except Exception as err:  # NVML missing: report it, do not fail the bench
+            self.error = repr(err)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *exc):
-        if self.proc:
-            self.proc.terminate()
-            self.thread.join(timeout=2)
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def measure_peaks(lib, _lib, device):
@@ -233,13 +248,14 @@ def run_native(args):
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
     dbg('e2e buffers ready')
     for _ in range(2):
-        model.step_from_host(host_pix, host_xy, loss_host)
+        model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
     barrier()
     dbg('e2e warm-up done')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        model.step_from_host(host_pix, host_xy, loss_host)
+        # this step's inputs come from pinned host memory (uploaded during the previous step's compute)
+        model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
     e1.record()
     barrier()
     dbg('e2e done')

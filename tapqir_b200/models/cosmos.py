@@ -176,18 +176,46 @@ class cosmos(Model):
         n += (0 if eng.full_n else 1) + (0 if eng.full_f else 1)
         return n
 
-    def step_from_host(self, host_pixels, host_xy, loss_host):
+    def step_from_host(self, host_pixels, host_xy, loss_host, prefetch_next=None):
         """
         One step fed from HOST buffers, the way the reference feeds every step
-        (utils/dataset.py:140-151: gather on the CPU, ``.to(device)``): pinned host pixels + target
-        locations are copied to the device store, the step runs, the loss is copied back.
+        (utils/dataset.py:140-151: gather on the CPU, ``.to(device)``): the step's pinned host pixels +
+        target locations are copied to the device, the step runs, the loss is copied back and awaited.
+
+        ``prefetch_next=(pixels, xy)`` (pinned host tensors of the NEXT step) starts their upload on a
+        copy stream into a staging buffer while this step computes; the next call then only pays a
+        device-to-device move.  Every step's inputs still cross PCIe inside the caller's timed region.
         """
-        eng = self.engine
-        eng.store.pixels.copy_(host_pixels, non_blocking=True)
-        eng.store.xy.copy_(host_xy, non_blocking=True)
+        eng, dev = self.engine, self.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_feed", None) is None:
+            self._feed = {
+                "copy": torch.cuda.Stream(device=dev),
+                "pix": torch.empty_like(eng.store.pixels), "xy": torch.empty_like(eng.store.xy),
+                "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "pending": None,
+            }
+            self._feed["free"].record(main)
+        fd = self._feed
+        if fd["pending"] is not None and fd["pending"] == (host_pixels.data_ptr(), host_xy.data_ptr()):
+            main.wait_event(fd["ready"])                      # upload issued during the previous step
+            eng.store.pixels.copy_(fd["pix"], non_blocking=True)
+            eng.store.xy.copy_(fd["xy"], non_blocking=True)
+        else:
+            eng.store.pixels.copy_(host_pixels, non_blocking=True)
+            eng.store.xy.copy_(host_xy, non_blocking=True)
+        fd["free"].record(main)                               # staging buffers may be overwritten from here on
+        fd["pending"] = None
         loss = self.step()
         loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if prefetch_next is not None:
+            npix, nxy = prefetch_next
+            fd["copy"].wait_event(fd["free"])
+            with torch.cuda.stream(fd["copy"]):
+                fd["pix"].copy_(npix, non_blocking=True)
+                fd["xy"].copy_(nxy, non_blocking=True)
+                fd["ready"].record(fd["copy"])
+            fd["pending"] = (npix.data_ptr(), nxy.data_ptr())
+        main.synchronize()
         return float(loss_host.item())
 
     # ---- posterior summaries -----------------------------------------------------------------------------------
