@@ -189,6 +189,25 @@ template <typename A> struct BetaSite {
 //   variate   base draw: standard gamma (Gamma sites) or (0,1) Beta draw; filled here when use_rng
 //   rec[NSO]  site record;  extra[NEX] background-prior record (s == S_B only)
 // Returns the guide sample.
+//
+// Both families have a "usual regime" path that reuses logarithms and reciprocals (the exp
+// transforms make log(conc), log(rate) free; lgamma and digamma share one log and one reciprocal;
+// the two Beta reparameterisation gradients share theirs) and fall back to the general functions
+// outside it.  Same formulas either way; tests/test_hostcheck_step.py pins both against the oracle.
+
+// log-density of v ~ Gamma(conc, rate) and partials, logs supplied: lv = log v, lr = log rate,
+// lconc = log conc
+TQ_HD void gamma_density(double v, double conc, double rate, double lv, double lr, double lconc,
+                         double& lp, double& d_v, double& d_conc, double& d_rate) {
+    double lg, psi;
+    if (conc > 10.0) lgamma_digamma_known(conc, lconc, 1.0 / conc, lg, psi);
+    else lgamma_digamma(conc, lg, psi);
+    lp = conc * lr + (conc - 1.0) * lv - rate * v - lg;
+    d_v = (conc - 1.0) / v - rate;
+    d_conc = lr + lv - psi;
+    d_rate = conc / rate - v;
+}
+
 TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, const ModelConst& mc, bool use_rng,
                        Philox* rng, double& variate, double* rec, double* extra) {
     using A = double;
@@ -197,27 +216,35 @@ TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, cons
         // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
         const A loc = exp(u0), beta = exp(u1);
         const A conc = loc * beta;
-        if (use_rng) variate = fmax((A)sample_std_gamma<float>(*rng, (float)conc), tiny);
+        if (use_rng) variate = fmax((A)sample_std_gamma_f32(*rng, (float)conc), tiny);
         const A v = fmax(variate / beta, tiny);
-        const GammaSite<A> q(v, conc, beta);
-        const A sgg = std_gamma_grad<A>(conc, v * beta);
-        rec[SO_LQ] = q.lp;
-        rec[SO_DQ] = q.d_v;
+        // exp transforms: log(rate) = u1 and log(conc) = u0 + u1 exactly
+        const A lvar = log(v * beta);
+        const A lv = lvar - u1, lconc = u0 + u1;
+        A lp, d_v, d_conc, d_rate;
+        gamma_density(v, conc, beta, lv, u1, lconc, lp, d_v, d_conc, d_rate);
+        const A x = v * beta;
+        const A sgg = (conc > 8.0 && x >= 0.8) ? std_gamma_grad_large(conc, x, lvar - lconc, 1.0 / conc)
+                                               : std_gamma_grad<A>(conc, x);
+        rec[SO_LQ] = lp;
+        rec[SO_DQ] = d_v;
         // v = variate / beta:  dv/du_loc = sgg * loc,  dv/du_beta = sgg * loc - v
         rec[SO_A0] = sgg * loc;
         rec[SO_A1] = sgg * loc - v;
-        rec[SO_B0] = q.d_conc * conc;
-        rec[SO_B1] = q.d_conc * conc + q.d_rate * beta;
+        rec[SO_B0] = d_conc * conc;
+        rec[SO_B1] = d_conc * conc + d_rate * beta;
         if (s == S_B) {
             // model prior Gamma((bm/bs)^2, bm/bs^2)                                       cosmos.py:233-239
             const A bm = exp(ubm), bs = exp(ubs);
-            const A pc = (bm / bs) * (bm / bs), pr = bm / (bs * bs);
-            const GammaSite<A> p(v, pc, pr);
-            extra[EX_LP] = p.lp;
-            extra[EX_DP] = p.d_v;
+            const A ibs = 1.0 / bs;
+            const A pc = (bm * ibs) * (bm * ibs), pr = bm * ibs * ibs;
+            A plp, pd_v, pd_conc, pd_rate;
+            gamma_density(v, pc, pr, lv, ubm - 2.0 * ubs, 2.0 * (ubm - ubs), plp, pd_v, pd_conc, pd_rate);
+            extra[EX_LP] = plp;
+            extra[EX_DP] = pd_v;
             // d/d u_bm, d/d u_bs (exp transforms: times bm, bs)
-            extra[EX_GBM] = (p.d_conc * (A(2) * bm / (bs * bs)) + p.d_rate / (bs * bs)) * bm;
-            extra[EX_GBS] = (p.d_conc * (-A(2) * bm * bm / (bs * bs * bs)) + p.d_rate * (-A(2) * bm / (bs * bs * bs))) * bs;
+            extra[EX_GBM] = (pd_conc * (A(2) * bm * ibs * ibs) + pd_rate * ibs * ibs) * bm;
+            extra[EX_GBS] = (pd_conc * (-A(2) * bm * bm * ibs * ibs * ibs) + pd_rate * (-A(2) * bm * ibs * ibs * ibs)) * bs;
         }
         return v;
     }
@@ -230,24 +257,76 @@ TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, cons
     const AffBeta<A> d(mean.v, size.v, lo, hi);
     if (use_rng) {
         // the base draws are made in fp32 (their value is random); everything done with them is double
-        const A g1 = (A)sample_std_gamma<float>(*rng, (float)d.c1), g2 = (A)sample_std_gamma<float>(*rng, (float)d.c0);
+        const A g1 = (A)sample_std_gamma_f32(*rng, (float)d.c1), g2 = (A)sample_std_gamma_f32(*rng, (float)d.c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
     const A v = d.clamp(d.low + d.scale * variate, mc);
-    const BetaSite<A> q(v, d);
-    A bg1, bg0;
-    beta_grad_pair<A>(q.x01, d.c1, d.c0, bg1, bg0);
-    const A dv_dc1 = d.scale * (A(1) - q.x01) * bg1;
-    const A dv_dc0 = -d.scale * q.x01 * bg0;
-    const A km = size.v / d.scale * mean.d;                  // d c1 / d u_mean = - d c0 / d u_mean
-    const A k1 = (mean.v - d.low) / d.scale * size.d;        // d c1 / d u_size
-    const A k0 = (d.low + d.scale - mean.v) / d.scale * size.d;
-    rec[SO_LQ] = q.lp;
-    rec[SO_DQ] = q.d_v;
+    const A iscale = 1.0 / d.scale;
+    const A x01 = (v - d.low) * iscale, y01 = 1.0 - x01;
+    const A tot = d.c1 + d.c0;
+    const A boundary = tot * x01 * y01;
+    A lp, d_v, d_c1, d_c0, bg1, bg0;
+    if (d.c1 > 10.0 && d.c0 > 10.0 && !(boundary < 2.5)) {
+        // ---- usual regime: five logarithms, five reciprocals, shared by the density, its partials
+        // and the pair of Rice expansions (beta_grad_alpha_mid for (x, c1, c0) and (1-x, c0, c1))
+        const A lx = log(x01), ly = log(y01), lt = log(tot), l1 = log(d.c1), l0 = log(d.c0);
+        const A it = 1.0 / tot, i1 = 1.0 / d.c1, i0 = 1.0 / d.c0, ix = 1.0 / x01, iy = 1.0 / y01;
+        A lgt, pt, lg1, p1, lg0, p0;
+        lgamma_digamma_known(tot, lt, it, lgt, pt);
+        lgamma_digamma_known(d.c1, l1, i1, lg1, p1);
+        lgamma_digamma_known(d.c0, l0, i0, lg0, p0);
+        lp = (d.c1 - 1.0) * lx + (d.c0 - 1.0) * ly + lgt - lg1 - lg0 - log(d.scale);
+        d_v = ((d.c1 - 1.0) * ix - (d.c0 - 1.0) * iy) * iscale;
+        d_c1 = lx + pt - p1;
+        d_c0 = ly + pt - p0;
+        const A m1 = d.c1 * it;                                   // mean of x
+        const A sd = sqrt(d.c1 * d.c0 / (tot + 1.0)) * it;
+        if (m1 - 0.1 * sd <= x01 && x01 <= m1 + 0.1 * sd) {
+            // Taylor patches around x = mean (both calls hit theirs together: |y - mean_y| = |x - mean_x|)
+            bg1 = beta_grad_alpha_mid<A>(x01, d.c1, d.c0);
+            bg0 = beta_grad_alpha_mid<A>(y01, d.c0, d.c1);
+        } else {
+            const A r2 = 1.4142135623730950488;
+            const A sab = sqrt(d.c1 * d.c0 * it), isab = 1.0 / sab;
+            const A st1 = 1.0 + i1 * (1.0 / 12.0) + i1 * i1 * (1.0 / 288.0);
+            const A st0 = 1.0 + i0 * (1.0 / 12.0) + i0 * i0 * (1.0 / 288.0);
+            const A stt = 1.0 + it * (1.0 / 12.0) + it * it * (1.0 / 288.0);
+            const A stirling = st1 * st0 / stt;
+            const A axbx = d.c0 * x01 - d.c1 * y01;
+            const A iax = 1.0 / axbx;
+            const A rab = sqrt(d.c1 * i0), irab = sqrt(d.c0 * i1);  // sqrt(alpha/beta) and its inverse
+            const A i15 = iax * iax * it * sqrt(it) * (1.0 / r2);     // 1 / (sqrt2 total^1.5 axbx^2)
+            const A L1 = l1 - lt - lx, L0 = l0 - lt - ly;
+            const A t4b = d.c0 * L0 + d.c1 * L1;
+            const A t4 = 1.0 / (t4b * sqrt(t4b));
+            const A s8 = 2.8284271247461900976 * sab;
+            {
+                const A t1 = (-2.0 * d.c1 * d.c1 * y01 - d.c1 * d.c0 * y01 - x01 * d.c0 * d.c0) * (irab * i15);
+                const A t3 = s8 * iax;
+                bg1 = stirling * (-x01 * isab * (1.0 / r2)) * (t1 + 0.5 * L1 * (t3 + (x01 < m1 ? t4 : -t4)));
+            }
+            {
+                const A t1 = (-2.0 * d.c0 * d.c0 * x01 - d.c1 * d.c0 * x01 - y01 * d.c1 * d.c1) * (rab * i15);
+                const A t3 = -s8 * iax;
+                bg0 = stirling * (-y01 * isab * (1.0 / r2)) * (t1 + 0.5 * L0 * (t3 + (y01 < d.c0 * it ? t4 : -t4)));
+            }
+        }
+    } else {
+        const BetaSite<A> q(v, d);
+        lp = q.lp; d_v = q.d_v; d_c1 = q.d_c1; d_c0 = q.d_c0;
+        beta_grad_pair<A>(q.x01, d.c1, d.c0, bg1, bg0);
+    }
+    const A dv_dc1 = d.scale * y01 * bg1;
+    const A dv_dc0 = -d.scale * x01 * bg0;
+    const A km = size.v * iscale * mean.d;                   // d c1 / d u_mean = - d c0 / d u_mean
+    const A k1 = (mean.v - d.low) * iscale * size.d;         // d c1 / d u_size
+    const A k0 = (d.low + d.scale - mean.v) * iscale * size.d;
+    rec[SO_LQ] = lp;
+    rec[SO_DQ] = d_v;
     rec[SO_A0] = (dv_dc1 - dv_dc0) * km;
-    rec[SO_B0] = (q.d_c1 - q.d_c0) * km;
+    rec[SO_B0] = (d_c1 - d_c0) * km;
     rec[SO_A1] = dv_dc1 * k1 + dv_dc0 * k0;
-    rec[SO_B1] = q.d_c1 * k1 + q.d_c0 * k0;
+    rec[SO_B1] = d_c1 * k1 + d_c0 * k0;
     return v;
 }
 

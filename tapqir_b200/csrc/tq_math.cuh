@@ -146,6 +146,26 @@ TQ_HD void lgamma_digamma_large(double x, double& lg, double& psi) {
     p = p * z + 8.33333333333333333333E-2;
     psi = lx - 0.5 * ix - z * p;
 }
+// same with log(x) and 1/x supplied by the caller (x >= 10)
+TQ_HD void lgamma_digamma_known(double x, double lx, double ix, double& lg, double& psi) {
+    const double z = ix * ix;
+    double r = 6.41025641025641025641e-3;
+    r = 1.91752691752691752692e-3 - z * r;
+    r = 8.41750841750841750842e-4 - z * r;
+    r = 5.95238095238095238095e-4 - z * r;
+    r = 7.93650793650793650794e-4 - z * r;
+    r = 2.77777777777777777778e-3 - z * r;
+    r = 8.33333333333333333333e-2 - z * r;
+    lg = (x - 0.5) * lx - x + 0.91893853320467274178 + ix * r;
+    double p = 8.33333333333333333333E-2;
+    p = p * z + -2.10927960927960927961E-2;
+    p = p * z + 7.57575757575757575758E-3;
+    p = p * z + -4.16666666666666666667E-3;
+    p = p * z + 3.96825396825396825397E-3;
+    p = p * z + -8.33333333333333333333E-3;
+    p = p * z + 8.33333333333333333333E-2;
+    psi = lx - 0.5 * ix - z * p;
+}
 TQ_HD void lgamma_digamma(double x, double& lg, double& psi) {
     if (x > 10.0) { lgamma_digamma_large(x, lg, psi); return; }
     lg = lgamma_pos(x);
@@ -205,6 +225,26 @@ template <typename T> TQ_HD_NOINLINE T std_gamma_grad(T alpha, T x) {
     const T p = cv[0] + v * (cv[1] + v * (cv[2] + v * cv[3]));
     const T q = cv[4] + v * (cv[5] + v * (cv[6] + v * cv[7]));
     return R::exp(p / q);
+}
+
+// std_gamma_grad for alpha > 8, x >= 0.8 with lxa = log(x / alpha) and ia = 1 / alpha supplied
+// (the Rice expansion and its Taylor patch, same formulas as above)
+TQ_HD double std_gamma_grad_large(double alpha, double x, double lxa, double ia) {
+    if (0.9 * alpha <= x && x <= 1.1 * alpha) {
+        const double n1 = 1.0 + 24.0 * alpha * (1.0 + 12.0 * alpha);
+        const double n2 = 1440.0 * (alpha * alpha) + 6.0 * x * (53.0 - 120.0 * x) - 65.0 * x * x * ia + alpha * (107.0 + 3600.0 * x);
+        const double ia2 = ia * ia;
+        return n1 * n2 * (ia2 * ia2) * (1.0 / 1244160.0);
+    }
+    const double den = sqrt(8.0 * alpha);
+    const double iamx = 1.0 / (alpha - x);
+    const double t2 = den * iamx;
+    const double t3b = x - alpha - alpha * lxa;
+    const double t3 = 1.0 / (t3b * sqrt(t3b));
+    const double t23 = (x < alpha) ? t2 - t3 : t2 + t3;
+    const double t1 = lxa * t23 - sqrt(2.0 * ia) * (alpha + x) * (iamx * iamx);
+    const double stirling = 1.0 + ia * (1.0 / 12.0) * (1.0 + ia * (1.0 / 24.0));
+    return -stirling * (x * t1) / den;
 }
 
 // ---- scaled reparameterisation gradient of a Beta(alpha, total-alpha) draw x wrt alpha --------
@@ -410,6 +450,31 @@ struct Philox {
         return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
     }
 };
+
+// fp32 inline variant of the sampler below for the per-site kernels: inlining keeps the Philox state
+// in registers (the out-of-line generic version takes it by reference, i.e. through local memory).
+TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
+    float scale = 1.0f;
+    if (alpha < 1.0f) {
+        scale = powf((float)rng.uniform_d(), 1.0f / alpha);
+        alpha += 1.0f;
+    }
+    const float d = alpha - 1.0f / 3.0f;
+    const float c = 1.0f / sqrtf(9.0f * d);
+    for (int it = 0; it < 64; ++it) {
+        float xn, yv;
+        do {
+            xn = rng.normal();
+            yv = 1.0f + c * xn;
+        } while (yv <= 0.0f);
+        const float v = yv * yv * yv;
+        const float u = rng.uniform();
+        const float xx = xn * xn;
+        if (u < 1.0f - 0.0331f * xx * xx) return scale * d * v;
+        if (logf(u) < 0.5f * xx + d * (1.0f - v + logf(v))) return scale * d * v;
+    }
+    return scale * d;
+}
 
 // Marsaglia & Tsang (2000) standard gamma sampler (doi:10.1145/358407.358414), alpha > 0.
 template <typename T> TQ_HD_NOINLINE T sample_std_gamma(Philox& rng, T alpha) {
