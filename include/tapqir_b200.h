@@ -65,9 +65,9 @@ typedef struct {
 int tq_version(void);
 const char* tq_last_error(void);
 
-/* gaussian_spots (distributions/util.py:15-64).
+/* gaussian_spots (distributions/util.py:15-64) for U target locations with K spots each.
  * height,width,x,y: (K, U); target_xy: (U, 2); m: (K, U) or NULL; out: (U, K, P, P). */
-int tq_gaussian_spots(int dtype, int64_t U, int P, const void* height, const void* width,
+int tq_gaussian_spots(int dtype, int64_t U, int K, int P, const void* height, const void* width,
                       const void* x, const void* y, const void* target_xy, const void* m,
                       void* out, void* stream);
 

@@ -38,7 +38,7 @@ _VP = c_void_p
 SIGNATURES = {
     "tq_version": (c_int, []),
     "tq_last_error": (c_char_p, []),
-    "tq_gaussian_spots": (c_int, [c_int, c_int64, c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tq_gaussian_spots": (c_int, [c_int, c_int64, c_int, c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tq_ksmogn_fwd": (c_int, [c_int, POINTER(PatchView), _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_int, _VP, _VP]),
     "tq_ksmogn_fwd_bwd": (c_int, [c_int, POINTER(PatchView), _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_int, _VP,
                                    _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -399,17 +399,17 @@ static int check_view(const tq_patch_view* v) {
 
 // ---- gaussian_spots -----------------------------------------------------------------------------
 template <typename T>
-__global__ void gaussian_spots_kernel(int64_t U, int P, const T* __restrict__ height,
+__global__ void gaussian_spots_kernel(int64_t U, int K, int P, const T* __restrict__ height,
                                       const T* __restrict__ width, const T* __restrict__ x,
                                       const T* __restrict__ y, const T* __restrict__ target,
                                       const T* __restrict__ m, T* __restrict__ out) {
-    const int64_t total = U * kK * P * P;
+    const int64_t total = U * K * P * P;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int col = (int)(i % P);
         const int row = (int)((i / P) % P);
-        const int k = (int)((i / ((int64_t)P * P)) % kK);
-        const int64_t u = i / ((int64_t)P * P * kK);
+        const int k = (int)((i / ((int64_t)P * P)) % K);
+        const int64_t u = i / ((int64_t)P * P * K);
         const T w = width[k * U + u];
         T h = height[k * U + u];
         if (m) h *= m[k * U + u];
@@ -424,23 +424,23 @@ __global__ void gaussian_spots_kernel(int64_t U, int P, const T* __restrict__ he
 
 using namespace tq;
 
-extern "C" int tq_gaussian_spots(int dtype, int64_t U, int P, const void* height, const void* width,
+extern "C" int tq_gaussian_spots(int dtype, int64_t U, int K, int P, const void* height, const void* width,
                                  const void* x, const void* y, const void* target_xy, const void* m,
                                  void* out, void* stream) {
-    TQ_CHECK_ARG(U >= 0 && P >= 1, "bad shape");
+    TQ_CHECK_ARG(U >= 0 && P >= 1 && K >= 1, "bad shape");
     if (U == 0) return TQ_OK;
     TQ_CHECK_ARG(height && width && x && y && target_xy && out, "NULL pointer");
-    const int64_t total = U * kK * P * P;
+    const int64_t total = U * K * P * P;
     const int block = 256;
     int64_t grid = (total + block - 1) / block;
     const int64_t cap = (int64_t)sm_count() * 32;
     if (grid > cap) grid = cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TQ_F32)
-        gaussian_spots_kernel<float><<<(int)grid, block, 0, st>>>(U, P, (const float*)height, (const float*)width,
+        gaussian_spots_kernel<float><<<(int)grid, block, 0, st>>>(U, K, P, (const float*)height, (const float*)width,
             (const float*)x, (const float*)y, (const float*)target_xy, (const float*)m, (float*)out);
     else if (dtype == TQ_F64)
-        gaussian_spots_kernel<double><<<(int)grid, block, 0, st>>>(U, P, (const double*)height, (const double*)width,
+        gaussian_spots_kernel<double><<<(int)grid, block, 0, st>>>(U, K, P, (const double*)height, (const double*)width,
             (const double*)x, (const double*)y, (const double*)target_xy, (const double*)m, (double*)out);
     else { set_error("tq_gaussian_spots: bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("gaussian_spots_kernel launch");

@@ -19,28 +19,29 @@ def gaussian_spots(height, width, x, y, target_locs, P, m=None):
     .. math:: \mu^S_{i,j} = \frac{m\,h}{2\pi w^2}
               \exp\left(-\frac{(i-x-x^{target})^2 + (j-y-y^{target})^2}{2w^2}\right)
 
-    ``height, width, x, y`` broadcast to ``batch + (K,)``; ``target_locs`` to ``batch + (1, 2)``;
-    returns ``batch + (K, P, P)`` with x along the last axis.  Forward only (the differentiable
+    Same broadcasting as the reference: ``height, width, x, y`` (and ``m``) broadcast to a common
+    ``batch`` shape, ``target_locs`` to ``batch + (2,)``; returns ``batch + (P, P)`` with x along the
+    last axis (in the model ``batch = (N, F, C, K)`` with ``target_locs (N, F, C, 1, 2)``; the post-fit
+    statistics call it with ``batch = (K, F, Q)``, stats.py:65-72).  Forward only (the differentiable
     route is :class:`tapqir_b200.distributions.KSMOGN`); CUDA tensors only.
     """
     tensors = [height, width, x, y] + ([m] if m is not None else [])
     if any(t.requires_grad for t in tensors if isinstance(t, torch.Tensor)) and torch.is_grad_enabled():
         raise NotImplementedError("gaussian_spots is forward-only; differentiate through KSMOGN.log_prob")
     dtype = height.dtype
-    shape = torch.broadcast_shapes(*[t.shape for t in tensors], target_locs.shape[:-2] + (1,))
-    if shape[-1] != _lib.K:
-        raise ValueError(f"kernels are built for K={_lib.K} spots, got {shape[-1]}")
+    shape = torch.broadcast_shapes(*[t.shape for t in tensors], target_locs.shape[:-1])
     U = 1
-    for s in shape[:-1]:
+    for s in shape:
         U *= s
-    flat = lambda t: t.to(dtype).expand(shape).reshape(U, _lib.K).t().contiguous()
+    flat = lambda t: t.to(dtype).expand(shape).reshape(1, U).contiguous()
     h, w, xx, yy = flat(height), flat(width), flat(x), flat(y)
     mm = flat(m) if m is not None else None
-    tgt = target_locs.to(dtype).expand(shape[:-1] + (1, 2)).reshape(U, 2).contiguous()
-    out = torch.empty((U, _lib.K, P, P), dtype=dtype, device=height.device)
+    tgt = target_locs.to(dtype).expand(shape + (2,)).reshape(U, 2).contiguous()
+    out = torch.empty((U, 1, P, P), dtype=dtype, device=height.device)
     lib = _lib.load()
     with torch.cuda.device(height.device):
-        _lib.check(lib.tq_gaussian_spots(_lib.dtype_code(dtype), U, P, _lib.ptr(h), _lib.ptr(w), _lib.ptr(xx),
+        # every broadcast element is an independent "spot": K = 1 in the kernel's (K, U) layout
+        _lib.check(lib.tq_gaussian_spots(_lib.dtype_code(dtype), U, 1, P, _lib.ptr(h), _lib.ptr(w), _lib.ptr(xx),
                                          _lib.ptr(yy), _lib.ptr(tgt), _lib.ptr(mm), _lib.ptr(out),
                                          _lib.stream_ptr(height.device)), "tq_gaussian_spots")
     return out.reshape(shape + (P, P))

@@ -1,0 +1,144 @@
+"""
+Post-fit statistics with the reference's outputs (tapqir/utils/stats.py:29-293, row N2):
+credible intervals of every guide distribution, SNR and chi2 per patch, classification metrics
+against simulation labels, and the files ``<name>_params.tpqr`` / ``.mat`` / ``<name>_summary.csv``.
+
+Like the reference this is CPU post-processing (scipy inverse CDFs, sklearn metrics); the
+per-patch rendering goes through the CUDA ``gaussian_spots``.  The rastergram PNGs of
+stats.py:110-128 need matplotlib (not a dependency here) and are skipped, as the reference does
+when the ``CI`` environment variable is set.
+"""
+
+import logging
+from pathlib import Path
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from tapqir_b200.distributions.util import gaussian_spots
+
+logger = logging.getLogger(__name__)
+
+
+def quantile(samples: torch.Tensor, q: float) -> torch.Tensor:
+    """pyro.ops.stats.quantile [third party]: linear interpolation between order statistics."""
+    s, _ = samples.flatten().double().sort()
+    pos = q * (s.numel() - 1)
+    lo, hi = int(np.floor(pos)), int(np.ceil(pos))
+    return s[lo] + (s[hi] - s[lo]) * (pos - lo)
+
+
+def hpdi(samples: torch.Tensor, prob: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """pyro.ops.stats.hpdi [third party]: narrowest interval holding ``prob`` of the samples."""
+    s, _ = samples.flatten().double().sort()
+    n = s.numel()
+    mass = int(prob * n)
+    widths = s[mass:] - s[: n - mass]
+    i = int(torch.argmin(widths))
+    return s[i], s[i + mass]
+
+
+def snr_and_chi2(data, height, width, x, y, target_locs, background, gain, offset_mean, offset_var, P,
+                 theta_probs) -> Tuple[torch.Tensor, torch.Tensor]:
+    r"""
+    Signal-to-noise ratio and chi2 of the fitted spots (reference: stats.py:29-86).
+
+    .. math:: \text{SNR}_{knf} = \frac{\sum_{ij} (D_{nfij} - b_{nf} - \mu_{offset})\,\mathcal N_{ij}}
+              {\sqrt{\sigma^2_{offset} + b_{nf}\, g}}
+    """
+    gaussians = gaussian_spots(height, width, x, y, target_locs, P)
+    weights = gaussians / height[..., None, None]
+    signal = ((data - background[..., None, None] - offset_mean) * weights).sum(dim=(-2, -1))
+    noise = (offset_var + background * gain).sqrt()
+    # spots are stacked along the FIRST axis: (K, F, Q) per AOI in the reference (its sum(-5)), (K, n, F, Q) here
+    img_ideal = background[..., None, None] + gaussians.sum(0)
+    chi2 = (data - img_ideal - offset_mean) ** 2 / img_ideal
+    return signal / noise, chi2.mean(dim=(-1, -2))
+
+
+def save_stats(model, path, CI=0.95, save_matlab=False):
+    """Reference: stats.py:89-259."""
+    import pandas as pd
+    from sklearn.metrics import confusion_matrix, matthews_corrcoef, precision_score, recall_score
+
+    global_params = model._global_params
+    ll, ul = f"{int(100 * CI)}% LL", f"{int(100 * CI)}% UL"
+    summary = pd.DataFrame(index=global_params, columns=["Mean", ll, ul], dtype=object)
+    logger.info("- credible intervals & spot probabilities")
+    ci_stats = model.compute_params(CI)
+    for param in global_params:
+        scalar = ci_stats[param]["Mean"].ndim == 0
+        for col, key in (("Mean", "Mean"), (ll, "LL"), (ul, "UL")):
+            summary.loc[param, col] = ci_stats[param][key].item() if scalar else ci_stats[param][key].tolist()
+
+    theta_mask = ci_stats["theta_probs"] > 0.5
+    hmax = np.percentile(ci_stats["height"]["Mean"][theta_mask], 99) if theta_mask.sum() else 1
+    ci_stats["height"]["vmin"], ci_stats["height"]["vmax"] = -0.03 * hmax, 1.3 * hmax
+    ci_stats["width"]["vmin"], ci_stats["width"]["vmax"] = 0.5, 2.5
+    ci_stats["x"]["vmin"], ci_stats["x"]["vmax"] = -9, 9
+    ci_stats["y"]["vmin"], ci_stats["y"]["vmax"] = -9, 9
+    bmax = np.percentile(ci_stats["background"]["Mean"].flatten(), 99)
+    ci_stats["background"]["vmin"], ci_stats["background"]["vmax"] = -0.03 * bmax, 1.3 * bmax
+    if model.data.time1 is not None:
+        ci_stats["time1"] = model.data.time1
+    if model.data.ttb is not None:
+        ci_stats["ttb"] = model.data.ttb
+    model.params = ci_stats
+
+    logger.info("- SNR and Chi2-test")
+    data, dev = model.data, model.device
+    Nt, F, Q, K = data.Nt, data.F, model.Q, model.K
+    snr = torch.zeros(K, Nt, F, Q)
+    chi2 = torch.zeros(Nt, F, Q)
+    to = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32)
+    chunk = max(1, (1 << 22) // max(F * Q * K, 1))
+    for lo in range(0, Nt, chunk):  # AOI blocks instead of the reference's per-AOI Python loop
+        sl = slice(lo, min(lo + chunk, Nt))
+        s, c = snr_and_chi2(
+            to(data.images[sl]), to(ci_stats["height"]["Mean"][:, sl]), to(ci_stats["width"]["Mean"][:, sl]),
+            to(ci_stats["x"]["Mean"][:, sl]), to(ci_stats["y"]["Mean"][:, sl]), to(data.xy[sl]),
+            to(ci_stats["background"]["Mean"][sl]), float(ci_stats["gain"]["Mean"]), data.offset.mean, data.offset.var,
+            data.P, None)
+        snr[:, sl], chi2[sl] = s.cpu(), c.cpu()
+    for q in range(Q):
+        masked = snr[..., q][ci_stats["theta_probs"][..., q] > 0.5]
+        summary.loc[f"SNR_{q}", "Mean"] = masked.mean().item() if masked.numel() else float("nan")
+    cmax = quantile(chi2, 0.99).item()
+    ci_stats["chi2"] = {"values": chi2, "vmin": -0.03 * cmax, "vmax": 1.3 * cmax}
+
+    if data.labels is not None:
+        pred = model.z_map[data.is_ontarget].cpu().numpy().ravel()
+        true = data.labels["z"][: data.N].ravel()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            summary.loc["MCC", "Mean"] = matthews_corrcoef(true, pred)
+        summary.loc["Recall", "Mean"] = recall_score(true, pred, zero_division=0)
+        summary.loc["Precision", "Mean"] = precision_score(true, pred, zero_division=0)
+        (summary.loc["TN", "Mean"], summary.loc["FP", "Mean"], summary.loc["FN", "Mean"],
+         summary.loc["TP", "Mean"]) = confusion_matrix(true, pred, labels=(0, 1)).ravel()
+        mask = torch.from_numpy(data.labels["z"][: data.N]) > 0
+        samples = torch.masked_select(model.z_probs[data.is_ontarget].argmax(dim=-1).cpu(), mask)
+        if len(samples):
+            z_ll, z_ul = hpdi(samples, CI)
+            summary.loc["p(specific)", "Mean"] = quantile(samples, 0.5).item()
+            summary.loc["p(specific)", ll], summary.loc["p(specific)", ul] = z_ll.item(), z_ul.item()
+        else:
+            summary.loc["p(specific)", ["Mean", ll, ul]] = 0.0
+    model.summary = summary
+
+    if path is not None:
+        path = Path(path)
+        torch.save(ci_stats, path / f"{model.name}_params.tpqr")
+        logger.info(f"Parameters were saved in {path / f'{model.name}_params.tpqr'}")
+        if save_matlab:
+            from scipy.io import savemat
+
+            mat = {}
+            for param, field in ci_stats.items():
+                if isinstance(field, dict):
+                    mat[param] = {k: np.asarray(v) for k, v in field.items()}
+                else:
+                    mat[param] = np.asarray(field)
+            savemat(path / f"{model.name}_params.mat", mat)
+        summary.to_csv(path / f"{model.name}_summary.csv")
+        logger.info(f"Summary statistics were saved in {path / f'{model.name}_summary.csv'}")

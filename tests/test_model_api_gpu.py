@@ -102,3 +102,68 @@ def test_minibatch_run_with_device_subsampling(dataset_path):
     fdx = model.engine.fdx.cpu()
     assert len(set(fdx.tolist())) == 16 and fdx.max() < 40
     assert (model.engine.lparams != before).float().mean().item() > 0.9   # dense update: (almost) every entry moved
+
+
+def test_compute_stats_writes_reference_files(dataset_path):
+    """Row N2: compute_stats -> cosmos_params.tpqr / .mat / cosmos_summary.csv with the reference's
+    keys and shapes (stats.py:131-258, cosmos.py:711-784), as `tapqir stats --matlab` does."""
+    import pandas as pd
+    import scipy.stats as st
+
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    save(simulate(4, 30, seed=2), dataset_path)
+    model = models["cosmos"](device="cuda")
+    model.load(dataset_path)
+    model.init(nbatch_size=4, fbatch_size=30)
+    model.run(50, progress_bar=lambda it: it)
+    model.compute_stats(CI=0.95, save_matlab=True)
+    params = torch.load(dataset_path / "cosmos_params.tpqr", weights_only=False)
+    Nt, F, K, Q = 4, 30, 2, 1
+    for name, shape in (("gain", ()), ("pi", (Q, 2)), ("lamda", (Q,)), ("proximity", ()), ("background", (Nt, F, Q)),
+                        ("height", (K, Nt, F, Q)), ("width", (K, Nt, F, Q)), ("x", (K, Nt, F, Q)), ("y", (K, Nt, F, Q))):
+        assert set(params[name]) >= {"LL", "UL", "Mean"}
+        for key in ("LL", "UL", "Mean"):
+            assert tuple(params[name][key].shape) == shape, (name, key)
+        assert (params[name]["LL"] <= params[name]["Mean"]).all() and (params[name]["Mean"] <= params[name]["UL"]).all()
+    assert params["m_probs"].shape == (K, Nt, F, Q) and params["z_probs"].shape == (Nt, F, Q, 2)
+    assert params["theta_probs"].shape == (K, Nt, F, Q) and params["z_map"].shape == (Nt, F, Q)
+    assert torch.allclose(params["p_specific"], params["theta_probs"].sum(0))
+    assert params["chi2"]["values"].shape == (Nt, F, Q) and {"vmin", "vmax"} <= set(params["height"])
+    # interval of one Gamma site against scipy directly
+    loc, beta = model.param("gain_loc").item(), model.param("gain_beta").item()
+    lo, hi = st.gamma(loc * beta, scale=1 / beta).interval(0.95)
+    assert abs(params["gain"]["LL"].item() - lo) < 1e-9 and abs(params["gain"]["UL"].item() - hi) < 1e-9
+    summary = pd.read_csv(dataset_path / "cosmos_summary.csv", index_col=0)
+    assert list(summary.columns) == ["Mean", "95% LL", "95% UL"]
+    assert {"gain", "proximity", "lamda", "pi", "SNR_0", "MCC", "Recall", "Precision", "TN", "FP", "FN", "TP",
+            "p(specific)"} <= set(summary.index)
+    assert (dataset_path / "cosmos_params.mat").exists()
+    # load(data_only=False) picks both files up (model.py:108-126)
+    again = models["cosmos"](device="cuda")
+    again.load(dataset_path, data_only=False)
+    assert "z_probs" in again.params and "gain" in again.summary.index
+
+
+def test_snr_and_chi2_matches_formula():
+    from tapqir_b200.utils.stats import snr_and_chi2
+
+    g = torch.Generator().manual_seed(0)
+    K, F, Q, P = 2, 5, 1, 14
+    r = lambda *s: torch.rand(*s, generator=g)
+    h, w, x, y = 1000 + 2000 * r(K, F, Q), 1.2 + r(K, F, Q), 2 * r(K, F, Q) - 1, 2 * r(K, F, Q) - 1
+    tgt = torch.full((F, Q, 2), 6.5)
+    b = 100 + 50 * r(F, Q)
+    data = 200 + 100 * r(F, Q, P, P)
+    snr, chi2 = snr_and_chi2(data.cuda(), h.cuda(), w.cuda(), x.cuda(), y.cuda(), tgt.cuda(), b.cuda(), 7.0, 90.0, 0.0, P, None)
+    from oracle import cosmos_oracle as O
+
+    ga = O.gaussian_spots(h.double()[..., None], w.double()[..., None], x.double()[..., None], y.double()[..., None],
+                          tgt.double()[None, :, :, None, :], P)[..., 0, :, :]   # (K,F,Q,P,P)
+    sig = ((data.double() - b.double()[..., None, None] - 90.0) * (ga / h.double()[..., None, None])).sum((-1, -2))
+    ref_snr = sig / (0.0 + b.double() * 7.0).sqrt()
+    ideal = b.double()[..., None, None] + ga.sum(0)
+    ref_chi2 = ((data.double() - ideal - 90.0) ** 2 / ideal).mean((-1, -2))
+    assert torch.allclose(snr.double().cpu(), ref_snr, rtol=1e-4) and torch.allclose(chi2.double().cpu(), ref_chi2, rtol=1e-4)
