@@ -1,0 +1,239 @@
+// Production (fp32) form of site_eval (cosmos_local.cuh): the same quantities -- guide sample, log q,
+// d log q / d sample and the linear maps A_p, B_p of the reparameterised gradient -- evaluated in
+// single precision without the cancellations that make the textbook formulas need double.
+//
+// The reference reaches these through torch (Gamma/Beta rsample -> ATen _standard_gamma_grad /
+// _dirichlet_grad, log_prob -> lgamma/digamma; models/cosmos.py:408-462, affine_beta.py:33-49).  All
+// of their ill-conditioned pieces are functions of ONE small quantity per site:
+//
+//   Gamma(conc, rate) draw x (standard variate):      u  = x / conc - 1
+//   Beta(c1, c0) draw x, mean m1 = c1 / (c1 + c0):     ua = (x - m1) / m1,   ub = -(x - m1) / m0
+//
+// u / ua are formed in DOUBLE (one exp and one fused multiply-add from the fp32 parameters); everything
+// after that is fp32 on (l, f) = (log1p(u), u - log1p(u)) and on the "small parts"
+// A = l/u - 1, F = 2 f/u^2 - 1, which an atanh series gives to full relative accuracy:
+//
+//   lgamma(a+b) - lgamma(a) - lgamma(b) + (a-1) log x + (b-1) log(1-x)
+//        = -(c1 fa + c0 fb) - log x - log(1-x) + (log c1 + log c0 - log tot)/2 - ln(2 pi)/2 + r(tot) - r(c1) - r(c0)
+//   psi(tot) - psi(c1) + log x  = la + q(c1) - q(tot)                  (r, q: Stirling remainders)
+//   Rice expansion of d x / d alpha (ATen, alpha > 8):   stirling (1 + u) [ l/u - H(u)/alpha ]
+//   Rice expansion of the Beta gradient (ATen, both > 6): stirling (x / c1) [ la/ua - (m1 m0 / tot) B / d^2 ]
+//
+// (H, B collect the terms that cancel to second order in ATen's form; tests/test_hostcheck_sites.py
+// pins every output of this file against site_eval in double over all regimes.)  Outside the regimes
+// handled here (tiny concentrations, samples on the clamps, ...) site_eval_fast returns false and the
+// caller runs the double-precision site_eval.
+#pragma once
+#include "cosmos_local.cuh"
+
+namespace tq {
+
+constexpr float kSiteHalfLn2Pi = 0.91893853320467274178f;
+
+// l = log1p(u), f = u - l, A = l/u - 1, F = 2 f / u^2 - 1, for u > -1; r = 1 + u rounded from its own
+// (double) evaluation, so that l keeps its accuracy when u is close to -1
+struct Lp1 { float l, f, A, F; };
+
+TQ_HD Lp1 lp1_parts(float u, float r) {
+    Lp1 o;
+    if (fabsf(u) <= 0.4f) {
+        // log1p(u) = 2 atanh(s), s = u / (2 + u);  u - 2 s = s u
+        const float inv = 1.0f / (2.0f + u);
+        const float s = u * inv, z = s * s;
+        const float P = 0.333333333f + z * (0.2f + z * (0.142857143f + z * (0.111111111f + z * (0.0909090909f + z * 0.0769230769f))));
+        const float R = z * P;
+        o.l = fmaf(2.0f * s, R, 2.0f * s);
+        o.f = s * (u - 2.0f * R);
+        o.A = (2.0f * R - u) * inv;
+        o.F = -(4.0f * (u * inv * inv * P) + u) * inv;
+    } else {
+        o.l = logf(r);
+        o.f = u - o.l;
+        o.A = o.l / u - 1.0f;
+        o.F = 2.0f * o.f / (u * u) - 1.0f;
+    }
+    return o;
+}
+
+// Stirling remainders for z >= 10 from iz = 1/z:
+//   lgamma(z) = (z - 1/2) ln z - z + ln(2 pi)/2 + r(z),   psi(z) = ln z - q(z)
+TQ_HD float stirling_r(float iz) { const float z2 = iz * iz; return iz * (0.0833333333f - z2 * (0.00277777778f - z2 * 0.000793650794f)); }
+TQ_HD float stirling_q(float iz) { const float z2 = iz * iz; return iz * (0.5f + iz * (0.0833333333f - z2 * (0.00833333333f - z2 * 0.00396825397f))); }
+
+// d x / d alpha of a standard Gamma(alpha) draw x = alpha (1 + u), alpha > 8, x >= 0.8: ATen's Rice
+// expansion and its Taylor patch, returned as  sgg  and  sgg - (1 + u)  (the latter without cancellation)
+TQ_HD void gamma_grad_rice(float alpha, float ia, float u, const Lp1& p, float& sgg, float& sgg_m1u) {
+    const float st = ia * (0.0833333333f + ia * 0.00347222222f);   // stirling - 1
+    if (fabsf(u) <= 0.1f) {
+        // n1 n2 / den = (1 + st) (1 + P),  P = u/2 - u^2/6 + (360 + 188 u - 65 u^2) / (4320 alpha)
+        const float c = (360.0f + u * (188.0f - 65.0f * u)) * (ia * (1.0f / 4320.0f));
+        const float Pm = -u * (0.5f + u * 0.166666667f) + c;   // P - u
+        const float P = Pm + u;
+        sgg_m1u = st + Pm + st * P;
+        sgg = 1.0f + u + sgg_m1u;
+        return;
+    }
+    // H(u) = [ (l/u) g^(-3/2) - (1 + u/2) ] / u^2,  g = 2 f / u^2
+    const float E = expm1f(-1.5f * log1pf(p.F));               // g^(-3/2) - 1
+    const float B = p.A + E + p.A * E - 0.5f * u;
+    const float H = B / (u * u);
+    const float inner = p.A - H * ia;                             // l/u - H/alpha - 1
+    sgg_m1u = (1.0f + u) * (st + inner + st * inner);             // (1+u)(1+st)(1+inner) - (1+u)
+    sgg = (1.0f + u) + sgg_m1u;
+}
+
+// Numerator polynomial of the Taylor patch of ATen's Beta gradient around x = mean
+// (beta_grad_alpha_mid, tq_math.cuh):  grad = pn / (1 - x) * poly / pd.  Evaluated in double because the
+// size gradient needs poly(x, a, b) - poly(1 - x, b, a), which cancels to first order.
+TQ_HD double beta_patch_poly(double x, double alpha, double beta) {
+    const double b2 = beta * beta;
+    return 47.0 * x * b2 * b2 + alpha * (
+               (43.0 + 20.0 * (16.0 + 27.0 * beta) * x) * b2 * beta + alpha * (
+               3.0 * (59.0 + 180.0 * beta - 90.0 * x) * b2 + alpha * (
+               (453.0 + 1620.0 * beta * (1.0 - x) - 455.0 * x) * beta + alpha * (
+               8.0 * (1.0 - x) * (135.0 * beta - 11.0)))));
+}
+
+// log-density of v ~ Gamma(conc, rate) and its partials from x = rate v = conc (1 + u):
+//   lp, d_v, and the two combinations the site maps need:  conc * d_conc  and  conc * d_conc + rate * d_rate
+TQ_HD void gamma_density_fast(float conc, float lconc, float lrate, float rate, float x, float u, const Lp1& p,
+                              float& lp, float& d_v, float& cdc, float& cdc_rdr) {
+    const float lx = lconc + p.l;
+    d_v = rate * (-fmaf(conc, u, 1.0f)) / x;                      // (conc - 1)/v - rate
+    if (conc > 10.0f) {
+        const float ic = 1.0f / conc;
+        const float q = stirling_q(ic);
+        lp = lrate - lx - conc * p.f + 0.5f * lconc - kSiteHalfLn2Pi - stirling_r(ic);
+        cdc = conc * (p.l + q);                                     // conc (lx - psi(conc))
+        cdc_rdr = conc * (q - p.f);                                 // ... + (conc - x)
+    } else {
+        const float psi = digamma<float>(conc);
+        lp = lrate - lx + conc * lx - x - lgammaf(conc);
+        cdc = conc * (lx - psi);
+        cdc_rdr = cdc - conc * u;
+    }
+}
+
+// Same arguments and outputs as site_eval, with float records.  Returns SITE_DONE, or -- when the site is
+// outside the regimes handled in fp32 -- SITE_FALLBACK (variate holds the base draw: call site_eval in
+// replay mode) or SITE_FALLBACK_DRAW (nothing drawn yet: call site_eval as is).
+enum { SITE_DONE = 0, SITE_FALLBACK = 1, SITE_FALLBACK_DRAW = 2 };
+TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
+                         Philox* rng, double& variate, float& sample, float* rec, float* extra) {
+    if (!(mc.eps < 1e-12)) return SITE_FALLBACK_DRAW;   // fp32 reference conventions move the clamps into range
+    if (site_is_gamma(s)) {
+        // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
+        const float lconc = u0 + u1;
+        if (!(lconc > -4.0f && lconc < 13.0f) || fabsf(u1) > 40.0f) return SITE_FALLBACK_DRAW;
+        const double ed = exp(-((double)u0 + (double)u1));         // 1 / conc
+        const float ic = (float)ed, conc = 1.0f / ic;
+        if (use_rng) variate = fmax((double)sample_std_gamma_f32(*rng, conc), mc.tiny);
+        const double xd = variate;
+        if (!(xd > 1e-18) || !(xd < 1e18)) return SITE_FALLBACK;
+        const double rd = xd * ed;                                 // x / conc
+        const float u = (float)(rd - 1.0);
+        const float x = (float)xd;
+        if (x < 0.8f && conc > 30.0f) return SITE_FALLBACK;        // Taylor regime far in the tail: powers underflow in fp32
+        const float ibeta = expf(-u1), beta = 1.0f / ibeta, loc = conc * ibeta;
+        const float v = x * ibeta;
+        const Lp1 p = lp1_parts(u, (float)rd);
+        float lp, d_v, cdc, cdc_rdr;
+        gamma_density_fast(conc, lconc, u1, beta, x, u, p, lp, d_v, cdc, cdc_rdr);
+        float sgg, sgg_m1u;
+        if (x >= 0.8f && conc > 8.0f) {
+            gamma_grad_rice(conc, ic, u, p, sgg, sgg_m1u);
+        } else {
+            sgg = std_gamma_grad<float>(conc, x);
+            sgg_m1u = sgg - (1.0f + u);
+        }
+        if (s == S_B) {
+            // model prior Gamma(pc, pr), pc = (bm/bs)^2, pr = bm/bs^2 at the same v: pr v / pc = v / bm   cosmos.py:233-239
+            const float lpc = 2.0f * (ubm - ubs), lpr = ubm - 2.0f * ubs;
+            if (!(lpc > -4.0f && lpc < 13.0f) || fabsf(lpr) > 40.0f) return SITE_FALLBACK;
+            const double rpd = xd * exp(-((double)u1 + (double)ubm));
+            const float up = (float)(rpd - 1.0);
+            if (!(up > -1.0f)) return SITE_FALLBACK;
+            const float pc = expf(lpc), pr = expf(lpr);
+            const Lp1 pp = lp1_parts(up, (float)rpd);
+            float plp, pd_v, pcdc, pcdc_rdr;
+            gamma_density_fast(pc, lpc, lpr, pr, pr * v, up, pp, plp, pd_v, pcdc, pcdc_rdr);
+            extra[EX_LP] = plp;
+            extra[EX_DP] = pd_v;
+            // d pc / d u_bm = 2 pc, d pr / d u_bm = pr;  d pc / d u_bs = -2 pc, d pr / d u_bs = -2 pr
+            extra[EX_GBM] = pcdc + pcdc_rdr;
+            extra[EX_GBS] = -2.0f * pcdc_rdr;
+        }
+        sample = v;
+        rec[SO_LQ] = lp;
+        rec[SO_DQ] = d_v;
+        rec[SO_A0] = sgg * loc;
+        rec[SO_A1] = sgg_m1u * loc;                                 // sgg loc - v,  v = loc (1 + u)
+        rec[SO_B0] = cdc;
+        rec[SO_B1] = cdc_rdr;
+        return SITE_DONE;
+    }
+    // AffineBeta(mean, size, lo, hi): width cosmos.py:436-444, x :445-453, y :454-462
+    double lod, hid;
+    if (s < S_X) { lod = mc.width_min; hid = mc.width_max; } else { hid = 0.5 * (double)(mc.P + 1); lod = -hid; }
+    const float scale = (float)(hid - lod);
+    if (fabsf(u0) > 15.0f || !(u1 < 11.5f)) return SITE_FALLBACK_DRAW;
+    const double ed = exp(-(double)u0);                           // m1 = 1 / (1 + e), m0 = e m1
+    const float e = (float)ed;
+    const float m1 = 1.0f / (1.0f + e), m0 = e * m1;
+    const float sz = expf(u1), S = 2.0f + sz;                     // size - 2 = d size / d u, size
+    const float c1 = S * m1, c0 = S * m0;
+    if (!(c1 > 10.0f && c0 > 10.0f)) return SITE_FALLBACK_DRAW;
+    if (use_rng) {
+        const double g1 = (double)sample_std_gamma_f32(*rng, c1), g2 = (double)sample_std_gamma_f32(*rng, c0);
+        variate = beta01_from_gammas(g1, g2, mc);
+    }
+    const double x01d = variate;   // (v - low) / scale of the reference, to rounding
+    const float ua = (float)fma(x01d, ed, x01d - 1.0);            // (x - m1) / m1
+    const float x = (float)x01d, y = (float)(1.0 - x01d);
+    const float ub = -ua / e;                                     // -(x - m1) / m0
+    if (!(S * x * y >= 2.5f) || !(ua > -1.0f) || !(ub > -1.0f)) return SITE_FALLBACK;
+    const float d = ua * m1;                                      // x - m1
+    const Lp1 pa = lp1_parts(ua, x / m1), pb = lp1_parts(ub, y / m0);
+    const float i1 = 1.0f / c1, i0 = 1.0f / c0, it = 1.0f / S;
+    const float q1 = stirling_q(i1), q0 = stirling_q(i0), qt = stirling_q(it);
+    const float lm1 = -log1pf(e), lm0 = lm1 - u0;                 // log m1, log m0
+    const float lt = logf(S);
+    const float kl = m1 * pa.f + m0 * pb.f;                       // S kl = c1 log(m1/x) + c0 log(m0/y) >= 0
+    const float lp = -S * kl - (lm1 + pa.l) - (lm0 + pb.l) + 0.5f * (lt + lm1 + lm0) - kSiteHalfLn2Pi
+                     + stirling_r(it) - stirling_r(i1) - stirling_r(i0) - logf(scale);
+    const float d_v = (-S * d + (x - y)) / (x * y * scale);
+    const float d_c1 = pa.l + q1 - qt, d_c0 = pb.l + q0 - qt;
+    const float mm = m1 * m0;
+    float A0, A1;
+    if (d * d <= 0.01f * mm / (S + 1.0f)) {
+        // y bg1 = K P1 / c1,  x bg0 = K P0 / c0,  K = pn / (12960 c1^2 c0^2 (1 + 12 S))
+        const double P1 = beta_patch_poly(x01d, (double)c1, (double)c0), P0 = beta_patch_poly(1.0 - x01d, (double)c0, (double)c1);
+        const float pn = (1.0f + 12.0f * c1) * (1.0f + 12.0f * c0) * (it * it);
+        const float K = pn / (12960.0f * (c1 * c1) * (c0 * c0) * (1.0f + 12.0f * S));
+        A0 = scale * K * ((float)P1 * m0 + (float)P0 * m1);
+        A1 = scale * sz * it * K * (float)(P1 - P0);
+    } else {
+        const float Gs = m0 * pa.F + m1 * pb.F;                   // 2 m1 m0 kl / d^2 - 1
+        const float E = expm1f(-1.5f * log1pf(Gs));
+        const float h = d / (2.0f * mm);
+        const float Ba = pa.A + E + pa.A * E - h * (m0 - 2.0f * m1);
+        const float Bb = pb.A + E + pb.A * E + h * (m1 - 2.0f * m0);
+        const float w = mm / (S * d * d);
+        const float ta = pa.A - w * Ba, tb = pb.A - w * Bb;      // bg1 = stir (x/c1) (1 + ta), bg0 = stir (y/c0) (1 + tb)
+        const float stir = (1.0f + i1 * (0.0833333333f + i1 * 0.00347222222f)) * (1.0f + i0 * (0.0833333333f + i0 * 0.00347222222f))
+                         / (1.0f + it * (0.0833333333f + it * 0.00347222222f));
+        const float sxy = scale * stir * x * y;
+        A0 = sxy * (m0 * (1.0f + ta) + m1 * (1.0f + tb));
+        A1 = sxy * sz * it * (ta - tb);
+    }
+    sample = (float)(lod + (hid - lod) * variate);
+    rec[SO_LQ] = lp;
+    rec[SO_DQ] = d_v;
+    rec[SO_A0] = A0;
+    rec[SO_A1] = A1;
+    rec[SO_B0] = S * mm * (d_c1 - d_c0);
+    rec[SO_B1] = sz * (m1 * q1 + m0 * q0 - qt - kl);
+    return SITE_DONE;
+}
+
+}  // namespace tq

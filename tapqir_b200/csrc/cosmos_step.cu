@@ -9,6 +9,7 @@
 // tests/hostcheck); this file is gather/scatter, reductions and launch plumbing.
 #include "common.cuh"
 #include "cosmos_globals.cuh"
+#include "cosmos_sites_fast.cuh"
 
 namespace tq {
 
@@ -100,25 +101,38 @@ __global__ void __launch_bounds__(kLocalBlock) site_kernel(const LocalArgs<T> a)
     const int64_t u = t - (int64_t)s * a.U;
     const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
     const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
-    const double u0 = (double)a.lparams[a.lo.index(site_param0(s), ui.aoi, f, ui.c)];
-    const double u1 = (double)a.lparams[a.lo.index(site_param1(s), ui.aoi, f, ui.c)];
-    double ubm = 0.0, ubs = 0.0;
+    const T p0 = a.lparams[a.lo.index(site_param0(s), ui.aoi, f, ui.c)];
+    const T p1 = a.lparams[a.lo.index(site_param1(s), ui.aoi, f, ui.c)];
+    T pbm = T(0), pbs = T(0);
     if (s == S_B) {
-        ubm = (double)a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)];
-        ubs = (double)a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
+        pbm = a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)];
+        pbs = a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
     }
-    const bool use_rng = a.noise_in == nullptr;
+    bool use_rng = a.noise_in == nullptr;
     const unsigned long long gid = (((unsigned long long)(a.aoi_offset + ui.aoi)) * a.v.F + f) * a.v.C + ui.c;
     Philox rng(a.seed, a.state->step, ((gid + 1ull) << 12) + ((unsigned long long)s << 8));
     double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u];
-    double rec[NSO], extra[NEX];
-    const double v = site_eval(s, u0, u1, ubm, ubs, a.mc, use_rng, &rng, variate, rec, extra);
-    a.samples[(int64_t)s * a.U + u] = (T)v;
+    T v, rec[NSO], extra[NEX];
+    int status = SITE_FALLBACK_DRAW;
+    if constexpr (sizeof(T) == sizeof(float)) {
+        // production: fp32 forms of cosmos_sites_fast.cuh; the double form only outside their regimes
+        status = site_eval_fast(s, p0, p1, pbm, pbs, a.mc, use_rng, &rng, variate, v, rec, extra);
+    }
+    if (status != SITE_DONE) {
+        double drec[NSO], dextra[NEX];
+        v = (T)site_eval(s, (double)p0, (double)p1, (double)pbm, (double)pbs, a.mc, use_rng && status == SITE_FALLBACK_DRAW,
+                         &rng, variate, drec, dextra);
 #pragma unroll
-    for (int j = 0; j < NSO; ++j) a.rec[((int64_t)s * NSO + j) * a.U + u] = (T)rec[j];
+        for (int j = 0; j < NSO; ++j) rec[j] = (T)drec[j];
+#pragma unroll
+        for (int j = 0; j < NEX; ++j) extra[j] = (T)dextra[j];
+    }
+    a.samples[(int64_t)s * a.U + u] = v;
+#pragma unroll
+    for (int j = 0; j < NSO; ++j) a.rec[((int64_t)s * NSO + j) * a.U + u] = rec[j];
     if (s == S_B) {
 #pragma unroll
-        for (int j = 0; j < NEX; ++j) a.rec[((int64_t)NSAMP * NSO + j) * a.U + u] = (T)extra[j];
+        for (int j = 0; j < NEX; ++j) a.rec[((int64_t)NSAMP * NSO + j) * a.U + u] = extra[j];
         // weights of the likelihood kernel: q(m) from the unconstrained m_probs
         T q1[kK], q0[kK], qm[kM];
 #pragma unroll
@@ -228,30 +242,31 @@ __global__ void reduce_acc_kernel(const double* __restrict__ block_partial, int 
 }
 
 // d loss / d (background_mean_loc, background_std_loc)[n, 0, c]: sum over the minibatch frames of the
-// per-unit contributions + the AOI-level prior; one warp per (ni, c)
+// per-unit contributions + the AOI-level prior; one 128-thread block per (ni, c), fixed-order tree
 template <typename T>
-__global__ void reduce_aoi_kernel(const LocalArgs<T> a) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int nb = a.v.nb, fb = a.v.fb, C = a.v.C;
-    if (warp >= (int64_t)nb * C) return;
-    const int ni = (int)(warp / C), c = (int)(warp - (int64_t)ni * C);
+__global__ void __launch_bounds__(128) reduce_aoi_kernel(const LocalArgs<T> a) {
+    __shared__ double red[2][4];
+    const int fb = a.v.fb, C = a.v.C;
+    const int ni = blockIdx.x / C, c = blockIdx.x - ni * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double sbm = 0.0, sbs = 0.0;
-    for (int fi = lane; fi < fb; fi += 32) {
+    for (int fi = threadIdx.x; fi < fb; fi += blockDim.x) {
         const int64_t u = ((int64_t)ni * fb + fi) * C + c;
         sbm += a.aoi_partial[u];
         sbs += a.aoi_partial[a.U + u];
     }
     sbm = warp_sum(sbm);
     sbs = warp_sum(sbs);
-    if (lane == 0) {
+    if (lane == 0) { red[0][warp] = sbm; red[1][warp] = sbs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sbm = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+        sbs = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
         const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
         const double mu = a.v.mask[n] ? 1.0 : 0.0;
         const int64_t ibm = a.lo.index(LP_BM, n, 0, c), ibs = a.lo.index(LP_BS, n, 0, c);
-        const Transformed<double> bm = t_positive<double>((double)a.lparams[ibm]);
-        const Transformed<double> bs = t_positive<double>((double)a.lparams[ibs]);
-        const double s1 = a.mc.bg_mean_std, s2 = a.mc.bg_std_std;
-        const double pbm = -bm.v / (s1 * s1) * bm.d, pbs = -bs.v / (s2 * s2) * bs.d;
+        double pbm, pbs;
+        aoi_prior_grad((double)a.lparams[ibm], (double)a.lparams[ibs], a.mc, pbm, pbs);
         a.lgrads[ibm] = (T)(-(a.sN * a.sF * sbm + a.sN * mu * pbm));
         a.lgrads[ibs] = (T)(-(a.sN * a.sF * sbs + a.sN * mu * pbs));
     }
@@ -408,8 +423,7 @@ static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelCons
     if (a.U > 0) {
         local_post_kernel<T><<<nblocks, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("local_post_kernel launch");
-        const int64_t warps = (int64_t)view->nb * view->C;
-        reduce_aoi_kernel<T><<<(int)((warps * 32 + 127) / 128), 128, 0, st>>>(a);
+        reduce_aoi_kernel<T><<<view->nb * view->C, 128, 0, st>>>(a);
         TQ_LAUNCH_CHECK("reduce_aoi_kernel launch");
     }
     const int rw = view->C * NACC;

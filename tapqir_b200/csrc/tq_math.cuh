@@ -447,7 +447,14 @@ struct Philox {
     }
     TQ_HD float normal() {  // Box-Muller, one value per call (the partner is discarded)
         const float u1 = uniform(), u2 = uniform();
+#ifdef __CUDA_ARCH__
+        // MUFU forms (lg2 / sqrt / cos): absolute errors ~1e-6, irrelevant for a random draw
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+        return r * __cosf(6.283185307179586f * u2);
+#else
         return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+#endif
     }
 };
 

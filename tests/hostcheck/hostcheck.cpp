@@ -106,6 +106,7 @@ void hc_sample_gamma_f64(uint64_t seed, uint64_t stream, double alpha, int n, do
 
 // ---- whole-step emulation: the same sequence of device functions the kernels run -------------------
 #include "cosmos_globals.cuh"
+#include "cosmos_sites_fast.cuh"
 
 namespace {
 
@@ -157,6 +158,18 @@ double cosmos_step_host(int nb, int fb, int Nt, int F_, int C, int P, int O, con
         for (int st = 0; st < NSAMP; ++st) {
             double r[NSO], ex[NEX];
             double variate = (double)lnoise[st * U + u];
+            bool done = false;
+            if (sizeof(T) == sizeof(float)) {   // production path of site_kernel<float>
+                float rf[NSO], exf[NEX], vf;
+                if (site_eval_fast(st, (float)lparams[lo.index(site_param0(st), n, f, c)], (float)lparams[lo.index(site_param1(st), n, f, c)],
+                                   (float)ubm, (float)ubs, mc, false, nullptr, variate, vf, rf, exf) == SITE_DONE) {
+                    done = true;
+                    sample[st] = (T)vf;
+                    for (int j2 = 0; j2 < NSO; ++j2) rec[st * NSO + j2] = (T)rf[j2];
+                    if (st == S_B) for (int j2 = 0; j2 < NEX; ++j2) rec[NSAMP * NSO + j2] = (T)exf[j2];
+                }
+            }
+            if (done) continue;
             const double v = site_eval(st, (double)lparams[lo.index(site_param0(st), n, f, c)],
                                        (double)lparams[lo.index(site_param1(st), n, f, c)], ubm, ubs, mc, false, nullptr,
                                        variate, r, ex);
@@ -255,4 +268,29 @@ void hc_gamma_draws_f32(float alpha, uint64_t seed, int n, float* out) {
     for (int i = 0; i < n; ++i) { Philox rng(seed, 3ull, (uint64_t)i << 8); out[i] = sample_std_gamma<float>(rng, alpha); }
 }
 int hc_sizeof_model_const() { return (int)sizeof(ModelConst); }
+// one site in replay mode: double reference form and fp32 production form; out = [sample, rec[NSO], extra[NEX]]
+void hc_site_eval_f64(int s, double u0, double u1, double ubm, double ubs, const ModelConst* mc, double variate, double* out) {
+    double rec[NSO], ex[NEX] = {0, 0, 0, 0};
+    out[0] = site_eval(s, u0, u1, ubm, ubs, *mc, false, nullptr, variate, rec, ex);
+    for (int j = 0; j < NSO; ++j) out[1 + j] = rec[j];
+    for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
+}
+int hc_site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const ModelConst* mc, double variate, double* out) {
+    float rec[NSO], ex[NEX] = {0, 0, 0, 0}, v = 0.0f;
+    const int status = site_eval_fast(s, u0, u1, ubm, ubs, *mc, false, nullptr, variate, v, rec, ex);
+    out[0] = v;
+    for (int j = 0; j < NSO; ++j) out[1 + j] = rec[j];
+    for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
+    return status;
+}
+// RNG-mode draws through the production form (falls back like site_kernel<float>)
+void hc_site_draws_fast(int s, float u0, float u1, const ModelConst* mc, uint64_t seed, int n, double* out) {
+    for (int i = 0; i < n; ++i) {
+        Philox rng(seed, 7ull, ((uint64_t)(i + 1) << 12) + ((uint64_t)s << 8));
+        double variate = 0.0, rec[NSO], ex[NEX];
+        float recf[NSO], exf[NEX], v = 0.0f;
+        const int status = site_eval_fast(s, u0, u1, 0.0f, 0.0f, *mc, true, &rng, variate, v, recf, exf);
+        out[i] = status == SITE_DONE ? (double)v : site_eval(s, u0, u1, 0.0, 0.0, *mc, status == SITE_FALLBACK_DRAW, &rng, variate, rec, ex);
+    }
+}
 }

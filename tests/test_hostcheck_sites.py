@@ -1,0 +1,124 @@
+"""
+CPU: the fp32 production form of the guide sites (csrc/cosmos_sites_fast.cuh, compiled for the host)
+against the double-precision form (csrc/cosmos_local.cuh::site_eval, itself pinned to the oracle by
+test_hostcheck_step.py).  Every output -- sample, log q, d log q / d sample and the four
+reparameterisation-map entries, plus the background prior record -- over the regimes the cosmos guide
+visits: small / medium / large Gamma concentrations (ATen's Taylor, rational and Rice branches) and
+Beta sample sizes from 20 to 6e4 (Rice expansion and its Taylor patch).
+
+Tolerance: 5e-6 of the largest entry of each output over the batch (the north-star asks 1e-5 for the
+gradients these feed); measured ~1e-6 or better.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cosmos_oracle as O
+from tapqir_b200.models import layout as L
+from tests import hostcheck
+
+NOUT = 1 + 6 + 4
+NAMES = ["sample", "LQ", "DQ", "A0", "B0", "A1", "B1", "EX_LP", "EX_DP", "EX_GBM", "EX_GBS"]
+
+
+def _run(hc, mc, s, u0, u1, ubm, ubs, var):
+    n = len(u0)
+    ref, fast, status = np.zeros((n, NOUT)), np.zeros((n, NOUT)), np.zeros(n, dtype=int)
+    buf = (ctypes.c_double * NOUT)()
+    f32 = lambda v: float(np.float32(v))
+    for i in range(n):
+        a, b, c, d = f32(u0[i]), f32(u1[i]), f32(ubm[i]), f32(ubs[i])
+        hc.hc_site_eval_f64(s, ctypes.c_double(a), ctypes.c_double(b), ctypes.c_double(c), ctypes.c_double(d),
+                            ctypes.byref(mc), ctypes.c_double(var[i]), buf)
+        ref[i] = buf[:]
+        status[i] = hc.hc_site_eval_fast(s, ctypes.c_float(a), ctypes.c_float(b), ctypes.c_float(c), ctypes.c_float(d),
+                                         ctypes.byref(mc), ctypes.c_double(var[i]), buf)
+        fast[i] = buf[:]
+    return ref, fast, status
+
+
+def _check(ref, fast, status, nout, min_fast, tol=5e-6):
+    ok = status == 0
+    assert ok.mean() >= min_fast, f"only {ok.mean():.2f} of the sites took the fp32 path"
+    bad = {}
+    for j in range(nout):
+        r, f = ref[ok, j], fast[ok, j]
+        rel = np.abs(f - r).max() / np.abs(r).max()
+        if not rel < tol:
+            bad[NAMES[j]] = rel
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("site", [0, 1])   # background (with its prior record), height
+@pytest.mark.parametrize("lconc", [(-1.0, 2.0), (2.0, 3.0), (3.0, 8.0), (8.0, 12.0)])
+def test_gamma_sites(site, lconc):
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    g = torch.Generator().manual_seed(int(10 * lconc[0]) + site + 50)
+    n = 1500
+    lc = torch.empty(n).uniform_(*lconc, generator=g).double()
+    u1 = torch.empty(n).uniform_(-7, 1, generator=g).double()
+    u0 = lc - u1
+    conc = torch.exp(u0.float().double() + u1.float().double())
+    var = torch.distributions.Gamma(conc, torch.ones_like(conc)).sample().float().double().clamp_min(1e-30)
+    ubm = u0 + 0.1 * torch.randn(n, generator=g).double()
+    ubs = ubm - torch.empty(n).uniform_(0.5, 3.0, generator=g).double()
+    ref, fast, status = _run(hc, mc, site, u0.numpy(), u1.numpy(), ubm.numpy(), ubs.numpy(), var.numpy())
+    _check(ref, fast, status, NOUT if site == 0 else 7, 0.99)
+
+
+@pytest.mark.parametrize("site", [3, 5, 8])   # width, x, y
+@pytest.mark.parametrize("lsize,min_fast", [((3.0, 5.0), 0.7), ((5.0, 8.0), 0.99), ((8.0, 11.0), 0.99)])
+def test_beta_sites(site, lsize, min_fast):
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    g = torch.Generator().manual_seed(int(10 * lsize[0]) + site)
+    n = 1500
+    u1 = torch.empty(n).uniform_(*lsize, generator=g).double()
+    u0 = torch.empty(n).uniform_(-1.5, 1.5, generator=g).double()
+    S = 2 + torch.exp(u1.float().double())
+    m1 = torch.sigmoid(u0.float().double())
+    var = torch.distributions.Beta(S * m1, S * (1 - m1)).sample().float().double()
+    # a slice of the batch sits in / next to the Taylor patch around the mean, where ATen's form cancels worst
+    k = n // 5
+    sd = torch.sqrt(m1 * (1 - m1) / (S + 1))
+    var[:k] = (m1[:k] + sd[:k] * torch.empty(k).uniform_(-0.3, 0.3, generator=g).double()).float().double()
+    z = np.zeros(n)
+    ref, fast, status = _run(hc, mc, site, u0.numpy(), u1.numpy(), z, z, var.numpy())
+    _check(ref, fast, status, 7, min_fast)
+
+
+def test_out_of_regime_falls_back():
+    """Tiny concentrations, samples on the clamps and fp32 reference conventions are left to the double form."""
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    buf = (ctypes.c_double * NOUT)()
+    call = lambda s, a, b, v, m=mc: hc.hc_site_eval_fast(s, ctypes.c_float(a), ctypes.c_float(b), ctypes.c_float(0), ctypes.c_float(0),
+                                                         ctypes.byref(m), ctypes.c_double(v), buf)
+    assert call(5, 0.0, 1.0, 0.5) != 0          # Beta with c1 = c0 = 2.4
+    assert call(5, 0.0, 6.0, 1e-9) != 0         # sample on the lower clamp
+    assert call(1, -9.0, 2.0, 1.0) != 0         # Gamma concentration < e^-4
+    assert call(5, 0.0, 6.0, 0.5) == 0
+    mc32 = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float32)
+    assert call(5, 0.0, 6.0, 0.5, mc32) != 0
+
+
+def test_rng_draws_through_fast_path_have_the_right_moments():
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    n = 40000
+    out = np.zeros(n)
+    p = out.ctypes.data_as(ctypes.c_void_p)
+    # height: Gamma(loc * beta, beta) with loc = 3000, beta = 0.02
+    hc.hc_site_draws_fast(1, ctypes.c_float(np.log(3000.0)), ctypes.c_float(np.log(0.02)), ctypes.byref(mc), ctypes.c_uint64(11), n, p)
+    assert abs(out.mean() - 3000.0) < 5 * np.sqrt(3000.0 / 0.02 / n)
+    assert abs(out.var() / (3000.0 / 0.02) - 1.0) < 0.05
+    # x: AffineBeta(mean 1.5, size 400) on [-7.5, 7.5]
+    m1 = (1.5 + 7.5) / 15.0
+    hc.hc_site_draws_fast(5, ctypes.c_float(np.log(m1 / (1 - m1))), ctypes.c_float(np.log(398.0)), ctypes.byref(mc), ctypes.c_uint64(12), n, p)
+    var = 15.0 ** 2 * m1 * (1 - m1) / 401.0
+    assert abs(out.mean() - 1.5) < 5 * np.sqrt(var / n)
+    assert abs(out.var() / var - 1.0) < 0.05
