@@ -95,6 +95,7 @@ int tq_ksmogn_fwd_bwd(int dtype, const tq_patch_view* view, const void* height, 
  *
  *   tq_subsample (x2, optional) -> tq_cosmos_globals_sample -> tq_cosmos_sites -> tq_ksmogn_fwd_bwd
  *   -> tq_cosmos_local_post -> [all-reduce of `acc` across ranks] -> tq_cosmos_globals_grad
+ *      (or tq_cosmos_globals_prepare any time after the sample + tq_cosmos_globals_finish here)
  *   -> tq_adam_dense (local buffer, global buffer) -> tq_step_advance
  *
  * Parameter buffers (unconstrained values, what pyro's param store holds; models/cosmos.py:471-598):
@@ -112,6 +113,7 @@ int tq_ksmogn_fwd_bwd(int dtype, const tq_patch_view* view, const void* height, 
 typedef struct {
     double bg_mean_std, bg_std_std, lamda_rate, height_std, width_min, width_max, proximity_rate, gain_std;
     double eps, tiny;
+    double logit_lim;   /* log((1 - eps) / eps) */
     int32_t P;
 } tq_model_const;
 
@@ -169,6 +171,18 @@ int tq_cosmos_zprobs(int dtype, const tq_patch_view* view, int64_t Nt, const voi
 int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, const void* mc,
                            const double* gstate, const double* acc, double sN, double sF,
                            void* ggrads, double* elbo_parts, double* loss, void* stream);
+
+/* The same reverse mode in two halves, so that its expensive part leaves the critical path: the gradient
+ * of a global site is affine in one or two linear functionals of `acc`; tq_cosmos_globals_prepare
+ * (right after tq_cosmos_globals_sample, e.g. on a side stream) evaluates the densities and implicit
+ * reparameterisation gradients into `gprep` (tq_sizeof_gprep() bytes of device memory),
+ * tq_cosmos_globals_finish (after `acc` is complete) writes ggrads and loss. */
+int tq_sizeof_gprep(void);
+int tq_cosmos_globals_prepare(int dtype, int Q, const void* gparams, const void* mc,
+                              const double* gstate, void* gprep, void* stream);
+int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gstate,
+                             const void* gprep, const double* acc, double sN, double sF,
+                             void* ggrads, double* loss, void* stream);
 
 /* torch.optim.Adam step (pyro.optim.Adam({"lr", "betas"}), models/model.py:168-171), dense over
  * the whole buffer; *state = number of completed steps. */

@@ -55,6 +55,9 @@ SIGNATURES = {
                                       c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_zprobs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP]),
     "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP, _VP]),
+    "tq_sizeof_gprep": (c_int, []),
+    "tq_cosmos_globals_prepare": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, _VP]),
+    "tq_cosmos_globals_finish": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),
     "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),

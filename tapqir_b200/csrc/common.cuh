@@ -49,4 +49,20 @@ __device__ __forceinline__ UnitIndex locate_unit(int64_t u, int fb, int C, int F
     return r;
 }
 
+// same for a unit index known to fit 32 bits (unsigned 32-bit divisions; none at all when C == 1)
+__device__ __forceinline__ UnitIndex locate_unit32(uint32_t u, int fb, int C, int F,
+                                                   const int32_t* __restrict__ ndx,
+                                                   const int32_t* __restrict__ fdx) {
+    UnitIndex r;
+    uint32_t nf = u;
+    r.c = 0;
+    if (C != 1) { nf = u / (uint32_t)C; r.c = (int)(u - nf * (uint32_t)C); }
+    r.ni = (int)(nf / (uint32_t)fb);
+    r.fi = (int)(nf - (uint32_t)r.ni * (uint32_t)fb);
+    r.aoi = ndx ? ndx[r.ni] : r.ni;
+    const int f = fdx ? fdx[r.fi] : r.fi;
+    r.patch = ((int64_t)r.aoi * F + f) * C + r.c;
+    return r;
+}
+
 }  // namespace tq

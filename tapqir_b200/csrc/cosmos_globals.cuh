@@ -142,21 +142,54 @@ TQ_HD void globals_pre_site(int site, const double* u, const GlobalLayout& gl, c
 }
 
 // ---- reverse: accumulators -> loss and d loss / d unconstrained globals ------------------------------
+// The data reach the reverse mode of a global site only through one or two LINEAR functionals of the
+// accumulators (its "drive"); everything else -- densities, digammas, implicit reparameterisation
+// gradients: the expensive part -- depends on the sample alone.  So the gradient is affine in the drive:
+//     grad(drive) = grad(0) + drive[0] (grad(e0) - grad(0)) + drive[1] (grad(e1) - grad(0)),
+// which lets the kernels evaluate grad(0), grad(e0), grad(e1) right after sampling, off the critical
+// path (globals_prepare), and finish with a handful of FMAs once the accumulators exist (globals_finish).
+//
 // acc: [Q][NACC] sums over all units of all ranks (unscaled, masked); sN = Nt/nb, sF = F/fb.
-// Returns this site's part of the ELBO (site 0 also carries the data terms); writes grad[i] =
-// d loss / d u[i] for the parameters of `site` only.
-TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc,
-                               const double* sample, const double* acc, double sN, double sF, double* grad) {
+TQ_HD void globals_drive(int site, const GlobalLayout& gl, const ModelConst& mc, const double* sample, const double* acc,
+                         double sN, double sF, double (&drive)[2], double& elbo_data) {
     const double s = sN * sF;
+    drive[0] = drive[1] = 0.0;
+    elbo_data = 0.0;
+    if (site == 0) {
+        for (int q = 0; q < gl.Q; ++q) {
+            const double* a = acc + q * NACC;
+            elbo_data += s * a[ACC_ELBO_FRAME] + sN * a[ACC_ELBO_AOI];
+            drive[0] += s * a[ACC_RATE];
+        }
+    } else if (site == 1) {
+        for (int q = 0; q < gl.Q; ++q) drive[0] += s * acc[q * NACC + ACC_SIZE1];
+    } else if (site < 2 + gl.Q) {
+        const double* a = acc + (site - 2) * NACC;
+        for (int z = 0; z < kZ; ++z) drive[z] = s * a[ACC_LOGPZ + z];
+    } else {
+        const int q = site - 2 - gl.Q;
+        const double* a = acc + q * NACC;
+        double pm0, d0, pm1, d1;
+        probs_m_k2(sample[gl.n_lamda(q)], pm0, d0, pm1, d1);
+        for (int th = 0; th < kTheta; ++th)
+            for (int k = 0; k < kK; ++k) {
+                if (th == k + 1) continue;  // certain spot: probability 1, no lamda dependence
+                const double p = th == 0 ? pm0 : pm1, dp = th == 0 ? d0 : d1;
+                if (p < mc.eps || p > 1.0 - mc.eps) continue;
+                const double* t = a + ACC_LOGPM + (th * kK + k) * 2;
+                drive[0] += s * (t[1] / p - t[0] / (1.0 - p)) * dp;
+            }
+    }
+}
+
+// Returns the site's own part of the ELBO (log prior - log q of its sample); writes grad[i] = d loss / d u[i]
+// for the parameters of `site` only.
+TQ_HD double globals_post_site_driven(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc,
+                                      const double* sample, const double (&drive)[2], double* grad) {
     const double hi = (mc.P + 1) / sqrt(12.0);
     double elbo = 0.0;
     if (site == 0) {
-        double rate_grad = 0.0;
-        for (int q = 0; q < gl.Q; ++q) {
-            const double* a = acc + q * NACC;
-            elbo += s * a[ACC_ELBO_FRAME] + sN * a[ACC_ELBO_AOI];
-            rate_grad += s * a[ACC_RATE];
-        }
+        const double rate_grad = drive[0];
         const double loc = exp(u[gl.gain_loc()]), beta = exp(u[gl.gain_beta()]);
         const double conc = loc * beta;
         const double g = sample[gl.n_gain()];
@@ -173,8 +206,7 @@ TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl
         return elbo;
     }
     if (site == 1) {
-        double size1_grad = 0.0;
-        for (int q = 0; q < gl.Q; ++q) size1_grad += s * acc[q * NACC + ACC_SIZE1];
+        const double size1_grad = drive[0];
         const Transformed<double> loc = t_interval<double>(u[gl.prox_loc()], 0.0, hi - mc.eps, mc);
         const Transformed<double> size = t_greater_than<double>(u[gl.prox_size()], 2.0);
         const AffBeta<double> d(loc.v, size.v, 0.0, hi);
@@ -195,7 +227,6 @@ TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl
     }
     if (site < 2 + gl.Q) {
         const int q = site - 2;
-        const double* a = acc + q * NACC;
         const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
         const double mxu = fmax(u0, u1);
         const double e0 = exp(u0 - mxu), e1 = exp(u1 - mxu);
@@ -214,13 +245,13 @@ TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl
             const double pz = x[z] / sx;
             const bool inside = pz >= mc.eps && pz <= 1.0 - mc.eps;
             gx[z] = (prior_c - 1.0) / x[z] - (conc[z] - 1.0) / x[z];
-            if (inside) gx[z] += s * a[ACC_LOGPZ + z] / x[z];
+            if (inside) gx[z] += drive[z] / x[z];
         }
         for (int z = 0; z < kZ; ++z) {
             const double pz = x[z] / sx;
             if (pz >= mc.eps && pz <= 1.0 - mc.eps) {
-                gx[0] -= s * a[ACC_LOGPZ + z] / sx;
-                gx[1] -= s * a[ACC_LOGPZ + z] / sx;
+                gx[0] -= drive[z] / sx;
+                gx[1] -= drive[z] / sx;
             }
         }
         elbo += lp - lq;
@@ -240,23 +271,12 @@ TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl
     }
     {
         const int q = site - 2 - gl.Q;
-        const double* a = acc + q * NACC;
         const double loc = exp(u[gl.lamda_loc(q)]), beta = exp(u[gl.lamda_beta(q)]);
         const double conc = loc * beta;
         const double lam = sample[gl.n_lamda(q)];
         const GammaSite<double> ql(lam, conc, beta);
         elbo += (log(mc.lamda_rate) - mc.lamda_rate * lam) - ql.lp;  // Exponential prior :176-181
-        double pm0, d0, pm1, d1;
-        probs_m_k2(lam, pm0, d0, pm1, d1);
-        double G = -mc.lamda_rate - ql.d_v;
-        for (int th = 0; th < kTheta; ++th)
-            for (int k = 0; k < kK; ++k) {
-                if (th == k + 1) continue;  // certain spot: probability 1, no lamda dependence
-                const double p = th == 0 ? pm0 : pm1, dp = th == 0 ? d0 : d1;
-                if (p < mc.eps || p > 1.0 - mc.eps) continue;
-                const double* t = a + ACC_LOGPM + (th * kK + k) * 2;
-                G += s * (t[1] / p - t[0] / (1.0 - p)) * dp;
-            }
+        const double G = -mc.lamda_rate - ql.d_v + drive[0];
         const double dv_dconc = std_gamma_grad<double>(conc, lam * beta) / beta;
         const double g_conc = G * dv_dconc - ql.d_conc;
         const double g_rate = G * (-lam / beta) - ql.d_rate;
@@ -265,6 +285,32 @@ TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl
         return elbo;
     }
 }
+
+// one-shot form: this site's part of the ELBO (site 0 also carries the data terms) and its gradients
+TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc,
+                               const double* sample, const double* acc, double sN, double sF, double* grad) {
+    double drive[2], elbo_data;
+    globals_drive(site, gl, mc, sample, acc, sN, sF, drive, elbo_data);
+    return elbo_data + globals_post_site_driven(site, u, gl, mc, sample, drive, grad);
+}
+
+// global site owning parameter i of the flat GlobalLayout
+TQ_HD int global_param_site(int i, int Q) {
+    if (i < 2) return 0;
+    if (i < 4) return 1;
+    if (i < 4 + kZ * Q) return 2 + (i - 4) / kZ;           // pi_mean (q, z)
+    if (i < 4 + (kZ + 1) * Q) return 2 + (i - 4 - kZ * Q);  // pi_size q
+    if (i < 4 + (kZ + 2) * Q) return 2 + Q + (i - 4 - (kZ + 1) * Q);
+    return 2 + Q + (i - 4 - (kZ + 2) * Q);
+}
+
+// prepared reverse mode: for every site, grad at drive = 0, e0, e1 (full GlobalLayout vectors; only the
+// site's own entries are meaningful) and the site's own ELBO part
+constexpr int kMaxGlobalSites = 2 + 2 * kMaxC;
+struct GlobalPrep {
+    double grad[kMaxGlobalSites][3][kMaxGlobals];
+    double elbo[kMaxGlobalSites];
+};
 
 // serial forms (host check, tests)
 TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst& mc, bool use_rng, Philox* rng,

@@ -29,6 +29,7 @@ struct ModelConst {
     double bg_mean_std, bg_std_std, lamda_rate, height_std, width_min, width_max, proximity_rate, gain_std;
     double eps;    // torch.finfo(reference dtype).eps: clamps of Categorical/Bernoulli/sigmoid/AffineBeta
     double tiny;   // torch.finfo(reference dtype).tiny
+    double logit_lim;  // log((1 - eps) / eps): logit of the Bernoulli probs clamp
     int P;
 };
 
@@ -337,7 +338,7 @@ template <typename F> struct SpotPresence {
     F q1, q0, lq1, lq0, dq1;
     TQ_HD SpotPresence(F u, const ModelConst& mc) {
         using R = Real<F>;
-        const F lim = F(log((1.0 - mc.eps) / mc.eps));
+        const F lim = F(mc.logit_lim);
         const bool inside = (u >= -lim) && (u <= lim);
         const F uc = R::min(R::max(u, -lim), lim);
         const F e = R::exp(-R::abs(uc));

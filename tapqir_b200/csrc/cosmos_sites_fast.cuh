@@ -30,6 +30,21 @@ namespace tq {
 
 constexpr float kSiteHalfLn2Pi = 0.91893853320467274178f;
 
+// reciprocal: one MUFU op on the device (1 ulp), exact division on the host
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float site_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+inline float site_rcp(float x) { return 1.0f / x; }
+#endif
+
+// (1 + g)^(-3/2) - 1 with full relative accuracy for small g
+TQ_HD float pow_m32_m1(float g) {
+    if (fabsf(g) <= 0.1f)
+        return g * (-1.5f + g * (1.875f + g * (-2.1875f + g * (2.4609375f + g * (-2.70703125f + g * (2.9326171875f
+                 + g * (-3.14208984375f + g * 3.338470458984375f)))))));
+    return expm1f(-1.5f * log1pf(g));
+}
+
 // l = log1p(u), f = u - l, A = l/u - 1, F = 2 f / u^2 - 1, for u > -1; r = 1 + u rounded from its own
 // (double) evaluation, so that l keeps its accuracy when u is close to -1
 struct Lp1 { float l, f, A, F; };
@@ -38,7 +53,7 @@ TQ_HD Lp1 lp1_parts(float u, float r) {
     Lp1 o;
     if (fabsf(u) <= 0.4f) {
         // log1p(u) = 2 atanh(s), s = u / (2 + u);  u - 2 s = s u
-        const float inv = 1.0f / (2.0f + u);
+        const float inv = site_rcp(2.0f + u);
         const float s = u * inv, z = s * s;
         const float P = 0.333333333f + z * (0.2f + z * (0.142857143f + z * (0.111111111f + z * (0.0909090909f + z * 0.0769230769f))));
         const float R = z * P;
@@ -49,8 +64,9 @@ TQ_HD Lp1 lp1_parts(float u, float r) {
     } else {
         o.l = logf(r);
         o.f = u - o.l;
-        o.A = o.l / u - 1.0f;
-        o.F = 2.0f * o.f / (u * u) - 1.0f;
+        const float iu = site_rcp(u);
+        o.A = o.l * iu - 1.0f;
+        o.F = 2.0f * o.f * (iu * iu) - 1.0f;
     }
     return o;
 }
@@ -59,6 +75,55 @@ TQ_HD Lp1 lp1_parts(float u, float r) {
 //   lgamma(z) = (z - 1/2) ln z - z + ln(2 pi)/2 + r(z),   psi(z) = ln z - q(z)
 TQ_HD float stirling_r(float iz) { const float z2 = iz * iz; return iz * (0.0833333333f - z2 * (0.00277777778f - z2 * 0.000793650794f)); }
 TQ_HD float stirling_q(float iz) { const float z2 = iz * iz; return iz * (0.5f + iz * (0.0833333333f - z2 * (0.00833333333f - z2 * 0.00396825397f))); }
+
+// lgamma(x) and digamma(x) in fp32 for x > 0: Stirling series for x >= 8, below that the recurrence shifted
+// by 8 with the eight reciprocals folded into two divisions and the eight factors into one logarithm
+TQ_HD void lgamma_digamma_f32(float x, float& lg, float& psi) {
+    float xs = x, lprod = 0.0f, rsum = 0.0f;
+    if (x < 8.0f) {
+        const float p01 = x * (x + 1.0f), p23 = (x + 2.0f) * (x + 3.0f), p45 = (x + 4.0f) * (x + 5.0f), p67 = (x + 6.0f) * (x + 7.0f);
+        const float tx = 2.0f * x;
+        const float pa = p01 * p23, pb = p45 * p67;
+        rsum = ((tx + 1.0f) * p23 + (tx + 5.0f) * p01) * site_rcp(pa) + ((tx + 9.0f) * p67 + (tx + 13.0f) * p45) * site_rcp(pb);
+        lprod = logf(pa * pb);
+        xs = x + 8.0f;
+    }
+    const float ix = site_rcp(xs), lxs = logf(xs);
+    lg = (xs - 0.5f) * lxs - xs + kSiteHalfLn2Pi + stirling_r(ix) - lprod;
+    psi = lxs - stirling_q(ix) - rsum;
+}
+
+// d x / d alpha of a standard Gamma(alpha) draw outside the Rice regime (ATen _standard_gamma_grad):
+// Taylor series of the incomplete gamma function for x < 0.8 (the x^alpha factors of cdf and pdf divided
+// out), else the bivariate rational fit in (log(x/alpha), log alpha).  lx = log x, l = log(x / alpha).
+TQ_HD float gamma_grad_small(float alpha, float x, float lx, float l, float lalpha, float psi) {
+    if (x < 0.8f) {
+        float numer = 1.0f, denom = alpha;
+        float r = site_rcp(denom);
+        float s1 = r, s2 = r * r;
+#pragma unroll
+        for (int i = 1; i <= 5; ++i) {
+            numer *= -x * (1.0f / float(i));
+            denom += 1.0f;
+            r = site_rcp(denom);
+            s1 = fmaf(numer, r, s1);
+            s2 = fmaf(numer, r * r, s2);
+        }
+        const float res = -x * expf(x) * ((lx - psi) * s1 - s2);
+        return (res != res) ? 0.0f : res;
+    }
+    const float c[3][8] = {
+        {0.16009398f, -0.094634809f, 0.025146376f, -0.0030648343f, 1.0f, 0.32668115f, 0.10406089f, 0.0014179084f},
+        {0.53487893f, 0.1298071f, 0.065735949f, -0.0015649758f, 0.16639465f, 0.020070113f, -0.0035938915f, -0.00058392623f},
+        {0.040121004f, -0.0065914022f, -0.0026286047f, -0.0013441777f, 0.017050642f, -0.0021309326f, 0.00085092367f, -1.5247877e-07f},
+    };
+    float cv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cv[i] = c[0][i] + l * (c[1][i] + l * c[2][i]);
+    const float pnum = cv[0] + lalpha * (cv[1] + lalpha * (cv[2] + lalpha * cv[3]));
+    const float qden = cv[4] + lalpha * (cv[5] + lalpha * (cv[6] + lalpha * cv[7]));
+    return expf(pnum * site_rcp(qden));
+}
 
 // d x / d alpha of a standard Gamma(alpha) draw x = alpha (1 + u), alpha > 8, x >= 0.8: ATen's Rice
 // expansion and its Taylor patch, returned as  sgg  and  sgg - (1 + u)  (the latter without cancellation)
@@ -74,9 +139,9 @@ TQ_HD void gamma_grad_rice(float alpha, float ia, float u, const Lp1& p, float& 
         return;
     }
     // H(u) = [ (l/u) g^(-3/2) - (1 + u/2) ] / u^2,  g = 2 f / u^2
-    const float E = expm1f(-1.5f * log1pf(p.F));               // g^(-3/2) - 1
+    const float E = pow_m32_m1(p.F);                              // g^(-3/2) - 1
     const float B = p.A + E + p.A * E - 0.5f * u;
-    const float H = B / (u * u);
+    const float H = B * site_rcp(u * u);
     const float inner = p.A - H * ia;                             // l/u - H/alpha - 1
     sgg_m1u = (1.0f + u) * (st + inner + st * inner);             // (1+u)(1+st)(1+inner) - (1+u)
     sgg = (1.0f + u) + sgg_m1u;
@@ -97,18 +162,20 @@ TQ_HD double beta_patch_poly(double x, double alpha, double beta) {
 // log-density of v ~ Gamma(conc, rate) and its partials from x = rate v = conc (1 + u):
 //   lp, d_v, and the two combinations the site maps need:  conc * d_conc  and  conc * d_conc + rate * d_rate
 TQ_HD void gamma_density_fast(float conc, float lconc, float lrate, float rate, float x, float u, const Lp1& p,
-                              float& lp, float& d_v, float& cdc, float& cdc_rdr) {
+                              float& lp, float& d_v, float& cdc, float& cdc_rdr, float& psi) {
     const float lx = lconc + p.l;
-    d_v = rate * (-fmaf(conc, u, 1.0f)) / x;                      // (conc - 1)/v - rate
+    d_v = rate * (-fmaf(conc, u, 1.0f)) * site_rcp(x);            // (conc - 1)/v - rate
     if (conc > 10.0f) {
-        const float ic = 1.0f / conc;
+        const float ic = site_rcp(conc);
         const float q = stirling_q(ic);
         lp = lrate - lx - conc * p.f + 0.5f * lconc - kSiteHalfLn2Pi - stirling_r(ic);
         cdc = conc * (p.l + q);                                     // conc (lx - psi(conc))
         cdc_rdr = conc * (q - p.f);                                 // ... + (conc - x)
+        psi = lconc - q;
     } else {
-        const float psi = digamma<float>(conc);
-        lp = lrate - lx + conc * lx - x - lgammaf(conc);
+        float lg;
+        lgamma_digamma_f32(conc, lg, psi);
+        lp = lrate - lx + conc * lx - x - lg;
         cdc = conc * (lx - psi);
         cdc_rdr = cdc - conc * u;
     }
@@ -126,7 +193,7 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
         const float lconc = u0 + u1;
         if (!(lconc > -4.0f && lconc < 13.0f) || fabsf(u1) > 40.0f) return SITE_FALLBACK_DRAW;
         const double ed = exp(-((double)u0 + (double)u1));         // 1 / conc
-        const float ic = (float)ed, conc = 1.0f / ic;
+        const float ic = (float)ed, conc = site_rcp(ic);
         if (use_rng) variate = fmax((double)sample_std_gamma_f32(*rng, conc), mc.tiny);
         const double xd = variate;
         if (!(xd > 1e-18) || !(xd < 1e18)) return SITE_FALLBACK;
@@ -134,16 +201,16 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
         const float u = (float)(rd - 1.0);
         const float x = (float)xd;
         if (x < 0.8f && conc > 30.0f) return SITE_FALLBACK;        // Taylor regime far in the tail: powers underflow in fp32
-        const float ibeta = expf(-u1), beta = 1.0f / ibeta, loc = conc * ibeta;
+        const float ibeta = expf(-u1), beta = site_rcp(ibeta), loc = conc * ibeta;
         const float v = x * ibeta;
         const Lp1 p = lp1_parts(u, (float)rd);
-        float lp, d_v, cdc, cdc_rdr;
-        gamma_density_fast(conc, lconc, u1, beta, x, u, p, lp, d_v, cdc, cdc_rdr);
+        float lp, d_v, cdc, cdc_rdr, psi;
+        gamma_density_fast(conc, lconc, u1, beta, x, u, p, lp, d_v, cdc, cdc_rdr, psi);
         float sgg, sgg_m1u;
         if (x >= 0.8f && conc > 8.0f) {
             gamma_grad_rice(conc, ic, u, p, sgg, sgg_m1u);
         } else {
-            sgg = std_gamma_grad<float>(conc, x);
+            sgg = gamma_grad_small(conc, x, lconc + p.l, p.l, lconc, psi);
             sgg_m1u = sgg - (1.0f + u);
         }
         if (s == S_B) {
@@ -155,8 +222,8 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
             if (!(up > -1.0f)) return SITE_FALLBACK;
             const float pc = expf(lpc), pr = expf(lpr);
             const Lp1 pp = lp1_parts(up, (float)rpd);
-            float plp, pd_v, pcdc, pcdc_rdr;
-            gamma_density_fast(pc, lpc, lpr, pr, pr * v, up, pp, plp, pd_v, pcdc, pcdc_rdr);
+            float plp, pd_v, pcdc, pcdc_rdr, ppsi;
+            gamma_density_fast(pc, lpc, lpr, pr, pr * v, up, pp, plp, pd_v, pcdc, pcdc_rdr, ppsi);
             extra[EX_LP] = plp;
             extra[EX_DP] = pd_v;
             // d pc / d u_bm = 2 pc, d pr / d u_bm = pr;  d pc / d u_bs = -2 pc, d pr / d u_bs = -2 pr
@@ -179,7 +246,7 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
     if (fabsf(u0) > 15.0f || !(u1 < 11.5f)) return SITE_FALLBACK_DRAW;
     const double ed = exp(-(double)u0);                           // m1 = 1 / (1 + e), m0 = e m1
     const float e = (float)ed;
-    const float m1 = 1.0f / (1.0f + e), m0 = e * m1;
+    const float m1 = site_rcp(1.0f + e), m0 = e * m1;
     const float sz = expf(u1), S = 2.0f + sz;                     // size - 2 = d size / d u, size
     const float c1 = S * m1, c0 = S * m0;
     if (!(c1 > 10.0f && c0 > 10.0f)) return SITE_FALLBACK_DRAW;
@@ -190,38 +257,38 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
     const double x01d = variate;   // (v - low) / scale of the reference, to rounding
     const float ua = (float)fma(x01d, ed, x01d - 1.0);            // (x - m1) / m1
     const float x = (float)x01d, y = (float)(1.0 - x01d);
-    const float ub = -ua / e;                                     // -(x - m1) / m0
+    const float ie = site_rcp(e), ub = -ua * ie;                                     // -(x - m1) / m0
     if (!(S * x * y >= 2.5f) || !(ua > -1.0f) || !(ub > -1.0f)) return SITE_FALLBACK;
     const float d = ua * m1;                                      // x - m1
-    const Lp1 pa = lp1_parts(ua, x / m1), pb = lp1_parts(ub, y / m0);
-    const float i1 = 1.0f / c1, i0 = 1.0f / c0, it = 1.0f / S;
+    const Lp1 pa = lp1_parts(ua, x * (1.0f + e)), pb = lp1_parts(ub, y * (1.0f + ie));
+    const float it = site_rcp(S), i1 = it * (1.0f + e), i0 = it * (1.0f + ie);
     const float q1 = stirling_q(i1), q0 = stirling_q(i0), qt = stirling_q(it);
     const float lm1 = -log1pf(e), lm0 = lm1 - u0;                 // log m1, log m0
     const float lt = logf(S);
     const float kl = m1 * pa.f + m0 * pb.f;                       // S kl = c1 log(m1/x) + c0 log(m0/y) >= 0
     const float lp = -S * kl - (lm1 + pa.l) - (lm0 + pb.l) + 0.5f * (lt + lm1 + lm0) - kSiteHalfLn2Pi
                      + stirling_r(it) - stirling_r(i1) - stirling_r(i0) - logf(scale);
-    const float d_v = (-S * d + (x - y)) / (x * y * scale);
+    const float d_v = (-S * d + (x - y)) * site_rcp(x * y * scale);
     const float d_c1 = pa.l + q1 - qt, d_c0 = pb.l + q0 - qt;
     const float mm = m1 * m0;
     float A0, A1;
-    if (d * d <= 0.01f * mm / (S + 1.0f)) {
+    if (d * d * (S + 1.0f) <= 0.01f * mm) {
         // y bg1 = K P1 / c1,  x bg0 = K P0 / c0,  K = pn / (12960 c1^2 c0^2 (1 + 12 S))
         const double P1 = beta_patch_poly(x01d, (double)c1, (double)c0), P0 = beta_patch_poly(1.0 - x01d, (double)c0, (double)c1);
         const float pn = (1.0f + 12.0f * c1) * (1.0f + 12.0f * c0) * (it * it);
-        const float K = pn / (12960.0f * (c1 * c1) * (c0 * c0) * (1.0f + 12.0f * S));
+        const float K = pn * site_rcp(12960.0f * (c1 * c1) * (c0 * c0) * (1.0f + 12.0f * S));
         A0 = scale * K * ((float)P1 * m0 + (float)P0 * m1);
         A1 = scale * sz * it * K * (float)(P1 - P0);
     } else {
         const float Gs = m0 * pa.F + m1 * pb.F;                   // 2 m1 m0 kl / d^2 - 1
-        const float E = expm1f(-1.5f * log1pf(Gs));
-        const float h = d / (2.0f * mm);
+        const float E = pow_m32_m1(Gs);
+        const float h = 0.5f * d * site_rcp(mm);
         const float Ba = pa.A + E + pa.A * E - h * (m0 - 2.0f * m1);
         const float Bb = pb.A + E + pb.A * E + h * (m1 - 2.0f * m0);
-        const float w = mm / (S * d * d);
+        const float w = mm * site_rcp(S * d * d);
         const float ta = pa.A - w * Ba, tb = pb.A - w * Bb;      // bg1 = stir (x/c1) (1 + ta), bg0 = stir (y/c0) (1 + tb)
         const float stir = (1.0f + i1 * (0.0833333333f + i1 * 0.00347222222f)) * (1.0f + i0 * (0.0833333333f + i0 * 0.00347222222f))
-                         / (1.0f + it * (0.0833333333f + it * 0.00347222222f));
+                         * site_rcp(1.0f + it * (0.0833333333f + it * 0.00347222222f));
         const float sxy = scale * stir * x * y;
         A0 = sxy * (m0 * (1.0f + ta) + m1 * (1.0f + tb));
         A1 = sxy * sz * it * (ta - tb);

@@ -93,57 +93,109 @@ template <typename T> struct LocalArgs {
 };
 
 // ---- sites: one thread per (site, unit), site-major so that a warp evaluates one family ------------------
+// grid = (blocks over units, site): no division to find the site, 32-bit index arithmetic (the host checks
+// U < 2^31).  Three kernels share the gather / scatter below:
+//   site_kernel<T>           the double-precision form for every site (dtype "double")
+//   site_fast_kernel         production: fp32 forms of cosmos_sites_fast.cuh; a site outside their regimes
+//                            leaves a NaN in its log-q slot ...
+//   site_fallback_kernel     ... and is redone here in double (same Philox stream, so the same draw whichever
+//                            kernel makes it).  Keeping the two apart holds the hot kernel at 66 registers.
+template <typename T> struct SiteInputs {
+    UnitIndex ui;
+    int64_t f;
+    T p0, p1, pbm, pbs;
+    unsigned long long rng_offset;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(kLocalBlock) site_kernel(const LocalArgs<T> a) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.U * NSAMP) return;
-    const int s = (int)(t / a.U);
-    const int64_t u = t - (int64_t)s * a.U;
-    const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
-    const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
-    const T p0 = a.lparams[a.lo.index(site_param0(s), ui.aoi, f, ui.c)];
-    const T p1 = a.lparams[a.lo.index(site_param1(s), ui.aoi, f, ui.c)];
-    T pbm = T(0), pbs = T(0);
+__device__ __forceinline__ SiteInputs<T> site_gather(const LocalArgs<T>& a, int s, uint32_t u32) {
+    SiteInputs<T> in;
+    in.ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    in.f = a.v.fdx ? a.v.fdx[in.ui.fi] : in.ui.fi;
+    in.p0 = a.lparams[a.lo.index(site_param0(s), in.ui.aoi, in.f, in.ui.c)];
+    in.p1 = a.lparams[a.lo.index(site_param1(s), in.ui.aoi, in.f, in.ui.c)];
+    in.pbm = in.pbs = T(0);
     if (s == S_B) {
-        pbm = a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)];
-        pbs = a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
+        in.pbm = a.lparams[a.lo.index(LP_BM, in.ui.aoi, in.f, in.ui.c)];
+        in.pbs = a.lparams[a.lo.index(LP_BS, in.ui.aoi, in.f, in.ui.c)];
     }
-    bool use_rng = a.noise_in == nullptr;
-    const unsigned long long gid = (((unsigned long long)(a.aoi_offset + ui.aoi)) * a.v.F + f) * a.v.C + ui.c;
-    Philox rng(a.seed, a.state->step, ((gid + 1ull) << 12) + ((unsigned long long)s << 8));
-    double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u];
-    T v, rec[NSO], extra[NEX];
-    int status = SITE_FALLBACK_DRAW;
-    if constexpr (sizeof(T) == sizeof(float)) {
-        // production: fp32 forms of cosmos_sites_fast.cuh; the double form only outside their regimes
-        status = site_eval_fast(s, p0, p1, pbm, pbs, a.mc, use_rng, &rng, variate, v, rec, extra);
-    }
-    if (status != SITE_DONE) {
-        double drec[NSO], dextra[NEX];
-        v = (T)site_eval(s, (double)p0, (double)p1, (double)pbm, (double)pbs, a.mc, use_rng && status == SITE_FALLBACK_DRAW,
-                         &rng, variate, drec, dextra);
-#pragma unroll
-        for (int j = 0; j < NSO; ++j) rec[j] = (T)drec[j];
-#pragma unroll
-        for (int j = 0; j < NEX; ++j) extra[j] = (T)dextra[j];
-    }
+    const unsigned long long gid = (((unsigned long long)(a.aoi_offset + in.ui.aoi)) * a.v.F + in.f) * a.v.C + in.ui.c;
+    in.rng_offset = ((gid + 1ull) << 12) + ((unsigned long long)s << 8);
+    return in;
+}
+
+template <typename T>
+__device__ __forceinline__ void site_scatter(const LocalArgs<T>& a, int s, int64_t u, T v, const T* rec, const T* extra) {
     a.samples[(int64_t)s * a.U + u] = v;
 #pragma unroll
     for (int j = 0; j < NSO; ++j) a.rec[((int64_t)s * NSO + j) * a.U + u] = rec[j];
     if (s == S_B) {
 #pragma unroll
         for (int j = 0; j < NEX; ++j) a.rec[((int64_t)NSAMP * NSO + j) * a.U + u] = extra[j];
-        // weights of the likelihood kernel: q(m) from the unconstrained m_probs
-        T q1[kK], q0[kK], qm[kM];
-#pragma unroll
-        for (int k = 0; k < kK; ++k) {
-            const SpotPresence<T> sp((T)a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, f, ui.c)], a.mc);
-            q1[k] = sp.q1; q0[k] = sp.q0;
-        }
-        presence_weights<T>(q1, q0, qm);
-#pragma unroll
-        for (int m = 0; m < kM; ++m) a.qm[m * a.U + u] = qm[m];
     }
+}
+
+// weights of the likelihood kernel: q(m) from the unconstrained m_probs (written by the background site's thread)
+template <typename T>
+__device__ __forceinline__ void write_presence_weights(const LocalArgs<T>& a, const SiteInputs<T>& in, int64_t u) {
+    T q1[kK], q0[kK], qm[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const SpotPresence<T> sp((T)a.lparams[a.lo.index(LP_M_PROBS + k, in.ui.aoi, in.f, in.ui.c)], a.mc);
+        q1[k] = sp.q1; q0[k] = sp.q0;
+    }
+    presence_weights<T>(q1, q0, qm);
+#pragma unroll
+    for (int m = 0; m < kM; ++m) a.qm[m * a.U + u] = qm[m];
+}
+
+template <typename T>
+__device__ __forceinline__ void site_double(const LocalArgs<T>& a, int s, uint32_t u32) {
+    const SiteInputs<T> in = site_gather(a, s, u32);
+    const bool use_rng = a.noise_in == nullptr;
+    Philox rng(a.seed, a.state->step, in.rng_offset);
+    double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
+    double drec[NSO], dextra[NEX];
+    const T v = (T)site_eval(s, (double)in.p0, (double)in.p1, (double)in.pbm, (double)in.pbs, a.mc, use_rng, &rng, variate, drec, dextra);
+    T rec[NSO], extra[NEX];
+#pragma unroll
+    for (int j = 0; j < NSO; ++j) rec[j] = (T)drec[j];
+#pragma unroll
+    for (int j = 0; j < NEX; ++j) extra[j] = (T)dextra[j];
+    site_scatter(a, s, (int64_t)u32, v, rec, extra);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) site_kernel(const LocalArgs<T> a) {
+    const int s = blockIdx.y;
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    site_double(a, s, u32);
+    if (s == S_B) write_presence_weights(a, site_gather(a, s, u32), (int64_t)u32);
+}
+
+__global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<float> a) {
+    const int s = blockIdx.y;
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    const SiteInputs<float> in = site_gather(a, s, u32);
+    const bool use_rng = a.noise_in == nullptr;
+    Philox rng(a.seed, a.state->step, in.rng_offset);
+    double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
+    float v = 0.0f, rec[NSO], extra[NEX];
+    const int status = site_eval_fast(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra);
+    if (status == SITE_DONE) site_scatter(a, s, (int64_t)u32, v, rec, extra);
+    else a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32] = nanf("");   // marker for site_fallback_kernel
+    if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
+}
+
+__global__ void __launch_bounds__(kLocalBlock) site_fallback_kernel(const LocalArgs<float> a) {
+    const int s = blockIdx.y;
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    const float marker = a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32];
+    if (marker == marker) return;
+    site_double(a, s, u32);
 }
 
 // ---- post: thread per unit (cheap) + deterministic block reduction of the channel accumulators -----------
@@ -305,6 +357,44 @@ __global__ void finalize_loss_kernel(const double* __restrict__ elbo_parts, int 
     loss[0] = -e;
 }
 
+// ---- globals, split reverse mode (see cosmos_globals.cuh): prepare runs right after sampling on the side stream,
+// finish after the accumulators exist.  prepare: one block per site, lanes 0..2 evaluate drive = 0, e0, e1.
+template <typename T>
+__global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+                                       const double* __restrict__ gstate, GlobalPrep* __restrict__ prep) {
+    const int site = blockIdx.x, lane = threadIdx.x;
+    if (lane >= 3 || site >= global_site_count(Q)) return;
+    GlobalLayout gl{Q};
+    double u[kMaxGlobals];
+    for (int i = 0; i < gl.count(); ++i) { u[i] = (double)gparams[i]; prep->grad[site][lane][i] = 0.0; }
+    const double drive[2] = {lane == 1 ? 1.0 : 0.0, lane == 2 ? 1.0 : 0.0};
+    const double e = globals_post_site_driven(site, u, gl, mc, gstate + kMaxGlobalNoise, drive, prep->grad[site][lane]);
+    if (lane == 0) prep->elbo[site] = e;
+}
+
+// finish: thread i owns global parameter i; thread 0 also sums the ELBO parts in a fixed order
+template <typename T>
+__global__ void globals_finish_kernel(int Q, ModelConst mc, const double* __restrict__ gstate,
+                                      const GlobalPrep* __restrict__ prep, const double* __restrict__ acc, double sN,
+                                      double sF, T* __restrict__ ggrads, double* __restrict__ loss) {
+    GlobalLayout gl{Q};
+    const int i = threadIdx.x;
+    if (blockIdx.x != 0) return;
+    if (i < gl.count()) {
+        const int site = global_param_site(i, Q);
+        double drive[2], elbo_data;
+        globals_drive(site, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, drive, elbo_data);
+        const double g0 = prep->grad[site][0][i];
+        ggrads[i] = (T)(g0 + drive[0] * (prep->grad[site][1][i] - g0) + drive[1] * (prep->grad[site][2][i] - g0));
+    }
+    if (i == 0) {
+        double drive[2], e;
+        globals_drive(0, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, drive, e);
+        for (int site = 0; site < global_site_count(Q); ++site) e += prep->elbo[site];
+        loss[0] = -e;
+    }
+}
+
 // ---- dense Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) --------------------------------------
 // models/model.py:168-171: pyro.optim.Adam({"lr", "betas": [0.9, 0.999]}) on every unconstrained tensor,
 // dense over the whole tensor.  `state->step` is the number of completed steps.
@@ -387,8 +477,17 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
     a.qm = (T*)qm;
     a.rec = (T*)rec;
     if (a.U == 0) return TQ_OK;
-    site_kernel<T><<<local_blocks(a.U * NSAMP), kLocalBlock, 0, st>>>(a);
-    TQ_LAUNCH_CHECK("site_kernel launch");
+    if (a.U >= (int64_t)1 << 31) { set_error("minibatch of %lld units exceeds the 2^31 limit of one launch", (long long)a.U); return TQ_ERR_ARG; }
+    const dim3 grid(local_blocks(a.U), NSAMP);
+    if constexpr (sizeof(T) == sizeof(float)) {
+        site_fast_kernel<<<grid, kLocalBlock, 0, st>>>(a);
+        TQ_LAUNCH_CHECK("site_fast_kernel launch");
+        site_fallback_kernel<<<grid, kLocalBlock, 0, st>>>(a);
+        TQ_LAUNCH_CHECK("site_fallback_kernel launch");
+    } else {
+        site_kernel<T><<<grid, kLocalBlock, 0, st>>>(a);
+        TQ_LAUNCH_CHECK("site_kernel launch");
+    }
     return TQ_OK;
 }
 
@@ -487,6 +586,38 @@ extern "C" int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, con
     TQ_LAUNCH_CHECK("globals_grad_kernel launch");
     finalize_loss_kernel<<<1, 32, 0, st>>>(elbo_parts, global_site_count(Q), loss);
     TQ_LAUNCH_CHECK("finalize_loss_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_sizeof_gprep(void) { return (int)sizeof(GlobalPrep); }
+
+extern "C" int tq_cosmos_globals_prepare(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
+                                         void* gprep, void* stream) {
+    TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
+    TQ_CHECK_ARG(gparams && mc && gstate && gprep, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ModelConst m = *(const ModelConst*)mc;
+    if (dtype == TQ_F32)
+        globals_prepare_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, gstate, (GlobalPrep*)gprep);
+    else if (dtype == TQ_F64)
+        globals_prepare_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, gstate, (GlobalPrep*)gprep);
+    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("globals_prepare_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
+                                        const double* acc, double sN, double sF, void* ggrads, double* loss, void* stream) {
+    TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
+    TQ_CHECK_ARG(mc && gstate && gprep && acc && ggrads && loss, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ModelConst m = *(const ModelConst*)mc;
+    if (dtype == TQ_F32)
+        globals_finish_kernel<float><<<1, 32, 0, st>>>(Q, m, gstate, (const GlobalPrep*)gprep, acc, sN, sF, (float*)ggrads, loss);
+    else if (dtype == TQ_F64)
+        globals_finish_kernel<double><<<1, 32, 0, st>>>(Q, m, gstate, (const GlobalPrep*)gprep, acc, sN, sF, (double*)ggrads, loss);
+    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    TQ_LAUNCH_CHECK("globals_finish_kernel launch");
     return TQ_OK;
 }
 

@@ -461,13 +461,22 @@ struct Philox {
 // fp32 inline variant of the sampler below for the per-site kernels: inlining keeps the Philox state
 // in registers (the out-of-line generic version takes it by reference, i.e. through local memory).
 TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
+#ifdef __CUDA_ARCH__
+    // MUFU forms: the accept/reject comparison tolerates their ~1e-6 absolute error (a borderline trial
+    // flips with probability ~1e-6; the accepted value d*v itself is exact arithmetic)
+#define TQ_SLOG(x) __logf(x)
+#define TQ_SRSQRT(x) rsqrtf(x)
+#else
+#define TQ_SLOG(x) logf(x)
+#define TQ_SRSQRT(x) (1.0f / sqrtf(x))
+#endif
     float scale = 1.0f;
     if (alpha < 1.0f) {
         scale = powf((float)rng.uniform_d(), 1.0f / alpha);
         alpha += 1.0f;
     }
     const float d = alpha - 1.0f / 3.0f;
-    const float c = 1.0f / sqrtf(9.0f * d);
+    const float c = TQ_SRSQRT(9.0f * d);
     for (int it = 0; it < 64; ++it) {
         float xn, yv;
         do {
@@ -478,9 +487,11 @@ TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
         const float u = rng.uniform();
         const float xx = xn * xn;
         if (u < 1.0f - 0.0331f * xx * xx) return scale * d * v;
-        if (logf(u) < 0.5f * xx + d * (1.0f - v + logf(v))) return scale * d * v;
+        if (TQ_SLOG(u) < 0.5f * xx + d * (1.0f - v + TQ_SLOG(v))) return scale * d * v;
     }
     return scale * d;
+#undef TQ_SLOG
+#undef TQ_SRSQRT
 }
 
 // Marsaglia & Tsang (2000) standard gamma sampler (doi:10.1145/358407.358414), alpha > 0.

@@ -53,7 +53,7 @@ class CosmosEngine:
         self.gain = z(1)
         self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
-        self.elbo_parts = torch.zeros(2 + 2 * 4, dtype=f64, device=dev)   # per-global-site ELBO terms
+        self.gprep = torch.zeros(self.lib.tq_sizeof_gprep() // 8, dtype=f64, device=dev)   # prepared global reverse mode
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
         self.use_graph = use_graph
         self._side = torch.cuda.Stream(device=self.device)
@@ -170,6 +170,9 @@ class CosmosEngine:
                                                         p(self.state), p(self.gstate), p(self.tables), p(self.gain),
                                                         _lib.stream_ptr(self.device)), "tq_cosmos_globals_sample")
                 self._ev_join0.record(self._side)
+                # acc-independent part of the globals' reverse mode: off the critical path, under the likelihood kernel
+                _lib.check(lib.tq_cosmos_globals_prepare(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.gprep),
+                                                         _lib.stream_ptr(self.device)), "tq_cosmos_globals_prepare")
             _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
                                            p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
                        "tq_cosmos_sites")
@@ -189,15 +192,15 @@ class CosmosEngine:
                        "tq_cosmos_local_post")
             if self.world_size > 1:
                 torch.distributed.all_reduce(self.acc, group=self.pg)
-            # the global reverse pass is a latency-bound single-warp kernel; the dense Adam over the
-            # AOI-local buffer does not depend on it, so the two run on forked streams
+            # finishing the global reverse pass (a few FMAs per parameter) + the global Adam run beside the dense
+            # Adam over the AOI-local buffer, which does not depend on them
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):
                 sst = _lib.stream_ptr(self.device)
-                _lib.check(lib.tq_cosmos_globals_grad(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.acc),
-                                                      self.sN, self.sF, p(self.ggrads), p(self.elbo_parts), p(self.loss), sst),
-                           "tq_cosmos_globals_grad")
+                _lib.check(lib.tq_cosmos_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc),
+                                                        self.sN, self.sF, p(self.ggrads), p(self.loss), sst),
+                           "tq_cosmos_globals_finish")
                 if update:
                     b1, b2 = self.betas
                     _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),

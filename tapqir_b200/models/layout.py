@@ -44,14 +44,14 @@ class ModelConst(ctypes.Structure):
 
     _fields_ = [(n, ctypes.c_double) for n in
                 ("bg_mean_std", "bg_std_std", "lamda_rate", "height_std", "width_min", "width_max",
-                 "proximity_rate", "gain_std", "eps", "tiny")] + [("P", ctypes.c_int)]
+                 "proximity_rate", "gain_std", "eps", "tiny", "logit_lim")] + [("P", ctypes.c_int)]
 
     @classmethod
     def make(cls, priors, P, ref_dtype=torch.float64):
         fi = torch.finfo(ref_dtype)
         return cls(priors["background_mean_std"], priors["background_std_std"], priors["lamda_rate"],
                    priors["height_std"], priors["width_min"], priors["width_max"], priors["proximity_rate"],
-                   priors["gain_std"], fi.eps, fi.tiny, int(P))
+                   priors["gain_std"], fi.eps, fi.tiny, math.log((1.0 - fi.eps) / fi.eps), int(P))
 
 
 class LocalLayout:

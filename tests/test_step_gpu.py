@@ -247,3 +247,28 @@ def test_c1_fit_matches_oracle_in_distribution():
     z = model.z_probs
     assert z.shape == (5, 100, 1, 2) and float(z[2:].abs().max()) == 0  # off-target AOIs stay 0
     assert torch.allclose(z[:2].sum(-1), torch.ones(2, 100, 1), atol=1e-4)
+
+
+@pytest.mark.parametrize("C", [1, 2])
+def test_split_global_reverse_mode_equals_one_shot(C):
+    """tq_cosmos_globals_prepare + tq_cosmos_globals_finish (what the engine runs) against the one-shot
+    tq_cosmos_globals_grad on the accumulators of the same step."""
+    import ctypes
+
+    from tapqir_b200 import _lib
+
+    cfg = dict(N=4, F=6, C=C, nb=4, fb=6, seed=11)
+    ds, data, params, ndx, fdx, noise = make_problem(**cfg)
+    eng = make_engine(ds, data, params, 4, 6, torch.float64)
+    loss = eng.step(update=False, **replay_args(eng, data, params, ndx, fdx, noise, torch.float64)).item()
+    split = eng.ggrads.clone()
+    one = torch.zeros_like(eng.ggrads)
+    parts = torch.zeros(2 + 2 * 4, dtype=torch.float64, device="cuda")
+    loss1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    p = _lib.ptr
+    _lib.check(eng.lib.tq_cosmos_globals_grad(eng.code, eng.C, p(eng.gparams), ctypes.byref(eng.mc), p(eng.gstate), p(eng.acc),
+                                              eng.sN, eng.sF, p(one), p(parts), p(loss1), _lib.stream_ptr(eng.device)),
+               "tq_cosmos_globals_grad")
+    torch.cuda.synchronize()
+    assert abs(loss - loss1.item()) <= 1e-13 * abs(loss)
+    assert (split - one).abs().max().item() <= 1e-11 * one.abs().max().item()
