@@ -37,10 +37,30 @@ WORKLOADS = {
     "c3": (1000, 5000, 1000, 5000, "cosmos C3: simulated N=1000 AOIs x F=5000 frames on this GPU, full batch"),
     "c1": (5, 100, 5, 100, "cosmos C1: simulated N=5 AOIs x F=100 frames, full batch"),
 }
-O_BINS = 3
-# algorithmic work per unit, forward + backward
-MUFU_PER_UNIT = 980 * O_BINS + 3276
-FLOP_PER_UNIT = 8232 * O_BINS + 63220
+O_BINS = 3   # offset bins of the simulated data (simulate.py:92,103): three IDENTICAL bins, merged to one on upload
+
+
+def algorithmic_work(o_exec):
+    """Work per unit (one 14x14 patch, K=2, 4 configurations, forward + backward) of the likelihood kernel for
+    ``o_exec`` distinct offset bins -- DESIGN.md section 4.1.  SURVEY.md 8d estimates 980*O + 3276 MUFU ops and
+    8232*O + 63220 flops; the figures here are the TIGHTER counts of this repository's formulation (shared
+    log(D - delta_j); lgamma and digamma from one lg2 + one rcp; one rcp for 1/a and 1/sum; no exp / log-sum
+    at all for a single bin), so that `frac` cannot be flattered by work the kernel does not need:
+      MUFU:  P^2 * O [lg2(D - delta)] + M P^2 * (O + 3) [ex2 per bin, rcp, lg2 a, lg2 sum]  (O > 1)
+             P^2     + M P^2 * 2      [rcp a, lg2 a]                                          (O = 1)
+             + 2 K P [separable render]
+      FP32:  lane-operations (an FMA counts once) of the packed two-pixel sweep, counted in its SASS:
+             98 pairs * (2 * packed + scalar) + ~600 per-patch prologue/epilogue."""
+    P2, M, K, P = 196, 4, 2, 14
+    if o_exec == 1:
+        mufu = P2 + M * P2 * 2 + 2 * K * P
+        fp32_ops = 98 * (2 * 104 + 13) + 600
+    else:
+        mufu = P2 * o_exec + M * P2 * (o_exec + 3) + 2 * K * P
+        fp32_ops = 98 * (2 * (35 + 53 * o_exec) - 2 * 1 + 13) + 600   # 193 packed at O = 3
+    return mufu, fp32_ops
+
+
 HBM_BYTES_PER_UNIT = 604 + 504
 KSMOGN_HBM_BYTES_PER_UNIT = 392 + 8 + 4 * 9 + 4 * 4 + 4 * 4 + 4 * 10  # pixels, xy, samples, W in; L, grads out
 
@@ -157,6 +177,7 @@ def run_native(args):
     ds, nb, fb, desc = make_shard(args.workload, rank, device)
     model = cosmos(device=str(device), dtype="float")
     model.data = ds
+    model.merge_offsets = not args.keep_offset_bins
     model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world, presharded=True)
     eng = model.engine
     units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step (C = 1)
@@ -211,6 +232,9 @@ def run_native(args):
     measured = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = measured.get("hbm_gbs", 6650.0)
     hbm_src = "measured" if "hbm_gbs" in measured else "fallback"
+    o_exec = int(eng.store.offset_samples.numel())   # distinct offset bins the kernels loop over
+    MUFU_PER_UNIT, FP32_OPS_PER_UNIT = algorithmic_work(o_exec)
+    FLOP_PER_UNIT = 2 * FP32_OPS_PER_UNIT                # FMA = 2 flops, like the measured peak
     mufu_ach = MUFU_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
     flop_ach = FLOP_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
     hbm_ach = KSMOGN_HBM_BYTES_PER_UNIT * units_per_step / (k_ms_avg * 1e-3) / 1e9
@@ -226,7 +250,7 @@ def run_native(args):
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
                        "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * units_per_step, "source": t["source"]}
     roofline = {
-        "kernel": "ksmogn_kernel<float,uint16,4,true> (fused render + offset-LSE likelihood fwd+bwd)",
+        "kernel": f"ksmogn_fast_kernel<uint16,{o_exec},true,true> (fused render + offset-marginalised likelihood fwd+bwd)",
         "bound": bound[1],
         "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
         "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
@@ -235,7 +259,9 @@ def run_native(args):
         "traffic": traffic,
         "kernel_ms": k_ms_avg,
         "kernel_share_of_step": k_ms_avg / ms_per_step,
-        "algorithmic_per_unit": {"mufu_ops": MUFU_PER_UNIT, "fp32_flop": FLOP_PER_UNIT, "hbm_bytes": KSMOGN_HBM_BYTES_PER_UNIT},
+        "algorithmic_per_unit": {"mufu_ops": MUFU_PER_UNIT, "fp32_flop": FLOP_PER_UNIT, "hbm_bytes": KSMOGN_HBM_BYTES_PER_UNIT,
+                                 "offset_bins_executed": o_exec,
+                                 "survey_8d_estimate": {"mufu_ops": 980 * o_exec + 3276, "fp32_flop": 8232 * o_exec + 63220}},
         "peaks_measured_here": {"mufu_Tops": peaks["mufu"] / 1e12, "fp32_TFLOPs": 2 * peaks["fma"] / 1e12,
                                 "hbm_GBs": hbm_peak, "hbm_source": hbm_src + " (MEASURED_PEAKS.json)"},
         "hbm_view": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak},
@@ -243,7 +269,7 @@ def run_native(args):
     }
 
     # ---- end to end through the public API with host buffers --------------------------------------------
-    host_pix = ds.device_store(device).pixels.cpu().pin_memory()
+    host_pix = eng.store.pixels.cpu().pin_memory()
     host_xy = eng.store.xy.cpu().pin_memory()
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
     dbg('e2e buffers ready')
@@ -278,8 +304,9 @@ def run_native(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
+                       "offset_bins_distinct": o_exec,
                        "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
-                       "local_terms_dtype": "f64", "likelihood_dtype": "f32"},
+                       "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall, "final_loss": float(eng.loss.item()),
@@ -366,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--keep-offset-bins", action="store_true",
+                    help="do not merge the simulator's three identical offset bins (exercises the O = 3 kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -162,8 +162,44 @@ __device__ __forceinline__ void sweep_patch(const float* __restrict__ pix, int P
     }
 }
 
+// P = 14 common case: lane `sub` takes the pixel pairs (row, col), (row + 7, col) with row * 14 + col = sub + 8 t,
+// t = 0..12 (98 pairs over 8 lanes), in packed two-wide FP32 (ksmogn_fast.cuh)
+template <int OC>
+__device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix, int sub, const float* gx, const float* gy,
+                                                  const PatchSpots<float>& s, const float (&norm)[kK], const FastConst& fc,
+                                                  const float* off_s_sm, const float* off_w2_sm, const float (&W)[kM],
+                                                  PatchOut<float, kM>& out) {
+    constexpr int NC = OC > 0 ? OC : 1;
+    float off_s[NC], off_w2[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { off_s[j] = off_s_sm[j]; off_w2[j] = off_w2_sm[j]; }
+    PairOut po;
+    po.zero();
+    int col = sub, row = 0;
+#pragma unroll 1
+    for (int t = 0; t < 13; ++t) {
+        if (row < 7) {
+            float gxn[kK], dx[kK];
+            F2 gyk[kK], dy[kK];
+            const float fr = float(row);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                gxn[k] = gx[k * kMaxP + col] * norm[k];
+                gyk[k] = F2{gy[k * kMaxP + row], gy[k * kMaxP + row + 7]};
+                dx[k] = float(col) - s.cx[k];
+                dy[k] = F2{fr - s.cy[k], (fr + 7.0f) - s.cy[k]};
+            }
+            const F2 D{pix[row * 14 + col], pix[(row + 7) * 14 + col]};
+            pixel_pair_accumulate_fast<NC>(D, gxn, gyk, dx, dy, s, fc, off_s, off_w2, W, po);
+        }
+        col += 8;
+        if (col >= 14) { col -= 14; ++row; }
+    }
+    finish_pair(po, fc.rate, out);
+}
+
 template <typename PIX, int OC, bool P14, bool BWD>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 5)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 ksmogn_fast_kernel(const KsmognArgs<float> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* off_s = reinterpret_cast<float*>(smem_raw);
@@ -218,6 +254,7 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
 
         // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
         __syncwarp();
+        float pix_min = 3.0e38f;   // smallest pixel of the patch (this lane's share): selects the no-clamp pair form
         {
             const PIX* src = pixels + ui.patch * PP;
             if (P14 && sizeof(PIX) == 2) {
@@ -228,14 +265,20 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
                     const int i = sub + t * kSub;
                     if (i < 49) {
                         const uint2 q = __ldg(v + i);
-                        spx[4 * i + 0] = float(q.x & 0xffffu);
-                        spx[4 * i + 1] = float(q.x >> 16);
-                        spx[4 * i + 2] = float(q.y & 0xffffu);
-                        spx[4 * i + 3] = float(q.y >> 16);
+                        const float p0 = float(q.x & 0xffffu), p1 = float(q.x >> 16), p2 = float(q.y & 0xffffu), p3 = float(q.y >> 16);
+                        spx[4 * i + 0] = p0;
+                        spx[4 * i + 1] = p1;
+                        spx[4 * i + 2] = p2;
+                        spx[4 * i + 3] = p3;
+                        pix_min = fminf(pix_min, fminf(fminf(p0, p1), fminf(p2, p3)));
                     }
                 }
             } else {
-                for (int p = sub; p < PP; p += kSub) spx[p] = float(src[p]);
+                for (int p = sub; p < PP; p += kSub) {
+                    const float pv = float(src[p]);
+                    spx[p] = pv;
+                    pix_min = fminf(pix_min, pv);
+                }
             }
         }
         for (int idx = sub; idx < 2 * kK * P; idx += kSub) {
@@ -252,7 +295,16 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
         const PIX* pix = pixels + ui.patch * PP;
         // a = image/gain is smallest without spots: one test per patch selects the Stirling variant
         const bool small = s.b * fc.rate < 4.0f;
-        if (__any_sync(0xffffffffu, small))
+        bool pairs = false;
+        if (P14 && BWD && OC > 0) {
+            // every pixel above every offset (no -inf handling needed) and no small concentration anywhere in the warp
+            float max_off = off_s[0];
+            for (int j = 1; j < OC; ++j) max_off = fmaxf(max_off, off_s[j]);
+            pairs = __all_sync(0xffffffffu, !small && pix_min > max_off);
+        }
+        if (pairs)
+            sweep_patch_pairs<OC>(spx, sub, gx, gy, s, norm, fc, off_s, off_w2, W, out);
+        else if (__any_sync(0xffffffffu, small))
             sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);
         else
             sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);

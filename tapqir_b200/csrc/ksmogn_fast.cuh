@@ -179,6 +179,161 @@ TQ_HD void pixel_accumulate_fast(float D, const float (&gxk)[kK], const float (&
     }
 }
 
+// ---- packed pairs -------------------------------------------------------------------------------------------
+// sm_100a has two-wide FP32 instructions (fma / add / sub / mul .f32x2 -> FFMA2 / FADD2 / FMUL2): one issue slot
+// for two operations on a 64-bit register pair, scalar operands broadcast for free.  The likelihood kernel
+// is bound by instruction issue, so its common case processes TWO pixels per lane in this form; MUFU ops
+// and the max stay scalar.  Host build (tests/hostcheck): plain pairs of floats.
+struct F2 { float x, y; };
+TQ_HD F2 f2(float a) { return F2{a, a}; }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    F2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+#define TQ_F2_BINARY(name, op)                                                                             \
+    __device__ __forceinline__ F2 name(F2 a, F2 b) {                                                       \
+        F2 d;                                                                                              \
+        asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n" op                    \
+            ".rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"                                                \
+            : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                              \
+        return d;                                                                                          \
+    }
+TQ_F2_BINARY(add2, "add")
+TQ_F2_BINARY(sub2, "sub")
+TQ_F2_BINARY(mul2, "mul")
+#undef TQ_F2_BINARY
+#else
+inline F2 fma2(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline F2 add2(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+inline F2 sub2(F2 a, F2 b) { return F2{a.x - b.x, a.y - b.y}; }
+inline F2 mul2(F2 a, F2 b) { return F2{a.x * b.x, a.y * b.y}; }
+#endif
+TQ_HD F2 lg2_2(F2 a) { return F2{f_lg2(a.x), f_lg2(a.y)}; }
+TQ_HD F2 ex2_2(F2 a) { return F2{f_ex2(a.x), f_ex2(a.y)}; }
+TQ_HD F2 rcp_2(F2 a) { return F2{f_rcp(a.x), f_rcp(a.y)}; }
+
+// per-patch sums of the pair form; gradients w.r.t. the image are accumulated WITHOUT the factor 1/gain
+// (applied once per patch by finish_pair)
+struct PairOut {
+    F2 logp[kM], g_b, g_rate, g_h[kK], g_w[kK], g_x[kK], g_y[kK];
+    F2 common;   // part of the log-probability shared by all configurations (single-offset form)
+    TQ_HD void zero() {
+#pragma unroll
+        for (int m = 0; m < kM; ++m) logp[m] = f2(0.0f);
+        g_b = g_rate = common = f2(0.0f);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) g_h[k] = g_w[k] = g_x[k] = g_y[k] = f2(0.0f);
+    }
+};
+
+// Two pixels of one COLUMN (same x-factor gxn = gx * norm, same dx) at once.  Common case only: every
+// pixel above every offset (no -inf handling) and a = image/gain >= 4 (no recurrence shift); the caller
+// checks both per patch.  Same quantities as pixel_accumulate_fast<kM, OC, true, false>.
+template <int OC>
+TQ_HD void pixel_pair_accumulate_fast(F2 D, const float (&gxn)[kK], const F2 (&gyk)[kK], const float (&dx)[kK],
+                                      const F2 (&dy)[kK], const PatchSpots<float>& s, const FastConst& fc,
+                                      const float (&off_s)[OC], const float (&off_w2)[OC], const float (&W)[kM],
+                                      PairOut& out) {
+    F2 mu[kK], img[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) mu[k] = mul2(gyk[k], f2(gxn[k] * s.h[k]));
+    img[0] = f2(s.b);
+    img[1] = add2(mu[0], f2(s.b));
+    img[2] = add2(mu[1], f2(s.b));
+    img[3] = add2(img[1], mu[1]);
+    F2 y[OC], l2[OC], b2[OC];
+#pragma unroll
+    for (int j = 0; j < OC; ++j) {
+        y[j] = sub2(D, f2(off_s[j]));
+        l2[j] = lg2_2(y[j]);
+        b2[j] = sub2(fma2(f2(-fc.rate2), y[j], f2(off_w2[j])), l2[j]);
+    }
+    // one offset bin (after merging identical support points: the simulated data, simulate.py:92,103): the
+    // log-sum-exp is its single term, softmax weight 1 -- no exponentials, no log / reciprocal of the sum
+    const F2 lny = mul2(l2[0], f2(kLn2));                       // ln y_0
+    const F2 c1 = add2(lny, f2(fc.log_rate));                   // d/da of [a log(rate) + lse] when OC == 1
+    if (OC == 1) out.common = fma2(b2[0], f2(kLn2), out.common);
+    F2 gsum = f2(0.0f), S[kK];
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        const F2 a = mul2(img[m], f2(fc.rate));
+        F2 ia, dl, ym;   // 1/a,  d lse / d a,  softmax mean of y
+        if (OC == 1) {
+            ia = rcp_2(a);
+            ym = y[0];
+        } else {
+            F2 v[OC], mx;
+#pragma unroll
+            for (int j = 0; j < OC; ++j) v[j] = fma2(a, l2[j], b2[j]);
+            mx = v[0];
+#pragma unroll
+            for (int j = 1; j < OC; ++j) { mx.x = fmaxf(mx.x, v[j].x); mx.y = fmaxf(mx.y, v[j].y); }
+            F2 se, sl, sy;
+#pragma unroll
+            for (int j = 0; j < OC; ++j) {
+                const F2 e = ex2_2(sub2(v[j], mx));
+                if (j == 0) { se = e; sl = mul2(e, l2[0]); sy = mul2(e, y[0]); }
+                else { se = add2(se, e); sl = fma2(e, l2[j], sl); sy = fma2(e, y[j], sy); }
+            }
+            const F2 inv = rcp_2(mul2(a, se));   // one reciprocal for 1/a and 1/se
+            ia = mul2(inv, se);
+            const F2 ise = mul2(inv, a);
+            dl = mul2(mul2(sl, ise), f2(kLn2));
+            ym = mul2(sy, ise);
+            out.logp[m] = fma2(add2(mx, lg2_2(se)), f2(kLn2), out.logp[m]);
+        }
+        const F2 la = mul2(lg2_2(a), f2(kLn2));
+        const F2 ia2 = mul2(ia, ia);
+        // Stirling: r = ia (1/12 + ia2 (-1/360 + ia2/1260)),  q = ia (1/2 + ia (1/12 + ia2 (-1/120 + ia2/252)))
+        const F2 r = mul2(ia, fma2(ia2, fma2(ia2, f2(0.000793650794f), f2(-0.00277777778f)), f2(0.0833333333f)));
+        const F2 q = mul2(ia, fma2(ia, fma2(ia2, fma2(ia2, f2(0.00396825397f), f2(-0.00833333333f)), f2(0.0833333333f)), f2(0.5f)));
+        // -lgamma(a) = (1/2 - a) ln a + a - ln(2 pi)/2 - r
+        const F2 nl = sub2(add2(fma2(sub2(f2(0.5f), a), la, a), f2(-kHalfLn2Pi)), r);
+        F2 dLda;   // d/da [a log(rate) - lgamma(a) + lse]
+        if (OC == 1) {
+            out.logp[m] = add2(out.logp[m], fma2(a, c1, nl));
+            dLda = sub2(c1, sub2(la, q));
+        } else {
+            out.logp[m] = add2(out.logp[m], fma2(a, f2(fc.log_rate), nl));
+            dLda = add2(dl, sub2(f2(fc.log_rate), sub2(la, q)));
+        }
+        const F2 gi = mul2(dLda, f2(W[m]));   // times rate: finish_pair
+        out.g_rate = fma2(sub2(fma2(img[m], dLda, img[m]), ym), f2(W[m]), out.g_rate);
+        gsum = add2(gsum, gi);
+        if (m == 1) S[0] = gi;
+        if (m == 2) S[1] = gi;
+        if (m == 3) { S[0] = add2(S[0], gi); S[1] = add2(S[1], gi); }
+    }
+    out.g_b = add2(out.g_b, gsum);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const F2 t = mul2(S[k], mu[k]);
+        out.g_h[k] = add2(out.g_h[k], t);
+        out.g_x[k] = fma2(t, f2(dx[k]), out.g_x[k]);
+        out.g_y[k] = fma2(t, dy[k], out.g_y[k]);
+        out.g_w[k] = fma2(t, fma2(dy[k], dy[k], f2(dx[k] * dx[k])), out.g_w[k]);
+    }
+}
+
+// lane-level fold of the pair sums into the scalar record (before the cross-lane reduction)
+TQ_HD void finish_pair(const PairOut& p, float rate, PatchOut<float, kM>& out) {
+#pragma unroll
+    for (int m = 0; m < kM; ++m) out.logp[m] = (p.logp[m].x + p.logp[m].y) + (p.common.x + p.common.y);
+    out.g_b = (p.g_b.x + p.g_b.y) * rate;
+    out.g_rate = p.g_rate.x + p.g_rate.y;
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        out.g_h[k] = (p.g_h[k].x + p.g_h[k].y) * rate;
+        out.g_w[k] = (p.g_w[k].x + p.g_w[k].y) * rate;
+        out.g_x[k] = (p.g_x[k].x + p.g_x[k].y) * rate;
+        out.g_y[k] = (p.g_y[k].x + p.g_y[k].y) * rate;
+    }
+}
+
 // Per-patch conversion of the accumulated moments (after the cross-lane reduction):
 //   A0 = sum t, A1 = sum t dx, A2 = sum t dy, A3 = sum t (dx^2 + dy^2)
 //   d/dh = A0 / h,  d/dx = A1 / w^2,  d/dy = A2 / w^2,  d/dw = A3 / w^3 - 2 A0 / w

@@ -114,7 +114,8 @@ class cosmos(Model):
         if self.device.type != "cuda":
             raise RuntimeError("tapqir_b200 has no CPU execution path: construct the model with device='cuda'")
         sl = self._shard()
-        store = self.data.device_store(self.device, self.dtype, sl)
+        # identical offset bins are merged on upload unless model.merge_offsets is set to False (utils/dataset.py)
+        store = self.data.device_store(self.device, self.dtype, sl, merge_offsets=getattr(self, "merge_offsets", True))
         self.engine = CosmosEngine(
             store, sl.stop - sl.start, self.data.F, self.data.C, self.data.P, self.priors, dtype=self.dtype,
             lr=self.lr, betas=self.optim_args["betas"], nbatch_size=self.nbatch_size, fbatch_size=self.fbatch_size,

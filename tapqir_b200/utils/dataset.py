@@ -53,6 +53,21 @@ class OffsetData(namedtuple("OffsetData", ["samples", "weights"])):
 DeviceStore = namedtuple("DeviceStore", ["pixels", "xy", "is_ontarget", "mask", "offset_samples", "offset_logits"])
 
 
+def merge_offset_support(samples, logits):
+    """
+    Distinct support points of the empirical offset distribution: bins with the same sample value are
+    merged and their weights added.  The likelihood marginalises the offset as ``sum_j w_j f(D - delta_j)``
+    (ksmogn.py:222-238), so this is an identity, and the kernels' work per pixel is proportional to the
+    number of bins.  The reference's simulator writes three identical bins (simulate.py:92,103); histograms
+    from real movies (glimpse_reader.py:421) have distinct bins and pass through unchanged.
+    """
+    uniq, inverse = torch.unique(samples, sorted=True, return_inverse=True)
+    if uniq.numel() == samples.numel():
+        return samples, logits
+    weights = torch.zeros_like(uniq, dtype=torch.float64).index_add_(0, inverse, logits.double().exp())
+    return uniq, weights.log().to(logits.dtype)
+
+
 class CosmosDataset:
     """AOI x frame x channel stack of PxP patches with target positions and labels."""
 
@@ -144,14 +159,15 @@ class CosmosDataset:
             self.is_ontarget[ndx].to(self.device),
         )
 
-    def device_store(self, device=None, dtype=torch.float32, aoi_slice=slice(None)) -> DeviceStore:
+    def device_store(self, device=None, dtype=torch.float32, aoi_slice=slice(None), merge_offsets=True) -> DeviceStore:
         """
         One-time upload of (a contiguous AOI shard of) the dataset in the layout the kernels read:
         pixels (Nt,F,C,P,P) uint16|float32, xy (Nt,F,C,2) ``dtype``, is_ontarget / mask (Nt,) uint8,
-        offset samples / log-weights (O,) ``dtype``.
+        offset samples / log-weights (O,) ``dtype``; identical offset bins merged
+        (:func:`merge_offset_support`) unless ``merge_offsets=False``.
         """
         device = torch.device(device or self.device)
-        key = (str(device), dtype, aoi_slice.start, aoi_slice.stop)
+        key = (str(device), dtype, aoi_slice.start, aoi_slice.stop, merge_offsets)
         if self._store is not None and self._store[0] == key:
             return self._store[1]
         img = self.images[aoi_slice]
@@ -160,13 +176,16 @@ class CosmosDataset:
             pixels = img.to(torch.int32).to(torch.uint16).contiguous().to(device)
         else:
             pixels = img.to(torch.float32).contiguous().to(device)
+        off_s, off_l = self.offset.samples, self.offset.logits
+        if merge_offsets:
+            off_s, off_l = merge_offset_support(off_s, off_l)
         store = DeviceStore(
             pixels=pixels,
             xy=self.xy[aoi_slice].to(device=device, dtype=dtype).contiguous(),
             is_ontarget=self.is_ontarget[aoi_slice].to(device=device, dtype=torch.uint8).contiguous(),
             mask=self.mask[aoi_slice].to(device=device, dtype=torch.uint8).contiguous(),
-            offset_samples=self.offset.samples.to(device=device, dtype=dtype).contiguous(),
-            offset_logits=self.offset.logits.to(device=device, dtype=dtype).contiguous(),
+            offset_samples=off_s.to(device=device, dtype=dtype).contiguous(),
+            offset_logits=off_l.to(device=device, dtype=dtype).contiguous(),
         )
         self._store = (key, store)
         return store

@@ -2,6 +2,7 @@
 // Compiled with g++ by tests/hostcheck/__init__.py; lets `-m "not gpu"` tests compare the exact
 // per-pixel / per-unit formulas the kernels execute against the oracle without a GPU.  Nothing
 // in the product imports or links this file.
+#include <algorithm>
 #include <cstdint>
 #include <vector>
 
@@ -70,6 +71,37 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
         for (int m = 0; m < kM; ++m) { Wm[m] = W[m * U + u]; Wr[m] = Wm[m] * fc.rate; }
         const bool small = s.b * fc.rate < 4.0f;
         PatchOut<float, kM> out; out.zero();
+        // the kernel's common case (P = 14, cached offsets, no small concentration, every pixel above every offset):
+        // packed pairs of pixels (rows r, r + 7 of one column)
+        bool pairs = P == 14 && OC >= 1 && OC <= 4 && OC == O && !small;
+        if (pairs) {
+            float max_off = off_s[0];
+            for (int j = 1; j < O; ++j) max_off = std::max(max_off, off_s[j]);
+            for (int p = 0; p < P * P; ++p) pairs = pairs && value[u * P * P + p] > max_off;
+        }
+        if (pairs) {
+            PairOut po; po.zero();
+            auto run = [&](auto oc_tag) {
+                constexpr int OCc = decltype(oc_tag)::value;
+                float os[OCc], ow[OCc];
+                for (int j = 0; j < OCc; ++j) { os[j] = off_s[j]; ow[j] = w2[j]; }
+                for (int row = 0; row < 7; ++row)
+                    for (int col = 0; col < 14; ++col) {
+                        float gxn[kK], dx[kK]; F2 gyk[kK], dy[kK];
+                        for (int k = 0; k < kK; ++k) {
+                            gxn[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k];
+                            gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
+                            dx[k] = float(col) - s.cx[k];
+                            dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
+                        }
+                        const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
+                        pixel_pair_accumulate_fast<OCc>(D, gxn, gyk, dx, dy, s, fc, os, ow, Wm, po);
+                    }
+            };
+            switch (OC) { case 1: run(std::integral_constant<int, 1>{}); break; case 2: run(std::integral_constant<int, 2>{}); break;
+                          case 3: run(std::integral_constant<int, 3>{}); break; default: run(std::integral_constant<int, 4>{}); break; }
+            finish_pair(po, fc.rate, out);
+        } else
         for (int row = 0; row < P; ++row)
             for (int col = 0; col < P; ++col) {
                 float gxk[kK], gyk[kK];

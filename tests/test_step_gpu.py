@@ -14,10 +14,10 @@ from tests.step_helpers import compare_grads, flat_inputs, make_problem
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(ds, data, params, nb, fb, dtype, **kw):
+def make_engine(ds, data, params, nb, fb, dtype, merge_offsets=True, **kw):
     from tapqir_b200.models.engine import CosmosEngine
 
-    store = ds.device_store("cuda", dtype)
+    store = ds.device_store("cuda", dtype, merge_offsets=merge_offsets)
     eng = CosmosEngine(store, data.Nt, data.F, data.C, data.P, O.DEFAULT_PRIORS, dtype=dtype, nbatch_size=nb,
                        fbatch_size=fb, **kw)
     eng.load_unconstrained(params)
@@ -272,3 +272,21 @@ def test_split_global_reverse_mode_equals_one_shot(C):
     torch.cuda.synchronize()
     assert abs(loss - loss1.item()) <= 1e-13 * abs(loss)
     assert (split - one).abs().max().item() <= 1e-11 * one.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
+def test_step_with_unmerged_offset_bins(dtype, ltol, gtol):
+    """The simulator's three identical offset bins kept as three (merge_offsets=False): the O = 3 kernels."""
+    cfg = dict(N=5, F=40, C=1, nb=5, fb=40, seed=13)
+    ds, data, params, ndx, fdx, noise = make_problem(**cfg)
+    if dtype == torch.float32:
+        params = {k: v.float().double() for k, v in params.items()}
+        noise = {k: v.float().double() for k, v in noise.items()}
+    ref_loss, ref_grads = O.loss_and_grads(params, data, ndx, fdx, noise)
+    eng = make_engine(ds, data, params, cfg["nb"], cfg["fb"], dtype, merge_offsets=False)
+    assert eng.store.offset_samples.numel() == 3
+    loss = eng.step(update=False, **replay_args(eng, data, params, ndx, fdx, noise, dtype)).item()
+    assert abs(loss - ref_loss) <= ltol * abs(ref_loss)
+    assert not compare_grads(eng.named_grads(), ref_grads, gtol)
+    merged = make_engine(ds, data, params, cfg["nb"], cfg["fb"], dtype)
+    assert merged.store.offset_samples.numel() == 1
