@@ -121,7 +121,10 @@ int tq_sizeof_model_const(void);   /* sizeof(tq_model_const) as compiled */
 int tq_sizeof_tables(void);        /* bytes of the device-side global tables blob */
 int tq_sizeof_gstate(void);        /* bytes of the device-side global variates+samples blob */
 int tq_site_record_rows(void);     /* rows NREC of the per-site record buffer (NREC, U) */
-int tq_local_post_blocks(int64_t U); /* thread blocks tq_cosmos_local_post launches for U units */
+/* scratch of tq_cosmos_local_post for a minibatch of nb AOIs x fb frames x C channels, in doubles:
+ * block_partial (plain scratch) and tickets (must be ZERO before the first call; left zeroed by every call) */
+int64_t tq_local_post_scratch(int nb, int fb, int C);
+int64_t tq_local_post_tickets(int nb, int fb, int C);
 
 /* pyro.plate(subsample_size=n) [third party: randperm(size)[:n]]: uniform sample without
  * replacement by a partial Fisher-Yates on the persistent permutation `perm` (n_total int32,
@@ -151,11 +154,13 @@ int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void
  * gs (9, U) and g_rate (U,) from tq_ksmogn_fwd_bwd with W = qm.  sN = Nt_total / nb_total and
  * sF = F / fb are the plate scales.  Outputs: lgrads (local flat layout; entries of the minibatch
  * units and of their AOIs), acc (C, 18) per-channel sums for the globals (double);
- * aoi_partial (2, U) and block_partial (tq_local_post_blocks(U), C, 18) are scratch (double). */
+ * tickets (tq_local_post_tickets doubles, zero-initialised once by the caller) and block_partial
+ * (tq_local_post_scratch doubles) are scratch: the cross-unit sums (channel accumulators, AOI-level gradients)
+ * are reduced inside the launch in a fixed order by the last block to finish. */
 int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
                          const void* lparams, const void* tables, const void* samples,
                          const void* rec, const void* L, const void* gs, const void* g_rate,
-                         double sN, double sF, void* lgrads, double* aoi_partial,
+                         double sN, double sF, void* lgrads, double* tickets,
                          double* block_partial, double* acc, void* stream);
 
 /* Posterior of the enumerated latents for one guide draw (cosmos.compute_probs, cosmos.py:609-672):

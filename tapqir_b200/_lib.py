@@ -46,7 +46,8 @@ SIGNATURES = {
     "tq_sizeof_tables": (c_int, []),
     "tq_sizeof_gstate": (c_int, []),
     "tq_sizeof_model_const": (c_int, []),
-    "tq_local_post_blocks": (c_int, [c_int64]),
+    "tq_local_post_scratch": (c_int64, [c_int, c_int, c_int]),
+    "tq_local_post_tickets": (c_int64, [c_int, c_int, c_int]),
     "tq_cosmos_globals_sample": (c_int, [c_int, c_int, _VP, _VP, _VP, c_uint64, _VP, _VP, _VP, _VP, _VP]),
     "tq_site_record_rows": (c_int, []),
     "tq_cosmos_sites": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,

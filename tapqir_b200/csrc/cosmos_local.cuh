@@ -455,10 +455,10 @@ TQ_HD void unit_post(const F (&rec)[NREC], const F (&sample)[NSAMP], const F (&L
         for (int z = 0; z < kZ; ++z)
 #pragma unroll
             for (int th = 0; th < kTheta; ++th) {
-                lj[z][th] = R::exp(lj[z][th] - mx);
+                lj[z][th] = R::exp_fast(lj[z][th] - mx);
                 se += lj[z][th];
             }
-        const F T = mx + R::log(se);
+        const F T = mx + R::log_fast(se);
         F q = F(1), lq = F(0), Cm = T + L[m];
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
@@ -572,7 +572,7 @@ TQ_HD void unit_ztheta_posterior(F x_[kK], F y_[kK], const F (&u_mp)[kK], const 
         for (int z = 0; z < kZ; ++z)
 #pragma unroll
             for (int th = 0; th < kTheta; ++th) {
-                lj[z][th] = R::exp(lj[z][th] - mx);
+                lj[z][th] = R::exp_fast(lj[z][th] - mx);
                 se += lj[z][th];
             }
         F q = F(1);

@@ -24,11 +24,12 @@ struct LocalOffsets {
         if (t < 4) return 2 * aoi + (t - 2) * unit;
         return 2 * aoi + 2 * unit + (int64_t)(t - 4) * kK * unit;
     }
+    // flat index of local record entry i (LP_* order) for (aoi n, frame f, channel c).  Entries 2.. are
+    // (Nt, F, C) slabs in LP_* order -- the K slabs of a (K, Nt, F, C) tensor are consecutive entries -- so
+    // one multiply-add serves them all
     __host__ __device__ int64_t index(int i, int64_t n, int64_t f, int64_t c) const {
-        if (i < 2) return tensor_off(i) + n * C + c;
-        if (i < 4) return tensor_off(i) + (n * F + f) * C + c;
-        const int t = 4 + (i - 4) / kK, k = (i - 4) % kK;
-        return tensor_off(t) + ((k * Nt + n) * F + f) * C + c;
+        if (i < 2) return (int64_t)i * (Nt * C) + n * C + c;
+        return 2 * (Nt * C) + (int64_t)(i - 2) * (Nt * F * C) + (n * F + f) * C + c;
     }
     __host__ __device__ int64_t numel() const { return tensor_off(12); }
 };
@@ -189,70 +190,165 @@ __global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<
     if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
 }
 
+constexpr int kFallbackUPT = 4;   // markers checked per thread: the kernel almost always finds none
 __global__ void __launch_bounds__(kLocalBlock) site_fallback_kernel(const LocalArgs<float> a) {
     const int s = blockIdx.y;
-    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
-    if (u32 >= (uint32_t)a.U) return;
-    const float marker = a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32];
-    if (marker == marker) return;
-    site_double(a, s, u32);
+    const uint32_t u0 = (blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x) * kFallbackUPT;
+    const float* marker = a.rec + ((int64_t)s * NSO + SO_LQ) * a.U;
+#pragma unroll 1
+    for (int j = 0; j < kFallbackUPT; ++j) {
+        const uint32_t u32 = u0 + j;
+        if (u32 >= (uint32_t)a.U) return;
+        const float m = marker[u32];
+        if (m != m) site_double(a, s, u32);
+    }
 }
 
-// ---- post: thread per unit (cheap) + deterministic block reduction of the channel accumulators -----------
-template <typename T>
-__global__ void __launch_bounds__(kLocalBlock) local_post_kernel(const LocalArgs<T> a) {
-    __shared__ double red[kLocalBlock / 32][NACC];
+// ---- post: blocks per (AOI, channel) chunk of frames, kPostUPT units per thread; the cross-unit sums are fused in ----
+// Every block reduces its NACC channel accumulators and the two AOI-level gradient sums in a fixed order into
+// block_partial; the last block of an (AOI, channel) to finish (atomic ticket) adds that AOI's partials in index
+// order and writes d loss / d (background_mean_loc, background_std_loc); the last block of the launch does the
+// same for the channel accumulators.  Fixed summation order => run-to-run deterministic, whichever block is last.
+// `tickets`: (nb * C + 1) zero-initialised counters, left zeroed for the next launch.
+constexpr int kPostRed = NACC + 2;
+
+// units per thread: 4 amortises the block reduction when there are enough blocks to fill the GPU, else 1
+__host__ __device__ inline int post_upt(int nb, int fb, int C) {
+    return (int64_t)nb * C * ((fb + kLocalBlock * 4 - 1) / (kLocalBlock * 4)) >= 2048 ? 4 : 1;
+}
+__host__ __device__ inline int post_chunks(int fb, int upt) { return (fb + kLocalBlock * upt - 1) / (kLocalBlock * upt); }
+
+template <typename T, int kPostUPT>
+__global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalArgs<T> a, int chunks, unsigned int* __restrict__ tickets,
+                                                                double* __restrict__ acc_out) {
+    __shared__ double red[kLocalBlock / 32][kPostRed];
     __shared__ GlobalTables<T> gt;
+    __shared__ int last_flags[2];
     if (threadIdx.x == 0) gt.convert_from(*a.tables);
     __syncthreads();
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = u < a.U;
-    UnitGrads<T> ug;
-    int my_c = -1;
-    double mu = 0.0;
-    if (live) {
-        const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
-        const int64_t f = a.v.fdx ? a.v.fdx[ui.fi] : ui.fi;
-        my_c = ui.c;
-        mu = a.v.mask[ui.aoi] ? 1.0 : 0.0;
+    const int fb = a.v.fb, C = a.v.C;
+    const int chunk = blockIdx.x % chunks;
+    const int nc = blockIdx.x / chunks;          // (ni, c) pair
+    const int c = nc % C, ni = nc / C;
+    const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
+    const double mu = a.v.mask[n] ? 1.0 : 0.0;
+    const bool ontarget = a.v.is_ontarget[n] != 0;
+    const T u_bm = a.lparams[a.lo.index(LP_BM, n, 0, c)], u_bs = a.lparams[a.lo.index(LP_BS, n, 0, c)];
+    const T scale = (T)(-a.sN * a.sF * mu);  // loss = -ELBO
+    T sum[kPostRed];   // this thread's kPostUPT units in T (a handful of terms); everything across threads in double
+#pragma unroll
+    for (int i = 0; i < kPostRed; ++i) sum[i] = T(0);
+#pragma unroll 1
+    for (int t = 0; t < kPostUPT; ++t) {
+        const int fi = (chunk * kPostUPT + t) * kLocalBlock + threadIdx.x;
+        if (fi >= fb) break;
+        const int64_t u = ((int64_t)ni * fb + fi) * C + c;
+        const int64_t f = a.v.fdx ? a.v.fdx[fi] : fi;
         T rec[NREC], sample[NSAMP], gs[NSAMP], L[kM], u_mp[kK];
+        {   // SoA rows are U apart: running pointers instead of a 64-bit multiply per load
+            const T* pr = a.rec + u;
 #pragma unroll
-        for (int i = 0; i < NREC; ++i) rec[i] = a.rec[(int64_t)i * a.U + u];
+            for (int i = 0; i < NREC; ++i, pr += a.U) rec[i] = *pr;
+            const T* ps = a.samples + u;
+            const T* pg = a.gs + u;
 #pragma unroll
-        for (int i = 0; i < NSAMP; ++i) {
-            sample[i] = a.samples[(int64_t)i * a.U + u];
-            gs[i] = a.gs[(int64_t)i * a.U + u];
+            for (int i = 0; i < NSAMP; ++i, ps += a.U, pg += a.U) { sample[i] = *ps; gs[i] = *pg; }
+            const T* pl = a.L + u;
+#pragma unroll
+            for (int m = 0; m < kM; ++m, pl += a.U) L[m] = *pl;
         }
 #pragma unroll
-        for (int m = 0; m < kM; ++m) L[m] = a.L[m * a.U + u];
+        for (int k = 0; k < kK; ++k) u_mp[k] = a.lparams[a.lo.index(LP_M_PROBS + k, n, f, c)];
+        UnitGrads<T> ug;
+        unit_post<T>(rec, sample, L, gs, a.g_rate[u], u_mp, u_bm, u_bs, a.mc, gt, c, ontarget, fi == 0, ug);
 #pragma unroll
-        for (int k = 0; k < kK; ++k) u_mp[k] = a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, f, ui.c)];
-        const T u_bm = a.lparams[a.lo.index(LP_BM, ui.aoi, f, ui.c)], u_bs = a.lparams[a.lo.index(LP_BS, ui.aoi, f, ui.c)];
-        unit_post<T>(rec, sample, L, gs, a.g_rate[u], u_mp, u_bm, u_bs, a.mc, gt, ui.c,
-                     a.v.is_ontarget[ui.aoi] != 0, ui.fi == 0, ug);
-        const T s = (T)(-a.sN * a.sF * mu);  // loss = -ELBO
+        for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, n, f, c)] = scale * ug.g[i];
 #pragma unroll
-        for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, ui.aoi, f, ui.c)] = s * ug.g[i];
-        a.aoi_partial[u] = mu * (double)ug.g[LP_BM];
-        a.aoi_partial[a.U + u] = mu * (double)ug.g[LP_BS];
+        for (int i = 0; i < NACC; ++i) sum[i] += ug.acc[i];
+        sum[NACC] += ug.g[LP_BM];
+        sum[NACC + 1] += ug.g[LP_BS];
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = 0; c < a.v.C; ++c) {
 #pragma unroll
-        for (int i = 0; i < NACC; ++i) {
-            double v = (live && my_c == c) ? mu * (double)ug.acc[i] : 0.0;
-            v = warp_sum(v);
-            if (lane == 0) red[warp][i] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < NACC) {
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < kLocalBlock / 32; ++w) v += red[w][threadIdx.x];
-            a.block_partial[((int64_t)blockIdx.x * a.v.C + c) * NACC + threadIdx.x] = v;
-        }
-        __syncthreads();
+    for (int i = 0; i < kPostRed; ++i) {
+        const double v = warp_sum((double)sum[i]);
+        if (lane == 0) red[warp][i] = v;
     }
+    __syncthreads();
+    if (threadIdx.x < kPostRed) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLocalBlock / 32; ++w) v += red[w][threadIdx.x];
+        a.block_partial[(int64_t)blockIdx.x * kPostRed + threadIdx.x] = mu * v;
+    }
+    // publish: the barrier orders the writers before thread 0, whose (cumulative) fence + ticket make them visible
+    // device-wide -- the pattern of a cooperative-groups grid barrier.  (Fencing in every thread instead makes each
+    // warp wait for its own gradient stores to drain.)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t1 = atomicAdd(&tickets[nc], 1u);
+        last_flags[0] = (t1 == (unsigned int)chunks - 1u);
+        if (last_flags[0]) { tickets[nc] = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    if (!last_flags[0]) return;
+
+    // ---- last block of this (AOI, channel): add its chunks in index order --------------------------------------------
+    const int n_nc = a.v.nb * C;
+    double* aoi_sums = a.block_partial + (int64_t)n_nc * chunks * kPostRed;   // (nb * C, kPostRed), after the chunk partials
+    if (threadIdx.x < kPostRed) {
+        const double* bp = a.block_partial + (int64_t)nc * chunks * kPostRed + threadIdx.x;
+        double v = 0.0;
+        for (int k0 = 0; k0 < chunks; k0 += 8) {
+            double t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldcg(bp + (int64_t)min(k0 + j, chunks - 1) * kPostRed);   // loads first ...
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v += (k0 + j < chunks) ? t[j] : 0.0;                                 // ... then a fixed-order sum
+        }
+        aoi_sums[(int64_t)nc * kPostRed + threadIdx.x] = v;
+        if (threadIdx.x >= NACC) {
+            // d loss / d (background_mean_loc, background_std_loc)[n, 0, c]: its frames + the AOI-level prior
+            double pbm, pbs;
+            aoi_prior_grad((double)u_bm, (double)u_bs, a.mc, pbm, pbs);
+            const bool is_bm = threadIdx.x == NACC;
+            a.lgrads[a.lo.index(is_bm ? LP_BM : LP_BS, n, 0, c)] = (T)(-(a.sN * a.sF * v + a.sN * mu * (is_bm ? pbm : pbs)));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t2 = atomicAdd(&tickets[n_nc], 1u);
+        last_flags[1] = (t2 == (unsigned int)n_nc - 1u);
+        if (last_flags[1]) { tickets[n_nc] = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    if (!last_flags[1]) return;
+
+    // ---- last block of the launch: channel accumulators = sum over AOIs, in index order ---------------------------------
+    // thread (cc, i, part) adds every kParts-th AOI of channel cc, loads batched eight at a time; the kParts partial sums
+    // are then combined in a fixed order
+    constexpr int kParts = 4;
+    __shared__ double fin[kMaxC * NACC][kParts];
+    for (int w = threadIdx.x; w < C * NACC * kParts; w += kLocalBlock) {
+        const int part = w % kParts, vi = w / kParts;
+        const int cc = vi / NACC, i = vi - cc * NACC;
+        double v = 0.0;
+        for (int q0 = part; q0 < a.v.nb; q0 += kParts * 8) {
+            double t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int q = min(q0 + kParts * j, a.v.nb - 1);
+                t[j] = __ldcg(aoi_sums + ((int64_t)q * C + cc) * kPostRed + i);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v += (q0 + kParts * j < a.v.nb) ? t[j] : 0.0;
+        }
+        fin[vi][part] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < C * NACC) acc_out[threadIdx.x] = (fin[threadIdx.x][0] + fin[threadIdx.x][1]) + (fin[threadIdx.x][2] + fin[threadIdx.x][3]);
 }
 
 // ---- z / theta posterior of one particle, accumulated into the running means (row N1) ---------------------
@@ -278,50 +374,6 @@ __global__ void __launch_bounds__(kLocalBlock) zprobs_kernel(const LocalArgs<T> 
     for (int z = 0; z < kZ; ++z) z_probs[u * kZ + z] += weight * pz[z];
 #pragma unroll
     for (int k = 0; k < kK; ++k) theta_probs[(int64_t)k * a.U + u] += weight * pth[k];
-}
-
-// ---- reductions (fixed order => run-to-run deterministic) ---------------------------------------------------
-// acc[c][i] = sum over blocks; one warp per (c, i)
-__global__ void reduce_acc_kernel(const double* __restrict__ block_partial, int nblocks, int C,
-                                  double* __restrict__ acc) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= C * NACC) return;
-    const int c = warp / NACC, i = warp - c * NACC;
-    double v = 0.0;
-    for (int b = lane; b < nblocks; b += 32) v += block_partial[((int64_t)b * C + c) * NACC + i];
-    v = warp_sum(v);
-    if (lane == 0) acc[c * NACC + i] = v;
-}
-
-// d loss / d (background_mean_loc, background_std_loc)[n, 0, c]: sum over the minibatch frames of the
-// per-unit contributions + the AOI-level prior; one 128-thread block per (ni, c), fixed-order tree
-template <typename T>
-__global__ void __launch_bounds__(128) reduce_aoi_kernel(const LocalArgs<T> a) {
-    __shared__ double red[2][4];
-    const int fb = a.v.fb, C = a.v.C;
-    const int ni = blockIdx.x / C, c = blockIdx.x - ni * C;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double sbm = 0.0, sbs = 0.0;
-    for (int fi = threadIdx.x; fi < fb; fi += blockDim.x) {
-        const int64_t u = ((int64_t)ni * fb + fi) * C + c;
-        sbm += a.aoi_partial[u];
-        sbs += a.aoi_partial[a.U + u];
-    }
-    sbm = warp_sum(sbm);
-    sbs = warp_sum(sbs);
-    if (lane == 0) { red[0][warp] = sbm; red[1][warp] = sbs; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        sbm = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-        sbs = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
-        const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
-        const double mu = a.v.mask[n] ? 1.0 : 0.0;
-        const int64_t ibm = a.lo.index(LP_BM, n, 0, c), ibs = a.lo.index(LP_BS, n, 0, c);
-        double pbm, pbs;
-        aoi_prior_grad((double)a.lparams[ibm], (double)a.lparams[ibs], a.mc, pbm, pbs);
-        a.lgrads[ibm] = (T)(-(a.sN * a.sF * sbm + a.sN * mu * pbm));
-        a.lgrads[ibs] = (T)(-(a.sN * a.sF * sbs + a.sN * mu * pbs));
-    }
 }
 
 // ---- globals: reverse mode; one block per global site, then a fixed-order sum of the ELBO parts -----------------
@@ -445,7 +497,12 @@ using namespace tq;
 extern "C" int tq_sizeof_tables(void) { return (int)sizeof(GlobalTables<double>); }
 extern "C" int tq_sizeof_gstate(void) { return (int)(2 * kMaxGlobalNoise * sizeof(double)); }
 extern "C" int tq_sizeof_model_const(void) { return (int)sizeof(ModelConst); }
-extern "C" int tq_local_post_blocks(int64_t U) { return local_blocks(U); }
+// doubles of `block_partial` scratch and 8-byte slots of zero-initialised `aoi_partial` (ticket) scratch that
+// tq_cosmos_local_post needs for a minibatch of nb AOIs x fb frames x C channels
+extern "C" int64_t tq_local_post_scratch(int nb, int fb, int C) {
+    return (int64_t)nb * C * (post_chunks(fb, post_upt(nb, fb, C)) + 1) * kPostRed;   // per-chunk partials + per-(AOI, channel) sums
+}
+extern "C" int64_t tq_local_post_tickets(int nb, int fb, int C) { (void)fb; return ((int64_t)nb * C + 1 + 1) / 2; }
 extern "C" int tq_site_record_rows(void) { return NREC; }
 
 extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
@@ -482,7 +539,7 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
     if constexpr (sizeof(T) == sizeof(float)) {
         site_fast_kernel<<<grid, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fast_kernel launch");
-        site_fallback_kernel<<<grid, kLocalBlock, 0, st>>>(a);
+        site_fallback_kernel<<<dim3((grid.x + kFallbackUPT - 1) / kFallbackUPT, NSAMP), kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fallback_kernel launch");
     } else {
         site_kernel<T><<<grid, kLocalBlock, 0, st>>>(a);
@@ -518,16 +575,17 @@ static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelCons
     a.lgrads = (T*)lgrads;
     a.aoi_partial = aoi_partial;
     a.block_partial = block_partial;
-    const int nblocks = local_blocks(a.U);
+    const int upt = post_upt(view->nb, view->fb, view->C);
+    const int chunks = post_chunks(view->fb, upt);
+    const int64_t nblocks = (int64_t)view->nb * view->C * chunks;
     if (a.U > 0) {
-        local_post_kernel<T><<<nblocks, kLocalBlock, 0, st>>>(a);
+        if (nblocks >= (int64_t)1 << 31) { set_error("minibatch too large for one launch"); return TQ_ERR_ARG; }
+        if (upt == 4) local_post_kernel<T, 4><<<(int)nblocks, kLocalBlock, 0, st>>>(a, chunks, (unsigned int*)aoi_partial, acc);
+        else local_post_kernel<T, 1><<<(int)nblocks, kLocalBlock, 0, st>>>(a, chunks, (unsigned int*)aoi_partial, acc);
         TQ_LAUNCH_CHECK("local_post_kernel launch");
-        reduce_aoi_kernel<T><<<view->nb * view->C, 128, 0, st>>>(a);
-        TQ_LAUNCH_CHECK("reduce_aoi_kernel launch");
+    } else {
+        cudaMemsetAsync(acc, 0, sizeof(double) * view->C * NACC, st);
     }
-    const int rw = view->C * NACC;
-    reduce_acc_kernel<<<(rw * 32 + 127) / 128, 128, 0, st>>>(block_partial, a.U > 0 ? nblocks : 0, view->C, acc);
-    TQ_LAUNCH_CHECK("reduce_acc_kernel launch");
     return TQ_OK;
 }
 

@@ -198,8 +198,8 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
     finish_pair(po, fc.rate, out);
 }
 
-template <typename PIX, int OC, bool P14, bool BWD>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+template <typename PIX, int OC, bool P14, bool BWD, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 ksmogn_fast_kernel(const KsmognArgs<float> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* off_s = reinterpret_cast<float*>(smem_raw);
@@ -343,10 +343,10 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
     }
 }
 
-template <typename PIX, int OC, bool P14, bool BWD>
-static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
+template <typename PIX, int OC, bool P14, bool BWD, int MINB>
+static int launch_fast_b(const KsmognArgs<float>& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * (2 * (size_t)a.v.O + kUnitsPerBlock * (2 * kK * kMaxP + (size_t)a.v.P * a.v.P));
-    auto kern = ksmogn_fast_kernel<PIX, OC, P14, BWD>;
+    auto kern = ksmogn_fast_kernel<PIX, OC, P14, BWD, MINB>;
     if (smem > 48 * 1024) {
         int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                               "cudaFuncSetAttribute(ksmogn_fast)");
@@ -360,6 +360,13 @@ static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
     kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
     TQ_LAUNCH_CHECK("ksmogn_fast_kernel launch");
     return TQ_OK;
+}
+
+template <typename PIX, int OC, bool P14, bool BWD>
+static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
+    // 4 resident blocks per SM (<= 128 registers): measured 115 us at C2 against 118 / 124 us when the single-bin
+    // form is squeezed to 5 / 6 blocks -- the FMA pipe, not latency, is what the sweep waits for
+    return launch_fast_b<PIX, OC, P14, BWD, 4>(a, st);
 }
 
 template <typename PIX, bool BWD>

@@ -57,6 +57,14 @@ template <> struct Real<float> {
     static TQ_HD float log(float x) { return logf(x); }
     static TQ_HD float exp(float x) { return expf(x); }
     static TQ_HD float log1p(float x) { return log1pf(x); }
+    // MUFU-based forms for log-sum-exp style use (arguments <= 0 resp. sums in [1, n]): absolute error ~1e-7
+#ifdef __CUDA_ARCH__
+    static __device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
+    static __device__ __forceinline__ float log_fast(float x) { return __logf(x); }
+#else
+    static inline float exp_fast(float x) { return expf(x); }
+    static inline float log_fast(float x) { return logf(x); }
+#endif
     static TQ_HD float lgamma(float x) { return lgammaf(x); }
     static TQ_HD float sqrt(float x) { return sqrtf(x); }
     static TQ_HD float pow(float x, float y) { return powf(x, y); }
@@ -72,6 +80,8 @@ template <> struct Real<double> {
     static TQ_HD double log(double x) { return ::log(x); }
     static TQ_HD double exp(double x) { return ::exp(x); }
     static TQ_HD double log1p(double x) { return ::log1p(x); }
+    static TQ_HD double exp_fast(double x) { return ::exp(x); }
+    static TQ_HD double log_fast(double x) { return ::log(x); }
     static TQ_HD double lgamma(double x) { return lgamma_pos(x); }
     static TQ_HD double sqrt(double x) { return ::sqrt(x); }
     static TQ_HD double pow(double x, double y) { return ::pow(x, y); }

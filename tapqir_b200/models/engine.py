@@ -78,9 +78,9 @@ class CosmosEngine:
         self.samples, self.gs = e(L.NSAMP, U), e(L.NSAMP, U)
         self.qm, self.Lm, self.g_rate = e(4, U), e(4, U), e(U)
         self.rec = e(self.lib.tq_site_record_rows(), U)   # per-site records (csrc/cosmos_local.cuh SO_*/EX_*)
-        self.aoi_partial = e(2, U, dt=torch.float64)
-        self.nblocks = self.lib.tq_local_post_blocks(U)
-        self.block_partial = e(max(self.nblocks, 1) * self.C * L.NACC, dt=torch.float64)
+        # scratch of tq_cosmos_local_post: per-block partial sums, and its (self-resetting) completion tickets
+        self.block_partial = e(max(self.lib.tq_local_post_scratch(self.nb, self.fb, self.C), 1), dt=torch.float64)
+        self.tickets = torch.zeros(max(self.lib.tq_local_post_tickets(self.nb, self.fb, self.C), 1), dtype=torch.float64, device=dev)
         # scale factors of the subsampled plates (cosmos.py:194-208): all ranks together draw
         # nb * world_size of Nt_total AOIs (stratified by shard)
         self.sN = self.Nt_total / (self.nb * self.world_size)
@@ -188,7 +188,7 @@ class CosmosEngine:
                 time_likelihood[1].record()
             _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
                                                 p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
-                                                p(self.aoi_partial), p(self.block_partial), p(self.acc), st),
+                                                p(self.tickets), p(self.block_partial), p(self.acc), st),
                        "tq_cosmos_local_post")
             if self.world_size > 1:
                 torch.distributed.all_reduce(self.acc, group=self.pg)
