@@ -54,7 +54,7 @@ def algorithmic_work(o_exec):
     P2, M, K, P = 196, 4, 2, 14
     if o_exec == 1:
         mufu = P2 + M * P2 * 2 + 2 * K * P
-        fp32_ops = 98 * (2 * 104 + 13) + 600
+        fp32_ops = 98 * (2 * 85 + 14) + 600               # 47 FFMA2 + 24 FADD2 + 14 FMUL2, 14 scalar per pair
     else:
         mufu = P2 * o_exec + M * P2 * (o_exec + 3) + 2 * K * P
         fp32_ops = 98 * (2 * (35 + 53 * o_exec) - 2 * 1 + 13) + 600   # 193 packed at O = 3

@@ -173,9 +173,37 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
     float off_s[NC], off_w2[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) { off_s[j] = off_s_sm[j]; off_w2[j] = off_w2_sm[j]; }
+    int col = sub, row = 0;
+    if (OC == 1) {
+        const SingleBinConst sc = single_bin_const(s.b, fc);
+        PairOut1 po;
+        po.zero();
+        int npix = 0;
+#pragma unroll 1
+        for (int t = 0; t < 13; ++t) {
+            if (row < 7) {
+                float gxn[kK], dx[kK];
+                F2 gyk[kK], dy[kK];
+                const float fr = float(row);
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    gxn[k] = gx[k * kMaxP + col] * norm[k];
+                    gyk[k] = F2{gy[k * kMaxP + row], gy[k * kMaxP + row + 7]};
+                    dx[k] = float(col) - s.cx[k];
+                    dy[k] = F2{fr - s.cy[k], (fr + 7.0f) - s.cy[k]};
+                }
+                const F2 D{pix[row * 14 + col], pix[(row + 7) * 14 + col]};
+                pixel_pair_single_bin(D, gxn, gyk, dx, dy, s, fc, sc, off_s[0], W, po);
+                npix += 2;
+            }
+            col += 8;
+            if (col >= 14) { col -= 14; ++row; }
+        }
+        finish_single_bin(po, sc, fc, s.b, off_w2[0] * kLn2, W[0], npix, out);
+        return;
+    }
     PairOut po;
     po.zero();
-    int col = sub, row = 0;
 #pragma unroll 1
     for (int t = 0; t < 13; ++t) {
         if (row < 7) {

@@ -319,6 +319,117 @@ TQ_HD void pixel_pair_accumulate_fast(F2 D, const float (&gxn)[kK], const F2 (&g
     }
 }
 
+// ---- single offset bin (the simulator's data after merging its identical bins) ---------------------------------
+// With one bin the log-sum-exp is its only term; per pixel-configuration what is left is lgamma / digamma of
+// a = image/gain and a handful of FMAs.  The spot-free configuration has the SAME a = b/gain at every pixel, so
+// its sums over pixels are closed forms of sum(y) and sum(ln(y/b)) (finish_single_bin); terms common to all
+// configurations and the constants of Stirling's formula are added once per patch as well.
+struct SingleBinConst {
+    float a0;      // b / gain
+    float la0p1;   // ln(a0) + 1
+    float q0p1;    // ln(a0) - psi(a0) + 1
+    float q0;
+    float K0;      // ln(a0)/2 + a0 - ln(2 pi)/2 - r(a0)  (= a0 ln a0 - lgamma(a0))
+    float neg_lnb; // -ln(b)
+};
+TQ_HD SingleBinConst single_bin_const(float b, const FastConst& fc) {
+    SingleBinConst c;
+    c.a0 = b * fc.rate;
+    const float ia = 1.0f / c.a0, la0 = logf(c.a0);
+    float r, q;
+    stirling(ia, r, q);
+    c.la0p1 = la0 + 1.0f;
+    c.q0 = q;
+    c.q0p1 = q + 1.0f;
+    c.K0 = 0.5f * la0 + c.a0 - kHalfLn2Pi - r;
+    c.neg_lnb = -logf(b);
+    return c;
+}
+
+struct PairOut1 {
+    F2 logp[kM], g_b, g_rate, g_h[kK], g_w[kK], g_x[kK], g_y[kK];   // logp[0] unused
+    F2 sum_dc, sum_yb;
+    TQ_HD void zero() {
+#pragma unroll
+        for (int m = 0; m < kM; ++m) logp[m] = f2(0.0f);
+        g_b = g_rate = sum_dc = sum_yb = f2(0.0f);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) g_h[k] = g_w[k] = g_x[k] = g_y[k] = f2(0.0f);
+    }
+};
+
+// Same contract as pixel_pair_accumulate_fast<1>: two pixels of one column, every pixel above the offset, a >= 4.
+TQ_HD void pixel_pair_single_bin(F2 D, const float (&gxn)[kK], const F2 (&gyk)[kK], const float (&dx)[kK],
+                                 const F2 (&dy)[kK], const PatchSpots<float>& s, const FastConst& fc,
+                                 const SingleBinConst& sc, float off, const float (&W)[kM], PairOut1& out) {
+    F2 mu[kK], img[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) mu[k] = mul2(gyk[k], f2(gxn[k] * s.h[k]));
+    img[1] = add2(mu[0], f2(s.b));
+    img[2] = add2(mu[1], f2(s.b));
+    img[3] = add2(img[1], mu[1]);
+    const F2 y = sub2(D, f2(off)), ny = sub2(f2(off), D);
+    const F2 dc = fma2(lg2_2(y), f2(kLn2), f2(sc.neg_lnb));   // ln(y / b)
+    out.sum_dc = add2(out.sum_dc, dc);
+    out.sum_yb = add2(out.sum_yb, sub2(y, f2(s.b)));          // deviations from b: small numbers, accurate sums
+    const F2 c1p1 = add2(dc, f2(sc.la0p1));                    // d/da [a log(rate) + lse] + 1
+    const F2 nry = mul2(ny, f2(fc.rate));                      // -y / gain
+    // spot-free configuration: only its (nonlinear in y) contribution to d/d(1/gain) is per pixel
+    out.g_rate = fma2(fma2(f2(s.b), add2(dc, f2(sc.q0p1)), ny), f2(W[0]), out.g_rate);
+    F2 gsum = f2(0.0f), S[kK];
+#pragma unroll
+    for (int m = 1; m < kM; ++m) {
+        const F2 a = mul2(img[m], f2(fc.rate));
+        const F2 ia = rcp_2(a);
+        const F2 la = mul2(lg2_2(a), f2(kLn2));
+        const F2 ia2 = mul2(ia, ia);
+        const F2 r = mul2(ia, fma2(ia2, fma2(ia2, f2(0.000793650794f), f2(-0.00277777778f)), f2(0.0833333333f)));
+        const F2 q = mul2(ia, fma2(ia, fma2(ia2, fma2(ia2, f2(0.00396825397f), f2(-0.00833333333f)), f2(0.0833333333f)), f2(0.5f)));
+        const F2 d = sub2(c1p1, la);
+        // a (c1 + 1 - ln a) - y/gain + ln(a)/2 - r  =  a log(rate) - lgamma(a) + a ln y - y/gain + ln(2 pi)/2:
+        // the first two terms nearly cancel (a ~ y/gain), so they are combined BEFORE entering the running sum
+        out.logp[m] = add2(out.logp[m], sub2(fma2(la, f2(0.5f), fma2(a, d, nry)), r));
+        const F2 e = add2(d, q);                               // dL/da + 1
+        out.g_rate = fma2(fma2(img[m], e, ny), f2(W[m]), out.g_rate);
+        const F2 gi = fma2(e, f2(W[m]), f2(-W[m]));            // W dL/da (times rate: finish)
+        gsum = add2(gsum, gi);
+        if (m == 1) S[0] = gi;
+        if (m == 2) S[1] = gi;
+        if (m == 3) { S[0] = add2(S[0], gi); S[1] = add2(S[1], gi); }
+    }
+    out.g_b = add2(out.g_b, gsum);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const F2 t = mul2(S[k], mu[k]);
+        out.g_h[k] = add2(out.g_h[k], t);
+        out.g_x[k] = fma2(t, f2(dx[k]), out.g_x[k]);
+        out.g_y[k] = fma2(t, dy[k], out.g_y[k]);
+        out.g_w[k] = fma2(t, fma2(dy[k], dy[k], f2(dx[k] * dx[k])), out.g_w[k]);
+    }
+}
+
+// lane-level fold for the single-bin form; npix = pixels this lane swept; log_w = log weight of the bin
+TQ_HD void finish_single_bin(const PairOut1& p, const SingleBinConst& sc, const FastConst& fc, float b, float log_w,
+                             float W0, int npix, PatchOut<float, kM>& out) {
+    const float n = float(npix);
+    const float sdc = p.sum_dc.x + p.sum_dc.y, syb = p.sum_yb.x + p.sum_yb.y;
+    // terms shared by all configurations, -y/gain excepted: sum over pixels of  log w - ln y
+    const float common = n * (log_w + sc.neg_lnb) - sdc;
+    // spot-free configuration: a0 ln(y/b) + [a0 ln a0 - lgamma(a0)] - y/gain, with y/gain = a0 + (y - b)/gain
+    out.logp[0] = sc.a0 * sdc + n * (sc.K0 - sc.a0) - fc.rate * syb + common;
+#pragma unroll
+    for (int m = 1; m < kM; ++m) out.logp[m] = (p.logp[m].x + p.logp[m].y) - n * kHalfLn2Pi + common;
+    out.g_b = ((p.g_b.x + p.g_b.y) + W0 * (sdc + n * sc.q0)) * fc.rate;
+    out.g_rate = p.g_rate.x + p.g_rate.y;
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        out.g_h[k] = (p.g_h[k].x + p.g_h[k].y) * fc.rate;
+        out.g_w[k] = (p.g_w[k].x + p.g_w[k].y) * fc.rate;
+        out.g_x[k] = (p.g_x[k].x + p.g_x[k].y) * fc.rate;
+        out.g_y[k] = (p.g_y[k].x + p.g_y[k].y) * fc.rate;
+    }
+}
+
 // lane-level fold of the pair sums into the scalar record (before the cross-lane reduction)
 TQ_HD void finish_pair(const PairOut& p, float rate, PatchOut<float, kM>& out) {
 #pragma unroll

@@ -79,7 +79,23 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
             for (int j = 1; j < O; ++j) max_off = std::max(max_off, off_s[j]);
             for (int p = 0; p < P * P; ++p) pairs = pairs && value[u * P * P + p] > max_off;
         }
-        if (pairs) {
+        if (pairs && OC == 1) {
+            const SingleBinConst sc = single_bin_const(s.b, fc);
+            PairOut1 po; po.zero();
+            for (int row = 0; row < 7; ++row)
+                for (int col = 0; col < 14; ++col) {
+                    float gxn[kK], dx[kK]; F2 gyk[kK], dy[kK];
+                    for (int k = 0; k < kK; ++k) {
+                        gxn[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k];
+                        gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
+                        dx[k] = float(col) - s.cx[k];
+                        dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
+                    }
+                    const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
+                    pixel_pair_single_bin(D, gxn, gyk, dx, dy, s, fc, sc, off_s[0], Wm, po);
+                }
+            finish_single_bin(po, sc, fc, s.b, w2[0] * kLn2, Wm[0], P * P, out);
+        } else if (pairs) {
             PairOut po; po.zero();
             auto run = [&](auto oc_tag) {
                 constexpr int OCc = decltype(oc_tag)::value;

@@ -17,7 +17,7 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def run_host_ksmogn(case, dtype, fast_oc=None):
+def run_host_ksmogn(case, dtype, fast_oc=None, merge=False):
     hc = hostcheck.load()
     i = case["inputs"]
     K, P = 2, i["P"]
@@ -31,6 +31,10 @@ def run_host_ksmogn(case, dtype, fast_oc=None):
     val = i["value"].reshape(U, P, P).contiguous().to(tdt)
     off_s = i["offset_samples"].to(tdt).contiguous()
     off_w = torch.distributions.utils.probs_to_logits(i["offset_weights"]).to(tdt).contiguous()
+    if merge:  # identical bins merged, as CosmosDataset.device_store does
+        from tapqir_b200.utils.dataset import merge_offset_support
+
+        off_s, off_w = (t.contiguous() for t in merge_offset_support(off_s, off_w))
     mcfg = case["m"].to(tdt).contiguous()
     NM = mcfg.shape[0]
     W = case["W"].reshape(NM, U).contiguous().to(tdt)
@@ -81,6 +85,16 @@ def test_fast_fp32_form_within_tolerance(golden, name, oc):
     """ksmogn_fast.cuh (Stirling lgamma/digamma, base-2 log-sum-exp, cached offsets) vs the reference."""
     case = golden["ksmogn"][name]
     out = run_host_ksmogn(case, "f32", fast_oc=oc)
+    assert relerr(out["log_prob"], case["log_prob"]) < 1e-5
+    for k in ("height", "width", "x", "y", "background", "gain"):
+        assert relerr(out[k], case["grads"][k]) < 1e-5, k
+
+
+def test_fast_fp32_single_bin_form_within_tolerance(golden):
+    """The simulator's three identical offset bins merged to one: the packed single-bin form
+    (ksmogn_fast.cuh::pixel_pair_single_bin, closed-form spot-free configuration) vs the reference's 3-bin result."""
+    case = golden["ksmogn"]["sim_O3"]
+    out = run_host_ksmogn(case, "f32", fast_oc=1, merge=True)
     assert relerr(out["log_prob"], case["log_prob"]) < 1e-5
     for k in ("height", "width", "x", "y", "background", "gain"):
         assert relerr(out[k], case["grads"][k]) < 1e-5, k
