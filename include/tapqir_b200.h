@@ -189,6 +189,23 @@ int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gst
                              const void* gprep, const double* acc, double sN, double sF,
                              void* ggrads, double* loss, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ingestion of raw .glimpse frames (imscroll/glimpse_reader.py:168-186, 354-381).
+ * frames_raw: (Fc, H, W) big-endian int16 exactly as stored in the file (device memory); pixel value =
+ * int16 + 2^15.  Frame f0 + i of the movie is chunk frame i.
+ *
+ * tq_crop_aois: for every AOI n and chunk frame, raw = aoi_xy[n] + drift[f] (x, y order; double),
+ * shift = round_half_even(raw - (P-1)/2), patches[n, f] = frame[shifty : shifty+P, shiftx : shiftx+P]
+ * (uint16, layout (N, F, P, P)), target_xy[n, f] = raw - shift.  *status |= 1 if a window leaves the frame
+ * (that patch is left untouched).
+ * tq_offset_hist: counts[v] += #pixels equal to v in frame[oy : oy+oP, ox : ox+oP] over the chunk
+ * (counts: 65536 uint64). */
+int tq_crop_aois(const void* frames_raw, int H, int W, int Fc, int f0, const double* aoi_xy,
+                 const double* drift, int N, int F, int P, void* patches, double* target_xy,
+                 int* status, void* stream);
+int tq_offset_hist(const void* frames_raw, int H, int W, int Fc, int offset_x, int offset_y,
+                   int offset_P, void* counts, void* stream);
+
 /* torch.optim.Adam step (pyro.optim.Adam({"lr", "betas"}), models/model.py:168-171), dense over
  * the whole buffer; *state = number of completed steps. */
 int tq_adam_dense(int dtype, int64_t n, void* params, const void* grads, void* exp_avg,

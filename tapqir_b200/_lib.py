@@ -59,6 +59,8 @@ SIGNATURES = {
     "tq_sizeof_gprep": (c_int, []),
     "tq_cosmos_globals_prepare": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_globals_finish": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP]),
+    "tq_crop_aois": (c_int, [_VP, c_int, c_int, c_int, c_int, _VP, _VP, c_int, c_int, c_int, _VP, _VP, _VP, _VP]),
+    "tq_offset_hist": (c_int, [_VP, c_int, c_int, c_int, c_int, c_int, c_int, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),
     "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),

@@ -1,0 +1,63 @@
+"""
+CPU: the glimpse-ingestion oracle and the host-side helpers of tapqir_b200.imscroll against the golden
+vectors made from the reference's own ``bin_hist`` (tests/golden/make_golden_glimpse.py), and against each
+other for the offset post-processing.
+"""
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glimpse_oracle as GO
+from tapqir_b200.imscroll import glimpse_reader as GR
+
+GOLDEN = Path(__file__).parent / "golden" / "ref_glimpse.pt"
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+@pytest.mark.parametrize("impl", [GO.bin_hist, GR.bin_hist], ids=["oracle", "product"])
+def test_bin_hist_matches_reference_bit_for_bit(cases, impl):
+    old = torch.get_default_dtype()
+    try:
+        for case in cases:
+            torch.set_default_dtype(torch.float64 if "64" in case["default"] else torch.float32)
+            out_s, out_w = impl(case["samples"], case["weights"], case["s"])
+            assert out_s.dtype == case["out_samples"].dtype and out_w.dtype == case["out_weights"].dtype
+            assert torch.equal(out_s, case["out_samples"]), (len(case["samples"]), case["s"])
+            assert torch.equal(out_w, case["out_weights"]), (len(case["samples"]), case["s"])
+    finally:
+        torch.set_default_dtype(old)
+
+
+def test_offset_distribution_matches_oracle():
+    rng = np.random.default_rng(3)
+    for min_data, bin_size in [(40, 3), (95, 1), (200, 5)]:
+        counts = np.zeros(65536, dtype=np.int64)
+        vals = np.clip(rng.normal(90, 6, 20000).round().astype(int), 60, 140)
+        np.add.at(counts, vals, 1)
+        counts[300] = 3   # far tail, removed with the top 0.5 %
+        offsets = {int(v): int(c) for v, c in enumerate(counts) if c}
+        ref_s, ref_w = GO.offset_distribution(offsets, min_data, bin_size)
+        out_s, out_w = GR.offset_distribution(counts, min_data, bin_size)
+        assert torch.equal(out_s, ref_s) and torch.equal(out_w, ref_w)
+        assert abs(out_w.sum().item() - 1.0) < 1e-6
+        if min_data <= vals.min():
+            assert out_s[0].item() == min_data - 1
+
+
+def test_decode_frame_is_big_endian_plus_offset():
+    raw = np.array([[-32768, -1], [0, 32767]], dtype=">i2").tobytes()
+    assert GO.decode_frame(raw, 2, 2).tolist() == [[0, 32767], [32768, 65535]]
+
+
+def test_crop_loop_rounds_half_to_even():
+    frames = np.arange(2 * 20 * 20).reshape(2, 20, 20)
+    # raw - (P-1)/2 = 4.5 and 5.5 -> shifts 4 and 6 (ties to even), like Python's round()
+    data, xy = GO.crop_loop(frames, np.array([[7.0, 8.0]]), np.zeros((2, 2)), P=6)
+    assert data[0, 0, 0, 0] == frames[0, 6, 4] and xy[0, 0].tolist() == [3.0, 2.0]
