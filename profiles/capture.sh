@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 # (1) every launch of this library with its device time (cold-cache, serialised: compare SHARES)
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'ksmogn|site_|local_post|reduce_|globals_|adam_kernel|finalize_loss|step_advance|subsample' -s 48 -c 48 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'ksmogn|site_|local_post|reduce_|globals_|adam_kernel|finalize_loss|step_advance|subsample' -s 40 -c 40 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
 # (2) full capture of the likelihood, site and post kernels (one launch each, after warm-up)
@@ -14,3 +14,9 @@ ncu --set full --clock-control none --import-source on -k regex:'ksmogn_fast_ker
     -o gpurun_out/step_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full rc=$?"
 tail -2 gpurun_out/ncu_full_${TAG}.log
+# (3) the same likelihood kernel with the simulator's three offset bins kept distinct (O = 3 forms)
+CMD3="$CMD --keep-offset-bins"
+$CMD3 > gpurun_out/plain3_${TAG}.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'ksmogn_fast_kernel' -s 4 -c 1 \
+    -o gpurun_out/ksmogn_o3_${TAG} $CMD3 > gpurun_out/ncu_o3_${TAG}.log 2>&1
+echo "o3 rc=$?"
