@@ -245,7 +245,7 @@ def run_native(args):
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists():
-        t = json.loads(tj.read_text()).get("ksmogn_fast_kernel", {})
+        t = json.loads(tj.read_text()).get("ksmogn_fast_kernel" if o_exec == 1 else "ksmogn_fast_kernel_o3", {})
         if t.get("workload") == args.workload and t.get("units_per_launch") == units_per_step:
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
                        "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * units_per_step, "source": t["source"]}
