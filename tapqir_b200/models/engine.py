@@ -190,14 +190,15 @@ class CosmosEngine:
                                                 p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
                                                 p(self.tickets), p(self.block_partial), p(self.acc), st),
                        "tq_cosmos_local_post")
-            if self.world_size > 1:
-                torch.distributed.all_reduce(self.acc, group=self.pg)
-            # finishing the global reverse pass (a few FMAs per parameter) + the global Adam run beside the dense
-            # Adam over the AOI-local buffer, which does not depend on them
+            # the all-reduce of the (C, 18) accumulators (multi-GPU), finishing the global reverse pass (a few FMAs per
+            # parameter) and the global Adam run on the side stream, beside the dense Adam over the AOI-local buffer,
+            # which depends on none of them: the collective's latency hides under the local update
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):
                 sst = _lib.stream_ptr(self.device)
+                if self.world_size > 1:
+                    torch.distributed.all_reduce(self.acc, group=self.pg)
                 _lib.check(lib.tq_cosmos_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc),
                                                         self.sN, self.sF, p(self.ggrads), p(self.loss), sst),
                            "tq_cosmos_globals_finish")
