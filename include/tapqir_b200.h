@@ -190,6 +190,41 @@ int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gst
                              void* ggrads, double* loss, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * hmm variant of cosmos (models/hmm.py): the guide enumerates a Markov chain z_f with AOI-local
+ * transition tables `z_trans` and spot presences conditional on z_f; every frame is used (fb == F, fdx == NULL).
+ * Call order of one step:
+ *   tq_hmm_globals_sample -> tq_hmm_globals_prepare, tq_cosmos_sites (continuous sites, unchanged) -> tq_hmm_forward
+ *   -> tq_ksmogn_fwd_bwd (W = qm of tq_hmm_forward) -> tq_hmm_local_post -> tq_hmm_backward
+ *   -> [all-reduce of acc and hacc] -> tq_hmm_globals_finish -> tq_adam_dense x2 -> tq_step_advance
+ * Local flat buffer (tq_hmm_local_numel values): the cosmos layout (its m_probs slabs hold m_probs[z = 0]), then
+ * m_probs[z = 1] (K, Nt, F, C), then z_trans (Nt, F, C, 2, 2) -- all unconstrained.
+ * Global flat buffer: the cosmos layout with pi_* read as init_*, then trans_mean (Q, 2, 2), trans_size (Q, 2);
+ * global noise: cosmos order, then trans (Q, 2, 2).
+ * a: (2, U) double forward marginals; v: (2, U) emission values of the two states; hpartial: (nb * C,
+ * tq_hmm_chain_sums()) and hacc: (C, tq_hmm_chain_sums()) double scratch / sums of the chain (ELBO terms, expected
+ * initial-state and transition counts). */
+int64_t tq_hmm_local_numel(int64_t Nt, int64_t F, int64_t C);
+int tq_hmm_chain_sums(void);
+int tq_hmm_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
+                          uint64_t seed, const void* state, double* gstate, void* tables,
+                          void* gain_out, void* stream);
+int tq_hmm_globals_prepare(int dtype, int Q, const void* gparams, const void* mc,
+                           const double* gstate, void* gprep, void* stream);
+int tq_hmm_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
+                          const double* acc, const double* hacc, double sN, void* ggrads,
+                          double* loss, void* stream);
+int tq_hmm_forward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                   const void* lparams, double* a_out, void* qm, void* stream);
+int tq_hmm_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                      const void* lparams, const void* tables, const void* samples, const void* rec,
+                      const void* L, const void* gs, const void* g_rate, const double* a_in, double sN,
+                      void* lgrads, void* v_out, double* tickets, double* block_partial, double* acc,
+                      void* stream);
+int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                    const void* lparams, const void* tables, const double* a_in, const void* v_in,
+                    double sN, void* lgrads, double* hpartial, double* hacc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Ingestion of raw .glimpse frames (imscroll/glimpse_reader.py:168-186, 354-381).
  * frames_raw: (Fc, H, W) big-endian int16 exactly as stored in the file (device memory); pixel value =
  * int16 + 2^15.  Frame f0 + i of the movie is chunk frame i.

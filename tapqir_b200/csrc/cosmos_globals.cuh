@@ -11,6 +11,7 @@ namespace tq {
 // flat layout of the global variational parameters (and of their gradient / Adam moments)
 struct GlobalLayout {
     int Q;
+    bool hmm = false;   // hmm variant (models/hmm.py): pi_* are init_*, plus trans_mean (Q,2,2) and trans_size (Q,2)
     TQ_HD int gain_loc() const { return 0; }
     TQ_HD int gain_beta() const { return 1; }
     TQ_HD int prox_loc() const { return 2; }
@@ -19,17 +20,20 @@ struct GlobalLayout {
     TQ_HD int pi_size(int q) const { return 4 + kZ * Q + q; }
     TQ_HD int lamda_loc(int q) const { return 4 + (kZ + 1) * Q + q; }
     TQ_HD int lamda_beta(int q) const { return 4 + (kZ + 2) * Q + q; }
-    TQ_HD int count() const { return 4 + (kZ + 3) * Q; }
-    // flat layout of the global base variates / samples: gain, proximity, pi (Q,2), lamda (Q)
+    TQ_HD int trans_mean(int q, int zr, int z) const { return 4 + (kZ + 3) * Q + (q * kZ + zr) * kZ + z; }
+    TQ_HD int trans_size(int q, int zr) const { return 4 + (kZ + 3) * Q + kZ * kZ * Q + q * kZ + zr; }
+    TQ_HD int count() const { return 4 + (kZ + 3) * Q + (hmm ? (kZ * kZ + kZ) * Q : 0); }
+    // flat layout of the global base variates / samples: gain, proximity, pi (Q,2), lamda (Q) [, trans (Q,2,2)]
     TQ_HD int n_gain() const { return 0; }
     TQ_HD int n_prox() const { return 1; }
     TQ_HD int n_pi(int q, int z) const { return 2 + q * kZ + z; }
     TQ_HD int n_lamda(int q) const { return 2 + kZ * Q + q; }
-    TQ_HD int n_count() const { return 2 + (kZ + 1) * Q; }
+    TQ_HD int n_trans(int q, int zr, int z) const { return 2 + (kZ + 1) * Q + (q * kZ + zr) * kZ + z; }
+    TQ_HD int n_count() const { return 2 + (kZ + 1) * Q + (hmm ? kZ * kZ * Q : 0); }
 };
 
-constexpr int kMaxGlobals = 4 + (kZ + 3) * kMaxC;
-constexpr int kMaxGlobalNoise = 2 + (kZ + 1) * kMaxC;
+constexpr int kMaxGlobals = 4 + (kZ + 3 + kZ * kZ + kZ) * kMaxC;
+constexpr int kMaxGlobalNoise = 2 + (kZ + 1 + kZ * kZ) * kMaxC;
 
 TQ_HD double clamp_prob(double p, const ModelConst& mc) {
     return fmin(fmax(p, mc.eps), 1.0 - mc.eps);
@@ -49,7 +53,8 @@ TQ_HD void probs_m_k2(double lam, double& p0, double& dp0, double& p1, double& d
 // kernels give each site its own lane (a serial single-thread version cost 80 us per step at C2
 // scale, as much as a third of the likelihood kernel).  Site ids: 0 gain, 1 proximity, 2+q pi_q,
 // 2+Q+q lamda_q.
-TQ_HD int global_site_count(int Q) { return 2 + 2 * Q; }
+// hmm: + one Dirichlet site per (channel, row of the transition matrix): 2 + 2Q + 2q + z'
+TQ_HD int global_site_count(int Q, bool hmm = false) { return 2 + 2 * Q + (hmm ? kZ * Q : 0); }
 
 // ---- forward: variates -> samples -> tables --------------------------------------------------------
 // u: unconstrained global params; variate: base draws (replay) or filled here from `rng`;
@@ -93,25 +98,37 @@ TQ_HD void globals_pre_site(int site, const double* u, const GlobalLayout& gl, c
         return;
     }
     const double le = log(mc.eps), l1e = log(1.0 - mc.eps);
-    if (site < 2 + gl.Q) {
-        const int q = site - 2;
-        // pi_q ~ Dirichlet(pi_mean * pi_size)                                             cosmos.py:349-352
-        const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
+    if (site < 2 + gl.Q || site >= 2 + 2 * gl.Q) {
+        // pi_q ~ Dirichlet(pi_mean * pi_size) (cosmos.py:349-352; hmm: init_q, hmm.py:279-284), or row z' of the hmm
+        // transition matrix trans_q ~ Dirichlet(trans_mean * trans_size) (hmm.py:285-290)
+        const bool is_trans = site >= 2 + 2 * gl.Q;
+        const int idx = is_trans ? site - 2 - 2 * gl.Q : site - 2;
+        const int q = is_trans ? idx / kZ : idx, zr = is_trans ? idx % kZ : 0;
+        const double u0 = u[is_trans ? gl.trans_mean(q, zr, 0) : gl.pi_mean(q, 0)];
+        const double u1 = u[is_trans ? gl.trans_mean(q, zr, 1) : gl.pi_mean(q, 1)];
+        const int n0 = is_trans ? gl.n_trans(q, zr, 0) : gl.n_pi(q, 0), n1 = n0 + 1;
         const double mxu = fmax(u0, u1);
         const double e0 = exp(u0 - mxu), e1 = exp(u1 - mxu);
-        const double size = exp(u[gl.pi_size(q)]);
+        const double size = exp(u[is_trans ? gl.trans_size(q, zr) : gl.pi_size(q)]);
         const double a0 = e0 / (e0 + e1) * size, a1 = e1 / (e0 + e1) * size;
         if (use_rng) {
             const double g0 = sample_std_gamma<double>(*rng, a0), g1 = sample_std_gamma<double>(*rng, a1);
-            variate[gl.n_pi(q, 0)] = fmin(fmax(g0 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
-            variate[gl.n_pi(q, 1)] = fmin(fmax(g1 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
+            variate[n0] = fmin(fmax(g0 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
+            variate[n1] = fmin(fmax(g1 / (g0 + g1), mc.tiny), 1.0 - mc.eps);
         }
-        const double p0 = variate[gl.n_pi(q, 0)], p1 = variate[gl.n_pi(q, 1)];
-        sample[gl.n_pi(q, 0)] = p0;
-        sample[gl.n_pi(q, 1)] = p1;
+        const double p0 = variate[n0], p1 = variate[n1];
+        sample[n0] = p0;
+        sample[n1] = p1;
         ChannelTables<double>& ct = gt.ch[q];
-        // Categorical(probs).logits = log(clamp(probs / sum))                           cosmos.py:242-246
-        ct.logpz[0][0] = l1e;  // off-target: [1, 0]                                       util.py:133-151
+        // Categorical(probs).logits = log(clamp(probs / sum)); off-target rows are [1, 0]          util.py:133-151
+        if (is_trans) {
+            ct.logptrans[0][zr][0] = l1e;
+            ct.logptrans[0][zr][1] = le;
+            ct.logptrans[1][zr][0] = log(clamp_prob(p0 / (p0 + p1), mc));
+            ct.logptrans[1][zr][1] = log(clamp_prob(p1 / (p0 + p1), mc));
+            return;
+        }
+        ct.logpz[0][0] = l1e;
         ct.logpz[0][1] = le;
         ct.logpz[1][0] = log(clamp_prob(p0 / (p0 + p1), mc));
         ct.logpz[1][1] = log(clamp_prob(p1 / (p0 + p1), mc));
@@ -150,22 +167,29 @@ TQ_HD void globals_pre_site(int site, const double* u, const GlobalLayout& gl, c
 // path (globals_prepare), and finish with a handful of FMAs once the accumulators exist (globals_finish).
 //
 // acc: [Q][NACC] sums over all units of all ranks (unscaled, masked); sN = Nt/nb, sF = F/fb.
+// hacc (hmm only): [Q][NHACC] sums over (AOI, frame) of the chain's ELBO terms and of the expected initial-state /
+// transition counts (cosmos_hmm.cuh), unscaled, masked, on-target AOIs only for the counts.
 TQ_HD void globals_drive(int site, const GlobalLayout& gl, const ModelConst& mc, const double* sample, const double* acc,
-                         double sN, double sF, double (&drive)[2], double& elbo_data) {
+                         const double* hacc, double sN, double sF, double (&drive)[2], double& elbo_data) {
     const double s = sN * sF;
     drive[0] = drive[1] = 0.0;
     elbo_data = 0.0;
+    constexpr int kHaccElbo = 0, kHaccInit = 1, kHaccTrans = 1 + kZ, kNHacc = 1 + kZ + kZ * kZ;   // = cosmos_hmm.cuh HACC_*
     if (site == 0) {
         for (int q = 0; q < gl.Q; ++q) {
             const double* a = acc + q * NACC;
             elbo_data += s * a[ACC_ELBO_FRAME] + sN * a[ACC_ELBO_AOI];
+            if (gl.hmm) elbo_data += s * hacc[q * kNHacc + kHaccElbo];
             drive[0] += s * a[ACC_RATE];
         }
     } else if (site == 1) {
         for (int q = 0; q < gl.Q; ++q) drive[0] += s * acc[q * NACC + ACC_SIZE1];
     } else if (site < 2 + gl.Q) {
-        const double* a = acc + (site - 2) * NACC;
-        for (int z = 0; z < kZ; ++z) drive[z] = s * a[ACC_LOGPZ + z];
+        const int q = site - 2;
+        for (int z = 0; z < kZ; ++z) drive[z] = gl.hmm ? s * hacc[q * kNHacc + kHaccInit + z] : s * acc[q * NACC + ACC_LOGPZ + z];
+    } else if (site >= 2 + 2 * gl.Q) {
+        const int idx = site - 2 - 2 * gl.Q, q = idx / kZ, zr = idx % kZ;
+        for (int z = 0; z < kZ; ++z) drive[z] = s * hacc[q * kNHacc + kHaccTrans + zr * kZ + z];
     } else {
         const int q = site - 2 - gl.Q;
         const double* a = acc + q * NACC;
@@ -225,15 +249,21 @@ TQ_HD double globals_post_site_driven(int site, const double* u, const GlobalLay
         grad[gl.prox_size()] = -((g_c1 * (loc.v - d.low) / d.scale + g_c0 * (d.low + d.scale - loc.v) / d.scale) * size.d);
         return elbo;
     }
-    if (site < 2 + gl.Q) {
-        const int q = site - 2;
-        const double u0 = u[gl.pi_mean(q, 0)], u1 = u[gl.pi_mean(q, 1)];
+    if (site < 2 + gl.Q || site >= 2 + 2 * gl.Q) {
+        // Dirichlet over two states: pi_q / init_q, or row z' of trans_q (same prior Dirichlet(1/2, 1/2), hmm.py:87-98)
+        const bool is_trans = site >= 2 + 2 * gl.Q;
+        const int idx = is_trans ? site - 2 - 2 * gl.Q : site - 2;
+        const int q = is_trans ? idx / kZ : idx, zr = is_trans ? idx % kZ : 0;
+        const int i_m0 = is_trans ? gl.trans_mean(q, zr, 0) : gl.pi_mean(q, 0), i_m1 = i_m0 + 1;
+        const int i_sz = is_trans ? gl.trans_size(q, zr) : gl.pi_size(q);
+        const int n0 = is_trans ? gl.n_trans(q, zr, 0) : gl.n_pi(q, 0);
+        const double u0 = u[i_m0], u1 = u[i_m1];
         const double mxu = fmax(u0, u1);
         const double e0 = exp(u0 - mxu), e1 = exp(u1 - mxu);
         const double mean[2] = {e0 / (e0 + e1), e1 / (e0 + e1)};
-        const double size = exp(u[gl.pi_size(q)]);
+        const double size = exp(u[i_sz]);
         const double conc[2] = {mean[0] * size, mean[1] * size};
-        const double x[2] = {sample[gl.n_pi(q, 0)], sample[gl.n_pi(q, 1)]};
+        const double x[2] = {sample[n0], sample[n0 + 1]};
         const double tot = conc[0] + conc[1], sx = x[0] + x[1];
         const double prior_c = 1.0 / kZ;  // Dirichlet(1/(S+1))                               cosmos.py:171-174
         double lp = lgamma_pos(prior_c * kZ), lq = lgamma_pos(tot);
@@ -264,9 +294,9 @@ TQ_HD double globals_post_site_driven(int site, const double* u, const GlobalLay
         // conc = softmax(u_mean) * exp(u_size)
         const double gm[2] = {g_conc[0] * size, g_conc[1] * size};
         const double gmdot = mean[0] * gm[0] + mean[1] * gm[1];
-        grad[gl.pi_mean(q, 0)] = -(mean[0] * (gm[0] - gmdot));
-        grad[gl.pi_mean(q, 1)] = -(mean[1] * (gm[1] - gmdot));
-        grad[gl.pi_size(q)] = -((g_conc[0] * mean[0] + g_conc[1] * mean[1]) * size);
+        grad[i_m0] = -(mean[0] * (gm[0] - gmdot));
+        grad[i_m1] = -(mean[1] * (gm[1] - gmdot));
+        grad[i_sz] = -((g_conc[0] * mean[0] + g_conc[1] * mean[1]) * size);
         return elbo;
     }
     {
@@ -288,9 +318,10 @@ TQ_HD double globals_post_site_driven(int site, const double* u, const GlobalLay
 
 // one-shot form: this site's part of the ELBO (site 0 also carries the data terms) and its gradients
 TQ_HD double globals_post_site(int site, const double* u, const GlobalLayout& gl, const ModelConst& mc,
-                               const double* sample, const double* acc, double sN, double sF, double* grad) {
+                               const double* sample, const double* acc, double sN, double sF, double* grad,
+                               const double* hacc = nullptr) {
     double drive[2], elbo_data;
-    globals_drive(site, gl, mc, sample, acc, sN, sF, drive, elbo_data);
+    globals_drive(site, gl, mc, sample, acc, hacc, sN, sF, drive, elbo_data);
     return elbo_data + globals_post_site_driven(site, u, gl, mc, sample, drive, grad);
 }
 
@@ -301,12 +332,15 @@ TQ_HD int global_param_site(int i, int Q) {
     if (i < 4 + kZ * Q) return 2 + (i - 4) / kZ;           // pi_mean (q, z)
     if (i < 4 + (kZ + 1) * Q) return 2 + (i - 4 - kZ * Q);  // pi_size q
     if (i < 4 + (kZ + 2) * Q) return 2 + Q + (i - 4 - (kZ + 1) * Q);
-    return 2 + Q + (i - 4 - (kZ + 2) * Q);
+    if (i < 4 + (kZ + 3) * Q) return 2 + Q + (i - 4 - (kZ + 2) * Q);
+    const int j = i - 4 - (kZ + 3) * Q;                     // hmm: trans_mean (q, z', z) then trans_size (q, z')
+    if (j < kZ * kZ * Q) return 2 + 2 * Q + j / kZ;
+    return 2 + 2 * Q + (j - kZ * kZ * Q);
 }
 
 // prepared reverse mode: for every site, grad at drive = 0, e0, e1 (full GlobalLayout vectors; only the
 // site's own entries are meaningful) and the site's own ELBO part
-constexpr int kMaxGlobalSites = 2 + 2 * kMaxC;
+constexpr int kMaxGlobalSites = 2 + (2 + kZ) * kMaxC;
 struct GlobalPrep {
     double grad[kMaxGlobalSites][3][kMaxGlobals];
     double elbo[kMaxGlobalSites];
@@ -315,13 +349,13 @@ struct GlobalPrep {
 // serial forms (host check, tests)
 TQ_HD void globals_pre(const double* u, const GlobalLayout& gl, const ModelConst& mc, bool use_rng, Philox* rng,
                        double* variate, double* sample, GlobalTables<double>& gt) {
-    for (int site = 0; site < global_site_count(gl.Q); ++site)
+    for (int site = 0; site < global_site_count(gl.Q, gl.hmm); ++site)
         globals_pre_site(site, u, gl, mc, use_rng, rng, variate, sample, gt);
 }
 TQ_HD double globals_post(const double* u, const GlobalLayout& gl, const ModelConst& mc, const double* sample,
                           const double* acc, double sN, double sF, double* grad) {
     double elbo = 0.0;
-    for (int site = 0; site < global_site_count(gl.Q); ++site)
+    for (int site = 0; site < global_site_count(gl.Q, gl.hmm); ++site)
         elbo += globals_post_site(site, u, gl, mc, sample, acc, sN, sF, grad);
     return elbo;
 }

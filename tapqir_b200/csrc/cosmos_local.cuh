@@ -38,6 +38,7 @@ template <typename A> struct ChannelTables {
     A logpz[2][kZ];             // [is_ontarget][z]           cosmos.py:242-246, util.py:133-151
     A logptheta[2][kTheta];     // [min(z,1)][theta]          cosmos.py:247-255, util.py:154-173
     A logpm[kTheta][kK][2];     // [theta][k][m_k]            cosmos.py:262-267, util.py:94-130
+    A logptrans[2][kZ][kZ];     // hmm only: [is_ontarget][z'][z]  hmm.py:165-169 (logpz is then the initial distribution)
 };
 template <typename A> struct GlobalTables {
     A gain, rate, log_rate;
@@ -56,6 +57,8 @@ template <typename A> struct GlobalTables {
             for (int a = 0; a < 2; ++a) for (int t = 0; t < kTheta; ++t) ch[q].logptheta[a][t] = (A)o.ch[q].logptheta[a][t];
             for (int t = 0; t < kTheta; ++t) for (int k = 0; k < kK; ++k) for (int m = 0; m < 2; ++m)
                 ch[q].logpm[t][k][m] = (A)o.ch[q].logpm[t][k][m];
+            for (int a = 0; a < 2; ++a) for (int z = 0; z < kZ; ++z) for (int y = 0; y < kZ; ++y)
+                ch[q].logptrans[a][z][y] = (A)o.ch[q].logptrans[a][z][y];
         }
     }
 };

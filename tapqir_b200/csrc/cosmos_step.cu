@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "cosmos_globals.cuh"
 #include "cosmos_sites_fast.cuh"
+#include "cosmos_hmm.cuh"
 
 namespace tq {
 
@@ -43,14 +44,14 @@ constexpr int kLocalBlock = 128;
 
 // ---- globals: sample + tables; one block per global site --------------------------------------------------
 template <typename T>
-__global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+__global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
                                       const double* __restrict__ noise_in, unsigned long long seed,
                                       const StepState* __restrict__ state, double* __restrict__ gstate,
                                       GlobalTables<double>* __restrict__ tables, T* __restrict__ gain_out) {
     // one BLOCK per site: lanes of one warp would serialise the divergent per-site code paths
     const int site = blockIdx.x;
-    if (threadIdx.x != 0 || site >= global_site_count(Q)) return;
-    GlobalLayout gl{Q};
+    if (threadIdx.x != 0 || site >= global_site_count(Q, hmm)) return;
+    GlobalLayout gl{Q, hmm};
     double u[kMaxGlobals];
     for (int i = 0; i < gl.count(); ++i) u[i] = (double)gparams[i];
     const bool use_rng = noise_in == nullptr;
@@ -62,7 +63,11 @@ __global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, Mode
         if (site == 0) variate[gl.n_gain()] = noise_in[gl.n_gain()];
         else if (site == 1) variate[gl.n_prox()] = noise_in[gl.n_prox()];
         else if (site < 2 + Q) { for (int z = 0; z < kZ; ++z) variate[gl.n_pi(site - 2, z)] = noise_in[gl.n_pi(site - 2, z)]; }
-        else variate[gl.n_lamda(site - 2 - Q)] = noise_in[gl.n_lamda(site - 2 - Q)];
+        else if (site < 2 + 2 * Q) variate[gl.n_lamda(site - 2 - Q)] = noise_in[gl.n_lamda(site - 2 - Q)];
+        else {
+            const int idx = site - 2 - 2 * Q;
+            for (int z = 0; z < kZ; ++z) variate[gl.n_trans(idx / kZ, idx % kZ, z)] = noise_in[gl.n_trans(idx / kZ, idx % kZ, z)];
+        }
     }
     globals_pre_site(site, u, gl, mc, use_rng, &rng, variate, sample, *tables);
     if (site == 0) gain_out[0] = (T)tables->gain;
@@ -91,6 +96,16 @@ template <typename T> struct LocalArgs {
     T* lgrads;                   // flat, LocalOffsets layout
     double* aoi_partial;         // (2, U): per-unit contributions to d/d(bm, bs)
     double* block_partial;       // (gridDim.x, C, NACC)
+    // hmm variant (cosmos_hmm.cuh): the extra local slabs live behind the cosmos layout in the same flat buffers --
+    // m_probs[z = 1] (K slabs of (Nt, F, C)), then z_trans (Nt, F, C, 2, 2); m_probs[z = 0] are the cosmos m_probs slabs
+    const double* hmm_a;         // (kZ, U) forward marginals of the guide's chain
+    T* hmm_v;                    // (kZ, U) centred emission values V_f(z)
+    __host__ __device__ int64_t hmm_mprobs1(int k, int64_t n, int64_t f, int64_t c) const {
+        return lo.numel() + (int64_t)k * (lo.Nt * lo.F * lo.C) + (n * lo.F + f) * lo.C + c;
+    }
+    __host__ __device__ int64_t hmm_ztrans(int64_t n, int64_t f, int64_t c) const {   // + z' * 2 + z
+        return lo.numel() + (int64_t)kK * (lo.Nt * lo.F * lo.C) + ((n * lo.F + f) * lo.C + c) * (kZ * kZ);
+    }
 };
 
 // ---- sites: one thread per (site, unit), site-major so that a warp evaluates one family ------------------
@@ -218,7 +233,7 @@ __host__ __device__ inline int post_upt(int nb, int fb, int C) {
 }
 __host__ __device__ inline int post_chunks(int fb, int upt) { return (fb + kLocalBlock * upt - 1) / (kLocalBlock * upt); }
 
-template <typename T, int kPostUPT>
+template <typename T, int kPostUPT, bool HMM = false>
 __global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalArgs<T> a, int chunks, unsigned int* __restrict__ tickets,
                                                                 double* __restrict__ acc_out) {
     __shared__ double red[kLocalBlock / 32][kPostRed];
@@ -260,7 +275,24 @@ __global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalA
 #pragma unroll
         for (int k = 0; k < kK; ++k) u_mp[k] = a.lparams[a.lo.index(LP_M_PROBS + k, n, f, c)];
         UnitGrads<T> ug;
-        unit_post<T>(rec, sample, L, gs, a.g_rate[u], u_mp, u_bm, u_bs, a.mc, gt, c, ontarget, fi == 0, ug);
+        if (HMM) {
+            T ump2[kZ][kK], az[kZ];
+            HmmUnitOut<T> ho;
+#pragma unroll
+            for (int k = 0; k < kK; ++k) { ump2[0][k] = u_mp[k]; ump2[1][k] = a.lparams[a.hmm_mprobs1(k, n, f, c)]; }
+#pragma unroll
+            for (int z = 0; z < kZ; ++z) az[z] = (T)a.hmm_a[(int64_t)z * a.U + u];
+            unit_post_hmm<T>(rec, sample, L, gs, a.g_rate[u], ump2, az, u_bm, u_bs, a.mc, gt, c, fi == 0, ug, ho);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                ug.g[LP_M_PROBS + k] = ho.gmp[0][k];
+                a.lgrads[a.hmm_mprobs1(k, n, f, c)] = scale * ho.gmp[1][k];
+            }
+#pragma unroll
+            for (int z = 0; z < kZ; ++z) a.hmm_v[(int64_t)z * a.U + u] = ho.v[z];
+        } else {
+            unit_post<T>(rec, sample, L, gs, a.g_rate[u], u_mp, u_bm, u_bs, a.mc, gt, c, ontarget, fi == 0, ug);
+        }
 #pragma unroll
         for (int i = LP_B_LOC; i < NLOCAL; ++i) a.lgrads[a.lo.index(i, n, f, c)] = scale * ug.g[i];
 #pragma unroll
@@ -351,6 +383,117 @@ __global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalA
     if (threadIdx.x < C * NACC) acc_out[threadIdx.x] = (fin[threadIdx.x][0] + fin[threadIdx.x][1]) + (fin[threadIdx.x][2] + fin[threadIdx.x][3]);
 }
 
+// ---- hmm: the guide's chain (cosmos_hmm.cuh).  One thread per (AOI, channel) walks the frames; everything in double
+// (a few dozen flops per unit; only differences of the big emission values propagate, see HmmUnitOut::v) -------------
+template <typename T>
+__global__ void hmm_forward_kernel(const LocalArgs<T> a, double* __restrict__ a_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = a.v.C, F = a.v.F;
+    if (t >= a.v.nb * C) return;
+    const int ni = t / C, c = t - ni * C;
+    const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
+    double a0 = 1.0, a1 = 0.0;   // a_{-1} = e_0: row 0 of z_trans is the initial distribution            hmm.py:355-359
+    const T* zt = a.lparams + a.hmm_ztrans(n, 0, c);
+    for (int f = 0; f < F; ++f, zt += C * kZ * kZ) {
+        const ChainRow r0 = chain_row((double)zt[0], (double)zt[1], a.mc), r1 = chain_row((double)zt[2], (double)zt[3], a.mc);
+        const double b0 = a0 * r0.q[0] + a1 * r1.q[0], b1 = a0 * r0.q[1] + a1 * r1.q[1];
+        a0 = b0; a1 = b1;
+        const int64_t u = ((int64_t)ni * F + f) * C + c;
+        a_out[u] = a0;
+        a_out[a.U + u] = a1;
+    }
+}
+
+// likelihood-kernel weights W(m) = sum_z a(z) q(m | z) per unit
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) hmm_weights_kernel(const LocalArgs<T> a) {
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    const UnitIndex ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    T ump[kZ][kK], az[kZ], qm[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        ump[0][k] = a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, ui.fi, ui.c)];
+        ump[1][k] = a.lparams[a.hmm_mprobs1(k, ui.aoi, ui.fi, ui.c)];
+    }
+#pragma unroll
+    for (int z = 0; z < kZ; ++z) az[z] = (T)a.hmm_a[(int64_t)z * a.U + u32];
+    hmm_presence_weights<T>(ump, az, a.mc, qm);
+#pragma unroll
+    for (int m = 0; m < kM; ++m) a.qm[m * a.U + u32] = qm[m];
+}
+
+// backward recursion: gradients of the unconstrained z_trans, the chain's ELBO terms and the expected
+// initial-state / transition counts of this (AOI, channel) -> hpartial[(ni * C + c)][NHACC]
+//   Delta_f = V_f(1) - V_f(0) + [rho_{f+1}(1) - rho_{f+1}(0)] + [q_{f+1}(1|1) - q_{f+1}(1|0)] Delta_{f+1},
+//   rho_f(z') = sum_z q_f(z|z') R_f(z', z),   R_f = log p_f - log q_f,
+//   d ELBO / d u_f(z', 1) = a_{f-1}(z') q_f(1|z') q_f(0|z') [ R_f(z',1) - R_f(z',0) + Delta_f ] = - d / d u_f(z', 0)
+template <typename T>
+__global__ void hmm_backward_kernel(const LocalArgs<T> a, double* __restrict__ hpartial) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = a.v.C, F = a.v.F;
+    if (t >= a.v.nb * C) return;
+    const int ni = t / C, c = t - ni * C;
+    const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
+    const double mu = a.v.mask[n] ? 1.0 : 0.0;
+    const int ot = a.v.is_ontarget[n] ? 1 : 0;
+    const ChannelTables<double>& ct = a.tables->ch[c];
+    double acc[NHACC];
+#pragma unroll
+    for (int i = 0; i < NHACC; ++i) acc[i] = 0.0;
+    double carry = 0.0;   // [rho_{f+1}(1) - rho_{f+1}(0)] + [q_{f+1}(1|1) - q_{f+1}(1|0)] Delta_{f+1}
+    const double scale = -a.sN * mu;   // loss = -ELBO; all frames: no frame scale
+    for (int f = F - 1; f >= 0; --f) {
+        const int64_t u = ((int64_t)ni * F + f) * C + c;
+        const int64_t iz = a.hmm_ztrans(n, f, c);
+        const ChainRow r0 = chain_row((double)a.lparams[iz + 0], (double)a.lparams[iz + 1], a.mc);
+        const ChainRow r1 = chain_row((double)a.lparams[iz + 2], (double)a.lparams[iz + 3], a.mc);
+        const double delta = ((double)a.hmm_v[a.U + u] - (double)a.hmm_v[u]) + carry;
+        double ap0 = 1.0, ap1 = 0.0;   // a_{f-1}
+        if (f > 0) { ap0 = a.hmm_a[u - C]; ap1 = a.hmm_a[a.U + u - C]; }
+        // log p_f(z | z'): the initial distribution at f = 0 (only row z' = 0 carries weight), else the transition matrix
+        double R0[kZ], R1[kZ];
+#pragma unroll
+        for (int z = 0; z < kZ; ++z) {
+            R0[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][0][z]) - r0.lq[z];
+            R1[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][1][z]) - r1.lq[z];
+        }
+        const double g0 = ap0 * r0.q[1] * r0.q[0] * (R0[1] - R0[0] + delta);
+        const double g1 = ap1 * r1.q[1] * r1.q[0] * (R1[1] - R1[0] + delta);
+        a.lgrads[iz + 0] = (T)(-scale * g0);
+        a.lgrads[iz + 1] = (T)(scale * g0);
+        a.lgrads[iz + 2] = (T)(-scale * g1);
+        a.lgrads[iz + 3] = (T)(scale * g1);
+        const double rho0 = r0.q[0] * R0[0] + r0.q[1] * R0[1], rho1 = r1.q[0] * R1[0] + r1.q[1] * R1[1];
+        acc[HACC_ELBO] += ap0 * rho0 + ap1 * rho1;
+        if (ot) {
+            if (f == 0) {
+#pragma unroll
+                for (int z = 0; z < kZ; ++z) acc[HACC_INIT + z] += ap0 * r0.q[z];
+            } else {
+#pragma unroll
+                for (int z = 0; z < kZ; ++z) {
+                    acc[HACC_TRANS + z] += ap0 * r0.q[z];
+                    acc[HACC_TRANS + kZ + z] += ap1 * r1.q[z];
+                }
+            }
+        }
+        carry = (rho1 - rho0) + (r1.q[1] - r0.q[1]) * delta;
+    }
+#pragma unroll
+    for (int i = 0; i < NHACC; ++i) hpartial[(int64_t)t * NHACC + i] = mu * acc[i];
+}
+
+// hacc[c][i] = sum over the minibatch AOIs, in index order (one thread per value: a few hundred terms)
+__global__ void hmm_reduce_kernel(const double* __restrict__ hpartial, int nb, int C, double* __restrict__ hacc) {
+    const int t = threadIdx.x;
+    if (blockIdx.x != 0 || t >= C * NHACC) return;
+    const int c = t / NHACC, i = t - c * NHACC;
+    double s = 0.0;
+    for (int ni = 0; ni < nb; ++ni) s += hpartial[((int64_t)ni * C + c) * NHACC + i];
+    hacc[t] = s;
+}
+
 // ---- z / theta posterior of one particle, accumulated into the running means (row N1) ---------------------
 template <typename T>
 __global__ void __launch_bounds__(kLocalBlock) zprobs_kernel(const LocalArgs<T> a, T weight, T* __restrict__ z_probs,
@@ -412,11 +555,11 @@ __global__ void finalize_loss_kernel(const double* __restrict__ elbo_parts, int 
 // ---- globals, split reverse mode (see cosmos_globals.cuh): prepare runs right after sampling on the side stream,
 // finish after the accumulators exist.  prepare: one block per site, lanes 0..2 evaluate drive = 0, e0, e1.
 template <typename T>
-__global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+__global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
                                        const double* __restrict__ gstate, GlobalPrep* __restrict__ prep) {
     const int site = blockIdx.x, lane = threadIdx.x;
-    if (lane >= 3 || site >= global_site_count(Q)) return;
-    GlobalLayout gl{Q};
+    if (lane >= 3 || site >= global_site_count(Q, hmm)) return;
+    GlobalLayout gl{Q, hmm};
     double u[kMaxGlobals];
     for (int i = 0; i < gl.count(); ++i) { u[i] = (double)gparams[i]; prep->grad[site][lane][i] = 0.0; }
     const double drive[2] = {lane == 1 ? 1.0 : 0.0, lane == 2 ? 1.0 : 0.0};
@@ -426,23 +569,24 @@ __global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, Mod
 
 // finish: thread i owns global parameter i; thread 0 also sums the ELBO parts in a fixed order
 template <typename T>
-__global__ void globals_finish_kernel(int Q, ModelConst mc, const double* __restrict__ gstate,
-                                      const GlobalPrep* __restrict__ prep, const double* __restrict__ acc, double sN,
+__global__ void globals_finish_kernel(int Q, bool hmm, ModelConst mc, const double* __restrict__ gstate,
+                                      const GlobalPrep* __restrict__ prep, const double* __restrict__ acc,
+                                      const double* __restrict__ hacc, double sN,
                                       double sF, T* __restrict__ ggrads, double* __restrict__ loss) {
-    GlobalLayout gl{Q};
+    GlobalLayout gl{Q, hmm};
     const int i = threadIdx.x;
     if (blockIdx.x != 0) return;
     if (i < gl.count()) {
         const int site = global_param_site(i, Q);
         double drive[2], elbo_data;
-        globals_drive(site, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, drive, elbo_data);
+        globals_drive(site, gl, mc, gstate + kMaxGlobalNoise, acc, hacc, sN, sF, drive, elbo_data);
         const double g0 = prep->grad[site][0][i];
         ggrads[i] = (T)(g0 + drive[0] * (prep->grad[site][1][i] - g0) + drive[1] * (prep->grad[site][2][i] - g0));
     }
     if (i == 0) {
         double drive[2], e;
-        globals_drive(0, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, drive, e);
-        for (int site = 0; site < global_site_count(Q); ++site) e += prep->elbo[site];
+        globals_drive(0, gl, mc, gstate + kMaxGlobalNoise, acc, hacc, sN, sF, drive, e);
+        for (int site = 0; site < global_site_count(Q, hmm); ++site) e += prep->elbo[site];
         loss[0] = -e;
     }
 }
@@ -505,22 +649,33 @@ extern "C" int64_t tq_local_post_scratch(int nb, int fb, int C) {
 extern "C" int64_t tq_local_post_tickets(int nb, int fb, int C) { (void)fb; return ((int64_t)nb * C + 1 + 1) / 2; }
 extern "C" int tq_site_record_rows(void) { return NREC; }
 
-extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
-                                        uint64_t seed, const void* state, double* gstate, void* tables,
-                                        void* gain_out, void* stream) {
+static int globals_sample_impl(int dtype, int Q, bool hmm, const void* gparams, const void* mc, const double* noise_in,
+                               uint64_t seed, const void* state, double* gstate, void* tables, void* gain_out, void* stream) {
     TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
     TQ_CHECK_ARG(gparams && mc && state && gstate && tables && gain_out, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
+    const int sites = global_site_count(Q, hmm);
     if (dtype == TQ_F32)
-        globals_sample_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+        globals_sample_kernel<float><<<sites, 32, 0, st>>>((const float*)gparams, Q, hmm, m, noise_in, seed, (const StepState*)state,
                                                       gstate, (GlobalTables<double>*)tables, (float*)gain_out);
     else if (dtype == TQ_F64)
-        globals_sample_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, noise_in, seed, (const StepState*)state,
+        globals_sample_kernel<double><<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, noise_in, seed, (const StepState*)state,
                                                        gstate, (GlobalTables<double>*)tables, (double*)gain_out);
     else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("globals_sample_kernel launch");
     return TQ_OK;
+}
+
+extern "C" int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
+                                        uint64_t seed, const void* state, double* gstate, void* tables,
+                                        void* gain_out, void* stream) {
+    return globals_sample_impl(dtype, Q, false, gparams, mc, noise_in, seed, state, gstate, tables, gain_out, stream);
+}
+extern "C" int tq_hmm_globals_sample(int dtype, int Q, const void* gparams, const void* mc, const double* noise_in,
+                                     uint64_t seed, const void* state, double* gstate, void* tables,
+                                     void* gain_out, void* stream) {
+    return globals_sample_impl(dtype, Q, true, gparams, mc, noise_in, seed, state, gstate, tables, gain_out, stream);
 }
 
 template <typename T>
@@ -604,6 +759,125 @@ extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_
     return TQ_ERR_ARG;
 }
 
+// ---- hmm variant: host side ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int run_hmm_forward(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, double* a_out,
+                           void* qm, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, nullptr, 0, 0, nullptr);
+    a.hmm_a = a_out;
+    a.qm = (T*)qm;
+    if (a.U == 0) return TQ_OK;
+    const int chains = view->nb * view->C;
+    hmm_forward_kernel<T><<<(chains + 63) / 64, 64, 0, st>>>(a, a_out);
+    TQ_LAUNCH_CHECK("hmm_forward_kernel launch");
+    hmm_weights_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a);
+    TQ_LAUNCH_CHECK("hmm_weights_kernel launch");
+    return TQ_OK;
+}
+
+static int hmm_check_view(const tq_patch_view* view) {
+    TQ_CHECK_ARG(view != nullptr, "NULL view");
+    TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
+    TQ_CHECK_ARG(view->fb == view->F && view->fdx == nullptr, "the hmm variant uses every frame (models/hmm.py:127-131): fb == F, fdx == NULL");
+    TQ_CHECK_ARG((int64_t)view->nb * view->fb * view->C < ((int64_t)1 << 31), "minibatch too large for one launch");
+    return TQ_OK;
+}
+
+extern "C" int64_t tq_hmm_local_numel(int64_t Nt, int64_t F, int64_t C) {
+    LocalOffsets lo{Nt, F, C};
+    return lo.numel() + (int64_t)kK * Nt * F * C + Nt * F * C * kZ * kZ;
+}
+extern "C" int tq_hmm_chain_sums(void) { return NHACC; }
+
+extern "C" int tq_hmm_forward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                              double* a_out, void* qm, void* stream) {
+    int stv = hmm_check_view(view);
+    if (stv != TQ_OK) return stv;
+    TQ_CHECK_ARG(mc && lparams && a_out && qm, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_hmm_forward<float>(view, Nt, (const ModelConst*)mc, lparams, a_out, qm, st);
+    if (dtype == TQ_F64) return run_hmm_forward<double>(view, Nt, (const ModelConst*)mc, lparams, a_out, qm, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T>
+static int run_hmm_post(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                        const void* samples, const void* rec, const void* L, const void* gs, const void* g_rate, const double* a_in,
+                        double sN, void* lgrads, void* v_out, double* tickets, double* block_partial, double* acc, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
+    a.samples = (T*)samples;
+    a.rec = (T*)rec;
+    a.L = (const T*)L;
+    a.gs = (const T*)gs;
+    a.g_rate = (const T*)g_rate;
+    a.sN = sN; a.sF = 1.0;
+    a.lgrads = (T*)lgrads;
+    a.block_partial = block_partial;
+    a.hmm_a = a_in;
+    a.hmm_v = (T*)v_out;
+    const int upt = post_upt(view->nb, view->fb, view->C);
+    const int chunks = post_chunks(view->fb, upt);
+    const int64_t nblocks = (int64_t)view->nb * view->C * chunks;
+    if (a.U == 0) { cudaMemsetAsync(acc, 0, sizeof(double) * view->C * NACC, st); return TQ_OK; }
+    if (nblocks >= (int64_t)1 << 31) { set_error("minibatch too large for one launch"); return TQ_ERR_ARG; }
+    if (upt == 4) local_post_kernel<T, 4, true><<<(int)nblocks, kLocalBlock, 0, st>>>(a, chunks, (unsigned int*)tickets, acc);
+    else local_post_kernel<T, 1, true><<<(int)nblocks, kLocalBlock, 0, st>>>(a, chunks, (unsigned int*)tickets, acc);
+    TQ_LAUNCH_CHECK("local_post_kernel<hmm> launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_hmm_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                 const void* tables, const void* samples, const void* rec, const void* L, const void* gs,
+                                 const void* g_rate, const double* a_in, double sN, void* lgrads, void* v_out, double* tickets,
+                                 double* block_partial, double* acc, void* stream) {
+    int stv = hmm_check_view(view);
+    if (stv != TQ_OK) return stv;
+    TQ_CHECK_ARG(mc && lparams && tables && samples && rec && L && gs && g_rate && a_in, "NULL input pointer");
+    TQ_CHECK_ARG(lgrads && v_out && tickets && block_partial && acc, "NULL output pointer");
+    TQ_CHECK_ARG(view->mask && view->is_ontarget, "view needs mask and is_ontarget");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_hmm_post<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, a_in, sN, lgrads, v_out, tickets, block_partial, acc, st);
+    if (dtype == TQ_F64) return run_hmm_post<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, rec, L, gs, g_rate, a_in, sN, lgrads, v_out, tickets, block_partial, acc, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T>
+static int run_hmm_backward(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                            const double* a_in, const void* v_in, double sN, void* lgrads, double* hpartial, double* hacc, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
+    a.sN = sN; a.sF = 1.0;
+    a.lgrads = (T*)lgrads;
+    a.hmm_a = a_in;
+    a.hmm_v = (T*)v_in;
+    const int chains = view->nb * view->C;
+    if (chains > 0 && a.U > 0) {
+        hmm_backward_kernel<T><<<(chains + 63) / 64, 64, 0, st>>>(a, hpartial);
+        TQ_LAUNCH_CHECK("hmm_backward_kernel launch");
+    }
+    hmm_reduce_kernel<<<1, 64, 0, st>>>(hpartial, a.U > 0 ? view->nb : 0, view->C, hacc);
+    TQ_LAUNCH_CHECK("hmm_reduce_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                               const void* tables, const double* a_in, const void* v_in, double sN, void* lgrads,
+                               double* hpartial, double* hacc, void* stream) {
+    int stv = hmm_check_view(view);
+    if (stv != TQ_OK) return stv;
+    TQ_CHECK_ARG(mc && lparams && tables && a_in && v_in && lgrads && hpartial && hacc, "NULL pointer");
+    TQ_CHECK_ARG(view->mask && view->is_ontarget, "view needs mask and is_ontarget");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_hmm_backward<float>(view, Nt, (const ModelConst*)mc, lparams, tables, a_in, v_in, sN, lgrads, hpartial, hacc, st);
+    if (dtype == TQ_F64) return run_hmm_backward<double>(view, Nt, (const ModelConst*)mc, lparams, tables, a_in, v_in, sN, lgrads, hpartial, hacc, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
 template <typename T>
 static int run_zprobs(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
                       const void* samples, double weight, void* z_probs, void* theta_probs, cudaStream_t st) {
@@ -649,34 +923,52 @@ extern "C" int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, con
 
 extern "C" int tq_sizeof_gprep(void) { return (int)sizeof(GlobalPrep); }
 
-extern "C" int tq_cosmos_globals_prepare(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
-                                         void* gprep, void* stream) {
+static int globals_prepare_impl(int dtype, int Q, bool hmm, const void* gparams, const void* mc, const double* gstate,
+                                void* gprep, void* stream) {
     TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
     TQ_CHECK_ARG(gparams && mc && gstate && gprep, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
+    const int sites = global_site_count(Q, hmm);
     if (dtype == TQ_F32)
-        globals_prepare_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, gstate, (GlobalPrep*)gprep);
+        globals_prepare_kernel<float><<<sites, 32, 0, st>>>((const float*)gparams, Q, hmm, m, gstate, (GlobalPrep*)gprep);
     else if (dtype == TQ_F64)
-        globals_prepare_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, gstate, (GlobalPrep*)gprep);
+        globals_prepare_kernel<double><<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, gstate, (GlobalPrep*)gprep);
     else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("globals_prepare_kernel launch");
     return TQ_OK;
 }
 
-extern "C" int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
-                                        const double* acc, double sN, double sF, void* ggrads, double* loss, void* stream) {
+static int globals_finish_impl(int dtype, int Q, bool hmm, const void* mc, const double* gstate, const void* gprep,
+                               const double* acc, const double* hacc, double sN, double sF, void* ggrads, double* loss, void* stream) {
     TQ_CHECK_ARG(Q >= 1 && Q <= kMaxC, "Q (channels) must be in [1, 4]");
-    TQ_CHECK_ARG(mc && gstate && gprep && acc && ggrads && loss, "NULL pointer");
+    TQ_CHECK_ARG(mc && gstate && gprep && acc && ggrads && loss && (hacc || !hmm), "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
     if (dtype == TQ_F32)
-        globals_finish_kernel<float><<<1, 32, 0, st>>>(Q, m, gstate, (const GlobalPrep*)gprep, acc, sN, sF, (float*)ggrads, loss);
+        globals_finish_kernel<float><<<1, 64, 0, st>>>(Q, hmm, m, gstate, (const GlobalPrep*)gprep, acc, hacc, sN, sF, (float*)ggrads, loss);
     else if (dtype == TQ_F64)
-        globals_finish_kernel<double><<<1, 32, 0, st>>>(Q, m, gstate, (const GlobalPrep*)gprep, acc, sN, sF, (double*)ggrads, loss);
+        globals_finish_kernel<double><<<1, 64, 0, st>>>(Q, hmm, m, gstate, (const GlobalPrep*)gprep, acc, hacc, sN, sF, (double*)ggrads, loss);
     else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("globals_finish_kernel launch");
     return TQ_OK;
+}
+
+extern "C" int tq_cosmos_globals_prepare(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
+                                         void* gprep, void* stream) {
+    return globals_prepare_impl(dtype, Q, false, gparams, mc, gstate, gprep, stream);
+}
+extern "C" int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
+                                        const double* acc, double sN, double sF, void* ggrads, double* loss, void* stream) {
+    return globals_finish_impl(dtype, Q, false, mc, gstate, gprep, acc, nullptr, sN, sF, ggrads, loss, stream);
+}
+extern "C" int tq_hmm_globals_prepare(int dtype, int Q, const void* gparams, const void* mc, const double* gstate,
+                                      void* gprep, void* stream) {
+    return globals_prepare_impl(dtype, Q, true, gparams, mc, gstate, gprep, stream);
+}
+extern "C" int tq_hmm_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
+                                     const double* acc, const double* hacc, double sN, void* ggrads, double* loss, void* stream) {
+    return globals_finish_impl(dtype, Q, true, mc, gstate, gprep, acc, hacc, sN, 1.0, ggrads, loss, stream);
 }
 
 extern "C" int tq_adam_dense(int dtype, int64_t n, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,

@@ -1,0 +1,146 @@
+"""
+One SVI step of the *hmm* variant (reference: tapqir/models/hmm.py) on the kernels of csrc/: the continuous guide
+sites and the 4-configuration likelihood kernel are cosmos' own; around them the guide's Markov chain
+(tq_hmm_forward / tq_hmm_backward), the per-state emission terms (tq_hmm_local_post) and the init / trans global
+sites (tq_hmm_globals_*).  See include/tapqir_b200.h for the call order and csrc/cosmos_hmm.cuh for the maths.
+"""
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from tapqir_b200 import _lib
+from tapqir_b200.models import layout as L
+from tapqir_b200.models.engine import CosmosEngine
+
+
+class HmmEngine(CosmosEngine):
+    def __init__(self, store, Nt_local, F, C, P, priors, **kw):
+        kw["fbatch_size"] = F   # every frame, every step (hmm.py:127-131)
+        super().__init__(store, Nt_local, F, C, P, priors, **kw)
+        dev, dtype, f64 = self.device, self.dtype, torch.float64
+        self.ll = L.HmmLocalLayout(self.Nt, self.F, self.C)
+        assert self.ll.numel == self.lib.tq_hmm_local_numel(self.Nt, self.F, self.C)
+        self.gl = L.HmmGlobalLayout(self.C)
+        z = lambda n, dt=dtype: torch.zeros(n, dtype=dt, device=dev)
+        self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
+        self.gparams, self.ggrads, self.gm, self.gv = z(self.gl.numel), z(self.gl.numel), z(self.gl.numel), z(self.gl.numel)
+        self.nh = self.lib.tq_hmm_chain_sums()
+        self.hacc = z(self.C * self.nh, f64)
+        self.set_batch(kw.get("nbatch_size") or self.Nt, F)
+
+    def set_batch(self, nbatch_size, fbatch_size):
+        super().set_batch(nbatch_size, self.F)
+        if not hasattr(self, "nh"):
+            return
+        dev = self.device
+        self.chain_a = torch.empty(2, self.U, dtype=torch.float64, device=dev)
+        self.chain_v = torch.empty(2, self.U, dtype=self.dtype, device=dev)
+        self.hpartial = torch.empty(max(self.nb * self.C, 1) * self.nh, dtype=torch.float64, device=dev)
+
+    # ---- parameter access (reference names / shapes) ------------------------------------------------------------------
+    def named_unconstrained(self):
+        out = OrderedDict(self.ll.named(self.lparams))
+        out.update(self.gl.views(self.gparams))
+        return out
+
+    def named_grads(self):
+        out = OrderedDict(self.ll.named(self.lgrads))
+        out.update(self.gl.views(self.ggrads))
+        return out
+
+    def load_unconstrained(self, tensors):
+        self.ll.load_named(self.lparams, tensors)
+        for k, v in self.gl.views(self.gparams).items():
+            v.copy_(tensors[k].to(device=self.device, dtype=self.dtype).reshape(v.shape))
+
+    # ---- one step ------------------------------------------------------------------------------------------------------
+    def _enqueue(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
+        assert fdx is None, "the hmm variant uses every frame"
+        lib, st, code = self.lib, _lib.stream_ptr(self.device), self.code
+        p = _lib.ptr
+        mc = ctypes.byref(self.mc)
+        with torch.cuda.device(self.device):
+            if ndx is None and not self.full_n:
+                _lib.check(lib.tq_subsample(self.Nt, self.nb, self.seed, p(self.state), 2 + self.rank, p(self.perm_n),
+                                            p(self.ndx), st), "tq_subsample")
+                ndx = self.ndx
+            view = self._view(ndx, None)
+            if not self.full_n:
+                self.lgrads.zero_()
+            main = torch.cuda.current_stream(self.device)
+            self._ev_fork0.record(main)
+            self._side.wait_event(self._ev_fork0)
+            with torch.cuda.stream(self._side):
+                sst = _lib.stream_ptr(self.device)
+                _lib.check(lib.tq_hmm_globals_sample(code, self.C, p(self.gparams), mc, p(global_noise), self.seed,
+                                                     p(self.state), p(self.gstate), p(self.tables), p(self.gain), sst),
+                           "tq_hmm_globals_sample")
+                self._ev_join0.record(self._side)
+                _lib.check(lib.tq_hmm_globals_prepare(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.gprep), sst),
+                           "tq_hmm_globals_prepare")
+            _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                           p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
+                       "tq_cosmos_sites")
+            _lib.check(lib.tq_hmm_forward(code, view, self.Nt, mc, p(self.lparams), p(self.chain_a), p(self.qm), st),
+                       "tq_hmm_forward")
+            main.wait_event(self._ev_join0)
+            S, G, K = self.samples, self.gs, L.K
+            if time_likelihood is not None:
+                time_likelihood[0].record()
+            _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
+                                             p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg_arg), 4, p(self.qm),
+                                             p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
+                                             p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
+            if time_likelihood is not None:
+                time_likelihood[1].record()
+            _lib.check(lib.tq_hmm_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
+                                             p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), p(self.chain_a), self.sN,
+                                             p(self.lgrads), p(self.chain_v), p(self.tickets), p(self.block_partial), p(self.acc),
+                                             st), "tq_hmm_local_post")
+            _lib.check(lib.tq_hmm_backward(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.chain_a),
+                                           p(self.chain_v), self.sN, p(self.lgrads), p(self.hpartial), p(self.hacc), st),
+                       "tq_hmm_backward")
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                sst = _lib.stream_ptr(self.device)
+                if self.world_size > 1:
+                    torch.distributed.all_reduce(self.acc, group=self.pg)
+                    torch.distributed.all_reduce(self.hacc, group=self.pg)
+                _lib.check(lib.tq_hmm_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc), p(self.hacc),
+                                                     self.sN, p(self.ggrads), p(self.loss), sst), "tq_hmm_globals_finish")
+                if update:
+                    b1, b2 = self.betas
+                    _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
+                                                 p(self.gv), self.lr, b1, b2, self.adam_eps, p(self.state), sst),
+                               "tq_adam_dense")
+                self._ev_join.record(self._side)
+            if update:
+                b1, b2 = self.betas
+                _lib.check(lib.tq_adam_dense(code, self.ll.numel, p(self.lparams), p(self.lgrads), p(self.lm), p(self.lv),
+                                             self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
+            main.wait_event(self._ev_join)
+            if update:
+                _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
+        return self.loss
+
+    # ---- posterior of the chain (hmm.py:627-633) --------------------------------------------------------------------------
+    @torch.no_grad()
+    def z_probs(self):
+        """Forward marginals a_f(z) of the guide's chain for every local AOI: (Nt, F, C, 2)."""
+        lib, p = self.lib, _lib.ptr
+        view = _lib.make_view(self.store.pixels, self.store.xy, self.store.offset_samples, self.store.offset_logits, nb=self.Nt,
+                              fb=self.F, C=self.C, F=self.F, P=self.P, ndx=None, fdx=None, is_ontarget=self.store.is_ontarget,
+                              mask=self.store.mask)
+        U = self.Nt * self.F * self.C
+        a = torch.empty(2, U, dtype=torch.float64, device=self.device)
+        qm = torch.empty(4, U, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tq_hmm_forward(self.code, view, self.Nt, ctypes.byref(self.mc), p(self.lparams), p(a), p(qm),
+                                          _lib.stream_ptr(self.device)), "tq_hmm_forward")
+        return a.view(2, self.Nt, self.F, self.C).permute(1, 2, 3, 0).contiguous()
+
+    def compute_probs(self, *args, **kwargs):
+        raise NotImplementedError("theta_probs of the hmm variant (hmm.py:541-625) is not built yet")

@@ -141,3 +141,66 @@ def pack_local_noise(noise, dtype, device):
     for site in ("height", "width", "x", "y"):
         rows.append(noise[site].reshape(K, -1))
     return torch.cat(rows, 0).to(dtype=dtype, device=device).contiguous()
+
+
+# ---- hmm variant (models/hmm.py) -------------------------------------------------------------------------------------
+class HmmGlobalLayout(GlobalLayout):
+    """cosmos global layout with ``pi_*`` read as ``init_*``, then ``trans_mean (Q,2,2)``, ``trans_size (Q,2,1)``."""
+
+    def __init__(self, Q):
+        super().__init__(Q)
+        shapes = OrderedDict()
+        for n, s in self.shapes.items():
+            shapes[{"pi_mean": "init_mean", "pi_size": "init_size"}.get(n, n)] = s
+        shapes["trans_mean"] = (self.Q, S + 1, S + 1)
+        shapes["trans_size"] = (self.Q, S + 1, 1)
+        self.shapes = shapes
+        self.offsets, off = OrderedDict(), 0
+        for n, s in shapes.items():
+            self.offsets[n] = off
+            off += math.prod(s)
+        self.numel = off  # 4 + 11Q
+        self.noise_shapes = OrderedDict([("gain", ()), ("proximity", ()), ("init", (self.Q, S + 1)), ("lamda", (self.Q,)),
+                                         ("trans", (self.Q, S + 1, S + 1))])
+        self.noise_offsets, off = OrderedDict(), 0
+        for n, s in self.noise_shapes.items():
+            self.noise_offsets[n] = off
+            off += math.prod(s)
+        self.noise_numel = off
+
+
+class HmmLocalLayout(LocalLayout):
+    """
+    Flat local buffer of the hmm variant: the cosmos layout (whose ``m_probs`` slabs hold ``m_probs[z = 0]``), then
+    ``m_probs[z = 1]`` (K,Nt,F,C), then ``z_trans`` (Nt,F,C,2,2).  ``views`` exposes the raw pieces
+    (``m_probs_z0``, ``m_probs_z1``); :meth:`named` / :meth:`load_named` convert from / to the reference's
+    ``m_probs (1+S,K,Nt,F,C)``.
+    """
+
+    def __init__(self, Nt, F, C):
+        super().__init__(Nt, F, C)
+        self.std_numel = self.numel
+        unit = self.Nt * self.F * self.C
+        shapes, offsets = OrderedDict(), OrderedDict()
+        for n in self.shapes:
+            shapes["m_probs_z0" if n == "m_probs" else n] = self.shapes[n]
+            offsets["m_probs_z0" if n == "m_probs" else n] = self.offsets[n]
+        shapes["m_probs_z1"], offsets["m_probs_z1"] = (K, self.Nt, self.F, self.C), self.std_numel
+        shapes["z_trans"], offsets["z_trans"] = (self.Nt, self.F, self.C, S + 1, S + 1), self.std_numel + K * unit
+        self.shapes, self.offsets = shapes, offsets
+        self.numel = self.std_numel + K * unit + unit * (S + 1) ** 2
+
+    def named(self, flat):
+        """name -> tensor with the reference's names and shapes (``m_probs`` is a stacked copy)."""
+        v = self.views(flat)
+        out = OrderedDict((n, t) for n, t in v.items() if not n.startswith("m_probs_z"))
+        out["m_probs"] = torch.stack([v["m_probs_z0"], v["m_probs_z1"]], 0)
+        return out
+
+    def load_named(self, flat, tensors):
+        v = self.views(flat)
+        for n, t in v.items():
+            if n.startswith("m_probs_z"):
+                t.copy_(tensors["m_probs"][int(n[-1])].to(device=flat.device, dtype=flat.dtype).reshape(t.shape))
+            else:
+                t.copy_(tensors[n].to(device=flat.device, dtype=flat.dtype).reshape(t.shape))
