@@ -36,7 +36,12 @@ WORKLOADS = {
     "c2mb": (100, 1000, 10, 512, "cosmos C2 with the reference-default minibatch 10 AOIs x 512 frames (main.py:1428-1431)"),
     "c3": (1000, 5000, 1000, 5000, "cosmos C3: simulated N=1000 AOIs x F=5000 frames on this GPU, full batch"),
     "c1": (5, 100, 5, 100, "cosmos C1: simulated N=5 AOIs x F=100 frames, full batch"),
+    # BASELINE configs 4 and 5 (parity-test cases; here for per-config timings, not the headline line)
+    "c4": (500, 2000, 500, 2000, "cosmos C4: two-channel (C=2) simulated N=500 AOIs x F=2000 frames on this GPU, full batch"),
+    "c5": (200, 2000, 200, 2000, "cosmos+hmm C5: simulated N=200 AOIs x F=2000 frames on this GPU, all frames per step"),
 }
+WORKLOAD_CHANNELS = {"c4": 2}
+WORKLOAD_MODEL = {"c5": "cosmos+hmm"}
 O_BINS = 3   # offset bins of the simulated data (simulate.py:92,103): three IDENTICAL bins, merged to one on upload
 
 
@@ -156,14 +161,14 @@ def make_shard(workload, rank, device):
     from tapqir_b200.utils.simulate import simulate
 
     n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
-    ds = simulate(n_aoi, n_frames, C=1, P=14, seed=rank, device=device, aoi_chunk=50)
+    ds = simulate(n_aoi, n_frames, C=WORKLOAD_CHANNELS.get(workload, 1), P=14, seed=rank, device=device, aoi_chunk=50)
     return ds, nb, fb, desc
 
 
 def run_native(args):
     from oracle import cosmos_oracle as O
     from tapqir_b200 import _lib
-    from tapqir_b200.models.cosmos import cosmos
+    from tapqir_b200.models import models as model_registry
 
     rank, world, local = dist_env()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
@@ -175,12 +180,13 @@ def run_native(args):
     lib = _lib.load()  # raises if the sm_100a library is missing: no fallback
 
     ds, nb, fb, desc = make_shard(args.workload, rank, device)
-    model = cosmos(device=str(device), dtype="float")
+    model = model_registry[WORKLOAD_MODEL.get(args.workload, "cosmos")](device=str(device), dtype="float")
     model.data = ds
     model.merge_offsets = not args.keep_offset_bins
     model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world, presharded=True)
     eng = model.engine
-    units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step (C = 1)
+    units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step
+    patches_per_step = units_per_step * eng.C   # units of the kernels: one per (AOI, frame, channel)
     launches_per_step = model.launches_per_step
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
@@ -235,9 +241,9 @@ def run_native(args):
     o_exec = int(eng.store.offset_samples.numel())   # distinct offset bins the kernels loop over
     MUFU_PER_UNIT, FP32_OPS_PER_UNIT = algorithmic_work(o_exec)
     FLOP_PER_UNIT = 2 * FP32_OPS_PER_UNIT                # FMA = 2 flops, like the measured peak
-    mufu_ach = MUFU_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
-    flop_ach = FLOP_PER_UNIT * units_per_step / (k_ms_avg * 1e-3)
-    hbm_ach = KSMOGN_HBM_BYTES_PER_UNIT * units_per_step / (k_ms_avg * 1e-3) / 1e9
+    mufu_ach = MUFU_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3)
+    flop_ach = FLOP_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3)
+    hbm_ach = KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3) / 1e9
     t_mufu, t_fp32 = MUFU_PER_UNIT / peaks["mufu"], FLOP_PER_UNIT / (2 * peaks["fma"])
     t_hbm = KSMOGN_HBM_BYTES_PER_UNIT / (hbm_peak * 1e9)
     bound = max((t_mufu, "mufu"), (t_fp32, "fp32"), (t_hbm, "hbm"))
@@ -246,16 +252,16 @@ def run_native(args):
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists():
         t = json.loads(tj.read_text()).get("ksmogn_fast_kernel" if o_exec == 1 else "ksmogn_fast_kernel_o3", {})
-        if t.get("workload") == args.workload and t.get("units_per_launch") == units_per_step:
+        if t.get("workload") == args.workload and t.get("units_per_launch") == patches_per_step:
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
-                       "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * units_per_step, "source": t["source"]}
+                       "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step, "source": t["source"]}
     roofline = {
         "kernel": f"ksmogn_fast_kernel<uint16,{o_exec},true,true> (fused render + offset-marginalised likelihood fwd+bwd)",
         "bound": bound[1],
         "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
         "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
         "unit": "Top/s (MUFU)" if bound[1] == "mufu" else ("TFLOP/s" if bound[1] == "fp32" else "GB/s"),
-        "frac": (units_per_step / (k_ms_avg * 1e-3)) / roof_units_per_s,
+        "frac": (patches_per_step / (k_ms_avg * 1e-3)) / roof_units_per_s,
         "traffic": traffic,
         "kernel_ms": k_ms_avg,
         "kernel_share_of_step": k_ms_avg / ms_per_step,
@@ -265,7 +271,7 @@ def run_native(args):
         "peaks_measured_here": {"mufu_Tops": peaks["mufu"] / 1e12, "fp32_TFLOPs": 2 * peaks["fma"] / 1e12,
                                 "hbm_GBs": hbm_peak, "hbm_source": hbm_src + " (MEASURED_PEAKS.json)"},
         "hbm_view": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak},
-        "step_roofline_frac": value / world / roof_units_per_s,
+        "step_roofline_frac": value * eng.C / world / roof_units_per_s,
     }
 
     # ---- end to end through the public API with host buffers --------------------------------------------
@@ -303,7 +309,7 @@ def run_native(args):
             "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value, "unit": "AOI-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
+            "config": {"workload": desc, "model": model.name, "channels": eng.C, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
                        "offset_bins_distinct": o_exec,
                        "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
                        "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},

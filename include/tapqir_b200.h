@@ -194,6 +194,7 @@ int tq_cosmos_globals_finish(int dtype, int Q, const void* mc, const double* gst
  * transition tables `z_trans` and spot presences conditional on z_f; every frame is used (fb == F, fdx == NULL).
  * Call order of one step:
  *   tq_hmm_globals_sample -> tq_hmm_globals_prepare, tq_cosmos_sites (continuous sites, unchanged) -> tq_hmm_forward
+ *   (needs the tables of tq_hmm_globals_sample)
  *   -> tq_ksmogn_fwd_bwd (W = qm of tq_hmm_forward) -> tq_hmm_local_post -> tq_hmm_backward
  *   -> [all-reduce of acc and hacc] -> tq_hmm_globals_finish -> tq_adam_dense x2 -> tq_step_advance
  * Local flat buffer (tq_hmm_local_numel values): the cosmos layout (its m_probs slabs hold m_probs[z = 0]), then
@@ -213,16 +214,19 @@ int tq_hmm_globals_prepare(int dtype, int Q, const void* gparams, const void* mc
 int tq_hmm_globals_finish(int dtype, int Q, const void* mc, const double* gstate, const void* gprep,
                           const double* acc, const double* hacc, double sN, void* ggrads,
                           double* loss, void* stream);
+int tq_hmm_chain_rows(void);   /* rows: (tq_hmm_chain_rows(), U) double per-frame terms of the chain, written by forward */
 int tq_hmm_forward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
-                   const void* lparams, double* a_out, void* qm, void* stream);
+                   const void* lparams, const void* tables, double* rows, double* a_out, void* qm,
+                   void* stream);
 int tq_hmm_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
                       const void* lparams, const void* tables, const void* samples, const void* rec,
                       const void* L, const void* gs, const void* g_rate, const double* a_in, double sN,
                       void* lgrads, void* v_out, double* tickets, double* block_partial, double* acc,
                       void* stream);
 int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
-                    const void* lparams, const void* tables, const double* a_in, const void* v_in,
-                    double sN, void* lgrads, double* hpartial, double* hacc, void* stream);
+                    const void* lparams, const void* tables, const double* rows, const double* a_in,
+                    const void* v_in, double sN, void* lgrads, double* hpartial, double* hacc,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ingestion of raw .glimpse frames (imscroll/glimpse_reader.py:168-186, 354-381).

@@ -64,10 +64,11 @@ SIGNATURES = {
     "tq_hmm_globals_sample": (c_int, [c_int, c_int, _VP, _VP, _VP, c_uint64, _VP, _VP, _VP, _VP, _VP]),
     "tq_hmm_globals_prepare": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, _VP]),
     "tq_hmm_globals_finish": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP]),
-    "tq_hmm_forward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP]),
+    "tq_hmm_chain_rows": (c_int, []),
+    "tq_hmm_forward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tq_hmm_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double,
                                   _VP, _VP, _VP, _VP, _VP, _VP]),
-    "tq_hmm_backward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP, _VP]),
+    "tq_hmm_backward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP, _VP]),
     "tq_crop_aois": (c_int, [_VP, c_int, c_int, c_int, c_int, _VP, _VP, c_int, c_int, c_int, _VP, _VP, _VP, _VP]),
     "tq_offset_hist": (c_int, [_VP, c_int, c_int, c_int, c_int, c_int, c_int, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),

@@ -383,24 +383,82 @@ __global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalA
     if (threadIdx.x < C * NACC) acc_out[threadIdx.x] = (fin[threadIdx.x][0] + fin[threadIdx.x][1]) + (fin[threadIdx.x][2] + fin[threadIdx.x][3]);
 }
 
-// ---- hmm: the guide's chain (cosmos_hmm.cuh).  One thread per (AOI, channel) walks the frames; everything in double
-// (a few dozen flops per unit; only differences of the big emission values propagate, see HmmUnitOut::v) -------------
+// ---- hmm: the guide's chain (cosmos_hmm.cuh) -------------------------------------------------------------------------
+// Everything the recursions need from one frame is local to it, so a per-unit kernel prepares it in parallel (the
+// exps / logs of the softmax rows), and the recursions themselves are warp-per-chain chunked scans of cheap maps:
+// lane l takes frames [l L, (l+1) L), composes its chunk, the 32 chunk maps are scanned with shuffles, and a second
+// sweep over the chunk produces the per-frame values.  All in double (a few dozen flops per unit; only differences of
+// the big emission values propagate, see HmmUnitOut::v).  One thread per chain walking 2000 frames cost 5.4 ms at C5.
+//
+// rows (6, U): q(1|z'=0), q(1|z'=1), rho(0), rho(1), rd(0), rd(1) with, for row z' of frame f,
+//   rho(z') = sum_z q(z|z') R(z', z),  rd(z') = R(z', 1) - R(z', 0),  R = log p_f(z|z') - log q_f(z|z')
+// (log p_f: the initial distribution at f = 0 -- only row 0 carries weight there -- else the transition matrix).
+enum { ROW_Q0 = 0, ROW_Q1, ROW_RHO0, ROW_RHO1, ROW_RD0, ROW_RD1, NROW };
+
 template <typename T>
-__global__ void hmm_forward_kernel(const LocalArgs<T> a, double* __restrict__ a_out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kLocalBlock) hmm_rows_kernel(const LocalArgs<T> a, double* __restrict__ rows) {
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    const UnitIndex ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    const int f = ui.fi;
+    const int ot = a.v.is_ontarget[ui.aoi] ? 1 : 0;
+    const ChannelTables<double>& ct = a.tables->ch[ui.c];
+    const T* zt = a.lparams + a.hmm_ztrans(ui.aoi, f, ui.c);
+    const ChainRow r[kZ] = {chain_row((double)zt[0], (double)zt[1], a.mc), chain_row((double)zt[2], (double)zt[3], a.mc)};
+#pragma unroll
+    for (int zr = 0; zr < kZ; ++zr) {
+        double R[kZ];
+#pragma unroll
+        for (int z = 0; z < kZ; ++z) R[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][zr][z]) - r[zr].lq[z];
+        rows[(int64_t)(ROW_Q0 + zr) * a.U + u32] = r[zr].q[1];
+        rows[(int64_t)(ROW_RHO0 + zr) * a.U + u32] = r[zr].q[0] * R[0] + r[zr].q[1] * R[1];
+        rows[(int64_t)(ROW_RD0 + zr) * a.U + u32] = R[1] - R[0];
+    }
+}
+
+// frames of lane `lane` of a warp-per-chain scan
+__device__ __forceinline__ void chain_chunk(int F, int lane, int& f_lo, int& f_hi) {
+    const int L = (F + 31) / 32;
+    f_lo = lane * L < F ? lane * L : F;
+    f_hi = (lane + 1) * L < F ? (lane + 1) * L : F;
+}
+
+// forward marginals a_f(z): a_f = a_{f-1} T_f, T_f = [[1-p, p], [1-r, r]], a_{-1} = e_0 (row 0 of z_trans is the
+// initial distribution, hmm.py:355-359).  Products of row-stochastic 2x2 matrices stay row-stochastic: (p, r) suffice.
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) hmm_forward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
+                                                                 double* __restrict__ a_out) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int C = a.v.C, F = a.v.F;
-    if (t >= a.v.nb * C) return;
-    const int ni = t / C, c = t - ni * C;
-    const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
-    double a0 = 1.0, a1 = 0.0;   // a_{-1} = e_0: row 0 of z_trans is the initial distribution            hmm.py:355-359
-    const T* zt = a.lparams + a.hmm_ztrans(n, 0, c);
-    for (int f = 0; f < F; ++f, zt += C * kZ * kZ) {
-        const ChainRow r0 = chain_row((double)zt[0], (double)zt[1], a.mc), r1 = chain_row((double)zt[2], (double)zt[3], a.mc);
-        const double b0 = a0 * r0.q[0] + a1 * r1.q[0], b1 = a0 * r0.q[1] + a1 * r1.q[1];
-        a0 = b0; a1 = b1;
-        const int64_t u = ((int64_t)ni * F + f) * C + c;
-        a_out[u] = a0;
-        a_out[a.U + u] = a1;
+    if (chain >= a.v.nb * C) return;
+    const int ni = chain / C, c = chain - ni * C;
+    int f_lo, f_hi;
+    chain_chunk(F, lane, f_lo, f_hi);
+    const int64_t u0 = ((int64_t)ni * F) * C + c;
+    const double* q0 = rows + (int64_t)ROW_Q0 * a.U + u0;
+    const double* q1 = rows + (int64_t)ROW_Q1 * a.U + u0;
+    double p = 0.0, r = 1.0;   // identity
+    for (int f = f_lo; f < f_hi; ++f) {
+        const double p2 = q0[(int64_t)f * C], r2 = q1[(int64_t)f * C];
+        const double np = (1.0 - p) * p2 + p * r2, nr = (1.0 - r) * p2 + r * r2;
+        p = np; r = nr;
+    }
+    // inclusive scan of the chunk products (earlier chunks multiply from the left), then shift to exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double po = __shfl_up_sync(0xffffffffu, p, o), ro = __shfl_up_sync(0xffffffffu, r, o);
+        if (lane >= o) {
+            const double np = (1.0 - po) * p + po * r, nr = (1.0 - ro) * p + ro * r;
+            p = np; r = nr;
+        }
+    }
+    double a1 = __shfl_up_sync(0xffffffffu, p, 1);   // e_0 P = (1 - p, p) of the product of the earlier chunks
+    if (lane == 0) a1 = 0.0;
+    for (int f = f_lo; f < f_hi; ++f) {
+        const double p2 = q0[(int64_t)f * C], r2 = q1[(int64_t)f * C];
+        a1 = (1.0 - a1) * p2 + a1 * r2;
+        a_out[u0 + (int64_t)f * C] = 1.0 - a1;
+        a_out[a.U + u0 + (int64_t)f * C] = a1;
     }
 }
 
@@ -425,63 +483,82 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_weights_kernel(const LocalArg
 
 // backward recursion: gradients of the unconstrained z_trans, the chain's ELBO terms and the expected
 // initial-state / transition counts of this (AOI, channel) -> hpartial[(ni * C + c)][NHACC]
-//   Delta_f = V_f(1) - V_f(0) + [rho_{f+1}(1) - rho_{f+1}(0)] + [q_{f+1}(1|1) - q_{f+1}(1|0)] Delta_{f+1},
-//   rho_f(z') = sum_z q_f(z|z') R_f(z', z),   R_f = log p_f - log q_f,
-//   d ELBO / d u_f(z', 1) = a_{f-1}(z') q_f(1|z') q_f(0|z') [ R_f(z',1) - R_f(z',0) + Delta_f ] = - d / d u_f(z', 0)
+//   Delta_f = V_f(1) - V_f(0) + [rho_{f+1}(1) - rho_{f+1}(0)] + [q_{f+1}(1|1) - q_{f+1}(1|0)] Delta_{f+1}
+//           = c_f + kappa_f Delta_{f+1}                                  (an affine map per frame: scanned right to left)
+//   d ELBO / d u_f(z', 1) = a_{f-1}(z') q_f(1|z') q_f(0|z') [ rd_f(z') + Delta_f ] = - d / d u_f(z', 0)
 template <typename T>
-__global__ void hmm_backward_kernel(const LocalArgs<T> a, double* __restrict__ hpartial) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kLocalBlock) hmm_backward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
+                                                                  double* __restrict__ hpartial) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int C = a.v.C, F = a.v.F;
-    if (t >= a.v.nb * C) return;
-    const int ni = t / C, c = t - ni * C;
+    if (chain >= a.v.nb * C) return;
+    const int ni = chain / C, c = chain - ni * C;
     const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
     const double mu = a.v.mask[n] ? 1.0 : 0.0;
-    const int ot = a.v.is_ontarget[n] ? 1 : 0;
-    const ChannelTables<double>& ct = a.tables->ch[c];
+    const bool ot = a.v.is_ontarget[n] != 0;
+    int f_lo, f_hi;
+    chain_chunk(F, lane, f_lo, f_hi);
+    const int64_t u0 = ((int64_t)ni * F) * C + c;
+    auto row = [&](int j, int f) { return rows[(int64_t)j * a.U + u0 + (int64_t)f * C]; };
+    auto c_of = [&](int f) {   // c_f and kappa_f
+        const int64_t u = u0 + (int64_t)f * C;
+        double cf = (double)a.hmm_v[a.U + u] - (double)a.hmm_v[u], kf = 0.0;
+        if (f + 1 < F) { cf += row(ROW_RHO1, f + 1) - row(ROW_RHO0, f + 1); kf = row(ROW_Q1, f + 1) - row(ROW_Q0, f + 1); }
+        return make_double2(cf, kf);
+    };
+    // this chunk as one map  Delta_first = A + B Delta_(first frame of the next chunk)
+    double A = 0.0, B = 1.0;
+    for (int f = f_hi - 1; f >= f_lo; --f) {
+        const double2 ck = c_of(f);
+        A = ck.x + ck.y * A;
+        B = ck.y * B;
+    }
+    // inclusive suffix scan: G_l = map_l o map_{l+1} o ... o map_31; beyond the last frame Delta = 0, so Delta at the
+    // first frame of chunk l is the constant part of G_l
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ao = __shfl_down_sync(0xffffffffu, A, o), Bo = __shfl_down_sync(0xffffffffu, B, o);
+        if (lane + o < 32) { A = A + B * Ao; B = B * Bo; }
+    }
+    double delta_next = __shfl_down_sync(0xffffffffu, A, 1);
+    if (lane == 31) delta_next = 0.0;
     double acc[NHACC];
 #pragma unroll
     for (int i = 0; i < NHACC; ++i) acc[i] = 0.0;
-    double carry = 0.0;   // [rho_{f+1}(1) - rho_{f+1}(0)] + [q_{f+1}(1|1) - q_{f+1}(1|0)] Delta_{f+1}
-    const double scale = -a.sN * mu;   // loss = -ELBO; all frames: no frame scale
-    for (int f = F - 1; f >= 0; --f) {
-        const int64_t u = ((int64_t)ni * F + f) * C + c;
-        const int64_t iz = a.hmm_ztrans(n, f, c);
-        const ChainRow r0 = chain_row((double)a.lparams[iz + 0], (double)a.lparams[iz + 1], a.mc);
-        const ChainRow r1 = chain_row((double)a.lparams[iz + 2], (double)a.lparams[iz + 3], a.mc);
-        const double delta = ((double)a.hmm_v[a.U + u] - (double)a.hmm_v[u]) + carry;
+    const double scale = -a.sN * mu;   // loss = -ELBO; every frame is used: no frame scale
+    for (int f = f_hi - 1; f >= f_lo; --f) {
+        const double2 ck = c_of(f);
+        const double delta = ck.x + ck.y * delta_next;
+        delta_next = delta;
+        const int64_t u = u0 + (int64_t)f * C;
         double ap0 = 1.0, ap1 = 0.0;   // a_{f-1}
         if (f > 0) { ap0 = a.hmm_a[u - C]; ap1 = a.hmm_a[a.U + u - C]; }
-        // log p_f(z | z'): the initial distribution at f = 0 (only row z' = 0 carries weight), else the transition matrix
-        double R0[kZ], R1[kZ];
-#pragma unroll
-        for (int z = 0; z < kZ; ++z) {
-            R0[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][0][z]) - r0.lq[z];
-            R1[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][1][z]) - r1.lq[z];
-        }
-        const double g0 = ap0 * r0.q[1] * r0.q[0] * (R0[1] - R0[0] + delta);
-        const double g1 = ap1 * r1.q[1] * r1.q[0] * (R1[1] - R1[0] + delta);
+        const double q01 = row(ROW_Q0, f), q11 = row(ROW_Q1, f);
+        const double g0 = ap0 * q01 * (1.0 - q01) * (row(ROW_RD0, f) + delta);
+        const double g1 = ap1 * q11 * (1.0 - q11) * (row(ROW_RD1, f) + delta);
+        const int64_t iz = a.hmm_ztrans(n, f, c);
         a.lgrads[iz + 0] = (T)(-scale * g0);
         a.lgrads[iz + 1] = (T)(scale * g0);
         a.lgrads[iz + 2] = (T)(-scale * g1);
         a.lgrads[iz + 3] = (T)(scale * g1);
-        const double rho0 = r0.q[0] * R0[0] + r0.q[1] * R0[1], rho1 = r1.q[0] * R1[0] + r1.q[1] * R1[1];
-        acc[HACC_ELBO] += ap0 * rho0 + ap1 * rho1;
+        acc[HACC_ELBO] += ap0 * row(ROW_RHO0, f) + ap1 * row(ROW_RHO1, f);
         if (ot) {
             if (f == 0) {
-#pragma unroll
-                for (int z = 0; z < kZ; ++z) acc[HACC_INIT + z] += ap0 * r0.q[z];
+                acc[HACC_INIT + 0] += ap0 * (1.0 - q01);
+                acc[HACC_INIT + 1] += ap0 * q01;
             } else {
-#pragma unroll
-                for (int z = 0; z < kZ; ++z) {
-                    acc[HACC_TRANS + z] += ap0 * r0.q[z];
-                    acc[HACC_TRANS + kZ + z] += ap1 * r1.q[z];
-                }
+                acc[HACC_TRANS + 0] += ap0 * (1.0 - q01);
+                acc[HACC_TRANS + 1] += ap0 * q01;
+                acc[HACC_TRANS + kZ + 0] += ap1 * (1.0 - q11);
+                acc[HACC_TRANS + kZ + 1] += ap1 * q11;
             }
         }
-        carry = (rho1 - rho0) + (r1.q[1] - r0.q[1]) * delta;
     }
 #pragma unroll
-    for (int i = 0; i < NHACC; ++i) hpartial[(int64_t)t * NHACC + i] = mu * acc[i];
+    for (int i = 0; i < NHACC; ++i) {
+        const double v = warp_sum(acc[i]);   // fixed shuffle order: deterministic
+        if (lane == 0) hpartial[(int64_t)chain * NHACC + i] = mu * v;
+    }
 }
 
 // hacc[c][i] = sum over the minibatch AOIs, in index order (one thread per value: a few hundred terms)
@@ -761,15 +838,17 @@ extern "C" int tq_cosmos_local_post(int dtype, const tq_patch_view* view, int64_
 
 // ---- hmm variant: host side ---------------------------------------------------------------------------------------------------
 template <typename T>
-static int run_hmm_forward(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, double* a_out,
-                           void* qm, cudaStream_t st) {
+static int run_hmm_forward(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                           double* rows, double* a_out, void* qm, cudaStream_t st) {
     LocalArgs<T> a{};
-    fill_common(a, view, Nt, mc, lparams, nullptr, 0, 0, nullptr);
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
     a.hmm_a = a_out;
     a.qm = (T*)qm;
     if (a.U == 0) return TQ_OK;
     const int chains = view->nb * view->C;
-    hmm_forward_kernel<T><<<(chains + 63) / 64, 64, 0, st>>>(a, a_out);
+    hmm_rows_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a, rows);
+    TQ_LAUNCH_CHECK("hmm_rows_kernel launch");
+    hmm_forward_kernel<T><<<(chains * 32 + kLocalBlock - 1) / kLocalBlock, kLocalBlock, 0, st>>>(a, rows, a_out);
     TQ_LAUNCH_CHECK("hmm_forward_kernel launch");
     hmm_weights_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a);
     TQ_LAUNCH_CHECK("hmm_weights_kernel launch");
@@ -790,14 +869,17 @@ extern "C" int64_t tq_hmm_local_numel(int64_t Nt, int64_t F, int64_t C) {
 }
 extern "C" int tq_hmm_chain_sums(void) { return NHACC; }
 
+extern "C" int tq_hmm_chain_rows(void) { return NROW; }
+
 extern "C" int tq_hmm_forward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
-                              double* a_out, void* qm, void* stream) {
+                              const void* tables, double* rows, double* a_out, void* qm, void* stream) {
     int stv = hmm_check_view(view);
     if (stv != TQ_OK) return stv;
-    TQ_CHECK_ARG(mc && lparams && a_out && qm, "NULL pointer");
+    TQ_CHECK_ARG(mc && lparams && tables && rows && a_out && qm, "NULL pointer");
+    TQ_CHECK_ARG(view->is_ontarget, "view needs is_ontarget");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_hmm_forward<float>(view, Nt, (const ModelConst*)mc, lparams, a_out, qm, st);
-    if (dtype == TQ_F64) return run_hmm_forward<double>(view, Nt, (const ModelConst*)mc, lparams, a_out, qm, st);
+    if (dtype == TQ_F32) return run_hmm_forward<float>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_out, qm, st);
+    if (dtype == TQ_F64) return run_hmm_forward<double>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_out, qm, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }
@@ -847,7 +929,8 @@ extern "C" int tq_hmm_local_post(int dtype, const tq_patch_view* view, int64_t N
 
 template <typename T>
 static int run_hmm_backward(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
-                            const double* a_in, const void* v_in, double sN, void* lgrads, double* hpartial, double* hacc, cudaStream_t st) {
+                            const double* rows, const double* a_in, const void* v_in, double sN, void* lgrads, double* hpartial,
+                            double* hacc, cudaStream_t st) {
     LocalArgs<T> a{};
     fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
     a.sN = sN; a.sF = 1.0;
@@ -856,7 +939,7 @@ static int run_hmm_backward(const tq_patch_view* view, int64_t Nt, const ModelCo
     a.hmm_v = (T*)v_in;
     const int chains = view->nb * view->C;
     if (chains > 0 && a.U > 0) {
-        hmm_backward_kernel<T><<<(chains + 63) / 64, 64, 0, st>>>(a, hpartial);
+        hmm_backward_kernel<T><<<(chains * 32 + kLocalBlock - 1) / kLocalBlock, kLocalBlock, 0, st>>>(a, rows, hpartial);
         TQ_LAUNCH_CHECK("hmm_backward_kernel launch");
     }
     hmm_reduce_kernel<<<1, 64, 0, st>>>(hpartial, a.U > 0 ? view->nb : 0, view->C, hacc);
@@ -865,15 +948,15 @@ static int run_hmm_backward(const tq_patch_view* view, int64_t Nt, const ModelCo
 }
 
 extern "C" int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
-                               const void* tables, const double* a_in, const void* v_in, double sN, void* lgrads,
-                               double* hpartial, double* hacc, void* stream) {
+                               const void* tables, const double* rows, const double* a_in, const void* v_in, double sN,
+                               void* lgrads, double* hpartial, double* hacc, void* stream) {
     int stv = hmm_check_view(view);
     if (stv != TQ_OK) return stv;
-    TQ_CHECK_ARG(mc && lparams && tables && a_in && v_in && lgrads && hpartial && hacc, "NULL pointer");
+    TQ_CHECK_ARG(mc && lparams && tables && rows && a_in && v_in && lgrads && hpartial && hacc, "NULL pointer");
     TQ_CHECK_ARG(view->mask && view->is_ontarget, "view needs mask and is_ontarget");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_hmm_backward<float>(view, Nt, (const ModelConst*)mc, lparams, tables, a_in, v_in, sN, lgrads, hpartial, hacc, st);
-    if (dtype == TQ_F64) return run_hmm_backward<double>(view, Nt, (const ModelConst*)mc, lparams, tables, a_in, v_in, sN, lgrads, hpartial, hacc, st);
+    if (dtype == TQ_F32) return run_hmm_backward<float>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_in, v_in, sN, lgrads, hpartial, hacc, st);
+    if (dtype == TQ_F64) return run_hmm_backward<double>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_in, v_in, sN, lgrads, hpartial, hacc, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }

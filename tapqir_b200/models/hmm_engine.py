@@ -36,6 +36,7 @@ class HmmEngine(CosmosEngine):
             return
         dev = self.device
         self.chain_a = torch.empty(2, self.U, dtype=torch.float64, device=dev)
+        self.chain_rows = torch.empty(self.lib.tq_hmm_chain_rows(), self.U, dtype=torch.float64, device=dev)
         self.chain_v = torch.empty(2, self.U, dtype=self.dtype, device=dev)
         self.hpartial = torch.empty(max(self.nb * self.C, 1) * self.nh, dtype=torch.float64, device=dev)
 
@@ -83,9 +84,9 @@ class HmmEngine(CosmosEngine):
             _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
                                            p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
                        "tq_cosmos_sites")
-            _lib.check(lib.tq_hmm_forward(code, view, self.Nt, mc, p(self.lparams), p(self.chain_a), p(self.qm), st),
-                       "tq_hmm_forward")
-            main.wait_event(self._ev_join0)
+            main.wait_event(self._ev_join0)   # the chain's per-frame terms need the sampled init / trans tables
+            _lib.check(lib.tq_hmm_forward(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.chain_rows),
+                                          p(self.chain_a), p(self.qm), st), "tq_hmm_forward")
             S, G, K = self.samples, self.gs, L.K
             if time_likelihood is not None:
                 time_likelihood[0].record()
@@ -99,8 +100,9 @@ class HmmEngine(CosmosEngine):
                                              p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), p(self.chain_a), self.sN,
                                              p(self.lgrads), p(self.chain_v), p(self.tickets), p(self.block_partial), p(self.acc),
                                              st), "tq_hmm_local_post")
-            _lib.check(lib.tq_hmm_backward(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.chain_a),
-                                           p(self.chain_v), self.sN, p(self.lgrads), p(self.hpartial), p(self.hacc), st),
+            _lib.check(lib.tq_hmm_backward(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.chain_rows),
+                                           p(self.chain_a), p(self.chain_v), self.sN, p(self.lgrads), p(self.hpartial),
+                                           p(self.hacc), st),
                        "tq_hmm_backward")
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
@@ -136,10 +138,12 @@ class HmmEngine(CosmosEngine):
                               mask=self.store.mask)
         U = self.Nt * self.F * self.C
         a = torch.empty(2, U, dtype=torch.float64, device=self.device)
+        rows = torch.empty(lib.tq_hmm_chain_rows(), U, dtype=torch.float64, device=self.device)
         qm = torch.empty(4, U, dtype=self.dtype, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(lib.tq_hmm_forward(self.code, view, self.Nt, ctypes.byref(self.mc), p(self.lparams), p(a), p(qm),
-                                          _lib.stream_ptr(self.device)), "tq_hmm_forward")
+            # (the forward marginals use the guide's rows only; the tables enter the other per-frame terms)
+            _lib.check(lib.tq_hmm_forward(self.code, view, self.Nt, ctypes.byref(self.mc), p(self.lparams), p(self.tables),
+                                          p(rows), p(a), p(qm), _lib.stream_ptr(self.device)), "tq_hmm_forward")
         return a.view(2, self.Nt, self.F, self.C).permute(1, 2, 3, 0).contiguous()
 
     def compute_probs(self, *args, **kwargs):

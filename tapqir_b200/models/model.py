@@ -252,9 +252,10 @@ class Model:
     def optim_state(self):
         """``pyro.optim.Adam.get_state()`` layout [third party]: {param name: torch Adam state_dict}."""
         eng = self.engine
-        moments = dict(eng.ll.views(eng.lm))
+        local_named = getattr(eng.ll, "named", eng.ll.views)   # reference names / shapes (hmm: m_probs is stacked)
+        moments = dict(local_named(eng.lm))
         moments.update(eng.gl.views(eng.gm))
-        second = dict(eng.ll.views(eng.lv))
+        second = dict(local_named(eng.lv))
         second.update(eng.gl.views(eng.gv))
         step = torch.tensor(float(eng.iteration))
         group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": eng.adam_eps, "weight_decay": 0, "amsgrad": False,
@@ -284,8 +285,12 @@ class Model:
             self._rolling = defaultdict(lambda: deque([], maxlen=100), checkpoint["rolling"])
             self.iter = checkpoint["iter"]
             opt = checkpoint["optimizer"]
-            for views, key in ((dict(eng.ll.views(eng.lm), **eng.gl.views(eng.gm)), "exp_avg"),
-                               (dict(eng.ll.views(eng.lv), **eng.gl.views(eng.gv)), "exp_avg_sq")):
+            for lflat, gflat, key in ((eng.lm, eng.gm, "exp_avg"), (eng.lv, eng.gv, "exp_avg_sq")):
+                if hasattr(eng.ll, "load_named"):
+                    eng.ll.load_named(lflat, {k: opt[k]["state"][0][key] for k in opt})
+                    views = eng.gl.views(gflat)
+                else:
+                    views = dict(eng.ll.views(lflat), **eng.gl.views(gflat))
                 for k, v in views.items():
                     v.copy_(opt[k]["state"][0][key].to(device=self.device, dtype=eng.dtype).reshape(v.shape))
             steps = [int(opt[k]["state"][0]["step"]) for k in opt]

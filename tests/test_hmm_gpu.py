@@ -66,3 +66,34 @@ def test_hmm_z_probs_match_oracle_and_default_step_runs():
     losses = [eng.step().item() for _ in range(5)]
     assert all(torch.isfinite(torch.tensor(losses)))
     assert eng.iteration == 5
+
+
+def test_hmm_model_api_fit_checkpoint_resume(tmp_path):
+    """`tapqir fit --model cosmos+hmm` surface: registry key, parameter names / shapes (hmm.py:419-467), posterior
+    properties, checkpoint written and resumed."""
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+
+    data = simulate(3, 8, C=1, P=14, seed=0)
+    save(data, tmp_path)
+    model = models["cosmos+hmm"](device="cuda", dtype="float")
+    model.load(tmp_path)
+    model.init(lr=0.005, nbatch_size=3)
+    model.run(1, progress_bar=lambda it: it)   # the checkpoint of iteration 0 holds the parameters after this step
+    assert model.iter == 1 and model.iter_loss == model.iter_loss
+    ckpt = torch.load(tmp_path / ".tapqir" / "cosmos+hmm_model.tpqr", weights_only=False)
+    p = ckpt["params"]["params"]
+    assert p["m_probs"].shape == (2, 2, 3, 8, 1) and p["z_trans"].shape == (3, 8, 1, 2, 2)
+    assert p["init_mean"].shape == (1, 2) and p["trans_mean"].shape == (1, 2, 2) and p["trans_size"].shape == (1, 2, 1)
+    assert "pi_mean" not in p and set(ckpt["optimizer"]) == set(p)
+    zp = model.z_probs
+    assert zp.shape == (3, 8, 1, 2) and torch.allclose(zp.sum(-1), torch.ones(3, 8, 1), atol=1e-6)
+    assert model.m_probs.shape == (2, 3, 8, 1) and model.z_map.shape == (3, 8, 1)
+    again = models["cosmos+hmm"](device="cuda", dtype="float")
+    again.load(tmp_path)
+    again.init(lr=0.005, nbatch_size=3)
+    assert again.iter == ckpt["iter"]
+    a, b = model.engine.named_unconstrained(), again.engine.named_unconstrained()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(model.engine.lm, again.engine.lm) and torch.equal(model.engine.gv, again.engine.gv)
