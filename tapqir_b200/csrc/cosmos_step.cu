@@ -416,24 +416,27 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_rows_kernel(const LocalArgs<T
     }
 }
 
-// frames of lane `lane` of a warp-per-chain scan
-__device__ __forceinline__ void chain_chunk(int F, int lane, int& f_lo, int& f_hi) {
-    const int L = (F + 31) / 32;
-    f_lo = lane * L < F ? lane * L : F;
-    f_hi = (lane + 1) * L < F ? (lane + 1) * L : F;
+// One BLOCK of kChainThreads threads per chain: thread t takes frames [t L, (t+1) L), L = ceil(F / kChainThreads);
+// chunk maps are scanned inside each warp with shuffles and across the warps through shared memory.
+constexpr int kChainThreads = 128;
+constexpr int kChainWarps = kChainThreads / 32;
+__device__ __forceinline__ void chain_chunk(int F, int t, int& f_lo, int& f_hi) {
+    const int L = (F + kChainThreads - 1) / kChainThreads;
+    f_lo = t * L < F ? t * L : F;
+    f_hi = (t + 1) * L < F ? (t + 1) * L : F;
 }
 
 // forward marginals a_f(z): a_f = a_{f-1} T_f, T_f = [[1-p, p], [1-r, r]], a_{-1} = e_0 (row 0 of z_trans is the
 // initial distribution, hmm.py:355-359).  Products of row-stochastic 2x2 matrices stay row-stochastic: (p, r) suffice.
 template <typename T>
-__global__ void __launch_bounds__(kLocalBlock) hmm_forward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
-                                                                 double* __restrict__ a_out) {
-    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kChainThreads) hmm_forward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
+                                                                    double* __restrict__ a_out) {
+    __shared__ double wp[kChainWarps], wr[kChainWarps];
+    const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = a.v.C, F = a.v.F;
-    if (chain >= a.v.nb * C) return;
     const int ni = chain / C, c = chain - ni * C;
     int f_lo, f_hi;
-    chain_chunk(F, lane, f_lo, f_hi);
+    chain_chunk(F, threadIdx.x, f_lo, f_hi);
     const int64_t u0 = ((int64_t)ni * F) * C + c;
     const double* q0 = rows + (int64_t)ROW_Q0 * a.U + u0;
     const double* q1 = rows + (int64_t)ROW_Q1 * a.U + u0;
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_forward_kernel(const LocalArg
         const double np = (1.0 - p) * p2 + p * r2, nr = (1.0 - r) * p2 + r * r2;
         p = np; r = nr;
     }
-    // inclusive scan of the chunk products (earlier chunks multiply from the left), then shift to exclusive
+    // inclusive scan of the chunk products inside the warp (earlier chunks multiply from the left)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const double po = __shfl_up_sync(0xffffffffu, p, o), ro = __shfl_up_sync(0xffffffffu, r, o);
@@ -452,8 +455,15 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_forward_kernel(const LocalArg
             p = np; r = nr;
         }
     }
-    double a1 = __shfl_up_sync(0xffffffffu, p, 1);   // e_0 P = (1 - p, p) of the product of the earlier chunks
-    if (lane == 0) a1 = 0.0;
+    if (lane == 31) { wp[warp] = p; wr[warp] = r; }
+    // exclusive within the warp: product of the earlier lanes
+    double ep = __shfl_up_sync(0xffffffffu, p, 1), er = __shfl_up_sync(0xffffffffu, r, 1);
+    if (lane == 0) { ep = 0.0; er = 1.0; }
+    __syncthreads();
+    // e_0 (earlier warps' product) (earlier lanes' product): only the probability of state 1 is needed
+    double a1 = 0.0;   // e_0 -> state 1 with probability 0
+    for (int w = 0; w < warp; ++w) a1 = (1.0 - a1) * wp[w] + a1 * wr[w];
+    a1 = (1.0 - a1) * ep + a1 * er;
     for (int f = f_lo; f < f_hi; ++f) {
         const double p2 = q0[(int64_t)f * C], r2 = q1[(int64_t)f * C];
         a1 = (1.0 - a1) * p2 + a1 * r2;
@@ -487,17 +497,17 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_weights_kernel(const LocalArg
 //           = c_f + kappa_f Delta_{f+1}                                  (an affine map per frame: scanned right to left)
 //   d ELBO / d u_f(z', 1) = a_{f-1}(z') q_f(1|z') q_f(0|z') [ rd_f(z') + Delta_f ] = - d / d u_f(z', 0)
 template <typename T>
-__global__ void __launch_bounds__(kLocalBlock) hmm_backward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
-                                                                  double* __restrict__ hpartial) {
-    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kChainThreads) hmm_backward_kernel(const LocalArgs<T> a, const double* __restrict__ rows,
+                                                                     double* __restrict__ hpartial) {
+    __shared__ double wA[kChainWarps], wB[kChainWarps], wacc[kChainWarps][NHACC];
+    const int chain = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = a.v.C, F = a.v.F;
-    if (chain >= a.v.nb * C) return;
     const int ni = chain / C, c = chain - ni * C;
     const int64_t n = a.v.ndx ? a.v.ndx[ni] : ni;
     const double mu = a.v.mask[n] ? 1.0 : 0.0;
     const bool ot = a.v.is_ontarget[n] != 0;
     int f_lo, f_hi;
-    chain_chunk(F, lane, f_lo, f_hi);
+    chain_chunk(F, threadIdx.x, f_lo, f_hi);
     const int64_t u0 = ((int64_t)ni * F) * C + c;
     auto row = [&](int j, int f) { return rows[(int64_t)j * a.U + u0 + (int64_t)f * C]; };
     auto c_of = [&](int f) {   // c_f and kappa_f
@@ -513,15 +523,21 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_backward_kernel(const LocalAr
         A = ck.x + ck.y * A;
         B = ck.y * B;
     }
-    // inclusive suffix scan: G_l = map_l o map_{l+1} o ... o map_31; beyond the last frame Delta = 0, so Delta at the
-    // first frame of chunk l is the constant part of G_l
+    // inclusive suffix scan inside the warp: G_l = map_l o map_{l+1} o ... o map_31
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const double Ao = __shfl_down_sync(0xffffffffu, A, o), Bo = __shfl_down_sync(0xffffffffu, B, o);
         if (lane + o < 32) { A = A + B * Ao; B = B * Bo; }
     }
-    double delta_next = __shfl_down_sync(0xffffffffu, A, 1);
-    if (lane == 31) delta_next = 0.0;
+    if (lane == 0) { wA[warp] = A; wB[warp] = B; }
+    double eA = __shfl_down_sync(0xffffffffu, A, 1), eB = __shfl_down_sync(0xffffffffu, B, 1);   // later lanes of this warp
+    if (lane == 31) { eA = 0.0; eB = 1.0; }
+    __syncthreads();
+    // Delta at the first frame after this thread's chunk: later warps applied to Delta = 0 beyond the last frame, then the
+    // later lanes of this warp
+    double later = 0.0;
+    for (int w = kChainWarps - 1; w > warp; --w) later = wA[w] + wB[w] * later;
+    double delta_next = eA + eB * later;
     double acc[NHACC];
 #pragma unroll
     for (int i = 0; i < NHACC; ++i) acc[i] = 0.0;
@@ -557,18 +573,28 @@ __global__ void __launch_bounds__(kLocalBlock) hmm_backward_kernel(const LocalAr
 #pragma unroll
     for (int i = 0; i < NHACC; ++i) {
         const double v = warp_sum(acc[i]);   // fixed shuffle order: deterministic
-        if (lane == 0) hpartial[(int64_t)chain * NHACC + i] = mu * v;
+        if (lane == 0) wacc[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NHACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kChainWarps; ++w) v += wacc[w][threadIdx.x];
+        hpartial[(int64_t)chain * NHACC + threadIdx.x] = mu * v;
     }
 }
 
-// hacc[c][i] = sum over the minibatch AOIs, in index order (one thread per value: a few hundred terms)
-__global__ void hmm_reduce_kernel(const double* __restrict__ hpartial, int nb, int C, double* __restrict__ hacc) {
-    const int t = threadIdx.x;
-    if (blockIdx.x != 0 || t >= C * NHACC) return;
-    const int c = t / NHACC, i = t - c * NHACC;
-    double s = 0.0;
-    for (int ni = 0; ni < nb; ++ni) s += hpartial[((int64_t)ni * C + c) * NHACC + i];
-    hacc[t] = s;
+// hacc[c][i] = sum over the minibatch AOIs: one warp per value, lanes stride over the AOIs, fixed combination order
+__global__ void __launch_bounds__(256) hmm_reduce_kernel(const double* __restrict__ hpartial, int nb, int C, double* __restrict__ hacc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x != 0) return;
+    for (int t = warp; t < C * NHACC; t += 8) {
+        const int c = t / NHACC, i = t - c * NHACC;
+        double s = 0.0;
+        for (int ni = lane; ni < nb; ni += 32) s += hpartial[((int64_t)ni * C + c) * NHACC + i];
+        s = warp_sum(s);
+        if (lane == 0) hacc[t] = s;
+    }
 }
 
 // ---- z / theta posterior of one particle, accumulated into the running means (row N1) ---------------------
@@ -848,7 +874,7 @@ static int run_hmm_forward(const tq_patch_view* view, int64_t Nt, const ModelCon
     const int chains = view->nb * view->C;
     hmm_rows_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a, rows);
     TQ_LAUNCH_CHECK("hmm_rows_kernel launch");
-    hmm_forward_kernel<T><<<(chains * 32 + kLocalBlock - 1) / kLocalBlock, kLocalBlock, 0, st>>>(a, rows, a_out);
+    hmm_forward_kernel<T><<<chains, kChainThreads, 0, st>>>(a, rows, a_out);
     TQ_LAUNCH_CHECK("hmm_forward_kernel launch");
     hmm_weights_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a);
     TQ_LAUNCH_CHECK("hmm_weights_kernel launch");
@@ -939,10 +965,10 @@ static int run_hmm_backward(const tq_patch_view* view, int64_t Nt, const ModelCo
     a.hmm_v = (T*)v_in;
     const int chains = view->nb * view->C;
     if (chains > 0 && a.U > 0) {
-        hmm_backward_kernel<T><<<(chains * 32 + kLocalBlock - 1) / kLocalBlock, kLocalBlock, 0, st>>>(a, rows, hpartial);
+        hmm_backward_kernel<T><<<chains, kChainThreads, 0, st>>>(a, rows, hpartial);
         TQ_LAUNCH_CHECK("hmm_backward_kernel launch");
     }
-    hmm_reduce_kernel<<<1, 64, 0, st>>>(hpartial, a.U > 0 ? view->nb : 0, view->C, hacc);
+    hmm_reduce_kernel<<<1, 256, 0, st>>>(hpartial, a.U > 0 ? view->nb : 0, view->C, hacc);
     TQ_LAUNCH_CHECK("hmm_reduce_kernel launch");
     return TQ_OK;
 }
