@@ -697,24 +697,43 @@ __global__ void globals_finish_kernel(int Q, bool hmm, ModelConst mc, const doub
 // ---- dense Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) --------------------------------------
 // models/model.py:168-171: pyro.optim.Adam({"lr", "betas": [0.9, 0.999]}) on every unconstrained tensor,
 // dense over the whole tensor.  `state->step` is the number of completed steps.
+template <typename T> struct alignas(4 * sizeof(T)) Vec4 { T x, y, z, w; };
+
 template <typename T>
-__global__ void adam_kernel(int64_t n, T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
-                            T* __restrict__ v, double lr, double b1, double b2, double eps,
-                            const StepState* __restrict__ state) {
+__device__ __forceinline__ void adam_update(T& p, T g, T& m, T& v, T step_size, T inv_sqrt_bc2, T tb1, T tb2, T teps) {
+    m = m + (g - m) * (T(1) - tb1);              // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * tb2 + (T(1) - tb2) * g * g;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    const T denom = Real<T>::sqrt(v) * inv_sqrt_bc2 + teps;
+    p = p - step_size * (m / denom);
+}
+
+// 28 B of HBM traffic per element (p, g, m, v read; p, m, v written): four elements per thread through 16-byte
+// (float) / 32-byte (double) accesses, scalar tail
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) adam_kernel(int64_t n, T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
+                                                   T* __restrict__ v, double lr, double b1, double b2, double eps,
+                                                   const StepState* __restrict__ state) {
     const double t = (double)(state->step + 1ull);
     const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
     const T step_size = (T)(lr / bc1);
     const T inv_sqrt_bc2 = (T)(1.0 / sqrt(bc2));
     const T tb1 = (T)b1, tb2 = (T)b2, teps = (T)eps;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const T gi = g[i];
-        const T mi = m[i] + (gi - m[i]) * (T(1) - tb1);          // exp_avg.lerp_(grad, 1 - beta1)
-        const T vi = v[i] * tb2 + (T(1) - tb2) * gi * gi;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-        m[i] = mi;
-        v[i] = vi;
-        const T denom = Real<T>::sqrt(vi) * inv_sqrt_bc2 + teps;
-        p[i] = p[i] - step_size * (mi / denom);
+    const int64_t n4 = VEC ? n / 4 : 0;
+    Vec4<T>* p4 = reinterpret_cast<Vec4<T>*>(p);
+    const Vec4<T>* g4 = reinterpret_cast<const Vec4<T>*>(g);
+    Vec4<T>* m4 = reinterpret_cast<Vec4<T>*>(m);
+    Vec4<T>* v4 = reinterpret_cast<Vec4<T>*>(v);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec4<T> pi = p4[i], mi = m4[i], vi = v4[i];
+        const Vec4<T> gi = g4[i];
+        adam_update(pi.x, gi.x, mi.x, vi.x, step_size, inv_sqrt_bc2, tb1, tb2, teps);
+        adam_update(pi.y, gi.y, mi.y, vi.y, step_size, inv_sqrt_bc2, tb1, tb2, teps);
+        adam_update(pi.z, gi.z, mi.z, vi.z, step_size, inv_sqrt_bc2, tb1, tb2, teps);
+        adam_update(pi.w, gi.w, mi.w, vi.w, step_size, inv_sqrt_bc2, tb1, tb2, teps);
+        p4[i] = pi; m4[i] = mi; v4[i] = vi;
     }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        adam_update(p[i], g[i], m[i], v[i], step_size, inv_sqrt_bc2, tb1, tb2, teps);
 }
 
 __global__ void step_advance_kernel(StepState* state) {
@@ -1087,14 +1106,21 @@ extern "C" int tq_adam_dense(int dtype, int64_t n, void* params, const void* gra
     TQ_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int block = 256;
-    int64_t grid = (n + block - 1) / block;
+    int64_t grid = (n / 4 + block - 1) / block;
+    if (grid < 1) grid = 1;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
-    if (dtype == TQ_F32)
-        adam_kernel<float><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
-    else if (dtype == TQ_F64)
-        adam_kernel<double><<<(int)grid, block, 0, st>>>(n, (double*)params, (const double*)grads, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
-    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    // the four-wide path needs 16-byte (float) / 32-byte (double) aligned buffers; anything else takes the scalar path
+    const size_t esz = dtype == TQ_F64 ? 8 : 4;
+    const bool vec = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % (4 * esz)) == 0;
+    if (!vec) { grid = (n + block - 1) / block; if (grid > cap) grid = cap; }
+    if (dtype == TQ_F32) {
+        if (vec) adam_kernel<float, true><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+        else adam_kernel<float, false><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+    } else if (dtype == TQ_F64) {
+        if (vec) adam_kernel<double, true><<<(int)grid, block, 0, st>>>(n, (double*)params, (const double*)grads, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+        else adam_kernel<double, false><<<(int)grid, block, 0, st>>>(n, (double*)params, (const double*)grads, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
+    } else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("adam_kernel launch");
     return TQ_OK;
 }
