@@ -161,7 +161,9 @@ def make_shard(workload, rank, device):
     from tapqir_b200.utils.simulate import simulate
 
     n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
-    ds = simulate(n_aoi, n_frames, C=WORKLOAD_CHANNELS.get(workload, 1), P=14, seed=rank, device=device, aoi_chunk=50)
+    kinetic = {"kon": 0.2, "koff": 0.2} if WORKLOAD_MODEL.get(workload) == "cosmos+hmm" else None   # test_tapqir.py:31-33
+    ds = simulate(n_aoi, n_frames, C=WORKLOAD_CHANNELS.get(workload, 1), P=14, seed=rank, device=device, aoi_chunk=50,
+                  params=kinetic)
     return ds, nb, fb, desc
 
 

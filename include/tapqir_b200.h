@@ -223,6 +223,11 @@ int tq_hmm_local_post(int dtype, const tq_patch_view* view, int64_t Nt, const vo
                       const void* L, const void* gs, const void* g_rate, const double* a_in, double sN,
                       void* lgrads, void* v_out, double* tickets, double* block_partial, double* acc,
                       void* stream);
+/* theta_probs (K, nb, F, C) += weight * p(theta = k+1 | z_map, m, x, y) averaged over m with q(m | z_map), for one guide
+ * draw (samples of tq_cosmos_sites, tables of tq_hmm_globals_sample); z_map: (nb, F, C) uint8 (hmm.py:541-625). */
+int tq_hmm_theta_probs(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                       const void* lparams, const void* tables, const void* samples, const void* z_map,
+                       double weight, void* theta_probs, void* stream);
 int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
                     const void* lparams, const void* tables, const double* rows, const double* a_in,
                     const void* v_in, double sN, void* lgrads, double* hpartial, double* hacc,

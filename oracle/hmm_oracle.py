@@ -245,3 +245,46 @@ def z_probs(unconstrained, data: O.OracleData):
         a = (a[..., :, None] * zt[:, f]).sum(-2)
         out.append(a)
     return torch.stack(out, 1)                                                          # (Nt,F,C,1+S)
+
+
+@torch.no_grad()
+def theta_probs(unconstrained, data: O.OracleData, ndx, noises, z_map, priors=DEFAULT_PRIORS, K=2, S=1):
+    """
+    hmm.py:541-625: for every particle, p(theta | z = z_MAP, m, x, y) -- the model's theta / m / x / y log-probs with the
+    chain state fixed, normalised over theta (the chain's own terms cancel there) -- averaged over m with the guide's
+    q(m | z_MAP), then over the particles.  Returns (K, nb, F, C).  ``z_map``: (nb, F, C) long.
+    """
+    dt, P = data.dtype, data.P
+    nb, F, C = len(ndx), data.F, data.C
+    half = (P + 1) / 2
+    p = to_constrained(unconstrained, P, dt)
+    loc = _gather_local(p, ndx)
+    g = guide_dists(p, loc, P, priors)
+    t = lambda v: torch.as_tensor(v, dtype=dt)
+    mcfg = O.m_configs(K, dt)
+    M = mcfg.shape[0]
+    mp = torch.gather(loc["m_probs"], 0, z_map[None, None].expand(1, K, nb, F, C))[0]           # (K,nb,F,C): m_probs[z_MAP]
+    logq_mk = D.Categorical(probs=torch.stack([1 - mp, mp], -1), validate_args=False).logits      # (K,nb,F,C,2)
+    q_m = sum(logq_mk[k][..., mcfg[:, k].long()] for k in range(K)).exp()                      # (nb,F,C,M)
+    logp_theta = D.Categorical(probs=O.probs_theta(K, dt), validate_args=False).logits[z_map.clamp(0, 1)]   # (nb,F,C,1+K)
+    out = torch.zeros(K, nb, F, C, dtype=dt)
+    for noise in noises:
+        lamda = O.rsample_gamma(*g["lamda"], noise["lamda"])
+        proximity = O.rsample_affine_beta(g["proximity"], noise["proximity"])
+        size = torch.stack([torch.full_like(proximity, 2.0), ((P + 1) / (2 * proximity)) ** 2 - 1], -1)
+        x = O.rsample_affine_beta(g["x"], noise["x"])
+        y = O.rsample_affine_beta(g["y"], noise["y"])
+        pm = O.probs_m(lamda, K)
+        logp_mk = D.Categorical(probs=torch.stack([1 - pm, pm], -1), validate_args=False).logits      # (Q,1+K,K,2)
+        xy_prior = [O.AffineBeta(t(0.0), size[s], -half, half) for s in range(2)]
+        logp_xy = torch.stack([d.log_prob(x) + d.log_prob(y) for d in xy_prior])                    # (2,K,nb,F,C)
+        terms = []
+        for th in range(K + 1):
+            term = logp_theta[..., th][..., None] + torch.zeros(nb, F, C, M, dtype=dt)
+            for k in range(K):
+                mk = mcfg[:, k]
+                term = term + logp_mk[:, th, k][:, mk.long()][None, None] + mk * logp_xy[int(th == k + 1), k][..., None]
+            terms.append(term)
+        post = torch.softmax(torch.stack(terms), 0)                                                 # (1+K,nb,F,C,M)
+        out += (q_m * post[1:]).sum(-1) / len(noises)
+    return out

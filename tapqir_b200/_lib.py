@@ -68,6 +68,7 @@ SIGNATURES = {
     "tq_hmm_forward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tq_hmm_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double,
                                   _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tq_hmm_theta_probs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP]),
     "tq_hmm_backward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP, _VP]),
     "tq_crop_aois": (c_int, [_VP, c_int, c_int, c_int, c_int, _VP, _VP, c_int, c_int, c_int, _VP, _VP, _VP, _VP]),
     "tq_offset_hist": (c_int, [_VP, c_int, c_int, c_int, c_int, c_int, c_int, _VP, _VP]),

@@ -191,6 +191,57 @@ TQ_HD void unit_post_hmm(const F (&rec)[NREC], const F (&sample)[NSAMP], const F
     }
 }
 
+// ---- posterior of theta for one guide draw, given the chain state (hmm.py:541-625, "next" row N1 for hmm) --------------
+// p(theta | z, m, x, y) from the model's theta / m / x / y log-probs, averaged over m with the guide weights q(m | z):
+// pth[k] = that probability at theta = k + 1.  (Terms that do not depend on theta -- the chain's p(z_f | z_{f-1}) -- cancel
+// in the normalisation over theta, which is why only z itself is needed.)
+template <typename F>
+TQ_HD void unit_theta_given_z(const F (&x_)[kK], const F (&y_)[kK], const F (&u_mp)[kK], int z, const ModelConst& mc,
+                              const GlobalTables<F>& gt, int c, F (&pth)[kK]) {
+    using R = Real<F>;
+    const ChannelTables<F>& ct = gt.ch[c];
+    const F half = F(mc.P + 1) / F(2);
+    const F cs1 = gt.size1 * F(0.5) - F(1);
+    F q1[kK], q0[kK], lxy1[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const SpotPresence<F> sp(u_mp[k], mc);
+        q1[k] = sp.q1; q0[k] = sp.q0;
+        const F tx = x_[k] / half, ty = y_[k] / half;
+        lxy1[k] = cs1 * (R::log1p(-tx * tx) + R::log1p(-ty * ty)) + gt.cxy1;
+        pth[k] = F(0);
+    }
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        F lj[kTheta];
+        F mx = -R::inf();
+#pragma unroll
+        for (int th = 0; th < kTheta; ++th) {
+            F v = ct.logptheta[z][th];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                const int mk = (m >> k) & 1;
+                v += ct.logpm[th][k][mk];
+                if (mk) v += (th == k + 1) ? lxy1[k] : gt.lxy0;
+            }
+            lj[th] = v;
+            mx = R::max(mx, v);
+        }
+        F se = F(0);
+#pragma unroll
+        for (int th = 0; th < kTheta; ++th) {
+            lj[th] = R::exp(lj[th] - mx);
+            se += lj[th];
+        }
+        F q = F(1);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) q *= ((m >> k) & 1) ? q1[k] : q0[k];
+        const F qi = q / se;
+#pragma unroll
+        for (int k = 0; k < kK; ++k) pth[k] += qi * lj[k + 1];
+    }
+}
+
 // ---- the guide's chain ---------------------------------------------------------------------------------------------------
 // Row z' of one frame's transition table: q(z | z') = clamp(softmax(u[z'][:])) and its log (Categorical(probs).logits,
 // hmm.py:355-364 with torch's probs clamp).

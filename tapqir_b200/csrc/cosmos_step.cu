@@ -584,6 +584,29 @@ __global__ void __launch_bounds__(kChainThreads) hmm_backward_kernel(const Local
     }
 }
 
+// theta posterior of one particle given the MAP chain state, accumulated into the running mean (hmm.py:541-625)
+template <typename T>
+__global__ void __launch_bounds__(kLocalBlock) hmm_theta_kernel(const LocalArgs<T> a, const uint8_t* __restrict__ z_map, T weight,
+                                                               T* __restrict__ theta_probs) {
+    __shared__ GlobalTables<T> gt;
+    if (threadIdx.x == 0) gt.convert_from(*a.tables);
+    __syncthreads();
+    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
+    if (u32 >= (uint32_t)a.U) return;
+    const UnitIndex ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+    const int z = z_map[u32] ? 1 : 0;
+    T x[kK], y[kK], u_mp[kK], pth[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        x[k] = a.samples[(int64_t)(S_X + k) * a.U + u32];
+        y[k] = a.samples[(int64_t)(S_Y + k) * a.U + u32];
+        u_mp[k] = z ? a.lparams[a.hmm_mprobs1(k, ui.aoi, ui.fi, ui.c)] : a.lparams[a.lo.index(LP_M_PROBS + k, ui.aoi, ui.fi, ui.c)];
+    }
+    unit_theta_given_z<T>(x, y, u_mp, z, a.mc, gt, ui.c, pth);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) theta_probs[(int64_t)k * a.U + u32] += weight * pth[k];
+}
+
 // hacc[c][i] = sum over the minibatch AOIs: one warp per value, lanes stride over the AOIs, fixed combination order
 __global__ void __launch_bounds__(256) hmm_reduce_kernel(const double* __restrict__ hpartial, int nb, int C, double* __restrict__ hacc) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1002,6 +1025,31 @@ extern "C" int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt,
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TQ_F32) return run_hmm_backward<float>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_in, v_in, sN, lgrads, hpartial, hacc, st);
     if (dtype == TQ_F64) return run_hmm_backward<double>(view, Nt, (const ModelConst*)mc, lparams, tables, rows, a_in, v_in, sN, lgrads, hpartial, hacc, st);
+    set_error("bad dtype %d", dtype);
+    return TQ_ERR_ARG;
+}
+
+template <typename T>
+static int run_hmm_theta(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
+                         const void* samples, const void* z_map, double weight, void* theta_probs, cudaStream_t st) {
+    LocalArgs<T> a{};
+    fill_common(a, view, Nt, mc, lparams, tables, 0, 0, nullptr);
+    a.samples = (T*)samples;
+    if (a.U == 0) return TQ_OK;
+    hmm_theta_kernel<T><<<local_blocks(a.U), kLocalBlock, 0, st>>>(a, (const uint8_t*)z_map, (T)weight, (T*)theta_probs);
+    TQ_LAUNCH_CHECK("hmm_theta_kernel launch");
+    return TQ_OK;
+}
+
+extern "C" int tq_hmm_theta_probs(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                  const void* tables, const void* samples, const void* z_map, double weight,
+                                  void* theta_probs, void* stream) {
+    int stv = hmm_check_view(view);
+    if (stv != TQ_OK) return stv;
+    TQ_CHECK_ARG(mc && lparams && tables && samples && z_map && theta_probs, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TQ_F32) return run_hmm_theta<float>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, z_map, weight, theta_probs, st);
+    if (dtype == TQ_F64) return run_hmm_theta<double>(view, Nt, (const ModelConst*)mc, lparams, tables, samples, z_map, weight, theta_probs, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
 }

@@ -7,7 +7,7 @@ ELBO that Pyro's ``TraceEnum_ELBO`` / ``TraceMarkovEnum_ELBO`` assembles for the
 evaluated by :class:`tapqir_b200.models.hmm_engine.HmmEngine` (csrc/cosmos_hmm.cuh): forward marginals of the guide's
 chain, the cosmos likelihood kernel with weights sum_z a_f(z) q_f(m|z), per-state emission terms, a backward recursion
 for the gradients of ``z_trans``.  Built: the SVI step, ``z_probs`` / ``z_map`` / ``m_probs`` / ``pspecific``,
-checkpoints.  Not built yet: ``theta_probs`` (hmm.py:541-625, 5-particle funsor trace) and ``z_sample``.
+``theta_probs`` (5 guide particles given ``z_MAP``), checkpoints.  Not built yet: ``z_sample``.
 """
 
 from collections import OrderedDict
@@ -109,7 +109,18 @@ class hmm(cosmos):
 
     @property
     def theta_probs(self) -> torch.Tensor:
-        raise NotImplementedError("theta_probs of the hmm variant (hmm.py:541-625) is not built yet")
+        r"""Posterior target-specific spot probability :math:`q(\theta = k, z=z_\mathsf{MAP})` from 5 guide particles for
+        the on-target AOIs (hmm.py:541-625, 639-644): ``(K, Nt, F, Q)``; off-target AOIs stay 0.  Cached."""
+        if getattr(self, "_theta_probs", None) is None:
+            eng, data = self.engine, self.data
+            ont = data.is_ontarget[self._shard()]
+            n_on = int(ont.sum().item())
+            assert bool(ont[:n_on].all()), "on-target AOIs must come first (as written by glimpse/simulate)"
+            out = torch.zeros(self.K, eng.Nt, data.F, self.Q, dtype=eng.dtype)
+            if n_on:
+                out[:, :n_on] = eng.compute_theta_probs(self.z_map[:n_on], aoi_count=n_on, particles=5).cpu()
+            self._theta_probs = out
+        return self._theta_probs
 
     @property
     def m_probs(self) -> torch.Tensor:

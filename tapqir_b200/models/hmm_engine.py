@@ -146,5 +146,41 @@ class HmmEngine(CosmosEngine):
                                           p(rows), p(a), p(qm), _lib.stream_ptr(self.device)), "tq_hmm_forward")
         return a.view(2, self.Nt, self.F, self.C).permute(1, 2, 3, 0).contiguous()
 
+    @torch.no_grad()
+    def compute_theta_probs(self, z_map, aoi_count=None, particles=5, local_noise=None, global_noise=None, seed_offset=1 << 40):
+        """
+        theta_probs (K, n, F, C) for local AOIs [0, aoi_count): ``q(theta = k | z = z_MAP)`` averaged over ``particles``
+        guide draws (reference: hmm.py:541-625, 5 particles).  ``z_map``: (n, F, C) integer / bool CUDA tensor.
+        ``local_noise`` / ``global_noise`` (lists, one per particle) replay given draws for the parity test.
+        """
+        lib, code, p = self.lib, self.code, _lib.ptr
+        mc = ctypes.byref(self.mc)
+        dev, dtype = self.device, self.dtype
+        n = self.Nt if aoi_count is None else int(aoi_count)
+        ndx = torch.arange(n, dtype=torch.int32, device=dev)
+        U = n * self.F * self.C
+        s = self.store
+        view = _lib.make_view(s.pixels, s.xy, s.offset_samples, s.offset_logits, nb=n, fb=self.F, C=self.C, F=self.F, P=self.P,
+                              ndx=ndx, fdx=None, is_ontarget=s.is_ontarget, mask=s.mask)
+        samples = torch.empty(L.NSAMP, U, dtype=dtype, device=dev)
+        qm = torch.empty(4, U, dtype=dtype, device=dev)
+        rec = torch.empty(lib.tq_site_record_rows(), U, dtype=dtype, device=dev)
+        theta_probs = torch.zeros(L.K, n, self.F, self.C, dtype=dtype, device=dev)
+        zm = z_map.to(device=dev, dtype=torch.uint8).contiguous()
+        assert zm.numel() == U
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            for i in range(particles):
+                pstate = torch.tensor([seed_offset + i], dtype=torch.int64, device=dev)
+                gn = None if global_noise is None else global_noise[i]
+                ln = None if local_noise is None else local_noise[i]
+                _lib.check(lib.tq_hmm_globals_sample(code, self.C, p(self.gparams), mc, p(gn), self.seed, p(pstate),
+                                                     p(self.gstate), p(self.tables), p(self.gain), st), "tq_hmm_globals_sample")
+                _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                               p(pstate), p(ln), p(samples), p(qm), p(rec), st), "tq_cosmos_sites")
+                _lib.check(lib.tq_hmm_theta_probs(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(samples), p(zm),
+                                                  1.0 / particles, p(theta_probs), st), "tq_hmm_theta_probs")
+        return theta_probs
+
     def compute_probs(self, *args, **kwargs):
-        raise NotImplementedError("theta_probs of the hmm variant (hmm.py:541-625) is not built yet")
+        raise NotImplementedError("use z_probs() and compute_theta_probs() for the hmm variant")

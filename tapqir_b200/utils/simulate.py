@@ -41,7 +41,8 @@ def simulate(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0,
     """
     Draw a dataset of ``N`` AOIs (half on-target) x ``F`` frames x ``C`` channels of PxP patches.
 
-    ``offset_samples / offset_weights`` default to the reference's three equal bins at
+    ``params`` with ``"kon"`` and ``"koff"`` selects the kinetic (hidden-Markov) recipe for ``z`` instead of the
+    time-independent ``"pi"`` one.  ``offset_samples / offset_weights`` default to the reference's three equal bins at
     ``params["offset"]`` (simulate.py:92,103); pass a histogram for the secondary realism runs.
     Images are returned on the CPU as float32 with integer values (simulate.py:122 floors them).
     """
@@ -75,7 +76,19 @@ def simulate(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0,
         n = hi - lo
         ont = is_ontarget[lo:hi].to(dev)[:, None, None]
         u = lambda *s: torch.rand(*s, generator=gen, **f64)
-        z = (u(n, F, C) < prm["pi"]) & ont
+        if "kon" in prm and "koff" in prm:
+            # kinetic simulation (simulate.py:66-90): two-state Markov chain with init = stationary distribution
+            # [koff, kon] / (kon + koff) and trans = [[1 - kon, kon], [koff, 1 - koff]]
+            kon, koff = float(prm["kon"]), float(prm["koff"])
+            draws = u(n, F, C)
+            z = torch.zeros(n, F, C, dtype=torch.bool, device=dev)
+            z[:, 0] = draws[:, 0] < kon / (kon + koff)
+            for f in range(1, F):
+                p_on = torch.where(z[:, f - 1], torch.full((), 1.0 - koff, **f64), torch.full((), kon, **f64))
+                z[:, f] = draws[:, f] < p_on
+            z = z & ont
+        else:
+            z = (u(n, F, C) < prm["pi"]) & ont
         theta = torch.where(z, 1 + torch.floor(u(n, F, C) * K).clamp(max=K - 1).long(), torch.zeros((), dtype=torch.long, device=dev))
         image = torch.full((n, F, C, P, P), float(prm["background"]), **f64)
         cdx = torch.arange(C, device=dev)[None, None, :].expand(n, F, C)

@@ -89,6 +89,8 @@ def test_hmm_model_api_fit_checkpoint_resume(tmp_path):
     zp = model.z_probs
     assert zp.shape == (3, 8, 1, 2) and torch.allclose(zp.sum(-1), torch.ones(3, 8, 1), atol=1e-6)
     assert model.m_probs.shape == (2, 3, 8, 1) and model.z_map.shape == (3, 8, 1)
+    th = model.theta_probs
+    assert th.shape == (2, 3, 8, 1) and bool((th >= 0).all()) and bool((th.sum(0) <= 1 + 1e-5).all())
     again = models["cosmos+hmm"](device="cuda", dtype="float")
     again.load(tmp_path)
     again.init(lr=0.005, nbatch_size=3)
@@ -97,3 +99,23 @@ def test_hmm_model_api_fit_checkpoint_resume(tmp_path):
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert torch.equal(model.engine.lm, again.engine.lm) and torch.equal(model.engine.gv, again.engine.gv)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)])
+def test_hmm_theta_probs_match_oracle(dtype, tol):
+    """theta_probs given z_MAP (hmm.py:541-625) for 3 replayed guide particles."""
+    ds, data, params, _, g = make_problem(N=4, F=7, C=1, nb=4, seed=8)
+    if dtype == torch.float32:
+        params = {k: v.float().double() for k, v in params.items()}
+    ndx = torch.arange(3)
+    noises = [H.draw_noise(params, data, ndx, g) for _ in range(3)]
+    if dtype == torch.float32:
+        noises = [{k: v.float().double() for k, v in n.items()} for n in noises]
+    z_map = H.z_probs(params, data)[ndx].argmax(-1)
+    ref = H.theta_probs(params, data, ndx, noises, z_map)
+    eng = make_engine(ds, data, params, 4, dtype)
+    out = eng.compute_theta_probs(z_map.cuda(), aoi_count=3, particles=3,
+                                  local_noise=[L.pack_local_noise(n, dtype, "cuda") for n in noises],
+                                  global_noise=[eng.gl.pack_noise(n).cuda() for n in noises])
+    assert out.shape == (2, 3, 7, 1)
+    assert (out.cpu().double() - ref).abs().max().item() < tol
