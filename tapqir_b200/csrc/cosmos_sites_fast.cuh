@@ -71,10 +71,16 @@ TQ_HD Lp1 lp1_parts(float u, float r) {
     return o;
 }
 
-// Stirling remainders for z >= 10 from iz = 1/z:
+// Stirling remainders for z >= 6 from iz = 1/z (next terms: 5e-12 / 1e-11 at z = 6):
 //   lgamma(z) = (z - 1/2) ln z - z + ln(2 pi)/2 + r(z),   psi(z) = ln z - q(z)
-TQ_HD float stirling_r(float iz) { const float z2 = iz * iz; return iz * (0.0833333333f - z2 * (0.00277777778f - z2 * 0.000793650794f)); }
-TQ_HD float stirling_q(float iz) { const float z2 = iz * iz; return iz * (0.5f + iz * (0.0833333333f - z2 * (0.00833333333f - z2 * 0.00396825397f))); }
+TQ_HD float stirling_r(float iz) {
+    const float z2 = iz * iz;
+    return iz * (0.0833333333f - z2 * (0.00277777778f - z2 * (0.000793650794f - z2 * (0.000595238095f - z2 * 0.000841750842f))));
+}
+TQ_HD float stirling_q(float iz) {
+    const float z2 = iz * iz;
+    return iz * (0.5f + iz * (0.0833333333f - z2 * (0.00833333333f - z2 * (0.00396825397f - z2 * (0.00416666667f - z2 * 0.00757575758f)))));
+}
 
 // lgamma(x) and digamma(x) in fp32 for x > 0: Stirling series for x >= 8, below that the recurrence shifted
 // by 8 with the eight reciprocals folded into two divisions and the eight factors into one logarithm
@@ -145,6 +151,29 @@ TQ_HD void gamma_grad_rice(float alpha, float ia, float u, const Lp1& p, float& 
     const float inner = p.A - H * ia;                             // l/u - H/alpha - 1
     sgg_m1u = (1.0f + u) * (st + inner + st * inner);             // (1+u)(1+st)(1+inner) - (1+u)
     sgg = (1.0f + u) + sgg_m1u;
+}
+
+// ATen's Beta reparameterisation gradient (tq_math.cuh::beta_grad) in fp32 with y = 1 - x supplied by the caller (formed
+// in double: for the small concentrations this is used with, draws pile up against 0 and 1).  Plain formulas: with
+// total <= 64 nothing in them is large enough to cancel.
+TQ_HD bool beta_grad_f32(float x, float y, float alpha, float total, float& g) {
+    const float beta = total - alpha;
+    const float boundary = total * x * y;
+    // the power series of the two small-x regimes alternate with terms ~ (beta x)^i / i!: fine in fp32 while beta x < 2
+    // (measured: 4e-6 at 2, 1e-5 at 2.5, 3e-5 at 3.5), double beyond
+    if (x <= 0.5f && boundary < 2.5f) {
+        if (!(beta * x < 2.0f)) return false;
+        g = beta_grad_alpha_small<float>(x, alpha, beta);
+        return true;
+    }
+    if (x >= 0.5f && boundary < 0.75f) {
+        if (!(alpha * y < 2.0f)) return false;
+        g = -beta_grad_beta_small<float>(y, beta, alpha);
+        return true;
+    }
+    if (alpha > 6.0f && beta > 6.0f) return false;   // Rice expansion outside the reformulated regime: double
+    g = beta_grad<float>(x, alpha, total);           // rational correction (no 1 - x inside)
+    return true;
 }
 
 // Numerator polynomial of the Taylor patch of ATen's Beta gradient around x = mean
@@ -249,16 +278,37 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
     const float m1 = site_rcp(1.0f + e), m0 = e * m1;
     const float sz = expf(u1), S = 2.0f + sz;                     // size - 2 = d size / d u, size
     const float c1 = S * m1, c0 = S * m0;
-    if (!(c1 > 10.0f && c0 > 10.0f)) return SITE_FALLBACK_DRAW;
     if (use_rng) {
-        const double g1 = (double)sample_std_gamma_f32(*rng, c1), g2 = (double)sample_std_gamma_f32(*rng, c0);
+        const double g1 = sample_std_gamma_f32(*rng, c1), g2 = sample_std_gamma_f32(*rng, c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
     const double x01d = variate;   // (v - low) / scale of the reference, to rounding
     const float ua = (float)fma(x01d, ed, x01d - 1.0);            // (x - m1) / m1
     const float x = (float)x01d, y = (float)(1.0 - x01d);
-    const float ie = site_rcp(e), ub = -ua * ie;                                     // -(x - m1) / m0
-    if (!(S * x * y >= 2.5f) || !(ua > -1.0f) || !(ub > -1.0f)) return SITE_FALLBACK;
+    const float ie = site_rcp(e), ub = -ua * ie;                  // -(x - m1) / m0
+    if (!(c1 > 6.0f && c0 > 6.0f && S * x * y >= 2.5f && ua > -1.0f && ub > -1.0f)) {
+        // ---- small concentrations (absent spots: the guide relaxes towards the flat prior), or a draw in the far tail:
+        // the textbook formulas in fp32 -- nothing large enough to cancel while total <= 64
+        if (!(S <= 64.0f) || !(x > 1e-30f) || !(y > 1e-30f)) return SITE_FALLBACK;
+        float lgt, pt, lg1, p1, lg0, p0;
+        lgamma_digamma_f32(S, lgt, pt);
+        lgamma_digamma_f32(c1, lg1, p1);
+        lgamma_digamma_f32(c0, lg0, p0);
+        const float lx = logf(x), ly = logf(y);
+        const float d_c1 = lx + pt - p1, d_c0 = ly + pt - p0;
+        float bg1, bg0;
+        if (!beta_grad_f32(x, y, c1, S, bg1) || !beta_grad_f32(y, x, c0, S, bg0)) return SITE_FALLBACK;
+        const float dv_dc1 = scale * y * bg1, dv_dc0 = -scale * x * bg0;
+        const float km = S * m1 * m0, k1 = m1 * sz, k0 = m0 * sz;
+        sample = (float)(lod + (hid - lod) * variate);
+        rec[SO_LQ] = (c1 - 1.0f) * lx + (c0 - 1.0f) * ly + lgt - lg1 - lg0 - logf(scale);
+        rec[SO_DQ] = ((c1 - 1.0f) * site_rcp(x) - (c0 - 1.0f) * site_rcp(y)) * site_rcp(scale);
+        rec[SO_A0] = (dv_dc1 - dv_dc0) * km;
+        rec[SO_B0] = (d_c1 - d_c0) * km;
+        rec[SO_A1] = dv_dc1 * k1 + dv_dc0 * k0;
+        rec[SO_B1] = d_c1 * k1 + d_c0 * k0;
+        return SITE_DONE;
+    }
     const float d = ua * m1;                                      // x - m1
     const Lp1 pa = lp1_parts(ua, x * (1.0f + e)), pb = lp1_parts(ub, y * (1.0f + ie));
     const float it = site_rcp(S), i1 = it * (1.0f + e), i0 = it * (1.0f + ie);

@@ -140,9 +140,22 @@ __device__ __forceinline__ SiteInputs<T> site_gather(const LocalArgs<T>& a, int 
     return in;
 }
 
+// The reference clamps a sample into its support with the margins of ITS dtype (double: tiny for Gamma.rsample,
+// eps * scale for pyro's AffineBeta.rsample).  Stored as float those margins round away -- the sample would sit exactly
+// ON the bound (height 0, x = -(P+1)/2) and the model's log-densities there are infinite -- so the float sample gets the
+// float-sized margin.  Only samples that were on the clamp anyway are touched.
+template <typename T>
+__device__ __forceinline__ T sample_into_support(int s, T v, const ModelConst& mc) {
+    if (sizeof(T) != sizeof(float)) return v;
+    if (site_is_gamma(s)) return v > T(1.17549435e-38f) ? v : T(1.17549435e-38f);
+    const T lo = s < S_X ? (T)mc.width_min : T(-0.5) * T(mc.P + 1), hi = s < S_X ? (T)mc.width_max : T(0.5) * T(mc.P + 1);
+    const T margin = (hi - lo) * T(1.1920929e-7f);
+    return v < lo + margin ? lo + margin : (v > hi - margin ? hi - margin : v);
+}
+
 template <typename T>
 __device__ __forceinline__ void site_scatter(const LocalArgs<T>& a, int s, int64_t u, T v, const T* rec, const T* extra) {
-    a.samples[(int64_t)s * a.U + u] = v;
+    a.samples[(int64_t)s * a.U + u] = sample_into_support(s, v, a.mc);
 #pragma unroll
     for (int j = 0; j < NSO; ++j) a.rec[((int64_t)s * NSO + j) * a.U + u] = rec[j];
     if (s == S_B) {
@@ -205,18 +218,29 @@ __global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<
     if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
 }
 
-constexpr int kFallbackUPT = 4;   // markers checked per thread: the kernel almost always finds none
+// A block scans kFallbackUPT * 128 markers of one site, compacts the hits into shared memory and then works through
+// them with dense warps: a trained model leaves the fp32 forms at a percent or so of its sites (draws in the far tail,
+// Rice expansion at small concentrations), and scattered over the warps every one of them would drag 31 idle lanes
+// through the ~3000-instruction double form.
+constexpr int kFallbackUPT = 16;
 __global__ void __launch_bounds__(kLocalBlock) site_fallback_kernel(const LocalArgs<float> a) {
+    __shared__ uint32_t hits[kLocalBlock * kFallbackUPT];
+    __shared__ unsigned int n_hits;
     const int s = blockIdx.y;
-    const uint32_t u0 = (blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x) * kFallbackUPT;
+    if (threadIdx.x == 0) n_hits = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * (uint32_t)(kLocalBlock * kFallbackUPT);
     const float* marker = a.rec + ((int64_t)s * NSO + SO_LQ) * a.U;
-#pragma unroll 1
+#pragma unroll 4
     for (int j = 0; j < kFallbackUPT; ++j) {
-        const uint32_t u32 = u0 + j;
-        if (u32 >= (uint32_t)a.U) return;
-        const float m = marker[u32];
-        if (m != m) site_double(a, s, u32);
+        const uint32_t u32 = base + j * kLocalBlock + threadIdx.x;
+        if (u32 < (uint32_t)a.U) {
+            const float m = marker[u32];
+            if (m != m) hits[atomicAdd(&n_hits, 1u)] = u32;
+        }
     }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < n_hits; i += kLocalBlock) site_double(a, s, hits[i]);
 }
 
 // ---- post: blocks per (AOI, channel) chunk of frames, kPostUPT units per thread; the cross-unit sums are fused in ----

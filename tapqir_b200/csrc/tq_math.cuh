@@ -470,7 +470,11 @@ struct Philox {
 
 // fp32 inline variant of the sampler below for the per-site kernels: inlining keeps the Philox state
 // in registers (the out-of-line generic version takes it by reference, i.e. through local memory).
-TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
+// Returns a double: the Marsaglia-Tsang core runs in fp32 (its value d*v is O(alpha)), but the alpha < 1 boost
+// u^(1/alpha) spans hundreds of orders of magnitude and is applied in double -- in fp32 it underflows to an exact 0 with
+// probability ~(1e-38)^alpha, which puts the guide sample ON its clamp (seen after ~3000 SVI iterations on absent spots,
+// whose Beta concentrations drift below 1: x = -7.5 exactly -> log1p(-1) = -inf downstream).
+TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
 #ifdef __CUDA_ARCH__
     // MUFU forms: the accept/reject comparison tolerates their ~1e-6 absolute error (a borderline trial
     // flips with probability ~1e-6; the accepted value d*v itself is exact arithmetic)
@@ -480,9 +484,9 @@ TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
 #define TQ_SLOG(x) logf(x)
 #define TQ_SRSQRT(x) (1.0f / sqrtf(x))
 #endif
-    float scale = 1.0f;
+    double scale = 1.0;
     if (alpha < 1.0f) {
-        scale = powf((float)rng.uniform_d(), 1.0f / alpha);
+        scale = pow(rng.uniform_d(), 1.0 / (double)alpha);
         alpha += 1.0f;
     }
     const float d = alpha - 1.0f / 3.0f;
@@ -496,10 +500,10 @@ TQ_HD float sample_std_gamma_f32(Philox& rng, float alpha) {
         const float v = yv * yv * yv;
         const float u = rng.uniform();
         const float xx = xn * xn;
-        if (u < 1.0f - 0.0331f * xx * xx) return scale * d * v;
-        if (TQ_SLOG(u) < 0.5f * xx + d * (1.0f - v + TQ_SLOG(v))) return scale * d * v;
+        if (u < 1.0f - 0.0331f * xx * xx) return scale * (double)(d * v);
+        if (TQ_SLOG(u) < 0.5f * xx + d * (1.0f - v + TQ_SLOG(v))) return scale * (double)(d * v);
     }
-    return scale * d;
+    return scale * (double)d;
 #undef TQ_SLOG
 #undef TQ_SRSQRT
 }

@@ -331,6 +331,13 @@ int hc_site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const Mod
     for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
     return status;
 }
+// status of the production form for one RNG-mode evaluation (profiles/fallback_probe.py)
+int hc_site_status_rng(int s, float u0, float u1, float ubm, float ubs, const ModelConst* mc, uint64_t seed) {
+    Philox rng(seed, 11ull, ((uint64_t)(s + 1) << 8));
+    double variate = 0.0;
+    float rec[NSO], ex[NEX], v = 0.0f;
+    return site_eval_fast(s, u0, u1, ubm, ubs, *mc, true, &rng, variate, v, rec, ex);
+}
 // RNG-mode draws through the production form (falls back like site_kernel<float>)
 void hc_site_draws_fast(int s, float u0, float u1, const ModelConst* mc, uint64_t seed, int n, double* out) {
     for (int i = 0; i < n; ++i) {
