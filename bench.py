@@ -199,6 +199,8 @@ def run_native(args):
         torch.cuda.synchronize(device)
 
     dbg('model ready')
+    for _ in range(args.train_iters):
+        model.step()
     for _ in range(max(args.warmup, 3)):
         model.step()
     barrier()
@@ -312,7 +314,7 @@ def run_native(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "model": model.name, "channels": eng.C, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
-                       "offset_bins_distinct": o_exec,
+                       "offset_bins_distinct": o_exec, "train_iters_before_timing": args.train_iters,
                        "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
                        "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
@@ -401,6 +403,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-iters", type=int, default=0,
+                    help="untimed SVI iterations before the warm-up: times the TRAINED state (absent spots' guides relax to "
+                         "small concentrations, a few percent of the sites leave the fp32 forms) instead of the initial point")
     ap.add_argument("--keep-offset-bins", action="store_true",
                     help="do not merge the simulator's three identical offset bins (exercises the O = 3 kernels)")
     args = ap.parse_args()

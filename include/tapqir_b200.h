@@ -149,6 +149,15 @@ int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void
                     const void* lparams, int64_t aoi_offset, uint64_t seed, const void* state,
                     const void* noise_in, void* samples, void* qm, void* rec, void* stream);
 
+/* The same with a workspace for the sites that leave the fp32 production forms (a percent or so of a trained model's):
+ * worklist: 9 * U 32-bit slots of device scratch -- it may alias any buffer that is only written LATER in the step, e.g.
+ * the likelihood kernel's gradient output --, work_count: one 32-bit device counter.  Those sites are then redone in
+ * double by dense warps instead of block by block.  (dtype double ignores the workspace.) */
+int tq_cosmos_sites_ws(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                       const void* lparams, int64_t aoi_offset, uint64_t seed, const void* state,
+                       const void* noise_in, void* samples, void* qm, void* rec, void* worklist,
+                       void* work_count, void* stream);
+
 /* Priors, (z, theta) log-sum-exp, q(m)-weighted ELBO summand and its reverse mode per unit
  * (TraceEnum_ELBO [third party] on cosmos.py:216-327).  Inputs: the buffers above plus L (4, U),
  * gs (9, U) and g_rate (U,) from tq_ksmogn_fwd_bwd with W = qm.  sN = Nt_total / nb_total and

@@ -52,6 +52,8 @@ SIGNATURES = {
     "tq_site_record_rows": (c_int, []),
     "tq_cosmos_sites": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,
                                  _VP, _VP]),
+    "tq_cosmos_sites_ws": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,
+                                 _VP, _VP, _VP, _VP]),
     "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                       c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_zprobs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP]),

@@ -153,26 +153,83 @@ TQ_HD void gamma_grad_rice(float alpha, float ia, float u, const Lp1& p, float& 
     sgg = (1.0f + u) + sgg_m1u;
 }
 
-// ATen's Beta reparameterisation gradient (tq_math.cuh::beta_grad) in fp32 with y = 1 - x supplied by the caller (formed
-// in double: for the small concentrations this is used with, draws pile up against 0 and 1).  Plain formulas: with
-// total <= 64 nothing in them is large enough to cancel.
-TQ_HD bool beta_grad_f32(float x, float y, float alpha, float total, float& g) {
+// ATen's Beta reparameterisation gradient (tq_math.cuh::beta_grad: same regimes, series and coefficient tables) in
+// fp32 for SMALL concentrations (total <= 64: nothing in the plain formulas is large enough to cancel), with what the
+// caller already has passed in instead of recomputed: y = 1 - x (formed in double: draws pile up against 0 and 1 at
+// these concentrations), lx = ln x, ly = ln y, and the digammas psi(alpha), psi(total).  Returns false where fp32 is
+// not enough (caller: double form).
+TQ_HD bool beta_grad_f32(float x, float y, float lx, float ly, float alpha, float total, float psi_a, float psi_t, float& g) {
     const float beta = total - alpha;
     const float boundary = total * x * y;
-    // the power series of the two small-x regimes alternate with terms ~ (beta x)^i / i!: fine in fp32 while beta x < 2
-    // (measured: 4e-6 at 2, 1e-5 at 2.5, 3e-5 at 3.5), double beyond
     if (x <= 0.5f && boundary < 2.5f) {
+        // power series in x around 0; terms alternate with size ~ (beta x)^i / i!: fine in fp32 while beta x < 2
+        // (measured: 4e-6 at 2, 1e-5 at 2.5, 3e-5 at 3.5)
         if (!(beta * x < 2.0f)) return false;
-        g = beta_grad_alpha_small<float>(x, alpha, beta);
+        const float factor = psi_a - psi_t - lx;
+        float numer = 1.0f, id = site_rcp(alpha);
+        float series = id * (factor + id);
+#pragma unroll
+        for (int i = 1; i <= 10; ++i) {
+            numer *= (float(i) - beta) * x * (1.0f / float(i));
+            id = site_rcp(alpha + float(i));
+            series = fmaf(numer * id, factor + id, series);
+        }
+        const float res = x * expf(-beta * ly) * series;           // x (1 - x)^(-beta) series
+        g = (res != res) ? 0.0f : res;
         return true;
     }
     if (x >= 0.5f && boundary < 0.75f) {
+        // the mirrored series in y = 1 - x
         if (!(alpha * y < 2.0f)) return false;
-        g = -beta_grad_beta_small<float>(y, beta, alpha);
+        const float factor = psi_t - psi_a;
+        float numer = 1.0f, betas = 1.0f, dbetas = 0.0f, series = factor * site_rcp(beta);
+#pragma unroll
+        for (int i = 1; i <= 8; ++i) {
+            numer *= -y * (1.0f / float(i));
+            dbetas = dbetas * (alpha - float(i)) + betas;
+            betas = betas * (alpha - float(i));
+            series = fmaf(numer * site_rcp(beta + float(i)), dbetas + factor * betas, series);
+        }
+        const float res = expf((1.0f - alpha) * lx) * series;      // -(-(1 - y)^(1 - alpha) series)
+        g = (res != res) ? 0.0f : res;
         return true;
     }
     if (alpha > 6.0f && beta > 6.0f) return false;   // Rice expansion outside the reformulated regime: double
-    g = beta_grad<float>(x, alpha, total);           // rational correction (no 1 - x inside)
+    // rational correction to an analytic approximation (coefficients: torch Distributions.h, as in tq_math.cuh)
+    const float c[2][3][3][4] = {
+        {{{1.003668233f, -0.01061107488f, -0.0657888334f, 0.01201642863f},
+          {0.6336835991f, -0.3557432599f, 0.05486251648f, -0.001465281033f},
+          {-0.03276231906f, 0.004474107445f, 0.002429354597f, -0.0001557569013f}},
+         {{0.221950385f, -0.3187676331f, 0.01799915743f, 0.01074823814f},
+          {-0.2951249643f, 0.06219954479f, 0.01535556598f, 0.001550077057f},
+          {0.02155310298f, 0.004170831599f, 0.001292462449f, 6.976601077e-05f}},
+         {{-0.05980841433f, 0.008441916499f, 0.01085618172f, 0.002319392565f},
+          {0.02911413504f, 0.01400243777f, -0.002721828457f, 0.000751041181f},
+          {0.005900514878f, -0.001936558688f, -9.495446725e-06f, 5.385558597e-05f}}},
+        {{{1.0f, -0.02924021934f, -0.04438342661f, 0.007285809825f},
+          {0.6357567472f, -0.3473456711f, 0.05454656494f, -0.002407477521f},
+          {-0.03301322327f, 0.004845219414f, 0.00231480583f, -0.0002307248149f}},
+         {{0.5925320577f, -0.1757678135f, 0.01505928619f, 0.000564515273f},
+          {0.1014815858f, -0.06589186703f, 0.01272886114f, -0.0007316646956f},
+          {-0.007258481865f, 0.001096195486f, 0.0003934994223f, -4.12701925e-05f}},
+         {{0.06469649321f, -0.0236701437f, 0.002902096474f, -5.896963079e-05f},
+          {0.001925008108f, -0.002869809258f, 0.0008000589141f, -6.063713228e-05f},
+          {-0.0003477407336f, 6.959756487e-05f, 1.097287507e-05f, -1.650964693e-06f}}},
+    };
+    const float ua = logf(alpha) - lx;
+    const float b = logf(total) - ua;
+    const float pu[3] = {1.0f, lx, lx * lx};
+    const float pa[3] = {1.0f, ua, ua * ua};
+    float p = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float w = pu[i] * pa[j];
+            p = fmaf(w, c[0][i][j][0] + b * (c[0][i][j][1] + b * (c[0][i][j][2] + b * c[0][i][j][3])), p);
+            q = fmaf(w, c[1][i][j][0] + b * (c[1][i][j][1] + b * (c[1][i][j][2] + b * c[1][i][j][3])), q);
+        }
+    g = p * site_rcp(q) * (x * (psi_t - psi_a) * site_rcp(beta));
     return true;
 }
 
@@ -297,7 +354,7 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
         const float lx = logf(x), ly = logf(y);
         const float d_c1 = lx + pt - p1, d_c0 = ly + pt - p0;
         float bg1, bg0;
-        if (!beta_grad_f32(x, y, c1, S, bg1) || !beta_grad_f32(y, x, c0, S, bg0)) return SITE_FALLBACK;
+        if (!beta_grad_f32(x, y, lx, ly, c1, S, p1, pt, bg1) || !beta_grad_f32(y, x, ly, lx, c0, S, p0, pt, bg0)) return SITE_FALLBACK;
         const float dv_dc1 = scale * y * bg1, dv_dc0 = -scale * x * bg0;
         const float km = S * m1 * m0, k1 = m1 * sz, k0 = m0 * sz;
         sample = (float)(lod + (hid - lod) * variate);

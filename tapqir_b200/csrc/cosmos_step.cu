@@ -96,6 +96,9 @@ template <typename T> struct LocalArgs {
     T* lgrads;                   // flat, LocalOffsets layout
     double* aoi_partial;         // (2, U): per-unit contributions to d/d(bm, bs)
     double* block_partial;       // (gridDim.x, C, NACC)
+    // sites outside the fp32 forms: appended here by site_fast_kernel, redone in double by site_worklist_kernel
+    uint32_t* worklist;          // (NSAMP * U) entries s * U + u, or NULL (block-local compaction instead)
+    unsigned int* work_count;    // [0]: entries appended this launch
     // hmm variant (cosmos_hmm.cuh): the extra local slabs live behind the cosmos layout in the same flat buffers --
     // m_probs[z = 1] (K slabs of (Nt, F, C)), then z_trans (Nt, F, C, 2, 2); m_probs[z = 0] are the cosmos m_probs slabs
     const double* hmm_a;         // (kZ, U) forward marginals of the guide's chain
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<
     float v = 0.0f, rec[NSO], extra[NEX];
     const int status = site_eval_fast(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra);
     if (status == SITE_DONE) site_scatter(a, s, (int64_t)u32, v, rec, extra);
+    else if (a.worklist) a.worklist[atomicAdd(a.work_count, 1u)] = (uint32_t)s * (uint32_t)a.U + u32;
     else a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32] = nanf("");   // marker for site_fallback_kernel
     if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
 }
@@ -241,6 +245,19 @@ __global__ void __launch_bounds__(kLocalBlock) site_fallback_kernel(const LocalA
     }
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < n_hits; i += kLocalBlock) site_double(a, s, hits[i]);
+}
+
+// The same with a device-wide worklist (tq_cosmos_sites_ws): every thread of the fixed-size grid takes entries, so the
+// double form runs in full warps at full occupancy whatever the hit rate (block-local compaction above: 75 us for the
+// 4.5 % of sites a trained C2 model sends here; this: the cost of the work itself).
+__global__ void __launch_bounds__(kLocalBlock) site_worklist_kernel(const LocalArgs<float> a) {
+    const unsigned int n = *a.work_count;
+    const uint32_t U = (uint32_t)a.U;
+    for (unsigned int i = blockIdx.x * kLocalBlock + threadIdx.x; i < n; i += gridDim.x * kLocalBlock) {
+        const uint32_t e = a.worklist[i];
+        const uint32_t s = e / U;
+        site_double(a, (int)s, e - s * U);
+    }
 }
 
 // ---- post: blocks per (AOI, channel) chunk of frames, kPostUPT units per thread; the cross-unit sums are fused in ----
@@ -850,7 +867,7 @@ extern "C" int tq_hmm_globals_sample(int dtype, int Q, const void* gparams, cons
 template <typename T>
 static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams,
                      int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in, void* samples,
-                     void* qm, void* rec, cudaStream_t st) {
+                     void* qm, void* rec, void* worklist, void* work_count, cudaStream_t st) {
     LocalArgs<T> a{};
     fill_common(a, view, Nt, mc, lparams, nullptr, aoi_offset, seed, state);
     a.noise_in = (const T*)noise_in;
@@ -861,10 +878,22 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
     if (a.U >= (int64_t)1 << 31) { set_error("minibatch of %lld units exceeds the 2^31 limit of one launch", (long long)a.U); return TQ_ERR_ARG; }
     const dim3 grid(local_blocks(a.U), NSAMP);
     if constexpr (sizeof(T) == sizeof(float)) {
+        const bool ws = worklist != nullptr && work_count != nullptr && a.U * NSAMP < ((int64_t)1 << 32);
+        a.worklist = ws ? (uint32_t*)worklist : nullptr;
+        a.work_count = ws ? (unsigned int*)work_count : nullptr;
+        if (ws) {
+            int stm = cuda_status(cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work_count)");
+            if (stm != TQ_OK) return stm;
+        }
         site_fast_kernel<<<grid, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fast_kernel launch");
-        site_fallback_kernel<<<dim3((grid.x + kFallbackUPT - 1) / kFallbackUPT, NSAMP), kLocalBlock, 0, st>>>(a);
-        TQ_LAUNCH_CHECK("site_fallback_kernel launch");
+        if (ws) {
+            site_worklist_kernel<<<sm_count() * 8, kLocalBlock, 0, st>>>(a);
+            TQ_LAUNCH_CHECK("site_worklist_kernel launch");
+        } else {
+            site_fallback_kernel<<<dim3((grid.x + kFallbackUPT - 1) / kFallbackUPT, NSAMP), kLocalBlock, 0, st>>>(a);
+            TQ_LAUNCH_CHECK("site_fallback_kernel launch");
+        }
     } else {
         site_kernel<T><<<grid, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_kernel launch");
@@ -872,16 +901,29 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
     return TQ_OK;
 }
 
-extern "C" int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
-                               int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
-                               void* samples, void* qm, void* rec, void* stream) {
+static int sites_impl(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                      int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
+                      void* samples, void* qm, void* rec, void* worklist, void* work_count, void* stream) {
     TQ_CHECK_ARG(view && mc && lparams && state && samples && qm && rec, "NULL pointer");
     TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_sites<float>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, st);
-    if (dtype == TQ_F64) return run_sites<double>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, st);
+    if (dtype == TQ_F32) return run_sites<float>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, st);
+    if (dtype == TQ_F64) return run_sites<double>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
+}
+
+extern "C" int tq_cosmos_sites(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                               int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
+                               void* samples, void* qm, void* rec, void* stream) {
+    return sites_impl(dtype, view, Nt, mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, nullptr, nullptr, stream);
+}
+
+extern "C" int tq_cosmos_sites_ws(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                                  int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
+                                  void* samples, void* qm, void* rec, void* worklist, void* work_count, void* stream) {
+    TQ_CHECK_ARG(worklist && work_count, "NULL workspace");
+    return sites_impl(dtype, view, Nt, mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, stream);
 }
 
 template <typename T>

@@ -486,7 +486,8 @@ TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
 #endif
     double scale = 1.0;
     if (alpha < 1.0f) {
-        scale = pow(rng.uniform_d(), 1.0 / (double)alpha);
+        // u^(1/alpha): the logarithm of a random number needs no more than fp32, the exponential needs double's range
+        scale = exp((double)(logf((float)rng.uniform_d()) / alpha));
         alpha += 1.0f;
     }
     const float d = alpha - 1.0f / 3.0f;

@@ -173,7 +173,7 @@ class cosmos(Model):
     def launches_per_step(self):
         """Kernels of this library launched by one default step (for bench.py's gpu_launches)."""
         eng = self.engine
-        # globals_sample, globals_prepare, site_fast, site_fallback, ksmogn, local_post, globals_finish, adam x2, advance
+        # globals_sample, globals_prepare, site_fast, site_worklist, ksmogn, local_post, globals_finish, adam x2, advance
         # (dtype "double": one site kernel)
         n = 10 if eng.dtype == torch.float32 else 9
         n += (0 if eng.full_n else 1) + (0 if eng.full_f else 1)

@@ -53,6 +53,7 @@ class CosmosEngine:
         self.gain = z(1)
         self.acc = torch.zeros(self.C * L.NACC, dtype=f64, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
+        self.work_count = torch.zeros(2, dtype=torch.int32, device=dev)   # entries of the double-fallback worklist
         self.gprep = torch.zeros(self.lib.tq_sizeof_gprep() // 8, dtype=f64, device=dev)   # prepared global reverse mode
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
         self.use_graph = use_graph
@@ -173,9 +174,11 @@ class CosmosEngine:
                 # acc-independent part of the globals' reverse mode: off the critical path, under the likelihood kernel
                 _lib.check(lib.tq_cosmos_globals_prepare(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.gprep),
                                                          _lib.stream_ptr(self.device)), "tq_cosmos_globals_prepare")
-            _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
-                                           p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
-                       "tq_cosmos_sites")
+            # sites that leave the fp32 forms are collected in a worklist (the not-yet-written gradient buffer of the
+            # likelihood kernel serves as its storage) and redone in double by dense warps
+            _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                              p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
+                                              p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
             main.wait_event(self._ev_join0)
             S, G, K = self.samples, self.gs, L.K
             if time_likelihood is not None:

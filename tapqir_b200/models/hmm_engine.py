@@ -81,9 +81,11 @@ class HmmEngine(CosmosEngine):
                 self._ev_join0.record(self._side)
                 _lib.check(lib.tq_hmm_globals_prepare(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.gprep), sst),
                            "tq_hmm_globals_prepare")
-            _lib.check(lib.tq_cosmos_sites(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
-                                           p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec), st),
-                       "tq_cosmos_sites")
+            # sites that leave the fp32 forms are collected in a worklist (the not-yet-written gradient buffer of the
+            # likelihood kernel serves as its storage) and redone in double by dense warps
+            _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                              p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
+                                              p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
             main.wait_event(self._ev_join0)   # the chain's per-frame terms need the sampled init / trans tables
             _lib.check(lib.tq_hmm_forward(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.chain_rows),
                                           p(self.chain_a), p(self.qm), st), "tq_hmm_forward")
