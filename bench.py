@@ -303,6 +303,33 @@ def run_native(args):
            "h2d_bytes_per_step": host_pix.numel() * host_pix.element_size() + host_xy.numel() * host_xy.element_size(),
            "d2h_bytes_per_step": 8}
 
+    # ---- the same measurement after training ----------------------------------------------------------------
+    # The timed steps above start from the initial variational parameters (the contract: W warm-up steps, then K timed
+    # ones).  As SVI proceeds the guides of absent spots relax to small concentrations, a few percent of the guide sites
+    # leave the fp32 forms and neighbouring units take different branches; the step slows down.  Reported beside the
+    # headline so that it is not mistaken for the steady state of a long fit.
+    trained = None
+    if args.trained_iters > 0 and args.train_iters == 0:
+        for _ in range(args.trained_iters):
+            model.step()
+        barrier()
+        tev = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.step()
+            e1.record()
+            tev.append((e0, e1))
+        barrier()
+        t_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in tev)], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+        trained = {"extra_svi_iterations": args.trained_iters,
+                   "ms_per_step": t_ms.item() / args.steps, "value": units_per_step * world / (t_ms.item() / args.steps * 1e-3),
+                   "unit": "AOI-frames/s"}
+    dbg('trained-state timing done')
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -317,7 +344,7 @@ def run_native(args):
                        "offset_bins_distinct": o_exec, "train_iters_before_timing": args.train_iters,
                        "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
                        "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "trained_state": trained,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall, "final_loss": float(eng.loss.item()),
         }
@@ -406,6 +433,9 @@ def main():
     ap.add_argument("--train-iters", type=int, default=0,
                     help="untimed SVI iterations before the warm-up: times the TRAINED state (absent spots' guides relax to "
                          "small concentrations, a few percent of the sites leave the fp32 forms) instead of the initial point")
+    ap.add_argument("--trained-iters", type=int, default=2000,
+                    help="after the timed steps, run this many more SVI iterations and time K steps again (reported as "
+                         "`trained_state`); 0 to skip")
     ap.add_argument("--keep-offset-bins", action="store_true",
                     help="do not merge the simulator's three identical offset bins (exercises the O = 3 kernels)")
     args = ap.parse_args()

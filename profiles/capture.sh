@@ -20,3 +20,8 @@ $CMD3 > gpurun_out/plain3_${TAG}.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'ksmogn_fast_kernel' -s 4 -c 1 \
     -o gpurun_out/ksmogn_o3_${TAG} $CMD3 > gpurun_out/ncu_o3_${TAG}.log 2>&1
 echo "o3 rc=$?"
+# (4) the guide-site kernels of a TRAINED model (3000 SVI iterations before the capture)
+CMD4="$CMD --train-iters 3000"
+ncu --set full --clock-control none --import-source on -k regex:'site_fast_kernel|site_worklist_kernel' -s 6010 -c 2 \
+    -o gpurun_out/sites_trained_${TAG} $CMD4 > gpurun_out/ncu_sites_trained_${TAG}.log 2>&1
+echo "trained rc=$?"
