@@ -243,6 +243,25 @@ int tq_hmm_backward(int dtype, const tq_patch_view* view, int64_t Nt, const void
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Latency-bound sum of <= tq_p2p_max_values() doubles across the <= tq_p2p_max_ranks() GPUs of one box (the global
+ * sites' accumulators), over NVLink peer memory instead of NCCL: tq_p2p_alloc gives a device buffer and
+ * its 64-byte CUDA IPC handle; exchange the handles (any host channel), tq_p2p_open the peers', put the `world` buffer
+ * pointers (own at index `rank`) in a device array.  Per step, on one stream: tq_p2p_push (writes this rank's values
+ * into every peer's buffer, then a flag) ... tq_p2p_wait_sum (polls this rank's own buffer until every peer's flag has
+ * arrived, adds the slots in rank order into `out`: bit-identical on all ranks).  Graph-capturable; a wait gives up
+ * after seconds instead of hanging (tq_p2p_timed_out). */
+int64_t tq_p2p_bytes(void);
+int tq_p2p_max_values(void);
+int tq_p2p_max_ranks(void);
+int tq_p2p_alloc(void** buffer, unsigned char* handle64);
+int tq_p2p_open(const unsigned char* handle64, void** buffer);
+int tq_p2p_close(void* buffer);
+int tq_p2p_free(void* buffer);
+int tq_p2p_push(const double* values, int n, int rank, int world, const void* peers, void* stream);
+int tq_p2p_wait_sum(void* own_buffer, int n, int world, double* out, void* stream);
+int tq_p2p_timed_out(const void* own_buffer, unsigned long long* seq);
+
+/* ---------------------------------------------------------------------------------------------
  * Ingestion of raw .glimpse frames (imscroll/glimpse_reader.py:168-186, 354-381).
  * frames_raw: (Fc, H, W) big-endian int16 exactly as stored in the file (device memory); pixel value =
  * int16 + 2^15.  Frame f0 + i of the movie is chunk frame i.

@@ -72,6 +72,16 @@ SIGNATURES = {
                                   _VP, _VP, _VP, _VP, _VP, _VP]),
     "tq_hmm_theta_probs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP]),
     "tq_hmm_backward": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP, _VP]),
+    "tq_p2p_bytes": (c_int64, []),
+    "tq_p2p_max_values": (c_int, []),
+    "tq_p2p_max_ranks": (c_int, []),
+    "tq_p2p_alloc": (c_int, [POINTER(c_void_p), _VP]),
+    "tq_p2p_open": (c_int, [_VP, POINTER(c_void_p)]),
+    "tq_p2p_close": (c_int, [_VP]),
+    "tq_p2p_free": (c_int, [_VP]),
+    "tq_p2p_push": (c_int, [_VP, c_int, c_int, c_int, _VP, _VP]),
+    "tq_p2p_wait_sum": (c_int, [_VP, c_int, c_int, _VP, _VP]),
+    "tq_p2p_timed_out": (c_int, [_VP, POINTER(c_uint64)]),
     "tq_crop_aois": (c_int, [_VP, c_int, c_int, c_int, c_int, _VP, _VP, c_int, c_int, c_int, _VP, _VP, _VP, _VP]),
     "tq_offset_hist": (c_int, [_VP, c_int, c_int, c_int, c_int, c_int, c_int, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),

@@ -13,6 +13,7 @@ sm_100a library or without a CUDA device raises.
 """
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -56,6 +57,20 @@ class CosmosEngine:
         self.work_count = torch.zeros(2, dtype=torch.int32, device=dev)   # entries of the double-fallback worklist
         self.gprep = torch.zeros(self.lib.tq_sizeof_gprep() // 8, dtype=f64, device=dev)   # prepared global reverse mode
         self.mcfg = torch.tensor([[(m >> k) & 1 for k in range(L.K)] for m in range(2**L.K)], dtype=dtype, device=dev)
+        self.acc_all = self.acc   # everything that is summed across ranks, contiguous (the hmm engine appends its chain sums)
+        # cross-rank sum of the accumulators: NVLink peer-memory push (csrc/p2p_allreduce.cu) unless TQ_ALLREDUCE=nccl or the
+        # IPC set-up is not possible (then NCCL; 120-160 us per step at 8 GPUs against ~10 us)
+        self.p2p = None
+        if self.world_size > 1 and os.environ.get("TQ_ALLREDUCE", "p2p") == "p2p":
+            try:
+                from tapqir_b200.models.p2p import P2PAllReduce
+
+                self.p2p = P2PAllReduce(dev, self.rank, self.world_size, self.pg)
+            except Exception as err:   # no peer access / IPC (e.g. containers without it): NCCL does the same sum
+                import logging
+
+                logging.getLogger(__name__).warning(f"peer-memory all-reduce unavailable ({err}); using NCCL")
+                self.p2p = None
         self.use_graph = use_graph
         self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -196,12 +211,16 @@ class CosmosEngine:
             # the all-reduce of the (C, 18) accumulators (multi-GPU), finishing the global reverse pass (a few FMAs per
             # parameter) and the global Adam run on the side stream, beside the dense Adam over the AOI-local buffer,
             # which depends on none of them: the collective's latency hides under the local update
+            if self.p2p is not None:
+                self.p2p.push(self.acc_all, st)     # straight into every peer's buffer, as early as the values exist
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):
                 sst = _lib.stream_ptr(self.device)
-                if self.world_size > 1:
-                    torch.distributed.all_reduce(self.acc, group=self.pg)
+                if self.p2p is not None:
+                    self.p2p.wait_sum(self.acc_all, sst)
+                elif self.world_size > 1 and not os.environ.get("TQ_DIAG_NO_ALLREDUCE"):   # (diagnostic switch: wrong results)
+                    torch.distributed.all_reduce(self.acc_all, group=self.pg)
                 _lib.check(lib.tq_cosmos_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc),
                                                         self.sN, self.sF, p(self.ggrads), p(self.loss), sst),
                            "tq_cosmos_globals_finish")

@@ -27,7 +27,9 @@ class HmmEngine(CosmosEngine):
         self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
         self.gparams, self.ggrads, self.gm, self.gv = z(self.gl.numel), z(self.gl.numel), z(self.gl.numel), z(self.gl.numel)
         self.nh = self.lib.tq_hmm_chain_sums()
-        self.hacc = z(self.C * self.nh, f64)
+        # accumulators and chain sums in one buffer: one cross-rank sum covers both
+        self.acc_all = z(self.C * (L.NACC + self.nh), f64)
+        self.acc, self.hacc = self.acc_all[:self.C * L.NACC], self.acc_all[self.C * L.NACC:]
         self.set_batch(kw.get("nbatch_size") or self.Nt, F)
 
     def set_batch(self, nbatch_size, fbatch_size):
@@ -106,13 +108,16 @@ class HmmEngine(CosmosEngine):
                                            p(self.chain_a), p(self.chain_v), self.sN, p(self.lgrads), p(self.hpartial),
                                            p(self.hacc), st),
                        "tq_hmm_backward")
+            if self.p2p is not None:
+                self.p2p.push(self.acc_all, st)
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):
                 sst = _lib.stream_ptr(self.device)
-                if self.world_size > 1:
-                    torch.distributed.all_reduce(self.acc, group=self.pg)
-                    torch.distributed.all_reduce(self.hacc, group=self.pg)
+                if self.p2p is not None:
+                    self.p2p.wait_sum(self.acc_all, sst)
+                elif self.world_size > 1:
+                    torch.distributed.all_reduce(self.acc_all, group=self.pg)
                 _lib.check(lib.tq_hmm_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc), p(self.hacc),
                                                      self.sN, p(self.ggrads), p(self.loss), sst), "tq_hmm_globals_finish")
                 if update:
