@@ -7,7 +7,7 @@ ELBO that Pyro's ``TraceEnum_ELBO`` / ``TraceMarkovEnum_ELBO`` assembles for the
 evaluated by :class:`tapqir_b200.models.hmm_engine.HmmEngine` (csrc/cosmos_hmm.cuh): forward marginals of the guide's
 chain, the cosmos likelihood kernel with weights sum_z a_f(z) q_f(m|z), per-state emission terms, a backward recursion
 for the gradients of ``z_trans``.  Built: the SVI step, ``z_probs`` / ``z_map`` / ``m_probs`` / ``pspecific``,
-``theta_probs`` (5 guide particles given ``z_MAP``), checkpoints.  Not built yet: ``z_sample``.
+``theta_probs`` (5 guide particles given ``z_MAP``), ``z_sample``, checkpoints.
 """
 
 from collections import OrderedDict
@@ -128,6 +128,23 @@ class hmm(cosmos):
         mp = self.param("m_probs").detach().cpu()                  # (1+S, K, Nt, F, Q)
         zmap = self.z_map.long()                                   # (Nt, F, Q)
         return torch.gather(mp, 0, zmap[None, None].expand(1, *mp.shape[1:]))[0]
+
+    @torch.no_grad()
+    def z_sample(self, num_samples):
+        """
+        ``num_samples`` draws of the guide's chain for the on-target AOIs, ``(num_samples, N, F, Q)`` (reference:
+        hmm.py:662-672, which composes per-frame index maps with ``_sequential_index``; here the chain is simply walked).
+        """
+        zt = self.param("z_trans").detach()[: self.data.N]                      # (N, F, Q, z', z)
+        N, F, Q = zt.shape[:3]
+        out = torch.empty(num_samples, N, F, Q, dtype=torch.long, device=zt.device)
+        prev = torch.zeros(num_samples, N, Q, dtype=torch.long, device=zt.device)   # row 0 is the initial distribution
+        for f in range(F):
+            rows = zt[:, f].expand(num_samples, N, Q, 2, 2)
+            probs = torch.gather(rows, 3, prev[..., None, None].expand(num_samples, N, Q, 1, 2))[..., 0, :]
+            prev = torch.multinomial(probs.reshape(-1, 2), 1).reshape(num_samples, N, Q)
+            out[:, :, f] = prev
+        return out
 
     def param(self, name):
         return transform_to(self.constraints()[name])(self.engine.named_unconstrained()[name])

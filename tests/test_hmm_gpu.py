@@ -89,6 +89,8 @@ def test_hmm_model_api_fit_checkpoint_resume(tmp_path):
     zp = model.z_probs
     assert zp.shape == (3, 8, 1, 2) and torch.allclose(zp.sum(-1), torch.ones(3, 8, 1), atol=1e-6)
     assert model.m_probs.shape == (2, 3, 8, 1) and model.z_map.shape == (3, 8, 1)
+    zs = model.z_sample(64)
+    assert zs.shape == (64, data.N, 8, 1) and abs(zs.float().mean().item() - zp[: data.N, :, :, 1].mean().item()) < 0.15
     th = model.theta_probs
     assert th.shape == (2, 3, 8, 1) and bool((th >= 0).all()) and bool((th.sum(0) <= 1 + 1e-5).all())
     again = models["cosmos+hmm"](device="cuda", dtype="float")
