@@ -219,7 +219,7 @@ class CosmosEngine:
                 sst = _lib.stream_ptr(self.device)
                 if self.p2p is not None:
                     self.p2p.wait_sum(self.acc_all, sst)
-                elif self.world_size > 1 and not os.environ.get("TQ_DIAG_NO_ALLREDUCE"):   # (diagnostic switch: wrong results)
+                elif self.world_size > 1:
                     torch.distributed.all_reduce(self.acc_all, group=self.pg)
                 _lib.check(lib.tq_cosmos_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc),
                                                         self.sN, self.sF, p(self.ggrads), p(self.loss), sst),

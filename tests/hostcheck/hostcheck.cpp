@@ -277,6 +277,165 @@ double cosmos_step_host(int nb, int fb, int Nt, int F_, int C, int P, int O, con
 
 }  // namespace
 
+// ---- hmm variant: the same device functions (cosmos_hmm.cuh, cosmos_globals.cuh with the hmm layout) in the order the
+// kernels of csrc/cosmos_step.cu run them; the chain recursions are walked frame by frame here (the kernels scan them).
+#include "cosmos_hmm.cuh"
+
+namespace {
+
+// local flat buffer of the hmm variant: cosmos layout, then m_probs[z = 1] (K slabs), then z_trans (Nt, F, C, 2, 2)
+struct HmmOffsets {
+    LocalOffsets lo;
+    int64_t std_numel() const { return lo.tensor_off(12); }
+    int64_t mprobs1(int k, int64_t n, int64_t f, int64_t c) const { return std_numel() + (int64_t)k * (lo.Nt * lo.F * lo.C) + (n * lo.F + f) * lo.C + c; }
+    int64_t ztrans(int64_t n, int64_t f, int64_t c) const { return std_numel() + (int64_t)kK * (lo.Nt * lo.F * lo.C) + ((n * lo.F + f) * lo.C + c) * (kZ * kZ); }
+    int64_t numel() const { return std_numel() + (int64_t)kK * lo.Nt * lo.F * lo.C + lo.Nt * lo.F * lo.C * kZ * kZ; }
+};
+
+template <typename T>
+double hmm_step_host(int nb, int Nt, int F_, int C, int P, int O, const int32_t* ndx, const T* pixels, const T* xy,
+                     const uint8_t* ontarget, const uint8_t* mask, const T* off_s, const T* off_w, const ModelConst* mcp, double sN,
+                     const T* lparams, const double* gparams, const T* lnoise, const double* gnoise, T* lgrads, double* ggrads) {
+    const ModelConst& mc = *mcp;
+    GlobalLayout gl{C, true};
+    GlobalTables<double> gtd;
+    double gvar[kMaxGlobalNoise], gsamp[kMaxGlobalNoise];
+    for (int i = 0; i < gl.n_count(); ++i) gvar[i] = gnoise[i];
+    globals_pre(gparams, gl, mc, false, nullptr, gvar, gsamp, gtd);
+    GlobalTables<T> gt;
+    gt.convert_from(gtd);
+    HmmOffsets ho{{Nt, F_, C}};
+    const LocalOffsets& lo = ho.lo;
+    const int fb = F_;
+    const int64_t U = (int64_t)nb * fb * C;
+    std::vector<double> acc((size_t)C * NACC, 0.0), hacc((size_t)C * NHACC, 0.0);
+    for (int64_t i = 0; i < ho.numel(); ++i) lgrads[i] = T(0);
+    T mcfg[kM][kK];
+    for (int m = 0; m < kM; ++m) for (int k = 0; k < kK; ++k) mcfg[m][k] = T((m >> k) & 1);
+    std::vector<double> a_fwd((size_t)2 * fb), vdiff((size_t)fb);
+    for (int ni = 0; ni < nb; ++ni)
+        for (int c = 0; c < C; ++c) {
+            const int64_t n = ndx ? ndx[ni] : ni;
+            const double mu = mask[n] ? 1.0 : 0.0;
+            const int ot = ontarget[n] ? 1 : 0;
+            // forward marginals of the guide's chain
+            double a0 = 1.0, a1 = 0.0;
+            for (int f = 0; f < fb; ++f) {
+                const T* zt = lparams + ho.ztrans(n, f, c);
+                const ChainRow r0 = chain_row((double)zt[0], (double)zt[1], mc), r1 = chain_row((double)zt[2], (double)zt[3], mc);
+                const double b0 = a0 * r0.q[0] + a1 * r1.q[0], b1 = a0 * r0.q[1] + a1 * r1.q[1];
+                a0 = b0; a1 = b1;
+                a_fwd[2 * f] = a0; a_fwd[2 * f + 1] = a1;
+            }
+            // per unit: sites, weights, likelihood, emission terms
+            for (int f = 0; f < fb; ++f) {
+                const int64_t u = ((int64_t)ni * fb + f) * C + c;
+                T rec[NREC], sample[NSAMP], qm[kM], ump[kZ][kK], az[kZ] = {(T)a_fwd[2 * f], (T)a_fwd[2 * f + 1]};
+                const double ubm = (double)lparams[lo.index(LP_BM, n, f, c)], ubs = (double)lparams[lo.index(LP_BS, n, f, c)];
+                for (int st = 0; st < NSAMP; ++st) {
+                    double r[NSO], ex[NEX];
+                    double variate = (double)lnoise[st * U + u];
+                    bool done = false;
+                    if (sizeof(T) == sizeof(float)) {
+                        float rf[NSO], exf[NEX], vf;
+                        if (site_eval_fast(st, (float)lparams[lo.index(site_param0(st), n, f, c)], (float)lparams[lo.index(site_param1(st), n, f, c)],
+                                           (float)ubm, (float)ubs, mc, false, nullptr, variate, vf, rf, exf) == SITE_DONE) {
+                            done = true;
+                            sample[st] = (T)vf;
+                            for (int j2 = 0; j2 < NSO; ++j2) rec[st * NSO + j2] = (T)rf[j2];
+                            if (st == S_B) for (int j2 = 0; j2 < NEX; ++j2) rec[NSAMP * NSO + j2] = (T)exf[j2];
+                        }
+                    }
+                    if (done) continue;
+                    const double v = site_eval(st, (double)lparams[lo.index(site_param0(st), n, f, c)],
+                                               (double)lparams[lo.index(site_param1(st), n, f, c)], ubm, ubs, mc, false, nullptr, variate, r, ex);
+                    sample[st] = (T)v;
+                    for (int j2 = 0; j2 < NSO; ++j2) rec[st * NSO + j2] = (T)r[j2];
+                    if (st == S_B) for (int j2 = 0; j2 < NEX; ++j2) rec[NSAMP * NSO + j2] = (T)ex[j2];
+                }
+                for (int k = 0; k < kK; ++k) { ump[0][k] = lparams[lo.index(LP_M_PROBS + k, n, f, c)]; ump[1][k] = lparams[ho.mprobs1(k, n, f, c)]; }
+                hmm_presence_weights<T>(ump, az, mc, qm);
+                const int64_t patch = (n * F_ + f) * C + c;
+                PatchSpots<T> sp;
+                for (int k = 0; k < kK; ++k) {
+                    sp.h[k] = sample[S_H + k]; sp.w[k] = sample[S_W + k];
+                    sp.cx[k] = sample[S_X + k] + xy[patch * 2]; sp.cy[k] = sample[S_Y + k] + xy[patch * 2 + 1];
+                }
+                sp.b = sample[S_B];
+                PatchOut<T, kM> po; po.zero();
+                for (int row = 0; row < P; ++row)
+                    for (int col = 0; col < P; ++col) {
+                        T gxk[kK], gyk[kK];
+                        for (int k = 0; k < kK; ++k) { gxk[k] = axis_factor<T>(col, sp.cx[k], sp.w[k]); gyk[k] = axis_factor<T>(row, sp.cy[k], sp.w[k]); }
+                        pixel_accumulate<T, kM, true>(pixels[(patch * P + row) * P + col], gxk, gyk, col, row, sp, mcfg, (T)gtd.rate, (T)gtd.log_rate, O, off_s, off_w, qm, po);
+                    }
+                T gs[NSAMP], Lm[kM];
+                gs[S_B] = po.g_b;
+                for (int k = 0; k < kK; ++k) { gs[S_H + k] = po.g_h[k]; gs[S_W + k] = po.g_w[k]; gs[S_X + k] = po.g_x[k]; gs[S_Y + k] = po.g_y[k]; }
+                for (int m = 0; m < kM; ++m) Lm[m] = po.logp[m];
+                UnitGrads<T> ug;
+                HmmUnitOut<T> hu;
+                unit_post_hmm<T>(rec, sample, Lm, gs, po.g_rate, ump, az, (T)ubm, (T)ubs, mc, gt, c, f == 0, ug, hu);
+                for (int k = 0; k < kK; ++k) { ug.g[LP_M_PROBS + k] = hu.gmp[0][k]; lgrads[ho.mprobs1(k, n, f, c)] += (T)(-sN * mu * (double)hu.gmp[1][k]); }
+                vdiff[f] = (double)hu.v[1] - (double)hu.v[0];
+                for (int i = 0; i < NACC; ++i) acc[(size_t)c * NACC + i] += mu * (double)ug.acc[i];
+                for (int i = 0; i < NLOCAL; ++i) lgrads[lo.index(i, n, f, c)] += (T)(-sN * mu * (double)ug.g[i]);
+                if (f == 0) {
+                    double gbm, gbs;
+                    aoi_prior_grad(ubm, ubs, mc, gbm, gbs);
+                    lgrads[lo.index(LP_BM, n, f, c)] += (T)(-sN * mu * gbm);
+                    lgrads[lo.index(LP_BS, n, f, c)] += (T)(-sN * mu * gbs);
+                }
+            }
+            // backward recursion (hmm_backward_kernel, frame by frame)
+            const ChannelTables<double>& ct = gtd.ch[c];
+            double carry = 0.0;
+            for (int f = fb - 1; f >= 0; --f) {
+                const int64_t iz = ho.ztrans(n, f, c);
+                const ChainRow r0 = chain_row((double)lparams[iz + 0], (double)lparams[iz + 1], mc);
+                const ChainRow r1 = chain_row((double)lparams[iz + 2], (double)lparams[iz + 3], mc);
+                const double delta = vdiff[f] + carry;
+                const double ap0 = f > 0 ? a_fwd[2 * (f - 1)] : 1.0, ap1 = f > 0 ? a_fwd[2 * (f - 1) + 1] : 0.0;
+                double R0[kZ], R1[kZ];
+                for (int z = 0; z < kZ; ++z) {
+                    R0[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][0][z]) - r0.lq[z];
+                    R1[z] = (f == 0 ? ct.logpz[ot][z] : ct.logptrans[ot][1][z]) - r1.lq[z];
+                }
+                const double g0 = ap0 * r0.q[1] * r0.q[0] * (R0[1] - R0[0] + delta), g1 = ap1 * r1.q[1] * r1.q[0] * (R1[1] - R1[0] + delta);
+                lgrads[iz + 0] = (T)(sN * mu * g0); lgrads[iz + 1] = (T)(-sN * mu * g0);
+                lgrads[iz + 2] = (T)(sN * mu * g1); lgrads[iz + 3] = (T)(-sN * mu * g1);
+                const double rho0 = r0.q[0] * R0[0] + r0.q[1] * R0[1], rho1 = r1.q[0] * R1[0] + r1.q[1] * R1[1];
+                hacc[(size_t)c * NHACC + HACC_ELBO] += mu * (ap0 * rho0 + ap1 * rho1);
+                if (ot) for (int z = 0; z < kZ; ++z) {
+                    if (f == 0) hacc[(size_t)c * NHACC + HACC_INIT + z] += mu * ap0 * r0.q[z];
+                    else { hacc[(size_t)c * NHACC + HACC_TRANS + z] += mu * ap0 * r0.q[z]; hacc[(size_t)c * NHACC + HACC_TRANS + kZ + z] += mu * ap1 * r1.q[z]; }
+                }
+                carry = (rho1 - rho0) + (r1.q[1] - r0.q[1]) * delta;
+            }
+        }
+    double elbo = 0.0;
+    for (int site = 0; site < global_site_count(gl.Q, true); ++site)
+        elbo += globals_post_site(site, gparams, gl, mc, gsamp, acc.data(), sN, 1.0, ggrads, hacc.data());
+    return -elbo;
+}
+
+}  // namespace
+
+extern "C" {
+double hc_hmm_step_f64(int nb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const double* pixels, const double* xy,
+                       const uint8_t* ontarget, const uint8_t* mask, const double* off_s, const double* off_w, const ModelConst* mc,
+                       double sN, const double* lparams, const double* gparams, const double* lnoise, const double* gnoise,
+                       double* lgrads, double* ggrads) {
+    return hmm_step_host<double>(nb, Nt, F, C, P, O, ndx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, lparams, gparams, lnoise, gnoise, lgrads, ggrads);
+}
+double hc_hmm_step_f32(int nb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const float* pixels, const float* xy,
+                       const uint8_t* ontarget, const uint8_t* mask, const float* off_s, const float* off_w, const ModelConst* mc,
+                       double sN, const float* lparams, const double* gparams, const float* lnoise, const double* gnoise,
+                       float* lgrads, double* ggrads) {
+    return hmm_step_host<float>(nb, Nt, F, C, P, O, ndx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, lparams, gparams, lnoise, gnoise, lgrads, ggrads);
+}
+}
+
 extern "C" {
 double hc_cosmos_step_f64(int nb, int fb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const int32_t* fdx,
                           const double* pixels, const double* xy, const uint8_t* ontarget, const uint8_t* mask,

@@ -74,3 +74,56 @@ def test_hmm_layouts_round_trip():
         assert torch.equal(back[n], t), n
     # z_trans sits behind the cosmos layout and m_probs[z = 1]
     assert ll.offsets["z_trans"] == ll.std_numel + 2 * 3 * 4 * 2
+
+
+# ---- the kernels' arithmetic (csrc/cosmos_hmm.cuh + the hmm global sites) compiled for the host, against the oracle ----
+import ctypes
+
+import pytest
+
+from tests import hostcheck
+from tests.step_helpers import compare_grads
+
+
+def host_hmm_step(hc, data, params, ndx, noise, dtype):
+    ll, gl = L.HmmLocalLayout(data.Nt, data.F, data.C), L.HmmGlobalLayout(data.C)
+    lparams = torch.zeros(ll.numel, dtype=dtype)
+    ll.load_named(lparams, params)
+    gparams = gl.pack({k: params[k] for k in gl.shapes}, dtype=torch.float64)
+    lnoise = L.pack_local_noise(noise, dtype, "cpu")
+    gnoise = gl.pack_noise(noise)
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, data.P, torch.float64)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    ndx32 = ndx.to(torch.int32).contiguous()
+    pixels, xy = data.images.to(dtype).contiguous(), data.xy.to(dtype).contiguous()
+    ont, mask = data.is_ontarget.to(torch.uint8).contiguous(), data.mask.to(torch.uint8).contiguous()
+    off_s, off_w = data.offset_samples.to(dtype).contiguous(), data.offset_logits.to(dtype).contiguous()
+    lgrads = torch.empty_like(lparams)
+    ggrads = torch.zeros(gl.numel, dtype=torch.float64)
+    fn = hc.hc_hmm_step_f64 if dtype == torch.float64 else hc.hc_hmm_step_f32
+    fn.restype = ctypes.c_double
+    loss = fn(len(ndx), data.Nt, data.F, data.C, data.P, off_s.numel(), p(ndx32), p(pixels), p(xy), p(ont), p(mask), p(off_s),
+              p(off_w), ctypes.byref(mc), ctypes.c_double(data.Nt / len(ndx)), p(lparams), p(gparams), p(lnoise), p(gnoise),
+              p(lgrads), p(ggrads))
+    grads = dict(ll.named(lgrads))
+    grads.update(gl.views(ggrads))
+    return loss, grads
+
+
+@pytest.mark.parametrize("cfg", [dict(N=3, F=5, C=1, seed=0), dict(N=3, F=4, C=2, seed=1)])
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
+def test_hmm_step_arithmetic_matches_oracle_on_the_host(cfg, dtype, ltol, gtol):
+    hc = hostcheck.load()
+    ds, data, params, ndx, noise = small_problem(**cfg)
+    ndx = torch.tensor([2, 0])
+    if dtype == torch.float32:
+        params = {k: v.float().double() for k, v in params.items()}
+    g = torch.Generator().manual_seed(3)
+    noise = H.draw_noise(params, data, ndx, g)
+    if dtype == torch.float32:
+        noise = {k: v.float().double() for k, v in noise.items()}
+    ref_loss, ref_grads = H.loss_and_grads(params, data, ndx, noise)
+    loss, grads = host_hmm_step(hc, data, params, ndx, noise, dtype)
+    assert abs(loss - ref_loss) <= ltol * abs(ref_loss)
+    bad = compare_grads(grads, ref_grads, gtol)
+    assert not bad, bad
