@@ -255,12 +255,12 @@ def run_native(args):
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists():
-        t = json.loads(tj.read_text()).get("ksmogn_fast_kernel" if o_exec == 1 else "ksmogn_fast_kernel_o3", {})
+        t = json.loads(tj.read_text()).get("ksmogn_stream_kernel" if o_exec == 1 else "ksmogn_stream_kernel_o3", {})
         if t.get("workload") == args.workload and t.get("units_per_launch") == patches_per_step:
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
                        "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step, "source": t["source"]}
     roofline = {
-        "kernel": f"ksmogn_fast_kernel<uint16,{o_exec},true,true> (fused render + offset-marginalised likelihood fwd+bwd)",
+        "kernel": f"ksmogn_stream_kernel<uint16,{o_exec},true,true> (fused render + offset-marginalised likelihood fwd+bwd)",
         "bound": bound[1],
         "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
         "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),

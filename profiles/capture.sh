@@ -10,18 +10,18 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'ksmogn|site_
 echo "launch list rc=$?"
 # (2) full capture of the likelihood, site and post kernels (one launch each, after warm-up)
 $CMD > gpurun_out/plain2_${TAG}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'ksmogn_fast_kernel|site_fast_kernel|local_post_kernel' -s 12 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:'ksmogn_stream_kernel|site_fast_kernel|local_post_kernel' -s 12 -c 3 \
     -o gpurun_out/step_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full rc=$?"
 tail -2 gpurun_out/ncu_full_${TAG}.log
 # (3) the same likelihood kernel with the simulator's three offset bins kept distinct (O = 3 forms)
 CMD3="$CMD --keep-offset-bins"
 $CMD3 > gpurun_out/plain3_${TAG}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'ksmogn_fast_kernel' -s 4 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:'ksmogn_stream_kernel' -s 4 -c 1 \
     -o gpurun_out/ksmogn_o3_${TAG} $CMD3 > gpurun_out/ncu_o3_${TAG}.log 2>&1
 echo "o3 rc=$?"
-# (4) the guide-site kernels of a TRAINED model (3000 SVI iterations before the capture)
-CMD4="$CMD --train-iters 3000"
-ncu --set full --clock-control none --import-source on -k regex:'site_fast_kernel|site_worklist_kernel' -s 6010 -c 2 \
+# (4) the guide-site kernels of a TRAINED model (2000 SVI iterations before the capture)
+CMD4="$CMD --train-iters 2000"
+ncu --set full --clock-control none --import-source on -k regex:'site_fast_kernel|site_worklist_kernel' -s 4010 -c 2 \
     -o gpurun_out/sites_trained_${TAG} $CMD4 > gpurun_out/ncu_sites_trained_${TAG}.log 2>&1
 echo "trained rc=$?"

@@ -153,84 +153,129 @@ TQ_HD void gamma_grad_rice(float alpha, float ia, float u, const Lp1& p, float& 
     sgg = (1.0f + u) + sgg_m1u;
 }
 
-// ATen's Beta reparameterisation gradient (tq_math.cuh::beta_grad: same regimes, series and coefficient tables) in
-// fp32 for SMALL concentrations (total <= 64: nothing in the plain formulas is large enough to cancel), with what the
-// caller already has passed in instead of recomputed: y = 1 - x (formed in double: draws pile up against 0 and 1 at
-// these concentrations), lx = ln x, ly = ln y, and the digammas psi(alpha), psi(total).  Returns false where fp32 is
-// not enough (caller: double form).
-TQ_HD bool beta_grad_f32(float x, float y, float lx, float ly, float alpha, float total, float psi_a, float psi_t, float& g) {
-    const float beta = total - alpha;
+// reciprocal of a positive double from the fp32 MUFU seed and one Newton step (1e-14): the series below need their
+// divisions in double, and a DP division costs several times this
+TQ_HD double rcp_d(double d) {
+#ifdef __CUDA_ARCH__
+    const double r = (double)site_rcp((float)d);
+    return fma(r, fma(-d, r, 1.0), r);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// ATen's Beta reparameterisation gradient d x / d alpha (tq_math.cuh::beta_grad: same regimes, series and coefficient
+// tables) OUTSIDE the regime site_eval_fast reformulates (both concentrations > 6 and the draw in the bulk): small
+// concentrations -- absent spots, whose guides relax towards the flat prior -- and draws in the tails.  The caller
+// passes what it already has:
+//   xd, yd       the draw and 1 - draw (double: draws pile up against 0 and 1 at small concentrations)
+//   lx, ly       ln x, ln y (log1p of the small one where the other is close to 1)
+//   dpsi         psi(total) - psi(alpha);   dc = ln x + dpsi  (= d log q / d alpha, already needed for the density)
+//   la, lb       ln(alpha) - ln x  and  ln(x total / alpha)  when have_logs (formed without cancellation at large total)
+//   rice         the reformulated Rice value when have_rice (alpha, beta > 6: the draw is then in a tail, where that
+//                expansion has nothing left to cancel)
+// The two power series alternate with terms up to e^(beta x) times their sum: their ten / eight terms are accumulated in
+// double (arguments and result stay fp32; FP64 FMAs run at half the FP32 rate on sm_100, it is double TRANSCENDENTALS
+// that are slow).  Returns false where no fp32 form applies (caller: double form).
+TQ_HD_NOINLINE bool beta_grad_tierb(double xd, double yd, float lx, float ly, float alpha, float beta, float total, float dpsi,
+                                    float dc, bool have_logs, float la, float lb, bool have_rice, float rice, float& g) {
+    const float x = (float)xd, y = (float)yd;
     const float boundary = total * x * y;
     if (x <= 0.5f && boundary < 2.5f) {
-        // power series in x around 0; terms alternate with size ~ (beta x)^i / i!: fine in fp32 while beta x < 2
-        // (measured: 4e-6 at 2, 1e-5 at 2.5, 3e-5 at 3.5)
-        if (!(beta * x < 2.0f)) return false;
-        const float factor = psi_a - psi_t - lx;
-        float numer = 1.0f, id = site_rcp(alpha);
-        float series = id * (factor + id);
-#pragma unroll
+        // power series in x around 0
+        const double f = -(double)dc, a = alpha, b = beta;
+        double numer = 1.0, id = rcp_d(a);
+        double series = id * (f + id);
+#pragma unroll 1
         for (int i = 1; i <= 10; ++i) {
-            numer *= (float(i) - beta) * x * (1.0f / float(i));
-            id = site_rcp(alpha + float(i));
-            series = fmaf(numer * id, factor + id, series);
+            numer *= ((double)i - b) * xd * rcp_d((double)i);
+            id = rcp_d(a + (double)i);
+            series = fma(numer * id, f + id, series);
         }
-        const float res = x * expf(-beta * ly) * series;           // x (1 - x)^(-beta) series
+        const float res = x * expf(-beta * ly) * (float)series;       // x (1 - x)^(-beta) series
         g = (res != res) ? 0.0f : res;
         return true;
     }
     if (x >= 0.5f && boundary < 0.75f) {
         // the mirrored series in y = 1 - x
-        if (!(alpha * y < 2.0f)) return false;
-        const float factor = psi_t - psi_a;
-        float numer = 1.0f, betas = 1.0f, dbetas = 0.0f, series = factor * site_rcp(beta);
-#pragma unroll
+        const double f = dpsi, a = alpha, b = beta;
+        double numer = 1.0, betas = 1.0, dbetas = 0.0, series = f * rcp_d(b);
+#pragma unroll 1
         for (int i = 1; i <= 8; ++i) {
-            numer *= -y * (1.0f / float(i));
-            dbetas = dbetas * (alpha - float(i)) + betas;
-            betas = betas * (alpha - float(i));
-            series = fmaf(numer * site_rcp(beta + float(i)), dbetas + factor * betas, series);
+            numer *= -yd * rcp_d((double)i);
+            dbetas = dbetas * (a - (double)i) + betas;
+            betas = betas * (a - (double)i);
+            series = fma(numer * rcp_d(b + (double)i), dbetas + f * betas, series);
         }
-        const float res = expf((1.0f - alpha) * lx) * series;      // -(-(1 - y)^(1 - alpha) series)
+        const float res = expf((1.0f - alpha) * lx) * (float)series;   // -(-(1 - y)^(1 - alpha) series)
         g = (res != res) ? 0.0f : res;
         return true;
     }
-    if (alpha > 6.0f && beta > 6.0f) return false;   // Rice expansion outside the reformulated regime: double
+    if (alpha > 6.0f && beta > 6.0f) {
+        g = rice;
+        return have_rice;
+    }
     // rational correction to an analytic approximation (coefficients: torch Distributions.h, as in tq_math.cuh)
-    const float c[2][3][3][4] = {
-        {{{1.003668233f, -0.01061107488f, -0.0657888334f, 0.01201642863f},
-          {0.6336835991f, -0.3557432599f, 0.05486251648f, -0.001465281033f},
-          {-0.03276231906f, 0.004474107445f, 0.002429354597f, -0.0001557569013f}},
-         {{0.221950385f, -0.3187676331f, 0.01799915743f, 0.01074823814f},
-          {-0.2951249643f, 0.06219954479f, 0.01535556598f, 0.001550077057f},
-          {0.02155310298f, 0.004170831599f, 0.001292462449f, 6.976601077e-05f}},
-         {{-0.05980841433f, 0.008441916499f, 0.01085618172f, 0.002319392565f},
-          {0.02911413504f, 0.01400243777f, -0.002721828457f, 0.000751041181f},
-          {0.005900514878f, -0.001936558688f, -9.495446725e-06f, 5.385558597e-05f}}},
-        {{{1.0f, -0.02924021934f, -0.04438342661f, 0.007285809825f},
-          {0.6357567472f, -0.3473456711f, 0.05454656494f, -0.002407477521f},
-          {-0.03301322327f, 0.004845219414f, 0.00231480583f, -0.0002307248149f}},
-         {{0.5925320577f, -0.1757678135f, 0.01505928619f, 0.000564515273f},
-          {0.1014815858f, -0.06589186703f, 0.01272886114f, -0.0007316646956f},
-          {-0.007258481865f, 0.001096195486f, 0.0003934994223f, -4.12701925e-05f}},
-         {{0.06469649321f, -0.0236701437f, 0.002902096474f, -5.896963079e-05f},
-          {0.001925008108f, -0.002869809258f, 0.0008000589141f, -6.063713228e-05f},
-          {-0.0003477407336f, 6.959756487e-05f, 1.097287507e-05f, -1.650964693e-06f}}},
+    // (polynomials accumulated in double: d sample / d size is a difference of two of these gradients that cancels ten- to
+    // thirty-fold for lopsided guides, and 72 FP64 FMAs are cheap on sm_100)
+    const double c[2][3][3][4] = {
+        {{{1.003668233, -0.01061107488, -0.0657888334, 0.01201642863},
+          {0.6336835991, -0.3557432599, 0.05486251648, -0.001465281033},
+          {-0.03276231906, 0.004474107445, 0.002429354597, -0.0001557569013}},
+         {{0.221950385, -0.3187676331, 0.01799915743, 0.01074823814},
+          {-0.2951249643, 0.06219954479, 0.01535556598, 0.001550077057},
+          {0.02155310298, 0.004170831599, 0.001292462449, 6.976601077e-05}},
+         {{-0.05980841433, 0.008441916499, 0.01085618172, 0.002319392565},
+          {0.02911413504, 0.01400243777, -0.002721828457, 0.000751041181},
+          {0.005900514878, -0.001936558688, -9.495446725e-06, 5.385558597e-05}}},
+        {{{1.0, -0.02924021934, -0.04438342661, 0.007285809825},
+          {0.6357567472, -0.3473456711, 0.05454656494, -0.002407477521},
+          {-0.03301322327, 0.004845219414, 0.00231480583, -0.0002307248149}},
+         {{0.5925320577, -0.1757678135, 0.01505928619, 0.000564515273},
+          {0.1014815858, -0.06589186703, 0.01272886114, -0.0007316646956},
+          {-0.007258481865, 0.001096195486, 0.0003934994223, -4.12701925e-05}},
+         {{0.06469649321, -0.0236701437, 0.002902096474, -5.896963079e-05},
+          {0.001925008108, -0.002869809258, 0.0008000589141, -6.063713228e-05},
+          {-0.0003477407336, 6.959756487e-05, 1.097287507e-05, -1.650964693e-06}}},
     };
-    const float ua = logf(alpha) - lx;
-    const float b = logf(total) - ua;
-    const float pu[3] = {1.0f, lx, lx * lx};
-    const float pa[3] = {1.0f, ua, ua * ua};
-    float p = 0.0f, q = 0.0f;
+    const float uaf = have_logs ? la : logf(alpha) - lx;
+    const double ua = uaf, b = have_logs ? lb : logf(total) - uaf, u = lx;
+    const double pu[3] = {1.0, u, u * u};
+    const double pa[3] = {1.0, ua, ua * ua};
+    double p = 0.0, q = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const float w = pu[i] * pa[j];
-            p = fmaf(w, c[0][i][j][0] + b * (c[0][i][j][1] + b * (c[0][i][j][2] + b * c[0][i][j][3])), p);
-            q = fmaf(w, c[1][i][j][0] + b * (c[1][i][j][1] + b * (c[1][i][j][2] + b * c[1][i][j][3])), q);
+            const double w = pu[i] * pa[j];
+            p = fma(w, c[0][i][j][0] + b * (c[0][i][j][1] + b * (c[0][i][j][2] + b * c[0][i][j][3])), p);
+            q = fma(w, c[1][i][j][0] + b * (c[1][i][j][1] + b * (c[1][i][j][2] + b * c[1][i][j][3])), q);
         }
-    g = p * site_rcp(q) * (x * (psi_t - psi_a) * site_rcp(beta));
+    g = (float)(p * rcp_d(q) * (xd * (double)dpsi * rcp_d((double)beta)));
     return true;
+}
+
+// Density pieces of Beta(cs, cb) with total S > 16 and ONE small concentration cs <= 6 (a guide pushed against an edge of
+// its interval): Stirling for lgamma(S) - lgamma(cb), the small side directly.
+//   xs, lxs, us   the draw on the small side, its log, and (xs - ms) / ms
+//   pb            log1p parts of the big side's (xb - mb) / mb;  lmb = ln mb
+//   lqs           log q + ln(scale);  d_cs, d_cb = d log q / d c;  dpsi_* = psi(S) - psi(c_*);  b1 = ms d_cs + mb d_cb
+struct BetaLopsided { float lqs, d_cs, d_cb, dpsi_s, dpsi_b, b1; };
+TQ_HD BetaLopsided beta_density_lopsided(float cs, float cb, float S, float xs, float lxs, float us, const Lp1& pb, float ms,
+                                         float mb, float lmb) {
+    BetaLopsided o;
+    float lgs, psis;
+    lgamma_digamma_f32(cs, lgs, psis);
+    const float it = site_rcp(S), ib = site_rcp(cb);
+    const float qt = stirling_q(it), qb = stirling_q(ib);
+    const float lSx = logf(S * xs);
+    o.lqs = (cb - 1.0f) * pb.l - 0.5f * lmb + cs * lSx - lxs - cs + stirling_r(it) - stirling_r(ib) - lgs;
+    o.d_cs = lSx - qt - psis;
+    o.d_cb = pb.l + qb - qt;
+    o.dpsi_s = logf(S) - qt - psis;
+    o.dpsi_b = qb - qt - lmb;
+    o.b1 = ms * (lSx - psis - us) - mb * pb.f + mb * qb - qt;       // ms us + mb ub = 0 used
+    return o;
 }
 
 // Numerator polynomial of the Taylor patch of ATen's Beta gradient around x = mean
@@ -248,10 +293,10 @@ TQ_HD double beta_patch_poly(double x, double alpha, double beta) {
 // log-density of v ~ Gamma(conc, rate) and its partials from x = rate v = conc (1 + u):
 //   lp, d_v, and the two combinations the site maps need:  conc * d_conc  and  conc * d_conc + rate * d_rate
 TQ_HD void gamma_density_fast(float conc, float lconc, float lrate, float rate, float x, float u, const Lp1& p,
-                              float& lp, float& d_v, float& cdc, float& cdc_rdr, float& psi) {
+                              float& lp, float& d_v, float& cdc, float& cdc_rdr, float& psi, bool known_big = false) {
     const float lx = lconc + p.l;
     d_v = rate * (-fmaf(conc, u, 1.0f)) * site_rcp(x);            // (conc - 1)/v - rate
-    if (conc > 10.0f) {
+    if (known_big || conc > 10.0f) {
         const float ic = site_rcp(conc);
         const float q = stirling_q(ic);
         lp = lrate - lx - conc * p.f + 0.5f * lconc - kSiteHalfLn2Pi - stirling_r(ic);
@@ -270,9 +315,17 @@ TQ_HD void gamma_density_fast(float conc, float lconc, float lrate, float rate, 
 // Same arguments and outputs as site_eval, with float records.  Returns SITE_DONE, or -- when the site is
 // outside the regimes handled in fp32 -- SITE_FALLBACK (variate holds the base draw: call site_eval in
 // replay mode) or SITE_FALLBACK_DRAW (nothing drawn yet: call site_eval as is).
-enum { SITE_DONE = 0, SITE_FALLBACK = 1, SITE_FALLBACK_DRAW = 2 };
-TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
-                         Philox* rng, double& variate, float& sample, float* rec, float* extra) {
+//
+// MODE splits the work for site_fast_kernel, whose warps would otherwise drag every lane through every regime any lane is in
+// (a trained model: 13.6 of 32 lanes active per instruction): 1 = draw, classify, and evaluate only the BULK regime
+// (Gamma: concentration > 10 and draw >= 0.8; Beta: both concentrations > 6 and the draw away from the tails), returning
+// SITE_DEFER with `variate` and a regime class in `cls` otherwise; 2 = replay a deferred site (everything but the bulk
+// forms and the sampler compiled out); 0 = everything in one call.
+enum { SITE_DONE = 0, SITE_FALLBACK = 1, SITE_FALLBACK_DRAW = 2, SITE_DEFER = 3 };
+constexpr int kSiteClasses = 4;   // regime classes of deferred sites
+template <int MODE>
+TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
+                           Philox* rng, double& variate, float& sample, float* rec, float* extra, int& cls) {
     if (!(mc.eps < 1e-12)) return SITE_FALLBACK_DRAW;   // fp32 reference conventions move the clamps into range
     if (site_is_gamma(s)) {
         // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
@@ -287,13 +340,18 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
         const float u = (float)(rd - 1.0);
         const float x = (float)xd;
         if (x < 0.8f && conc > 30.0f) return SITE_FALLBACK;        // Taylor regime far in the tail: powers underflow in fp32
+        const bool bulk = conc > 10.0f && x >= 0.8f;
+        if (MODE == 1 && !bulk) {
+            cls = conc > 10.0f ? 2 : (x < 0.8f ? 0 : 1);
+            return SITE_DEFER;
+        }
         const float ibeta = expf(-u1), beta = site_rcp(ibeta), loc = conc * ibeta;
         const float v = x * ibeta;
         const Lp1 p = lp1_parts(u, (float)rd);
         float lp, d_v, cdc, cdc_rdr, psi;
-        gamma_density_fast(conc, lconc, u1, beta, x, u, p, lp, d_v, cdc, cdc_rdr, psi);
+        gamma_density_fast(conc, lconc, u1, beta, x, u, p, lp, d_v, cdc, cdc_rdr, psi, MODE == 1);
         float sgg, sgg_m1u;
-        if (x >= 0.8f && conc > 8.0f) {
+        if (MODE == 1 || (x >= 0.8f && conc > 8.0f)) {
             gamma_grad_rice(conc, ic, u, p, sgg, sgg_m1u);
         } else {
             sgg = gamma_grad_small(conc, x, lconc + p.l, p.l, lconc, psi);
@@ -343,27 +401,92 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
     const float ua = (float)fma(x01d, ed, x01d - 1.0);            // (x - m1) / m1
     const float x = (float)x01d, y = (float)(1.0 - x01d);
     const float ie = site_rcp(e), ub = -ua * ie;                  // -(x - m1) / m0
-    if (!(c1 > 6.0f && c0 > 6.0f && S * x * y >= 2.5f && ua > -1.0f && ub > -1.0f)) {
-        // ---- small concentrations (absent spots: the guide relaxes towards the flat prior), or a draw in the far tail:
-        // the textbook formulas in fp32 -- nothing large enough to cancel while total <= 64
-        if (!(S <= 64.0f) || !(x > 1e-30f) || !(y > 1e-30f)) return SITE_FALLBACK;
-        float lgt, pt, lg1, p1, lg0, p0;
-        lgamma_digamma_f32(S, lgt, pt);
-        lgamma_digamma_f32(c1, lg1, p1);
-        lgamma_digamma_f32(c0, lg0, p0);
-        const float lx = logf(x), ly = logf(y);
-        const float d_c1 = lx + pt - p1, d_c0 = ly + pt - p0;
+    const bool bulk = c1 > 6.0f && c0 > 6.0f && S * x * y >= 2.5f && ua > -1.0f && ub > -1.0f;
+    if (MODE == 1 && !bulk) {
+        cls = S <= 16.0f ? 0 : (c1 <= 6.0f ? 1 : (c0 <= 6.0f ? 2 : 3));
+        return SITE_DEFER;
+    }
+    if (MODE != 1 && (MODE == 2 || !bulk)) {
+        // ---- small concentrations (absent spots: the guide relaxes towards the flat prior), a guide pushed against an
+        // edge of its interval, or a draw in a tail: per-gradient regimes of beta_grad_tierb, and for the density
+        //   S <= 16                      the textbook formulas (nothing large enough to cancel)
+        //   S > 16, both c > 6           the Stirling / log1p forms of the bulk regime below
+        //   S > 16, one c <= 6           beta_density_lopsided (the other is then >= 10)
+        if (!(x > 1e-30f) || !(y > 1e-30f) || !(ua > -1.0f) || !(ub > -1.0f)) return SITE_FALLBACK;
+        const bool big = c1 > 6.0f && c0 > 6.0f;
+        const float lx = x > 0.5f ? log1pf(-y) : logf(x), ly = y > 0.5f ? log1pf(-x) : logf(y);
+        const float d = ua * m1, mm = m1 * m0;
+        float lqs, d_c1, d_c0, dpsi1, dpsi0, b1, la1 = 0.0f, lb1 = 0.0f, la0 = 0.0f, lb0 = 0.0f, rice1 = 0.0f, rice0 = 0.0f;
+        bool have_logs = false;
+        Lp1 pa, pb;
+        if (big || S > 16.0f) {
+            pa = lp1_parts(ua, x * (1.0f + e));
+            pb = lp1_parts(ub, y * (1.0f + ie));
+        }
+        if (big) {
+            // Rice expansion of the bulk regime (below): here the draw is in a tail, d is not small
+            const float it = site_rcp(S), i1 = it * (1.0f + e), i0 = it * (1.0f + ie);
+            const float Gs = m0 * pa.F + m1 * pb.F;
+            const float E = pow_m32_m1(Gs);
+            const float h = 0.5f * d * site_rcp(mm);
+            const float Ba = pa.A + E + pa.A * E - h * (m0 - 2.0f * m1);
+            const float Bb = pb.A + E + pb.A * E + h * (m1 - 2.0f * m0);
+            const float w = mm * site_rcp(S * d * d);
+            const float stir = (1.0f + i1 * (0.0833333333f + i1 * 0.00347222222f)) * (1.0f + i0 * (0.0833333333f + i0 * 0.00347222222f))
+                             * site_rcp(1.0f + it * (0.0833333333f + it * 0.00347222222f));
+            rice1 = stir * x * site_rcp(c1) * (1.0f + (pa.A - w * Ba));
+            rice0 = stir * y * site_rcp(c0) * (1.0f + (pb.A - w * Bb));
+        }
+        if (S <= 16.0f) {
+            float lgt, pt, lg1, p1, lg0, p0;
+            lgamma_digamma_f32(S, lgt, pt);
+            lgamma_digamma_f32(c1, lg1, p1);
+            lgamma_digamma_f32(c0, lg0, p0);
+            dpsi1 = pt - p1;
+            dpsi0 = pt - p0;
+            d_c1 = lx + dpsi1;
+            d_c0 = ly + dpsi0;
+            lqs = (c1 - 1.0f) * lx + (c0 - 1.0f) * ly + lgt - lg1 - lg0;
+            b1 = m1 * d_c1 + m0 * d_c0;
+        } else if (big) {
+            const float it = site_rcp(S), i1 = it * (1.0f + e), i0 = it * (1.0f + ie);
+            const float q1 = stirling_q(i1), q0 = stirling_q(i0), qt = stirling_q(it);
+            const float lm1 = -log1pf(e), lm0 = -log1pf(ie), lt = logf(S);
+            const float kl = m1 * pa.f + m0 * pb.f;
+            lqs = -S * kl - (lm1 + pa.l) - (lm0 + pb.l) + 0.5f * (lt + lm1 + lm0) - kSiteHalfLn2Pi
+                  + stirling_r(it) - stirling_r(i1) - stirling_r(i0);
+            d_c1 = pa.l + q1 - qt;
+            d_c0 = pb.l + q0 - qt;
+            dpsi1 = q1 - qt - lm1;
+            dpsi0 = q0 - qt - lm0;
+            b1 = m1 * q1 + m0 * q0 - qt - kl;
+            have_logs = true;
+            lb1 = pa.l; la1 = lt - lb1; lb0 = pb.l; la0 = lt - lb0;
+        } else if (c1 <= 6.0f) {
+            const float lm0 = -log1pf(ie), lt = logf(S);
+            const BetaLopsided o = beta_density_lopsided(c1, c0, S, x, lx, ua, pb, m1, m0, lm0);
+            lqs = o.lqs; d_c1 = o.d_cs; d_c0 = o.d_cb; dpsi1 = o.dpsi_s; dpsi0 = o.dpsi_b; b1 = o.b1;
+            have_logs = true;
+            lb1 = pa.l; la1 = lt - lb1; lb0 = pb.l; la0 = lt - lb0;
+        } else {
+            const float lm1 = -log1pf(e), lt = logf(S);
+            const BetaLopsided o = beta_density_lopsided(c0, c1, S, y, ly, ub, pa, m0, m1, lm1);
+            lqs = o.lqs; d_c0 = o.d_cs; d_c1 = o.d_cb; dpsi0 = o.dpsi_s; dpsi1 = o.dpsi_b; b1 = o.b1;
+            have_logs = true;
+            lb1 = pa.l; la1 = lt - lb1; lb0 = pb.l; la0 = lt - lb0;
+        }
+        const double y01d = 1.0 - x01d;
         float bg1, bg0;
-        if (!beta_grad_f32(x, y, lx, ly, c1, S, p1, pt, bg1) || !beta_grad_f32(y, x, ly, lx, c0, S, p0, pt, bg0)) return SITE_FALLBACK;
+        if (!beta_grad_tierb(x01d, y01d, lx, ly, c1, c0, S, dpsi1, d_c1, have_logs, la1, lb1, big, rice1, bg1) ||
+            !beta_grad_tierb(y01d, x01d, ly, lx, c0, c1, S, dpsi0, d_c0, have_logs, la0, lb0, big, rice0, bg0)) return SITE_FALLBACK;
         const float dv_dc1 = scale * y * bg1, dv_dc0 = -scale * x * bg0;
-        const float km = S * m1 * m0, k1 = m1 * sz, k0 = m0 * sz;
         sample = (float)(lod + (hid - lod) * variate);
-        rec[SO_LQ] = (c1 - 1.0f) * lx + (c0 - 1.0f) * ly + lgt - lg1 - lg0 - logf(scale);
-        rec[SO_DQ] = ((c1 - 1.0f) * site_rcp(x) - (c0 - 1.0f) * site_rcp(y)) * site_rcp(scale);
-        rec[SO_A0] = (dv_dc1 - dv_dc0) * km;
-        rec[SO_B0] = (d_c1 - d_c0) * km;
-        rec[SO_A1] = dv_dc1 * k1 + dv_dc0 * k0;
-        rec[SO_B1] = d_c1 * k1 + d_c0 * k0;
+        rec[SO_LQ] = lqs - logf(scale);
+        rec[SO_DQ] = (-S * d + (x - y)) * site_rcp(x * y * scale);
+        rec[SO_A0] = (dv_dc1 - dv_dc0) * (S * mm);
+        rec[SO_B0] = (d_c1 - d_c0) * (S * mm);
+        rec[SO_A1] = sz * (dv_dc1 * m1 + dv_dc0 * m0);
+        rec[SO_B1] = sz * b1;
         return SITE_DONE;
     }
     const float d = ua * m1;                                      // x - m1
@@ -408,6 +531,12 @@ TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const 
     rec[SO_B0] = S * mm * (d_c1 - d_c0);
     rec[SO_B1] = sz * (m1 * q1 + m0 * q0 - qt - kl);
     return SITE_DONE;
+}
+
+TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
+                         Philox* rng, double& variate, float& sample, float* rec, float* extra) {
+    int cls = 0;
+    return site_eval_fast_t<0>(s, u0, u1, ubm, ubs, mc, use_rng, rng, variate, sample, rec, extra, cls);
 }
 
 }  // namespace tq

@@ -206,20 +206,68 @@ __global__ void __launch_bounds__(kLocalBlock) site_kernel(const LocalArgs<T> a)
     if (s == S_B) write_presence_weights(a, site_gather(a, s, u32), (int64_t)u32);
 }
 
-__global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<float> a) {
-    const int s = blockIdx.y;
-    const uint32_t u32 = blockIdx.x * (uint32_t)kLocalBlock + threadIdx.x;
-    if (u32 >= (uint32_t)a.U) return;
-    const SiteInputs<float> in = site_gather(a, s, u32);
-    const bool use_rng = a.noise_in == nullptr;
-    Philox rng(a.seed, a.state->step, in.rng_offset);
-    double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
-    float v = 0.0f, rec[NSO], extra[NEX];
-    const int status = site_eval_fast(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra);
+// Two passes per block.  Pass 1: every thread draws its site's sample and classifies it; the bulk regime (what every site is
+// in at the initial point) is evaluated on the spot, the rest -- small concentrations of absent spots' guides, draws in the
+// tails, ... -- are compacted by regime class into shared memory.  Pass 2: the block's first threads replay those sites,
+// neighbours in the same regime.  (Without the compaction a trained model ran this kernel at 13.6 of 32 lanes per
+// instruction: every warp held a few sites of every regime and walked through all of them.)
+__device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int s, uint32_t u32, int status, float v, const float* rec,
+                                                 const float* extra) {
     if (status == SITE_DONE) site_scatter(a, s, (int64_t)u32, v, rec, extra);
     else if (a.worklist) a.worklist[atomicAdd(a.work_count, 1u)] = (uint32_t)s * (uint32_t)a.U + u32;
     else a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32] = nanf("");   // marker for site_fallback_kernel
-    if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
+}
+
+__global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<float> a) {
+    __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1];
+    __shared__ double s_var[kLocalBlock];
+    __shared__ unsigned char s_idx[kLocalBlock];
+    static_assert(kLocalBlock <= 256, "thread index stored in a byte");
+    const int s = blockIdx.y;
+    const uint32_t base = blockIdx.x * (uint32_t)kLocalBlock, u32 = base + threadIdx.x;
+    if (threadIdx.x < kSiteClasses) cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    int cls = 0;
+    unsigned int rank = 0u;
+    bool deferred = false;
+    double variate = 0.0;
+    if (u32 < (uint32_t)a.U) {
+        const SiteInputs<float> in = site_gather(a, s, u32);
+        const bool use_rng = a.noise_in == nullptr;
+        Philox rng(a.seed, a.state->step, in.rng_offset);
+        if (!use_rng) variate = (double)a.noise_in[(int64_t)s * a.U + u32];
+        float v = 0.0f, rec[NSO], extra[NEX];
+        const int status = site_eval_fast_t<1>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra, cls);
+        if (status == SITE_DEFER) {
+            deferred = true;
+            rank = atomicAdd(&cnt[cls], 1u);
+        } else {
+            site_fast_finish(a, s, u32, status, v, rec, extra);
+        }
+        if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
+    }
+    if (!__syncthreads_or(deferred)) return;   // every site was in the bulk regime (always so at the initial point)
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0u;
+#pragma unroll
+        for (int c = 0; c < kSiteClasses; ++c) { off[c] = acc; acc += cnt[c]; }
+        off[kSiteClasses] = acc;
+    }
+    __syncthreads();
+    if (deferred) {
+        const unsigned int pos = off[cls] + rank;
+        s_var[pos] = variate;
+        s_idx[pos] = (unsigned char)threadIdx.x;
+    }
+    __syncthreads();
+    if (threadIdx.x < off[kSiteClasses]) {
+        const uint32_t u = base + s_idx[threadIdx.x];
+        const SiteInputs<float> in = site_gather(a, s, u);
+        double var = s_var[threadIdx.x];
+        float v = 0.0f, rec[NSO], extra[NEX];
+        const int status = site_eval_fast_t<2>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, false, nullptr, var, v, rec, extra, cls);
+        site_fast_finish(a, s, u, status, v, rec, extra);
+    }
 }
 
 // A block scans kFallbackUPT * 128 markers of one site, compacts the hits into shared memory and then works through

@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "ksmogn_core.cuh"
 #include "ksmogn_fast.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace tq {
 
@@ -226,20 +228,40 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
     finish_pair(po, fc.rate, out);
 }
 
+// ---- streaming form of the production kernel -----------------------------------------------------------------
+// Persistent warps: every warp walks its own sequence of 4-patch groups and, while it sweeps one group, the next
+// group's pixels (49 x 8 B per patch) and its 15 per-patch scalars are already in flight into a per-slot staging
+// area (cp.async), so the HBM/L2 latency of a patch is hidden behind the previous patch's arithmetic instead of
+// stalling the warp at the head of every block (19 % of warp time in the one-block-per-16-patches form).
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int kParFloats = 16;   // h0 h1 w0 w1 x0 x1 y0 y1 | b W0 W1 W2 | W3 tx ty -
+template <bool PF> constexpr int stage_bytes() { return kParFloats * 4 + (PF ? 400 : 0); }   // 392 B of pixels, 16 B aligned slots
+
 template <typename PIX, int OC, bool P14, bool BWD, int MINB>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
-ksmogn_fast_kernel(const KsmognArgs<float> a) {
+ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ counters) {
+    constexpr bool PF = P14 && sizeof(PIX) == 2;
+    constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int O = a.v.O, offpad = (2 * O + 3) & ~3;
     float* off_s = reinterpret_cast<float*>(smem_raw);
-    float* off_w2 = off_s + a.v.O;
-    const int slot = threadIdx.x / kSub, sub = threadIdx.x % kSub;
-    float* gx = off_w2 + a.v.O + slot * (2 * kK * kMaxP);
+    float* off_w2 = off_s + O;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = threadIdx.x / kSub, sub = threadIdx.x % kSub, wslot = lane / kSub;
+    const int P = P14 ? 14 : a.v.P, PP = P * P;
+    float* gx = off_s + offpad + slot * (2 * kK * kMaxP);
     float* gy = gx + kK * kMaxP;
-    const int PPs = (P14 ? 14 * 14 : a.v.P * a.v.P);
-    // staged pixels of this slot's patch: all global loads of a patch are issued back to back up
-    // front instead of one dependent load per sweep (long-scoreboard stalls dominated before)
-    float* spx = off_w2 + a.v.O + kUnitsPerBlock * (2 * kK * kMaxP) + slot * PPs;
-    for (int j = threadIdx.x; j < a.v.O; j += blockDim.x) {
+    float* spx = off_s + offpad + kUnitsPerBlock * (2 * kK * kMaxP) + slot * PP;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(off_s + offpad + kUnitsPerBlock * (2 * kK * kMaxP + PP))
+                           + slot * stage_bytes<PF>();
+    for (int j = threadIdx.x; j < O; j += blockDim.x) {
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
         off_w2[j] = static_cast<const float*>(a.v.offset_logits)[j] * kLog2e;
     }
@@ -250,77 +272,117 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
     fc.log_rate = logf(fc.rate);
     __syncthreads();
 
-    const int P = P14 ? 14 : a.v.P, PP = P * P;
     const PIX* pixels = static_cast<const PIX*>(a.v.pixels);
     const float* xy = static_cast<const float*>(a.v.xy);
-    const int64_t n_groups = (a.U + kUnitsPerBlock - 1) / kUnitsPerBlock;
+    const unsigned U = (unsigned)a.U, n_wg = (U + 3u) >> 2;
+    const unsigned stride = gridDim.x * kWarpsPerBlock;
 
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int64_t u_raw = grp * kUnitsPerBlock + slot;
-        const bool live = u_raw < a.U;
-        const int64_t u = live ? u_raw : a.U - 1;   // idle slots shadow the last patch and write nothing
-        const UnitIndex ui = locate_unit(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
-        PatchSpots<float> s;
-        float norm[kK], iw[kK];
-        const float tx = xy[ui.patch * 2 + 0], ty = xy[ui.patch * 2 + 1];
+    // issue the copies of group g: this lane's share of its slot's patch and two of the slot's 15 scalars
+    auto prefetch = [&](unsigned g) {
+        const unsigned u_raw = g * 4u + wslot, u = u_raw < U ? u_raw : U - 1u;
+        const UnitIndex ui = locate_unit32(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        if (PF) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(pixels + ui.patch * 196);
 #pragma unroll
-        for (int k = 0; k < kK; ++k) {
-            s.h[k] = a.height[k * a.U + u];
-            s.w[k] = a.width[k * a.U + u];
-            s.cx[k] = a.x[k * a.U + u] + tx;
-            s.cy[k] = a.y[k * a.U + u] + ty;
-            iw[k] = 1.0f / s.w[k];
-            norm[k] = 0.15915494309189535f * iw[k] * iw[k];
-        }
-        s.b = a.background[u];
-        float W[kM], Wr[kM];
-#pragma unroll
-        for (int m = 0; m < kM; ++m) {
-            W[m] = BWD ? a.W[m * a.U + u] : 0.0f;
-            Wr[m] = W[m] * fc.rate;
-        }
-
-        // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
-        __syncwarp();
-        float pix_min = 3.0e38f;   // smallest pixel of the patch (this lane's share): selects the no-clamp pair form
-        {
-            const PIX* src = pixels + ui.patch * PP;
-            if (P14 && sizeof(PIX) == 2) {
-                // 196 uint16 = 49 x 8 bytes, 8-byte aligned (392 B per patch)
-                const uint2* v = reinterpret_cast<const uint2*>(src);
-#pragma unroll
-                for (int t = 0; t < 7; ++t) {
-                    const int i = sub + t * kSub;
-                    if (i < 49) {
-                        const uint2 q = __ldg(v + i);
-                        const float p0 = float(q.x & 0xffffu), p1 = float(q.x >> 16), p2 = float(q.y & 0xffffu), p3 = float(q.y >> 16);
-                        spx[4 * i + 0] = p0;
-                        spx[4 * i + 1] = p1;
-                        spx[4 * i + 2] = p2;
-                        spx[4 * i + 3] = p3;
-                        pix_min = fminf(pix_min, fminf(fminf(p0, p1), fminf(p2, p3)));
-                    }
-                }
-            } else {
-                for (int p = sub; p < PP; p += kSub) {
-                    const float pv = float(src[p]);
-                    spx[p] = pv;
-                    pix_min = fminf(pix_min, pv);
-                }
+            for (int t = 0; t < 7; ++t) {
+                const int i = sub + t * kSub;
+                if (i < 49) cp_async_8(stage + kParFloats * 4 + 8 * i, src + 8 * i);
             }
         }
-        for (int idx = sub; idx < 2 * kK * P; idx += kSub) {
-            const int axis = idx / (kK * P), rem = idx - axis * (kK * P);
-            const int k = rem / P, i = rem - k * P;
-            const float c = axis == 0 ? s.cx[k] : s.cy[k];
-            const float d = float(i) - c;
-            (axis == 0 ? gx : gy)[k * kMaxP + i] = __expf(-0.5f * (d * d) * (iw[k] * iw[k]));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = sub + r * kSub;
+            const float* src;
+            if (j < 8) {
+                const float* base = j < 2 ? a.height : j < 4 ? a.width : j < 6 ? a.x : a.y;
+                src = base + (size_t)(j & 1) * U + u;
+            } else if (j == 8) {
+                src = a.background + u;
+            } else if (j < 13) {
+                src = BWD ? a.W + (size_t)(j - 9) * U + u : nullptr;
+            } else {
+                src = xy + ui.patch * 2 + (j - 13);
+            }
+            if (j < 15 && src) cp_async_4(stage + 4 * j, src);
+        }
+    };
+
+    // first group by position (no dependent atomic at the head of the kernel); later ones from the counter, which
+    // counts the groups handed out beyond the first `stride`
+    unsigned cur = blockIdx.x * kWarpsPerBlock + warp, pending = 0;
+    if (lane == 0) pending = stride + atomicAdd(counters, 1u);
+    if (cur < n_wg) prefetch(cur);
+
+    while (cur < n_wg) {
+        const unsigned u_raw = cur * 4u + wslot;
+        const bool live = u_raw < U;
+        const unsigned u = live ? u_raw : U - 1u;   // idle slots shadow the last patch and write nothing
+        cp_async_wait_all();
+        __syncwarp();
+        PatchSpots<float> s;
+        float W[kM], Wr[kM], tx, ty;
+        {
+            const float4* par = reinterpret_cast<const float4*>(stage);
+            const float4 p0 = par[0], p1 = par[1], p2 = par[2], p3 = par[3];
+            s.h[0] = p0.x; s.h[1] = p0.y; s.w[0] = p0.z; s.w[1] = p0.w;
+            tx = p3.y; ty = p3.z;
+            s.cx[0] = p1.x + tx; s.cx[1] = p1.y + tx; s.cy[0] = p1.z + ty; s.cy[1] = p1.w + ty;
+            s.b = p2.x;
+            W[0] = BWD ? p2.y : 0.0f; W[1] = BWD ? p2.z : 0.0f; W[2] = BWD ? p2.w : 0.0f; W[3] = BWD ? p3.x : 0.0f;
+        }
+#pragma unroll
+        for (int m = 0; m < kM; ++m) Wr[m] = W[m] * fc.rate;
+        float pix_min = 3.0e38f;   // smallest pixel of the patch (this lane's share): selects the no-clamp pair form
+        if (PF) {
+            const uint2* raw = reinterpret_cast<const uint2*>(stage + kParFloats * 4);
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const int i = sub + t * kSub;
+                if (i < 49) {
+                    const uint2 q = raw[i];
+                    const float4 v = make_float4(float(q.x & 0xffffu), float(q.x >> 16), float(q.y & 0xffffu), float(q.y >> 16));
+                    reinterpret_cast<float4*>(spx)[i] = v;
+                    pix_min = fminf(pix_min, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+                }
+            }
+        } else {
+            const UnitIndex ui = locate_unit32(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+            const PIX* src = pixels + ui.patch * PP;
+            for (int p = sub; p < PP; p += kSub) {
+                const float pv = float(src[p]);
+                spx[p] = pv;
+                pix_min = fminf(pix_min, pv);
+            }
+        }
+        __syncwarp();   // the staging area has been read by every lane: the next group may land in it
+        const unsigned nxt = __shfl_sync(kFull, pending, 0);   // asked for one group ago: the atomic's latency is hidden
+        if (lane == 0) pending = stride + atomicAdd(counters, 1u);
+        if (nxt < n_wg) prefetch(nxt);
+
+        // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
+        float norm[kK];
+        {
+            float c2[kK];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                const float iw = rcp_newton(s.w[k]);
+                norm[k] = 0.15915494309189535f * iw * iw;
+                c2[k] = (-0.5f * kLog2e) * iw * iw;
+            }
+            for (int i = sub; i < P; i += kSub) {
+                const float fi = float(i);
+#pragma unroll
+                for (int k = 0; k < kK; ++k) {
+                    const float dx = fi - s.cx[k], dy = fi - s.cy[k];
+                    gx[k * kMaxP + i] = f_ex2(c2[k] * dx * dx);
+                    gy[k * kMaxP + i] = f_ex2(c2[k] * dy * dy);
+                }
+            }
         }
         __syncwarp();
 
         PatchOut<float, kM> out;
         out.zero();
-        const PIX* pix = pixels + ui.patch * PP;
         // a = image/gain is smallest without spots: one test per patch selects the Stirling variant
         const bool small = s.b * fc.rate < 4.0f;
         bool pairs = false;
@@ -328,14 +390,14 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
             // every pixel above every offset (no -inf handling needed) and no small concentration anywhere in the warp
             float max_off = off_s[0];
             for (int j = 1; j < OC; ++j) max_off = fmaxf(max_off, off_s[j]);
-            pairs = __all_sync(0xffffffffu, !small && pix_min > max_off);
+            pairs = __all_sync(kFull, !small && pix_min > max_off);
         }
         if (pairs)
             sweep_patch_pairs<OC>(spx, sub, gx, gy, s, norm, fc, off_s, off_w2, W, out);
-        else if (__any_sync(0xffffffffu, small))
-            sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);
+        else if (__any_sync(kFull, small))
+            sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
         else
-            sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, fc, a.v.O, off_s, off_w2, W, Wr, out);
+            sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
 
 #pragma unroll
         for (int m = 0; m < kM; ++m) out.logp[m] = sub_sum(out.logp[m]);
@@ -354,47 +416,79 @@ ksmogn_fast_kernel(const KsmognArgs<float> a) {
         if (live && sub == 0) {
             if (a.logp) {
 #pragma unroll
-                for (int m = 0; m < kM; ++m) a.logp[m * a.U + u] = out.logp[m];
+                for (int m = 0; m < kM; ++m) a.logp[(size_t)m * U + u] = out.logp[m];
             }
             if (BWD) {
                 a.g_background[u] = out.g_b;
                 a.g_rate[u] = out.g_rate;
 #pragma unroll
                 for (int k = 0; k < kK; ++k) {
-                    a.g_height[k * a.U + u] = out.g_h[k];
-                    a.g_width[k * a.U + u] = out.g_w[k];
-                    a.g_x[k * a.U + u] = out.g_x[k];
-                    a.g_y[k * a.U + u] = out.g_y[k];
+                    a.g_height[(size_t)k * U + u] = out.g_h[k];
+                    a.g_width[(size_t)k * U + u] = out.g_w[k];
+                    a.g_x[(size_t)k * U + u] = out.g_x[k];
+                    a.g_y[(size_t)k * U + u] = out.g_y[k];
                 }
             }
+        }
+        cur = nxt;
+    }
+    if (lane == 0) {
+        // the last warp out re-arms the counters for the next launch on this stream
+        __threadfence();
+        const unsigned done = atomicAdd(counters + 1, 1u);
+        if (done == stride - 1u) {
+            counters[0] = 0u;
+            counters[1] = 0u;
         }
     }
 }
 
-template <typename PIX, int OC, bool P14, bool BWD, int MINB>
-static int launch_fast_b(const KsmognArgs<float>& a, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (2 * (size_t)a.v.O + kUnitsPerBlock * (2 * kK * kMaxP + (size_t)a.v.P * a.v.P));
-    auto kern = ksmogn_fast_kernel<PIX, OC, P14, BWD, MINB>;
-    if (smem > 48 * 1024) {
-        int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                              "cudaFuncSetAttribute(ksmogn_fast)");
-        if (st2 != TQ_OK) return st2;
-    }
-    // one block per 16 patches, no persistence: equal-cost blocks + the hardware block scheduler balance
-    // better than a capped grid (2.64 static iterations per block left the last wave 64 % full)
-    const int64_t blocks_needed = (a.U + kUnitsPerBlock - 1) / kUnitsPerBlock;
-    const int64_t cap = 0x7fffffff;
-    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
-    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
-    TQ_LAUNCH_CHECK("ksmogn_fast_kernel launch");
-    return TQ_OK;
+// Work counters of the kernel above: {groups handed out beyond the first per warp, warps finished}, re-armed by the
+// kernel itself.  One set per stream (launches on a stream are ordered, so they can share; launches on different streams
+// may overlap and must not).
+constexpr int kCounterSets = 64;
+__device__ unsigned int g_stream_counters[kCounterSets][2];
+
+static int counter_set_of(cudaStream_t st) {
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, int> sets;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = sets.find(st);
+    if (it != sets.end()) return it->second;
+    const int k = (int)(sets.size() % kCounterSets);   // more than 64 live streams: sets are shared again
+    sets.emplace(st, k);
+    return k;
 }
 
 template <typename PIX, int OC, bool P14, bool BWD>
 static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
-    // 4 resident blocks per SM (<= 128 registers): measured 115 us at C2 against 118 / 124 us when the single-bin
-    // form is squeezed to 5 / 6 blocks -- the FMA pipe, not latency, is what the sweep waits for
-    return launch_fast_b<PIX, OC, P14, BWD, 4>(a, st);
+    constexpr bool PF = P14 && sizeof(PIX) == 2;
+    constexpr int MINB = 4;   // 4 resident blocks per SM (<= 128 registers): 5 / 6 blocks measured slower (spills)
+    if (a.U > 0x7fffffff) {
+        set_error("ksmogn: %lld patches in one launch (limit 2^31 - 1)", (long long)a.U);
+        return TQ_ERR_ARG;
+    }
+    const int PP = a.v.P * a.v.P, offpad = (2 * a.v.O + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)offpad + kUnitsPerBlock * (2 * kK * kMaxP + (size_t)PP)) +
+                        (size_t)kUnitsPerBlock * stage_bytes<PF>();
+    auto kern = ksmogn_stream_kernel<PIX, OC, P14, BWD, MINB>;
+    if (smem > 48 * 1024) {
+        int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                              "cudaFuncSetAttribute(ksmogn_stream)");
+        if (st2 != TQ_OK) return st2;
+    }
+    void* base = nullptr;
+    int st2 = cuda_status(cudaGetSymbolAddress(&base, g_stream_counters), "cudaGetSymbolAddress(g_stream_counters)");
+    if (st2 != TQ_OK) return st2;
+    unsigned int* counters = static_cast<unsigned int*>(base) + 2 * counter_set_of(st);
+    // one resident wave of persistent warps; groups beyond each warp's first are handed out dynamically, so SMs that
+    // run slower (a neighbour kernel on the side stream, clock differences) simply take fewer
+    const int64_t n_wg = (a.U + 3) / 4, blocks_needed = (n_wg + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = (int64_t)sm_count() * MINB;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    kern<<<grid, kWarpsPerBlock * 32, smem, st>>>(a, counters);
+    TQ_LAUNCH_CHECK("ksmogn_stream_kernel launch");
+    return TQ_OK;
 }
 
 template <typename PIX, bool BWD>

@@ -27,6 +27,16 @@ inline float f_ex2(float x) { return exp2f(x); }
 inline float f_rcp(float x) { return 1.0f / x; }
 #endif
 
+// reciprocal without the denormal/overflow slow path of 1.0f / x (arguments are widths, heights: normal numbers)
+TQ_HD float rcp_newton(float x) {
+#ifdef __CUDA_ARCH__
+    const float r = f_rcp(x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+
 constexpr float kLn2 = 0.69314718055994530942f;
 constexpr float kLog2e = 1.44269504088896340736f;
 constexpr float kHalfLn2Pi = 0.91893853320467274178f;
@@ -335,7 +345,7 @@ struct SingleBinConst {
 TQ_HD SingleBinConst single_bin_const(float b, const FastConst& fc) {
     SingleBinConst c;
     c.a0 = b * fc.rate;
-    const float ia = 1.0f / c.a0, la0 = logf(c.a0);
+    const float ia = rcp_newton(c.a0), la0 = logf(c.a0);
     float r, q;
     stirling(ia, r, q);
     c.la0p1 = la0 + 1.0f;
@@ -452,8 +462,8 @@ TQ_HD void finish_spot_moments(const PatchSpots<float>& s, PatchOut<float, kM>& 
 #pragma unroll
     for (int k = 0; k < kK; ++k) {
         const float A0 = out.g_h[k], A3 = out.g_w[k];
-        const float iw = 1.0f / s.w[k], iw2 = iw * iw;
-        out.g_h[k] = A0 / s.h[k];
+        const float iw = rcp_newton(s.w[k]), iw2 = iw * iw;
+        out.g_h[k] = A0 * rcp_newton(s.h[k]);
         out.g_x[k] *= iw2;
         out.g_y[k] *= iw2;
         out.g_w[k] = iw * (iw2 * A3 - 2.0f * A0);

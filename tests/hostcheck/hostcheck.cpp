@@ -490,12 +490,54 @@ int hc_site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const Mod
     for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
     return status;
 }
+// the two-pass form site_fast_kernel runs (MODE 1: draw + classify + bulk regime; MODE 2: replay of a deferred site), RNG mode;
+// out as above, returns the final status, *deferred_cls = regime class or -1 when pass 1 finished the site
+int hc_site_eval_fast_split(int s, float u0, float u1, float ubm, float ubs, const ModelConst* mc, uint64_t seed, double* out, int* deferred_cls,
+                            double* variate_out) {
+    Philox rng(seed, 11ull, ((uint64_t)(s + 1) << 8));
+    float rec[NSO], ex[NEX] = {0, 0, 0, 0}, v = 0.0f;
+    double variate = 0.0;
+    int cls = -1;
+    int status = site_eval_fast_t<1>(s, u0, u1, ubm, ubs, *mc, true, &rng, variate, v, rec, ex, cls);
+    *deferred_cls = -1;
+    if (status == SITE_DEFER) {
+        *deferred_cls = cls;
+        status = site_eval_fast_t<2>(s, u0, u1, ubm, ubs, *mc, false, nullptr, variate, v, rec, ex, cls);
+    }
+    *variate_out = variate;
+    out[0] = v;
+    for (int j = 0; j < NSO; ++j) out[1 + j] = rec[j];
+    for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
+    return status;
+}
+// ... and the one-call form on the same RNG stream
+int hc_site_eval_fast_rng(int s, float u0, float u1, float ubm, float ubs, const ModelConst* mc, uint64_t seed, double* out, double* variate_out) {
+    Philox rng(seed, 11ull, ((uint64_t)(s + 1) << 8));
+    float rec[NSO], ex[NEX] = {0, 0, 0, 0}, v = 0.0f;
+    double variate = 0.0;
+    const int status = site_eval_fast(s, u0, u1, ubm, ubs, *mc, true, &rng, variate, v, rec, ex);
+    *variate_out = variate;
+    out[0] = v;
+    for (int j = 0; j < NSO; ++j) out[1 + j] = rec[j];
+    for (int j = 0; j < NEX; ++j) out[1 + NSO + j] = ex[j];
+    return status;
+}
 // status of the production form for one RNG-mode evaluation (profiles/fallback_probe.py)
 int hc_site_status_rng(int s, float u0, float u1, float ubm, float ubs, const ModelConst* mc, uint64_t seed) {
     Philox rng(seed, 11ull, ((uint64_t)(s + 1) << 8));
     double variate = 0.0;
     float rec[NSO], ex[NEX], v = 0.0f;
     return site_eval_fast(s, u0, u1, ubm, ubs, *mc, true, &rng, variate, v, rec, ex);
+}
+// the same for n sites at once, returning the base draws too (profiles/site_regimes.py)
+void hc_site_status_batch(int s, int n, const float* u0, const float* u1, const float* ubm, const float* ubs, const ModelConst* mc,
+                          uint64_t seed, int* status, double* variate) {
+    for (int i = 0; i < n; ++i) {
+        Philox rng(seed, 11ull, ((uint64_t)(i + 1) << 12) + ((uint64_t)(s + 1) << 8));
+        float rec[NSO], ex[NEX], v = 0.0f;
+        variate[i] = 0.0;
+        status[i] = site_eval_fast(s, u0[i], u1[i], ubm ? ubm[i] : 0.0f, ubs ? ubs[i] : 0.0f, *mc, true, &rng, variate[i], v, rec, ex);
+    }
 }
 // RNG-mode draws through the production form (falls back like site_kernel<float>)
 void hc_site_draws_fast(int s, float u0, float u1, const ModelConst* mc, uint64_t seed, int n, double* out) {

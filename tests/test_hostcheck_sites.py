@@ -128,3 +128,91 @@ def test_rng_draws_through_fast_path_have_the_right_moments():
     var = 15.0 ** 2 * m1 * (1 - m1) / 401.0
     assert abs(out.mean() - 1.5) < 5 * np.sqrt(var / n)
     assert abs(out.var() / var - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("site", [3, 6])   # width, x
+@pytest.mark.parametrize("regime", ["tails", "tails_large", "lopsided", "lopsided_far", "small_series"])
+def test_beta_sites_outside_the_bulk(site, regime):
+    """What a TRAINED model sends outside the reformulated bulk regime (profiles/site_regimes.py): draws in the tails of
+    moderately concentrated guides (series in double on one side, Rice on the other), guides pushed against an edge of
+    their interval (one concentration <= 6 with total > 64) and the small-x series with beta x >= 2."""
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    seed = {"tails": 1, "tails_large": 2, "lopsided": 3, "lopsided_far": 4, "small_series": 5}[regime] * 10 + site
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed + 1000)
+    n = 3000
+    U = lambda lo, hi: torch.empty(n).uniform_(lo, hi, generator=g).double()
+    if regime in ("tails", "tails_large"):
+        u1 = U(2.5, 4.1) if regime == "tails" else U(4.2, 8.0)
+        u0 = U(-1.5, 1.5)
+        widen = 0.12 if regime == "tails" else 0.03          # draws from a much flatter Beta: mostly tails of the guide
+    elif regime in ("lopsided", "lopsided_far"):
+        u1 = U(2.7, 9.0) if regime == "lopsided" else U(4.2, 9.0)
+        u0 = (U(2.0, 5.0) if regime == "lopsided" else U(5.0, 9.0)) * torch.where(U(0, 1) < 0.5, -1.0, 1.0)
+        widen = 1.0
+    else:
+        u1 = U(0.5, 4.1)
+        u0 = U(-2.5, 2.5)
+        widen = 1.0
+    S = 2 + torch.exp(u1.float().double())
+    m1 = torch.sigmoid(u0.float().double())
+    var = torch.distributions.Beta(widen * S * m1, widen * S * (1 - m1)).sample().float().double().clamp(1e-7, 1 - 1e-7)   # closer to a bound the float sample is clamped anyway
+    if regime == "tails_large":
+        t = U(0.05, 2.6) / S                                 # total x (1 - x) around / below ATen's 2.5 and 0.75 boundaries
+        var = torch.where(U(0, 1) < 0.5, t, 1 - t).float().double()
+    z = np.zeros(n)
+    ref, fast, status = _run(hc, mc, site, u0.numpy(), u1.numpy(), z, z, var.numpy())
+    x, c1, c0 = var.numpy(), (S * m1).numpy(), (S * (1 - m1)).numpy()
+    bulk = (c1 > 6) & (c0 > 6) & (S.numpy() * x * (1 - x) >= 2.5)
+    assert (~bulk).mean() > 0.25, "the batch is meant to sit outside the bulk regime"
+    ok = status == 0
+    sane = np.minimum(c1, c0) > 0.3        # below that the draws underflow fp32 (x ~ u^(1/c)): the double form's business
+    assert ok[sane].mean() >= 0.995, f"only {ok[sane].mean():.3f} of the sites took the fp32 path"
+    # entry by entry here (a tail draw's log q is tens of times the typical one), relative to the entry or -- for entries
+    # that pass through zero -- to the batch's typical size: 1e-5, the north-star bound.  Three outputs are differences
+    # that cancel in ANY fp32 evaluation from fp32 parameters (d log q / d sample ~ (c1 - 1)/x - (c0 - 1)/y at c1 -> 1;
+    # d sample / d size = m1 dx/dc1 + m0 dx/dc0, ten- to thirty-fold for lopsided guides; likewise d log q / d size):
+    # for those, 1e-5 on all but a few percent of the entries and 5e-5 on the rest.
+    bad = {}
+    keep = ok & ~bulk & sane
+    for j in range(7):
+        r, f = ref[keep, j], fast[keep, j]
+        err = np.abs(f - r) / np.maximum(np.abs(r), np.median(np.abs(r)))
+        if NAMES[j] == "LQ":
+            # a sum of lgamma-sized terms (tens) that feeds only the ELBO value, where it is one of ~10 per unit next to
+            # a likelihood term of order -1000: judged against that sum's scale
+            err = np.abs(f - r) / np.maximum(np.abs(r), 10.0)
+        loose = NAMES[j] in ("DQ", "A1", "B1")
+        if not (err.max() < (5e-5 if loose else 1e-5) and np.mean(err > 1e-5) < 0.03):
+            i = err.argmax()
+            bad[NAMES[j]] = (err.max(), float(np.mean(err > 1e-5)), r[i], f[i], c1[keep][i], c0[keep][i], x[keep][i])
+    assert not bad, bad
+
+
+def test_two_pass_form_equals_the_one_call_form():
+    """site_fast_kernel evaluates the bulk regime in a first pass and replays the other sites, compacted by regime class, in
+    a second (site_eval_fast_t<1> / <2>): same draws, same outputs as the one-call form, and every class is exercised."""
+    hc = hostcheck.load()
+    mc = L.ModelConst.make(O.DEFAULT_PRIORS, 14, torch.float64)
+    hc.hc_site_eval_fast_split.restype = ctypes.c_int
+    hc.hc_site_eval_fast_rng.restype = ctypes.c_int
+    g = np.random.default_rng(0)
+    a, b = (ctypes.c_double * NOUT)(), (ctypes.c_double * NOUT)()
+    va, vb, cls = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    seen = {"gamma": set(), "beta": set()}
+    for i in range(6000):
+        s = int(g.integers(0, 9))
+        if s < 3:
+            lc = g.uniform(-1.0, 9.0); u1 = g.uniform(-7, 1); u0 = lc - u1
+            ubm = u0 + 0.1 * g.normal(); ubs = ubm - g.uniform(0.5, 3.0)
+        else:
+            u0 = g.uniform(-6, 6) if i % 3 == 0 else g.uniform(-1.5, 1.5); u1 = g.uniform(-1, 9); ubm = ubs = 0.0
+        args = (s, ctypes.c_float(u0), ctypes.c_float(u1), ctypes.c_float(ubm), ctypes.c_float(ubs), ctypes.byref(mc), ctypes.c_uint64(i))
+        st2 = hc.hc_site_eval_fast_split(*args, a, ctypes.byref(cls), ctypes.byref(va))
+        st1 = hc.hc_site_eval_fast_rng(*args, b, ctypes.byref(vb))
+        assert st1 == st2 and va.value == vb.value, (i, s, st1, st2)
+        if st1 == 0:
+            assert list(a) == list(b), (i, s, cls.value, list(a), list(b))
+        seen["gamma" if s < 3 else "beta"].add(cls.value)
+    assert seen["gamma"] >= {-1, 0, 1} and seen["beta"] >= {-1, 0, 1, 2, 3}, seen
