@@ -218,7 +218,8 @@ __device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int 
     else a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32] = nanf("");   // marker for site_fallback_kernel
 }
 
-__global__ void __launch_bounds__(kLocalBlock) site_fast_kernel(const LocalArgs<float> a) {
+// (8 resident blocks per SM = 64 registers, no spills: 5 us faster on a trained model than 6 blocks at 71 registers)
+__global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalArgs<float> a) {
     __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1];
     __shared__ double s_var[kLocalBlock];
     __shared__ unsigned char s_idx[kLocalBlock];
