@@ -1296,9 +1296,38 @@ extern "C" int tq_step_advance(void* state, void* stream) {
 }
 
 // ---- minibatch subsampling (pyro.plate(subsample_size=...) [third party]: randperm(size)[:n]) -----------
-// Partial Fisher-Yates on a persistent permutation: after n_pick swaps the first n_pick entries are
-// a uniform sample without replacement whatever permutation the array held before.
+// A uniform ordered sample without replacement = the n_pick smallest of n_total i.i.d. random keys, in key order.
+// Every block derives all keys (Philox keyed by (seed, stream, step), counter = element) into shared memory and each
+// thread ranks its own element against them (shared-memory broadcast reads): a few microseconds for the sizes of a
+// minibatch axis, where a serial Fisher-Yates took 85 us for 512 of 1000 frames -- most of the reference-default
+// 10 x 512 step.  Axes longer than kSubsampleMaxRank keep the serial partial Fisher-Yates on a persistent permutation
+// (after n_pick swaps the first n_pick entries are a uniform sample whatever permutation the array held before).
 namespace tq {
+constexpr int kSubsampleMaxRank = 16384;
+constexpr int kSubsampleBlock = 256;
+
+__global__ void __launch_bounds__(kSubsampleBlock) subsample_rank_kernel(int n_total, int n_pick, unsigned long long seed,
+                                                                         const StepState* state, unsigned long long stream_id,
+                                                                         int32_t* __restrict__ out) {
+    extern __shared__ unsigned int keys[];
+    const unsigned long long sd = seed ^ (0x9E3779B97F4A7C15ull * (stream_id + 1ull)), step = state->step;
+    for (int j = threadIdx.x; j < n_total; j += kSubsampleBlock) {
+        Philox rng(sd, step, (unsigned long long)j);
+        keys[j] = rng.next();
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kSubsampleBlock + threadIdx.x;
+    if (i >= n_total) return;
+    const unsigned int ki = keys[i];
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < n_total; ++j) {
+        const unsigned int kj = keys[j];
+        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;   // ties (2^-32 per pair) broken by position
+    }
+    if (rank < n_pick) out[rank] = i;
+}
+
 __global__ void subsample_kernel(int n_total, int n_pick, unsigned long long seed, const StepState* state,
                                  unsigned long long stream_id, int32_t* __restrict__ perm, int32_t* __restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -1314,13 +1343,26 @@ __global__ void subsample_kernel(int n_total, int n_pick, unsigned long long see
 }
 }  // namespace tq
 
-// perm: (n_total,) int32 scratch holding a permutation of 0..n_total-1 (initialise to arange once);
-// out: (n_pick,) int32.  stream_id separates independent draws (AOIs vs frames, ranks).
+// perm: (n_total,) int32 scratch holding a permutation of 0..n_total-1 (initialise to arange once; only touched when
+// n_total > 16384); out: (n_pick,) int32.  stream_id separates independent draws (AOIs vs frames, ranks).
 extern "C" int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* state, uint64_t stream_id, void* perm,
                             void* out, void* stream) {
     TQ_CHECK_ARG(n_total >= 1 && n_pick >= 0 && n_pick <= n_total, "bad sizes");
     TQ_CHECK_ARG(state && perm && out, "NULL pointer");
     if (n_pick == 0) return TQ_OK;
+    if (n_total <= tq::kSubsampleMaxRank) {
+        const size_t smem = sizeof(unsigned int) * (size_t)n_total;
+        if (smem > 48 * 1024) {
+            int st2 = tq::cuda_status(cudaFuncSetAttribute(tq::subsample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                      "cudaFuncSetAttribute(subsample_rank)");
+            if (st2 != TQ_OK) return st2;
+        }
+        const int grid = (n_total + tq::kSubsampleBlock - 1) / tq::kSubsampleBlock;
+        tq::subsample_rank_kernel<<<grid, tq::kSubsampleBlock, smem, (cudaStream_t)stream>>>(n_total, n_pick, seed, (const tq::StepState*)state,
+                                                                                           stream_id, (int32_t*)out);
+        TQ_LAUNCH_CHECK("subsample_rank_kernel launch");
+        return TQ_OK;
+    }
     tq::subsample_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_total, n_pick, seed, (const tq::StepState*)state, stream_id,
                                                           (int32_t*)perm, (int32_t*)out);
     TQ_LAUNCH_CHECK("subsample_kernel launch");
