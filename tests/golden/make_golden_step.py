@@ -1,0 +1,147 @@
+"""
+Generates tests/golden/ref_step.pt by running the REFERENCE's own model code in the build container.
+
+Run as:  python tests/golden/make_golden_step.py    (needs /root/reference; never runs on the GPU box)
+
+Executed verbatim from /root/reference (nothing is copied into the repository, only numeric outputs are stored):
+  tapqir/models/cosmos.py        cosmos.__init__, init_parameters/_init_parameters (:464-598), guide (:329-462),
+                                 model (:82-327), TraceELBO (:600-607)
+  tapqir/models/model.py         Model.__init__/to/Q, Model.init (:153-186) and the loop body ``self.svi.step()`` (:212)
+  tapqir/utils/dataset.py        CosmosDataset, OffsetData (fetch, median, offset mean / logits)
+  tapqir/distributions/*.py      util.py, ksmogn.py (torch branch, use_pykeops=False), affine_beta.py
+Third-party packages that are absent and not installable here (pyro-ppl, pyroapi, pykeops; funsor is only imported by
+``tapqir/distributions/__init__.py``, which is bypassed) are replaced by tests/golden/minipyro.py, a restatement of the
+Pyro semantics this code touches.  So the model/guide/parameter code is the reference's; Pyro's inference machinery
+remains restated -- DESIGN.md section 6 states the pinning status accordingly.
+
+What is stored per case: the dataset, the reference's initial unconstrained parameters, and for every SVI iteration the
+minibatch indices, the guide's base variates (recovered from the recorded samples: standard-gamma variate = sample x
+rate, Beta variate = (sample - low) / scale, the Dirichlet sample itself), the loss and all 20 gradients; finally the
+parameters after the last Adam update.
+"""
+
+import importlib.util
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(HERE))
+REF = Path("/root/reference")
+
+
+def load_reference():
+    import minipyro
+
+    minipyro.install()
+    pk = types.ModuleType("pykeops")
+    pk.set_verbose = lambda *a, **k: None
+    pkt = types.ModuleType("pykeops.torch")
+    pkt.Genred = object
+    sys.modules.update({"pykeops": pk, "pykeops.torch": pkt})
+    for name in ("tapqir", "tapqir.distributions", "tapqir.models", "tapqir.utils"):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        sys.modules[name] = mod
+    sys.modules["tapqir"].__version__ = "reference"
+    stats = types.ModuleType("tapqir.utils.stats")      # imports matplotlib; only post-processing helpers live there
+    stats.save_stats = stats.torch_to_scipy_dist = None
+    sys.modules["tapqir.utils.stats"] = stats
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, REF / rel)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    load("tapqir.exceptions", "tapqir/exceptions.py")
+    load("tapqir.distributions.util", "tapqir/distributions/util.py")
+    ks = load("tapqir.distributions.ksmogn", "tapqir/distributions/ksmogn.py")
+    ab = load("tapqir.distributions.affine_beta", "tapqir/distributions/affine_beta.py")
+    sys.modules["tapqir.distributions"].KSMOGN, sys.modules["tapqir.distributions"].AffineBeta = ks.KSMOGN, ab.AffineBeta
+    ds = load("tapqir.utils.dataset", "tapqir/utils/dataset.py")
+    load("tapqir.models.model", "tapqir/models/model.py")
+    cm = load("tapqir.models.cosmos", "tapqir/models/cosmos.py")
+    return minipyro, ds, cm
+
+
+def noise_from_trace(nodes, K):
+    """Base variates of the guide's reparameterised sites, in the oracle's / kernels' convention."""
+    gam = lambda s: (s["value"] * (s["fn"].base_dist.rate if hasattr(s["fn"], "base_dist") else s["fn"].rate)).detach()
+    beta = lambda s: ((s["value"] - s["fn"].low) / s["fn"].scale).detach()
+    n = {"gain": gam(nodes["gain"]), "pi": nodes["pi"]["value"].detach(), "lamda": gam(nodes["lamda"]),
+         "proximity": beta(nodes["proximity"]), "background": gam(nodes["background"])}
+    n["height"] = torch.stack([gam(nodes[f"height_k{k}"]) for k in range(K)])
+    for name in ("width", "x", "y"):
+        n[name] = torch.stack([beta(nodes[f"{name}_k{k}"]) for k in range(K)])
+    return {k: v.clone() for k, v in n.items()}
+
+
+def run_case(minipyro, ds_mod, cosmos_mod, N, F, C, nb, fb, seed, offsets, perturb, masked, iters):
+    from tapqir_b200.utils.simulate import simulate   # input data only (any images would do)
+
+    kw = {}
+    if offsets == "hist":
+        s = torch.arange(80.0, 96.0)
+        w = torch.exp(-0.5 * ((s - 90) / 3) ** 2) + 1e-3
+        kw = dict(offset_samples=s, offset_weights=w / w.sum())
+    sim = simulate(N, F, C=C, seed=seed, **kw)
+    mask = sim.mask.clone()
+    if masked is not None:
+        mask[masked] = False
+    model = cosmos_mod.cosmos(device="cpu", dtype="double", use_pykeops=False)     # sets the default dtype to double
+    data = ds_mod.CosmosDataset(sim.images.double(), sim.xy.double(), sim.is_ontarget, mask, None,
+                                sim.offset.samples.double(), sim.offset.weights.double())
+    model.data = data
+    model.run_path = Path(tempfile.mkdtemp())
+    torch.manual_seed(seed)
+    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb)
+    store = minipyro.get_param_store().unconstrained()
+    init_unconstrained = {k: v.detach().clone() for k, v in store.items()}
+    if perturb:
+        g = torch.Generator().manual_seed(seed + 100)
+        with torch.no_grad():
+            for v in store.values():
+                v.add_(0.3 * torch.randn(v.shape, generator=g, dtype=v.dtype))
+    start = {k: v.detach().clone() for k, v in store.items()}
+    steps = []
+    for _ in range(iters):
+        loss = model.svi.step()                        # model.py:212
+        nodes = model.elbo.last_guide_trace
+        ndx = nodes["aois"]["value"] if "aois" in nodes else torch.arange(N)
+        fdx = nodes["frames"]["value"] if "frames" in nodes else torch.arange(F)
+        model_nodes = model.elbo.last_model_trace
+        shapes = {k: tuple(model_nodes[k]["value"].shape) for k in ("z", "theta", "m_k0", "m_k1")}
+        steps.append(dict(ndx=ndx.clone(), fdx=fdx.clone(), noise=noise_from_trace(nodes, model.K), loss=loss,
+                          grads={k: v.clone() for k, v in model.svi.last_grads.items()}, enum_shapes=shapes))
+    final = {k: v.detach().clone() for k, v in store.items()}
+    assert sim.images.min() >= 0 and sim.images.max() < 65536 and (sim.images == sim.images.floor()).all()
+    return dict(config=dict(N=N, F=F, C=C, nb=nb, fb=fb, seed=seed, offsets=offsets, lr=0.005),
+                images=sim.images.to(torch.int32), xy=sim.xy.double(), is_ontarget=sim.is_ontarget, mask=mask,
+                offset_samples=sim.offset.samples.double(), offset_weights=sim.offset.weights.double(),
+                init_unconstrained=init_unconstrained, start=start, steps=steps, final=final)
+
+
+def main():
+    minipyro, ds_mod, cosmos_mod = load_reference()
+    cases = {
+        "c1_initial_point": dict(N=4, F=6, C=1, nb=3, fb=4, seed=0, offsets="sim", perturb=False, masked=None, iters=5),
+        "c1_perturbed_masked": dict(N=5, F=6, C=1, nb=4, fb=4, seed=1, offsets="sim", perturb=True, masked=2, iters=5),
+        "c2_hist_offsets": dict(N=4, F=5, C=2, nb=3, fb=3, seed=2, offsets="hist", perturb=True, masked=None, iters=4),
+        "c1_full_batch": dict(N=3, F=4, C=1, nb=3, fb=4, seed=3, offsets="sim", perturb=True, masked=None, iters=3),
+    }
+    out = {name: run_case(minipyro, ds_mod, cosmos_mod, **kw) for name, kw in cases.items()}
+    torch.save(out, HERE / "ref_step.pt")
+    for name, c in out.items():
+        print(name, "losses", [round(s["loss"], 4) for s in c["steps"]], c["steps"][0]["enum_shapes"])
+    print("wrote", HERE / "ref_step.pt", (HERE / "ref_step.pt").stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -76,3 +76,28 @@ def compare_grads(ours, ref, tol, names=None):
         if not rel < tol:
             bad[k] = rel
     return bad
+
+
+def golden_step_case(name):
+    """A case of tests/golden/ref_step.pt (SVI iterations of the reference's own cosmos.py / model.py, produced by
+    tests/golden/make_golden_step.py): returns (dataset, oracle data view, case dict)."""
+    from pathlib import Path
+
+    from tapqir_b200.utils.dataset import CosmosDataset
+
+    case = torch.load(Path(__file__).resolve().parent / "golden" / "ref_step.pt", weights_only=False)[name]
+    ds = CosmosDataset(case["images"].to(torch.float32), case["xy"], case["is_ontarget"], case["mask"].clone(), None,
+                       case["offset_samples"], case["offset_weights"])
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    return ds, data, case
+
+
+def masked_loss_constant(case, step):
+    """What the reference's reported loss lacks relative to ours for masked AOIs in the minibatch: Pyro still sums over
+    the values of enumerated sites whose log-probabilities the mask zeroed, 4 configurations x ln 6 states per unit
+    (parameter-independent; tests/test_oracle.py)."""
+    import math
+
+    cfg = case["config"]
+    n_masked = int((~case["mask"][step["ndx"]]).sum())
+    return n_masked * cfg["fb"] * cfg["C"] * 4 * math.log(6) * (cfg["N"] / cfg["nb"]) * (cfg["F"] / cfg["fb"])

@@ -52,3 +52,29 @@ def test_step_f32_within_tolerance(cfg):
     assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss)
     bad = compare_grads(grads, ref_grads, 1e-5)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["c1_initial_point", "c1_perturbed_masked", "c2_hist_offsets", "c1_full_batch"])
+def test_step_f64_matches_reference_model_code(name):
+    """The kernels' arithmetic (host build) against tests/golden/ref_step.pt directly -- losses and gradients the
+    reference's own cosmos.py guide()/model() produced (tests/golden/make_golden_step.py) -- for every recorded
+    iteration, at the parameters the reference had at that iteration (replayed here with the oracle's Adam, which
+    tests/test_oracle.py pins to the same file)."""
+    from tests.step_helpers import golden_step_case, masked_loss_constant
+
+    hc = hostcheck.load()
+    ds, data, case = golden_step_case(name)
+    cfg = case["config"]
+    svi = O.OracleSVI(data, lr=cfg["lr"], nbatch_size=cfg["nb"], fbatch_size=cfg["fb"])
+    with torch.no_grad():
+        for k, v in svi.params.items():
+            v.copy_(case["start"][k].reshape(v.shape))
+    for step in case["steps"]:
+        params = {k: v.detach().clone() for k, v in svi.params.items()}
+        loss, grads, _ = host_step(hc, data, params, step["ndx"], step["fdx"], step["noise"], torch.float64)
+        ref_loss = step["loss"] + masked_loss_constant(case, step)
+        assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)
+        ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
+        bad = compare_grads(grads, ref_grads, 1e-8)
+        assert not bad, bad
+        svi.step(step["ndx"], step["fdx"], step["noise"])
