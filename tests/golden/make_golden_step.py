@@ -17,7 +17,8 @@ remains restated -- DESIGN.md section 6 states the pinning status accordingly.
 What is stored per case: the dataset, the reference's initial unconstrained parameters, and for every SVI iteration the
 minibatch indices, the guide's base variates (recovered from the recorded samples: standard-gamma variate = sample x
 rate, Beta variate = (sample - low) / scale, the Dirichlet sample itself), the loss and all 20 gradients; finally the
-parameters after the last Adam update.
+parameters after the last Adam update, and the reference's ``compute_probs`` (cosmos.py:609-672: z_probs, theta_probs from 50
+guide particles, with the particles' variates) at those parameters.
 """
 
 import importlib.util
@@ -121,11 +122,30 @@ def run_case(minipyro, ds_mod, cosmos_mod, N, F, C, nb, fb, seed, offsets, pertu
         steps.append(dict(ndx=ndx.clone(), fdx=fdx.clone(), noise=noise_from_trace(nodes, model.K), loss=loss,
                           grads={k: v.clone() for k, v in model.svi.last_grads.items()}, enum_shapes=shapes))
     final = {k: v.detach().clone() for k, v in store.items()}
+    # posterior of z / theta at the final parameters: the reference's own compute_probs (cosmos.py:609-672), with the
+    # batch sizes opened up so that ONE set of 50 guide particles covers all on-target AOIs and frames
+    model.nbatch_size, model.fbatch_size = N, F
+    minipyro.LAST_TRACES.clear()
+    z_probs, theta_probs = model.compute_probs
+    gnodes = minipyro.LAST_TRACES[0].nodes            # the first trace compute_probs takes is the guide's
+    K = model.K
+    gam = lambda s: (s["value"] * (s["fn"].base_dist.rate if hasattr(s["fn"], "base_dist") else s["fn"].rate)).detach()
+    beta = lambda s: ((s["value"] - s["fn"].low) / s["fn"].scale).detach()
+    lam, prox, pi = gam(gnodes["lamda"]), beta(gnodes["proximity"]), gnodes["pi"]["value"].detach()
+    xs = torch.stack([beta(gnodes[f"x_k{k}"]) for k in range(K)], 1)       # (50, K, n_on, F, C)
+    ys = torch.stack([beta(gnodes[f"y_k{k}"]) for k in range(K)], 1)
+    stack = lambda name, f: torch.stack([f(gnodes[f"{name}_k{k}"]) for k in range(K)], 1)
+    particles = dict(pi=pi[:, 0, 0, 0].clone(), lamda=lam[:, 0, 0, 0].clone(), proximity=prox[:, 0, 0, 0].clone(),
+                     x=xs.clone(), y=ys.clone(), gain=gam(gnodes["gain"])[:, 0, 0, 0].clone(),
+                     background=gam(gnodes["background"]).clone(), height=stack("height", gam),
+                     width=stack("width", beta))          # leading axis = the 50 particles
+    probs = dict(z_probs=z_probs.clone(), theta_probs=theta_probs.clone(), particles=particles,
+                 n_on=int(sim.is_ontarget.sum()))
     assert sim.images.min() >= 0 and sim.images.max() < 65536 and (sim.images == sim.images.floor()).all()
     return dict(config=dict(N=N, F=F, C=C, nb=nb, fb=fb, seed=seed, offsets=offsets, lr=0.005),
                 images=sim.images.to(torch.int32), xy=sim.xy.double(), is_ontarget=sim.is_ontarget, mask=mask,
                 offset_samples=sim.offset.samples.double(), offset_weights=sim.offset.weights.double(),
-                init_unconstrained=init_unconstrained, start=start, steps=steps, final=final)
+                init_unconstrained=init_unconstrained, start=start, steps=steps, final=final, probs=probs)
 
 
 def main():

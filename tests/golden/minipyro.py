@@ -7,7 +7,7 @@ never runs on the GPU box.
 
 It restates, from Pyro's published semantics, exactly the pieces that code touches and nothing else:
 
-* effect handlers: ``trace``, ``replay``, ``mask``, ``plate`` (subsampling as a replayable site, plate scale
+* effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``mask``, ``plate`` (subsampling as a replayable site, plate scale
   size / subsample_size, broadcasting of the distribution to the plate shape) and parallel enumeration
   (``infer={"enumerate": "parallel"}``: the support of the site is placed on a fresh tensor dimension to the left
   of ``max_plate_nesting``; the guide allocates first, the model continues to the left);
@@ -41,6 +41,8 @@ _ENUM = {"next": None}       # next free enumeration dimension (negative)
 # effect handlers
 # ---------------------------------------------------------------------------------------------------------------------
 class Messenger:
+    fn = None
+
     def __enter__(self):
         _STACK.append(self)
         return self
@@ -54,12 +56,9 @@ class Messenger:
     def postprocess(self, msg):
         pass
 
-    def __call__(self, fn):
-        def wrapped(*a, **kw):
-            with self:
-                return fn(*a, **kw)
-
-        return wrapped
+    def __call__(self, *a, **kw):      # handler(fn) form: run the wrapped callable under this handler
+        with self:
+            return self.fn(*a, **kw)
 
 
 def apply_stack(msg):
@@ -79,9 +78,33 @@ def apply_stack(msg):
     return msg
 
 
+class Trace:
+    """What ``handlers.trace(fn).get_trace()`` returns: the recorded sites and ``compute_log_prob``."""
+
+    def __init__(self, nodes):
+        self.nodes = nodes
+
+    def compute_log_prob(self):
+        for s in self.nodes.values():
+            if s["type"] == "sample" and not s.get("subsample") and "log_prob" not in s:
+                lp = s["fn"].log_prob(s["value"])
+                s["unscaled_log_prob"] = lp                      # before scale AND mask, as in Pyro
+                if s["mask"] is not None:
+                    lp = torch.where(s["mask"], lp, lp.new_zeros(()))
+                s["log_prob"] = lp * s["scale"]
+
+
+LAST_TRACES = []     # every Trace handed out by get_trace(), so that a caller can look at a callee's traces
+
+
 class trace(Messenger):
-    def __init__(self, param_only=False):
-        self.nodes, self.param_only = OrderedDict(), param_only
+    def __init__(self, fn=None, param_only=False):
+        self.fn, self.nodes, self.param_only = fn, OrderedDict(), param_only
+
+    def get_trace(self, *a, **kw):
+        self(*a, **kw)
+        LAST_TRACES.append(Trace(self.nodes))
+        return LAST_TRACES[-1]
 
     def postprocess(self, msg):
         if self.param_only and msg["type"] != "param":
@@ -92,8 +115,8 @@ class trace(Messenger):
 
 
 class replay(Messenger):
-    def __init__(self, guide_nodes):
-        self.guide = guide_nodes
+    def __init__(self, fn=None, trace=None):
+        self.fn, self.guide = fn, (trace.nodes if isinstance(trace, Trace) else trace)
 
     def process(self, msg):
         if msg["type"] == "sample" and msg["name"] in self.guide and not msg["is_observed"]:
@@ -101,9 +124,18 @@ class replay(Messenger):
             msg["value"], msg["done"], msg["infer"] = g["value"], True, g["infer"]
 
 
+class block(Messenger):
+    def __init__(self, fn=None, hide=()):
+        self.fn, self.hide = fn, set(hide)
+
+    def process(self, msg):
+        if msg["name"] in self.hide:
+            msg["stop"] = True
+
+
 class mask(Messenger):
-    def __init__(self, mask):
-        self.mask = mask
+    def __init__(self, fn=None, mask=None):
+        self.fn, self.mask = fn, mask
 
     def process(self, msg):
         if msg["type"] == "sample":
@@ -405,7 +437,7 @@ class TraceEnum_ELBO:
         with gt, g_enum:
             guide()
         mt = trace()
-        with mt, replay(gt.nodes), m_enum:
+        with mt, replay(trace=gt.nodes), m_enum:
             model()
         return gt.nodes, mt.nodes, g_enum.dims, m_enum.dims
 
@@ -509,7 +541,7 @@ def install():
     ops.__path__ = []
     module("pyro.ops.indexing", Vindex=Vindex)
     module("pyro.ops.stats", quantile=None, hpdi=None)
-    handlers = module("pyro.poutine", mask=mask, trace=trace, replay=replay, enum=enum)
+    handlers = module("pyro.poutine", mask=mask, trace=trace, replay=replay, enum=enum, block=block)
     infer = module("pyro.infer", TraceEnum_ELBO=TraceEnum_ELBO, JitTraceEnum_ELBO=TraceEnum_ELBO, SVI=SVI)
     optim = module("pyro.optim", Adam=Adam)
     pyro = module("pyro", sample=sample, param=param, plate=plate, clear_param_store=clear_param_store,

@@ -461,3 +461,27 @@ def test_svi_iterations_match_reference_model_code(ref_steps, name):
     # Pyro's enumeration layout the kernels' configuration index follows: m_0 at dim -4, m_1 at -5, z at -6, theta at -7
     assert case["steps"][0]["enum_shapes"] == {"z": (2, 1, 1, 1, 1, 1), "theta": (3, 1, 1, 1, 1, 1, 1), "m_k0": (2, 1, 1, 1),
                                                "m_k1": (2, 1, 1, 1, 1)}
+
+
+def _particles(case):
+    p = case["probs"]["particles"]
+    return [{k: v[i] for k, v in p.items()} for i in range(p["pi"].shape[0])]
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_compute_probs_matches_reference_model_code(ref_steps, name):
+    """cosmos.compute_probs (cosmos.py:609-672) run verbatim at the parameters after the recorded iterations, 50 guide
+    particles: z_probs and theta_probs of the on-target AOIs (the reference leaves off-target AOIs at zero).
+    The reference sums Pyro's ``unscaled_log_prob`` of x_k, y_k, which is taken BEFORE the ``m_k > 0`` mask; the oracle
+    applies the mask.  The two differ only where p(m_k = 0 | theta = k) = eps enters: below 1e-9 in the probabilities."""
+    case = ref_steps[name]
+    data = _golden_data(case)
+    n_on = case["probs"]["n_on"]
+    assert bool(data.is_ontarget[:n_on].all()) and not bool(data.is_ontarget[n_on:].any())
+    final = {k: v.reshape(O.init_constrained(data)[k].shape) for k, v in case["final"].items()}
+    z, th = O.compute_probs(final, data, torch.arange(n_on), torch.arange(data.F), _particles(case))
+    zr, thr = case["probs"]["z_probs"], case["probs"]["theta_probs"]
+    assert zr.shape == (data.Nt, data.F, data.C, 2) and thr.shape == (2, data.Nt, data.F, data.C)
+    assert (z - zr[:n_on]).abs().max().item() <= 1e-9 and (th - thr[:, :n_on]).abs().max().item() <= 1e-9
+    assert zr[n_on:].abs().max().item() == 0 and thr[:, n_on:].abs().max().item() == 0
+    assert 0.0 < zr[:n_on, ..., 1].max().item() <= 1.0

@@ -321,3 +321,24 @@ def test_svi_iterations_match_reference_model_code(name):
     for k, v in case["final"].items():
         err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
         assert err <= 1e-8 * max(1.0, v.abs().max().item()), (k, err)
+
+
+@pytest.mark.parametrize("name", ["c1_perturbed_masked", "c2_hist_offsets"])
+def test_compute_probs_matches_reference_model_code(name):
+    """z_probs / theta_probs of the reference's own compute_probs (cosmos.py:609-672, 50 guide particles, run by
+    tests/golden/make_golden_step.py) from the fp64 kernels fed the same particles' variates; 1e-9 (the reference's
+    unmasked x, y terms differ from the masked form at the eps level, tests/test_oracle.py)."""
+    from tests.step_helpers import golden_step_case
+
+    ds, data, case = golden_step_case(name)
+    cfg, probs = case["config"], case["probs"]
+    final = {k: v.reshape(O.init_constrained(data)[k].shape).clone() for k, v in case["final"].items()}
+    n_on, part = probs["n_on"], probs["particles"]
+    noises = [{k: v[i] for k, v in part.items()} for i in range(part["pi"].shape[0])]
+    eng = make_engine(ds, data, final, cfg["nb"], cfg["fb"], torch.float64)
+    ndx, fdx = torch.arange(n_on), torch.arange(data.F)
+    flat = [flat_inputs(data, final, n, torch.float64) for n in noises]
+    z, th = eng.compute_probs(particles=len(noises), ndx=ndx.to(torch.int32).cuda(), fdx=fdx.to(torch.int32).cuda(),
+                              local_noise=[f[4].cuda() for f in flat], global_noise=[f[5].cuda() for f in flat])
+    assert (z.double().cpu() - probs["z_probs"][:n_on]).abs().max().item() < 1e-9
+    assert (th.double().cpu() - probs["theta_probs"][:, :n_on]).abs().max().item() < 1e-9
