@@ -18,12 +18,15 @@ Pinning status
   ``expand_offtarget`` and ``ksmogn_log_prob`` are PINNED: ``tests/golden/make_golden.py`` imports the
   reference's own ``tapqir/distributions/util.py`` and ``ksmogn.py`` (torch branch,
   ``use_pykeops=False``) in the build container and stores their outputs in
-  ``tests/golden/*.pt``; ``tests/test_oracle.py`` checks this file against them.
-* The ELBO assembly (what ``TraceEnum_ELBO`` does with the model/guide traces), the AffineBeta
-  wrapper around ``pyro.distributions.AffineBeta`` and the SVI/Adam loop are UNPINNED ("parity
-  unpinned"): the reference's tests assert only ``exit_code == 0`` (``test/test_tapqir.py:91-93``)
-  and Pyro cannot be imported.  They are cross-checked against ``torch.distributions`` and scipy
-  closed forms instead.
+  ``tests/golden/ref_distributions.pt``; ``tests/test_oracle.py`` checks this file against them.
+* One whole ``svi.step()`` (loss, all 20 gradients, Adam update), the initial parameters and ``compute_probs`` are
+  PINNED against the reference's own ``models/cosmos.py`` / ``models/model.py`` run verbatim by
+  ``tests/golden/make_golden_step.py`` -> ``tests/golden/ref_step.pt`` (``tests/test_oracle.py``), with the absent
+  pyro / pyroapi packages replaced by the restatement ``tests/golden/minipyro.py``.
+* Pyro's own machinery (what ``TraceEnum_ELBO`` does with the traces, ``pyro.distributions.AffineBeta``, the param
+  store, ``pyro.optim.Adam``) therefore remains UNPINNED ("parity unpinned"): the reference's tests assert only
+  ``exit_code == 0`` (``test/test_tapqir.py:91-93``) and Pyro cannot be imported.  It is cross-checked against a
+  scalar scipy restatement of the ELBO, quantile finite differences and a hand-written Adam instead.
 """
 
 import itertools
