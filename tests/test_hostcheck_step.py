@@ -9,6 +9,7 @@ import torch
 
 from oracle import cosmos_oracle as O
 from tests import hostcheck
+from tapqir_b200.models import layout as L
 from tests.step_helpers import compare_grads, host_step, make_problem
 
 
@@ -76,5 +77,33 @@ def test_step_f64_matches_reference_model_code(name):
         assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)
         ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
         bad = compare_grads(grads, ref_grads, 1e-8)
+        assert not bad, bad
+        svi.step(step["ndx"], step["fdx"], step["noise"])
+
+
+@pytest.mark.parametrize("name", ["c1_initial_point", "c1_perturbed_masked", "c2_hist_offsets", "c1_full_batch"])
+def test_step_f32_within_north_star_of_reference_model_code(name):
+    """The fp32 production arithmetic against the reference's own fp64 numbers (tests/golden/ref_step.pt), nothing
+    rounded on the reference side: loss 1e-6, gradients of the AOI-local tensors 1e-5 of each tensor's largest entry at
+    every iteration (global scalars 1e-4, below)."""
+    from tests.step_helpers import golden_step_case, masked_loss_constant
+
+    hc = hostcheck.load()
+    ds, data, case = golden_step_case(name)
+    cfg = case["config"]
+    svi = O.OracleSVI(data, lr=cfg["lr"], nbatch_size=cfg["nb"], fbatch_size=cfg["fb"])
+    with torch.no_grad():
+        for k, v in svi.params.items():
+            v.copy_(case["start"][k].reshape(v.shape))
+    for step in case["steps"]:
+        params = {k: v.detach().clone() for k, v in svi.params.items()}
+        loss, grads, _ = host_step(hc, data, params, step["ndx"], step["fdx"], step["noise"], torch.float32)
+        ref_loss = step["loss"] + masked_loss_constant(case, step)
+        assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss)
+        ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
+        bad = compare_grads(grads, ref_grads, 1e-5, names=L.LOCAL_NAMES)
+        # the 8 global gradients are scalars (or 2-4 values) measured against THEMSELVES, and they pass through zero
+        # during a fit: the fp64 oracle fed fp32-rounded inputs is itself 5e-5 from the reference at such a point
+        bad.update(compare_grads(grads, ref_grads, 1e-4, names=L.GLOBAL_NAMES))
         assert not bad, bad
         svi.step(step["ndx"], step["fdx"], step["noise"])

@@ -291,54 +291,3 @@ def test_step_with_unmerged_offset_bins(dtype, ltol, gtol):
     merged = make_engine(ds, data, params, cfg["nb"], cfg["fb"], dtype)
     assert merged.store.offset_samples.numel() == 1
 
-
-@pytest.mark.parametrize("name", ["c1_initial_point", "c1_perturbed_masked", "c2_hist_offsets", "c1_full_batch"])
-def test_svi_iterations_match_reference_model_code(name):
-    """tests/golden/ref_step.pt: SVI iterations produced by the reference's own cosmos.py (init_parameters, guide,
-    model) and model.py (Model.init, svi.step) -- tests/golden/make_golden_step.py.  The fp64 kernels replay the recorded
-    minibatches and base variates from the recorded starting parameters: every loss (1e-11; plus the constant Pyro
-    adds for masked AOIs, tests/test_oracle.py), the gradients of the first iteration (1e-8 of each tensor's largest
-    entry) and the parameters after the last Adam update (1e-8; the host build of the same arithmetic is at 1e-11)."""
-    from tests.step_helpers import golden_step_case, masked_loss_constant
-
-    ds, data, case = golden_step_case(name)
-    cfg = case["config"]
-    start = {k: v.reshape(O.init_constrained(data)[k].shape).clone() for k, v in case["start"].items()}
-    eng = make_engine(ds, data, start, cfg["nb"], cfg["fb"], torch.float64, lr=cfg["lr"])
-    first = case["steps"][0]
-    loss = eng.step(update=False, **replay_args(eng, data, start, first["ndx"], first["fdx"], first["noise"], torch.float64)).item()
-    ref_loss = first["loss"] + masked_loss_constant(case, first)
-    assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)
-    ref_grads = {k: g.reshape(start[k].shape) for k, g in first["grads"].items()}
-    bad = compare_grads(eng.named_grads(), ref_grads, 1e-8)
-    assert not bad, bad
-    for it, step in enumerate(case["steps"]):
-        loss = eng.step(**replay_args(eng, data, start, step["ndx"], step["fdx"], step["noise"], torch.float64)).item()
-        ref_loss = step["loss"] + masked_loss_constant(case, step)
-        assert abs(loss - ref_loss) <= 1e-9 * abs(ref_loss), (it, loss, ref_loss)
-    assert eng.iteration == len(case["steps"])
-    ours = eng.named_unconstrained()
-    for k, v in case["final"].items():
-        err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
-        assert err <= 1e-8 * max(1.0, v.abs().max().item()), (k, err)
-
-
-@pytest.mark.parametrize("name", ["c1_perturbed_masked", "c2_hist_offsets"])
-def test_compute_probs_matches_reference_model_code(name):
-    """z_probs / theta_probs of the reference's own compute_probs (cosmos.py:609-672, 50 guide particles, run by
-    tests/golden/make_golden_step.py) from the fp64 kernels fed the same particles' variates; 1e-9 (the reference's
-    unmasked x, y terms differ from the masked form at the eps level, tests/test_oracle.py)."""
-    from tests.step_helpers import golden_step_case
-
-    ds, data, case = golden_step_case(name)
-    cfg, probs = case["config"], case["probs"]
-    final = {k: v.reshape(O.init_constrained(data)[k].shape).clone() for k, v in case["final"].items()}
-    n_on, part = probs["n_on"], probs["particles"]
-    noises = [{k: v[i] for k, v in part.items()} for i in range(part["pi"].shape[0])]
-    eng = make_engine(ds, data, final, cfg["nb"], cfg["fb"], torch.float64)
-    ndx, fdx = torch.arange(n_on), torch.arange(data.F)
-    flat = [flat_inputs(data, final, n, torch.float64) for n in noises]
-    z, th = eng.compute_probs(particles=len(noises), ndx=ndx.to(torch.int32).cuda(), fdx=fdx.to(torch.int32).cuda(),
-                              local_noise=[f[4].cuda() for f in flat], global_noise=[f[5].cuda() for f in flat])
-    assert (z.double().cpu() - probs["z_probs"][:n_on]).abs().max().item() < 1e-9
-    assert (th.double().cpu() - probs["theta_probs"][:, :n_on]).abs().max().item() < 1e-9

@@ -1,0 +1,97 @@
+"""
+GPU: the CUDA path against tests/golden/ref_step.pt -- SVI iterations and posteriors produced by the reference's OWN
+``models/cosmos.py`` (init_parameters, guide, model, compute_probs) and ``models/model.py`` (Model.init, svi.step), run
+verbatim in the build container by tests/golden/make_golden_step.py with the absent pyro / pyroapi packages replaced by
+tests/golden/minipyro.py.  Replay mode: recorded minibatch indices and guide variates.
+"""
+
+import pytest
+import torch
+
+from oracle import cosmos_oracle as O
+from tapqir_b200.models import layout as L
+from tests.step_helpers import compare_grads, flat_inputs, golden_step_case, masked_loss_constant
+from tests.test_step_gpu import make_engine, replay_args
+
+pytestmark = pytest.mark.gpu
+CASES = ["c1_initial_point", "c1_perturbed_masked", "c2_hist_offsets", "c1_full_batch"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_svi_iterations_match_reference_model_code(name):
+    """tests/golden/ref_step.pt: SVI iterations produced by the reference's own cosmos.py (init_parameters, guide,
+    model) and model.py (Model.init, svi.step) -- tests/golden/make_golden_step.py.  The fp64 kernels replay the recorded
+    minibatches and base variates from the recorded starting parameters: every loss (1e-11; plus the constant Pyro
+    adds for masked AOIs, tests/test_oracle.py), the gradients of the first iteration (1e-8 of each tensor's largest
+    entry) and the parameters after the last Adam update (1e-8; the host build of the same arithmetic is at 1e-11)."""
+    ds, data, case = golden_step_case(name)
+    cfg = case["config"]
+    start = {k: v.reshape(O.init_constrained(data)[k].shape).clone() for k, v in case["start"].items()}
+    eng = make_engine(ds, data, start, cfg["nb"], cfg["fb"], torch.float64, lr=cfg["lr"])
+    first = case["steps"][0]
+    loss = eng.step(update=False, **replay_args(eng, data, start, first["ndx"], first["fdx"], first["noise"], torch.float64)).item()
+    ref_loss = first["loss"] + masked_loss_constant(case, first)
+    assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)
+    ref_grads = {k: g.reshape(start[k].shape) for k, g in first["grads"].items()}
+    bad = compare_grads(eng.named_grads(), ref_grads, 1e-8)
+    assert not bad, bad
+    for it, step in enumerate(case["steps"]):
+        loss = eng.step(**replay_args(eng, data, start, step["ndx"], step["fdx"], step["noise"], torch.float64)).item()
+        ref_loss = step["loss"] + masked_loss_constant(case, step)
+        assert abs(loss - ref_loss) <= 1e-9 * abs(ref_loss), (it, loss, ref_loss)
+    assert eng.iteration == len(case["steps"])
+    ours = eng.named_unconstrained()
+    for k, v in case["final"].items():
+        err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
+        assert err <= 1e-8 * max(1.0, v.abs().max().item()), (k, err)
+
+
+@pytest.mark.parametrize("name", ["c1_perturbed_masked", "c2_hist_offsets"])
+def test_compute_probs_matches_reference_model_code(name):
+    """z_probs / theta_probs of the reference's own compute_probs (cosmos.py:609-672, 50 guide particles, run by
+    tests/golden/make_golden_step.py) from the fp64 kernels fed the same particles' variates; 1e-9 (the reference's
+    unmasked x, y terms differ from the masked form at the eps level, tests/test_oracle.py)."""
+    ds, data, case = golden_step_case(name)
+    cfg, probs = case["config"], case["probs"]
+    final = {k: v.reshape(O.init_constrained(data)[k].shape).clone() for k, v in case["final"].items()}
+    n_on, part = probs["n_on"], probs["particles"]
+    noises = [{k: v[i] for k, v in part.items()} for i in range(part["pi"].shape[0])]
+    eng = make_engine(ds, data, final, cfg["nb"], cfg["fb"], torch.float64)
+    ndx, fdx = torch.arange(n_on), torch.arange(data.F)
+    flat = [flat_inputs(data, final, n, torch.float64) for n in noises]
+    z, th = eng.compute_probs(particles=len(noises), ndx=ndx.to(torch.int32).cuda(), fdx=fdx.to(torch.int32).cuda(),
+                              local_noise=[f[4].cuda() for f in flat], global_noise=[f[5].cuda() for f in flat])
+    assert (z.double().cpu() - probs["z_probs"][:n_on]).abs().max().item() < 1e-9
+    assert (th.double().cpu() - probs["theta_probs"][:, :n_on]).abs().max().item() < 1e-9
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_production_kernels_within_north_star_of_reference_model_code(name):
+    """The fp32 production kernels at every recorded iteration (parameters of the reference's trajectory, replayed by
+    the oracle's Adam which tests/test_oracle.py pins to the same file), against the reference's fp64 numbers with
+    NO rounding on the reference side: loss and gradients within the north-star 1e-5 (gradients relative to each
+    tensor's largest entry; 3e-5 allowed because our side alone sees fp32-rounded parameters and variates -- the host
+    build of the same arithmetic measures <= 7e-7 / < 1e-5, tests/test_hostcheck_step.py)."""
+    ds, data, case = golden_step_case(name)
+    cfg = case["config"]
+    svi = O.OracleSVI(data, lr=cfg["lr"], nbatch_size=cfg["nb"], fbatch_size=cfg["fb"])
+    with torch.no_grad():
+        for k, v in svi.params.items():
+            v.copy_(case["start"][k].reshape(v.shape))
+    eng = None
+    for it, step in enumerate(case["steps"]):
+        params = {k: v.detach().clone() for k, v in svi.params.items()}
+        if eng is None:
+            eng = make_engine(ds, data, params, cfg["nb"], cfg["fb"], torch.float32)
+        else:
+            eng.load_unconstrained(params)
+        loss = eng.step(update=False, **replay_args(eng, data, params, step["ndx"], step["fdx"], step["noise"], torch.float32)).item()
+        ref_loss = step["loss"] + masked_loss_constant(case, step)
+        assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss), (it, loss, ref_loss)
+        ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
+        bad = compare_grads(eng.named_grads(), ref_grads, 3e-5, names=L.LOCAL_NAMES)
+        # global gradients are scalars measured against themselves and pass through zero during a fit: the fp64
+        # oracle fed fp32-rounded inputs is itself 5e-5 from the reference at such a point (tests/test_hostcheck_step.py)
+        bad.update(compare_grads(eng.named_grads(), ref_grads, 1e-4, names=L.GLOBAL_NAMES))
+        assert not bad, (it, bad)
+        svi.step(step["ndx"], step["fdx"], step["noise"])
