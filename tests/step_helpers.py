@@ -101,3 +101,23 @@ def masked_loss_constant(case, step):
     cfg = case["config"]
     n_masked = int((~case["mask"][step["ndx"]]).sum())
     return n_masked * cfg["fb"] * cfg["C"] * 4 * math.log(6) * (cfg["N"] / cfg["nb"]) * (cfg["F"] / cfg["fb"])
+
+
+GLOBAL_PAIRS = [("gain_loc", "gain_beta"), ("lamda_loc", "lamda_beta"), ("proximity_loc", "proximity_size"), ("pi_mean", "pi_size")]
+
+
+def compare_global_grads(ours, ref, tol):
+    """Global gradients are one to four numbers each; measured against themselves they have no scale when they pass
+    through zero.  The two parameters of one guide distribution (mean-like, concentration-like) share their terms: the
+    gradient of the concentration-like one is the difference of two terms of the mean-like one's size (moving it keeps
+    the mean), e.g. 58 against 4472 for ``gain`` on the test data.  Errors are therefore measured against the largest
+    entry of the PAIR -- the conditioning of the quantity, as the largest entry of a tensor is for the local ones."""
+    bad = {}
+    for pair in GLOBAL_PAIRS:
+        scale = max(ref[k].double().abs().max().item() for k in pair)
+        for k in pair:
+            r = ref[k].double()
+            err = (ours[k].double().cpu().reshape(r.shape) - r).abs().max().item()
+            if not err <= tol * scale:
+                bad[k] = err / scale
+    return bad

@@ -10,7 +10,7 @@ import torch
 
 from oracle import cosmos_oracle as O
 from tapqir_b200.models import layout as L
-from tests.step_helpers import compare_grads, flat_inputs, golden_step_case, masked_loss_constant
+from tests.step_helpers import compare_global_grads, compare_grads, flat_inputs, golden_step_case, masked_loss_constant
 from tests.test_step_gpu import make_engine, replay_args
 
 pytestmark = pytest.mark.gpu
@@ -69,9 +69,10 @@ def test_compute_probs_matches_reference_model_code(name):
 def test_fp32_production_kernels_within_north_star_of_reference_model_code(name):
     """The fp32 production kernels at every recorded iteration (parameters of the reference's trajectory, replayed by
     the oracle's Adam which tests/test_oracle.py pins to the same file), against the reference's fp64 numbers with
-    NO rounding on the reference side: loss and gradients within the north-star 1e-5 (gradients relative to each
-    tensor's largest entry; 3e-5 allowed because our side alone sees fp32-rounded parameters and variates -- the host
-    build of the same arithmetic measures <= 7e-7 / < 1e-5, tests/test_hostcheck_step.py)."""
+    NO rounding on the reference side: the north-star tolerance -- loss 1e-6, gradients 1e-5 of each tensor's largest
+    entry (global ones: of their distribution's parameter pair, step_helpers.compare_global_grads).  Measured on a
+    B200 (profiles/r1s5_parity_vs_reference_code.log): loss <= 7.6e-7, local gradients <= 8.9e-6, global <= 1.8e-6;
+    replay mode is deterministic (fixed-order reductions), so the margins do not move between runs."""
     ds, data, case = golden_step_case(name)
     cfg = case["config"]
     svi = O.OracleSVI(data, lr=cfg["lr"], nbatch_size=cfg["nb"], fbatch_size=cfg["fb"])
@@ -87,11 +88,12 @@ def test_fp32_production_kernels_within_north_star_of_reference_model_code(name)
             eng.load_unconstrained(params)
         loss = eng.step(update=False, **replay_args(eng, data, params, step["ndx"], step["fdx"], step["noise"], torch.float32)).item()
         ref_loss = step["loss"] + masked_loss_constant(case, step)
-        assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss), (it, loss, ref_loss)
+        assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss), (it, loss, ref_loss)
         ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
-        bad = compare_grads(eng.named_grads(), ref_grads, 3e-5, names=L.LOCAL_NAMES)
-        # global gradients are scalars measured against themselves and pass through zero during a fit: the fp64
-        # oracle fed fp32-rounded inputs is itself 5e-5 from the reference at such a point (tests/test_hostcheck_step.py)
-        bad.update(compare_grads(eng.named_grads(), ref_grads, 1e-4, names=L.GLOBAL_NAMES))
+        bad = compare_grads(eng.named_grads(), ref_grads, 1e-5, names=L.LOCAL_NAMES)
+        print(f"[{name} it {it}] loss rel {abs(loss - ref_loss) / abs(ref_loss):.2e}; worst local gradient rel "
+              f"{max(compare_grads(eng.named_grads(), ref_grads, 0.0, names=L.LOCAL_NAMES).values()):.2e}; worst global (pair scale) "
+              f"{max(compare_global_grads(eng.named_grads(), ref_grads, 0.0).values()):.2e}")
+        bad.update(compare_global_grads(eng.named_grads(), ref_grads, 1e-5))   # against the pair's largest entry, see there
         assert not bad, (it, bad)
         svi.step(step["ndx"], step["fdx"], step["noise"])
