@@ -2,11 +2,16 @@
 CPU fp64 restatement of one SVI step of the reference's *hmm* model (tapqir/models/hmm.py) --
 TEST INFRASTRUCTURE ONLY (imported by tests/, never by tapqir_b200/).
 
-Parity status: like the cosmos oracle, the continuous sites, the prior tables and the image likelihood are the
-functions of oracle/cosmos_oracle.py (pinned against the reference's own distributions code); the ELBO assembly
--- what Pyro's ``TraceEnum_ELBO`` computes for a guide that enumerates the Markov chain ``z_f`` and the spot
-presences ``m_k`` (hmm.py:355-377) and a model that enumerates ``theta`` (hmm.py:178-186) -- is the closed form
-of SURVEY.md App. B.2 ("parity unpinned": pyro / funsor are not installable here).
+Parity status: the continuous sites, the prior tables and the image likelihood are the functions of
+oracle/cosmos_oracle.py (pinned against the reference's own distributions code).  The ELBO assembly -- what Pyro's
+``TraceEnum_ELBO`` computes for a guide that enumerates the Markov chain ``z_f`` and the spot presences ``m_k``
+(hmm.py:355-377) and a model that enumerates ``theta`` (hmm.py:178-186) -- is the closed form of SURVEY.md App. B.2
+below.  It is PINNED against the reference's own ``models/hmm.py`` (init_parameters, guide, model) run verbatim in its
+sequential form (``vectorized=False``: pyro.markov + TraceEnum_ELBO) by tests/golden/make_golden_step.py ->
+tests/golden/ref_step_hmm.pt, where the expectation over the enumerated chain is taken by brute force over every
+enumerated dimension: losses 1e-15, gradients 7e-10, Adam trajectory 1e-11 (tests/test_hmm_cpu.py).  Pyro itself
+(absent, not installable; funsor for the vectorised form likewise) is restated by tests/golden/minipyro.py -- "parity
+unpinned" for Pyro's own machinery, as for cosmos.
 
     a_f(z)      = sum_z' a_{f-1}(z') q_f(z | z'),  a_{-1} = e_0          (row 0 of z_trans is used at f = 0)
     ELBO_nc     = sum_f sum_{z',z} a_{f-1}(z') q_f(z|z') [log p_f(z|z') - log q_f(z|z')]

@@ -6,6 +6,8 @@ Run as:  python tests/golden/make_golden_step.py    (needs /root/reference; neve
 Executed verbatim from /root/reference (nothing is copied into the repository, only numeric outputs are stored):
   tapqir/models/cosmos.py        cosmos.__init__, init_parameters/_init_parameters (:464-598), guide (:329-462),
                                  model (:82-327), TraceELBO (:600-607)
+  tapqir/models/hmm.py           hmm.__init__, init_parameters (:419-467), guide (:268-417), model (:82-266) in the sequential form
+                                 ``vectorized=False`` (pyro.markov + TraceEnum_ELBO; the vectorised form needs funsor)
   tapqir/models/model.py         Model.__init__/to/Q, Model.init (:153-186) and the loop body ``self.svi.step()`` (:212)
   tapqir/utils/dataset.py        CosmosDataset, OffsetData (fetch, median, offset mean / logits)
   tapqir/distributions/*.py      util.py, ksmogn.py (torch branch, use_pykeops=False), affine_beta.py
@@ -69,7 +71,16 @@ def load_reference():
     ds = load("tapqir.utils.dataset", "tapqir/utils/dataset.py")
     load("tapqir.models.model", "tapqir/models/model.py")
     cm = load("tapqir.models.cosmos", "tapqir/models/cosmos.py")
-    return minipyro, ds, cm
+    # hmm.py: its vectorised form needs funsor (tapqir/handlers.py, tapqir/infer/); ``vectorized=False`` is the reference's
+    # own sequential form of the same model (pyro.markov + TraceEnum_ELBO, hmm.py:126-131, 474-478) and needs neither
+    for name, attrs in {"funsor": {}, "pyro.distributions.hmm": {"_logmatmulexp": None, "_sequential_index": None},
+                        "tapqir.handlers": {"trace": None, "vectorized_markov": None}, "tapqir.infer": {},
+                        "tapqir.infer.elbo": {"TraceMarkovEnum_ELBO": None}}.items():
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+    hm = load("tapqir.models.hmm", "tapqir/models/hmm.py")
+    return minipyro, ds, cm, hm
 
 
 def noise_from_trace(nodes, K):
@@ -148,8 +159,52 @@ def run_case(minipyro, ds_mod, cosmos_mod, N, F, C, nb, fb, seed, offsets, pertu
                 init_unconstrained=init_unconstrained, start=start, steps=steps, final=final, probs=probs)
 
 
+def run_hmm_case(minipyro, ds_mod, hmm_mod, N, F, C, nb, seed, perturb, iters):
+    """hmm.model / hmm.guide / hmm.init_parameters (models/hmm.py:82-467) in the reference's sequential form
+    (``vectorized=False``): the guide enumerates the chain z_f and m_k|z_f, the model theta_f; all frames every step."""
+    from tapqir_b200.utils.simulate import simulate
+
+    sim = simulate(N, F, C=C, seed=seed, params={"kon": 0.2, "koff": 0.2})
+    model = hmm_mod.hmm(device="cpu", dtype="double", use_pykeops=False, vectorized=False)
+    model.data = ds_mod.CosmosDataset(sim.images.double(), sim.xy.double(), sim.is_ontarget, sim.mask.clone(), None,
+                                      sim.offset.samples.double(), sim.offset.weights.double())
+    model.run_path = Path(tempfile.mkdtemp())
+    torch.manual_seed(seed)
+    model.init(lr=0.005, nbatch_size=nb, fbatch_size=F)
+    store = minipyro.get_param_store().unconstrained()
+    init_unconstrained = {k: v.detach().clone() for k, v in store.items()}
+    if perturb:
+        g = torch.Generator().manual_seed(seed + 100)
+        with torch.no_grad():
+            for v in store.values():
+                v.add_(0.3 * torch.randn(v.shape, generator=g, dtype=v.dtype))
+    start = {k: v.detach().clone() for k, v in store.items()}
+    gam = lambda s: (s["value"] * (s["fn"].base_dist.rate if hasattr(s["fn"], "base_dist") else s["fn"].rate)).detach()
+    beta = lambda s: ((s["value"] - s["fn"].low) / s["fn"].scale).detach()
+    K = model.K
+    steps = []
+    for _ in range(iters):
+        loss = model.svi.step()
+        nodes = model.elbo.last_guide_trace
+        ndx = nodes["aois"]["value"] if "aois" in nodes else torch.arange(N)
+        frames = lambda name, f: torch.cat([f(nodes[f"{name}_f{i}"]) for i in range(F)], -2)       # (nb, F, C)
+        noise = {"gain": gam(nodes["gain"]), "init": nodes["init"]["value"].detach(), "trans": nodes["trans"]["value"].detach(),
+                 "lamda": gam(nodes["lamda"]), "proximity": beta(nodes["proximity"]), "background": frames("background", gam),
+                 "height": torch.stack([frames(f"height_k{k}", gam) for k in range(K)]),
+                 "width": torch.stack([frames(f"width_k{k}", beta) for k in range(K)]),
+                 "x": torch.stack([frames(f"x_k{k}", beta) for k in range(K)]),
+                 "y": torch.stack([frames(f"y_k{k}", beta) for k in range(K)])}
+        steps.append(dict(ndx=ndx.clone(), noise={k: v.clone() for k, v in noise.items()}, loss=loss,
+                          grads={k: v.clone() for k, v in model.svi.last_grads.items()}))
+    final = {k: v.detach().clone() for k, v in store.items()}
+    return dict(config=dict(N=N, F=F, C=C, nb=nb, seed=seed, lr=0.005), images=sim.images.to(torch.int32), xy=sim.xy.double(),
+                is_ontarget=sim.is_ontarget, mask=sim.mask.clone(), offset_samples=sim.offset.samples.double(),
+                offset_weights=sim.offset.weights.double(), init_unconstrained=init_unconstrained, start=start, steps=steps,
+                final=final)
+
+
 def main():
-    minipyro, ds_mod, cosmos_mod = load_reference()
+    minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
     cases = {
         "c1_initial_point": dict(N=4, F=6, C=1, nb=3, fb=4, seed=0, offsets="sim", perturb=False, masked=None, iters=5),
         "c1_perturbed_masked": dict(N=5, F=6, C=1, nb=4, fb=4, seed=1, offsets="sim", perturb=True, masked=2, iters=5),
@@ -157,6 +212,14 @@ def main():
         "c1_full_batch": dict(N=3, F=4, C=1, nb=3, fb=4, seed=3, offsets="sim", perturb=True, masked=None, iters=3),
     }
     out = {name: run_case(minipyro, ds_mod, cosmos_mod, **kw) for name, kw in cases.items()}
+    hmm_cases = {
+        "hmm_c1": dict(N=3, F=4, C=1, nb=2, seed=5, perturb=True, iters=3),
+        "hmm_c2_initial_point": dict(N=2, F=3, C=2, nb=2, seed=6, perturb=False, iters=3),
+    }
+    hmm_out = {name: run_hmm_case(minipyro, ds_mod, hmm_mod, **kw) for name, kw in hmm_cases.items()}
+    torch.save(hmm_out, HERE / "ref_step_hmm.pt")
+    for name, c in hmm_out.items():
+        print(name, "losses", [round(s["loss"], 4) for s in c["steps"]])
     torch.save(out, HERE / "ref_step.pt")
     for name, c in out.items():
         print(name, "losses", [round(s["loss"], 4) for s in c["steps"]], c["steps"][0]["enum_shapes"])

@@ -8,7 +8,8 @@ never runs on the GPU box.
 It restates, from Pyro's published semantics, exactly the pieces that code touches and nothing else:
 
 * effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``mask``, ``plate`` (subsampling as a replayable site, plate scale
-  size / subsample_size, broadcasting of the distribution to the plate shape) and parallel enumeration
+  size / subsample_size, broadcasting of the distribution to the plate shape; sequential plates and ``markov`` loops
+  without dimension recycling) and parallel enumeration
   (``infer={"enumerate": "parallel"}``: the support of the site is placed on a fresh tensor dimension to the left
   of ``max_plate_nesting``; the guide allocates first, the model continues to the left);
 * ``pyro.param`` with the unconstrained value stored (``transform_to(constraint).inv``) and the constrained one
@@ -19,7 +20,8 @@ It restates, from Pyro's published semantics, exactly the pieces that code touch
   the MODEL enumerated, minus the guide sites' log-probabilities, weighted by the probabilities of the sites the
   GUIDE enumerated (exact expectation, differentiable), summed over plates and multiplied by the plate scale;
   reparameterised sites contribute pathwise gradients only.  The general tensor-variable-elimination of Pyro is not
-  needed because every enumerated site of cosmos sits inside all three plates (asserted);
+  needed because every enumerated site of cosmos (and of hmm's sequential form) sits in the deepest plate context
+  (asserted), where the expectation is evaluated by brute force over all enumerated dimensions;
 * ``SVI.step`` (loss and gradients, one ``torch.optim.Adam`` per parameter acting on the unconstrained value, zero
   the gradients) and ``optim.Adam``.
 """
@@ -189,7 +191,7 @@ class _Subsample(td.Distribution):
 
 class plate(Messenger):
     def __init__(self, name, size, subsample_size=None, subsample=None, dim=None, **unused):
-        assert dim is not None and dim < 0
+        assert dim is None or dim < 0
         self.name, self.size, self.dim = name, size, dim
         if subsample is not None:
             self.indices = subsample
@@ -204,6 +206,11 @@ class plate(Messenger):
     def __enter__(self):
         super().__enter__()
         return self.indices
+
+    def __iter__(self):
+        """Sequential plate (``for k in pyro.plate("spots", K)``): plain integers, no tensor dimension, no scaling."""
+        assert self.dim is None and self.subsample_size == self.size
+        return iter(range(self.size))
 
     def process(self, msg):
         if msg["type"] != "sample" or msg.get("subsample"):
@@ -252,6 +259,12 @@ def _param_value(name, init=None, constraint=constraints.real):
 def param(name, init_tensor=None, constraint=constraints.real, event_dim=None):
     msg = _new_msg("param", name, args=(init_tensor, constraint))
     return apply_stack(msg)["value"]
+
+
+def markov(iterable, history=1):
+    """``pyro.markov`` only lets enumeration dimensions be recycled ``history + 1`` steps later; without recycling every
+    step keeps its own dimensions, which changes tensor shapes but no value."""
+    return iterable
 
 
 def clear_param_store():
@@ -544,7 +557,7 @@ def install():
     handlers = module("pyro.poutine", mask=mask, trace=trace, replay=replay, enum=enum, block=block)
     infer = module("pyro.infer", TraceEnum_ELBO=TraceEnum_ELBO, JitTraceEnum_ELBO=TraceEnum_ELBO, SVI=SVI)
     optim = module("pyro.optim", Adam=Adam)
-    pyro = module("pyro", sample=sample, param=param, plate=plate, clear_param_store=clear_param_store,
+    pyro = module("pyro", sample=sample, param=param, plate=plate, markov=markov, clear_param_store=clear_param_store,
                   get_param_store=get_param_store, set_rng_seed=set_rng_seed, distributions=dist, poutine=handlers,
                   infer=infer, optim=optim, ops=ops)
     pyro.__path__ = []

@@ -1,6 +1,7 @@
 """
-CPU: the hmm oracle's chain algebra against brute-force enumeration of every z path (tiny F), and the host-side
-layouts of the hmm variant.  (The oracle's ELBO assembly itself is "parity unpinned": pyro / funsor are absent.)
+CPU: the hmm oracle's chain algebra against brute-force enumeration of every z path (tiny F), the host-side
+layouts of the hmm variant, and -- at the end -- oracle and host build of the hmm kernels' arithmetic against golden SVI
+iterations of the reference's own models/hmm.py (tests/golden/ref_step_hmm.pt).
 """
 
 import itertools
@@ -127,3 +128,94 @@ def test_hmm_step_arithmetic_matches_oracle_on_the_host(cfg, dtype, ltol, gtol):
     assert abs(loss - ref_loss) <= ltol * abs(ref_loss)
     bad = compare_grads(grads, ref_grads, gtol)
     assert not bad, bad
+
+
+# ---- golden SVI iterations of the reference's own hmm.py (sequential form) ---------------------------------------------
+HMM_GOLDEN = ["hmm_c1", "hmm_c2_initial_point"]
+
+
+def hmm_golden_case(name):
+    """tests/golden/ref_step_hmm.pt: ``models/hmm.py`` (init_parameters, guide, model) run verbatim with ``vectorized=False``
+    -- the reference's own pyro.markov + TraceEnum_ELBO form of the model -- by tests/golden/make_golden_step.py under
+    tests/golden/minipyro.py, which evaluates the expectation over the guide's enumerated chain and spot presences by
+    brute force over every enumerated dimension (no forward recursion, no closed form)."""
+    from pathlib import Path
+
+    from tapqir_b200.utils.dataset import CosmosDataset
+
+    case = torch.load(Path(__file__).resolve().parent / "golden" / "ref_step_hmm.pt", weights_only=False)[name]
+    ds = CosmosDataset(case["images"].to(torch.float32), case["xy"], case["is_ontarget"], case["mask"].clone(), None,
+                       case["offset_samples"], case["offset_weights"])
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    return ds, data, case
+
+
+def adam_update(p, grads, m, v, t, lr=0.005):
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) on every tensor (model.py:168-171)."""
+    for k in p:
+        m[k] = 0.9 * m[k] + 0.1 * grads[k]
+        v[k] = 0.999 * v[k] + 0.001 * grads[k] ** 2
+        p[k] = p[k] - lr * (m[k] / (1 - 0.9 ** t)) / ((v[k] / (1 - 0.999 ** t)).sqrt() + 1e-8)
+
+
+@pytest.mark.parametrize("name", HMM_GOLDEN)
+def test_hmm_oracle_matches_reference_model_code(name):
+    """Initial parameters (hmm.py:419-467), then every recorded iteration: the closed form of SURVEY App. B.2 (forward
+    recursion) against the reference code's brute-force value -- loss 1e-12, gradients 1e-8 of each tensor's largest entry
+    (measured <= 7e-10), parameters after the last Adam update 1e-10."""
+    ds, data, case = hmm_golden_case(name)
+    init = H.to_unconstrained(H.init_constrained(data), data.P, data.dtype)
+    assert set(init) == set(case["init_unconstrained"])
+    for k, v in case["init_unconstrained"].items():
+        assert (init[k] - v.reshape(init[k].shape)).abs().max().item() <= 1e-13 * max(1.0, v.abs().max().item()), k
+    p = {k: v.reshape(init[k].shape).clone() for k, v in case["start"].items()}
+    m, v2 = {k: torch.zeros_like(x) for k, x in p.items()}, {k: torch.zeros_like(x) for k, x in p.items()}
+    for t, step in enumerate(case["steps"], 1):
+        loss, grads = H.loss_and_grads(p, data, step["ndx"], step["noise"])
+        assert abs(loss - step["loss"]) <= 1e-12 * abs(step["loss"]), (t, loss, step["loss"])
+        ref_grads = {k: g.reshape(p[k].shape) for k, g in step["grads"].items()}
+        bad = compare_grads(grads, ref_grads, 1e-8)
+        assert not bad, (t, bad)
+        adam_update(p, grads, m, v2, t)
+    for k, v in case["final"].items():
+        assert (p[k] - v.reshape(p[k].shape)).abs().max().item() <= 1e-10 * max(1.0, v.abs().max().item()), k
+
+
+@pytest.mark.parametrize("name", HMM_GOLDEN)
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
+def test_hmm_host_arithmetic_matches_reference_model_code(name, dtype, ltol, gtol):
+    """The hmm kernels' arithmetic (host build) against the same file, at the reference's parameters of every iteration;
+    fp32: nothing rounded on the reference side (global gradients on the scale of their parameter pair)."""
+    hc = hostcheck.load()
+    ds, data, case = hmm_golden_case(name)
+    shapes = {k: v.shape for k, v in H.init_constrained(data).items()}
+    p = {k: v.reshape(shapes[k]).clone() for k, v in case["start"].items()}
+    m, v2 = {k: torch.zeros_like(x) for k, x in p.items()}, {k: torch.zeros_like(x) for k, x in p.items()}
+    for t, step in enumerate(case["steps"], 1):
+        loss, grads = host_hmm_step(hc, data, p, step["ndx"], step["noise"], dtype)
+        assert abs(loss - step["loss"]) <= ltol * abs(step["loss"]), (t, loss, step["loss"])
+        ref_grads = {k: g.reshape(shapes[k]) for k, g in step["grads"].items()}
+        if dtype == torch.float64:
+            bad = compare_grads(grads, ref_grads, gtol)
+        else:
+            bad = compare_grads(grads, ref_grads, gtol, names=[k for k in ref_grads if k not in H.GLOBAL_PARAMS])
+            bad.update(hmm_global_grads(grads, ref_grads, gtol))
+        assert not bad, (t, bad)
+        _, og = H.loss_and_grads(p, data, step["ndx"], step["noise"])
+        adam_update(p, og, m, v2, t)
+
+
+HMM_GLOBAL_PAIRS = [("gain_loc", "gain_beta"), ("lamda_loc", "lamda_beta"), ("proximity_loc", "proximity_size"),
+                    ("init_mean", "init_size"), ("trans_mean", "trans_size")]
+
+
+def hmm_global_grads(ours, ref, tol):
+    """Global gradients against the largest entry of their distribution's parameter pair (tests/step_helpers.py)."""
+    bad = {}
+    for pair in HMM_GLOBAL_PAIRS:
+        scale = max(ref[k].double().abs().max().item() for k in pair)
+        for k in pair:
+            err = (ours[k].double().cpu().reshape(ref[k].shape) - ref[k].double()).abs().max().item()
+            if not err <= tol * scale:
+                bad[k] = err / scale
+    return bad

@@ -97,3 +97,46 @@ def test_fp32_production_kernels_within_north_star_of_reference_model_code(name)
         bad.update(compare_global_grads(eng.named_grads(), ref_grads, 1e-5))   # against the pair's largest entry, see there
         assert not bad, (it, bad)
         svi.step(step["ndx"], step["fdx"], step["noise"])
+
+
+# ---- hmm: tests/golden/ref_step_hmm.pt (models/hmm.py run verbatim in its sequential form) -----------------------------
+@pytest.mark.parametrize("name", ["hmm_c1", "hmm_c2_initial_point"])
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
+def test_hmm_iterations_match_reference_model_code(name, dtype, ltol, gtol):
+    """Every recorded iteration of the reference's hmm guide()/model() (brute-force expectation over the enumerated
+    chain) from the hmm kernels (chunked scans): loss and all gradients at the reference's parameters of that
+    iteration; fp64 additionally follows the Adam trajectory to the recorded final parameters."""
+    from oracle import hmm_oracle as H
+    from tests.test_hmm_cpu import adam_update, hmm_global_grads, hmm_golden_case
+    from tests.test_hmm_gpu import make_engine as make_hmm_engine
+
+    ds, data, case = hmm_golden_case(name)
+    shapes = {k: v.shape for k, v in H.init_constrained(data).items()}
+    p = {k: v.reshape(shapes[k]).clone() for k, v in case["start"].items()}
+    m, v2 = {k: torch.zeros_like(x) for k, x in p.items()}, {k: torch.zeros_like(x) for k, x in p.items()}
+    nb = case["config"]["nb"]
+    eng = make_hmm_engine(ds, data, p, nb, dtype)
+    traj = make_hmm_engine(ds, data, p, nb, dtype) if dtype == torch.float64 else None
+    for t, step in enumerate(case["steps"], 1):
+        eng.load_unconstrained(p)
+        lnoise = L.pack_local_noise(step["noise"], dtype, "cuda")
+        gnoise = eng.gl.pack_noise(step["noise"]).cuda()
+        ndx = step["ndx"].to(torch.int32).cuda()
+        loss = eng.step(update=False, ndx=ndx, local_noise=lnoise, global_noise=gnoise).item()
+        assert abs(loss - step["loss"]) <= ltol * abs(step["loss"]), (t, loss, step["loss"])
+        ref_grads = {k: g.reshape(shapes[k]) for k, g in step["grads"].items()}
+        if dtype == torch.float64:
+            bad = compare_grads(eng.named_grads(), ref_grads, gtol)
+        else:
+            bad = compare_grads(eng.named_grads(), ref_grads, gtol, names=[k for k in ref_grads if k not in H.GLOBAL_PARAMS])
+            bad.update(hmm_global_grads(eng.named_grads(), ref_grads, gtol))
+        assert not bad, (t, bad)
+        if traj is not None:
+            traj.step(ndx=ndx, local_noise=lnoise, global_noise=gnoise)
+        _, og = H.loss_and_grads(p, data, step["ndx"], step["noise"])
+        adam_update(p, og, m, v2, t)
+    if traj is not None:
+        ours = traj.named_unconstrained()
+        for k, v in case["final"].items():
+            err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
+            assert err <= 1e-8 * max(1.0, v.abs().max().item()), (k, err)
