@@ -73,7 +73,11 @@ def load_reference():
     cm = load("tapqir.models.cosmos", "tapqir/models/cosmos.py")
     # hmm.py: its vectorised form needs funsor (tapqir/handlers.py, tapqir/infer/); ``vectorized=False`` is the reference's
     # own sequential form of the same model (pyro.markov + TraceEnum_ELBO, hmm.py:126-131, 474-478) and needs neither
-    for name, attrs in {"funsor": {}, "pyro.distributions.hmm": {"_logmatmulexp": None, "_sequential_index": None},
+    def _logmatmulexp(x, y):      # pyro.distributions.hmm [third party]: log(exp(x) @ exp(y)), max-shifted
+        xs, ys = x.detach().max(-1, keepdim=True)[0], y.detach().max(-2, keepdim=True)[0]
+        return torch.matmul((x - xs).exp(), (y - ys).exp()).log() + xs + ys
+
+    for name, attrs in {"funsor": {}, "pyro.distributions.hmm": {"_logmatmulexp": _logmatmulexp, "_sequential_index": None},
                         "tapqir.handlers": {"trace": None, "vectorized_markov": None}, "tapqir.infer": {},
                         "tapqir.infer.elbo": {"TraceMarkovEnum_ELBO": None}}.items():
         mod = types.ModuleType(name)
@@ -197,7 +201,8 @@ def run_hmm_case(minipyro, ds_mod, hmm_mod, N, F, C, nb, seed, perturb, iters):
         steps.append(dict(ndx=ndx.clone(), noise={k: v.clone() for k, v in noise.items()}, loss=loss,
                           grads={k: v.clone() for k, v in model.svi.last_grads.items()}))
     final = {k: v.detach().clone() for k, v in store.items()}
-    return dict(config=dict(N=N, F=F, C=C, nb=nb, seed=seed, lr=0.005), images=sim.images.to(torch.int32), xy=sim.xy.double(),
+    z_probs = model.z_probs.clone()       # hmm.py:627-633 via its own _sequential_logmatmulexp (:480-533), all AOIs
+    return dict(config=dict(N=N, F=F, C=C, nb=nb, seed=seed, lr=0.005), z_probs=z_probs, images=sim.images.to(torch.int32), xy=sim.xy.double(),
                 is_ontarget=sim.is_ontarget, mask=sim.mask.clone(), offset_samples=sim.offset.samples.double(),
                 offset_weights=sim.offset.weights.double(), init_unconstrained=init_unconstrained, start=start, steps=steps,
                 final=final)
@@ -215,6 +220,7 @@ def main():
     hmm_cases = {
         "hmm_c1": dict(N=3, F=4, C=1, nb=2, seed=5, perturb=True, iters=3),
         "hmm_c2_initial_point": dict(N=2, F=3, C=2, nb=2, seed=6, perturb=False, iters=3),
+        "hmm_zprobs_only": dict(N=3, F=23, C=2, nb=3, seed=7, perturb=True, iters=0),       # odd chain length for the scan
     }
     hmm_out = {name: run_hmm_case(minipyro, ds_mod, hmm_mod, **kw) for name, kw in hmm_cases.items()}
     torch.save(hmm_out, HERE / "ref_step_hmm.pt")

@@ -219,3 +219,15 @@ def hmm_global_grads(ours, ref, tol):
             if not err <= tol * scale:
                 bad[k] = err / scale
     return bad
+
+
+@pytest.mark.parametrize("name", HMM_GOLDEN + ["hmm_zprobs_only"])
+def test_hmm_z_probs_match_reference_model_code(name):
+    """hmm.z_probs (hmm.py:627-633, the reference's own parallel scan ``_sequential_logmatmulexp`` :480-533) at the
+    recorded final parameters, chains of 3, 4 and 23 frames: the oracle's plain forward recursion, 1e-13."""
+    ds, data, case = hmm_golden_case(name)
+    shapes = {k: v.shape for k, v in H.init_constrained(data).items()}
+    final = {k: v.reshape(shapes[k]) for k, v in case["final"].items()}
+    zp = H.z_probs(final, data)
+    assert zp.shape == case["z_probs"].shape == (data.Nt, data.F, data.C, 2)
+    assert (zp - case["z_probs"]).abs().max().item() <= 1e-13

@@ -140,3 +140,18 @@ def test_hmm_iterations_match_reference_model_code(name, dtype, ltol, gtol):
         for k, v in case["final"].items():
             err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
             assert err <= 1e-8 * max(1.0, v.abs().max().item()), (k, err)
+
+
+@pytest.mark.parametrize("name", ["hmm_c1", "hmm_zprobs_only"])
+def test_hmm_z_probs_match_reference_model_code(name):
+    """hmm.z_probs (hmm.py:627-633, the reference's own ``_sequential_logmatmulexp`` scan) at the recorded parameters."""
+    from oracle import hmm_oracle as H
+    from tests.test_hmm_cpu import hmm_golden_case
+    from tests.test_hmm_gpu import make_engine as make_hmm_engine
+
+    ds, data, case = hmm_golden_case(name)
+    shapes = {k: v.shape for k, v in H.init_constrained(data).items()}
+    final = {k: v.reshape(shapes[k]).clone() for k, v in case["final"].items()}
+    eng = make_hmm_engine(ds, data, final, case["config"]["nb"], torch.float64)
+    zp = eng.z_probs().cpu().double()
+    assert zp.shape == case["z_probs"].shape and (zp - case["z_probs"]).abs().max().item() <= 1e-12
