@@ -208,8 +208,42 @@ def run_hmm_case(minipyro, ds_mod, hmm_mod, N, F, C, nb, seed, perturb, iters):
                 final=final)
 
 
+def run_data_case(ds_mod):
+    """``data.tpqr`` as written by the reference's own ``utils/dataset.py::save`` (:195-213), plus what its CosmosDataset /
+    OffsetData report for it -- the state-file contract of SURVEY 8(b)."""
+    import numpy as np
+
+    from tapqir_b200.utils.simulate import simulate
+
+    N, F, C = 4, 5, 2
+    s = torch.arange(85.0, 96.0)
+    w = torch.exp(-0.5 * ((s - 90) / 2.5) ** 2)
+    sim = simulate(N, F, C=C, seed=11, offset_samples=s, offset_weights=w / w.sum())
+    labels = np.zeros((N // 2, F, C), dtype=[("aoi", int), ("frame", int), ("z", int)])      # simulate.py:110-113
+    labels["aoi"] = np.arange(N // 2).reshape(-1, 1, 1)
+    labels["frame"] = np.arange(F).reshape(-1, 1)
+    labels["z"] = (np.arange(N // 2 * F * C).reshape(N // 2, F, C) % 3 == 0)
+    mask = torch.tensor([True, True, False, True])
+    ref = ds_mod.CosmosDataset(sim.images.double(), sim.xy.double(), sim.is_ontarget, mask, labels, sim.offset.samples.double(),
+                               sim.offset.weights.double(), name="golden", time1=torch.arange(F).double(), ttb=None,
+                               channels=("green", "red"))
+    out_dir = HERE / "ref_data"
+    out_dir.mkdir(exist_ok=True)
+    ds_mod.save(ref, out_dir)
+    facts = dict(N=int(ref.N), Nc=int(ref.Nc), Nt=int(ref.Nt), F=ref.F, C=ref.C, P=ref.P, median=ref.median.clone(),
+                 x=ref.x.clone(), y=ref.y.clone(), offset_min=ref.offset.min, offset_max=ref.offset.max,
+                 offset_mean=ref.offset.mean, offset_var=ref.offset.var, offset_logits=ref.offset.logits.clone(),
+                 channels=ref.channels, name=ref.name)
+    ndx, fdx, cdx = torch.tensor([3, 0])[:, None, None], torch.tensor([4, 1, 2])[:, None], torch.arange(C)
+    obs, target, ont = ref.fetch(ndx, fdx, cdx)                                                  # dataset.py:140-151
+    facts.update(fetch_ndx=ndx, fetch_fdx=fdx, fetch_obs=obs.clone(), fetch_target=target.clone(), fetch_ontarget=ont.clone())
+    torch.save(facts, out_dir / "facts.pt")
+    print("wrote", out_dir)
+
+
 def main():
     minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
+    run_data_case(ds_mod)
     cases = {
         "c1_initial_point": dict(N=4, F=6, C=1, nb=3, fb=4, seed=0, offsets="sim", perturb=False, masked=None, iters=5),
         "c1_perturbed_masked": dict(N=5, F=6, C=1, nb=4, fb=4, seed=1, offsets="sim", perturb=True, masked=2, iters=5),
