@@ -241,9 +241,42 @@ def run_data_case(ds_mod):
     print("wrote", out_dir)
 
 
+def run_c1_fit(minipyro, ds_mod, cosmos_mod, iters=100, seed=0):
+    """BASELINE.json configs[0]: cosmos, simulated N=5 AOIs x F=100 frames, P=14, K=2, 100 SVI iterations on the CPU, full
+    batch (the reference's test-suite scale, test/test_tapqir.py:22-50,91-93, which asserts only the exit code).  Only the
+    losses and the parameters after the last update are stored: with a full batch nothing but the guide's variates consumes
+    the random stream, in the guide's site order, so ``torch.manual_seed(seed)`` + the same draws (oracle.draw_noise)
+    reproduce the run; the first iteration's variates are stored to check that alignment."""
+    from tapqir_b200.utils.simulate import simulate
+
+    N, F = 5, 100
+    sim = simulate(N, F, C=1, seed=seed)
+    model = cosmos_mod.cosmos(device="cpu", dtype="double", use_pykeops=False)
+    model.data = ds_mod.CosmosDataset(sim.images.double(), sim.xy.double(), sim.is_ontarget, sim.mask.clone(), None,
+                                      sim.offset.samples.double(), sim.offset.weights.double())
+    model.run_path = Path(tempfile.mkdtemp())
+    assert sim.images.max() < 32768
+    model.init(lr=0.005, nbatch_size=N, fbatch_size=F)
+    torch.manual_seed(seed + 1000)
+    losses, first = [], None
+    for it in range(iters):
+        losses.append(model.svi.step())
+        if it == 0:
+            first = noise_from_trace(model.elbo.last_guide_trace, model.K)
+    store = minipyro.get_param_store().unconstrained()
+    return dict(config=dict(N=N, F=F, C=1, nb=N, fb=F, seed=seed, rng_seed=seed + 1000, lr=0.005, iters=iters),
+                images=sim.images.to(torch.int16), xy=sim.xy.double(), is_ontarget=sim.is_ontarget, mask=sim.mask.clone(),
+                offset_samples=sim.offset.samples.double(), offset_weights=sim.offset.weights.double(),
+                losses=torch.tensor(losses, dtype=torch.float64), first_noise=first,
+                final={k: v.detach().clone() for k, v in store.items()})
+
+
 def main():
     minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
     run_data_case(ds_mod)
+    c1 = run_c1_fit(minipyro, ds_mod, cosmos_mod)
+    torch.save(c1, HERE / "ref_c1_fit.pt")
+    print("c1 fit: loss", c1["losses"][0].item(), "->", c1["losses"][-1].item())
     cases = {
         "c1_initial_point": dict(N=4, F=6, C=1, nb=3, fb=4, seed=0, offsets="sim", perturb=False, masked=None, iters=5),
         "c1_perturbed_masked": dict(N=5, F=6, C=1, nb=4, fb=4, seed=1, offsets="sim", perturb=True, masked=2, iters=5),

@@ -106,7 +106,7 @@ def masked_loss_constant(case, step):
 GLOBAL_PAIRS = [("gain_loc", "gain_beta"), ("lamda_loc", "lamda_beta"), ("proximity_loc", "proximity_size"), ("pi_mean", "pi_size")]
 
 
-def compare_global_grads(ours, ref, tol):
+def compare_global_grads(ours, ref, tol, running_scale=None):
     """Global gradients are one to four numbers each; measured against themselves they have no scale when they pass
     through zero.  The two parameters of one guide distribution (mean-like, concentration-like) share their terms: the
     gradient of the concentration-like one is the difference of two terms of the mean-like one's size (moving it keeps
@@ -115,9 +115,30 @@ def compare_global_grads(ours, ref, tol):
     bad = {}
     for pair in GLOBAL_PAIRS:
         scale = max(ref[k].double().abs().max().item() for k in pair)
+        if running_scale is not None:
+            # along a fit the global gradients go to zero (gain: 118 k at the first iteration, 24 k at the 91st) while
+            # the fp32 error of the sums they are made of stays put (0.2-0.5 for gain at C1); what Adam divides by is the
+            # running scale of the gradient, so that is what the error is measured against
+            scale = running_scale[pair] = max(scale, running_scale.get(pair, 0.0))
         for k in pair:
             r = ref[k].double()
             err = (ours[k].double().cpu().reshape(r.shape) - r).abs().max().item()
             if not err <= tol * scale:
                 bad[k] = err / scale
     return bad
+
+
+def golden_c1_fit():
+    """tests/golden/ref_c1_fit.pt: BASELINE configs[0] (N=5 x F=100, full batch, 100 SVI iterations) run by the reference's
+    own cosmos.py / model.py (tests/golden/make_golden_step.py::run_c1_fit).  Only losses and final parameters are stored:
+    with a full batch the guide's variates are the only consumers of torch's random stream, in the guide's site order, so
+    ``torch.manual_seed(rng_seed)`` + ``oracle.draw_noise`` at the current parameters reproduces every draw."""
+    from pathlib import Path
+
+    from tapqir_b200.utils.dataset import CosmosDataset
+
+    case = torch.load(Path(__file__).resolve().parent / "golden" / "ref_c1_fit.pt", weights_only=False)
+    ds = CosmosDataset(case["images"].to(torch.float32), case["xy"], case["is_ontarget"], case["mask"].clone(), None,
+                       case["offset_samples"], case["offset_weights"])
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    return ds, data, case

@@ -105,3 +105,46 @@ def test_step_f32_within_north_star_of_reference_model_code(name):
         bad.update(compare_global_grads(grads, ref_grads, 1e-5))      # against the pair's largest entry, see there
         assert not bad, bad
         svi.step(step["ndx"], step["fdx"], step["noise"])
+
+
+def test_c1_hundred_iterations_of_the_kernel_arithmetic_match_the_reference_run():
+    """BASELINE configs[0] (tests/golden/ref_c1_fit.pt: the reference's own 100-iteration fit): the fp64 host build of the
+    kernels with a dense Adam follows it from the same seed -- every loss 1e-11, final parameters 1e-8; the fp32
+    production arithmetic, evaluated every tenth iteration at that trajectory's parameters on identical fp32-rounded
+    inputs, stays within loss 1e-6 / gradients 1e-5 of the fp64 one (global gradients against their running scale over the
+    fit, step_helpers.compare_global_grads)."""
+    from tests.step_helpers import compare_global_grads, golden_c1_fit
+
+    hc = hostcheck.load()
+    ds, data, case = golden_c1_fit()
+    cfg = case["config"]
+    p = O.to_unconstrained(O.init_constrained(data), data.P, data.dtype)
+    m, v2 = {k: torch.zeros_like(x) for k, x in p.items()}, {k: torch.zeros_like(x) for k, x in p.items()}
+    ndx, fdx = torch.arange(cfg["N"]), torch.arange(cfg["F"])
+    scales = {}
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(cfg["rng_seed"])
+        for t in range(1, cfg["iters"] + 1):
+            noise = O.draw_noise(p, data, ndx, fdx)
+            loss, grads, _ = host_step(hc, data, p, ndx, fdx, noise, torch.float64)
+            assert abs(loss - case["losses"][t - 1].item()) <= 1e-11 * abs(loss), (t, loss)
+            if t % 10 == 1:
+                # identical (fp32-representable) inputs on both sides, as the north star words it
+                pr, nr = {k: v.float().double() for k, v in p.items()}, {k: v.float().double() for k, v in noise.items()}
+                loss64, grads64, _ = host_step(hc, data, pr, ndx, fdx, nr, torch.float64)
+                loss32, grads32, _ = host_step(hc, data, pr, ndx, fdx, nr, torch.float32)
+                assert abs(loss32 - loss64) <= 1e-6 * abs(loss64), t
+                ref = {k: g.reshape(p[k].shape) for k, g in grads64.items()}
+                bad = compare_grads(grads32, ref, 1e-5, names=L.LOCAL_NAMES)
+                bad.update(compare_global_grads(grads32, ref, 1e-5, running_scale=scales))
+                assert not bad, (t, bad)
+            for k in p:
+                g = grads[k].reshape(p[k].shape)
+                m[k] = 0.9 * m[k] + 0.1 * g
+                v2[k] = 0.999 * v2[k] + 0.001 * g * g
+                p[k] = p[k] - cfg["lr"] * (m[k] / (1 - 0.9 ** t)) / ((v2[k] / (1 - 0.999 ** t)).sqrt() + 1e-8)
+    finally:
+        torch.set_rng_state(state)
+    for k, v in case["final"].items():
+        assert (p[k] - v.reshape(p[k].shape)).abs().max().item() <= 1e-8, k

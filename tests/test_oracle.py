@@ -485,3 +485,30 @@ def test_compute_probs_matches_reference_model_code(ref_steps, name):
     assert (z - zr[:n_on]).abs().max().item() <= 1e-9 and (th - thr[:, :n_on]).abs().max().item() <= 1e-9
     assert zr[n_on:].abs().max().item() == 0 and thr[:, n_on:].abs().max().item() == 0
     assert 0.0 < zr[:n_on, ..., 1].max().item() <= 1.0
+
+
+def test_c1_hundred_iterations_match_the_reference_run():
+    """BASELINE configs[0]: the reference's own 100-iteration fit at N=5 x F=100 (tests/golden/ref_c1_fit.pt), replayed by
+    the oracle from the same seed: every loss 1e-12 (measured 1.4e-14), parameters after 100 Adam updates 1e-8
+    (measured 2.5e-10)."""
+    from tests.step_helpers import golden_c1_fit
+
+    ds, data, case = golden_c1_fit()
+    cfg = case["config"]
+    svi = O.OracleSVI(data, lr=cfg["lr"], nbatch_size=cfg["nb"], fbatch_size=cfg["fb"])
+    ndx, fdx = torch.arange(cfg["N"]), torch.arange(cfg["F"])
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(cfg["rng_seed"])
+        for it in range(cfg["iters"]):
+            noise = O.draw_noise(svi.params, data, ndx, fdx)
+            if it == 0:     # the random stream lines up with the reference's guide
+                for k, v in case["first_noise"].items():
+                    close(noise[k], v.reshape(noise[k].shape), 1e-14)
+            loss = svi.step(ndx, fdx, noise)
+            assert abs(loss - case["losses"][it].item()) <= 1e-12 * abs(loss), (it, loss, case["losses"][it].item())
+    finally:
+        torch.set_rng_state(state)
+    for k, v in case["final"].items():
+        assert (svi.params[k].detach() - v.reshape(svi.params[k].shape)).abs().max().item() <= 1e-8, k
+    assert case["losses"][-10:].mean() < 0.9 * case["losses"][:10].mean()       # and it is a fit: the loss went down
