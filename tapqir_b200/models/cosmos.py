@@ -267,35 +267,10 @@ class cosmos(Model):
         Mean and ``CI`` credible interval of every guide distribution + the posterior summaries
         (reference: cosmos.py:711-784; scipy inverse CDFs on the CPU as in stats.py:262-293).
         """
-        import scipy.stats as st
+        from tapqir_b200.utils.stats import credible_intervals
 
-        P = self.data.P
-        half = (P + 1) / 2
-        v = lambda name: self.param(name).detach().double().cpu()
-        gamma = lambda loc, beta: (st.gamma((loc * beta).numpy(), scale=(1 / beta).numpy()), loc)
-
-        def affine_beta(mean, size, lo, hi):
-            c1, c0 = size * (mean - lo) / (hi - lo), size * (hi - mean) / (hi - lo)
-            return st.beta(a=c1.numpy(), b=c0.numpy(), loc=lo, scale=hi - lo), mean
-
-        conc = v("pi_mean") * v("pi_size")
-        dists = {
-            "gain": gamma(v("gain_loc"), v("gain_beta")),
-            # Dirichlet marginals are Beta(conc_i, sum - conc_i) (stats.py:281-288)
-            "pi": (st.beta(a=conc.numpy(), b=(conc.sum(-1, keepdim=True) - conc).numpy()), conc / conc.sum(-1, keepdim=True)),
-            "lamda": gamma(v("lamda_loc"), v("lamda_beta")),
-            "proximity": affine_beta(v("proximity_loc"), v("proximity_size"), 0.0, (P + 1) / math.sqrt(12)),
-            "background": gamma(v("b_loc"), v("b_beta")),
-            "height": gamma(v("h_loc"), v("h_beta")),
-            "width": affine_beta(v("w_mean"), v("w_size"), self.priors["width_min"], self.priors["width_max"]),
-            "x": affine_beta(v("x_mean"), v("size"), -half, half),
-            "y": affine_beta(v("y_mean"), v("size"), -half, half),
-        }
-        params = {}
-        for name in self.ci_params:
-            dist, mean = dists[name]
-            LL, UL = dist.interval(CI)
-            params[name] = {"LL": torch.as_tensor(LL), "UL": torch.as_tensor(UL), "Mean": mean}
+        value = lambda name: self.param(name).detach().double().cpu()
+        params = credible_intervals(self.ci_params, value, self.data.P, self.priors, CI)
         params["m_probs"] = self.m_probs.cpu()
         params["z_probs"] = self.z_probs.cpu()
         params["theta_probs"] = self.theta_probs.cpu()

@@ -39,6 +39,60 @@ def hpdi(samples: torch.Tensor, prob: float) -> Tuple[torch.Tensor, torch.Tensor
     return s[i], s[i + mass]
 
 
+def guide_scipy_dist(name, value, P, priors):
+    """
+    ``(scipy frozen distribution, mean)`` of the guide of the latent ``name`` (``model.ci_params``), from the constrained
+    variational parameters ``value(param_name) -> CPU double tensor``.  Reference: the branches of ``compute_params``
+    (cosmos.py:713-772) followed by ``torch_to_scipy_dist`` (stats.py:262-293): Gamma(loc * beta, rate beta);
+    Dirichlet(mean * size) summarised by its Beta marginals (``pi``; hmm's ``init`` and ``trans``); AffineBeta as a
+    located and scaled Beta.
+    """
+    import math
+
+    import scipy.stats as st
+
+    half = (P + 1) / 2
+
+    def gamma(loc, beta):
+        return st.gamma((loc * beta).numpy(), scale=(1 / beta).numpy()), loc
+
+    def affine_beta(mean, size, lo, hi):
+        c1, c0 = size * (mean - lo) / (hi - lo), size * (hi - mean) / (hi - lo)
+        return st.beta(a=c1.numpy(), b=c0.numpy(), loc=lo, scale=hi - lo), mean
+
+    if name in ("pi", "init", "trans"):
+        conc = value(f"{name}_mean") * value(f"{name}_size")
+        total = conc.sum(-1, keepdim=True)
+        return st.beta(a=conc.numpy(), b=(total - conc).numpy()), conc / total
+    if name == "gain":
+        return gamma(value("gain_loc"), value("gain_beta"))
+    if name == "lamda":
+        return gamma(value("lamda_loc"), value("lamda_beta"))
+    if name == "proximity":
+        return affine_beta(value("proximity_loc"), value("proximity_size"), 0.0, (P + 1) / math.sqrt(12))
+    if name == "background":
+        return gamma(value("b_loc"), value("b_beta"))
+    if name == "height":
+        return gamma(value("h_loc"), value("h_beta"))
+    if name == "width":
+        return affine_beta(value("w_mean"), value("w_size"), priors["width_min"], priors["width_max"])
+    if name == "x":
+        return affine_beta(value("x_mean"), value("size"), -half, half)
+    if name == "y":
+        return affine_beta(value("y_mean"), value("size"), -half, half)
+    raise NotImplementedError(f"no credible interval for '{name}'")
+
+
+def credible_intervals(ci_params, value, P, priors, CI):
+    """``{name: {"LL", "UL", "Mean"}}`` for every latent in ``ci_params`` (cosmos.py:773-778)."""
+    out = {}
+    for name in ci_params:
+        dist, mean = guide_scipy_dist(name, value, P, priors)
+        LL, UL = dist.interval(CI)
+        out[name] = {"LL": torch.as_tensor(LL), "UL": torch.as_tensor(UL), "Mean": mean}
+    return out
+
+
 def snr_and_chi2(data, height, width, x, y, target_locs, background, gain, offset_mean, offset_var, P,
                  theta_probs) -> Tuple[torch.Tensor, torch.Tensor]:
     r"""

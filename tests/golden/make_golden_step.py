@@ -52,9 +52,14 @@ def load_reference():
         mod.__path__ = []
         sys.modules[name] = mod
     sys.modules["tapqir"].__version__ = "reference"
-    stats = types.ModuleType("tapqir.utils.stats")      # imports matplotlib; only post-processing helpers live there
-    stats.save_stats = stats.torch_to_scipy_dist = None
-    sys.modules["tapqir.utils.stats"] = stats
+    for name in ("matplotlib", "matplotlib.pyplot"):      # utils/stats.py imports them for the rastergram PNGs only
+        sys.modules[name] = types.ModuleType(name)
+    # SciPy 1.11 renamed ``rv_frozen.interval(alpha=...)`` to ``confidence``; cosmos.compute_params (cosmos.py:774) still
+    # passes ``alpha``.  Accept both, as the SciPy versions the reference was written for did.
+    from scipy.stats._distn_infrastructure import rv_frozen
+
+    _interval = rv_frozen.interval
+    rv_frozen.interval = lambda self, confidence=None, alpha=None: _interval(self, alpha if confidence is None else confidence)
 
     def load(name, rel):
         spec = importlib.util.spec_from_file_location(name, REF / rel)
@@ -69,6 +74,7 @@ def load_reference():
     ab = load("tapqir.distributions.affine_beta", "tapqir/distributions/affine_beta.py")
     sys.modules["tapqir.distributions"].KSMOGN, sys.modules["tapqir.distributions"].AffineBeta = ks.KSMOGN, ab.AffineBeta
     ds = load("tapqir.utils.dataset", "tapqir/utils/dataset.py")
+    load("tapqir.utils.stats", "tapqir/utils/stats.py")
     load("tapqir.models.model", "tapqir/models/model.py")
     cm = load("tapqir.models.cosmos", "tapqir/models/cosmos.py")
     # hmm.py: its vectorised form needs funsor (tapqir/handlers.py, tapqir/infer/); ``vectorized=False`` is the reference's
@@ -202,7 +208,16 @@ def run_hmm_case(minipyro, ds_mod, hmm_mod, N, F, C, nb, seed, perturb, iters):
                           grads={k: v.clone() for k, v in model.svi.last_grads.items()}))
     final = {k: v.detach().clone() for k, v in store.items()}
     z_probs = model.z_probs.clone()       # hmm.py:627-633 via its own _sequential_logmatmulexp (:480-533), all AOIs
-    return dict(config=dict(N=N, F=F, C=C, nb=nb, seed=seed, lr=0.005), z_probs=z_probs, images=sim.images.to(torch.int32), xy=sim.xy.double(),
+    # credible intervals of the two sites cosmos does not have: the branches of cosmos.compute_params for "init" / "trans"
+    # (cosmos.py:722-725 + :773-778); the method as a whole needs hmm.theta_probs, which is written in funsor terms
+    from tapqir.utils.stats import torch_to_scipy_dist
+
+    ci = {}
+    for name in ("init", "trans"):
+        fn = minipyro.Dirichlet(minipyro.param(f"{name}_mean") * minipyro.param(f"{name}_size"))
+        LL, UL = torch_to_scipy_dist(fn).interval(alpha=0.95)
+        ci[name] = dict(LL=torch.as_tensor(LL).clone(), UL=torch.as_tensor(UL).clone(), Mean=fn.mean.detach().clone())
+    return dict(config=dict(N=N, F=F, C=C, nb=nb, seed=seed, lr=0.005), z_probs=z_probs, ci=ci, CI=0.95, images=sim.images.to(torch.int32), xy=sim.xy.double(),
                 is_ontarget=sim.is_ontarget, mask=sim.mask.clone(), offset_samples=sim.offset.samples.double(),
                 offset_weights=sim.offset.weights.double(), init_unconstrained=init_unconstrained, start=start, steps=steps,
                 final=final)
@@ -264,7 +279,9 @@ def run_c1_fit(minipyro, ds_mod, cosmos_mod, iters=100, seed=0):
         if it == 0:
             first = noise_from_trace(model.elbo.last_guide_trace, model.K)
     store = minipyro.get_param_store().unconstrained()
-    return dict(config=dict(N=N, F=F, C=1, nb=N, fb=F, seed=seed, rng_seed=seed + 1000, lr=0.005, iters=iters),
+    stats = model.compute_params(0.95)                  # cosmos.py:711-784 (scipy intervals through stats.torch_to_scipy_dist)
+    ci = {k: {s: torch.as_tensor(v).clone() for s, v in stats[k].items()} for k in model.ci_params}
+    return dict(config=dict(N=N, F=F, C=1, nb=N, fb=F, seed=seed, rng_seed=seed + 1000, lr=0.005, iters=iters), ci=ci, CI=0.95,
                 images=sim.images.to(torch.int16), xy=sim.xy.double(), is_ontarget=sim.is_ontarget, mask=sim.mask.clone(),
                 offset_samples=sim.offset.samples.double(), offset_weights=sim.offset.weights.double(),
                 losses=torch.tensor(losses, dtype=torch.float64), first_noise=first,

@@ -547,7 +547,7 @@ def install():
 
     dist = module("pyro.distributions", TorchDistribution=TorchDistribution, HalfNormal=HalfNormal, Dirichlet=Dirichlet,
                   Exponential=Exponential, Gamma=Gamma, Categorical=Categorical, Bernoulli=Bernoulli, Beta=Beta, Delta=Delta,
-                  AffineBeta=AffineBeta)
+                  AffineBeta=AffineBeta, Independent=Independent)
     dist.__path__ = []
     module("pyro.distributions.util", broadcast_shape=broadcast_shape)
     ops = module("pyro.ops")
