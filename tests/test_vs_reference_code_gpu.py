@@ -188,3 +188,34 @@ def test_c1_hundred_iterations_match_the_reference_run():
     for k, v in case["final"].items():
         err = (ours[k].double().cpu().reshape(-1) - v.reshape(-1)).abs().max().item()
         assert err <= 1e-7 * max(1.0, v.abs().max().item()), (k, err)
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes ran out: not yet run on a device")
+def test_hmm_compute_stats_writes_reference_files(tmp_path):
+    """`tapqir stats` for cosmos+hmm: credible intervals of hmm's own latents (``init``, ``trans``; hmm.py:70-81) next to
+    the shared ones, posterior summaries and the three files (stats.py:131-258).  The interval arithmetic itself is pinned
+    on the CPU (tests/test_stats_cpu.py)."""
+    import pandas as pd
+
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    save(simulate(4, 12, C=1, P=14, seed=3, params={"kon": 0.2, "koff": 0.2}), tmp_path)
+    model = models["cosmos+hmm"](device="cuda", dtype="float")
+    model.load(tmp_path)
+    model.init(lr=0.005, nbatch_size=4)
+    model.run(20, progress_bar=lambda it: it)
+    model.compute_stats(CI=0.95, save_matlab=True)
+    params = torch.load(tmp_path / "cosmos+hmm_params.tpqr", weights_only=False)
+    Nt, F, K, Q = 4, 12, 2, 1
+    for name, shape in (("gain", ()), ("init", (Q, 2)), ("trans", (Q, 2, 2)), ("lamda", (Q,)), ("proximity", ()),
+                        ("background", (Nt, F, Q)), ("height", (K, Nt, F, Q)), ("x", (K, Nt, F, Q))):
+        for key in ("LL", "UL", "Mean"):
+            assert tuple(params[name][key].shape) == shape, (name, key)
+        assert (params[name]["LL"] <= params[name]["Mean"]).all() and (params[name]["Mean"] <= params[name]["UL"]).all()
+    assert params["m_probs"].shape == (K, Nt, F, Q) and params["z_probs"].shape == (Nt, F, Q, 2)
+    assert params["theta_probs"].shape == (K, Nt, F, Q) and params["z_map"].shape == (Nt, F, Q)
+    summary = pd.read_csv(tmp_path / "cosmos+hmm_summary.csv", index_col=0)
+    assert {"gain", "proximity", "lamda", "trans", "SNR_0", "MCC"} <= set(summary.index)
+    assert (tmp_path / "cosmos+hmm_params.mat").exists()
