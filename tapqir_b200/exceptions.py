@@ -1,36 +1,41 @@
 """
-Error types of the drop-in boundary (reference: tapqir/exceptions.py:8-39).  Same class names,
-constructor arguments and messages so callers that catch them keep working.
+Error types of the drop-in boundary.  The reference's callers catch these by name and read ``.msg`` / ``.name`` /
+``.path`` (tapqir/exceptions.py:8-39, raised at models/model.py:233-235,341 and utils/dataset.py:219-221), so the class
+names, constructor arguments, attributes and message texts are part of the contract; ``NativeLibraryError`` is this
+repository's own (no CPU fallback exists, a missing sm_100a library is an error).
 """
 
-from pathlib import Path
-from typing import Union
+__all__ = ["TapqirException", "TapqirFileNotFoundError", "CudaOutOfMemoryError", "NativeLibraryError"]
 
 
 class TapqirException(Exception):
-    """Root of the error hierarchy; ``msg`` must be non-empty."""
+    """Root of the hierarchy: carries a non-empty message in ``msg``."""
 
-    def __init__(self, msg, *args):
-        assert msg
+    def __init__(self, msg, *extra):
+        if not msg:
+            raise AssertionError("a TapqirException needs a message")
+        Exception.__init__(self, msg, *extra)
         self.msg = msg
-        super().__init__(msg, *args)
 
 
 class TapqirFileNotFoundError(TapqirException):
-    """A data / model / parameter / summary file expected at ``path`` is missing."""
+    """A file of kind ``name`` ("data", "model", "parameter", "summary") expected at ``path`` does not exist."""
 
-    def __init__(self, name: str, path: Union[str, Path]):
-        self.name = name
-        self.path = path
-        super().__init__(f"Unable to find {name} file '{path}'")
+    template = "Unable to find {name} file '{path}'"
+
+    def __init__(self, name, path):
+        TapqirException.__init__(self, self.template.format(name=name, path=path))
+        self.name, self.path = name, path
 
 
 class CudaOutOfMemoryError(TapqirException):
-    """The device ran out of memory; the fix is a smaller AOI / frame minibatch."""
+    """The device ran out of memory during a step or while computing statistics."""
+
+    message = "CUDA out of memory. Try to use smaller AOI/frame batch size"
 
     def __init__(self):
-        super().__init__("CUDA out of memory. Try to use smaller AOI/frame batch size")
+        TapqirException.__init__(self, self.message)
 
 
 class NativeLibraryError(TapqirException):
-    """The sm_100a shared library is missing or could not be loaded.  There is no CPU fallback."""
+    """libtapqir_b200.so (sm_100a) is missing or could not be loaded."""
