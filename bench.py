@@ -157,13 +157,19 @@ def measure_peaks(lib, _lib, device):
     return out
 
 
-def make_shard(workload, rank, device):
+def make_shard(workload, rank, device, offset_hist=0):
     from tapqir_b200.utils.simulate import simulate
 
     n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
     kinetic = {"kon": 0.2, "koff": 0.2} if WORKLOAD_MODEL.get(workload) == "cosmos+hmm" else None   # test_tapqir.py:31-33
+    kw = {}
+    if offset_hist:     # SURVEY 8d "secondary realism run": a non-degenerate offset histogram of `offset_hist` distinct bins
+        s = torch.arange(90 - offset_hist // 2, 90 - offset_hist // 2 + offset_hist, dtype=torch.float64)
+        w = torch.exp(-0.5 * ((s - 90) / max(offset_hist / 8.0, 1.0)) ** 2) + 1e-4
+        kw = dict(offset_samples=s, offset_weights=w / w.sum())
+        desc += f"; offsets: Gaussian-shaped histogram of {offset_hist} distinct integer bins around 90 instead of O=3"
     ds = simulate(n_aoi, n_frames, C=WORKLOAD_CHANNELS.get(workload, 1), P=14, seed=rank, device=device, aoi_chunk=50,
-                  params=kinetic)
+                  params=kinetic, **kw)
     return ds, nb, fb, desc
 
 
@@ -181,7 +187,7 @@ def run_native(args):
         torch.distributed.init_process_group("nccl", device_id=device)
     lib = _lib.load()  # raises if the sm_100a library is missing: no fallback
 
-    ds, nb, fb, desc = make_shard(args.workload, rank, device)
+    ds, nb, fb, desc = make_shard(args.workload, rank, device, args.offset_hist)
     model = model_registry[WORKLOAD_MODEL.get(args.workload, "cosmos")](device=str(device), dtype="float")
     model.data = ds
     model.merge_offsets = not args.keep_offset_bins
@@ -255,12 +261,13 @@ def run_native(args):
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists():
-        t = json.loads(tj.read_text()).get("ksmogn_stream_kernel" if o_exec == 1 else "ksmogn_stream_kernel_o3", {})
+        t = json.loads(tj.read_text()).get({1: "ksmogn_stream_kernel", 3: "ksmogn_stream_kernel_o3"}.get(o_exec, "none"), {})
         if t.get("workload") == args.workload and t.get("units_per_launch") == patches_per_step:
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
                        "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step, "source": t["source"]}
     roofline = {
-        "kernel": f"ksmogn_stream_kernel<uint16,{o_exec},true,true> (fused render + offset-marginalised likelihood fwd+bwd)",
+        "kernel": f"ksmogn_stream_kernel<uint16,{o_exec if o_exec <= 4 else 0},true,true> (fused render + offset-marginalised "
+                  f"likelihood fwd+bwd" + ("; O > 4 runs the two-pass form, the work counts are the cached-offset form's" if o_exec > 4 else "") + ")",
         "bound": bound[1],
         "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
         "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
@@ -340,7 +347,7 @@ def run_native(args):
             "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value, "unit": "AOI-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "model": model.name, "channels": eng.C, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": O_BINS,
+            "config": {"workload": desc, "model": model.name, "channels": eng.C, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": args.offset_hist or O_BINS,
                        "offset_bins_distinct": o_exec, "train_iters_before_timing": args.train_iters,
                        "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
                        "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},
@@ -436,6 +443,9 @@ def main():
     ap.add_argument("--trained-iters", type=int, default=2000,
                     help="after the timed steps, run this many more SVI iterations and time K steps again (reported as "
                          "`trained_state`); 0 to skip")
+    ap.add_argument("--offset-hist", type=int, default=0, metavar="O",
+                    help="simulate with a histogram of O distinct offset bins (SURVEY 8d's secondary realism run, e.g. 64) "
+                         "instead of the reference simulator's three identical bins; not the headline configuration")
     ap.add_argument("--keep-offset-bins", action="store_true",
                     help="do not merge the simulator's three identical offset bins (exercises the O = 3 kernels)")
     args = ap.parse_args()
