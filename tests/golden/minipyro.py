@@ -1,15 +1,16 @@
 """
 Stand-in for the absent third-party packages ``pyro`` / ``pyroapi`` (pyro-ppl >= 1.8.5, reference ``setup.py:69``),
 used ONLY by tests/golden/make_golden_step.py in the build container to run the reference's own
-``tapqir/models/cosmos.py`` (``init_parameters``, ``guide``, ``model``) and ``tapqir/models/model.py`` (``Model.init``,
-the ``svi.step()`` of the run loop) UNMODIFIED.  Test infrastructure; nothing in ``tapqir_b200`` imports it and it
-never runs on the GPU box.
+``tapqir/models/cosmos.py`` (``init_parameters``, ``guide``, ``model``, ``compute_probs``, ``compute_params``),
+``tapqir/models/hmm.py`` (sequential form) and ``tapqir/models/model.py`` (``Model.init``, the ``svi.step()`` of the run
+loop) UNMODIFIED.  Test infrastructure; nothing in ``tapqir_b200`` imports it and it never runs on the GPU box
+(tests/test_minipyro.py checks it against closed-form answers on the CPU).
 
 It restates, from Pyro's published semantics, exactly the pieces that code touches and nothing else:
 
-* effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``mask``, ``plate`` (subsampling as a replayable site, plate scale
-  size / subsample_size, broadcasting of the distribution to the plate shape; sequential plates and ``markov`` loops
-  without dimension recycling) and parallel enumeration
+* effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``mask``, ``plate``
+  (subsampling as a replayable site, plate scale size / subsample_size, broadcasting of the distribution to the plate
+  shape; sequential plates and ``markov`` loops without dimension recycling) and parallel enumeration
   (``infer={"enumerate": "parallel"}``: the support of the site is placed on a fresh tensor dimension to the left
   of ``max_plate_nesting``; the guide allocates first, the model continues to the left);
 * ``pyro.param`` with the unconstrained value stored (``transform_to(constraint).inv``) and the constrained one
