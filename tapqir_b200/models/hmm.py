@@ -130,6 +130,14 @@ class hmm(cosmos):
         return torch.gather(mp, 0, zmap[None, None].expand(1, *mp.shape[1:]))[0]
 
     @torch.no_grad()
+    def compute_params(self, CI):
+        """cosmos' summaries (with ``init`` / ``trans`` among the credible intervals) + the guide's chain ``z_trans``
+        (hmm.py:669-676)."""
+        params = super().compute_params(CI)
+        params["z_trans"] = self.param("z_trans").detach().cpu()
+        return params
+
+    @torch.no_grad()
     def z_sample(self, num_samples):
         """
         ``num_samples`` draws of the guide's chain for the on-target AOIs, ``(num_samples, N, F, Q)`` (reference:

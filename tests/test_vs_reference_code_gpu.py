@@ -216,6 +216,7 @@ def test_hmm_compute_stats_writes_reference_files(tmp_path):
         assert (params[name]["LL"] <= params[name]["Mean"]).all() and (params[name]["Mean"] <= params[name]["UL"]).all()
     assert params["m_probs"].shape == (K, Nt, F, Q) and params["z_probs"].shape == (Nt, F, Q, 2)
     assert params["theta_probs"].shape == (K, Nt, F, Q) and params["z_map"].shape == (Nt, F, Q)
+    assert params["z_trans"].shape == (Nt, F, Q, 2, 2)                                   # hmm.py:669-676
     summary = pd.read_csv(tmp_path / "cosmos+hmm_summary.csv", index_col=0)
     assert {"gain", "proximity", "lamda", "trans", "SNR_0", "MCC"} <= set(summary.index)
     assert (tmp_path / "cosmos+hmm_params.mat").exists()
