@@ -295,7 +295,8 @@ struct HmmOffsets {
 template <typename T>
 double hmm_step_host(int nb, int Nt, int F_, int C, int P, int O, const int32_t* ndx, const T* pixels, const T* xy,
                      const uint8_t* ontarget, const uint8_t* mask, const T* off_s, const T* off_w, const ModelConst* mcp, double sN,
-                     const T* lparams, const double* gparams, const T* lnoise, const double* gnoise, T* lgrads, double* ggrads) {
+                     const T* lparams, const double* gparams, const T* lnoise, const double* gnoise, T* lgrads, double* ggrads,
+                     double* acc_out = nullptr, double* hacc_out = nullptr) {
     const ModelConst& mc = *mcp;
     GlobalLayout gl{C, true};
     GlobalTables<double> gtd;
@@ -413,6 +414,9 @@ double hmm_step_host(int nb, int Nt, int F_, int C, int P, int O, const int32_t*
                 carry = (rho1 - rho0) + (r1.q[1] - r0.q[1]) * delta;
             }
         }
+    // what a rank contributes to the cross-rank sum (the sharded step: all-reduce these, then hc_hmm_globals_post)
+    if (acc_out) for (size_t i = 0; i < acc.size(); ++i) acc_out[i] = acc[i];
+    if (hacc_out) for (size_t i = 0; i < hacc.size(); ++i) hacc_out[i] = hacc[i];
     double elbo = 0.0;
     for (int site = 0; site < global_site_count(gl.Q, true); ++site)
         elbo += globals_post_site(site, gparams, gl, mc, gsamp, acc.data(), sN, 1.0, ggrads, hacc.data());
@@ -427,6 +431,27 @@ double hc_hmm_step_f64(int nb, int Nt, int F, int C, int P, int O, const int32_t
                        double sN, const double* lparams, const double* gparams, const double* lnoise, const double* gnoise,
                        double* lgrads, double* ggrads) {
     return hmm_step_host<double>(nb, Nt, F, C, P, O, ndx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, lparams, gparams, lnoise, gnoise, lgrads, ggrads);
+}
+// the sharded hmm step in two halves: local part of one rank (accumulators out), then -- after the cross-rank sum of
+// (C, NACC) + (C, NHACC) doubles -- the replicated reverse mode of the global sites
+double hc_hmm_step_acc_f64(int nb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const double* pixels, const double* xy,
+                           const uint8_t* ontarget, const uint8_t* mask, const double* off_s, const double* off_w, const ModelConst* mc,
+                           double sN, const double* lparams, const double* gparams, const double* lnoise, const double* gnoise,
+                           double* lgrads, double* ggrads, double* acc, double* hacc) {
+    return hmm_step_host<double>(nb, Nt, F, C, P, O, ndx, pixels, xy, ontarget, mask, off_s, off_w, mc, sN, lparams, gparams, lnoise, gnoise, lgrads, ggrads, acc, hacc);
+}
+int hc_hmm_acc_sizes(int* nacc, int* nhacc) { *nacc = NACC; *nhacc = NHACC; return 0; }
+double hc_hmm_globals_post(int C, const ModelConst* mc, const double* gparams, const double* gnoise, const double* acc,
+                           const double* hacc, double sN, double* ggrads) {
+    GlobalLayout gl{C, true};
+    GlobalTables<double> gt;
+    double gvar[kMaxGlobalNoise], gsamp[kMaxGlobalNoise];
+    for (int i = 0; i < gl.n_count(); ++i) gvar[i] = gnoise[i];
+    globals_pre(gparams, gl, *mc, false, nullptr, gvar, gsamp, gt);
+    double elbo = 0.0;
+    for (int site = 0; site < global_site_count(gl.Q, true); ++site)
+        elbo += globals_post_site(site, gparams, gl, *mc, gsamp, acc, sN, 1.0, ggrads, hacc);
+    return -elbo;
 }
 double hc_hmm_step_f32(int nb, int Nt, int F, int C, int P, int O, const int32_t* ndx, const float* pixels, const float* xy,
                        const uint8_t* ontarget, const uint8_t* mask, const float* off_s, const float* off_w, const ModelConst* mc,

@@ -118,3 +118,96 @@ def test_aoi_sharding_covers_every_aoi_once():
             sl = m._shard()
             seen += list(range(sl.start, sl.stop))
         assert seen == list(range(Nt))
+
+
+# ---- hmm variant: the exchange is (C, NACC) + (C, NHACC) doubles (the chain's expected counts ride along) ---------------
+def _hmm_worker(rank, world, port, cfg, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import hmm_oracle as H
+        from tests import hostcheck
+        from tests.test_hmm_cpu import small_problem
+
+        hc = hostcheck.load()
+        ds, data, params, _, _ = small_problem(N=cfg["N"], F=cfg["F"], C=cfg["C"], seed=cfg["seed"])
+        ndx = torch.tensor(cfg["ndx"])
+        noise = H.draw_noise(params, data, ndx, torch.Generator().manual_seed(cfg["seed"] + 9))
+        per = data.Nt // world
+        lo, hi = rank * per, (rank + 1) * per
+        sel = (ndx >= lo) & (ndx < hi)
+        shard = O.OracleData(data.images[lo:hi], data.xy[lo:hi], data.is_ontarget[lo:hi], data.mask[lo:hi],
+                             data.offset_samples, data.offset_weights)
+        aoi_axis = {"m_probs": 2, "z_trans": 0}
+        sparams = {}
+        for k, v in params.items():
+            if k in H.GLOBAL_PARAMS:
+                sparams[k] = v
+            else:
+                ax = aoi_axis.get(k, 1 if v.dim() == 4 else 0)
+                sparams[k] = v.narrow(ax, lo, hi - lo).contiguous()
+        snoise = dict(noise)
+        snoise["background"] = noise["background"][sel]
+        for k in ("height", "width", "x", "y"):
+            snoise[k] = noise[k][:, sel]
+        sndx = (ndx[sel] - lo).to(torch.int32).contiguous()
+        ll, gl = L.HmmLocalLayout(shard.Nt, shard.F, shard.C), L.HmmGlobalLayout(shard.C)
+        lparams = torch.zeros(ll.numel, dtype=torch.float64)
+        ll.load_named(lparams, sparams)
+        gparams = gl.pack({k: params[k] for k in gl.shapes}, dtype=torch.float64)
+        lnoise, gnoise = L.pack_local_noise(snoise, torch.float64, "cpu"), gl.pack_noise(noise)
+        mc = L.ModelConst.make(O.DEFAULT_PRIORS, shard.P, torch.float64)
+        nacc, nhacc = ctypes.c_int(), ctypes.c_int()
+        hc.hc_hmm_acc_sizes(ctypes.byref(nacc), ctypes.byref(nhacc))
+        acc = torch.zeros(shard.C * nacc.value + shard.C * nhacc.value, dtype=torch.float64)     # one buffer, one all-reduce
+        hacc = acc[shard.C * nacc.value:]
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        lgrads, ggrads = torch.empty_like(lparams), torch.zeros(gl.numel, dtype=torch.float64)
+        pix, xy = shard.images.contiguous(), shard.xy.contiguous()
+        ont, mask = shard.is_ontarget.to(torch.uint8).contiguous(), shard.mask.to(torch.uint8).contiguous()
+        off_s, off_w = shard.offset_samples.contiguous(), shard.offset_logits.contiguous()
+        sN = data.Nt / len(ndx)
+        hc.hc_hmm_step_acc_f64.restype = ctypes.c_double
+        hc.hc_hmm_step_acc_f64(len(sndx), shard.Nt, shard.F, shard.C, shard.P, off_s.numel(), p(sndx), p(pix), p(xy), p(ont), p(mask),
+                               p(off_s), p(off_w), ctypes.byref(mc), ctypes.c_double(sN), p(lparams), p(gparams), p(lnoise), p(gnoise),
+                               p(lgrads), p(ggrads), p(acc), p(hacc))
+        dist.all_reduce(acc)
+        ggrads.zero_()
+        hc.hc_hmm_globals_post.restype = ctypes.c_double
+        loss = hc.hc_hmm_globals_post(shard.C, ctypes.byref(mc), p(gparams), p(gnoise), p(acc), p(hacc), ctypes.c_double(sN), p(ggrads))
+        grads = {k: v.numpy().copy() for k, v in ll.named(lgrads).items()}
+        grads.update({k: v.numpy().copy() for k, v in gl.views(ggrads).items()})
+        out_q.put((rank, loss, grads, lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [dict(N=4, F=5, C=1, seed=0, ndx=[3, 0, 2]), dict(N=4, F=4, C=2, seed=1, ndx=[1, 2, 3, 0])])
+def test_two_rank_sharded_hmm_step_equals_single_process_oracle(cfg):
+    from oracle import hmm_oracle as H
+    from tests.test_hmm_cpu import small_problem
+
+    world = 2
+    ds, data, params, _, _ = small_problem(N=cfg["N"], F=cfg["F"], C=cfg["C"], seed=cfg["seed"])
+    ndx = torch.tensor(cfg["ndx"])
+    noise = H.draw_noise(params, data, ndx, torch.Generator().manual_seed(cfg["seed"] + 9))
+    ref_loss, ref_grads = H.loss_and_grads(params, data, ndx, noise)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 300
+    procs = [ctx.Process(target=_hmm_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    aoi_axis = {"m_probs": 2, "z_trans": 0}
+    for rank, loss, grads, lo, hi in results:
+        assert abs(loss - ref_loss) <= 1e-11 * abs(ref_loss)
+        for k, ref in ref_grads.items():
+            g = torch.from_numpy(grads[k])
+            if k not in H.GLOBAL_PARAMS:
+                ref = ref.narrow(aoi_axis.get(k, 1 if ref.dim() == 4 else 0), lo, hi - lo)
+            err = (g.reshape(ref.shape) - ref).abs().max().item()
+            assert err <= 1e-8 * max(ref_grads[k].abs().max().item(), 1e-30), (k, err)
