@@ -90,6 +90,7 @@ def load_reference():
         mod.__dict__.update(attrs)
         sys.modules[name] = mod
     hm = load("tapqir.models.hmm", "tapqir/models/hmm.py")
+    load("tapqir.utils.simulate", "tapqir/utils/simulate.py")
     return minipyro, ds, cm, hm
 
 
@@ -288,9 +289,36 @@ def run_c1_fit(minipyro, ds_mod, cosmos_mod, iters=100, seed=0):
                 final={k: v.detach().clone() for k, v in store.items()})
 
 
+def run_simulate_case(cosmos_mod):
+    """The reference's own ``utils/simulate.py::simulate`` (:12-138: Predictive over the unconditioned cosmos model, pixels
+    from ``KSMOGN.rsample``) with the constants of its test-suite (test/test_tapqir.py:22-50): what is stored are summary
+    statistics of the simulated movie, which the simulator of this repository has to reproduce in distribution."""
+    from tapqir.utils.simulate import simulate
+
+    prm = {"pi": 0.15, "width": 1.4, "gain": 7.0, "lamda": 0.15, "proximity": 0.2, "offset": 90.0, "height": 3000, "background": 150}
+    N, F, C, P = 40, 100, 1, 14
+    model = cosmos_mod.cosmos(device="cpu", dtype="double", use_pykeops=False)
+    data = simulate(model, N, F, C, P, seed=4, params=prm)
+    img = data.images.double()
+    corners = torch.stack([img[..., 0, 0], img[..., 0, P - 1], img[..., P - 1, 0], img[..., P - 1, P - 1]], -1)
+    patch_sum = img.sum((-1, -2)) - (prm["background"] + prm["offset"] - 0.5) * P * P      # photons above background
+    z = torch.as_tensor(data.labels["z"])
+    stats = dict(params=prm, N=N, F=F, C=C, P=P, shape=tuple(img.shape), is_ontarget=data.is_ontarget.clone(),
+                 xy_unique=torch.unique(data.xy), offset_samples=data.offset.samples.clone(), offset_weights=data.offset.weights.clone(),
+                 images_dtype=str(data.images.dtype), integral=bool((img == img.floor()).all()),
+                 z_fraction=z.double().mean().item(), labels_shape=tuple(data.labels.shape), labels_fields=data.labels.dtype.names,
+                 corner_mean=corners.mean().item(), corner_var=corners.var().item(), pixel_mean=img.mean().item(),
+                 patch_sum_on=patch_sum[: N // 2].mean().item(), patch_sum_off=patch_sum[N // 2:].mean().item(),
+                 patch_sum_q=torch.quantile(patch_sum.flatten(), torch.tensor([0.5, 0.9, 0.99], dtype=torch.float64)),
+                 min=img.min().item())
+    torch.save(stats, HERE / "ref_simulate_stats.pt")
+    print("simulate:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in stats.items() if k in ("z_fraction", "corner_mean", "corner_var", "pixel_mean", "patch_sum_on", "patch_sum_off")})
+
+
 def main():
     minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
     run_data_case(ds_mod)
+    run_simulate_case(cosmos_mod)
     c1 = run_c1_fit(minipyro, ds_mod, cosmos_mod)
     torch.save(c1, HERE / "ref_c1_fit.pt")
     print("c1 fit: loss", c1["losses"][0].item(), "->", c1["losses"][-1].item())

@@ -8,7 +8,8 @@ loop) UNMODIFIED.  Test infrastructure; nothing in ``tapqir_b200`` imports it an
 
 It restates, from Pyro's published semantics, exactly the pieces that code touches and nothing else:
 
-* effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``mask``, ``plate``
+* effect handlers: ``trace`` (+ ``get_trace`` / ``compute_log_prob``), ``replay``, ``block``, ``condition``,
+  ``uncondition`` (+ ``Predictive`` built on them), ``mask``, ``plate``
   (subsampling as a replayable site, plate scale size / subsample_size, broadcasting of the distribution to the plate
   shape; sequential plates and ``markov`` loops without dimension recycling) and parallel enumeration
   (``infer={"enumerate": "parallel"}``: the support of the site is placed on a fresh tensor dimension to the left
@@ -134,6 +135,50 @@ class block(Messenger):
     def process(self, msg):
         if msg["name"] in self.hide:
             msg["stop"] = True
+
+
+class condition(Messenger):
+    """Fix the named sites to given values (they become observed)."""
+
+    def __init__(self, fn=None, data=None):
+        self.fn, self.data = fn, data
+
+    def process(self, msg):
+        if msg["type"] == "sample" and not msg.get("subsample") and msg["name"] in self.data:
+            msg["value"], msg["is_observed"] = self.data[msg["name"]], True
+
+
+class uncondition(Messenger):
+    """Turn observed sites back into sampled ones (used to simulate data from a model)."""
+
+    def __init__(self, fn=None):
+        self.fn = fn
+
+    def process(self, msg):
+        if msg["type"] == "sample" and msg["is_observed"]:
+            msg["infer"] = dict(msg["infer"], was_observed=True)
+            msg["is_observed"], msg["value"], msg["done"] = False, None, False
+
+
+class Predictive:
+    """``pyro.infer.Predictive(model, posterior_samples=...)`` in its sequential form: for every index i along the leading
+    axis of the given samples, run the model with those sites fixed to ``sample[i]`` and sample the rest; returns the
+    remaining sample sites stacked along a new leading axis."""
+
+    def __init__(self, model, posterior_samples=None, num_samples=None, **unused):
+        self.model, self.samples = model, posterior_samples or {}
+        sizes = {v.shape[0] for v in self.samples.values()}
+        assert len(sizes) <= 1
+        self.num_samples = sizes.pop() if sizes else num_samples
+
+    def __call__(self, *a, **kw):
+        out = {}
+        for i in range(self.num_samples):
+            tr = trace(condition(self.model, data={k: v[i] for k, v in self.samples.items()})).get_trace(*a, **kw)
+            for name, site in tr.nodes.items():
+                if site["type"] == "sample" and not site.get("subsample") and name not in self.samples:
+                    out.setdefault(name, []).append(site["value"])
+        return {k: torch.stack(v) for k, v in out.items()}
 
 
 class mask(Messenger):
@@ -555,8 +600,9 @@ def install():
     ops.__path__ = []
     module("pyro.ops.indexing", Vindex=Vindex)
     module("pyro.ops.stats", quantile=None, hpdi=None)
-    handlers = module("pyro.poutine", mask=mask, trace=trace, replay=replay, enum=enum, block=block)
-    infer = module("pyro.infer", TraceEnum_ELBO=TraceEnum_ELBO, JitTraceEnum_ELBO=TraceEnum_ELBO, SVI=SVI)
+    handlers = module("pyro.poutine", mask=mask, trace=trace, replay=replay, enum=enum, block=block, condition=condition,
+                      uncondition=uncondition)
+    infer = module("pyro.infer", TraceEnum_ELBO=TraceEnum_ELBO, JitTraceEnum_ELBO=TraceEnum_ELBO, SVI=SVI, Predictive=Predictive)
     optim = module("pyro.optim", Adam=Adam)
     pyro = module("pyro", sample=sample, param=param, plate=plate, markov=markov, clear_param_store=clear_param_store,
                   get_param_store=get_param_store, set_rng_seed=set_rng_seed, distributions=dist, poutine=handlers,
