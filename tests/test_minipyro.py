@@ -176,3 +176,18 @@ def test_param_store_and_svi_step_are_adam_on_the_unconstrained_value():
     u1 = mp.get_param_store().unconstrained()["scale"].item()
     assert abs(u1 - (u0 - 0.1 * math.copysign(1.0, g.item()))) < 1e-6      # first Adam step: lr * sign(gradient)
     assert abs(dict(mp.get_param_store().items())["scale"].item() - math.exp(u1)) < 1e-6
+
+
+def test_predictive_fixes_given_sites_unconditions_observations_and_samples_the_rest():
+    Normal = mp._wrap(torch.distributions.Normal)
+
+    def model():
+        a = mp.sample("a", Normal(0.0, 1.0))
+        with mp.plate("n", 1000, dim=-1):
+            return mp.sample("x", Normal(a, 0.1), obs=torch.zeros(1000))
+
+    torch.manual_seed(0)
+    out = mp.Predictive(mp.uncondition(model), posterior_samples={"a": torch.tensor([5.0, -3.0])})()
+    assert set(out) == {"x"} and out["x"].shape == (2, 1000)                 # 'a' was given; 'x' is sampled, not its obs
+    assert abs(out["x"][0].mean().item() - 5.0) < 0.02 and abs(out["x"][1].mean().item() + 3.0) < 0.02
+    assert abs(out["x"][0].std().item() - 0.1) < 0.01
