@@ -289,7 +289,7 @@ def run_c1_fit(minipyro, ds_mod, cosmos_mod, iters=100, seed=0):
                 final={k: v.detach().clone() for k, v in store.items()})
 
 
-def run_simulate_case(cosmos_mod):
+def run_simulate_case(cosmos_mod, hmm_mod):
     """The reference's own ``utils/simulate.py::simulate`` (:12-138: Predictive over the unconditioned cosmos model, pixels
     from ``KSMOGN.rsample``) with the constants of its test-suite (test/test_tapqir.py:22-50): what is stored are summary
     statistics of the simulated movie, which the simulator of this repository has to reproduce in distribution."""
@@ -311,6 +311,22 @@ def run_simulate_case(cosmos_mod):
                  patch_sum_on=patch_sum[: N // 2].mean().item(), patch_sum_off=patch_sum[N // 2:].mean().item(),
                  patch_sum_q=torch.quantile(patch_sum.flatten(), torch.tensor([0.5, 0.9, 0.99], dtype=torch.float64)),
                  min=img.min().item())
+    # kinetic recipe (test/test_tapqir.py:30-33): the reference's hmm model in its sequential form, kon = koff = 0.2
+    hprm = {k: v for k, v in prm.items() if k != "pi"}
+    hprm.update(kon=0.2, koff=0.2)
+    hN, hF = 100, 100
+    hmodel = hmm_mod.hmm(device="cpu", dtype="double", use_pykeops=False, vectorized=False)
+    hdata = simulate(hmodel, hN, hF, C, P, seed=5, params=hprm)
+    hz = torch.as_tensor(hdata.labels["z"])[..., 0]                                   # (N/2, F)
+    prev, cur = hz[:, :-1], hz[:, 1:]
+    himg = hdata.images.double()
+    hsum = himg.sum((-1, -2)) - (prm["background"] + prm["offset"] - 0.5) * P * P
+    stats["hmm"] = dict(params=hprm, N=hN, F=hF, z_fraction=hz.double().mean().item(), z0_fraction=hz[:, 0].double().mean().item(),
+                        p01=((prev == 0) & (cur == 1)).sum().item() / max((prev == 0).sum().item(), 1),
+                        p10=((prev == 1) & (cur == 0)).sum().item() / max((prev == 1).sum().item(), 1),
+                        patch_sum_on=hsum[: hN // 2].mean().item(), patch_sum_off=hsum[hN // 2:].mean().item(),
+                        shape=tuple(himg.shape), labels_shape=tuple(hdata.labels.shape))
+    print("simulate hmm:", {k: v for k, v in stats["hmm"].items() if k not in ("params",)})
     torch.save(stats, HERE / "ref_simulate_stats.pt")
     print("simulate:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in stats.items() if k in ("z_fraction", "corner_mean", "corner_var", "pixel_mean", "patch_sum_on", "patch_sum_off")})
 
@@ -318,7 +334,7 @@ def run_simulate_case(cosmos_mod):
 def main():
     minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
     run_data_case(ds_mod)
-    run_simulate_case(cosmos_mod)
+    run_simulate_case(cosmos_mod, hmm_mod)
     c1 = run_c1_fit(minipyro, ds_mod, cosmos_mod)
     torch.save(c1, HERE / "ref_c1_fit.pt")
     print("c1 fit: loss", c1["losses"][0].item(), "->", c1["losses"][-1].item())

@@ -55,3 +55,27 @@ def test_simulated_movie_matches_the_reference_simulator_in_distribution():
 def test_simulator_is_reproducible_and_seed_dependent():
     a, b, c = simulate(4, 6, seed=3), simulate(4, 6, seed=3), simulate(4, 6, seed=4)
     assert torch.equal(a.images, b.images) and not torch.equal(a.images, c.images)
+
+
+def test_kinetic_recipe_matches_the_reference_simulator_in_distribution():
+    """kon / koff simulation (the data of BASELINE config 5): the reference's hmm model in its sequential form, simulated by
+    the reference's own ``simulate`` (test/test_tapqir.py:30-33), against ours: stationary occupancy, transition
+    frequencies, photons per on- / off-target patch."""
+    ref = torch.load(Path(__file__).resolve().parent / "golden" / "ref_simulate_stats.pt", weights_only=False)["hmm"]
+    prm, N, F, P = ref["params"], ref["N"], ref["F"], 14
+    d = simulate(N, F, C=1, P=P, seed=1, params={"kon": prm["kon"], "koff": prm["koff"]})
+    assert tuple(d.images.shape) == ref["shape"] and d.labels.shape == ref["labels_shape"]
+    z = torch.as_tensor(d.labels["z"])[..., 0]
+    prev, cur = z[:, :-1], z[:, 1:]
+    p01 = ((prev == 0) & (cur == 1)).sum().item() / (prev == 0).sum().item()
+    p10 = ((prev == 1) & (cur == 0)).sum().item() / (prev == 1).sum().item()
+    se = (0.2 * 0.8 / (prev.numel() / 2)) ** 0.5
+    assert abs(p01 - prm["kon"]) < 4 * se and abs(p10 - prm["koff"]) < 4 * se
+    assert abs(p01 - ref["p01"]) < 6 * se and abs(p10 - ref["p10"]) < 6 * se
+    # occupancy: the chain mixes slowly (correlation time ~ 1 / (kon + koff)), so ~ N/2 * F * (kon + koff) / 2 effective draws
+    occ_se = (0.25 / (z.numel() * (prm["kon"] + prm["koff"]) / 2)) ** 0.5
+    assert abs(z.double().mean().item() - 0.5) < 4 * occ_se and abs(z.double().mean().item() - ref["z_fraction"]) < 6 * occ_se
+    _, _, patch_sum = _stats(d, {"background": 150, "offset": 90.0}, P)
+    on, off = patch_sum[: N // 2].mean().item(), patch_sum[N // 2:].mean().item()
+    # 5000 patches per class; the off-target sum rides on ~750 non-specific spots of 3000 photons: +-4 % on either side
+    assert abs(on / ref["patch_sum_on"] - 1) < 0.10 and abs(off / ref["patch_sum_off"] - 1) < 0.20
