@@ -331,9 +331,76 @@ def run_simulate_case(cosmos_mod, hmm_mod):
     print("simulate:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in stats.items() if k in ("z_fraction", "corner_mean", "corner_var", "pixel_mean", "patch_sum_on", "patch_sum_off")})
 
 
+def run_glimpse_header_case():
+    """``imscroll/glimpse_reader.py::GlimpseDataset.__init__`` (:55-159) run verbatim on a small synthetic glimpse folder
+    (tests/golden/ref_glimpse_folder/, written here): header, AOI tables in the three accepted layouts, the cumulative
+    drift relative to the frame the AOIs were picked in, a frame range, spot-picker labels.  (``__getitem__`` / the frame loop
+    of ``read_glimpse`` add 2**15 to an int16 array, which numpy 2 refuses: they stay restated in oracle/glimpse_oracle.py.)"""
+    import numpy as np
+    from scipy.io import savemat
+
+    patches = types.ModuleType("matplotlib.patches")
+    patches.Rectangle = object
+    sys.modules["matplotlib.patches"] = patches
+    spec = importlib.util.spec_from_file_location("tapqir.imscroll.glimpse_reader", REF / "tapqir/imscroll/glimpse_reader.py")
+    pkg = types.ModuleType("tapqir.imscroll")
+    pkg.__path__ = []
+    sys.modules["tapqir.imscroll"] = pkg
+    gr = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = gr
+    spec.loader.exec_module(gr)
+
+    folder = HERE / "ref_glimpse_folder"
+    (folder / "glimpse").mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(3)
+    F, H, W = 12, 40, 48
+    vid = dict(height=float(H), width=float(W), filenumber=np.repeat(np.arange(3), 4).astype(np.int32),
+               offset=(np.arange(F) % 4 * H * W * 2).astype(np.int64), ttb=np.arange(F, dtype=float) * 50.0 + 7.0, time1=1234.5)
+    savemat(folder / "glimpse" / "header.mat", {"vid": vid})
+    dl = np.zeros((F, 4))
+    dl[:, 0] = np.arange(1, F + 1)
+    dl[:, 1:3] = rng.normal(0, 0.3, size=(F, 2))
+    savemat(folder / "driftlist.mat", {"driftlist": dl})
+
+    def table(n, frame):      # frame, ave, y, x, pixnum, aoi (MATLAB indexing)
+        xy = rng.uniform(10, 30, size=(n, 2))
+        return np.stack([np.full(n, float(frame)), np.full(n, 10.0), xy[:, 1], xy[:, 0], np.full(n, 5.0), np.arange(1, n + 1)], 1)
+
+    on, off = table(4, 5), table(3, 5)
+    savemat(folder / "ontarget_aoiinfo2.mat", {"aoiinfo2": on})                       # layout 1: plain aoiinfo2
+    savemat(folder / "offtarget_aoifits.mat", {"aoifits": {"aoiinfo2": off}})         # layout 2: inside aoifits
+    np.savetxt(folder / "ontarget.dat", on)                                           # layout 3: text
+    intervals = np.array([[-2.0, 1, 3, 2, 0, 0, 1], [1.0, 4, 9, 6, 0, 0, 1], [2.0, 10, 12, 3, 0, 0, 1],
+                          [-3.0, 1, 6, 6, 0, 0, 3], [0.0, 7, 12, 6, 0, 0, 3], [3.0, 2, 11, 10, 0, 0, 4]])
+    savemat(folder / "intervals.mat", {"Intervals": {"CumulativeIntervalArray": intervals}})
+
+    def kwargs(on_file, frame_range, labels):
+        return {"name": "green", "glimpse-folder": str(folder / "glimpse"), "driftlist": str(folder / "driftlist.mat"),
+                "ontarget-aoiinfo": str(folder / on_file), "offtarget-aoiinfo": str(folder / "offtarget_aoifits.mat"),
+                "use-offtarget": True, "frame-range": frame_range, "frame-start": 3, "frame-end": 10, "labels": labels,
+                "ontarget-labels": str(folder / "intervals.mat") if labels else None, "offtarget-labels": None,
+                "offset-x": 2, "offset-y": 3}
+
+    facts = {}
+    for name, kw in {"mat_full": kwargs("ontarget_aoiinfo2.mat", False, True), "text_range": kwargs("ontarget.dat", True, True),
+                     "mat_nolabels": kwargs("ontarget_aoiinfo2.mat", True, False)}.items():
+        g = gr.GlimpseDataset(**kw)
+        facts[name] = dict(
+            kwargs={k: (Path(v).name if isinstance(v, str) and "/" in v else v) for k, v in kw.items()},
+            height=g.height, width=g.width, dtypes=list(g.dtypes), offset=(g.offset_x, g.offset_y), name=g.name,
+            time1=float(g.header["time1"]), filenumber=np.asarray(g.header["filenumber"]).copy(),
+            aoiinfo={d: dict(index=g.aoiinfo[d].index.values.copy(), values=g.aoiinfo[d][["frame", "ave", "y", "x", "pixnum"]].values.copy())
+                     for d in g.dtypes},
+            cumdrift=dict(index=g.cumdrift.index.values.copy(), values=g.cumdrift[["dy", "dx", "ttb"]].values.copy()),
+            labels={d: (None if g.labels[d] is None else g.labels[d].copy()) for d in g.dtypes})
+    torch.save(facts, folder / "facts.pt")
+    print("wrote", folder)
+
+
 def main():
     minipyro, ds_mod, cosmos_mod, hmm_mod = load_reference()
     run_data_case(ds_mod)
+    run_glimpse_header_case()
     run_simulate_case(cosmos_mod, hmm_mod)
     c1 = run_c1_fit(minipyro, ds_mod, cosmos_mod)
     torch.save(c1, HERE / "ref_c1_fit.pt")

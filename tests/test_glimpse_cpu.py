@@ -61,3 +61,42 @@ def test_crop_loop_rounds_half_to_even():
     # raw - (P-1)/2 = 4.5 and 5.5 -> shifts 4 and 6 (ties to even), like Python's round()
     data, xy = GO.crop_loop(frames, np.array([[7.0, 8.0]]), np.zeros((2, 2)), P=6)
     assert data[0, 0, 0, 0] == frames[0, 6, 4] and xy[0, 0].tolist() == [3.0, 2.0]
+
+
+# ---- header / AOI table / drift / labels parsing against the reference's own GlimpseDataset constructor ------------------
+import pytest
+
+
+@pytest.mark.parametrize("case", ["mat_full", "text_range", "mat_nolabels"])
+def test_glimpse_dataset_parsing_matches_reference_constructor(case):
+    """tests/golden/ref_glimpse_folder/ holds a small synthetic glimpse folder (header.mat, driftlist.mat, AOI tables in the
+    three accepted layouts, spot-picker intervals) and facts.pt what the reference's ``GlimpseDataset.__init__``
+    (glimpse_reader.py:55-159, run verbatim by tests/golden/make_golden_step.py) makes of it."""
+    from pathlib import Path
+
+    import numpy as np
+    import torch
+
+    from tapqir_b200.imscroll.glimpse_reader import GlimpseDataset
+
+    folder = Path(__file__).resolve().parent / "golden" / "ref_glimpse_folder"
+    ref = torch.load(folder / "facts.pt", weights_only=False)[case]
+    kw = dict(ref["kwargs"])
+    kw["glimpse-folder"] = str(folder / "glimpse")
+    for k in ("driftlist", "ontarget-aoiinfo", "offtarget-aoiinfo", "ontarget-labels"):
+        if kw[k] is not None:
+            kw[k] = str(folder / kw[k])
+    g = GlimpseDataset(**kw)
+    assert (g.height, g.width, list(g.dtypes), (g.offset_x, g.offset_y), g.name) == \
+        (ref["height"], ref["width"], ref["dtypes"], ref["offset"], ref["name"])
+    assert float(g.header["time1"]) == ref["time1"] and np.array_equal(np.asarray(g.header["filenumber"]), ref["filenumber"])
+    for d in ref["dtypes"]:
+        assert np.array_equal(g.aoiinfo[d].index.values, ref["aoiinfo"][d]["index"])
+        assert np.array_equal(g.aoiinfo[d][["frame", "ave", "y", "x", "pixnum"]].values, ref["aoiinfo"][d]["values"])
+        if ref["labels"][d] is None:
+            assert g.labels[d] is None
+        else:
+            assert g.labels[d].dtype == ref["labels"][d].dtype and np.array_equal(g.labels[d], ref["labels"][d])
+    assert np.array_equal(g.cumdrift.index.values, ref["cumdrift"]["index"])
+    assert np.array_equal(g.cumdrift[["dy", "dx", "ttb"]].values, ref["cumdrift"]["values"])       # bit for bit
+    assert g.N == 4 and g.Nc == 3 and g.F == len(ref["cumdrift"]["index"])
