@@ -1,9 +1,11 @@
 """
 CPU restatement (numpy, plain Python loops) of the ingestion arithmetic of the reference's
 ``tapqir/imscroll/glimpse_reader.py`` -- TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing under
-tapqir_b200/).  Pinned: ``bin_hist`` against the reference's own function (tests/golden/ref_glimpse.pt, made
-by tests/golden/make_golden_glimpse.py from the reference source); the frame loop follows
-glimpse_reader.py:168-186 and :354-381 line by line (no reference test or fixture holds numbers for it).
+tapqir_b200/).  Pinned bit for bit (tests/test_glimpse_cpu.py): ``bin_hist`` against the reference's own function
+(tests/golden/ref_glimpse.pt, made by tests/golden/make_golden_glimpse.py from the reference source); the frame loop
+(glimpse_reader.py:168-186, :354-381) and the offset post-processing (:411-433) against ``data.tpqr`` as written by the
+reference's whole ``read_glimpse`` run verbatim on a synthetic movie (tests/golden/ref_glimpse_folder/, made by
+tests/golden/make_golden_step.py).
 """
 
 from collections import OrderedDict, defaultdict

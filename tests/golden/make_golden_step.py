@@ -393,6 +393,50 @@ def run_glimpse_header_case():
                      for d in g.dtypes},
             cumdrift=dict(index=g.cumdrift.index.values.copy(), values=g.cumdrift[["dy", "dx", "ttb"]].values.copy()),
             labels={d: (None if g.labels[d] is None else g.labels[d].copy()) for d in g.dtypes})
+    # ---- the whole of read_glimpse (:304-472) on the same folder: frame decoding, AOI cropping, offset histogram ----------
+    # Two third-party API changes stand between the reference and this environment, both bridged, not worked around in the
+    # reference's code: numpy 2 no longer promotes ``int16_array + 2**15`` (glimpse_reader.py:186) to a wider integer --
+    # numpy 1 gave int32 --, and matplotlib (the AOI overview PNGs of GlimpseDataset.plot) is absent.
+    class _PromotingInt16(np.ndarray):
+        def __add__(self, other):
+            return np.asarray(self).astype(np.int32) + other if isinstance(other, int) else np.asarray(self) + other
+
+    class _Numpy1(types.ModuleType):
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def fromfile(*a, **kw):
+            return np.fromfile(*a, **kw).view(_PromotingInt16)
+
+    class _Canvas:                              # every pyplot call is accepted and ignored
+        def __getattr__(self, name):
+            return self
+
+        def __call__(self, *a, **kw):
+            return self
+
+    gr.np, gr.plt = _Numpy1("numpy"), _Canvas()
+    gr.GlimpseDataset.plot = lambda self, *a, **kw: None
+    sys.modules["tapqir.utils.dataset"].quantile = lambda x, q: torch.quantile(x, q)      # pyro.ops.stats.quantile (vmin / vmax)
+    decoded = rng.integers(250, 1200, size=(F, H, W))
+    decoded[:, 3:13, 2:12] = rng.integers(85, 100, size=(F, 10, 10))                  # the dark corner the offsets are taken from
+    for number in range(3):
+        with open(folder / "glimpse" / f"{number}.glimpse", "wb") as fid:
+            fid.write((decoded[4 * number: 4 * number + 4] - 2 ** 15).astype(">i2").tobytes())
+    out_dir = folder / "out"
+    out_dir.mkdir(exist_ok=True)
+    kw = kwargs("ontarget_aoiinfo2.mat", True, True)
+    channel = {k: kw.pop(k) for k in ("name", "glimpse-folder", "driftlist", "ontarget-aoiinfo", "offtarget-aoiinfo",
+                                      "ontarget-labels", "offtarget-labels")}
+    kw.update({"P": 14, "num-channels": 1, "dataset": "golden-movie", "channels": [channel], "offset-P": 10, "bin-size": 3})
+    torch.set_default_dtype(torch.float32)          # `tapqir glimpse` runs under the FloatTensor default (main.py:205)
+    try:
+        gr.read_glimpse(out_dir, lambda it: it, **kw)
+    finally:
+        torch.set_default_dtype(torch.float64)
+    facts["read_glimpse"] = dict(decoded=torch.as_tensor(decoded, dtype=torch.int32), P=14, offset_P=10, bin_size=3,
+                                 frame_start=3, frame_end=10)
     torch.save(facts, folder / "facts.pt")
     print("wrote", folder)
 

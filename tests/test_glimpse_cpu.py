@@ -100,3 +100,46 @@ def test_glimpse_dataset_parsing_matches_reference_constructor(case):
     assert np.array_equal(g.cumdrift.index.values, ref["cumdrift"]["index"])
     assert np.array_equal(g.cumdrift[["dy", "dx", "ttb"]].values, ref["cumdrift"]["values"])       # bit for bit
     assert g.N == 4 and g.Nc == 3 and g.F == len(ref["cumdrift"]["index"])
+
+
+def test_read_glimpse_of_the_reference_pins_the_oracle_and_the_host_side_histogram():
+    """tests/golden/ref_glimpse_folder/out/data.tpqr was written by the reference's whole ``read_glimpse``
+    (glimpse_reader.py:304-472: frame decoding, drift-corrected AOI cropping, offset histogram, 0.5 % tail fold, ``bin_hist``)
+    run verbatim on the synthetic movie of that folder under the float32 default ``tapqir glimpse`` runs with.  Bit for
+    bit: the oracle's frame loop and offset post-processing (what the CUDA path is tested against on the GPU,
+    tests/test_glimpse_gpu.py), and the host-side ``offset_distribution`` of the product fed the same counts."""
+    from pathlib import Path
+
+    import numpy as np
+    import torch
+
+    from tapqir_b200.imscroll.glimpse_reader import offset_distribution
+    from tapqir_b200.utils.dataset import load
+
+    folder = Path(__file__).resolve().parent / "golden" / "ref_glimpse_folder"
+    facts = torch.load(folder / "facts.pt", weights_only=False)
+    rg, hdr = facts["read_glimpse"], facts["mat_nolabels"]                  # mat_nolabels: the same tables and frame range
+    ref = load(folder / "out")
+    P, f1, f2 = rg["P"], rg["frame_start"], rg["frame_end"]
+    frames = rg["decoded"].numpy().astype(np.int64)[f1 - 1:f2]              # frame numbers are 1-based
+    assert list(hdr["cumdrift"]["index"]) == list(range(f1, f2 + 1))
+    xy = np.concatenate([hdr["aoiinfo"][d]["values"][:, [3, 2]] for d in ("ontarget", "offtarget")], 0)     # columns x, y
+    cum = hdr["cumdrift"]["values"][:, [1, 0]]                              # (dy, dx, ttb) -> (dx, dy)
+    data, target = GO.crop_loop(frames, xy, cum, P)
+    assert ref.images.dtype == torch.int64 and np.array_equal(ref.images[:, :, 0].numpy(), data)
+    assert np.array_equal(ref.xy[:, :, 0].numpy(), target)
+    assert ref.is_ontarget.tolist() == [True] * 4 + [False] * 3 and ref.name == "golden-movie" and ref.channels == ("green",)
+    assert np.array_equal(ref.ttb[:, 0].numpy(), hdr["cumdrift"]["values"][:, 2]) and abs(ref.time1.item() - hdr["time1"]) < 1e-3
+    labels = facts["mat_full"]["labels"]["ontarget"][:, f1 - 1:f2]
+    assert ref.labels.shape == (4, f2 - f1 + 1, 1) and np.array_equal(ref.labels[..., 0], labels)
+    # offsets: pooled counts of the dark corner, guard bin, tail fold, thinning -- in float32 like the reference's run
+    ox, oy = hdr["offset"]
+    counts = GO.offset_counts(frames, ox, oy, rg["offset_P"])
+    assert torch.get_default_dtype() == torch.float32
+    s, w = GO.offset_distribution(counts, int(data.min()), rg["bin_size"])
+    assert torch.equal(s, ref.offset.samples) and torch.equal(w, ref.offset.weights) and w.dtype == torch.float32
+    dense = np.zeros(65536, dtype=np.int64)                                 # the product's form of the same counts
+    for value, count in counts.items():
+        dense[value] = count
+    ps, pw = offset_distribution(dense, int(data.min()), rg["bin_size"])
+    assert torch.equal(ps, ref.offset.samples) and torch.equal(pw, ref.offset.weights)
