@@ -220,3 +220,32 @@ def test_hmm_compute_stats_writes_reference_files(tmp_path):
     summary = pd.read_csv(tmp_path / "cosmos+hmm_summary.csv", index_col=0)
     assert {"gain", "proximity", "lamda", "trans", "SNR_0", "MCC"} <= set(summary.index)
     assert (tmp_path / "cosmos+hmm_params.mat").exists()
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes ran out: not yet run on a device")
+def test_read_glimpse_matches_the_reference_read_glimpse(tmp_path):
+    """The CUDA ingestion (tq_crop_aois, tq_offset_hist) on the synthetic movie of tests/golden/ref_glimpse_folder/ against
+    ``out/data.tpqr``, which the reference's own ``read_glimpse`` wrote for it (glimpse_reader.py:304-472, run verbatim by
+    tests/golden/make_golden_step.py): patches, target positions, offset samples / weights, labels -- bit for bit."""
+    from pathlib import Path
+
+    import numpy as np
+
+    from tapqir_b200.imscroll import read_glimpse
+    from tapqir_b200.utils.dataset import load
+
+    folder = Path(__file__).resolve().parent / "golden" / "ref_glimpse_folder"
+    ref = load(folder / "out")
+    kwargs = {"P": 14, "num-channels": 1, "dataset": "golden-movie", "offset-P": 10, "bin-size": 3, "offset-x": 2, "offset-y": 3,
+              "use-offtarget": True, "frame-range": True, "frame-start": 3, "frame-end": 10, "labels": True,
+              "channels": [{"name": "green", "glimpse-folder": str(folder / "glimpse"), "driftlist": str(folder / "driftlist.mat"),
+                            "ontarget-aoiinfo": str(folder / "ontarget_aoiinfo2.mat"),
+                            "offtarget-aoiinfo": str(folder / "offtarget_aoifits.mat"),
+                            "ontarget-labels": str(folder / "intervals.mat"), "offtarget-labels": None}]}
+    ds = read_glimpse(tmp_path, None, **kwargs)
+    assert np.array_equal(ds.images.cpu().numpy().astype(np.int64), ref.images.numpy())
+    assert np.array_equal(ds.xy.cpu().numpy(), ref.xy.numpy())
+    assert torch.equal(ds.offset.samples.cpu(), ref.offset.samples) and torch.equal(ds.offset.weights.cpu(), ref.offset.weights)
+    assert ds.is_ontarget.tolist() == ref.is_ontarget.tolist() and ds.name == ref.name and ds.channels == ref.channels
+    assert np.array_equal(ds.labels, ref.labels)
+    assert torch.equal(torch.as_tensor(ds.ttb).double().reshape(-1), ref.ttb.reshape(-1))
