@@ -133,7 +133,9 @@ int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* state, uint
                  void* perm, void* out, void* stream);
 
 /* Guide samples of the four global sites (cosmos.py:342-368) and the prior tables derived from
- * them (distributions/util.py:67-173).  gparams: global flat buffer (dtype).  noise_in: base
+ * them (distributions/util.py:67-173).  gparams: global flat buffer, ALWAYS float64 (as are ggrads and the
+ * global Adam moments; `dtype` here only types gain_out -- a dozen scalars whose concentration-like gradients
+ * cancel ~1e3-fold in the base variate, so fp32 storage alone would cost 1e-4 of gain_beta's gradient).  noise_in: base
  * variates (double; gain, proximity, pi (Q,2), lamda (Q)) for replay, or NULL to draw them with
  * Philox(seed, *state).  Outputs: gstate blob, tables blob, gain_out (1 value, dtype). */
 int tq_cosmos_globals_sample(int dtype, int Q, const void* gparams, const void* mc,

@@ -122,7 +122,7 @@ def ksmogn_image(height, width, x, y, target_locs, background, P, m=None):
 
 
 def ksmogn_log_prob(height, width, x, y, target_locs, background, gain, offset_samples,
-                    offset_logits, P, value, m=None):
+                    offset_logits, P, value, m=None, pixel_weights=None):
     """
     distributions/ksmogn.py:222-238 (``use_pykeops=False`` branch): per pixel
     ``logsumexp_j[ w_j + log 1(D>d_j) + Gamma(D-d_j; image/gain, 1/gain).log_prob ]``, summed over PxP.
@@ -135,7 +135,10 @@ def ksmogn_log_prob(height, width, x, y, target_locs, background, gain, offset_s
     yy = torch.where(ok, v - offset_samples, torch.ones((), dtype=v.dtype))
     per_offset = (conc * torch.log(rate) + (conc - 1) * torch.log(yy) - rate * yy
                   - torch.lgamma(conc) + offset_logits + torch.log(ok.to(v.dtype)))
-    return torch.logsumexp(per_offset, -1).sum((-1, -2))
+    per_pixel = torch.logsumexp(per_offset, -1)
+    if pixel_weights is not None:  # test hook (ones): d/d pixel_weights of a gradient = every pixel's contribution to it
+        per_pixel = per_pixel * pixel_weights
+    return per_pixel.sum((-1, -2))
 
 
 class AffineBeta:
@@ -410,17 +413,24 @@ def m_configs(K, dtype):
 
 
 def elbo(unconstrained, data: OracleData, ndx, fdx, noise, priors=DEFAULT_PRIORS, K=2, S=1,
-         return_parts=False):
+         return_parts=False, plate_sizes=None, unit_weights=None, pixel_weights=None):
     """
     ELBO of one guide+model execution with the given minibatch indices and base variates.
     Follows models/cosmos.py:82-327 (model), :329-462 (guide) and the TraceEnum_ELBO
     semantics of SURVEY.md App. A.3 [third party].  Differentiable w.r.t. ``unconstrained``.
+    ``plate_sizes=(Nt, F)``: sizes of the two subsampled plates when ``data`` holds only the gathered
+    minibatch block of a larger dataset (tests at BASELINE sizes: the plate scales are the only place
+    where the rest of the dataset enters a step, cosmos.py:194-208).  ``unit_weights`` (nb, fb, C), normally absent
+    (= ones): per-unit multipliers of the frame-level terms, so that a test can take d/d unit_weights of a gradient
+    and read off every unit's contribution to it (conditioning of the cross-unit sums); ``pixel_weights``
+    (nb, fb, C, P, P) likewise for the pixels of the likelihood.
     """
     assert S == 1, "cosmos enumerates z in {0, 1} (probs_theta has two rows, util.py:154-173)"
     dt, P = data.dtype, data.P
     Q = C = data.C
     nb, fb = len(ndx), len(fdx)
-    sN, sF = data.Nt / nb, data.F / fb
+    plate_n, plate_f = plate_sizes if plate_sizes is not None else (data.Nt, data.F)
+    sN, sF = plate_n / nb, plate_f / fb
     half = (P + 1) / 2
     p = to_constrained(unconstrained, P, dt)
     loc = _gather_local(p, ndx, fdx)
@@ -503,10 +513,11 @@ def elbo(unconstrained, data: OracleData, ndx, fdx, noise, priors=DEFAULT_PRIORS
     obs = data.images[ndx[:, None], fdx[None, :]]  # (nb,fb,C,P,P)
     L = ksmogn_log_prob(stk(height), stk(width), stk(x), stk(y), target, background, gain,
                         data.offset_samples, data.offset_logits, P, obs,
-                        m=mcfg[:, None, None, None, :])  # (M,nb,fb,C)
+                        m=mcfg[:, None, None, None, :], pixel_weights=pixel_weights)  # (M,nb,fb,C)
 
     per_config = T + L - logq_m + sum(mcfg[:, k][:, None, None, None] * spot_terms[k] for k in range(K))
-    e_frame = (mask * (e_b + (q_m * per_config).sum(0))).sum()
+    uw = 1.0 if unit_weights is None else unit_weights
+    e_frame = (mask * uw * (e_b + (q_m * per_config).sum(0))).sum()
     total = e_global + sN * e_aoi + sN * sF * e_frame
     if return_parts:
         parts = dict(e_global=e_global, e_aoi=e_aoi, e_frame=e_frame, T=T, L=L, q_m=q_m, logq_m=logq_m,

@@ -117,13 +117,14 @@ def draw_noise(unconstrained, data: O.OracleData, ndx, generator=None, priors=DE
     return noise
 
 
-def elbo(unconstrained, data: O.OracleData, ndx, noise, priors=DEFAULT_PRIORS, K=2, S=1, return_parts=False):
-    """ELBO of one guide + model execution over AOIs ``ndx`` and ALL frames, differentiable w.r.t. ``unconstrained``."""
+def elbo(unconstrained, data: O.OracleData, ndx, noise, priors=DEFAULT_PRIORS, K=2, S=1, return_parts=False, plate_n=None):
+    """ELBO of one guide + model execution over AOIs ``ndx`` and ALL frames, differentiable w.r.t. ``unconstrained``.
+    ``plate_n``: size of the AOI plate when ``data`` holds only the gathered AOIs of a larger dataset."""
     assert S == 1
     dt, P = data.dtype, data.P
     Q = C = data.C
     nb, F = len(ndx), data.F
-    sN = data.Nt / nb
+    sN = (plate_n if plate_n is not None else data.Nt) / nb
     half = (P + 1) / 2
     p = to_constrained(unconstrained, P, dt)
     loc = _gather_local(p, ndx)

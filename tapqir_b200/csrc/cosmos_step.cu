@@ -43,8 +43,11 @@ struct StepState {
 constexpr int kLocalBlock = 128;
 
 // ---- globals: sample + tables; one block per global site --------------------------------------------------
+// (the global parameters, their gradients and Adam moments are ALWAYS float64 buffers, whatever `dtype` the AOI-local
+// buffers use: a dozen scalars, and the concentration-like ones (gain_beta, ...) have gradients that cancel ~1e3-fold in
+// the base variate, so rounding their parameters to fp32 alone moves those gradients by 1e-4; T = type of gain_out)
 template <typename T>
-__global__ void globals_sample_kernel(const T* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
+__global__ void globals_sample_kernel(const double* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
                                       const double* __restrict__ noise_in, unsigned long long seed,
                                       const StepState* __restrict__ state, double* __restrict__ gstate,
                                       GlobalTables<double>* __restrict__ tables, T* __restrict__ gain_out) {
@@ -736,10 +739,9 @@ __global__ void __launch_bounds__(kLocalBlock) zprobs_kernel(const LocalArgs<T> 
 }
 
 // ---- globals: reverse mode; one block per global site, then a fixed-order sum of the ELBO parts -----------------
-template <typename T>
-__global__ void globals_grad_kernel(const T* __restrict__ gparams, int Q, ModelConst mc,
+__global__ void globals_grad_kernel(const double* __restrict__ gparams, int Q, ModelConst mc,
                                     const double* __restrict__ gstate, const double* __restrict__ acc,
-                                    double sN, double sF, T* __restrict__ ggrads, double* __restrict__ elbo_parts) {
+                                    double sN, double sF, double* __restrict__ ggrads, double* __restrict__ elbo_parts) {
     const int site = blockIdx.x;
     if (threadIdx.x != 0 || site >= global_site_count(Q)) return;
     GlobalLayout gl{Q};
@@ -747,17 +749,17 @@ __global__ void globals_grad_kernel(const T* __restrict__ gparams, int Q, ModelC
     for (int i = 0; i < gl.count(); ++i) { u[i] = (double)gparams[i]; grad[i] = 0.0; }
     elbo_parts[site] = globals_post_site(site, u, gl, mc, gstate + kMaxGlobalNoise, acc, sN, sF, grad);
     // each site owns its parameters' gradient entries
-    if (site == 0) { ggrads[gl.gain_loc()] = (T)grad[gl.gain_loc()]; ggrads[gl.gain_beta()] = (T)grad[gl.gain_beta()]; }
-    else if (site == 1) { ggrads[gl.prox_loc()] = (T)grad[gl.prox_loc()]; ggrads[gl.prox_size()] = (T)grad[gl.prox_size()]; }
+    if (site == 0) { ggrads[gl.gain_loc()] = grad[gl.gain_loc()]; ggrads[gl.gain_beta()] = grad[gl.gain_beta()]; }
+    else if (site == 1) { ggrads[gl.prox_loc()] = grad[gl.prox_loc()]; ggrads[gl.prox_size()] = grad[gl.prox_size()]; }
     else if (site < 2 + Q) {
         const int q = site - 2;
-        ggrads[gl.pi_mean(q, 0)] = (T)grad[gl.pi_mean(q, 0)];
-        ggrads[gl.pi_mean(q, 1)] = (T)grad[gl.pi_mean(q, 1)];
-        ggrads[gl.pi_size(q)] = (T)grad[gl.pi_size(q)];
+        ggrads[gl.pi_mean(q, 0)] = grad[gl.pi_mean(q, 0)];
+        ggrads[gl.pi_mean(q, 1)] = grad[gl.pi_mean(q, 1)];
+        ggrads[gl.pi_size(q)] = grad[gl.pi_size(q)];
     } else {
         const int q = site - 2 - Q;
-        ggrads[gl.lamda_loc(q)] = (T)grad[gl.lamda_loc(q)];
-        ggrads[gl.lamda_beta(q)] = (T)grad[gl.lamda_beta(q)];
+        ggrads[gl.lamda_loc(q)] = grad[gl.lamda_loc(q)];
+        ggrads[gl.lamda_beta(q)] = grad[gl.lamda_beta(q)];
     }
 }
 
@@ -770,8 +772,7 @@ __global__ void finalize_loss_kernel(const double* __restrict__ elbo_parts, int 
 
 // ---- globals, split reverse mode (see cosmos_globals.cuh): prepare runs right after sampling on the side stream,
 // finish after the accumulators exist.  prepare: one block per site, lanes 0..2 evaluate drive = 0, e0, e1.
-template <typename T>
-__global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
+__global__ void globals_prepare_kernel(const double* __restrict__ gparams, int Q, bool hmm, ModelConst mc,
                                        const double* __restrict__ gstate, GlobalPrep* __restrict__ prep) {
     const int site = blockIdx.x, lane = threadIdx.x;
     if (lane >= 3 || site >= global_site_count(Q, hmm)) return;
@@ -784,11 +785,10 @@ __global__ void globals_prepare_kernel(const T* __restrict__ gparams, int Q, boo
 }
 
 // finish: thread i owns global parameter i; thread 0 also sums the ELBO parts in a fixed order
-template <typename T>
 __global__ void globals_finish_kernel(int Q, bool hmm, ModelConst mc, const double* __restrict__ gstate,
                                       const GlobalPrep* __restrict__ prep, const double* __restrict__ acc,
                                       const double* __restrict__ hacc, double sN,
-                                      double sF, T* __restrict__ ggrads, double* __restrict__ loss) {
+                                      double sF, double* __restrict__ ggrads, double* __restrict__ loss) {
     GlobalLayout gl{Q, hmm};
     const int i = threadIdx.x;
     if (blockIdx.x != 0) return;
@@ -797,7 +797,7 @@ __global__ void globals_finish_kernel(int Q, bool hmm, ModelConst mc, const doub
         double drive[2], elbo_data;
         globals_drive(site, gl, mc, gstate + kMaxGlobalNoise, acc, hacc, sN, sF, drive, elbo_data);
         const double g0 = prep->grad[site][0][i];
-        ggrads[i] = (T)(g0 + drive[0] * (prep->grad[site][1][i] - g0) + drive[1] * (prep->grad[site][2][i] - g0));
+        ggrads[i] = g0 + drive[0] * (prep->grad[site][1][i] - g0) + drive[1] * (prep->grad[site][2][i] - g0);
     }
     if (i == 0) {
         double drive[2], e;
@@ -892,7 +892,7 @@ static int globals_sample_impl(int dtype, int Q, bool hmm, const void* gparams, 
     const ModelConst m = *(const ModelConst*)mc;
     const int sites = global_site_count(Q, hmm);
     if (dtype == TQ_F32)
-        globals_sample_kernel<float><<<sites, 32, 0, st>>>((const float*)gparams, Q, hmm, m, noise_in, seed, (const StepState*)state,
+        globals_sample_kernel<float><<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, noise_in, seed, (const StepState*)state,
                                                       gstate, (GlobalTables<double>*)tables, (float*)gain_out);
     else if (dtype == TQ_F64)
         globals_sample_kernel<double><<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, noise_in, seed, (const StepState*)state,
@@ -1201,11 +1201,8 @@ extern "C" int tq_cosmos_globals_grad(int dtype, int Q, const void* gparams, con
     TQ_CHECK_ARG(gparams && mc && gstate && acc && ggrads && elbo_parts && loss, "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
-    if (dtype == TQ_F32)
-        globals_grad_kernel<float><<<global_site_count(Q), 32, 0, st>>>((const float*)gparams, Q, m, gstate, acc, sN, sF, (float*)ggrads, elbo_parts);
-    else if (dtype == TQ_F64)
-        globals_grad_kernel<double><<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, gstate, acc, sN, sF, (double*)ggrads, elbo_parts);
-    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    if (dtype != TQ_F32 && dtype != TQ_F64) { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    globals_grad_kernel<<<global_site_count(Q), 32, 0, st>>>((const double*)gparams, Q, m, gstate, acc, sN, sF, (double*)ggrads, elbo_parts);
     TQ_LAUNCH_CHECK("globals_grad_kernel launch");
     finalize_loss_kernel<<<1, 32, 0, st>>>(elbo_parts, global_site_count(Q), loss);
     TQ_LAUNCH_CHECK("finalize_loss_kernel launch");
@@ -1221,11 +1218,8 @@ static int globals_prepare_impl(int dtype, int Q, bool hmm, const void* gparams,
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
     const int sites = global_site_count(Q, hmm);
-    if (dtype == TQ_F32)
-        globals_prepare_kernel<float><<<sites, 32, 0, st>>>((const float*)gparams, Q, hmm, m, gstate, (GlobalPrep*)gprep);
-    else if (dtype == TQ_F64)
-        globals_prepare_kernel<double><<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, gstate, (GlobalPrep*)gprep);
-    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    if (dtype != TQ_F32 && dtype != TQ_F64) { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    globals_prepare_kernel<<<sites, 32, 0, st>>>((const double*)gparams, Q, hmm, m, gstate, (GlobalPrep*)gprep);
     TQ_LAUNCH_CHECK("globals_prepare_kernel launch");
     return TQ_OK;
 }
@@ -1236,11 +1230,8 @@ static int globals_finish_impl(int dtype, int Q, bool hmm, const void* mc, const
     TQ_CHECK_ARG(mc && gstate && gprep && acc && ggrads && loss && (hacc || !hmm), "NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelConst m = *(const ModelConst*)mc;
-    if (dtype == TQ_F32)
-        globals_finish_kernel<float><<<1, 64, 0, st>>>(Q, hmm, m, gstate, (const GlobalPrep*)gprep, acc, hacc, sN, sF, (float*)ggrads, loss);
-    else if (dtype == TQ_F64)
-        globals_finish_kernel<double><<<1, 64, 0, st>>>(Q, hmm, m, gstate, (const GlobalPrep*)gprep, acc, hacc, sN, sF, (double*)ggrads, loss);
-    else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    if (dtype != TQ_F32 && dtype != TQ_F64) { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
+    globals_finish_kernel<<<1, 64, 0, st>>>(Q, hmm, m, gstate, (const GlobalPrep*)gprep, acc, hacc, sN, sF, (double*)ggrads, loss);
     TQ_LAUNCH_CHECK("globals_finish_kernel launch");
     return TQ_OK;
 }

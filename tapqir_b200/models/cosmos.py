@@ -163,7 +163,7 @@ class cosmos(Model):
                 u = value.log()  # SoftmaxTransform.inv
             else:
                 u = transform_to(cons[name]).inv(value)
-            views[name].copy_(u.to(eng.dtype).reshape(views[name].shape))
+            views[name].copy_(u.to(views[name].dtype).reshape(views[name].shape))
         for buf in (eng.lm, eng.lv, eng.gm, eng.gv, eng.lgrads, eng.ggrads):
             buf.zero_()
         eng.set_iteration(0)

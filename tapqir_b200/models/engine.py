@@ -46,7 +46,10 @@ class CosmosEngine:
         z = lambda n, dt=dtype: torch.zeros(n, dtype=dt, device=dev)
         # parameters, gradients, Adam moments (flat; see layout.py)
         self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
-        self.gparams, self.ggrads, self.gm, self.gv = z(self.gl.numel), z(self.gl.numel), z(self.gl.numel), z(self.gl.numel)
+        # the global parameters (4 + 5Q scalars), their gradients and moments are float64 whatever `dtype` is: the
+        # global sites are evaluated in double anyway, and rounding gain_loc / gain_beta to fp32 alone moves the
+        # gradient of gain_beta by 1e-4 of itself (it cancels ~1e3-fold in the base variate)
+        self.gparams, self.ggrads, self.gm, self.gv = (z(self.gl.numel, f64) for _ in range(4))
         # small device-resident state
         self.state = torch.zeros(1, dtype=torch.int64, device=dev)          # StepState.step
         self.tables = torch.zeros(self.lib.tq_sizeof_tables(), dtype=torch.uint8, device=dev)
@@ -121,7 +124,7 @@ class CosmosEngine:
     def load_unconstrained(self, tensors):
         views = self.named_unconstrained()
         for k, v in views.items():
-            v.copy_(tensors[k].to(device=self.device, dtype=self.dtype).reshape(v.shape))
+            v.copy_(tensors[k].to(device=self.device, dtype=v.dtype).reshape(v.shape))
 
     # ---- one step ------------------------------------------------------------------------------------------
     def step(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
@@ -226,7 +229,7 @@ class CosmosEngine:
                            "tq_cosmos_globals_finish")
                 if update:
                     b1, b2 = self.betas
-                    _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
+                    _lib.check(lib.tq_adam_dense(_lib.TQ_F64, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
                                                  p(self.gv), self.lr, b1, b2, self.adam_eps, p(self.state), sst),
                                "tq_adam_dense")
                 self._ev_join.record(self._side)

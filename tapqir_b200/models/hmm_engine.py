@@ -25,7 +25,7 @@ class HmmEngine(CosmosEngine):
         self.gl = L.HmmGlobalLayout(self.C)
         z = lambda n, dt=dtype: torch.zeros(n, dtype=dt, device=dev)
         self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
-        self.gparams, self.ggrads, self.gm, self.gv = z(self.gl.numel), z(self.gl.numel), z(self.gl.numel), z(self.gl.numel)
+        self.gparams, self.ggrads, self.gm, self.gv = (z(self.gl.numel, f64) for _ in range(4))   # always float64 (engine.py)
         self.nh = self.lib.tq_hmm_chain_sums()
         # accumulators and chain sums in one buffer: one cross-rank sum covers both
         self.acc_all = z(self.C * (L.NACC + self.nh), f64)
@@ -56,7 +56,7 @@ class HmmEngine(CosmosEngine):
     def load_unconstrained(self, tensors):
         self.ll.load_named(self.lparams, tensors)
         for k, v in self.gl.views(self.gparams).items():
-            v.copy_(tensors[k].to(device=self.device, dtype=self.dtype).reshape(v.shape))
+            v.copy_(tensors[k].to(device=self.device, dtype=v.dtype).reshape(v.shape))
 
     # ---- one step ------------------------------------------------------------------------------------------------------
     def _enqueue(self, ndx=None, fdx=None, local_noise=None, global_noise=None, update=True, time_likelihood=None):
@@ -122,7 +122,7 @@ class HmmEngine(CosmosEngine):
                                                      self.sN, p(self.ggrads), p(self.loss), sst), "tq_hmm_globals_finish")
                 if update:
                     b1, b2 = self.betas
-                    _lib.check(lib.tq_adam_dense(code, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
+                    _lib.check(lib.tq_adam_dense(_lib.TQ_F64, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),
                                                  p(self.gv), self.lr, b1, b2, self.adam_eps, p(self.state), sst),
                                "tq_adam_dense")
                 self._ev_join.record(self._side)

@@ -292,7 +292,7 @@ class Model:
                 else:
                     views = dict(eng.ll.views(lflat), **eng.gl.views(gflat))
                 for k, v in views.items():
-                    v.copy_(opt[k]["state"][0][key].to(device=self.device, dtype=eng.dtype).reshape(v.shape))
+                    v.copy_(opt[k]["state"][0][key].to(device=self.device, dtype=v.dtype).reshape(v.shape))
             steps = [int(opt[k]["state"][0]["step"]) for k in opt]
             eng.set_iteration(max(steps) if steps else 0)
             logger.info(f"Iteration #{self.iter}. Loaded a model checkpoint from {model_path}")

@@ -142,3 +142,76 @@ def golden_c1_fit():
                        case["offset_samples"], case["offset_weights"])
     data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
     return ds, data, case
+
+
+def global_grad_conditioning(params, data, ndx, fdx, noise, **kw):
+    """
+    Forward-error scale of every global gradient entry, from the fp64 oracle.  With s the guide samples of the global
+    sites (gain, pi, lamda, proximity):
+
+        d loss / d theta_i = sum_s J_is G_s + e_i,     G_s = d loss / d s = sum_units g_us + r_s
+
+    ``J`` (pathwise d sample / d theta), ``e`` (explicit part) and ``r`` (prior / guide terms of the sample itself) come
+    from the fp64 global-site code; the per-unit contributions ``g_us`` -- for the gain, sums over the pixels of a
+    patch of terms  img ln(y/img) + img - y + gain/2  whose expectation is ZERO at the true gain -- are what the fp32
+    kernels deliver, and they carry both signs: as a fit converges G_gain goes to zero while its terms do not (C1 fit:
+    118 k at iteration 1, 24 k at iteration 91, terms unchanged).  The scale a relative tolerance is measured against is
+    therefore  sum_s |J_is| (sum over pixels / units of |terms of G_s| + |r_s|) + |e_i|,  and its ratio to
+    |d loss / d theta_i| is the entry's condition number (1 = nothing cancels).  The terms are read off as
+    d G_s / d pixel_weights and d G_s / d unit_weights (one double-backward pass per sample component).
+    Returns name -> (scale tensor, worst condition number).
+    """
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    uw = torch.ones(len(ndx), len(fdx), data.C, dtype=data.dtype, requires_grad=True)
+    pw = torch.ones(len(ndx), len(fdx), data.C, data.P, data.P, dtype=data.dtype, requires_grad=True)
+    total, parts = O.elbo(leaves, data, ndx, fdx, noise, return_parts=True, unit_weights=uw, pixel_weights=pw, **kw)
+    loss = -total
+    gl = [leaves[k] for k in L.GLOBAL_NAMES]
+    samples = [parts[s] for s in ("gain", "pi", "lamda", "proximity")]
+    G = torch.autograd.grad(loss, samples, create_graph=True)
+    chain = [torch.zeros_like(t) for t in gl]
+    chain_abs = [torch.zeros_like(t) for t in gl]
+    for smp, Gs in zip(samples, G):
+        for j in range(Gs.numel()):
+            Gj = Gs.reshape(-1)[j]
+            g_units, g_pix = torch.autograd.grad(Gj, [uw, pw], retain_graph=True, allow_unused=True)
+            g_units = torch.zeros_like(uw) if g_units is None else g_units
+            g_pix = torch.zeros_like(pw) if g_pix is None else g_pix
+            # pixel terms, what a unit adds beyond its pixels, and what the sample's own prior / guide terms add
+            g_abs = g_pix.abs().sum() + (g_units - g_pix.sum((-1, -2))).abs().sum() + (Gj.detach() - g_units.sum()).abs()
+            Jj = torch.autograd.grad(smp.reshape(-1)[j], gl, retain_graph=True, allow_unused=True)
+            for i, J in enumerate(Jj):
+                if J is not None:
+                    chain[i] += J * Gj.detach()
+                    chain_abs[i] += J.abs() * g_abs
+    full = torch.autograd.grad(loss, gl)
+    out = {}
+    for k, f, c, ca in zip(L.GLOBAL_NAMES, full, chain, chain_abs):
+        scale = ca + (f - c).abs()
+        out[k] = (scale, (scale / f.abs().clamp_min(1e-300)).max().item())
+    return out
+
+
+def compare_global_grads_conditioned(ours, ref, cond, tol):
+    """|ours - ref| <= tol * (|J^T G| + |e|) entry by entry (see global_grad_conditioning); returns offenders as
+    name -> (error / scale, error / |ref|, condition number)."""
+    bad = {}
+    for k, (scale, kappa) in cond.items():
+        r = ref[k].double()
+        err = (ours[k].double().cpu().reshape(r.shape) - r).abs()
+        if not bool((err <= tol * scale.reshape(r.shape)).all()):
+            bad[k] = ((err / scale.reshape(r.shape)).max().item(), (err / r.abs()).max().item(), kappa)
+    return bad
+
+
+def check_global_grads(ours, ref, params, data, ndx, fdx, noise, tol=1e-5, **kw):
+    """North-star check of the global gradients: ``tol`` of each entry's forward-error scale
+    (global_grad_conditioning; implies ``tol`` x condition number relative to the entry itself), and ``tol`` relative
+    to the tensor's own largest entry wherever nothing cancels (condition number <= 1.5).  Returns the offenders
+    (empty = pass)."""
+    cond = global_grad_conditioning(params, data, ndx, fdx, noise, **kw)
+    bad = {k: ("conditioned",) + v for k, v in compare_global_grads_conditioned(ours, ref, cond, tol).items()}
+    well = [k for k, (_, kappa) in cond.items() if kappa <= 1.5]
+    if well:
+        bad.update({k: ("self-max", v) for k, v in compare_grads(ours, ref, tol, names=well).items()})
+    return bad

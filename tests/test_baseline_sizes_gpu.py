@@ -1,0 +1,321 @@
+"""
+GPU parity at the sizes and in the regimes BASELINE.json names: the fp32 production kernels
+through the C ABI against ``oracle.loss_and_grads`` on
+
+  (i)   a 10 x 512 minibatch (the reference default, main.py:1428-1431) drawn from a 100 x 1000 dataset (config 2),
+  (ii)  a two-channel minibatch inside a 500 x 2000 x 2 store (config 4),
+  (iii) the hmm variant with chains of 2000 frames inside a 200-AOI store (config 5),
+  (iv)  a 1000 x 5000 store (config 3) with the minibatch taken from the FAR END of every buffer,
+  (v)   parameters after 2000 device-RNG SVI iterations (the regimes a real fit spends its time in: relaxed guides of
+        absent spots, tail draws, the double-precision worklist),
+  (vi)  offset histograms: the simulator's three bins kept distinct (merge_offsets=False) and 64 distinct bins,
+  (vii) a full-batch launch of 10^5 units (persistent-kernel rounds, partial last round, tail) through size-independent
+        properties: a sum over disjoint AOI blocks, and equality with the same units evaluated as minibatches.
+
+How the big stores are compared with a CPU oracle that finishes in seconds: one step touches the dataset only through
+the minibatch block and the two plate sizes (cosmos.py:194-208), so the oracle is given the gathered block and
+``plate_sizes=(Nt, F)``; on the device side the block sits at its place inside buffers of the full size, every other
+entry of the gradient buffer must come out exactly zero.  Tolerances: the north star -- loss 1e-6, gradients 1e-5 of
+each tensor's largest entry; global gradients 1e-5 of their own magnitude where nothing cancels, else of their
+forward-error scale (step_helpers.check_global_grads).
+"""
+
+import math
+
+import pytest
+import torch
+
+from oracle import cosmos_oracle as O
+from tapqir_b200.models import layout as L
+from tapqir_b200.utils.dataset import DeviceStore
+from tapqir_b200.utils.simulate import simulate
+from tests.step_helpers import check_global_grads, compare_grads, flat_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def block_problem(nb, fb, C, seed, offsets="sim", perturb=0.3):
+    """Simulated (nb, fb, C) block + oracle parameters / variates for it (fp32-representable on both sides)."""
+    kw = {}
+    if offsets == "hist64":
+        s = torch.arange(58.0, 122.0)
+        w = torch.exp(-0.5 * ((s - 90) / 8) ** 2) + 1e-4
+        kw = dict(offset_samples=s, offset_weights=w / w.sum())
+    ds = simulate(nb, fb, C=C, seed=seed, **kw)
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    g = torch.Generator().manual_seed(seed + 100)
+    params = O.to_unconstrained(O.init_constrained(data), data.P, data.dtype)
+    for v in params.values():
+        v.add_(perturb * torch.randn(v.shape, generator=g, dtype=v.dtype))
+    params = {k: v.float().double() for k, v in params.items()}
+    ndx, fdx = torch.arange(nb), torch.arange(fb)
+    noise = {k: v.float().double() for k, v in O.draw_noise(params, data, ndx, fdx, g).items()}
+    return ds, data, params, noise
+
+
+def big_store(ds, Nt, F, ndx, fdx, merge_offsets=True):
+    """Device store of the full size (Nt, F, C) whose minibatch block (ndx x fdx) is ``ds``; every other patch is flat
+    background (it must not influence the step)."""
+    from tapqir_b200.utils.dataset import merge_offset_support
+
+    nb, fb, C, P = ds.images.shape[0], ds.images.shape[1], ds.images.shape[2], ds.images.shape[3]
+    pix = torch.full((Nt, F, C, P, P), 240, dtype=torch.int16, device=DEV)
+    n, f = ndx.to(DEV)[:, None], fdx.to(DEV)[None, :]
+    pix[n, f] = ds.images.to(torch.int16).to(DEV)
+    xy = torch.full((Nt, F, C, 2), (P - 1) / 2, dtype=torch.float32, device=DEV)
+    xy[n, f] = ds.xy.to(torch.float32).to(DEV)
+    ont = torch.zeros(Nt, dtype=torch.uint8, device=DEV)
+    ont[ndx.to(DEV)] = ds.is_ontarget.to(torch.uint8).to(DEV)
+    mask = torch.ones(Nt, dtype=torch.uint8, device=DEV)
+    off_s, off_l = ds.offset.samples, ds.offset.logits
+    if merge_offsets:
+        off_s, off_l = merge_offset_support(off_s, off_l)
+    return DeviceStore(pix.view(torch.uint16), xy, ont, mask, off_s.to(DEV, torch.float32).contiguous(),
+                       off_l.to(DEV, torch.float32).contiguous())
+
+
+def scatter_params(eng, params, ndx, fdx):
+    """Write the block's parameters at (ndx, fdx) of the engine's full-size buffers (the rest keeps a harmless fill)."""
+    n, f = ndx.to(DEV)[:, None], fdx.to(DEV)[None, :]
+    for name, view in eng.named_unconstrained().items():
+        src = params[name].to(DEV, view.dtype)
+        if name in L.GLOBAL_NAMES or name not in L.LOCAL_NAMES:
+            view.copy_(src.reshape(view.shape))
+        elif view.dim() == 3 and view.shape[1] == 1:          # (Nt, 1, C)
+            view[ndx.to(DEV)] = src
+        elif view.dim() == 3:                                  # (Nt, F, C)
+            view[n, f] = src
+        else:                                                  # (K, Nt, F, C)
+            view[:, n, f] = src
+
+
+def gather_grads(eng, ndx, fdx):
+    """Gradients of the block + the largest |gradient| outside it (must be zero)."""
+    n, f = ndx.to(DEV)[:, None], fdx.to(DEV)[None, :]
+    out, outside = {}, 0.0
+    for name, g in eng.named_grads().items():
+        if name not in L.LOCAL_NAMES:
+            out[name] = g
+            continue
+        if g.dim() == 3 and g.shape[1] == 1:
+            blk = g[ndx.to(DEV)]
+        elif g.dim() == 3:
+            blk = g[n, f]
+        else:
+            blk = g[:, n, f]
+        out[name] = blk
+        outside = max(outside, abs(g.double().abs().sum().item() - blk.double().abs().sum().item()) /
+                      max(blk.double().abs().sum().item(), 1e-300))
+    return out, outside
+
+
+def run_block_case(Nt, F, C, nb, fb, ndx, fdx, seed, offsets="sim", merge_offsets=True, perturb=0.3):
+    from tapqir_b200.models.engine import CosmosEngine
+
+    ds, data, params, noise = block_problem(nb, fb, C, seed, offsets, perturb)
+    store = big_store(ds, Nt, F, ndx, fdx, merge_offsets)
+    eng = CosmosEngine(store, Nt, F, C, data.P, O.DEFAULT_PRIORS, dtype=torch.float32, nbatch_size=nb, fbatch_size=fb)
+    eng.lparams.fill_(0.5)
+    scatter_params(eng, params, ndx, fdx)
+    bn, bf = torch.arange(nb), torch.arange(fb)
+    ref_loss, ref_grads = O.loss_and_grads(params, data, bn, bf, noise, plate_sizes=(Nt, F))
+    _, _, _, _, lnoise, gnoise = flat_inputs(data, params, noise, torch.float32)
+    loss = eng.step(update=False, ndx=ndx.to(torch.int32).to(DEV), fdx=fdx.to(torch.int32).to(DEV),
+                    local_noise=lnoise.to(DEV), global_noise=gnoise.to(DEV)).item()
+    assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss), (loss, ref_loss)
+    ours, outside = gather_grads(eng, ndx, fdx)
+    assert outside <= 1e-12, f"gradient mass outside the minibatch: {outside}"
+    bad = compare_grads(ours, ref_grads, 1e-5, names=L.LOCAL_NAMES)
+    bad.update(check_global_grads(ours, ref_grads, params, data, bn, bf, noise, plate_sizes=(Nt, F)))
+    assert not bad, bad
+    return eng
+
+
+def far_end(total, count, seed):
+    """``count`` distinct indices in shuffled order from the last ``2 * count`` entries, the very last one included."""
+    g = torch.Generator().manual_seed(seed)
+    pool = torch.arange(total - 2 * count, total - 1)
+    idx = torch.cat([pool[torch.randperm(len(pool), generator=g)[:count - 1]], torch.tensor([total - 1])])
+    return idx[torch.randperm(count, generator=g)]
+
+
+def test_c2_reference_default_minibatch():
+    """(i) 10 AOIs x 512 frames drawn at random from a 100 x 1000 dataset."""
+    g = torch.Generator().manual_seed(1)
+    run_block_case(100, 1000, 1, 10, 512, torch.randperm(100, generator=g)[:10], torch.randperm(1000, generator=g)[:512], seed=21)
+
+
+def test_c4_two_channel_minibatch_in_a_500_x_2000_store():
+    """(ii) C = 2: per-channel pi / lamda, shared gain and offsets."""
+    g = torch.Generator().manual_seed(2)
+    run_block_case(500, 2000, 2, 6, 300, torch.randperm(500, generator=g)[:6], torch.randperm(2000, generator=g)[:300], seed=22)
+
+
+def test_c3_store_far_end_of_every_buffer():
+    """(iv) 1000 x 5000: pixels 1.96 GB, 18 x 5 M parameters; the minibatch's AOIs and frames at the far end (byte
+    offsets beyond 2^31, parameter indices up to 9 x 10^7)."""
+    run_block_case(1000, 5000, 1, 8, 400, far_end(1000, 8, 3), far_end(5000, 400, 4), seed=23)
+
+
+@pytest.mark.parametrize("offsets,merge", [("sim", False), ("hist64", True)])
+def test_offset_histograms_at_minibatch_scale(offsets, merge):
+    """(vi) the O = 3 register-cached form (three identical bins kept) and the two-pass O > 4 form with 64 distinct bins."""
+    g = torch.Generator().manual_seed(5)
+    eng = run_block_case(100, 1000, 1, 6, 200, torch.randperm(100, generator=g)[:6], torch.randperm(1000, generator=g)[:200],
+                         seed=24, offsets=offsets, merge_offsets=merge)
+    assert eng.store.offset_samples.numel() == (3 if offsets == "sim" else 64)
+
+
+def test_c5_hmm_chains_of_2000_frames():
+    """(iii) cosmos+hmm: 3 chains of 2000 frames out of a 200-AOI store (chunked scans across 128 threads)."""
+    from oracle import hmm_oracle as H
+    from tapqir_b200.models.hmm_engine import HmmEngine
+
+    Nt, F, nb = 200, 2000, 3
+    ds = simulate(nb, F, C=1, seed=31, params={"kon": 0.2, "koff": 0.2})
+    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    g = torch.Generator().manual_seed(131)
+    params = H.to_unconstrained(H.init_constrained(data), data.P, data.dtype)
+    for v in params.values():
+        v.add_(0.3 * torch.randn(v.shape, generator=g, dtype=v.dtype))
+    params = {k: v.float().double() for k, v in params.items()}
+    bn = torch.arange(nb)
+    noise = {k: v.float().double() for k, v in H.draw_noise(params, data, bn, g).items()}
+    ref_loss, ref_grads = H.loss_and_grads(params, data, bn, noise, plate_n=Nt)
+    ndx = torch.tensor([199, 7, 120])
+    store = big_store(ds, Nt, F, ndx, torch.arange(F))
+    eng = HmmEngine(store, Nt, F, 1, data.P, O.DEFAULT_PRIORS, dtype=torch.float32, nbatch_size=nb)
+    eng.lparams.fill_(0.5)
+    full = {}
+    for name, view in eng.named_unconstrained().items():   # reference names / shapes; m_probs is a stacked copy
+        src = params[name].to(DEV, view.dtype)
+        if view.dim() <= 2 or name.startswith(("init_", "trans_")) or name in L.GLOBAL_NAMES:
+            full[name] = src.reshape(view.shape)
+            continue
+        t = view.clone()
+        nd = ndx.to(DEV)
+        if name == "m_probs":            # (2, K, Nt, F, C)
+            t[:, :, nd] = src
+        elif name == "z_trans":          # (Nt, F, C, 2, 2)
+            t[nd] = src
+        elif t.dim() == 3:               # (Nt, F, C) / (Nt, 1, C)
+            t[nd] = src
+        else:                            # (K, Nt, F, C)
+            t[:, nd] = src
+        full[name] = t
+    eng.load_unconstrained(full)
+    lnoise = L.pack_local_noise(noise, torch.float32, DEV)
+    gnoise = eng.gl.pack_noise(noise).to(DEV)
+    loss = eng.step(update=False, ndx=ndx.to(torch.int32).to(DEV), local_noise=lnoise, global_noise=gnoise).item()
+    assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss), (loss, ref_loss)
+    nd = ndx.to(DEV)
+    bad = {}
+    for name, gfull in eng.named_grads().items():
+        r = ref_grads[name]
+        if gfull.shape == r.shape:
+            ours = gfull
+        elif name == "m_probs":
+            ours = gfull[:, :, nd]
+        elif name == "z_trans" or gfull.dim() == 3:
+            ours = gfull[nd]
+        else:
+            ours = gfull[:, nd]
+        denom = r.abs().max().item()
+        rel = (ours.double().cpu() - r).abs().max().item() / denom if denom > 0 else 0.0
+        # hmm globals: the pair scale of tests/test_hmm_cpu.py::hmm_global_grads stays for the chain's init / trans sites
+        if name in H.GLOBAL_PARAMS:
+            continue
+        if not rel < 1e-5:
+            bad[name] = rel
+    from tests.test_hmm_cpu import hmm_global_grads
+
+    bad.update(hmm_global_grads({k: v for k, v in eng.named_grads().items()}, ref_grads, 1e-5))
+    assert not bad, bad
+
+
+def test_trained_state_after_2000_device_iterations():
+    """(v) 2000 SVI iterations with device-drawn minibatches / variates on a 40 x 300 dataset, then ONE replayed
+    10 x 128 minibatch step at those parameters against the oracle.  The fit must have left the initial regime: relaxed
+    height guides (concentration < 10) and small-concentration Beta sites present."""
+    from tapqir_b200.models.engine import CosmosEngine
+
+    Nt, F, nb, fb = 40, 300, 10, 128
+    ds = simulate(Nt, F, C=1, seed=41)
+    data_full = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
+    store = ds.device_store(DEV, torch.float32)
+    eng = CosmosEngine(store, Nt, F, 1, ds.P, O.DEFAULT_PRIORS, dtype=torch.float32, nbatch_size=Nt, fbatch_size=F, seed=7)
+    eng.load_unconstrained(O.to_unconstrained(O.init_constrained(data_full), ds.P, torch.float64))
+    for _ in range(2000):
+        eng.step()
+    torch.cuda.synchronize()
+    params = {k: v.detach().double().cpu().clone() for k, v in eng.named_unconstrained().items()}
+    assert all(bool(torch.isfinite(v).all()) for v in params.values())
+    h_conc = (params["h_loc"] + params["h_beta"]).exp()
+    assert (h_conc < 10).float().mean().item() > 0.2, "the fit has not relaxed the guides of absent spots"
+    g = torch.Generator().manual_seed(42)
+    ndx, fdx = torch.randperm(Nt, generator=g)[:nb], torch.randperm(F, generator=g)[:fb]
+    noise = {k: v.float().double() for k, v in O.draw_noise(params, data_full, ndx, fdx, g).items()}
+    ref_loss, ref_grads = O.loss_and_grads(params, data_full, ndx, fdx, noise)
+    eng.set_batch(nb, fb)
+    _, _, _, _, lnoise, gnoise = flat_inputs(data_full, params, noise, torch.float32)
+    loss = eng.step(update=False, ndx=ndx.to(torch.int32).to(DEV), fdx=fdx.to(torch.int32).to(DEV),
+                    local_noise=lnoise.to(DEV), global_noise=gnoise.to(DEV)).item()
+    assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss), (loss, ref_loss)
+    bad = compare_grads(eng.named_grads(), ref_grads, 1e-5, names=L.LOCAL_NAMES)
+    bad.update(check_global_grads(eng.named_grads(), ref_grads, params, data_full, ndx, fdx, noise))
+    assert not bad, bad
+
+
+def test_full_batch_launch_of_1e5_units_is_the_sum_of_its_aoi_blocks():
+    """(vii) 100 x 1000 full batch (10.56 rounds of the persistent likelihood kernel, partial last round, dynamic tail):
+    the accumulators of the full launch equal the sum over ten disjoint 10-AOI minibatch launches with the same
+    variates (plate scale corrected), and every AOI-local gradient entry equals the one its block launch produced --
+    whichever warp handled the unit, at whatever position of the round."""
+    from tapqir_b200.models.engine import CosmosEngine
+
+    Nt, F = 100, 1000
+    ds = simulate(Nt, F, C=1, seed=51)
+    store = ds.device_store(DEV, torch.float32)
+    data = O.OracleData(ds.images[:1], ds.xy[:1], ds.is_ontarget[:1], None, ds.offset.samples, ds.offset.weights)
+    eng = CosmosEngine(store, Nt, F, 1, ds.P, O.DEFAULT_PRIORS, dtype=torch.float32, nbatch_size=Nt, fbatch_size=F)
+    gen = torch.Generator(device=DEV).manual_seed(52)
+    eng.lparams.copy_(0.3 * torch.randn(eng.lparams.shape, generator=gen, device=DEV))
+    init = O.to_unconstrained(O.init_constrained(O.OracleData(ds.images[:2], ds.xy[:2], ds.is_ontarget[:2], None,
+                                                              ds.offset.samples, ds.offset.weights)), ds.P, torch.float64)
+    views = eng.named_unconstrained()
+    for name in L.LOCAL_NAMES:      # initial value + perturbation
+        views[name].add_(init[name].reshape(-1)[0].item())
+    for name in L.GLOBAL_NAMES:
+        views[name].copy_(init[name].to(DEV).reshape(views[name].shape))
+    U = Nt * F
+    # uniform base variates in (0, 1): valid for the Beta sites (a draw on [0, 1]) and as standard-gamma draws
+    lnoise = torch.rand(L.NSAMP, U, generator=gen, device=DEV) * 0.9 + 0.05
+    conc = {"background": (views["b_loc"] + views["b_beta"]).exp(), "height": (views["h_loc"] + views["h_beta"]).exp()}
+    lnoise[0] = (conc["background"].reshape(-1) * (1 + 0.2 * (lnoise[0] - 0.5))).float()          # gamma draws near their mean
+    lnoise[1:3] = (conc["height"].reshape(2, -1) * (1 + 0.2 * (lnoise[1:3] - 0.5))).float()
+    gn = torch.zeros(eng.gl.noise_numel, dtype=torch.float64, device=DEV)
+    nv = eng.gl.noise_views(gn)
+    nv["gain"].fill_(500.0)       # standard-gamma draw at concentration gain_loc gain_beta = 500
+    nv["proximity"].fill_(0.1)
+    nv["pi"].copy_(torch.tensor([[0.8, 0.2]]))
+    nv["lamda"].fill_(50.0)
+    loss_full = eng.step(update=False, local_noise=lnoise, global_noise=gn).item()
+    acc_full, grads_full = eng.acc.clone(), eng.lgrads.clone()
+    assert math.isfinite(loss_full)
+    blk = CosmosEngine(store, Nt, F, 1, ds.P, O.DEFAULT_PRIORS, dtype=torch.float32, nbatch_size=10, fbatch_size=F)
+    blk.lparams.copy_(eng.lparams)
+    blk.gparams.copy_(eng.gparams)
+    acc_sum = torch.zeros_like(acc_full)
+    ln3 = lnoise.view(L.NSAMP, Nt, F)
+    for b in range(10):
+        ndx = torch.arange(10 * b, 10 * b + 10, dtype=torch.int32, device=DEV)
+        blk.step(update=False, ndx=ndx, local_noise=ln3[:, 10 * b:10 * b + 10].reshape(L.NSAMP, -1).contiguous(), global_noise=gn)
+        acc_sum += blk.acc
+        gb, gf = dict(blk.ll.views(blk.lgrads)), dict(eng.ll.views(grads_full))
+        for name in L.LOCAL_NAMES:
+            a = gb[name][..., 10 * b:10 * b + 10, :, :] if gb[name].dim() == 4 else gb[name][10 * b:10 * b + 10]
+            f = gf[name][..., 10 * b:10 * b + 10, :, :] if gf[name].dim() == 4 else gf[name][10 * b:10 * b + 10]
+            # the block launch scales by Nt / 10, the full one by 1
+            assert torch.allclose(a / 10.0, f, rtol=2e-6, atol=0), (name, b)
+    assert torch.allclose(acc_sum, acc_full, rtol=1e-12, atol=1e-9 * acc_full.abs().max().item())

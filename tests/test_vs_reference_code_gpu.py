@@ -10,7 +10,7 @@ import torch
 
 from oracle import cosmos_oracle as O
 from tapqir_b200.models import layout as L
-from tests.step_helpers import compare_global_grads, compare_grads, flat_inputs, golden_step_case, masked_loss_constant
+from tests.step_helpers import check_global_grads, compare_grads, flat_inputs, golden_step_case, masked_loss_constant
 from tests.test_step_gpu import make_engine, replay_args
 
 pytestmark = pytest.mark.gpu
@@ -70,7 +70,8 @@ def test_fp32_production_kernels_within_north_star_of_reference_model_code(name)
     """The fp32 production kernels at every recorded iteration (parameters of the reference's trajectory, replayed by
     the oracle's Adam which tests/test_oracle.py pins to the same file), against the reference's fp64 numbers with
     NO rounding on the reference side: the north-star tolerance -- loss 1e-6, gradients 1e-5 of each tensor's largest
-    entry (global ones: of their distribution's parameter pair, step_helpers.compare_global_grads).  Measured on a
+    entry (global ones: of their OWN magnitude, or of their forward-error scale where the entry itself is a cancelling
+    sum, step_helpers.check_global_grads -- the global parameters are float64 on the device).  Measured on a
     B200 (profiles/r1s5_parity_vs_reference_code.log): loss <= 7.6e-7, local gradients <= 8.9e-6, global <= 1.8e-6;
     replay mode is deterministic (fixed-order reductions), so the margins do not move between runs."""
     ds, data, case = golden_step_case(name)
@@ -92,9 +93,10 @@ def test_fp32_production_kernels_within_north_star_of_reference_model_code(name)
         ref_grads = {k: g.reshape(params[k].shape) for k, g in step["grads"].items()}
         bad = compare_grads(eng.named_grads(), ref_grads, 1e-5, names=L.LOCAL_NAMES)
         print(f"[{name} it {it}] loss rel {abs(loss - ref_loss) / abs(ref_loss):.2e}; worst local gradient rel "
-              f"{max(compare_grads(eng.named_grads(), ref_grads, 0.0, names=L.LOCAL_NAMES).values()):.2e}; worst global (pair scale) "
-              f"{max(compare_global_grads(eng.named_grads(), ref_grads, 0.0).values()):.2e}")
-        bad.update(compare_global_grads(eng.named_grads(), ref_grads, 1e-5))   # against the pair's largest entry, see there
+              f"{max(compare_grads(eng.named_grads(), ref_grads, 0.0, names=L.LOCAL_NAMES).values()):.2e}; worst global (self) "
+              f"{max(compare_grads(eng.named_grads(), ref_grads, 0.0, names=L.GLOBAL_NAMES).values()):.2e}")
+        # global gradients: 1e-5 of their OWN magnitude where nothing cancels, of their forward-error scale elsewhere
+        bad.update(check_global_grads(eng.named_grads(), ref_grads, params, data, step["ndx"], step["fdx"], step["noise"]))
         assert not bad, (it, bad)
         svi.step(step["ndx"], step["fdx"], step["noise"])
 
@@ -190,7 +192,6 @@ def test_c1_hundred_iterations_match_the_reference_run():
         assert err <= 1e-7 * max(1.0, v.abs().max().item()), (k, err)
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes ran out: not yet run on a device")
 def test_hmm_compute_stats_writes_reference_files(tmp_path):
     """`tapqir stats` for cosmos+hmm: credible intervals of hmm's own latents (``init``, ``trans``; hmm.py:70-81) next to
     the shared ones, posterior summaries and the three files (stats.py:131-258).  The interval arithmetic itself is pinned
@@ -222,7 +223,6 @@ def test_hmm_compute_stats_writes_reference_files(tmp_path):
     assert (tmp_path / "cosmos+hmm_params.mat").exists()
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes ran out: not yet run on a device")
 def test_read_glimpse_matches_the_reference_read_glimpse(tmp_path):
     """The CUDA ingestion (tq_crop_aois, tq_offset_hist) on the synthetic movie of tests/golden/ref_glimpse_folder/ against
     ``out/data.tpqr``, which the reference's own ``read_glimpse`` wrote for it (glimpse_reader.py:304-472, run verbatim by
