@@ -1,25 +1,29 @@
 """
 Benchmark of the cosmos SVI hot path (ELBO forward + backward + dense Adam), AOI-frames/sec.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c3|c2mb]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c3|c2|c2mb|c4|c5|c1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one full SVI step over one minibatch of synthetic (tapqir-simulated) data.
-Default workload = BASELINE.json configs[1]: N=100 AOIs x F=1000 frames, P=14, K=2, C=1, O=3 offset
-bins, full local batch, per GPU (weak scaling: every rank holds its own 100-AOI shard; only the
-(C, 18) accumulator vector is all-reduced).  Prints ONE JSON line (rank 0).
 
-Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) before
-each timed step outside the event pair, max over ranks; clocks sampled with nvidia-smi during the
-timed region.  `--impl reference` times the reference's CPU path restated by oracle/ (Pyro cannot be
-installed here) on a bounded sample of the same workload.
+Headline workload = BASELINE.json configs[2], the north-star target: N=1000 AOIs x F=5000 frames, P=14, K=2, C=1, full
+batch, at every N.  It fits one B200 (1.96 GB of pixels, 1.44 GB of parameters / gradients / Adam moments), so N=1 runs the
+same workload and the 1/2/4/8 curve is STRONG scaling: rank r holds AOIs [r * 1000/N, (r+1) * 1000/N) and all ranks
+exchange one (C, 18) vector of doubles per step over NVLink peer memory.  At N=1 the line also carries `sub_results`
+for the other single-GPU configurations (C2 full batch -- round 1's headline --, the reference-default 10 x 512 minibatch
+of C2, C2 with the simulator's three offset bins kept distinct and with a 64-bin offset histogram), each with its own
+roofline object.  Prints ONE JSON line (rank 0).
+
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) before each timed step outside
+the event pair, max over ranks; clocks sampled through NVML during the timed region.  `--impl reference` times the
+reference's CPU path restated by oracle/ (Pyro cannot be installed here) on a bounded sample of the same
+workload: reference-default 10 x 512 minibatches of a 100-AOI x 1000-frame slice of it.
 """
 
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -31,39 +35,51 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (AOIs per GPU, frames, nb, fb, description)
-    "c2": (100, 1000, 100, 1000, "cosmos C2: simulated N=100 AOIs x F=1000 frames per GPU, P=14, K=2, C=1, O=3, full local batch"),
-    "c2mb": (100, 1000, 10, 512, "cosmos C2 with the reference-default minibatch 10 AOIs x 512 frames (main.py:1428-1431)"),
-    "c3": (1000, 5000, 1000, 5000, "cosmos C3: simulated N=1000 AOIs x F=5000 frames on this GPU, full batch"),
+    # name: (AOIs in total, frames, nb, fb, description)
+    "c3": (1000, 5000, 1000, 5000, "cosmos C3: simulated N=1000 AOIs x F=5000 frames, P=14, K=2, C=1, O=3, full batch, AOI-sharded"),
+    "c2": (100, 1000, 100, 1000, "cosmos C2: simulated N=100 AOIs x F=1000 frames, P=14, K=2, C=1, O=3, full batch"),
+    "c2mb": (100, 1000, 10, 512, "cosmos C2: simulated N=100 AOIs x F=1000 frames, reference-default minibatch 10 AOIs x 512 frames (main.py:1428-1431)"),
     "c1": (5, 100, 5, 100, "cosmos C1: simulated N=5 AOIs x F=100 frames, full batch"),
     # BASELINE configs 4 and 5 (parity-test cases; here for per-config timings, not the headline line)
-    "c4": (500, 2000, 500, 2000, "cosmos C4: two-channel (C=2) simulated N=500 AOIs x F=2000 frames on this GPU, full batch"),
-    "c5": (200, 2000, 200, 2000, "cosmos+hmm C5: simulated N=200 AOIs x F=2000 frames on this GPU, all frames per step"),
+    "c4": (500, 2000, 500, 2000, "cosmos C4: two-channel (C=2) simulated N=500 AOIs x F=2000 frames, full batch"),
+    "c5": (200, 2000, 200, 2000, "cosmos+hmm C5: simulated N=200 AOIs x F=2000 frames, all frames per step"),
 }
 WORKLOAD_CHANNELS = {"c4": 2}
 WORKLOAD_MODEL = {"c5": "cosmos+hmm"}
 O_BINS = 3   # offset bins of the simulated data (simulate.py:92,103): three IDENTICAL bins, merged to one on upload
+SUBS = {     # sub-results of the N=1 line: name -> (workload, offset_hist, keep_offset_bins)
+    "c2": ("c2", 0, False), "c2mb": ("c2mb", 0, False), "c2_o3": ("c2", 0, True), "c2_o64": ("c2", 64, False),
+}
 
 
 def algorithmic_work(o_exec):
-    """Work per unit (one 14x14 patch, K=2, 4 configurations, forward + backward) of the likelihood kernel for
-    ``o_exec`` distinct offset bins -- DESIGN.md section 4.1.  SURVEY.md 8d estimates 980*O + 3276 MUFU ops and
-    8232*O + 63220 flops; the figures here are the TIGHTER counts of this repository's formulation (shared
-    log(D - delta_j); lgamma and digamma from one lg2 + one rcp; one rcp for 1/a and 1/sum; no exp / log-sum
-    at all for a single bin), so that `frac` cannot be flattered by work the kernel does not need:
-      MUFU:  P^2 * O [lg2(D - delta)] + M P^2 * (O + 3) [ex2 per bin, rcp, lg2 a, lg2 sum]  (O > 1)
-             P^2     + M P^2 * 2      [rcp a, lg2 a]                                          (O = 1)
-             + 2 K P [separable render]
-      FP32:  lane-operations (an FMA counts once) of the packed two-pixel sweep, counted in its SASS:
-             98 pairs * (2 * packed + scalar) + ~600 per-patch prologue/epilogue."""
+    """Work per unit (one 14x14 patch, K=2, 4 configurations, forward + backward) of the likelihood sweep for ``o_exec``
+    distinct offset bins -- DESIGN.md section 4.1.  Two accountings, both reported:
+
+    * SURVEY.md 8(d)'s estimate: 980 O + 3276 MUFU ops, 8232 O + 63220 flops (an upper estimate written before the
+      kernel existed: per-bin terms for every configuration, separate lgamma / digamma / log-sum evaluations);
+    * the EXECUTED count of this repository's formulation, read off the SASS of the packed two-pixel sweep
+      (profiles/r2_sass_ksmogn_o1.txt: per pixel pair 47 FFMA2 + 24 FADD2 + 14 FMUL2 + 8 FADD + 6 FMUL + 14 MUFU):
+        MUFU:  P^2 O [lg2(D - delta)] + M P^2 (O + 3) [ex2 per bin, rcp, lg2 a, lg2 sum]   (O > 1)
+               P^2   + (M - 1) P^2 2  [rcp a, lg2 a; the spot-free configuration is a closed form]   (O = 1)
+               + 2 K P [separable render]
+        flops (an FMA = 2, an add or a multiply = 1 -- the measured peak is an FMA loop, so a kernel made of adds alone
+        would top out at half of it) and FP32-pipe lane operations (every FMA / add / multiply occupies one slot of the
+        pipe that binds this kernel: the honest measure of how busy the pipe can get)."""
     P2, M, K, P = 196, 4, 2, 14
+    pairs = P2 // 2
     if o_exec == 1:
-        mufu = P2 + M * P2 * 2 + 2 * K * P
-        fp32_ops = 98 * (2 * 85 + 14) + 600               # 47 FFMA2 + 24 FADD2 + 14 FMUL2, 14 scalar per pair
-    else:
+        mufu = P2 + (M - 1) * P2 * 2 + 2 * K * P
+        ffma2, fadd2, fmul2, fadd, fmul = 47, 24, 14, 8, 6
+    else:   # cached-offset form: per pair 35 + 53 O packed (of which ~55 % FMAs), 13 scalar
         mufu = P2 * o_exec + M * P2 * (o_exec + 3) + 2 * K * P
-        fp32_ops = 98 * (2 * (35 + 53 * o_exec) - 2 * 1 + 13) + 600   # 193 packed at O = 3
-    return mufu, fp32_ops
+        packed = 35 + 53 * o_exec - 1
+        ffma2, fadd2, fmul2, fadd, fmul = round(0.55 * packed), round(0.28 * packed), packed - round(0.55 * packed) - round(0.28 * packed), 7, 6
+    per_patch = 600   # prologue / epilogue: render tables, closed forms, reductions
+    lane_ops = pairs * (2 * (ffma2 + fadd2 + fmul2) + fadd + fmul) + per_patch
+    flops = pairs * (4 * ffma2 + 2 * (fadd2 + fmul2) + fadd + fmul) + per_patch * 3 // 2
+    return {"mufu_ops": mufu, "fp32_lane_ops": lane_ops, "fp32_flop": flops,
+            "survey_8d": {"mufu_ops": 980 * o_exec + 3276, "fp32_flop": 8232 * o_exec + 63220}}
 
 
 HBM_BYTES_PER_UNIT = 604 + 504
@@ -157,229 +173,299 @@ def measure_peaks(lib, _lib, device):
     return out
 
 
-def make_shard(workload, rank, device, offset_hist=0):
+def offset_histogram(n_bins):
+    """SURVEY 8d "secondary realism run": a Gaussian-shaped histogram of ``n_bins`` distinct integer offsets around 90."""
+    s = torch.arange(90 - n_bins // 2, 90 - n_bins // 2 + n_bins, dtype=torch.float64)
+    w = torch.exp(-0.5 * ((s - 90) / max(n_bins / 8.0, 1.0)) ** 2) + 1e-4
+    return dict(offset_samples=s, offset_weights=w / w.sum())
+
+
+def make_shard(workload, rank, world, device, offset_hist=0, scaling="strong"):
+    """This rank's AOI block of the workload (strong scaling: 1/world of its AOIs; weak: all of them), simulated on the
+    device with seed = rank."""
     from tapqir_b200.utils.simulate import simulate
 
     n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
+    if scaling == "strong" and world > 1:
+        if n_aoi % world:
+            raise SystemExit(f"workload {workload}: {n_aoi} AOIs do not split evenly over {world} ranks (bench shards are simulated per rank)")
+        n_aoi, nb = n_aoi // world, max(1, nb // world)
     kinetic = {"kon": 0.2, "koff": 0.2} if WORKLOAD_MODEL.get(workload) == "cosmos+hmm" else None   # test_tapqir.py:31-33
-    kw = {}
-    if offset_hist:     # SURVEY 8d "secondary realism run": a non-degenerate offset histogram of `offset_hist` distinct bins
-        s = torch.arange(90 - offset_hist // 2, 90 - offset_hist // 2 + offset_hist, dtype=torch.float64)
-        w = torch.exp(-0.5 * ((s - 90) / max(offset_hist / 8.0, 1.0)) ** 2) + 1e-4
-        kw = dict(offset_samples=s, offset_weights=w / w.sum())
+    kw = offset_histogram(offset_hist) if offset_hist else {}
+    if offset_hist:
         desc += f"; offsets: Gaussian-shaped histogram of {offset_hist} distinct integer bins around 90 instead of O=3"
     ds = simulate(n_aoi, n_frames, C=WORKLOAD_CHANNELS.get(workload, 1), P=14, seed=rank, device=device, aoi_chunk=50,
                   params=kinetic, **kw)
     return ds, nb, fb, desc
 
 
-def run_native(args):
-    from oracle import cosmos_oracle as O
-    from tapqir_b200 import _lib
+def config_of(workload, world, scaling, offset_hist, keep_offset_bins, train_iters=0):
+    """The `config` object of the JSON line -- the same for the native and the reference arm."""
+    n_aoi, n_frames, nb, fb, desc = WORKLOADS[workload]
+    per = n_aoi // world if scaling == "strong" else n_aoi
+    if offset_hist:
+        desc += f"; offsets: Gaussian-shaped histogram of {offset_hist} distinct integer bins around 90 instead of O=3"
+    return {"workload": desc, "model": WORKLOAD_MODEL.get(workload, "cosmos"), "channels": WORKLOAD_CHANNELS.get(workload, 1),
+            "aois_total": n_aoi if scaling == "strong" else n_aoi * world, "frames": n_frames,
+            "aois_per_gpu": per, "nb_per_gpu": max(1, nb // world) if scaling == "strong" else nb,
+            "fb": fb, "offset_bins": offset_hist or O_BINS,
+            "offset_bins_distinct": offset_hist or (O_BINS if keep_offset_bins else 1),
+            "train_iters_before_timing": train_iters, "parallelism": f"aoi-shard x{world} ({scaling} scaling)",
+            "l2": "flushed (256 MiB write) before every timed step",
+            "local_terms_dtype": "f32 (double fallback outside the fp32 regimes; global sites f64)", "likelihood_dtype": "f32"}
+
+
+class Timer:
+    def __init__(self, device, world):
+        self.device, self.world = device, world
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(self.device)
+
+    def steps(self, fn, n):
+        """n calls of fn, each bracketed by CUDA events after an (untimed) L2 flush; returns max-over-ranks ms per step."""
+        evs = []
+        for _ in range(n):
+            self.flush.fill_(1)  # evict the 126 MB L2 (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        self.barrier()
+        total = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            torch.distributed.all_reduce(total, op=torch.distributed.ReduceOp.MAX)
+        return total.item() / n
+
+
+def build_model(workload, rank, world, device, offset_hist, keep_offset_bins, scaling):
     from tapqir_b200.models import models as model_registry
+
+    ds, nb, fb, desc = make_shard(workload, rank, world, device, offset_hist, scaling)
+    model = model_registry[WORKLOAD_MODEL.get(workload, "cosmos")](device=str(device), dtype="float")
+    model.data = ds
+    model.merge_offsets = not keep_offset_bins
+    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world, presharded=True)
+    return model, desc
+
+
+def roofline_of(model, timer, peaks, hbm_peak, hbm_src, ms_per_step, steps, world, workload):
+    """Roofline object of the dominant kernel (the likelihood sweep), timed alone with CUDA events on its stream."""
+    eng = model.engine
+    patches = eng.nb * eng.fb * eng.C
+    k_ms = []
+    for _ in range(max(3, min(steps, 10))):
+        timer.flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        model.step(time_likelihood=(e0, e1))
+        torch.cuda.synchronize(timer.device)
+        k_ms.append(e0.elapsed_time(e1))
+    k_s = sum(k_ms) / len(k_ms) * 1e-3
+    o_exec = int(eng.store.offset_samples.numel())   # distinct offset bins the kernels loop over
+    w = algorithmic_work(o_exec)
+    fma_peak_ops, mufu_peak = peaks["fma"], peaks["mufu"]          # lane-ops / s, MUFU ops / s
+    flop_peak = 2 * fma_peak_ops
+    t_mufu, t_pipe = w["mufu_ops"] / mufu_peak, w["fp32_lane_ops"] / fma_peak_ops
+    t_hbm = KSMOGN_HBM_BYTES_PER_UNIT / (hbm_peak * 1e9)
+    bound = max((t_mufu, "mufu"), (t_pipe, "fp32"), (t_hbm, "hbm"))
+    units_per_s = patches / k_s
+    s8 = w["survey_8d"]
+    t8 = max(s8["mufu_ops"] / mufu_peak, s8["fp32_flop"] / flop_peak)
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text()).get({1: "ksmogn_stream_kernel", 3: "ksmogn_stream_kernel_o3"}.get(o_exec, "none"), {})
+        if t.get("workload") == workload and t.get("units_per_launch") == patches:
+            traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
+                       "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches, "source": t["source"]}
+    kernel = getattr(eng, "likelihood_kernel_name", None) or (
+        f"ksmogn_stream_kernel<uint16,{o_exec if o_exec <= 4 else 0},true,true> (fused render + offset-marginalised likelihood fwd+bwd"
+        + ("; O > 4 runs the tiled-offset form" if o_exec > 4 else "") + ")")
+    if bound[1] == "mufu":
+        achieved, peak, unit = w["mufu_ops"] * units_per_s / 1e12, mufu_peak / 1e12, "Top/s (MUFU)"
+        frac = achieved / peak
+    elif bound[1] == "fp32":
+        # flops with an FMA = 2 and an add / multiply = 1, against the FMA-loop peak
+        achieved, peak, unit = w["fp32_flop"] * units_per_s / 1e12, flop_peak / 1e12, "TFLOP/s"
+        frac = achieved / peak
+    else:
+        achieved, peak, unit = KSMOGN_HBM_BYTES_PER_UNIT * units_per_s / 1e9, hbm_peak, "GB/s"
+        frac = achieved / peak
+    return {
+        "kernel": kernel, "bound": bound[1], "achieved": achieved, "peak": peak, "unit": unit, "frac": frac,
+        "frac_definitions": {
+            "frac": "executed flops of the sweep (FMA = 2, add / mul = 1; SASS count) / kernel time / measured FMA-loop peak"
+                    if bound[1] == "fp32" else "executed ops of the binding unit / kernel time / its measured peak",
+            "frac_pipe_slots": "FP32-pipe lane operations (FMA, add, mul each one slot) / kernel time / measured lane-op peak: how busy the binding pipe is",
+            "frac_survey_8d": "SURVEY 8(d)'s per-unit estimate at the executed number of offset bins / kernel time / peak (estimate written before the kernel: > 1 possible, the kernel needs less work than it assumes)",
+        },
+        "frac_pipe_slots": units_per_s * max(t_pipe, t_mufu),
+        "frac_survey_8d": units_per_s * t8,
+        "traffic": traffic, "kernel_ms": k_s * 1e3, "kernel_share_of_step": k_s * 1e3 / ms_per_step,
+        "algorithmic_per_unit": dict(w, hbm_bytes=KSMOGN_HBM_BYTES_PER_UNIT, offset_bins_executed=o_exec),
+        "peaks_measured_here": {"mufu_Tops": mufu_peak / 1e12, "fp32_TFLOPs": flop_peak / 1e12, "fp32_lane_Tops": fma_peak_ops / 1e12,
+                                "hbm_GBs": hbm_peak, "hbm_source": hbm_src + " (MEASURED_PEAKS.json)"},
+        "hbm_view": {"achieved_GBs": KSMOGN_HBM_BYTES_PER_UNIT * units_per_s / 1e9, "peak_GBs": hbm_peak,
+                     "frac": KSMOGN_HBM_BYTES_PER_UNIT * units_per_s / 1e9 / hbm_peak},
+        # the whole step against the same roofline (time the likelihood's executed work would take at peak / step time)
+        "step_roofline_frac": (patches / (ms_per_step * 1e-3)) * (w["fp32_flop"] / flop_peak if bound[1] == "fp32" else bound[0]),
+        "step_frac_pipe_slots": (patches / (ms_per_step * 1e-3)) * max(t_pipe, t_mufu),
+    }
+
+
+def time_workload(workload, rank, world, local, args, peaks, hbm, offset_hist=0, keep_offset_bins=False, scaling="strong",
+                  with_e2e=True, trained_iters=0):
+    """Build the model for one workload and measure it; returns (result dict, model)."""
+    device = torch.device("cuda", local)
+    model, desc = build_model(workload, rank, world, device, offset_hist, keep_offset_bins, scaling)
+    eng = model.engine
+    timer = Timer(device, world)
+    units_per_step = eng.nb * eng.fb   # AOI-frames per rank per step
+    for _ in range(args.train_iters):
+        model.step()
+    for _ in range(max(args.warmup, 3)):
+        model.step()
+    timer.barrier()
+    with ClockSampler(local) as clocks:
+        timer.barrier()
+        t_wall = time.perf_counter()
+        ms_per_step = timer.steps(model.step, args.steps)
+        t_wall = time.perf_counter() - t_wall
+    value = units_per_step * world / (ms_per_step * 1e-3)
+    out = {"workload": desc, "ms_per_step": ms_per_step, "value": value, "unit": "AOI-frames/s",
+           "units_per_step_per_gpu": units_per_step, "launches_per_step": model.launches_per_step,
+           "wall_s_timed_region": t_wall, "clocks": clocks.summary()}
+    out["roofline"] = roofline_of(model, timer, peaks, hbm[0], hbm[1], ms_per_step, args.steps, world, workload)
+
+    if with_e2e:
+        # ---- end to end through the public API with host buffers: every step's pixels + target locations come from
+        # pinned host memory (what dataset.py:140-151 does), the loss is read back
+        host_pix = eng.store.pixels.cpu().pin_memory()
+        host_xy = eng.store.xy.cpu().pin_memory()
+        loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
+        timer.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
+        e1.record()
+        timer.barrier()
+        e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
+        out["e2e"] = {"value": units_per_step * world * args.steps / (e2e_ms.item() * 1e-3), "unit": "AOI-frames/s",
+                      "h2d_bytes_per_step": host_pix.numel() * host_pix.element_size() + host_xy.numel() * host_xy.element_size(),
+                      "d2h_bytes_per_step": 8}
+        del host_pix, host_xy
+
+    # ---- the same measurement after training: the timed steps above start from the initial variational parameters (the
+    # contract: W warm-up steps, then K timed ones).  As SVI proceeds the guides of absent spots relax to small
+    # concentrations and neighbouring units take different branches; reported beside the headline so that the initial
+    # point is not mistaken for the steady state of a long fit
+    if trained_iters > 0 and args.train_iters == 0:
+        for _ in range(trained_iters):
+            model.step()
+        timer.barrier()
+        t_ms = timer.steps(model.step, args.steps)
+        out["trained_state"] = {"extra_svi_iterations": trained_iters, "ms_per_step": t_ms,
+                                "value": units_per_step * world / (t_ms * 1e-3), "unit": "AOI-frames/s"}
+    out["final_loss"] = float(eng.loss.item())
+    return out, model
+
+
+def run_native(args):
+    from tapqir_b200 import _lib
 
     rank, world, local = dist_env()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    pg = None
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
     lib = _lib.load()  # raises if the sm_100a library is missing: no fallback
-
-    ds, nb, fb, desc = make_shard(args.workload, rank, device, args.offset_hist)
-    model = model_registry[WORKLOAD_MODEL.get(args.workload, "cosmos")](device=str(device), dtype="float")
-    model.data = ds
-    model.merge_offsets = not args.keep_offset_bins
-    model.init(lr=0.005, nbatch_size=nb, fbatch_size=fb, rank=rank, world_size=world, presharded=True)
-    eng = model.engine
-    units_per_step = eng.nb * eng.fb  # AOI-frames per rank per step
-    patches_per_step = units_per_step * eng.C   # units of the kernels: one per (AOI, frame, channel)
-    launches_per_step = model.launches_per_step
-
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize(device)
-
-    dbg('model ready')
-    for _ in range(args.train_iters):
-        model.step()
-    for _ in range(max(args.warmup, 3)):
-        model.step()
-    barrier()
-    dbg('warm-up done')
-
-    # ---- device-resident timing ("value") ----------------------------------------------------------
-    evs = []
-    with ClockSampler(local) as clocks:
-        barrier()
-        t_wall = time.perf_counter()
-        for _ in range(args.steps):
-            flush.fill_(1)  # evict the 126 MB L2 (untimed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            model.step()
-            e1.record()
-            evs.append((e0, e1))
-        barrier()
-        t_wall = time.perf_counter() - t_wall
-    dbg('timed region done')
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    ms_per_step = total_ms.item() / args.steps
-    value = units_per_step * world / (ms_per_step * 1e-3)
-
-    # ---- dominant kernel alone (roofline) -------------------------------------------------------------
-    k_ms = []
-    for _ in range(max(3, min(args.steps, 10))):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        model.step(time_likelihood=(e0, e1))
-        torch.cuda.synchronize(device)
-        k_ms.append(e0.elapsed_time(e1))
-    k_ms_avg = sum(k_ms) / len(k_ms)
-    dbg('kernel timing done')
     peaks = measure_peaks(lib, _lib, device)
     measured = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-    hbm_peak = measured.get("hbm_gbs", 6650.0)
-    hbm_src = "measured" if "hbm_gbs" in measured else "fallback"
-    o_exec = int(eng.store.offset_samples.numel())   # distinct offset bins the kernels loop over
-    MUFU_PER_UNIT, FP32_OPS_PER_UNIT = algorithmic_work(o_exec)
-    FLOP_PER_UNIT = 2 * FP32_OPS_PER_UNIT                # FMA = 2 flops, like the measured peak
-    mufu_ach = MUFU_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3)
-    flop_ach = FLOP_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3)
-    hbm_ach = KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step / (k_ms_avg * 1e-3) / 1e9
-    t_mufu, t_fp32 = MUFU_PER_UNIT / peaks["mufu"], FLOP_PER_UNIT / (2 * peaks["fma"])
-    t_hbm = KSMOGN_HBM_BYTES_PER_UNIT / (hbm_peak * 1e9)
-    bound = max((t_mufu, "mufu"), (t_fp32, "fp32"), (t_hbm, "hbm"))
-    roof_units_per_s = 1.0 / bound[0]
-    traffic = None
-    tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists():
-        t = json.loads(tj.read_text()).get({1: "ksmogn_stream_kernel", 3: "ksmogn_stream_kernel_o3"}.get(o_exec, "none"), {})
-        if t.get("workload") == args.workload and t.get("units_per_launch") == patches_per_step:
-            traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
-                       "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches_per_step, "source": t["source"]}
-    roofline = {
-        "kernel": f"ksmogn_stream_kernel<uint16,{o_exec if o_exec <= 4 else 0},true,true> (fused render + offset-marginalised "
-                  f"likelihood fwd+bwd" + ("; O > 4 runs the two-pass form, the work counts are the cached-offset form's" if o_exec > 4 else "") + ")",
-        "bound": bound[1],
-        "achieved": (mufu_ach / 1e12) if bound[1] == "mufu" else (flop_ach / 1e12 if bound[1] == "fp32" else hbm_ach),
-        "peak": (peaks["mufu"] / 1e12) if bound[1] == "mufu" else (2 * peaks["fma"] / 1e12 if bound[1] == "fp32" else hbm_peak),
-        "unit": "Top/s (MUFU)" if bound[1] == "mufu" else ("TFLOP/s" if bound[1] == "fp32" else "GB/s"),
-        "frac": (patches_per_step / (k_ms_avg * 1e-3)) / roof_units_per_s,
-        "traffic": traffic,
-        "kernel_ms": k_ms_avg,
-        "kernel_share_of_step": k_ms_avg / ms_per_step,
-        "algorithmic_per_unit": {"mufu_ops": MUFU_PER_UNIT, "fp32_flop": FLOP_PER_UNIT, "hbm_bytes": KSMOGN_HBM_BYTES_PER_UNIT,
-                                 "offset_bins_executed": o_exec,
-                                 "survey_8d_estimate": {"mufu_ops": 980 * o_exec + 3276, "fp32_flop": 8232 * o_exec + 63220}},
-        "peaks_measured_here": {"mufu_Tops": peaks["mufu"] / 1e12, "fp32_TFLOPs": 2 * peaks["fma"] / 1e12,
-                                "hbm_GBs": hbm_peak, "hbm_source": hbm_src + " (MEASURED_PEAKS.json)"},
-        "hbm_view": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak},
-        "step_roofline_frac": value * eng.C / world / roof_units_per_s,
-    }
+    hbm = (measured.get("hbm_gbs", 6650.0), "measured" if "hbm_gbs" in measured else "fallback")
 
-    # ---- end to end through the public API with host buffers --------------------------------------------
-    host_pix = eng.store.pixels.cpu().pin_memory()
-    host_xy = eng.store.xy.cpu().pin_memory()
-    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
-    dbg('e2e buffers ready')
-    for _ in range(2):
-        model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
-    barrier()
-    dbg('e2e warm-up done')
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        # this step's inputs come from pinned host memory (uploaded during the previous step's compute)
-        model.step_from_host(host_pix, host_xy, loss_host, prefetch_next=(host_pix, host_xy))
-    e1.record()
-    barrier()
-    dbg('e2e done')
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    main, model = time_workload(args.workload, rank, world, local, args, peaks, hbm, args.offset_hist, args.keep_offset_bins,
+                                args.scaling, with_e2e=True, trained_iters=args.trained_iters)
+    launches = model.launches_per_step * args.steps
     if world > 1:
-        torch.distributed.all_reduce(e2e_ms, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = units_per_step * world * args.steps / (e2e_ms.item() * 1e-3)
-    e2e = {"value": e2e_value, "unit": "AOI-frames/s",
-           "h2d_bytes_per_step": host_pix.numel() * host_pix.element_size() + host_xy.numel() * host_xy.element_size(),
-           "d2h_bytes_per_step": 8}
+        timer = Timer(device, world)
+        timer.barrier()
+        model.engine.close()
+    del model
+    torch.cuda.empty_cache()
 
-    # ---- the same measurement after training ----------------------------------------------------------------
-    # The timed steps above start from the initial variational parameters (the contract: W warm-up steps, then K timed
-    # ones).  As SVI proceeds the guides of absent spots relax to small concentrations, a few percent of the guide sites
-    # leave the fp32 forms and neighbouring units take different branches; the step slows down.  Reported beside the
-    # headline so that it is not mistaken for the steady state of a long fit.
-    trained = None
-    if args.trained_iters > 0 and args.train_iters == 0:
-        for _ in range(args.trained_iters):
-            model.step()
-        barrier()
-        tev = []
-        for _ in range(args.steps):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            model.step()
-            e1.record()
-            tev.append((e0, e1))
-        barrier()
-        t_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in tev)], dtype=torch.float64, device=device)
-        if world > 1:
-            torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
-        trained = {"extra_svi_iterations": args.trained_iters,
-                   "ms_per_step": t_ms.item() / args.steps, "value": units_per_step * world / (t_ms.item() / args.steps * 1e-3),
-                   "unit": "AOI-frames/s"}
-    dbg('trained-state timing done')
+    subs = None
+    if world == 1 and not args.no_subs and args.workload == "c3" and not args.offset_hist and not args.keep_offset_bins:
+        subs = {}
+        for name, (wl, oh, keep) in SUBS.items():
+            res, m = time_workload(wl, 0, 1, local, args, peaks, hbm, oh, keep, "strong", with_e2e=False,
+                                   trained_iters=args.trained_iters if name == "c2" else 0)
+            keepk = ("workload", "ms_per_step", "value", "unit", "units_per_step_per_gpu", "trained_state")
+            subs[name] = {k: res[k] for k in keepk if k in res}
+            r = res["roofline"]
+            subs[name]["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "frac_pipe_slots",
+                                                        "frac_survey_8d", "kernel_ms", "kernel_share_of_step", "step_roofline_frac")}
+            m.engine.close()
+            del m
+            torch.cuda.empty_cache()
 
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_cpu_sample(args, budget_s=20.0)
+        cpu_baseline = run_cpu_sample(budget_s=20.0)
 
     if rank == 0:
         line = {
-            "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value, "unit": "AOI-frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "model": model.name, "channels": eng.C, "nb_per_gpu": eng.nb, "fb": eng.fb, "offset_bins": args.offset_hist or O_BINS,
-                       "offset_bins_distinct": o_exec, "train_iters_before_timing": args.train_iters,
-                       "parallelism": f"aoi-shard x{world}", "l2": "flushed (256 MiB write) before every timed step",
-                       "local_terms_dtype": "f32 (double fallback outside the fp32 regimes)", "likelihood_dtype": "f32"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "trained_state": trained,
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
-            "wall_s_timed_region": t_wall, "final_loss": float(eng.loss.item()),
+            "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": main["value"], "unit": "AOI-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args.workload, world, args.scaling, args.offset_hist, args.keep_offset_bins, args.train_iters),
+            "roofline": main["roofline"], "cpu_baseline": cpu_baseline, "e2e": main["e2e"],
+            "trained_state": main.get("trained_state"), "sub_results": subs,
+            "gpu_launches": launches, "clocks": main["clocks"],
+            "wall_s_timed_region": main["wall_s_timed_region"], "final_loss": main["final_loss"],
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        # Tear-down: the captured CUDA graphs hold NCCL work; drop them, drain the device, and leave
-        # without destroy_process_group() (it can block behind graph-captured collectives).
-        barrier()
-        model.engine.release_graph()
+        # orderly tear-down (the engine's graph and peer buffers were released above), bounded by a watchdog: a process
+        # group that refuses to shut down must not keep the finished bench alive
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        torch.distributed.barrier()
         torch.cuda.synchronize(device)
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        torch.distributed.destroy_process_group()
 
 
-def run_cpu_sample(args, budget_s=20.0):
-    """The oracle (CPU, fp64, all host threads) on the reference-default 10 x 512 minibatch of the
-    same kind of data; returns the cpu_baseline object."""
+def cpu_problem():
+    """The bounded CPU sample shared by `cpu_baseline` and `--impl reference`: the oracle (fp64, all host threads) on
+    reference-default minibatches (10 AOIs x 512 frames, main.py:1428-1431) of a 100-AOI x 1000-frame slice of the
+    simulated workload -- dense Adam over the slice's 1.8 M parameters included, as in the reference."""
     from oracle import cosmos_oracle as O
     from tapqir_b200.utils.simulate import simulate
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_aoi, n_frames = 20, 600
-    nb, fb = 10, 512
+    n_aoi, n_frames, nb, fb = 100, 1000, 10, 512
     ds = simulate(n_aoi, n_frames, seed=0)
     data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
     svi = O.OracleSVI(data, nbatch_size=nb, fbatch_size=fb, seed=0)
+    what = (f"fp64 torch oracle (port of the reference step; Pyro not installable), minibatches of {nb} AOIs x {fb} frames "
+            f"(reference default) drawn from a {n_aoi}-AOI x {n_frames}-frame slice of the simulated workload (O=3), "
+            f"dense Adam over the slice's parameters")
+    return svi, nb * fb, what
+
+
+def run_cpu_sample(budget_s=20.0):
+    svi, units, what = cpu_problem()
     svi.step()
     times, t_start = [], time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 40):
@@ -387,27 +473,18 @@ def run_cpu_sample(args, budget_s=20.0):
         svi.step()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return {"value": nb * fb / med, "unit": "AOI-frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} steps of the fp64 torch oracle, minibatch {nb} AOIs x {fb} frames drawn from a "
-                      f"simulated {n_aoi} x {n_frames} dataset (O=3), median step {med * 1e3:.0f} ms"}
+    return {"value": units / med, "unit": "AOI-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} steps: {what}; median step {med * 1e3:.0f} ms"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation cannot be imported (pyro-ppl, funsor,
-    pykeops are not installable here), so this times its restatement in oracle/ on the host cores."""
+    """Reference arm: the reference's own CPU implementation cannot be imported (pyro-ppl, funsor, pykeops are not
+    installable here), so this times its restatement in oracle/ on the host cores, on the bounded sample of the SAME
+    workload / config as the native arm (rank 0 only)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    n_aoi, n_frames, _, _, desc = WORKLOADS[args.workload]
-    from oracle import cosmos_oracle as O
-    from tapqir_b200.utils.simulate import simulate
-
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    nb, fb = 10, 512
-    ds = simulate(20, 600, seed=0)
-    data = O.OracleData(ds.images, ds.xy, ds.is_ontarget, ds.mask, ds.offset.samples, ds.offset.weights)
-    svi = O.OracleSVI(data, nbatch_size=nb, fbatch_size=fb, seed=0)
+    svi, units, what = cpu_problem()
     for _ in range(max(args.warmup, 1)):
         svi.step()
     steps = min(args.steps, 30)
@@ -415,14 +492,14 @@ def run_reference(args):
     for _ in range(steps):
         svi.step()
     dt = (time.perf_counter() - t0) / steps
-    value = nb * fb / dt
-    sample = (f"fp64 torch oracle (port of the reference step, Pyro not installable), {steps} steps of the "
-              f"reference-default minibatch {nb} AOIs x {fb} frames from a simulated 20 x 600 dataset, O=3")
+    value = units / dt
+    sample = f"{steps} steps: {what}"
     print(json.dumps({
         "impl": "reference", "metric": "cosmos SVI AOI-frames/sec (ELBO fwd+bwd+Adam)", "value": value,
         "unit": "AOI-frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": desc, "sample": sample},
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": config_of(args.workload, args.gpus, args.scaling, args.offset_hist, args.keep_offset_bins, args.train_iters),
         "cpu_baseline": {"value": value, "unit": "AOI-frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "AOI-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -435,12 +512,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the workload's AOIs are split over the ranks; weak: every rank holds the whole workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subs", action="store_true", help="skip the sub_results (other single-GPU configurations) of the N=1 line")
     ap.add_argument("--train-iters", type=int, default=0,
                     help="untimed SVI iterations before the warm-up: times the TRAINED state (absent spots' guides relax to "
                          "small concentrations, a few percent of the sites leave the fp32 forms) instead of the initial point")
-    ap.add_argument("--trained-iters", type=int, default=2000,
+    ap.add_argument("--trained-iters", type=int, default=1000,
                     help="after the timed steps, run this many more SVI iterations and time K steps again (reported as "
                          "`trained_state`); 0 to skip")
     ap.add_argument("--offset-hist", type=int, default=0, metavar="O",

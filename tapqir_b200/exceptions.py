@@ -5,7 +5,8 @@ names, constructor arguments, attributes and message texts are part of the contr
 repository's own (no CPU fallback exists, a missing sm_100a library is an error).
 """
 
-__all__ = ["TapqirException", "TapqirFileNotFoundError", "CudaOutOfMemoryError", "NativeLibraryError"]
+__all__ = ["TapqirException", "TapqirFileNotFoundError", "CudaOutOfMemoryError", "NativeLibraryError",
+           "NonFiniteParameterError", "PeerTimeoutError"]
 
 
 class TapqirException(Exception):
@@ -39,3 +40,20 @@ class CudaOutOfMemoryError(TapqirException):
 
 class NativeLibraryError(TapqirException):
     """libtapqir_b200.so (sm_100a) is missing or could not be loaded."""
+
+
+class NonFiniteParameterError(ValueError):
+    """NaN / Inf found in a variational parameter at checkpoint time.  The reference raises a plain ``ValueError`` there
+    (models/model.py:246-250) and ``run`` answers it by restoring the last checkpoint with a new seed (:220-232); this
+    subclass keeps callers that catch ``ValueError`` working while ``Model.run`` catches ONLY it -- an argument error of
+    the C ABI is a ``ValueError`` too and must not be mistaken for a divergence."""
+
+
+class PeerTimeoutError(TapqirException):
+    """A rank stopped pushing its accumulators over NVLink peer memory (csrc/p2p_allreduce.cu gave up waiting): the sums
+    of that step -- and every parameter update since -- are garbage."""
+
+    def __init__(self, seq):
+        TapqirException.__init__(self, f"peer-memory all-reduce timed out at call #{seq}: a rank died or stalled; "
+                                       "parameters since the last checkpoint are not to be trusted")
+        self.seq = seq

@@ -99,14 +99,20 @@ class cosmos(Model):
             ("size", constraints.greater_than(2.0)),
         ])
 
-    def _shard(self):
-        """Contiguous AOI block of this rank (SURVEY.md 8e)."""
-        Nt, w, r = self.data.Nt, self.world_size, self.rank
+    def _shard_sizes(self):
+        """AOIs per rank: balanced contiguous blocks, the first ``Nt % world_size`` ranks hold one more."""
+        Nt, w = self.data.Nt, self.world_size
         if getattr(self, "presharded", False):
-            return slice(0, Nt)
-        per = (Nt + w - 1) // w
-        lo, hi = min(r * per, Nt), min((r + 1) * per, Nt)
-        return slice(lo, hi)
+            return [Nt] * w
+        return [Nt // w + (1 if r < Nt % w else 0) for r in range(w)]
+
+    def _shard(self):
+        """Contiguous AOI block of this rank."""
+        if getattr(self, "presharded", False):
+            return slice(0, self.data.Nt)
+        sizes = self._shard_sizes()
+        lo = sum(sizes[:self.rank])
+        return slice(lo, lo + sizes[self.rank])
 
     def build_engine(self, seed=0):
         from tapqir_b200.models.engine import CosmosEngine
@@ -114,6 +120,9 @@ class cosmos(Model):
         if self.device.type != "cuda":
             raise RuntimeError("tapqir_b200 has no CPU execution path: construct the model with device='cuda'")
         sl = self._shard()
+        if sl.stop - sl.start < 1:
+            raise ValueError(f"{self.data.Nt} AOIs cannot be sharded over {self.world_size} ranks: rank {self.rank} would "
+                             "hold none (use fewer GPUs)")
         # identical offset bins are merged on upload unless model.merge_offsets is set to False (utils/dataset.py)
         store = self.data.device_store(self.device, self.dtype, sl, merge_offsets=getattr(self, "merge_offsets", True))
         self.engine = CosmosEngine(
@@ -122,7 +131,7 @@ class cosmos(Model):
             seed=seed, ref_dtype=self.ref_dtype,
             Nt_total=self.data.Nt * (self.world_size if getattr(self, "presharded", False) else 1),
             aoi_offset=self.rank * self.data.Nt if getattr(self, "presharded", False) else sl.start, rank=self.rank,
-            world_size=self.world_size, process_group=self.process_group)
+            world_size=self.world_size, process_group=self.process_group, shard_sizes=self._shard_sizes())
         self.nbatch_size, self.fbatch_size = self.engine.nb, self.engine.fb
         return self.engine
 

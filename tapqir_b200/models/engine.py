@@ -25,7 +25,8 @@ from tapqir_b200.models import layout as L
 class CosmosEngine:
     def __init__(self, store, Nt_local, F, C, P, priors, dtype=torch.float32, lr=0.005, betas=(0.9, 0.999),
                  adam_eps=1e-8, nbatch_size=None, fbatch_size=None, seed=0, ref_dtype=torch.float64,
-                 Nt_total=None, aoi_offset=0, rank=0, world_size=1, process_group=None, use_graph=True):
+                 Nt_total=None, aoi_offset=0, rank=0, world_size=1, process_group=None, use_graph=True,
+                 shard_sizes=None):
         self.lib = _lib.load()
         self.store = store
         self.device = store.pixels.device
@@ -36,6 +37,11 @@ class CosmosEngine:
         self.Nt, self.F, self.C, self.P = int(Nt_local), int(F), int(C), int(P)
         self.Nt_total = int(Nt_total if Nt_total is not None else Nt_local)
         self.aoi_offset, self.rank, self.world_size, self.pg = int(aoi_offset), int(rank), int(world_size), process_group
+        # AOIs held by every rank (None: equal shards).  Unequal shards are fine: see set_batch
+        self.shard_sizes = [int(n) for n in shard_sizes] if shard_sizes is not None else [self.Nt] * self.world_size
+        if len(self.shard_sizes) != self.world_size or self.shard_sizes[self.rank] != self.Nt or min(self.shard_sizes) < 1:
+            raise ValueError(f"shard sizes {self.shard_sizes} do not describe {self.world_size} non-empty shards with "
+                             f"{self.Nt} AOIs on rank {self.rank}")
         self.lr, self.betas, self.adam_eps = float(lr), (float(betas[0]), float(betas[1])), float(adam_eps)
         self.seed = int(seed)
         self.mc = L.ModelConst.make(priors, P, ref_dtype)
@@ -65,11 +71,13 @@ class CosmosEngine:
         # IPC set-up is not possible (then NCCL; 120-160 us per step at 8 GPUs against ~10 us)
         self.p2p = None
         if self.world_size > 1 and os.environ.get("TQ_ALLREDUCE", "p2p") == "p2p":
-            try:
-                from tapqir_b200.models.p2p import P2PAllReduce
+            from tapqir_b200.models.p2p import P2PAllReduce, PeerMemoryUnavailable
 
+            try:
+                # collective: either EVERY rank gets the peer-memory path or every rank raises (the ranks agree on the
+                # outcome with an all-reduce inside), so the fallback below is taken by all ranks together
                 self.p2p = P2PAllReduce(dev, self.rank, self.world_size, self.pg)
-            except Exception as err:   # no peer access / IPC (e.g. containers without it): NCCL does the same sum
+            except PeerMemoryUnavailable as err:   # no peer access / IPC (e.g. containers without it): NCCL does the same sum
                 import logging
 
                 logging.getLogger(__name__).warning(f"peer-memory all-reduce unavailable ({err}); using NCCL")
@@ -100,9 +108,15 @@ class CosmosEngine:
         # scratch of tq_cosmos_local_post: per-block partial sums, and its (self-resetting) completion tickets
         self.block_partial = e(max(self.lib.tq_local_post_scratch(self.nb, self.fb, self.C), 1), dt=torch.float64)
         self.tickets = torch.zeros(max(self.lib.tq_local_post_tickets(self.nb, self.fb, self.C), 1), dtype=torch.float64, device=dev)
-        # scale factors of the subsampled plates (cosmos.py:194-208): all ranks together draw
-        # nb * world_size of Nt_total AOIs (stratified by shard)
-        self.sN = self.Nt_total / (self.nb * self.world_size)
+        # scale factors of the subsampled plates (cosmos.py:194-208).  The AOI minibatch is stratified by shard: rank r
+        # draws nb_r = min(nbatch_size, Nt_r) of its Nt_r AOIs, each with inclusion probability nb_r / Nt_r, so its terms
+        # carry sN = Nt_r / nb_r.  The cross-rank sum and the global reverse mode use ONE reference scale
+        # sN_ref = Nt_total / sum_r nb_r; a rank whose own scale differs (unequal shards) weights its accumulators by
+        # sN / sN_ref before the sum.  Equal shards: sN == sN_ref, weight 1.
+        nb_all = [min(int(nbatch_size), n) for n in self.shard_sizes]
+        self.sN = self.Nt / self.nb
+        self.sN_ref = self.Nt_total / sum(nb_all)
+        self.acc_weight = self.sN / self.sN_ref
         self.sF = self.F / self.fb
 
     def _view(self, ndx, fdx):
@@ -214,6 +228,8 @@ class CosmosEngine:
             # the all-reduce of the (C, 18) accumulators (multi-GPU), finishing the global reverse pass (a few FMAs per
             # parameter) and the global Adam run on the side stream, beside the dense Adam over the AOI-local buffer,
             # which depends on none of them: the collective's latency hides under the local update
+            if abs(self.acc_weight - 1.0) > 1e-15:
+                self.acc_all.mul_(self.acc_weight)  # unequal AOI shards (set_batch)
             if self.p2p is not None:
                 self.p2p.push(self.acc_all, st)     # straight into every peer's buffer, as early as the values exist
             self._ev_fork.record(main)
@@ -225,7 +241,7 @@ class CosmosEngine:
                 elif self.world_size > 1:
                     torch.distributed.all_reduce(self.acc_all, group=self.pg)
                 _lib.check(lib.tq_cosmos_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc),
-                                                        self.sN, self.sF, p(self.ggrads), p(self.loss), sst),
+                                                        self.sN_ref, self.sF, p(self.ggrads), p(self.loss), sst),
                            "tq_cosmos_globals_finish")
                 if update:
                     b1, b2 = self.betas
@@ -292,6 +308,15 @@ class CosmosEngine:
             z_out.append(z_probs)
             th_out.append(theta_probs)
         return torch.cat(z_out, 0), torch.cat(th_out, 1)
+
+    def close(self):
+        """Release what the caching allocator does not own: the captured graph and the peer-memory buffer with its IPC
+        mappings (an engine that is replaced, e.g. by the NaN restart of Model.run, must not leak them)."""
+        self._graph, self._eager_default_steps = None, 0
+        if self.p2p is not None:
+            torch.cuda.synchronize(self.device)
+            self.p2p.close()
+            self.p2p = None
 
     def release_graph(self):
         """Drop the captured CUDA graph (it keeps references to NCCL work when world_size > 1)."""

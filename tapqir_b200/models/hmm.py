@@ -51,6 +51,9 @@ class hmm(cosmos):
         if self.device.type != "cuda":
             raise RuntimeError("tapqir_b200 has no CPU execution path: construct the model with device='cuda'")
         sl = self._shard()
+        if sl.stop - sl.start < 1:
+            raise ValueError(f"{self.data.Nt} AOIs cannot be sharded over {self.world_size} ranks: rank {self.rank} would "
+                             "hold none (use fewer GPUs)")
         store = self.data.device_store(self.device, self.dtype, sl, merge_offsets=getattr(self, "merge_offsets", True))
         presharded = getattr(self, "presharded", False)
         self.engine = HmmEngine(
@@ -58,7 +61,7 @@ class hmm(cosmos):
             betas=self.optim_args["betas"], nbatch_size=self.nbatch_size, seed=seed, ref_dtype=self.ref_dtype,
             Nt_total=self.data.Nt * (self.world_size if presharded else 1),
             aoi_offset=self.rank * self.data.Nt if presharded else sl.start, rank=self.rank, world_size=self.world_size,
-            process_group=self.process_group)
+            process_group=self.process_group, shard_sizes=self._shard_sizes())
         self.nbatch_size, self.fbatch_size = self.engine.nb, self.engine.fb
         return self.engine
 

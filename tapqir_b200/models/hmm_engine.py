@@ -108,6 +108,8 @@ class HmmEngine(CosmosEngine):
                                            p(self.chain_a), p(self.chain_v), self.sN, p(self.lgrads), p(self.hpartial),
                                            p(self.hacc), st),
                        "tq_hmm_backward")
+            if abs(self.acc_weight - 1.0) > 1e-15:
+                self.acc_all.mul_(self.acc_weight)  # unequal AOI shards (CosmosEngine.set_batch)
             if self.p2p is not None:
                 self.p2p.push(self.acc_all, st)
             self._ev_fork.record(main)
@@ -119,7 +121,7 @@ class HmmEngine(CosmosEngine):
                 elif self.world_size > 1:
                     torch.distributed.all_reduce(self.acc_all, group=self.pg)
                 _lib.check(lib.tq_hmm_globals_finish(code, self.C, mc, p(self.gstate), p(self.gprep), p(self.acc), p(self.hacc),
-                                                     self.sN, p(self.ggrads), p(self.loss), sst), "tq_hmm_globals_finish")
+                                                     self.sN_ref, p(self.ggrads), p(self.loss), sst), "tq_hmm_globals_finish")
                 if update:
                     b1, b2 = self.betas
                     _lib.check(lib.tq_adam_dense(_lib.TQ_F64, self.gl.numel, p(self.gparams), p(self.ggrads), p(self.gm),

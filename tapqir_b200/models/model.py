@@ -21,7 +21,8 @@ from typing import Union
 import torch
 
 from tapqir_b200 import __version__ as tapqir_version
-from tapqir_b200.exceptions import CudaOutOfMemoryError, TapqirFileNotFoundError
+from tapqir_b200.exceptions import (CudaOutOfMemoryError, NonFiniteParameterError, PeerTimeoutError,
+                                    TapqirFileNotFoundError)
 from tapqir_b200.utils.dataset import load
 
 logger = logging.getLogger(__name__)
@@ -59,6 +60,14 @@ class Model:
         self.iter = 0
         self.converged = False
         self._loss_dev = None
+        # defaults of everything init() sets, so that the reference's `tapqir stats` flow (main.py:566: load();
+        # load_checkpoint(param_only=True); compute_stats()) works on a model that was never init()-ed
+        self.lr = 0.005
+        self.optim_args = {"lr": self.lr, "betas": [0.9, 0.999]}
+        self.rank, self.world_size, self.process_group = 0, 1, None
+        self.presharded = False
+        self.seed = 0
+        self._rolling = defaultdict(lambda: deque([], maxlen=100))
         self.to(device, dtype)
 
     def to(self, device: str, dtype: str = "double") -> None:
@@ -113,6 +122,8 @@ class Model:
         self.nbatch_size = min(nbatch_size, self.data.Nt)
         self.fbatch_size = min(fbatch_size, self.data.F)
         self.seed = seed
+        if self.engine is not None:
+            self.engine.close()   # peer-memory buffers / IPC mappings of the engine being replaced (restart path)
         self.build_engine(seed)
         try:
             self.load_checkpoint()
@@ -129,7 +140,26 @@ class Model:
 
     @property
     def iter_loss(self):
-        return float(self._loss_dev.item()) if self._loss_dev is not None else float("nan")
+        """-ELBO of the latest step as the reference reports it (model.py:212, 285-298), including the constant Pyro's
+        enumeration contributes for masked AOIs (4 configurations x ln 6 states per masked unit, times the plate
+        scales: the sites' log-probabilities are zeroed but still summed over; tests/test_oracle.py).  Synchronises;
+        with ``world_size > 1`` every rank must read it (one small all-reduce)."""
+        if self._loss_dev is None:
+            return float("nan")
+        return float(self._loss_dev.item()) + self.masked_loss_constant()
+
+    def masked_loss_constant(self):
+        import math
+
+        eng = self.engine
+        masked = (eng.store.mask == 0)
+        if eng.ndx is not None:
+            masked = masked[eng.ndx.long()]
+        count = masked.sum().to(torch.float64)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(count, group=self.process_group)
+        per_unit = getattr(self, "masked_unit_constant", 4 * math.log(6))
+        return float(count.item()) * eng.fb * eng.C * per_unit * eng.sN * eng.sF
 
     def run(self, num_iter: int = 0, progress_bar=None) -> None:
         """
@@ -164,9 +194,13 @@ class Model:
                             logger.info(f"Iteration #{self.iter} model converged.")
                             break
                     self.iter += 1
-                except ValueError:
-                    # NaN/Inf found at checkpoint time: go back to the last checkpoint with a new seed
-                    new_seed = random.randint(0, 100)
+                except NonFiniteParameterError:
+                    # NaN/Inf found at checkpoint time (on ANY rank: the scan is all-reduced, so every rank is here): go
+                    # back to the last checkpoint with a new seed -- rank 0 draws it, everyone uses it (model.py:220-232)
+                    seed_box = [random.randint(0, 100)]
+                    if self.world_size > 1:
+                        torch.distributed.broadcast_object_list(seed_box, src=0, group=self.process_group)
+                    new_seed = seed_box[0]
                     self.init(lr=self.lr, nbatch_size=self.nbatch_size, fbatch_size=self.fbatch_size, rank=self.rank,
                               world_size=self.world_size, process_group=self.process_group, seed=new_seed,
                               presharded=self.presharded)
@@ -177,6 +211,8 @@ class Model:
                     raise
             else:
                 logger.warning(f"Iteration #{self.iter} model has not converged.")
+            if self.world_size > 1 and self.run_path is not None:
+                self.consolidate_checkpoint()   # reference-layout file: single-GPU resume, `tapqir stats`
         finally:
             if writer is not None:
                 writer.close()
@@ -202,11 +238,18 @@ class Model:
         ``torch.save`` of {iter, params, optimizer, rolling, convergence_status}, tensorboard scalars.
         """
         eng = self.engine
-        flat_ok = torch.isfinite(eng.lparams).all() & torch.isfinite(eng.gparams).all()
+        if eng.p2p is not None:
+            seq = eng.p2p.timed_out()
+            if seq:
+                raise PeerTimeoutError(seq)
+        flat_ok = (torch.isfinite(eng.lparams).all() & torch.isfinite(eng.gparams).all()).to(torch.int32)
+        if self.world_size > 1:   # every rank takes the restart path together, or none does
+            torch.distributed.all_reduce(flat_ok, op=torch.distributed.ReduceOp.MIN, group=self.process_group)
         if not bool(flat_ok):
             for k, v in eng.named_unconstrained().items():
                 if not torch.isfinite(v).all():
-                    raise ValueError("Iteration #{}. Detected NaN values in {}".format(self.iter, k))
+                    raise NonFiniteParameterError("Iteration #{}. Detected NaN values in {}".format(self.iter, k))
+            raise NonFiniteParameterError("Iteration #{}. Detected NaN values on another rank".format(self.iter))
         loss = self.iter_loss
         for name in self.conv_params:
             if name == "-ELBO":
@@ -265,20 +308,73 @@ class Model:
                                   "exp_avg_sq": second[k].detach().clone()}},
                     "param_groups": [dict(group)]} for k in moments}
 
+    # ---- AOI-sharded checkpoints <-> the reference's single file ------------------------------------------------
+    def _aoi_axis(self, name, ndim):
+        """Axis of the AOI dimension of parameter ``name`` in the reference's shapes (None: a global parameter)."""
+        if self.engine is not None and name in self.engine.gl.shapes:
+            return None
+        if name in ("background_mean_loc", "background_std_loc", "b_loc", "b_beta", "z_trans"):
+            return 0
+        if ndim == 5:      # hmm m_probs (1+S, K, Nt, F, Q)
+            return 2
+        return 1 if ndim == 4 else None
+
+    def consolidate_checkpoint(self):
+        """
+        Multi-GPU fits checkpoint per rank (``<name>_model.tpqr.rank<r>``: every rank writes its AOI block in parallel,
+        nothing crosses NVLink).  This merges the latest rank files into ONE file in the reference's layout
+        (model.py:273-282: the AOI axes concatenated in rank order), so that a fit made on N GPUs resumes on one GPU,
+        on a different number of GPUs, or feeds ``tapqir stats``.  Collective: every rank calls it (``run`` does, when it
+        ends); rank 0 writes.
+        """
+        if self.world_size == 1 or self.run_path is None:
+            return
+        torch.distributed.barrier(group=self.process_group)
+        if self.rank == 0:
+            parts = [torch.load(self.run_path / f"{self.name}_model.tpqr.rank{r}", map_location="cpu", weights_only=False)
+                     for r in range(self.world_size)]
+            if len({p["iter"] for p in parts}) != 1:
+                raise RuntimeError(f"rank checkpoints of different iterations: {[p['iter'] for p in parts]}")
+
+            def cat(name, tensors):
+                axis = self._aoi_axis(name, tensors[0].dim())
+                return tensors[0] if axis is None else torch.cat(tensors, axis)
+
+            merged = parts[0]
+            merged["params"]["params"] = {k: cat(k, [p["params"]["params"][k] for p in parts]) for k in merged["params"]["params"]}
+            for k, entry in merged["optimizer"].items():
+                for key in ("exp_avg", "exp_avg_sq"):
+                    entry["state"][0][key] = cat(k, [p["optimizer"][k]["state"][0][key] for p in parts])
+            torch.save(merged, self.run_path / f"{self.name}_model.tpqr")
+        torch.distributed.barrier(group=self.process_group)
+
     def load_checkpoint(self, path: Union[str, Path] = None, param_only: bool = False, warnings: bool = False):
-        """Reference: model.py:325-357."""
+        """Reference: model.py:325-357.  With ``world_size > 1`` a rank reads its own ``.rank<r>`` file if there is one,
+        else its AOI block of the single reference-layout file (:meth:`consolidate_checkpoint`, or a single-GPU fit)."""
         path = Path(path) if path else self.run_path
         if path is None:
             raise TapqirFileNotFoundError("model", f"{self.name}_model.tpqr")
-        suffix = "" if getattr(self, "world_size", 1) == 1 else f".rank{self.rank}"
-        model_path = path / f"{self.name}_model.tpqr{suffix}"
+        model_path = path / f"{self.name}_model.tpqr"
+        shard_path = path / f"{self.name}_model.tpqr.rank{self.rank}"
+        use_shard = self.world_size > 1 and shard_path.exists()
         try:
-            checkpoint = torch.load(model_path, map_location=self.device, weights_only=False)
+            checkpoint = torch.load(shard_path if use_shard else model_path, map_location=self.device, weights_only=False)
         except FileNotFoundError:
             raise TapqirFileNotFoundError("model", model_path)
         if self.engine is None:
-            self.build_engine(getattr(self, "seed", 0))
+            self.build_engine(self.seed)
         eng = self.engine
+        if self.world_size > 1 and not use_shard:
+            lo = self.rank * eng.Nt if self.presharded else self._shard().start
+
+            def block(name, t):
+                axis = self._aoi_axis(name, t.dim())
+                return t if axis is None else t.narrow(axis, lo, eng.Nt)
+
+            checkpoint["params"]["params"] = {k: block(k, v) for k, v in checkpoint["params"]["params"].items()}
+            for k, entry in checkpoint["optimizer"].items():
+                for key in ("exp_avg", "exp_avg_sq"):
+                    entry["state"][0][key] = block(k, entry["state"][0][key])
         eng.load_unconstrained(checkpoint["params"]["params"])
         if not param_only:
             self.converged = checkpoint["convergence_status"]
@@ -300,8 +396,13 @@ class Model:
             logger.warning(f"Model at {path} has not been fully trained")
 
     def compute_stats(self, CI: float = 0.95, save_matlab: bool = False):
-        """Credible intervals and summary statistics (reference: model.py:359-371)."""
+        """Credible intervals and summary statistics (reference: model.py:359-371).  Single process: after a multi-GPU
+        fit, load the consolidated checkpoint on one GPU (``load``; ``load_checkpoint(param_only=True)``)."""
         from tapqir_b200.utils.stats import save_stats
+
+        if self.world_size != 1:
+            raise RuntimeError("compute_stats summarises the whole dataset on one GPU: run it in a single process on the "
+                               "consolidated checkpoint (Model.consolidate_checkpoint)")
 
         try:
             save_stats(self, self.path, CI=CI, save_matlab=save_matlab)

@@ -36,8 +36,26 @@ TEST_PARAMS = {  # test/test_tapqir.py:25-40
 }
 
 
-def simulate(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0, params: dict = None,
-             device="cpu", aoi_chunk: int = 64, offset_samples=None, offset_weights=None) -> CosmosDataset:
+def simulate(*args, **kwargs) -> CosmosDataset:
+    """
+    ``simulate(model, N, F, C=1, P=14, seed=0, params={})`` -- the reference's positional signature
+    (tapqir/utils/simulate.py:12-20; ``model`` may be a model instance, its registry name or None: the recipe below IS
+    the cosmos / cosmos+hmm generative model, selected by ``params``) -- or, without the leading model,
+    ``simulate(N, F, ...)``.  See :func:`simulate_dataset` for the remaining keywords.
+    """
+    if args and not isinstance(args[0], int):
+        args = args[1:]
+    elif "model" in kwargs:
+        kwargs.pop("model")
+    if len(args) > 2:      # reference order of the optional positionals: C, P, seed, params
+        for name, value in zip(("C", "P", "seed", "params"), args[2:]):
+            kwargs[name] = value
+        args = args[:2]
+    return simulate_dataset(*args, **kwargs)
+
+
+def simulate_dataset(N: int, F: int, C: int = 1, P: int = 14, K: int = 2, seed: int = 0, params: dict = None,
+                     device="cpu", aoi_chunk: int = 64, offset_samples=None, offset_weights=None) -> CosmosDataset:
     """
     Draw a dataset of ``N`` AOIs (half on-target) x ``F`` frames x ``C`` channels of PxP patches.
 

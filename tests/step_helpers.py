@@ -215,3 +215,22 @@ def check_global_grads(ours, ref, params, data, ndx, fdx, noise, tol=1e-5, **kw)
     if well:
         bad.update({k: ("self-max", v) for k, v in compare_grads(ours, ref, tol, names=well).items()})
     return bad
+
+
+def m_probs_grad_scale(params, data, ndx, fdx, noise, plate_sizes=None, **kw):
+    """
+    Forward-error scale of d loss / d m_probs (unconstrained, logit u_k):  s sum_m q(m) |m_k - p_k| |E(m)|  with E(m) the
+    per-configuration ELBO term (likelihood ~ -1e3 + priors - log q) and s the plate scales x mask.  The gradient itself
+    is  s sum_m q(m) (m_k - p_k) E(m): a q-weighted DIFFERENCE of the E(m), which goes to zero as the fit converges
+    (p -> sigmoid of that difference) while the E(m) -- each delivered to the loss tolerance, 1e-6 -- do not.
+    Returns a (K, nb, fb, C) tensor.
+    """
+    with torch.no_grad():
+        _, parts = O.elbo(params, data, ndx, fdx, noise, return_parts=True, plate_sizes=plate_sizes, **kw)
+        p = O.to_constrained(params, data.P, data.dtype)["m_probs"][:, ndx[:, None], fdx[None, :]]   # (K, nb, fb, C)
+        Nt, F = plate_sizes if plate_sizes is not None else (data.Nt, data.F)
+        s = (Nt / len(ndx)) * (F / len(fdx)) * data.mask[ndx].to(data.dtype)[:, None, None]
+        mcfg = O.m_configs(p.shape[0], data.dtype)
+        E, q = parts["per_config"].abs(), parts["q_m"]
+        return torch.stack([s * sum(q[m] * (mcfg[m, k] - p[k]).abs() * E[m] for m in range(mcfg.shape[0]))
+                            for k in range(p.shape[0])])

@@ -29,7 +29,7 @@ from oracle import cosmos_oracle as O
 from tapqir_b200.models import layout as L
 from tapqir_b200.utils.dataset import DeviceStore
 from tapqir_b200.utils.simulate import simulate
-from tests.step_helpers import check_global_grads, compare_grads, flat_inputs
+from tests.step_helpers import check_global_grads, compare_grads, flat_inputs, m_probs_grad_scale
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -262,8 +262,17 @@ def test_trained_state_after_2000_device_iterations():
     loss = eng.step(update=False, ndx=ndx.to(torch.int32).to(DEV), fdx=fdx.to(torch.int32).to(DEV),
                     local_noise=lnoise.to(DEV), global_noise=gnoise.to(DEV)).item()
     assert abs(loss - ref_loss) <= 1e-6 * abs(ref_loss), (loss, ref_loss)
-    bad = compare_grads(eng.named_grads(), ref_grads, 1e-5, names=L.LOCAL_NAMES)
-    bad.update(check_global_grads(eng.named_grads(), ref_grads, params, data_full, ndx, fdx, noise))
+    grads = eng.named_grads()
+    bad = compare_grads(grads, ref_grads, 1e-5, names=[k for k in L.LOCAL_NAMES if k != "m_probs"])
+    # m_probs: after 2000 iterations p has converged to the sigmoid of the difference its gradient measures, the largest
+    # entry of the tensor has shrunk to a few units while the fp32 error of the per-configuration terms it subtracts has
+    # not (measured on a B200: 2.0e-5 of the largest entry) -- checked against its forward-error scale at the loss
+    # tolerance instead, and against the largest entry at 5e-5
+    n, f = ndx[:, None], fdx[None, :]
+    err = (grads["m_probs"].double().cpu()[:, n, f] - ref_grads["m_probs"][:, n, f]).abs()
+    assert bool((err <= 1e-6 * m_probs_grad_scale(params, data_full, ndx, fdx, noise)).all())
+    bad.update(compare_grads(grads, ref_grads, 5e-5, names=["m_probs"]))
+    bad.update(check_global_grads(grads, ref_grads, params, data_full, ndx, fdx, noise))
     assert not bad, bad
 
 

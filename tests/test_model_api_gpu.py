@@ -167,3 +167,72 @@ def test_snr_and_chi2_matches_formula():
     ideal = b.double()[..., None, None] + ga.sum(0)
     ref_chi2 = ((data.double() - ideal - 90.0) ** 2 / ideal).mean((-1, -2))
     assert torch.allclose(snr.double().cpu(), ref_snr, rtol=1e-4) and torch.allclose(chi2.double().cpu(), ref_chi2, rtol=1e-4)
+
+
+def test_stats_flow_on_a_model_that_was_never_initialised(dataset_path):
+    """`tapqir stats` (main.py:566): ``load(); load_checkpoint(param_only=True); compute_stats()`` on a FRESH model --
+    no ``init()``: the engine is built from the constructor's defaults."""
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    save(simulate(4, 12, seed=5), dataset_path)
+    fit = models["cosmos"](device="cuda")
+    fit.load(dataset_path)
+    fit.init(nbatch_size=4, fbatch_size=12)
+    fit.run(1, progress_bar=lambda it: it)
+    stats = models["cosmos"](device="cuda")
+    stats.load(dataset_path)
+    stats.load_checkpoint(param_only=True)
+    for k, v in fit.engine.named_unconstrained().items():
+        assert torch.equal(v, stats.engine.named_unconstrained()[k]), k
+    stats.compute_stats(CI=0.95)
+    assert (dataset_path / "cosmos_params.tpqr").exists() and (dataset_path / "cosmos_summary.csv").exists()
+
+
+def test_reported_loss_carries_the_masked_aoi_constant(dataset_path):
+    """model.py:285-298 logs ``-ELBO`` as Pyro computes it: for a masked AOI the enumerated sites' log-probabilities are
+    zeroed but still summed over -- 4 configurations x ln 6 per masked unit, times the plate scales (tests/test_oracle.py
+    pins the constant against the reference's own run).  ``iter_loss`` adds it to the device loss; gradients are unaffected."""
+    import math
+
+    from tapqir_b200.models import models
+    from tapqir_b200.utils.dataset import save
+    from tapqir_b200.utils.simulate import simulate
+
+    ds = simulate(4, 10, seed=6)
+    ds.mask[1] = False
+    save(ds, dataset_path)
+    model = models["cosmos"](device="cuda")
+    model.load(dataset_path)
+    model.init(nbatch_size=4, fbatch_size=5)
+    model.step()
+    raw = float(model._loss_dev.item())
+    assert abs(model.iter_loss - raw - 1 * 5 * 1 * 4 * math.log(6) * (4 / 4) * (10 / 5)) < 1e-9
+    model.init(nbatch_size=2, fbatch_size=10)          # AOI minibatch: the constant follows the drawn indices
+    model.step()
+    n_masked = int((model.engine.ndx.cpu() == 1).sum())
+    assert abs(model.iter_loss - float(model._loss_dev.item()) - n_masked * 10 * 4 * math.log(6) * (4 / 2)) < 1e-9
+
+
+def test_nan_detection_has_its_own_exception_type(dataset_path):
+    """Model.run restarts only on NonFiniteParameterError (a ValueError, as in the reference): an argument error of the
+    C ABI -- also a ValueError -- must propagate instead of being retried as a divergence."""
+    from tapqir_b200.exceptions import NonFiniteParameterError
+    from tapqir_b200.models import models
+
+    model = models["cosmos"](device="cuda")
+    model.load(dataset_path)
+    model.init(nbatch_size=2, fbatch_size=5)
+    model.step()
+    model.engine.named_unconstrained()["gain_loc"].fill_(float("nan"))
+    with pytest.raises(NonFiniteParameterError):
+        model.save_checkpoint()
+    model.init(nbatch_size=2, fbatch_size=5)
+
+    def broken_step(**kw):
+        raise ValueError("tq_subsample: bad sizes")
+
+    model.step = broken_step
+    with pytest.raises(ValueError, match="bad sizes"):
+        model.run(3, progress_bar=lambda it: it)
