@@ -126,6 +126,23 @@ int tq_site_record_rows(void);     /* rows NREC of the per-site record buffer (N
 int64_t tq_local_post_scratch(int nb, int fb, int C);
 int64_t tq_local_post_tickets(int nb, int fb, int C);
 
+/* The AOI-local part of a step -- tq_cosmos_sites_ws + tq_ksmogn_fwd_bwd + tq_cosmos_local_post -- as ONE persistent
+ * kernel (csrc/cosmos_fused.cu): guide sites (cosmos.py:393-462), rendered likelihood forward + reverse
+ * (ksmogn.py:187-238, util.py:15-64), priors / (z, theta) sums / chain rule (cosmos.py:216-327 under TraceEnum_ELBO),
+ * the per-unit intermediates staying in shared memory.  Same inputs and outputs as the three calls it replaces (`gain`:
+ * the float written by tq_cosmos_globals_sample; noise_in: (9, U) base variates or NULL); samples_out (9, U) and L_out
+ * (4, U) are optional copies of the guide samples / configuration log-likelihoods.  tq_cosmos_fused_supported says
+ * whether a view qualifies (dtype float, P = 14, uint16 pixels, O <= 512); scratch as for tq_cosmos_local_post, sized
+ * by tq_cosmos_fused_scratch (doubles) / tq_cosmos_fused_tickets (8-byte slots, zero before the first call). */
+int tq_cosmos_fused_supported(int dtype, const tq_patch_view* view);
+int64_t tq_cosmos_fused_scratch(int nb, int fb, int C);
+int64_t tq_cosmos_fused_tickets(int nb, int fb, int C);
+int tq_cosmos_fused_step(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
+                         const void* tables, const void* gain, int64_t aoi_offset, uint64_t seed,
+                         const void* state, const void* noise_in, double sN, double sF, void* lgrads,
+                         double* tickets, double* block_partial, double* acc, void* samples_out, void* L_out,
+                         void* stream);
+
 /* pyro.plate(subsample_size=n) [third party: randperm(size)[:n]]: uniform sample without
  * replacement by a partial Fisher-Yates on the persistent permutation `perm` (n_total int32,
  * initialise to arange once).  out: (n_pick,) int32.  stream_id separates independent draws. */

@@ -56,6 +56,11 @@ SIGNATURES = {
                                  _VP, _VP, _VP, _VP]),
     "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                       c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
+    "tq_cosmos_fused_supported": (c_int, [c_int, POINTER(PatchView)]),
+    "tq_cosmos_fused_scratch": (c_int64, [c_int, c_int, c_int]),
+    "tq_cosmos_fused_tickets": (c_int64, [c_int, c_int, c_int]),
+    "tq_cosmos_fused_step": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, c_int64, c_uint64, _VP, _VP,
+                                      c_double, c_double, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_zprobs": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, c_double, _VP, _VP, _VP]),
     "tq_cosmos_globals_grad": (c_int, [c_int, c_int, _VP, _VP, _VP, _VP, c_double, c_double, _VP, _VP, _VP, _VP]),
     "tq_sizeof_gprep": (c_int, []),

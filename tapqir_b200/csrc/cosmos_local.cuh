@@ -377,8 +377,10 @@ template <typename F> struct UnitGrads {
 //   g_rate     d (sum_m q(m) L(m)) / d (1/gain) from K1
 //   u_mp       unconstrained m_probs of the K spots; u_bm/u_bs unconstrained AOI-level parameters
 //   first_frame  this unit carries the AOI-level prior terms of its (AOI, channel)
-template <typename F>
-TQ_HD void unit_post(const F (&rec)[NREC], const F (&sample)[NSAMP], const F (&L)[kM], const F (&gs)[NSAMP],
+// (rec / sample / gs: anything indexable -- plain arrays, or strided views of shared memory in the fused kernel, which
+// lets the compiler load each entry where it is used instead of holding all 76 in registers)
+template <typename F, typename RecT, typename SampT, typename GsT>
+TQ_HD void unit_post(const RecT& rec, const SampT& sample, const F (&L)[kM], const GsT& gs,
                      F g_rate, const F (&u_mp)[kK], F u_bm, F u_bs, const ModelConst& mc,
                      const GlobalTables<F>& gt, int c, bool ontarget, bool first_frame, UnitGrads<F>& out) {
     using R = Real<F>;
@@ -398,14 +400,14 @@ TQ_HD void unit_post(const F (&rec)[NREC], const F (&sample)[NSAMP], const F (&L
     }
 
     // ---- background ------------------------------------------------------------------------------------------
-    const F* ex = rec + NSAMP * NSO;
-    F elbo = ex[EX_LP] - R_(S_B, SO_LQ);
+    auto EX_ = [&](int j) -> F { return rec[NSAMP * NSO + j]; };
+    F elbo = EX_(EX_LP) - R_(S_B, SO_LQ);
     {
-        const F G = ex[EX_DP] - R_(S_B, SO_DQ) + gs[S_B];
+        const F G = EX_(EX_DP) - R_(S_B, SO_DQ) + gs[S_B];
         out.g[LP_B_LOC] = G * R_(S_B, SO_A0) - R_(S_B, SO_B0);
         out.g[LP_B_BETA] = G * R_(S_B, SO_A1) - R_(S_B, SO_B1);
-        out.g[LP_BM] = ex[EX_GBM];
-        out.g[LP_BS] = ex[EX_GBS];
+        out.g[LP_BM] = EX_(EX_GBM);
+        out.g[LP_BS] = EX_(EX_GBS);
     }
 
     // ---- per-spot terms that do not depend on (z, theta) ------------------------------------------------------

@@ -25,7 +25,7 @@ constexpr int kZ = 2;          // z states (S = 1)
 #ifdef __CUDACC__
 #define TQ_DEV __device__ __forceinline__
 #define TQ_HD __host__ __device__ __forceinline__
-#define TQ_HD_NOINLINE __host__ __device__ __noinline__
+#define TQ_HD_NOINLINE static __host__ __device__ __noinline__   // static: header-defined, several translation units
 #else
 #define TQ_DEV inline
 #define TQ_HD inline

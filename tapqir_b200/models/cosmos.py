@@ -185,6 +185,8 @@ class cosmos(Model):
         # globals_sample, globals_prepare, site_fast, site_worklist, ksmogn, local_post, globals_finish, adam x2, advance
         # (dtype "double": one site kernel)
         n = 10 if eng.dtype == torch.float32 else 9
+        if getattr(eng, "last_step_fused", False):
+            n -= 3   # site_fast + site_worklist + ksmogn + local_post -> cosmos_fused_kernel
         n += (0 if eng.full_n else 1) + (0 if eng.full_f else 1)
         return n
 

@@ -83,6 +83,11 @@ class CosmosEngine:
                 logging.getLogger(__name__).warning(f"peer-memory all-reduce unavailable ({err}); using NCCL")
                 self.p2p = None
         self.use_graph = use_graph
+        # sites -> likelihood -> post as ONE persistent kernel (csrc/cosmos_fused.cu) where it applies (dtype float,
+        # P = 14, uint16 pixels); TQ_FUSED=0 keeps the three per-stage kernels (the A/B reference, and what dtype
+        # "double" / float pixels / the hmm variant run)
+        self.fused = os.environ.get("TQ_FUSED", "1") != "0" and type(self).__name__ == "CosmosEngine"
+        self.keep_intermediates = False   # fused path: also write samples / L back to HBM (tests, diagnostics)
         self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._ev_fork0, self._ev_join0 = torch.cuda.Event(), torch.cuda.Event()
@@ -106,8 +111,10 @@ class CosmosEngine:
         self.qm, self.Lm, self.g_rate = e(4, U), e(4, U), e(U)
         self.rec = e(self.lib.tq_site_record_rows(), U)   # per-site records (csrc/cosmos_local.cuh SO_*/EX_*)
         # scratch of tq_cosmos_local_post: per-block partial sums, and its (self-resetting) completion tickets
-        self.block_partial = e(max(self.lib.tq_local_post_scratch(self.nb, self.fb, self.C), 1), dt=torch.float64)
-        self.tickets = torch.zeros(max(self.lib.tq_local_post_tickets(self.nb, self.fb, self.C), 1), dtype=torch.float64, device=dev)
+        self.block_partial = e(max(self.lib.tq_local_post_scratch(self.nb, self.fb, self.C),
+                                   self.lib.tq_cosmos_fused_scratch(self.nb, self.fb, self.C), 1), dt=torch.float64)
+        self.tickets = torch.zeros(max(self.lib.tq_local_post_tickets(self.nb, self.fb, self.C),
+                                       self.lib.tq_cosmos_fused_tickets(self.nb, self.fb, self.C), 1), dtype=torch.float64, device=dev)
         # scale factors of the subsampled plates (cosmos.py:194-208).  The AOI minibatch is stratified by shard: rank r
         # draws nb_r = min(nbatch_size, Nt_r) of its Nt_r AOIs, each with inclusion probability nb_r / Nt_r, so its terms
         # carry sN = Nt_r / nb_r.  The cross-rank sum and the global reverse mode use ONE reference scale
@@ -206,25 +213,23 @@ class CosmosEngine:
                 # acc-independent part of the globals' reverse mode: off the critical path, under the likelihood kernel
                 _lib.check(lib.tq_cosmos_globals_prepare(code, self.C, p(self.gparams), mc, p(self.gstate), p(self.gprep),
                                                          _lib.stream_ptr(self.device)), "tq_cosmos_globals_prepare")
-            # sites that leave the fp32 forms are collected in a worklist (the not-yet-written gradient buffer of the
-            # likelihood kernel serves as its storage) and redone in double by dense warps
-            _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
-                                              p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
-                                              p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
-            main.wait_event(self._ev_join0)
-            S, G, K = self.samples, self.gs, L.K
-            if time_likelihood is not None:
-                time_likelihood[0].record()
-            _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
-                                             p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg_arg), 4, p(self.qm),
-                                             p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
-                                             p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
-            if time_likelihood is not None:
-                time_likelihood[1].record()
-            _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
-                                                p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
-                                                p(self.tickets), p(self.block_partial), p(self.acc), st),
-                       "tq_cosmos_local_post")
+            fused = (self.fused and self.mcfg_arg is None and self.U > 0
+                     and bool(lib.tq_cosmos_fused_supported(code, ctypes.byref(view))))
+            self.last_step_fused = fused
+            if fused:
+                main.wait_event(self._ev_join0)   # the sampled gain and the prior tables
+                if time_likelihood is not None:
+                    time_likelihood[0].record()
+                keep = self.keep_intermediates
+                _lib.check(lib.tq_cosmos_fused_step(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.gain),
+                                                    self.aoi_offset, self.seed, p(self.state), p(local_noise), self.sN, self.sF,
+                                                    p(self.lgrads), p(self.tickets), p(self.block_partial), p(self.acc),
+                                                    p(self.samples) if keep else None, p(self.Lm) if keep else None, st),
+                           "tq_cosmos_fused_step")
+                if time_likelihood is not None:
+                    time_likelihood[1].record()
+            else:
+                self._enqueue_stages(view, local_noise, main, time_likelihood, st)
             # the all-reduce of the (C, 18) accumulators (multi-GPU), finishing the global reverse pass (a few FMAs per
             # parameter) and the global Adam run on the side stream, beside the dense Adam over the AOI-local buffer,
             # which depends on none of them: the collective's latency hides under the local update
@@ -257,6 +262,31 @@ class CosmosEngine:
             if update:
                 _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
         return self.loss
+
+    def _enqueue_stages(self, view, local_noise, main, time_likelihood, st):
+        """The AOI-local part of a step as three kernels with HBM scratch between them (dtype double, float pixels,
+        P != 14, the operator-level mcfg table, TQ_FUSED=0)."""
+        lib, code, p = self.lib, self.code, _lib.ptr
+        mc = ctypes.byref(self.mc)
+        # sites that leave the fp32 forms are collected in a worklist (the not-yet-written gradient buffer of the
+        # likelihood kernel serves as its storage) and redone in double by dense warps
+        _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
+                                          p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
+                                          p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
+        main.wait_event(self._ev_join0)
+        S, G, K = self.samples, self.gs, L.K
+        if time_likelihood is not None:
+            time_likelihood[0].record()
+        _lib.check(lib.tq_ksmogn_fwd_bwd(code, view, p(S[1:1 + K]), p(S[1 + K:1 + 2 * K]), p(S[1 + 2 * K:1 + 3 * K]),
+                                         p(S[1 + 3 * K:1 + 4 * K]), p(S[0]), p(self.gain), p(self.mcfg_arg), 4, p(self.qm),
+                                         p(self.Lm), p(G[1:1 + K]), p(G[1 + K:1 + 2 * K]), p(G[1 + 2 * K:1 + 3 * K]),
+                                         p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
+        if time_likelihood is not None:
+            time_likelihood[1].record()
+        _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
+                                            p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
+                                            p(self.tickets), p(self.block_partial), p(self.acc), st),
+                   "tq_cosmos_local_post")
 
     # ---- posterior of the enumerated latents (cosmos.compute_probs, row N1) --------------------------------
     @torch.no_grad()

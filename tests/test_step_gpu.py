@@ -121,6 +121,7 @@ def test_device_sampler_matches_guide_distribution():
     parameters (b ~ Gamma(b_loc b_beta, b_beta), x ~ AffineBeta(0, 200, -7.5, 7.5), ...)."""
     ds, data, params, _, _, _ = make_problem(N=8, F=200, C=1, nb=8, fb=200, seed=6, perturb=False)
     eng = make_engine(ds, data, params, 8, 200, torch.float32, seed=1)
+    eng.keep_intermediates = True   # the fused step kernel keeps the samples in shared memory unless asked
     eng.step(update=False)
     S = eng.samples.double().cpu()
     c = O.to_constrained(params, data.P, data.dtype)
