@@ -83,10 +83,12 @@ class CosmosEngine:
                 logging.getLogger(__name__).warning(f"peer-memory all-reduce unavailable ({err}); using NCCL")
                 self.p2p = None
         self.use_graph = use_graph
-        # sites -> likelihood -> post as ONE persistent kernel (csrc/cosmos_fused.cu) where it applies (dtype float,
-        # P = 14, uint16 pixels); TQ_FUSED=0 keeps the three per-stage kernels (the A/B reference, and what dtype
-        # "double" / float pixels / the hmm variant run)
-        self.fused = os.environ.get("TQ_FUSED", "1") != "0" and type(self).__name__ == "CosmosEngine"
+        # TQ_FUSED=1: sites -> likelihood -> post as ONE persistent kernel (csrc/cosmos_fused.cu; dtype float, P = 14,
+        # uint16 pixels).  Parity-green but NOT the default: measured on a B200 it is slower than the three per-stage
+        # kernels (C3: 9.7 vs 6.8 ms per step, C2: 0.267 vs 0.185 ms; profiles/r2_fused_ab.md) -- one register budget
+        # (128) for three very different phases leaves 16 warps per SM, and the site / post phases, which the
+        # stand-alone kernels run at 32 / 12 warps per SM, are latency-bound at 4 warps per block
+        self.fused = os.environ.get("TQ_FUSED", "0") == "1" and type(self).__name__ == "CosmosEngine"
         self.keep_intermediates = False   # fused path: also write samples / L back to HBM (tests, diagnostics)
         self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()

@@ -62,7 +62,9 @@ def test_fused_kernel_equals_the_per_stage_kernels(cfg, replay):
     # A warp sweeps four consecutive units and picks ONE form of the sweep for them (packed pairs / scalar / small-a).
     # When a minibatch AOI holds a multiple of 4 units both kernels group the same units, so everything per unit is
     # bit-identical; otherwise a unit can be swept by the other form (1e-6 differences).
-    aligned = (cfg["fb"] * cfg["C"]) % 4 == 0
+    # (and far from the initial point, cfg["scale"], the two kernels' separately compiled copies of the regime code
+    # outside the bulk forms may contract multiply-adds differently: last-bit differences in a site record)
+    aligned = (cfg["fb"] * cfg["C"]) % 4 == 0 and "scale" not in cfg
     if aligned:
         assert torch.equal(Lf, Ls), "configuration log-likelihoods differ"
         tol = dict(rtol=1e-12, atol=0)
