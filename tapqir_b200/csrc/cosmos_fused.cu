@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(kFThreads, 4) cosmos_fused_kernel(const FusedA
     const int O = a.v.O, offpad = (2 * O + 3) & ~3;
     float* off_s = reinterpret_cast<float*>(smem_raw);
     float* off_w2 = off_s + O;
-    float* tabs = off_s + offpad;                                        // kFSlots x (2 kK kMaxP)
-    float* spx_all = tabs + kFSlots * (2 * kK * kMaxP);                  // kFSlots x 196 (phase L); scratch in S and P
+    float* tabs = off_s + offpad;                                        // kFSlots x kTabFloats
+    float* spx_all = tabs + kFSlots * kTabFloats;                  // kFSlots x 196 (phase L); scratch in S and P
     float* unit_rows = spx_all + kFSlots * 196;                          // kFUnitRows x kFB
     float* rec_rows = unit_rows + kFUnitRows * kFB;                      // NREC x kFB
     unsigned char* stage_all = reinterpret_cast<unsigned char*>(rec_rows + NREC * kFB);   // kFSlots x kFStage
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(kFThreads, 4) cosmos_fused_kernel(const FusedA
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = tid / kSub, sub = tid % kSub, wslot = lane / kSub;
-    float* gx = tabs + slot * (2 * kK * kMaxP);
+    float* tab = tabs + slot * kTabFloats;
+    float* gx = tab;
     float* gy = gx + kK * kMaxP;
     float* spx = spx_all + slot * 196;
     unsigned char* stage = stage_all + slot * kFStage;
@@ -341,30 +342,6 @@ __global__ void __launch_bounds__(kFThreads, 4) cosmos_fused_kernel(const FusedA
 #pragma unroll
             for (int m = 0; m < kM; ++m) { W[m] = sm.qm[m * kFB + t]; Wr[m] = W[m] * fc.rate; }
 
-            // separable spot factors: 2 K P exponentials per patch instead of K P P
-            float norm[kK];
-            {
-                float c2[kK];
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
-                    const float iw = rcp_newton(s.w[k]);
-                    norm[k] = 0.15915494309189535f * iw * iw;
-                    c2[k] = (-0.5f * kLog2e) * iw * iw;
-                }
-                for (int i = sub; i < 14; i += kSub) {
-                    const float fi = float(i);
-#pragma unroll
-                    for (int k = 0; k < kK; ++k) {
-                        const float dx = fi - s.cx[k], dy = fi - s.cy[k];
-                        gx[k * kMaxP + i] = f_ex2(c2[k] * dx * dx);
-                        gy[k * kMaxP + i] = f_ex2(c2[k] * dy * dy);
-                    }
-                }
-            }
-            __syncwarp();
-
-            PatchOut<float, kM> out;
-            out.zero();
             const bool small = s.b * fc.rate < 4.0f;
             bool pairs = false;
             if (OC > 0) {
@@ -372,8 +349,16 @@ __global__ void __launch_bounds__(kFThreads, 4) cosmos_fused_kernel(const FusedA
                 for (int j = 1; j < OC; ++j) max_off = fmaxf(max_off, off_s[j]);
                 pairs = __all_sync(kFull, !small && pix_min > max_off);
             }
+            // separable spot factors: 2 K P exponentials per patch instead of K P P
+            float norm[kK];
+            if (pairs) build_tables_pairs(tab, sub, s);
+            else build_tables_generic(tab, 14, sub, s, norm);
+            __syncwarp();
+
+            PatchOut<float, kM> out;
+            out.zero();
             if (pairs)
-                sweep_patch_pairs<OC>(spx, sub, gx, gy, s, norm, fc, off_s, off_w2, W, out);
+                sweep_patch_pairs<OC>(spx, sub, tab, s, fc, off_s, off_w2, W, out);
             else if (__any_sync(kFull, small))
                 sweep_patch<OC, true, true, true>(spx, 14, 196, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
             else
@@ -551,7 +536,7 @@ static int fused_counter_set_of(cudaStream_t st) {
 
 static size_t fused_smem_bytes(int O) {
     const int offpad = (2 * O + 3) & ~3;
-    return sizeof(float) * ((size_t)offpad + kFSlots * (2 * kK * kMaxP) + kFSlots * 196 + (size_t)(kFUnitRows + NREC) * kFB) +
+    return sizeof(float) * ((size_t)offpad + kFSlots * kTabFloats + kFSlots * 196 + (size_t)(kFUnitRows + NREC) * kFB) +
            (size_t)kFSlots * kFStage;
 }
 

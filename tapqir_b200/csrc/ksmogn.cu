@@ -142,10 +142,11 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = threadIdx.x / kSub, sub = threadIdx.x % kSub, wslot = lane / kSub;
     const int P = P14 ? 14 : a.v.P, PP = P * P;
-    float* gx = off_s + offpad + slot * (2 * kK * kMaxP);
+    float* tab = off_s + offpad + slot * kTabFloats;
+    float* gx = tab;
     float* gy = gx + kK * kMaxP;
-    float* spx = off_s + offpad + kUnitsPerBlock * (2 * kK * kMaxP) + slot * PP;
-    unsigned char* stage = reinterpret_cast<unsigned char*>(off_s + offpad + kUnitsPerBlock * (2 * kK * kMaxP + PP))
+    float* spx = off_s + offpad + kUnitsPerBlock * kTabFloats + slot * PP;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(off_s + offpad + kUnitsPerBlock * (kTabFloats + PP))
                            + slot * stage_bytes<PF>();
     for (int j = threadIdx.x; j < O; j += blockDim.x) {
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
@@ -245,30 +246,6 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
         if (lane == 0) pending = stride + atomicAdd(counters, 1u);
         if (nxt < n_wg) prefetch(nxt);
 
-        // separable spot factors: 2*K*P exponentials per patch instead of K*P*P
-        float norm[kK];
-        {
-            float c2[kK];
-#pragma unroll
-            for (int k = 0; k < kK; ++k) {
-                const float iw = rcp_newton(s.w[k]);
-                norm[k] = 0.15915494309189535f * iw * iw;
-                c2[k] = (-0.5f * kLog2e) * iw * iw;
-            }
-            for (int i = sub; i < P; i += kSub) {
-                const float fi = float(i);
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
-                    const float dx = fi - s.cx[k], dy = fi - s.cy[k];
-                    gx[k * kMaxP + i] = f_ex2(c2[k] * dx * dx);
-                    gy[k * kMaxP + i] = f_ex2(c2[k] * dy * dy);
-                }
-            }
-        }
-        __syncwarp();
-
-        PatchOut<float, kM> out;
-        out.zero();
         // a = image/gain is smallest without spots: one test per patch selects the Stirling variant
         const bool small = s.b * fc.rate < 4.0f;
         bool pairs = false;
@@ -278,8 +255,16 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
             for (int j = 1; j < OC; ++j) max_off = fmaxf(max_off, off_s[j]);
             pairs = __all_sync(kFull, !small && pix_min > max_off);
         }
+        // separable spot factors: 2*K*P exponentials per patch instead of K*P*P (ksmogn_sweep.cuh: table layouts)
+        float norm[kK];
+        if (pairs) build_tables_pairs(tab, sub, s);
+        else build_tables_generic(tab, P, sub, s, norm);
+        __syncwarp();
+
+        PatchOut<float, kM> out;
+        out.zero();
         if (pairs)
-            sweep_patch_pairs<OC>(spx, sub, gx, gy, s, norm, fc, off_s, off_w2, W, out);
+            sweep_patch_pairs<OC>(spx, sub, tab, s, fc, off_s, off_w2, W, out);
         else if (__any_sync(kFull, small))
             sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
         else
@@ -355,7 +340,7 @@ static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
         return TQ_ERR_ARG;
     }
     const int PP = a.v.P * a.v.P, offpad = (2 * a.v.O + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)offpad + kUnitsPerBlock * (2 * kK * kMaxP + (size_t)PP)) +
+    const size_t smem = sizeof(float) * ((size_t)offpad + kUnitsPerBlock * (kTabFloats + (size_t)PP)) +
                         (size_t)kUnitsPerBlock * stage_bytes<PF>();
     auto kern = ksmogn_stream_kernel<PIX, OC, P14, BWD, MINB>;
     if (smem > 48 * 1024) {

@@ -41,18 +41,85 @@ __device__ __forceinline__ void sweep_patch(const float* __restrict__ pix, int P
     }
 }
 
+// ---- per-patch tables of the separable render (2 K P exponentials per patch instead of K P P) ---------------------------
+// One table area of kTabFloats floats per patch slot, in one of two layouts:
+//   generic   gx[k * kMaxP + i], gy[k * kMaxP + i] = exp(-(i - c)^2 / (2 w^2))             (any P; sweep_patch)
+//   pairs     P = 14, packed sweep: everything a pixel pair needs that depends on its column or on its row pair alone,
+//             so that the sweep's inner loop is left with the arithmetic that depends on BOTH (and with wide loads):
+//             col[c] (8 floats): gxh_0, gxh_1 (column factor x norm x height), dx_0, dx_1, dx_0^2, dx_1^2, -, -
+//             row[r] (8 floats), r = 0..6: gy_0(r), gy_0(r+7), gy_1(r), gy_1(r+7), dy_0(r), dy_0(r+7), dy_1(r), dy_1(r+7)
+constexpr int kTabFloats = 176;   // >= 2 kK kMaxP (generic) and >= 14 * 8 + 7 * 8 (pairs), 16-byte multiple
+static_assert(kTabFloats >= 2 * kK * kMaxP && kTabFloats >= 21 * 8 && kTabFloats % 4 == 0, "table area too small");
+
+__device__ __forceinline__ void build_tables_generic(float* tab, int P, int sub, const PatchSpots<float>& s, float (&norm)[kK]) {
+    float* gx = tab;
+    float* gy = tab + kK * kMaxP;
+    float c2[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const float iw = rcp_newton(s.w[k]);
+        norm[k] = 0.15915494309189535f * iw * iw;
+        c2[k] = (-0.5f * kLog2e) * iw * iw;
+    }
+    for (int i = sub; i < P; i += kSub) {
+        const float fi = float(i);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            const float dx = fi - s.cx[k], dy = fi - s.cy[k];
+            gx[k * kMaxP + i] = f_ex2(c2[k] * dx * dx);
+            gy[k * kMaxP + i] = f_ex2(c2[k] * dy * dy);
+        }
+    }
+}
+
+__device__ __forceinline__ void build_tables_pairs(float* tab, int sub, const PatchSpots<float>& s) {
+    float c2[kK], nh[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const float iw = rcp_newton(s.w[k]);
+        nh[k] = 0.15915494309189535f * iw * iw * s.h[k];
+        c2[k] = (-0.5f * kLog2e) * iw * iw;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = sub + j * kSub;
+        if (c < 14) {
+            const float fc_ = float(c);
+            const float dx0 = fc_ - s.cx[0], dx1 = fc_ - s.cx[1];
+            const float q0 = dx0 * dx0, q1 = dx1 * dx1;
+            float4* dst = reinterpret_cast<float4*>(tab + c * 8);
+            dst[0] = make_float4(f_ex2(c2[0] * q0) * nh[0], f_ex2(c2[1] * q1) * nh[1], dx0, dx1);
+            dst[1] = make_float4(q0, q1, 0.0f, 0.0f);
+        }
+    }
+    if (sub < 7) {
+        const float fr = float(sub);
+        const float a0 = fr - s.cy[0], b0 = (fr + 7.0f) - s.cy[0], a1 = fr - s.cy[1], b1 = (fr + 7.0f) - s.cy[1];
+        float4* dst = reinterpret_cast<float4*>(tab + 14 * 8 + sub * 8);
+        dst[0] = make_float4(f_ex2(c2[0] * a0 * a0), f_ex2(c2[0] * b0 * b0), f_ex2(c2[1] * a1 * a1), f_ex2(c2[1] * b1 * b1));
+        dst[1] = make_float4(a0, b0, a1, b1);
+    }
+}
+
 // P = 14 common case: lane `sub` takes the pixel pairs (row, col), (row + 7, col) with row * 14 + col = sub + 8 t,
-// t = 0..12 (98 pairs over 8 lanes), in packed two-wide FP32 (ksmogn_fast.cuh)
+// t = 0..12 (98 pairs over 8 lanes), in packed two-wide FP32 (ksmogn_fast.cuh); `tab`: build_tables_pairs
 template <int OC>
-__device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix, int sub, const float* gx, const float* gy,
-                                                  const PatchSpots<float>& s, const float (&norm)[kK], const FastConst& fc,
+__device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix, int sub, const float* __restrict__ tab,
+                                                  const PatchSpots<float>& s, const FastConst& fc,
                                                   const float* off_s_sm, const float* off_w2_sm, const float (&W)[kM],
                                                   PatchOut<float, kM>& out) {
     constexpr int NC = OC > 0 ? OC : 1;
     float off_s[NC], off_w2[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) { off_s[j] = off_s_sm[j]; off_w2[j] = off_w2_sm[j]; }
+    const float4* col4 = reinterpret_cast<const float4*>(tab);
+    const float4* row4 = reinterpret_cast<const float4*>(tab + 14 * 8);
     int col = sub, row = 0;
+    auto load = [&](float (&gxh)[kK], float (&dx)[kK], float (&dx2)[kK], F2 (&gyk)[kK], F2 (&dy)[kK]) {
+        const float4 c0 = col4[col * 2], c1 = col4[col * 2 + 1], r0 = row4[row * 2], r1 = row4[row * 2 + 1];
+        gxh[0] = c0.x; gxh[1] = c0.y; dx[0] = c0.z; dx[1] = c0.w; dx2[0] = c1.x; dx2[1] = c1.y;
+        gyk[0] = F2{r0.x, r0.y}; gyk[1] = F2{r0.z, r0.w}; dy[0] = F2{r1.x, r1.y}; dy[1] = F2{r1.z, r1.w};
+    };
     if (OC == 1) {
         const SingleBinConst sc = single_bin_const(s.b, fc);
         PairOut1 po;
@@ -61,18 +128,11 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
 #pragma unroll 1
         for (int t = 0; t < 13; ++t) {
             if (row < 7) {
-                float gxn[kK], dx[kK];
+                float gxh[kK], dx[kK], dx2[kK];
                 F2 gyk[kK], dy[kK];
-                const float fr = float(row);
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
-                    gxn[k] = gx[k * kMaxP + col] * norm[k];
-                    gyk[k] = F2{gy[k * kMaxP + row], gy[k * kMaxP + row + 7]};
-                    dx[k] = float(col) - s.cx[k];
-                    dy[k] = F2{fr - s.cy[k], (fr + 7.0f) - s.cy[k]};
-                }
+                load(gxh, dx, dx2, gyk, dy);
                 const F2 D{pix[row * 14 + col], pix[(row + 7) * 14 + col]};
-                pixel_pair_single_bin(D, gxn, gyk, dx, dy, s, fc, sc, off_s[0], W, po);
+                pixel_pair_single_bin(D, gxh, gyk, dx, dx2, dy, s, fc, sc, off_s[0], W, po);
                 npix += 2;
             }
             col += 8;
@@ -86,18 +146,11 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
 #pragma unroll 1
     for (int t = 0; t < 13; ++t) {
         if (row < 7) {
-            float gxn[kK], dx[kK];
+            float gxh[kK], dx[kK], dx2[kK];
             F2 gyk[kK], dy[kK];
-            const float fr = float(row);
-#pragma unroll
-            for (int k = 0; k < kK; ++k) {
-                gxn[k] = gx[k * kMaxP + col] * norm[k];
-                gyk[k] = F2{gy[k * kMaxP + row], gy[k * kMaxP + row + 7]};
-                dx[k] = float(col) - s.cx[k];
-                dy[k] = F2{fr - s.cy[k], (fr + 7.0f) - s.cy[k]};
-            }
+            load(gxh, dx, dx2, gyk, dy);
             const F2 D{pix[row * 14 + col], pix[(row + 7) * 14 + col]};
-            pixel_pair_accumulate_fast<NC>(D, gxn, gyk, dx, dy, s, fc, off_s, off_w2, W, po);
+            pixel_pair_accumulate_fast<NC>(D, gxh, gyk, dx, dx2, dy, s, fc, off_s, off_w2, W, po);
         }
         col += 8;
         if (col >= 14) { col -= 14; ++row; }

@@ -84,15 +84,16 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
             PairOut1 po; po.zero();
             for (int row = 0; row < 7; ++row)
                 for (int col = 0; col < 14; ++col) {
-                    float gxn[kK], dx[kK]; F2 gyk[kK], dy[kK];
+                    float gxh[kK], dx[kK], dx2[kK]; F2 gyk[kK], dy[kK];
                     for (int k = 0; k < kK; ++k) {
-                        gxn[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k];
+                        gxh[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k] * s.h[k];
                         gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
                         dx[k] = float(col) - s.cx[k];
+                        dx2[k] = dx[k] * dx[k];
                         dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
                     }
                     const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
-                    pixel_pair_single_bin(D, gxn, gyk, dx, dy, s, fc, sc, off_s[0], Wm, po);
+                    pixel_pair_single_bin(D, gxh, gyk, dx, dx2, dy, s, fc, sc, off_s[0], Wm, po);
                 }
             finish_single_bin(po, sc, fc, s.b, w2[0] * kLn2, Wm[0], P * P, out);
         } else if (pairs) {
@@ -103,15 +104,16 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
                 for (int j = 0; j < OCc; ++j) { os[j] = off_s[j]; ow[j] = w2[j]; }
                 for (int row = 0; row < 7; ++row)
                     for (int col = 0; col < 14; ++col) {
-                        float gxn[kK], dx[kK]; F2 gyk[kK], dy[kK];
+                        float gxh[kK], dx[kK], dx2[kK]; F2 gyk[kK], dy[kK];
                         for (int k = 0; k < kK; ++k) {
-                            gxn[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k];
+                            gxh[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k] * s.h[k];
                             gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
                             dx[k] = float(col) - s.cx[k];
+                            dx2[k] = dx[k] * dx[k];
                             dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
                         }
                         const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
-                        pixel_pair_accumulate_fast<OCc>(D, gxn, gyk, dx, dy, s, fc, os, ow, Wm, po);
+                        pixel_pair_accumulate_fast<OCc>(D, gxh, gyk, dx, dx2, dy, s, fc, os, ow, Wm, po);
                     }
             };
             switch (OC) { case 1: run(std::integral_constant<int, 1>{}); break; case 2: run(std::integral_constant<int, 2>{}); break;

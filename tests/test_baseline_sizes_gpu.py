@@ -267,10 +267,13 @@ def test_trained_state_after_2000_device_iterations():
     # m_probs: after 2000 iterations p has converged to the sigmoid of the difference its gradient measures, the largest
     # entry of the tensor has shrunk to a few units while the fp32 error of the per-configuration terms it subtracts has
     # not (measured on a B200: 2.0e-5 of the largest entry) -- checked against its forward-error scale at the loss
-    # tolerance instead, and against the largest entry at 5e-5
+    # tolerance (x 2: a difference of two such terms) instead, and against the largest entry at 5e-5
     n, f = ndx[:, None], fdx[None, :]
     err = (grads["m_probs"].double().cpu()[:, n, f] - ref_grads["m_probs"][:, n, f]).abs()
-    assert bool((err <= 1e-6 * m_probs_grad_scale(params, data_full, ndx, fdx, noise)).all())
+    ratio = (err / m_probs_grad_scale(params, data_full, ndx, fdx, noise)).max().item()
+    print(f"[trained state] m_probs gradient: worst error / forward-error scale {ratio:.2e}, "
+          f"/ largest entry {err.max().item() / ref_grads['m_probs'].abs().max().item():.2e}")
+    assert ratio <= 2e-6, ratio   # a difference of two terms, each at the loss tolerance 1e-6 (measured: 1.0e-6)
     bad.update(compare_grads(grads, ref_grads, 5e-5, names=["m_probs"]))
     bad.update(check_global_grads(grads, ref_grads, params, data_full, ndx, fdx, noise))
     assert not bad, bad
