@@ -14,7 +14,10 @@ import torch
 
 from tapqir_b200.exceptions import CudaOutOfMemoryError, NativeLibraryError
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtapqir_b200.so"
+import os
+
+# TQ_LIB: an experimental build of the same C ABI (csrc/build.py --variant=...) for A/B timings
+LIB_PATH = Path(os.environ["TQ_LIB"]) if os.environ.get("TQ_LIB") else Path(__file__).resolve().parent / "lib" / "libtapqir_b200.so"
 
 TQ_F32, TQ_F64 = 0, 1
 TQ_PIX_U16, TQ_PIX_F32, TQ_PIX_F64 = 0, 1, 2

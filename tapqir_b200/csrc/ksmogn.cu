@@ -334,7 +334,10 @@ static int counter_set_of(cudaStream_t st) {
 template <typename PIX, int OC, bool P14, bool BWD>
 static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
     constexpr bool PF = P14 && sizeof(PIX) == 2;
-    constexpr int MINB = 4;   // 4 resident blocks per SM (<= 128 registers): 5 / 6 blocks measured slower (spills)
+#ifndef TQ_KS_MINB
+#define TQ_KS_MINB 4
+#endif
+    constexpr int MINB = TQ_KS_MINB;   // 4 resident blocks per SM (<= 128 registers): 5 / 6 blocks measured slower (spills)
     if (a.U > 0x7fffffff) {
         set_error("ksmogn: %lld patches in one launch (limit 2^31 - 1)", (long long)a.U);
         return TQ_ERR_ARG;
