@@ -71,10 +71,17 @@ def algorithmic_work(o_exec):
     if o_exec == 1:
         mufu = P2 + (M - 1) * P2 * 2 + 2 * K * P
         ffma2, fadd2, fmul2, fadd, fmul = 41, 24, 14, 1, 0
-    else:   # cached-offset form: per pair 35 + 53 O packed (of which ~55 % FMAs), 13 scalar
+    elif o_exec <= 4:   # register-cached bins: per pair 35 + 53 O packed (of which ~55 % FMAs), 13 scalar
         mufu = P2 * o_exec + M * P2 * (o_exec + 3) + 2 * K * P
         packed = 35 + 53 * o_exec - 1
         ffma2, fadd2, fmul2, fadd, fmul = round(0.55 * packed), round(0.28 * packed), packed - round(0.55 * packed) - round(0.28 * packed), 7, 6
+    else:
+        # one-pass many-bins form (ksmogn_fast.cuh): per pixel and bin 1 lg2 + M ex2; per pixel lg2 y_ref and, per
+        # configuration, rcp / lg2 a / lg2 sum; per pair and bin 2 packed adds, M x (3 FFMA2 + 1 FADD2), 2 scalar max;
+        # per pair ~75 packed operations of Stirling / gradient assembly (as the cached form at O = 1)
+        mufu = P2 * o_exec * (1 + M) + P2 * (1 + 3 * M) + 2 * K * P
+        ffma2, fadd2, fmul2 = 3 * M * o_exec + 45, (2 + M) * o_exec + 20, 10
+        fadd, fmul = 2 * o_exec + 7, 6
     per_patch = 600   # prologue / epilogue: render tables, closed forms, reductions
     lane_ops = pairs * (2 * (ffma2 + fadd2 + fmul2) + fadd + fmul) + per_patch
     flops = pairs * (4 * ffma2 + 2 * (fadd2 + fmul2) + fadd + fmul) + per_patch * 3 // 2

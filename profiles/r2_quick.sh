@@ -12,3 +12,11 @@ try:
 except Exception as e: print('ERR', e)
 P
 done
+timeout 600 python bench.py --workload c2 --offset-hist 64 --steps 10 --warmup 3 --no-cpu-baseline --no-subs --trained-iters 0 > gpurun_out/${TAG}_bench_o64.json 2> gpurun_out/${TAG}_bench_o64.err; echo "o64 rc=$?"
+python - gpurun_out/${TAG}_bench_o64.json <<'P'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d['roofline']
+    print('O=64 c2 | ms', round(d['ms_per_step'],4), 'value', round(d['value']/1e6,1),'M | kern ms', round(r['kernel_ms'],4), r['bound'], 'frac', round(r['frac'],3))
+except Exception as e: print('ERR', e)
+P

@@ -136,17 +136,20 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     constexpr bool PF = P14 && sizeof(PIX) == 2;
     constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int O = a.v.O, offpad = (2 * O + 3) & ~3;
-    float* off_s = reinterpret_cast<float*>(smem_raw);
+    // O > 4 (OC == 0): per-bin constants of the one-pass form (4 floats per bin) in front of the offset tables
+    constexpr bool MANY = OC == 0 && P14 && BWD;
+    const int O = a.v.O, offpad = ((2 * O + 3) & ~3) + (MANY ? 4 * O : 0);
+    BinConst* bins = reinterpret_cast<BinConst*>(smem_raw);
+    float* off_s = reinterpret_cast<float*>(smem_raw) + (MANY ? 4 * O : 0);
     float* off_w2 = off_s + O;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = threadIdx.x / kSub, sub = threadIdx.x % kSub, wslot = lane / kSub;
     const int P = P14 ? 14 : a.v.P, PP = P * P;
-    float* tab = off_s + offpad + slot * kTabFloats;
+    float* tab = reinterpret_cast<float*>(smem_raw) + offpad + slot * kTabFloats;
     float* gx = tab;
     float* gy = gx + kK * kMaxP;
-    float* spx = off_s + offpad + kUnitsPerBlock * kTabFloats + slot * PP;
-    unsigned char* stage = reinterpret_cast<unsigned char*>(off_s + offpad + kUnitsPerBlock * (kTabFloats + PP))
+    float* spx = reinterpret_cast<float*>(smem_raw) + offpad + kUnitsPerBlock * kTabFloats + slot * PP;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(smem_raw) + offpad + kUnitsPerBlock * (kTabFloats + PP))
                            + slot * stage_bytes<PF>();
     for (int j = threadIdx.x; j < O; j += blockDim.x) {
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
@@ -158,6 +161,15 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     fc.rate2 = fc.rate * kLog2e;
     fc.log_rate = logf(fc.rate);
     __syncthreads();
+    int ref_bin = 0;
+    float delta_ref = 0.0f, w2_ref = 0.0f;
+    if (MANY) {
+        ref_bin = many_bins_reference(O, off_s);
+        delta_ref = off_s[ref_bin];
+        w2_ref = off_w2[ref_bin];
+        for (int j = threadIdx.x; j < O; j += blockDim.x) bins[j] = many_bins_const(j, ref_bin, off_s, off_w2, fc.rate2);
+        __syncthreads();
+    }
 
     const PIX* pixels = static_cast<const PIX*>(a.v.pixels);
     const float* xy = static_cast<const float*>(a.v.xy);
@@ -255,6 +267,8 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
             for (int j = 1; j < OC; ++j) max_off = fmaxf(max_off, off_s[j]);
             pairs = __all_sync(kFull, !small && pix_min > max_off);
         }
+        // many bins: every pixel above the SMALLEST offset (bins at or above a pixel drop out by underflow)
+        if (MANY) pairs = __all_sync(kFull, !small && pix_min > delta_ref);
         // separable spot factors: 2*K*P exponentials per patch instead of K*P*P (ksmogn_sweep.cuh: table layouts)
         float norm[kK];
         if (pairs) build_tables_pairs(tab, sub, s);
@@ -263,7 +277,9 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
 
         PatchOut<float, kM> out;
         out.zero();
-        if (pairs)
+        if (MANY && pairs)
+            sweep_patch_pairs_many(spx, sub, tab, s, fc, O, bins, delta_ref, w2_ref, W, out);
+        else if (pairs)
             sweep_patch_pairs<OC>(spx, sub, tab, s, fc, off_s, off_w2, W, out);
         else if (__any_sync(kFull, small))
             sweep_patch<OC, P14, BWD, true>(spx, P, PP, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
@@ -342,7 +358,7 @@ static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
         set_error("ksmogn: %lld patches in one launch (limit 2^31 - 1)", (long long)a.U);
         return TQ_ERR_ARG;
     }
-    const int PP = a.v.P * a.v.P, offpad = (2 * a.v.O + 3) & ~3;
+    const int PP = a.v.P * a.v.P, offpad = ((2 * a.v.O + 3) & ~3) + (OC == 0 && P14 && BWD ? 4 * a.v.O : 0);
     const size_t smem = sizeof(float) * ((size_t)offpad + kUnitsPerBlock * (kTabFloats + (size_t)PP)) +
                         (size_t)kUnitsPerBlock * stage_bytes<PF>();
     auto kern = ksmogn_stream_kernel<PIX, OC, P14, BWD, MINB>;

@@ -332,6 +332,118 @@ TQ_HD void pixel_pair_accumulate_fast(F2 D, const float (&gxh)[kK], const F2 (&g
     }
 }
 
+// ---- many offset bins (histograms of real movies: tens to hundreds of distinct bins, glimpse_reader.py:403-424) -------------
+// One pass over the bins per pixel pair, everything relative to a REFERENCE bin (the smallest offset delta_ref: its
+// y_ref = D - delta_ref is the largest, so it is valid for a pixel whenever any bin is):
+//     v_j(m) - v_ref(m) = (a_m - 1) (lg2 y_j - lg2 y_ref) + c_j,    c_j = (w2_j - w2_ref) + rate2 (delta_j - delta_ref)
+// -- c_j and y_j - y_ref = delta_ref - delta_j do not depend on the pixel (per-bin constants in shared memory), lg2 y_j is
+// shared by the four configurations, and the exponent needs no running maximum: bins spread over a few dozen counts
+// keep |v_j - v_ref| within a few tens of bits.  Per pixel and bin: 1 lg2 + 4 ex2, 9 packed FP32 operations per pair
+// (the two-pass form this replaces: 2 x 4 lg2 + 4 ex2 per pixel and bin, 6.75 ms per 100 000 patches at O = 64).
+// A bin at or below the pixel (y_j <= 0: excluded, ksmogn.py:225-236) has its y_j clamped to 2^-40: with a - 1 >= 3 its
+// term underflows to an exact zero.
+struct alignas(16) BinConst { float delta, c, dyc, pad; };
+struct ManyBinSums {
+    F2 se[kM], sl[kM], sy[kM];   // sum_j e_j, sum_j e_j (lg2 y_j - lg2 y_ref), sum_j e_j (y_j - y_ref),  e_j = 2^(v_j - v_ref)
+    TQ_HD void zero() {
+#pragma unroll
+        for (int m = 0; m < kM; ++m) se[m] = sl[m] = sy[m] = f2(0.0f);
+    }
+};
+constexpr float kTinyY = 9.094947017729282e-13f;   // 2^-40
+
+TQ_HD void many_bins_accumulate(F2 D, F2 l_ref, const F2 (&am1)[kM], const BinConst& bc, ManyBinSums& acc) {
+    F2 y = sub2(D, f2(bc.delta));
+    y.x = fmaxf(y.x, kTinyY);
+    y.y = fmaxf(y.y, kTinyY);
+    const F2 dl = sub2(lg2_2(y), l_ref);
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        const F2 e = ex2_2(fma2(am1[m], dl, f2(bc.c)));
+        acc.se[m] = add2(acc.se[m], e);
+        acc.sl[m] = fma2(e, dl, acc.sl[m]);
+        acc.sy[m] = fma2(e, f2(bc.dyc), acc.sy[m]);
+    }
+}
+
+// The rest of a pixel pair once its bins are summed: same quantities as pixel_pair_accumulate_fast.
+//   y_ref, l_ref   D - delta_ref and its lg2;  w2_ref  log2-weight of the reference bin
+TQ_HD void pixel_pair_finish_many(const F2 (&img)[kM], const F2 (&mu)[kK], F2 y_ref, F2 l_ref, float w2_ref,
+                                  const ManyBinSums& sums, const float (&dx)[kK], const float (&dx2)[kK], const F2 (&dy)[kK],
+                                  const FastConst& fc, const float (&W)[kM], PairOut& out) {
+    F2 gsum = f2(0.0f), S[kK];
+    const F2 vb = fma2(f2(-fc.rate2), y_ref, f2(w2_ref));            // v_ref(m) = (a_m - 1) l_ref + vb
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+        const F2 a = mul2(img[m], f2(fc.rate));
+        const F2 inv = rcp_2(mul2(a, sums.se[m]));                   // one reciprocal for 1/a and 1/se
+        const F2 ia = mul2(inv, sums.se[m]), ise = mul2(inv, a);
+        const F2 ml2 = fma2(sums.sl[m], ise, l_ref);                 // softmax mean of lg2 y
+        const F2 ym = fma2(sums.sy[m], ise, y_ref);                  // softmax mean of y
+        const F2 lse2 = add2(fma2(sub2(a, f2(1.0f)), l_ref, vb), lg2_2(sums.se[m]));
+        const F2 la = mul2(lg2_2(a), f2(kLn2));
+        const F2 ia2 = mul2(ia, ia);
+        const F2 r = mul2(ia, fma2(ia2, fma2(ia2, f2(0.000793650794f), f2(-0.00277777778f)), f2(0.0833333333f)));
+        const F2 q = mul2(ia, fma2(ia, fma2(ia2, fma2(ia2, f2(0.00396825397f), f2(-0.00833333333f)), f2(0.0833333333f)), f2(0.5f)));
+        const F2 nl = sub2(add2(fma2(sub2(f2(0.5f), a), la, a), f2(-kHalfLn2Pi)), r);   // -lgamma(a)
+        out.logp[m] = add2(out.logp[m], fma2(lse2, f2(kLn2), fma2(a, f2(fc.log_rate), nl)));
+        const F2 dLda = add2(mul2(ml2, f2(kLn2)), sub2(f2(fc.log_rate), sub2(la, q)));
+        const F2 gi = mul2(dLda, f2(W[m]));   // times rate: finish_pair
+        out.g_rate = fma2(sub2(fma2(img[m], dLda, img[m]), ym), f2(W[m]), out.g_rate);
+        gsum = add2(gsum, gi);
+        if (m == 1) S[0] = gi;
+        if (m == 2) S[1] = gi;
+        if (m == 3) { S[0] = add2(S[0], gi); S[1] = add2(S[1], gi); }
+    }
+    out.g_b = add2(out.g_b, gsum);
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const F2 t = mul2(S[k], mu[k]);
+        out.g_h[k] = add2(out.g_h[k], t);
+        out.g_x[k] = fma2(t, f2(dx[k]), out.g_x[k]);
+        out.g_y[k] = fma2(t, dy[k], out.g_y[k]);
+        out.g_w[k] = fma2(t, fma2(dy[k], dy[k], f2(dx2[k])), out.g_w[k]);
+    }
+}
+
+// One pixel pair against all bins (the kernel's loop; also what tests/hostcheck runs): bins[0..O) hold the per-bin
+// constants, ref = index of the reference bin.
+TQ_HD void pixel_pair_many_bins(F2 D, const float (&gxh)[kK], const F2 (&gyk)[kK], const float (&dx)[kK],
+                                const float (&dx2)[kK], const F2 (&dy)[kK], const PatchSpots<float>& s,
+                                const FastConst& fc, int O, const BinConst* __restrict__ bins, float delta_ref,
+                                float w2_ref, const float (&W)[kM], PairOut& out) {
+    F2 mu[kK], img[kM], am1[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) mu[k] = mul2(gyk[k], f2(gxh[k]));
+    img[0] = f2(s.b);
+    img[1] = add2(mu[0], f2(s.b));
+    img[2] = add2(mu[1], f2(s.b));
+    img[3] = add2(img[1], mu[1]);
+#pragma unroll
+    for (int m = 0; m < kM; ++m) am1[m] = fma2(img[m], f2(fc.rate), f2(-1.0f));
+    const F2 y_ref = sub2(D, f2(delta_ref)), l_ref = lg2_2(y_ref);
+    ManyBinSums sums;
+    sums.zero();
+#pragma unroll 2
+    for (int j = 0; j < O; ++j) many_bins_accumulate(D, l_ref, am1, bins[j], sums);
+    pixel_pair_finish_many(img, mu, y_ref, l_ref, w2_ref, sums, dx, dx2, dy, fc, W, out);
+}
+
+// per-bin constants for the form above; returns the reference bin (smallest offset)
+TQ_HD int many_bins_reference(int O, const float* off_s) {
+    int ref = 0;
+    for (int j = 1; j < O; ++j) if (off_s[j] < off_s[ref]) ref = j;
+    return ref;
+}
+TQ_HD BinConst many_bins_const(int j, int ref, const float* off_s, const float* off_w2, float rate2) {
+    BinConst b;
+    b.delta = off_s[j];
+    b.c = (off_w2[j] - off_w2[ref]) + rate2 * (off_s[j] - off_s[ref]);
+    b.dyc = off_s[ref] - off_s[j];
+    b.pad = 0.0f;
+    return b;
+}
+
 // ---- single offset bin (the simulator's data after merging its identical bins) ---------------------------------
 // With one bin the log-sum-exp is its only term; per pixel-configuration what is left is lgamma / digamma of
 // a = image/gain and a handful of FMAs.  The spot-free configuration has the SAME a = b/gain at every pixel, so

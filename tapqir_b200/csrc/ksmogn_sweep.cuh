@@ -158,6 +158,31 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
     finish_pair(po, fc.rate, out);
 }
 
+// the same pair mapping for O > 4 offset bins (ksmogn_fast.cuh: "many offset bins"); bins: per-bin constants in shared memory
+__device__ __forceinline__ void sweep_patch_pairs_many(const float* __restrict__ pix, int sub, const float* __restrict__ tab,
+                                                       const PatchSpots<float>& s, const FastConst& fc, int O,
+                                                       const BinConst* __restrict__ bins, float delta_ref, float w2_ref,
+                                                       const float (&W)[kM], PatchOut<float, kM>& out) {
+    const float4* col4 = reinterpret_cast<const float4*>(tab);
+    const float4* row4 = reinterpret_cast<const float4*>(tab + 14 * 8);
+    int col = sub, row = 0;
+    PairOut po;
+    po.zero();
+#pragma unroll 1
+    for (int t = 0; t < 13; ++t) {
+        if (row < 7) {
+            const float4 c0 = col4[col * 2], c1 = col4[col * 2 + 1], r0 = row4[row * 2], r1 = row4[row * 2 + 1];
+            const float gxh[kK] = {c0.x, c0.y}, dx[kK] = {c0.z, c0.w}, dx2[kK] = {c1.x, c1.y};
+            const F2 gyk[kK] = {F2{r0.x, r0.y}, F2{r0.z, r0.w}}, dy[kK] = {F2{r1.x, r1.y}, F2{r1.z, r1.w}};
+            const F2 D{pix[row * 14 + col], pix[(row + 7) * 14 + col]};
+            pixel_pair_many_bins(D, gxh, gyk, dx, dx2, dy, s, fc, O, bins, delta_ref, w2_ref, W, po);
+        }
+        col += 8;
+        if (col >= 14) { col -= 14; ++row; }
+    }
+    finish_pair(po, fc.rate, out);
+}
+
 // ---- streaming form of the production kernel -----------------------------------------------------------------
 // Persistent warps: every warp walks its own sequence of 4-patch groups and, while it sweeps one group, the next
 // group's pixels (49 x 8 B per patch) and its 15 per-patch scalars are already in flight into a per-slot staging

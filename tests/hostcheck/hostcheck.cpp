@@ -79,7 +79,33 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
             for (int j = 1; j < O; ++j) max_off = std::max(max_off, off_s[j]);
             for (int p = 0; p < P * P; ++p) pairs = pairs && value[u * P * P + p] > max_off;
         }
-        if (pairs && OC == 1) {
+        // O > 4 on a 14 x 14 patch: the one-pass many-bins form (every pixel above the smallest offset)
+        bool many = P == 14 && OC == 0 && O > 4 && !small;
+        if (many) {
+            float min_off = off_s[0];
+            for (int j = 1; j < O; ++j) min_off = std::min(min_off, off_s[j]);
+            for (int p = 0; p < P * P; ++p) many = many && value[u * P * P + p] > min_off;
+        }
+        if (many) {
+            const int ref = many_bins_reference(O, off_s);
+            std::vector<BinConst> bins(O);
+            for (int j = 0; j < O; ++j) bins[j] = many_bins_const(j, ref, off_s, w2.data(), fc.rate2);
+            PairOut po; po.zero();
+            for (int row = 0; row < 7; ++row)
+                for (int col = 0; col < 14; ++col) {
+                    float gxh[kK], dx[kK], dx2[kK]; F2 gyk[kK], dy[kK];
+                    for (int k = 0; k < kK; ++k) {
+                        gxh[k] = axis_factor<float>(col, s.cx[k], s.w[k]) * norm[k] * s.h[k];
+                        gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
+                        dx[k] = float(col) - s.cx[k];
+                        dx2[k] = dx[k] * dx[k];
+                        dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
+                    }
+                    const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
+                    pixel_pair_many_bins(D, gxh, gyk, dx, dx2, dy, s, fc, O, bins.data(), off_s[ref], w2[ref], Wm, po);
+                }
+            finish_pair(po, fc.rate, out);
+        } else if (pairs && OC == 1) {
             const SingleBinConst sc = single_bin_const(s.b, fc);
             PairOut1 po; po.zero();
             for (int row = 0; row < 7; ++row)
