@@ -311,6 +311,22 @@ int tq_step_advance(void* state, void* stream);
 int tq_peak_fma(int blocks, int iters, void* scratch, double* ops, void* stream);
 int tq_peak_mufu(int blocks, int iters, void* scratch, double* ops, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Post-fit statistics.  Central credible intervals of the guide distributions: what
+ * cosmos.compute_params (models/cosmos.py:711-784) obtains from scipy.stats.gamma / beta `.interval(CI)` through
+ * stats.torch_to_scipy_dist (utils/stats.py:262-293), for whole parameter arrays at once: n elements, all arrays
+ * DOUBLE device pointers, lo / hi = quantiles (1 -+ ci) / 2 of Gamma(conc, rate) resp. Beta(c1, c0) on [0, 1]
+ * (an AffineBeta's interval is low + scale * these; a Dirichlet's marginals are Beta(c_i, sum c - c_i)). */
+int tq_gamma_interval(int64_t n, const double* conc, const double* rate, double ci, double* lo, double* hi,
+                      void* stream);
+int tq_beta_interval(int64_t n, const double* c1, const double* c0, double ci, double* lo, double* hi,
+                     void* stream);
+/* stats.snr_and_chi2 (utils/stats.py:29-86) for U patches in store order: pixels (U, P, P) of `pixtype`
+ * (TQ_PIX_U16 / TQ_PIX_F32), xy (U, 2), height / width / x / y (2, U), background (U) float -> snr (2, U), chi2 (U). */
+int tq_snr_chi2(int64_t U, int P, int pixtype, const void* pixels, const void* xy, const void* height,
+                const void* width, const void* x, const void* y, const void* background, double gain,
+                double offset_mean, double offset_var, void* snr, void* chi2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

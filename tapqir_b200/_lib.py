@@ -92,6 +92,9 @@ SIGNATURES = {
     "tq_p2p_timed_out": (c_int, [_VP, POINTER(c_uint64)]),
     "tq_crop_aois": (c_int, [_VP, c_int, c_int, c_int, c_int, _VP, _VP, c_int, c_int, c_int, _VP, _VP, _VP, _VP]),
     "tq_offset_hist": (c_int, [_VP, c_int, c_int, c_int, c_int, c_int, c_int, _VP, _VP]),
+    "tq_gamma_interval": (c_int, [c_int64, _VP, _VP, c_double, _VP, _VP, _VP]),
+    "tq_beta_interval": (c_int, [c_int64, _VP, _VP, c_double, _VP, _VP, _VP]),
+    "tq_snr_chi2": (c_int, [c_int64, c_int, c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double, c_double, c_double, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),
     "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),

@@ -276,12 +276,12 @@ class cosmos(Model):
     def compute_params(self, CI):
         """
         Mean and ``CI`` credible interval of every guide distribution + the posterior summaries
-        (reference: cosmos.py:711-784; scipy inverse CDFs on the CPU as in stats.py:262-293).
+        (reference: cosmos.py:711-784; its scipy inverse CDFs, stats.py:262-293, evaluated on the device over whole arrays).
         """
         from tapqir_b200.utils.stats import credible_intervals
 
-        value = lambda name: self.param(name).detach().double().cpu()
-        params = credible_intervals(self.ci_params, value, self.data.P, self.priors, CI)
+        value = lambda name: self.param(name).detach().double()
+        params = credible_intervals(self.ci_params, value, self.data.P, self.priors, CI, self.device)
         params["m_probs"] = self.m_probs.cpu()
         params["z_probs"] = self.z_probs.cpu()
         params["theta_probs"] = self.theta_probs.cpu()

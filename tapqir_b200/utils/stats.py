@@ -3,8 +3,9 @@ Post-fit statistics with the reference's outputs (tapqir/utils/stats.py:29-293, 
 credible intervals of every guide distribution, SNR and chi2 per patch, classification metrics
 against simulation labels, and the files ``<name>_params.tpqr`` / ``.mat`` / ``<name>_summary.csv``.
 
-Like the reference this is CPU post-processing (scipy inverse CDFs, sklearn metrics); the
-per-patch rendering goes through the CUDA ``gaussian_spots``.  The rastergram PNGs of
+The two heavy parts run on the device (csrc/stats.cu): the inverse CDFs behind the credible intervals over whole
+(K, Nt, F, Q) arrays, and SNR / chi2 in one fused launch over the resident pixels; the classification metrics against
+simulation labels stay scipy / sklearn on a few thousand labels.  The rastergram PNGs of
 stats.py:110-128 need matplotlib (not a dependency here) and are skipped, as the reference does
 when the ``CI`` environment variable is set.
 """
@@ -15,8 +16,6 @@ from typing import Tuple
 
 import numpy as np
 import torch
-
-from tapqir_b200.distributions.util import gaussian_spots
 
 logger = logging.getLogger(__name__)
 
@@ -39,31 +38,29 @@ def hpdi(samples: torch.Tensor, prob: float) -> Tuple[torch.Tensor, torch.Tensor
     return s[i], s[i + mass]
 
 
-def guide_scipy_dist(name, value, P, priors):
+def guide_family(name, value, P, priors):
     """
-    ``(scipy frozen distribution, mean)`` of the guide of the latent ``name`` (``model.ci_params``), from the constrained
-    variational parameters ``value(param_name) -> CPU double tensor``.  Reference: the branches of ``compute_params``
-    (cosmos.py:713-772) followed by ``torch_to_scipy_dist`` (stats.py:262-293): Gamma(loc * beta, rate beta);
+    ``(family, p1, p2, low, scale, mean)`` of the guide of the latent ``name`` (``model.ci_params``) from the constrained
+    variational parameters ``value(param_name) -> double tensor``: family "gamma" (p1 = concentration, p2 = rate) or
+    "beta" (p1, p2 = concentrations on [0, 1]; the interval is ``low + scale * quantile``).  Reference: the branches of
+    ``compute_params`` (cosmos.py:713-772) with ``torch_to_scipy_dist`` (stats.py:262-293): Gamma(loc * beta, rate beta);
     Dirichlet(mean * size) summarised by its Beta marginals (``pi``; hmm's ``init`` and ``trans``); AffineBeta as a
     located and scaled Beta.
     """
     import math
 
-    import scipy.stats as st
-
     half = (P + 1) / 2
 
     def gamma(loc, beta):
-        return st.gamma((loc * beta).numpy(), scale=(1 / beta).numpy()), loc
+        return "gamma", loc * beta, beta, 0.0, 1.0, loc
 
     def affine_beta(mean, size, lo, hi):
-        c1, c0 = size * (mean - lo) / (hi - lo), size * (hi - mean) / (hi - lo)
-        return st.beta(a=c1.numpy(), b=c0.numpy(), loc=lo, scale=hi - lo), mean
+        return "beta", size * (mean - lo) / (hi - lo), size * (hi - mean) / (hi - lo), lo, hi - lo, mean
 
     if name in ("pi", "init", "trans"):
         conc = value(f"{name}_mean") * value(f"{name}_size")
         total = conc.sum(-1, keepdim=True)
-        return st.beta(a=conc.numpy(), b=(total - conc).numpy()), conc / total
+        return "beta", conc, total - conc, 0.0, 1.0, conc / total
     if name == "gain":
         return gamma(value("gain_loc"), value("gain_beta"))
     if name == "lamda":
@@ -83,32 +80,69 @@ def guide_scipy_dist(name, value, P, priors):
     raise NotImplementedError(f"no credible interval for '{name}'")
 
 
-def credible_intervals(ci_params, value, P, priors, CI):
-    """``{name: {"LL", "UL", "Mean"}}`` for every latent in ``ci_params`` (cosmos.py:773-778)."""
+def credible_intervals(ci_params, value, P, priors, CI, device):
+    """
+    ``{name: {"LL", "UL", "Mean"}}`` (CPU double tensors) for every latent in ``ci_params`` (cosmos.py:773-778): the
+    inverse CDFs of the Gamma / Beta guides evaluated on ``device`` over whole parameter arrays
+    (``tq_gamma_interval`` / ``tq_beta_interval``, csrc/stats.cu) -- the reference goes through scipy element by element
+    on the CPU (stats.py:262-293), 90 M inverse incomplete gamma / beta evaluations at 1000 AOIs x 5000 frames.
+    """
+    from tapqir_b200 import _lib
+
+    lib = _lib.load()
+    device = torch.device(device)
     out = {}
-    for name in ci_params:
-        dist, mean = guide_scipy_dist(name, value, P, priors)
-        LL, UL = dist.interval(CI)
-        out[name] = {"LL": torch.as_tensor(LL), "UL": torch.as_tensor(UL), "Mean": mean}
+    with torch.cuda.device(device):
+        st = _lib.stream_ptr(device)
+        for name in ci_params:
+            family, p1, p2, low, scale, mean = guide_family(name, value, P, priors)
+            shape = p1.shape
+            a = p1.to(device=device, dtype=torch.float64).reshape(-1).contiguous()
+            b = p2.to(device=device, dtype=torch.float64).expand(shape).reshape(-1).contiguous()
+            lo, hi = torch.empty_like(a), torch.empty_like(a)
+            fn = lib.tq_gamma_interval if family == "gamma" else lib.tq_beta_interval
+            _lib.check(fn(a.numel(), _lib.ptr(a), _lib.ptr(b), float(CI), _lib.ptr(lo), _lib.ptr(hi), st), f"interval({name})")
+            out[name] = {"LL": (low + scale * lo).reshape(shape).cpu(), "UL": (low + scale * hi).reshape(shape).cpu(),
+                         "Mean": mean.detach().double().cpu()}
     return out
 
 
 def snr_and_chi2(data, height, width, x, y, target_locs, background, gain, offset_mean, offset_var, P,
                  theta_probs) -> Tuple[torch.Tensor, torch.Tensor]:
     r"""
-    Signal-to-noise ratio and chi2 of the fitted spots (reference: stats.py:29-86).
+    Signal-to-noise ratio and chi2 of the fitted spots (reference: stats.py:29-86), one fused kernel over all patches
+    (``tq_snr_chi2``: separable spot factors, no (K, n, F, Q, P, P) temporaries).
 
     .. math:: \text{SNR}_{knf} = \frac{\sum_{ij} (D_{nfij} - b_{nf} - \mu_{offset})\,\mathcal N_{ij}}
               {\sqrt{\sigma^2_{offset} + b_{nf}\, g}}
+
+    ``data``: CUDA pixels ``(..., P, P)``, uint16 or float32 (the device store's own buffer works); spot parameters
+    ``(K, ...)`` and ``background (...)`` CUDA tensors, spots stacked along the FIRST axis; ``target_locs (..., 2)``.
+    Returns ``snr (K, ...)`` and ``chi2 (...)`` as float32 CUDA tensors.
     """
-    gaussians = gaussian_spots(height, width, x, y, target_locs, P)
-    weights = gaussians / height[..., None, None]
-    signal = ((data - background[..., None, None] - offset_mean) * weights).sum(dim=(-2, -1))
-    noise = (offset_var + background * gain).sqrt()
-    # spots are stacked along the FIRST axis: (K, F, Q) per AOI in the reference (its sum(-5)), (K, n, F, Q) here
-    img_ideal = background[..., None, None] + gaussians.sum(0)
-    chi2 = (data - img_ideal - offset_mean) ** 2 / img_ideal
-    return signal / noise, chi2.mean(dim=(-1, -2))
+    from tapqir_b200 import _lib
+
+    lib = _lib.load()
+    dev = data.device
+    batch = tuple(background.shape)
+    U = int(np.prod(batch)) if batch else 1
+    K = height.shape[0]
+    if K != 2:
+        raise NotImplementedError("tq_snr_chi2 is built for K = 2")
+    if data.dtype not in (torch.uint16, torch.float32):
+        data = data.to(torch.float32)
+    spot = lambda t: t.to(device=dev, dtype=torch.float32).reshape(K, U).contiguous()
+    pix = data.reshape(U, P, P).contiguous()
+    xy = target_locs.to(device=dev, dtype=torch.float32).reshape(U, 2).contiguous()
+    b = background.to(device=dev, dtype=torch.float32).reshape(U).contiguous()
+    h, w, xs, ys = spot(height), spot(width), spot(x), spot(y)
+    snr = torch.empty(K, U, dtype=torch.float32, device=dev)
+    chi2 = torch.empty(U, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.tq_snr_chi2(U, int(P), _lib.pix_code(pix.dtype), _lib.ptr(pix), _lib.ptr(xy), _lib.ptr(h), _lib.ptr(w),
+                                   _lib.ptr(xs), _lib.ptr(ys), _lib.ptr(b), float(gain), float(offset_mean), float(offset_var),
+                                   _lib.ptr(snr), _lib.ptr(chi2), _lib.stream_ptr(dev)), "tq_snr_chi2")
+    return snr.reshape((K,) + batch), chi2.reshape(batch)
 
 
 def save_stats(model, path, CI=0.95, save_matlab=False):
@@ -143,18 +177,14 @@ def save_stats(model, path, CI=0.95, save_matlab=False):
     logger.info("- SNR and Chi2-test")
     data, dev = model.data, model.device
     Nt, F, Q, K = data.Nt, data.F, model.Q, model.K
-    snr = torch.zeros(K, Nt, F, Q)
-    chi2 = torch.zeros(Nt, F, Q)
+    # one launch over the pixels already resident on the device (the reference loops over AOIs in Python, stats.py:193-215)
+    store = model.engine.store if model.engine is not None else data.device_store(dev, torch.float32)
     to = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32)
-    chunk = max(1, (1 << 22) // max(F * Q * K, 1))
-    for lo in range(0, Nt, chunk):  # AOI blocks instead of the reference's per-AOI Python loop
-        sl = slice(lo, min(lo + chunk, Nt))
-        s, c = snr_and_chi2(
-            to(data.images[sl]), to(ci_stats["height"]["Mean"][:, sl]), to(ci_stats["width"]["Mean"][:, sl]),
-            to(ci_stats["x"]["Mean"][:, sl]), to(ci_stats["y"]["Mean"][:, sl]), to(data.xy[sl]),
-            to(ci_stats["background"]["Mean"][sl]), float(ci_stats["gain"]["Mean"]), data.offset.mean, data.offset.var,
-            data.P, None)
-        snr[:, sl], chi2[sl] = s.cpu(), c.cpu()
+    snr, chi2 = snr_and_chi2(
+        store.pixels, to(ci_stats["height"]["Mean"]), to(ci_stats["width"]["Mean"]), to(ci_stats["x"]["Mean"]),
+        to(ci_stats["y"]["Mean"]), store.xy, to(ci_stats["background"]["Mean"]), float(ci_stats["gain"]["Mean"]),
+        data.offset.mean, data.offset.var, data.P, None)
+    snr, chi2 = snr.cpu(), chi2.cpu()
     for q in range(Q):
         masked = snr[..., q][ci_stats["theta_probs"][..., q] > 0.5]
         summary.loc[f"SNR_{q}", "Mean"] = masked.mean().item() if masked.numel() else float("nan")

@@ -308,6 +308,7 @@ double cosmos_step_host(int nb, int fb, int Nt, int F_, int C, int P, int O, con
 // ---- hmm variant: the same device functions (cosmos_hmm.cuh, cosmos_globals.cuh with the hmm layout) in the order the
 // kernels of csrc/cosmos_step.cu run them; the chain recursions are walked frame by frame here (the kernels scan them).
 #include "cosmos_hmm.cuh"
+#include "stats_math.cuh"
 
 namespace {
 
@@ -600,6 +601,22 @@ void hc_site_draws_fast(int s, float u0, float u1, const ModelConst* mc, uint64_
         float recf[NSO], exf[NEX], v = 0.0f;
         const int status = site_eval_fast(s, u0, u1, 0.0f, 0.0f, *mc, true, &rng, variate, v, recf, exf);
         out[i] = status == SITE_DONE ? (double)v : site_eval(s, u0, u1, 0.0, 0.0, *mc, status == SITE_FALLBACK_DRAW, &rng, variate, rec, ex);
+    }
+}
+}
+
+// ---- inverse CDFs of the credible intervals (stats_math.cuh) ------------------------------------------------------------
+extern "C" {
+void hc_gamma_interval(int64_t n, const double* conc, const double* rate, double ci, double* lo, double* hi) {
+    for (int64_t i = 0; i < n; ++i) {
+        lo[i] = tq::gamma_p_inv(0.5 * (1.0 - ci), conc[i]) / rate[i];
+        hi[i] = tq::gamma_p_inv(0.5 * (1.0 + ci), conc[i]) / rate[i];
+    }
+}
+void hc_beta_interval(int64_t n, const double* c1, const double* c0, double ci, double* lo, double* hi) {
+    for (int64_t i = 0; i < n; ++i) {
+        lo[i] = tq::beta_i_inv(0.5 * (1.0 - ci), c1[i], c0[i]);
+        hi[i] = tq::beta_i_inv(0.5 * (1.0 + ci), c1[i], c0[i]);
     }
 }
 }
