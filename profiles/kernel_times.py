@@ -13,7 +13,7 @@ from tapqir_b200.models.cosmos import cosmos  # noqa: E402
 workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda", 0)
-ds, nb, fb, desc = bench.make_shard(workload, 0, dev)
+ds, nb, fb, desc = bench.make_shard(workload, 0, 1, dev)
 model = cosmos(device="cuda:0", dtype="float")
 model.data = ds
 model.init(nbatch_size=nb, fbatch_size=fb)
