@@ -148,6 +148,11 @@ int tq_cosmos_fused_step(int dtype, const tq_patch_view* view, int64_t Nt, const
  * initialise to arange once).  out: (n_pick,) int32.  stream_id separates independent draws. */
 int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* state, uint64_t stream_id,
                  void* perm, void* out, void* stream);
+/* The AOI and the frame draw of one step in one launch (same keys as two tq_subsample calls: identical results); both
+ * axes <= 16384 entries (tq_subsample_pair_supported). */
+int tq_subsample_pair_supported(int n_total0, int n_total1);
+int tq_subsample_pair(int n_total0, int n_pick0, uint64_t stream_id0, void* out0, int n_total1, int n_pick1,
+                      uint64_t stream_id1, void* out1, uint64_t seed, const void* state, void* stream);
 
 /* Guide samples of the four global sites (cosmos.py:342-368) and the prior tables derived from
  * them (distributions/util.py:67-173).  gparams: global flat buffer, ALWAYS float64 (as are ggrads and the

@@ -100,6 +100,8 @@ SIGNATURES = {
     "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
     "tq_peak_mufu": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
     "tq_subsample": (c_int, [c_int, c_int, c_uint64, _VP, c_uint64, _VP, _VP, _VP]),
+    "tq_subsample_pair_supported": (c_int, [c_int, c_int]),
+    "tq_subsample_pair": (c_int, [c_int, c_int, c_uint64, _VP, c_int, c_int, c_uint64, _VP, c_uint64, _VP, _VP]),
 }
 
 _lib = None

@@ -67,29 +67,43 @@ __device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int 
 }
 
 // (8 resident blocks per SM = 64 registers, no spills: 5 us faster on a trained model than 6 blocks at 71 registers)
+// A block takes kSiteUPT x 128 consecutive units of one site: with 128 a trained model's deferred sites (a quarter of
+// them, four regime classes) left each class with a handful of sites per block -- partially filled warps in pass 2
+// (20 of 32 lanes per instruction over the kernel); four times the units fill them.
+#ifndef TQ_SITE_UPT
+#define TQ_SITE_UPT 4
+#endif
+constexpr int kSiteUPT = TQ_SITE_UPT;
+constexpr int kSiteSpan = kLocalBlock * kSiteUPT;
 __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalArgs<float> a) {
-    __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1];
-    __shared__ double s_var[kLocalBlock];
-    __shared__ unsigned char s_idx[kLocalBlock];
-    static_assert(kLocalBlock <= 256, "thread index stored in a byte");
+    __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1], fill[kSiteClasses], n_def;
+    __shared__ double t_var[kSiteSpan], s_var[kSiteSpan];
+    __shared__ unsigned short t_idx[kSiteSpan], s_idx[kSiteSpan];
+    __shared__ unsigned char t_cls[kSiteSpan];
     const int s = blockIdx.y;
-    const uint32_t base = blockIdx.x * (uint32_t)kLocalBlock, u32 = base + threadIdx.x;
-    if (threadIdx.x < kSiteClasses) cnt[threadIdx.x] = 0u;
+    const uint32_t base = blockIdx.x * (uint32_t)kSiteSpan;
+    if (threadIdx.x < kSiteClasses) { cnt[threadIdx.x] = 0u; fill[threadIdx.x] = 0u; }
+    if (threadIdx.x == 0) n_def = 0u;
     __syncthreads();
-    int cls = 0;
-    unsigned int rank = 0u;
+    const bool use_rng = a.noise_in == nullptr;
     bool deferred = false;
-    double variate = 0.0;
-    if (u32 < (uint32_t)a.U) {
+#pragma unroll 1
+    for (int j = 0; j < kSiteUPT; ++j) {
+        const uint32_t local = (uint32_t)j * kLocalBlock + threadIdx.x, u32 = base + local;
+        if (u32 >= (uint32_t)a.U) break;
         const SiteInputs<float> in = site_gather(a, s, u32);
-        const bool use_rng = a.noise_in == nullptr;
         Philox rng(a.seed, a.state->step, in.rng_offset);
-        if (!use_rng) variate = (double)a.noise_in[(int64_t)s * a.U + u32];
+        double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
         float v = 0.0f, rec[NSO], extra[NEX];
+        int cls = 0;
         const int status = site_eval_fast_t<1>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra, cls);
         if (status == SITE_DEFER) {
             deferred = true;
-            rank = atomicAdd(&cnt[cls], 1u);
+            const unsigned int pos = atomicAdd(&n_def, 1u);
+            atomicAdd(&cnt[cls], 1u);
+            t_var[pos] = variate;
+            t_idx[pos] = (unsigned short)local;
+            t_cls[pos] = (unsigned char)cls;
         } else {
             site_fast_finish(a, s, u32, status, v, rec, extra);
         }
@@ -103,17 +117,20 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
         off[kSiteClasses] = acc;
     }
     __syncthreads();
-    if (deferred) {
-        const unsigned int pos = off[cls] + rank;
-        s_var[pos] = variate;
-        s_idx[pos] = (unsigned char)threadIdx.x;
+    const unsigned int total = off[kSiteClasses];
+    for (unsigned int i = threadIdx.x; i < total; i += kLocalBlock) {   // counting sort by regime class
+        const int c = t_cls[i];
+        const unsigned int pos = off[c] + atomicAdd(&fill[c], 1u);
+        s_var[pos] = t_var[i];
+        s_idx[pos] = t_idx[i];
     }
     __syncthreads();
-    if (threadIdx.x < off[kSiteClasses]) {
-        const uint32_t u = base + s_idx[threadIdx.x];
+    for (unsigned int i = threadIdx.x; i < total; i += kLocalBlock) {
+        const uint32_t u = base + s_idx[i];
         const SiteInputs<float> in = site_gather(a, s, u);
-        double var = s_var[threadIdx.x];
+        double var = s_var[i];
         float v = 0.0f, rec[NSO], extra[NEX];
+        int cls = 0;
         const int status = site_eval_fast_t<2>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, false, nullptr, var, v, rec, extra, cls);
         site_fast_finish(a, s, u, status, v, rec, extra);
     }
@@ -778,7 +795,7 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
             int stm = cuda_status(cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work_count)");
             if (stm != TQ_OK) return stm;
         }
-        site_fast_kernel<<<grid, kLocalBlock, 0, st>>>(a);
+        site_fast_kernel<<<dim3((unsigned)((a.U + kSiteSpan - 1) / kSiteSpan), NSAMP), kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fast_kernel launch");
         if (ws) {
             site_worklist_kernel<<<sm_count() * 8, kLocalBlock, 0, st>>>(a);
@@ -1163,6 +1180,32 @@ __global__ void __launch_bounds__(kSubsampleBlock) subsample_rank_kernel(int n_t
     if (rank < n_pick) out[rank] = i;
 }
 
+// the AOI and the frame draw of one step in ONE launch (blockIdx.y selects the axis): the reference-default minibatch
+// step is launch-latency bound, and the two draws head its critical path
+struct SubsampleAxis { int n_total, n_pick; unsigned long long stream_id; int32_t* out; };
+__global__ void __launch_bounds__(kSubsampleBlock) subsample_rank_pair_kernel(SubsampleAxis ax0, SubsampleAxis ax1, unsigned long long seed,
+                                                                              const StepState* state) {
+    extern __shared__ unsigned int keys[];
+    const SubsampleAxis ax = blockIdx.y == 0 ? ax0 : ax1;
+    if ((int)(blockIdx.x * kSubsampleBlock) >= ax.n_total) return;
+    const unsigned long long sd = seed ^ (0x9E3779B97F4A7C15ull * (ax.stream_id + 1ull)), step = state->step;
+    for (int j = threadIdx.x; j < ax.n_total; j += kSubsampleBlock) {
+        Philox rng(sd, step, (unsigned long long)j);
+        keys[j] = rng.next();
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kSubsampleBlock + threadIdx.x;
+    if (i >= ax.n_total) return;
+    const unsigned int ki = keys[i];
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < ax.n_total; ++j) {
+        const unsigned int kj = keys[j];
+        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    if (rank < ax.n_pick) ax.out[rank] = i;
+}
+
 __global__ void subsample_kernel(int n_total, int n_pick, unsigned long long seed, const StepState* state,
                                  unsigned long long stream_id, int32_t* __restrict__ perm, int32_t* __restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -1201,5 +1244,30 @@ extern "C" int tq_subsample(int n_total, int n_pick, uint64_t seed, const void* 
     tq::subsample_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(n_total, n_pick, seed, (const tq::StepState*)state, stream_id,
                                                           (int32_t*)perm, (int32_t*)out);
     TQ_LAUNCH_CHECK("subsample_kernel launch");
+    return TQ_OK;
+}
+
+// Two independent draws (tq_subsample semantics, same keys: identical results) in one launch; both axes must be
+// <= 16384 long (tq_subsample_pair_supported), else call tq_subsample twice.
+extern "C" int tq_subsample_pair_supported(int n_total0, int n_total1) {
+    return n_total0 >= 1 && n_total1 >= 1 && n_total0 <= tq::kSubsampleMaxRank && n_total1 <= tq::kSubsampleMaxRank ? 1 : 0;
+}
+extern "C" int tq_subsample_pair(int n_total0, int n_pick0, uint64_t stream_id0, void* out0, int n_total1, int n_pick1,
+                                 uint64_t stream_id1, void* out1, uint64_t seed, const void* state, void* stream) {
+    TQ_CHECK_ARG(tq_subsample_pair_supported(n_total0, n_total1), "axes must hold 1..16384 entries");
+    TQ_CHECK_ARG(n_pick0 >= 1 && n_pick0 <= n_total0 && n_pick1 >= 1 && n_pick1 <= n_total1, "bad sizes");
+    TQ_CHECK_ARG(state && out0 && out1, "NULL pointer");
+    const int n_max = n_total0 > n_total1 ? n_total0 : n_total1;
+    const size_t smem = sizeof(unsigned int) * (size_t)n_max;
+    if (smem > 48 * 1024) {
+        int st2 = tq::cuda_status(cudaFuncSetAttribute(tq::subsample_rank_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                  "cudaFuncSetAttribute(subsample_rank_pair)");
+        if (st2 != TQ_OK) return st2;
+    }
+    const dim3 grid((n_max + tq::kSubsampleBlock - 1) / tq::kSubsampleBlock, 2);
+    tq::subsample_rank_pair_kernel<<<grid, tq::kSubsampleBlock, smem, (cudaStream_t)stream>>>(
+        tq::SubsampleAxis{n_total0, n_pick0, stream_id0, (int32_t*)out0}, tq::SubsampleAxis{n_total1, n_pick1, stream_id1, (int32_t*)out1},
+        seed, (const tq::StepState*)state);
+    TQ_LAUNCH_CHECK("subsample_rank_pair_kernel launch");
     return TQ_OK;
 }

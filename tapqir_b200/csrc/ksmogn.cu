@@ -11,6 +11,7 @@
 #include "ksmogn_core.cuh"
 #include "ksmogn_fast.cuh"
 #include "ksmogn_sweep.cuh"
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -22,6 +23,7 @@ template <typename T> struct KsmognArgs {
     const T* gain; const T* mcfg; const T* W;
     T* logp; T* g_height; T* g_width; T* g_x; T* g_y; T* g_background; T* g_rate;
     int64_t U;
+    int bulk;   // stream kernel, uint16 14 x 14 patches: stage the pixels with 1-D bulk copies (pixel base 16-byte aligned)
 };
 
 template <typename PIX> __device__ __forceinline__ float load_pixel_f(const PIX* p) { return (float)*p; }
@@ -151,6 +153,13 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     float* spx = reinterpret_cast<float*>(smem_raw) + offpad + kUnitsPerBlock * kTabFloats + slot * PP;
     unsigned char* stage = reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(smem_raw) + offpad + kUnitsPerBlock * (kTabFloats + PP))
                            + slot * stage_bytes<PF>();
+    // one mbarrier per patch slot behind the staging areas (bulk-copy staging)
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<unsigned char*>(reinterpret_cast<float*>(smem_raw) + offpad + kUnitsPerBlock * (kTabFloats + PP))
+        + kUnitsPerBlock * stage_bytes<PF>()) + slot;
+    const bool bulk = PF && a.bulk != 0;
+    if (bulk && sub == 0) mbar_init(bar, 1u);
+    if (bulk) mbar_fence_init();
     for (int j = threadIdx.x; j < O; j += blockDim.x) {
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
         off_w2[j] = static_cast<const float*>(a.v.offset_logits)[j] * kLog2e;
@@ -177,10 +186,28 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     const unsigned stride = gridDim.x * kWarpsPerBlock;
 
     // issue the copies of group g: this lane's share of its slot's patch and two of the slot's 15 scalars
+    unsigned pix_off = 0u, pix_off_next = 0u, phase = 0u;   // bulk staging: where the patch starts in its slot; mbarrier phase
     auto prefetch = [&](unsigned g) {
         const unsigned u_raw = g * 4u + wslot, u = u_raw < U ? u_raw : U - 1u;
         const UnitIndex ui = locate_unit32(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
-        if (PF) {
+        if (PF && bulk) {
+            // 392 B at an 8-byte stride: odd patches start 8 bytes off a 16-byte boundary.  The 384 aligned bytes go by
+            // one bulk copy, the other 8 (head of an odd patch, tail of an even one) by one cp.async; the patch lands
+            // at offset 0 (even) or 8 (odd) of the slot's pixel area so that the bulk destination is aligned too.
+            pix_off_next = (unsigned)(ui.patch & 1) * 8u;
+            if (sub == 0) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(pixels + ui.patch * 196);
+                unsigned char* dst = stage + kParFloats * 4;
+                mbar_expect_tx(bar, 384u);
+                if (pix_off_next) {
+                    cp_async_8(dst + 8, src);
+                    bulk_copy_g2s(dst + 16, src + 8, 384u, bar);
+                } else {
+                    bulk_copy_g2s(dst, src, 384u, bar);
+                    cp_async_8(dst + 384, src + 384);
+                }
+            }
+        } else if (PF) {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(pixels + ui.patch * 196);
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
@@ -210,13 +237,19 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     // counts the groups handed out beyond the first `stride`
     unsigned cur = blockIdx.x * kWarpsPerBlock + warp, pending = 0;
     if (lane == 0) pending = stride + atomicAdd(counters, 1u);
+    __syncthreads();   // mbarriers initialised before the first copy can complete on them
     if (cur < n_wg) prefetch(cur);
 
     while (cur < n_wg) {
         const unsigned u_raw = cur * 4u + wslot;
         const bool live = u_raw < U;
         const unsigned u = live ? u_raw : U - 1u;   // idle slots shadow the last patch and write nothing
+        pix_off = pix_off_next;
         cp_async_wait_all();
+        if (bulk) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
         __syncwarp();
         PatchSpots<float> s;
         float W[kM], Wr[kM], tx, ty;
@@ -233,7 +266,7 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
         for (int m = 0; m < kM; ++m) Wr[m] = W[m] * fc.rate;
         float pix_min = 3.0e38f;   // smallest pixel of the patch (this lane's share): selects the no-clamp pair form
         if (PF) {
-            const uint2* raw = reinterpret_cast<const uint2*>(stage + kParFloats * 4);
+            const uint2* raw = reinterpret_cast<const uint2*>(stage + kParFloats * 4 + pix_off);
 #pragma unroll
             for (int t = 0; t < 7; ++t) {
                 const int i = sub + t * kSub;
@@ -360,7 +393,7 @@ static int launch_fast(const KsmognArgs<float>& a, cudaStream_t st) {
     }
     const int PP = a.v.P * a.v.P, offpad = ((2 * a.v.O + 3) & ~3) + (OC == 0 && P14 && BWD ? 4 * a.v.O : 0);
     const size_t smem = sizeof(float) * ((size_t)offpad + kUnitsPerBlock * (kTabFloats + (size_t)PP)) +
-                        (size_t)kUnitsPerBlock * stage_bytes<PF>();
+                        (size_t)kUnitsPerBlock * stage_bytes<PF>() + (size_t)kUnitsPerBlock * sizeof(unsigned long long);
     auto kern = ksmogn_stream_kernel<PIX, OC, P14, BWD, MINB>;
     if (smem > 48 * 1024) {
         int st2 = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -449,6 +482,7 @@ static int run_ksmogn(const tq_patch_view* view, const void* height, const void*
     a.g_height = (T*)g_height; a.g_width = (T*)g_width; a.g_x = (T*)g_x; a.g_y = (T*)g_y;
     a.g_background = (T*)g_background; a.g_rate = (T*)g_rate;
     a.U = (int64_t)view->nb * view->fb * view->C;
+    a.bulk = ((uintptr_t)view->pixels % 16 == 0 && !getenv("TQ_NO_BULK")) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     bool handled = false;
     const int fst = try_fast<BWD>(a, NM, st, handled);

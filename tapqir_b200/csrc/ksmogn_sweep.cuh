@@ -196,6 +196,35 @@ __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- 1-D bulk copies (TMA, cp.async.bulk -> SASS UBLKCP) completing on an mbarrier ------------------------------------------
+// One elected lane per patch slot moves the patch's pixels with ONE instruction instead of seven 8-byte cp.async per lane
+// of the slot.  A bulk copy needs 16-byte aligned addresses and sizes; a 14 x 14 uint16 patch is 392 B at an 8-byte
+// stride, so the copy takes the 384 bytes of the patch that ARE 16-byte aligned and one 8-byte cp.async the remaining
+// head (odd patches) or tail (even patches) -- exact bytes, nothing read beyond the patch.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// wait for phase `parity`; a copy that never lands (a bug, not a data condition) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
+}
+
 constexpr int kParFloats = 16;   // h0 h1 w0 w1 x0 x1 y0 y1 | b W0 W1 W2 | W3 tx ty -
 template <bool PF> constexpr int stage_bytes() { return kParFloats * 4 + (PF ? 400 : 0); }   // 392 B of pixels, 16 B aligned slots
 

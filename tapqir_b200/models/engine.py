@@ -190,6 +190,12 @@ class CosmosEngine:
         p = _lib.ptr
         mc = ctypes.byref(self.mc)
         with torch.cuda.device(self.device):
+            if (ndx is None and not self.full_n and fdx is None and not self.full_f
+                    and lib.tq_subsample_pair_supported(self.Nt, self.F)):
+                # both draws in one launch (the same frame subset on every rank: its stream id does not depend on the rank)
+                _lib.check(lib.tq_subsample_pair(self.Nt, self.nb, 2 + self.rank, p(self.ndx), self.F, self.fb, 1, p(self.fdx),
+                                                 self.seed, p(self.state), st), "tq_subsample_pair")
+                ndx, fdx = self.ndx, self.fdx
             if ndx is None and not self.full_n:
                 _lib.check(lib.tq_subsample(self.Nt, self.nb, self.seed, p(self.state), 2 + self.rank, p(self.perm_n),
                                             p(self.ndx), st), "tq_subsample")

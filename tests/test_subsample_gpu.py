@@ -46,3 +46,20 @@ def test_every_index_and_every_position_is_equally_likely():
     p = n_pick / n_total
     assert np.abs(hits / reps - p).max() < 5 * np.sqrt(p * (1 - p) / reps)
     assert np.abs(first / reps - 1 / n_total).max() < 5 * np.sqrt((1 / n_total) / reps)
+
+
+@pytest.mark.parametrize("sizes", [((100, 10), (1000, 512)), ((7, 3), (5, 5)), ((16384, 40), (300, 300))])
+def test_pair_launch_draws_the_same_indices_as_two_launches(sizes):
+    """tq_subsample_pair (both axes of a step in one launch) = two tq_subsample calls, index for index."""
+    from tapqir_b200 import _lib
+
+    lib, p = _lib.load(), _lib.ptr
+    dev = torch.device("cuda")
+    (n0, k0), (n1, k1) = sizes
+    assert lib.tq_subsample_pair_supported(n0, n1) == 1 and lib.tq_subsample_pair_supported(20000, 10) == 0
+    state = torch.tensor([17], dtype=torch.int64, device=dev)
+    out0 = torch.full((k0,), -1, dtype=torch.int32, device=dev)
+    out1 = torch.full((k1,), -1, dtype=torch.int32, device=dev)
+    _lib.check(lib.tq_subsample_pair(n0, k0, 2, p(out0), n1, k1, 1, p(out1), 5, p(state), _lib.stream_ptr(dev)), "tq_subsample_pair")
+    torch.cuda.synchronize()
+    assert (out0.cpu().numpy() == draw(n0, k0, 5, 17, 2)).all() and (out1.cpu().numpy() == draw(n1, k1, 5, 17, 1)).all()
