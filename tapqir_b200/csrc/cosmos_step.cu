@@ -70,12 +70,11 @@ __device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int 
 // A block takes kSiteUPT x 128 consecutive units of one site: with 128 a trained model's deferred sites (a quarter of
 // them, four regime classes) left each class with a handful of sites per block -- partially filled warps in pass 2
 // (20 of 32 lanes per instruction over the kernel); four times the units fill them.
-#ifndef TQ_SITE_UPT
-#define TQ_SITE_UPT 4
-#endif
-constexpr int kSiteUPT = TQ_SITE_UPT;
-constexpr int kSiteSpan = kLocalBlock * kSiteUPT;
+// Measured (B200, profiles/r2_bulk_ab.sh): C3 (5 M units) step 6.48 -> 6.40 ms, after 1000 iterations 7.09 -> 6.95 ms;
+// at C2 (100 k units) the four-times-smaller grid is 1.5 waves and 5 % slower, so small launches keep one unit per thread.
+template <int kSiteUPT>
 __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalArgs<float> a) {
+    constexpr int kSiteSpan = kLocalBlock * kSiteUPT;
     __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1], fill[kSiteClasses], n_def;
     __shared__ double t_var[kSiteSpan], s_var[kSiteSpan];
     __shared__ unsigned short t_idx[kSiteSpan], s_idx[kSiteSpan];
@@ -795,7 +794,12 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
             int stm = cuda_status(cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work_count)");
             if (stm != TQ_OK) return stm;
         }
-        site_fast_kernel<<<dim3((unsigned)((a.U + kSiteSpan - 1) / kSiteSpan), NSAMP), kLocalBlock, 0, st>>>(a);
+        // four units per thread once the grid still covers the GPU several times over (>= 4 waves of 8 blocks per SM)
+        const int64_t blocks4 = (a.U + 4 * kLocalBlock - 1) / (4 * kLocalBlock);
+        if (blocks4 * NSAMP >= (int64_t)sm_count() * 8 * 4)
+            site_fast_kernel<4><<<dim3((unsigned)blocks4, NSAMP), kLocalBlock, 0, st>>>(a);
+        else
+            site_fast_kernel<1><<<grid, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fast_kernel launch");
         if (ws) {
             site_worklist_kernel<<<sm_count() * 8, kLocalBlock, 0, st>>>(a);

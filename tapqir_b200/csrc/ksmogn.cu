@@ -482,7 +482,12 @@ static int run_ksmogn(const tq_patch_view* view, const void* height, const void*
     a.g_height = (T*)g_height; a.g_width = (T*)g_width; a.g_x = (T*)g_x; a.g_y = (T*)g_y;
     a.g_background = (T*)g_background; a.g_rate = (T*)g_rate;
     a.U = (int64_t)view->nb * view->fb * view->C;
-    a.bulk = ((uintptr_t)view->pixels % 16 == 0 && !getenv("TQ_NO_BULK")) ? 1 : 0;
+    // TQ_BULK=1: stage the pixels with 1-D bulk copies (TMA) instead of seven 8-byte cp.async per lane.  Correct
+    // (tests/test_ksmogn_gpu.py) and measured 1 % SLOWER on a B200 (C3 kernel 3.85 vs 3.81 ms, profiles/r2_bulk_ab.sh): a
+    // 392-byte patch at an 8-byte stride needs a bulk copy plus an 8-byte cp.async anyway, and the mbarrier wait costs more
+    // than cp.async.wait_all on copies that have long landed -- so cp.async stays the default.
+    const char* bulk_env = getenv("TQ_BULK");
+    a.bulk = ((uintptr_t)view->pixels % 16 == 0 && bulk_env && bulk_env[0] == '1') ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     bool handled = false;
     const int fst = try_fast<BWD>(a, NM, st, handled);
