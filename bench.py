@@ -90,6 +90,7 @@ def algorithmic_work(o_exec):
             "survey_8d": {"mufu_ops": 980 * o_exec + 3276, "fp32_flop": 8232 * o_exec + 63220}}
 
 
+ROUND1_LANE_OPS = {1: 98 * (2 * 85 + 14) + 600}   # what round 1's sweep executed per unit (single offset bin)
 HBM_BYTES_PER_UNIT = 604 + 504
 KSMOGN_HBM_BYTES_PER_UNIT = 392 + 8 + 4 * 9 + 4 * 4 + 4 * 4 + 4 * 10  # pixels, xy, samples, W in; L, grads out
 
@@ -286,7 +287,7 @@ def roofline_of(model, timer, peaks, hbm_peak, hbm_src, ms_per_step, steps, worl
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists():
-        t = json.loads(tj.read_text()).get({1: "ksmogn_stream_kernel", 3: "ksmogn_stream_kernel_o3"}.get(o_exec, "none"), {})
+        t = json.loads(tj.read_text()).get({1: f"ksmogn_stream_kernel_{workload}", 3: "ksmogn_stream_kernel_o3"}.get(o_exec, "none"), {})
         if t.get("workload") == workload and t.get("units_per_launch") == patches:
             traffic = {"dram_bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"],
                        "algorithmic_bytes_per_launch": KSMOGN_HBM_BYTES_PER_UNIT * patches, "source": t["source"]}
@@ -310,9 +311,11 @@ def roofline_of(model, timer, peaks, hbm_peak, hbm_src, ms_per_step, steps, worl
                     if bound[1] == "fp32" else "executed ops of the binding unit / kernel time / its measured peak",
             "frac_pipe_slots": "FP32-pipe lane operations (FMA, add, mul each one slot) / kernel time / measured lane-op peak: how busy the binding pipe is",
             "frac_survey_8d": "SURVEY 8(d)'s per-unit estimate at the executed number of offset bins / kernel time / peak (estimate written before the kernel: > 1 possible, the kernel needs less work than it assumes)",
+            "frac_round1_work_count": "round 1's accounting kept for continuity: ITS executed count (18632 FP32 lane operations per unit at one bin, every packed instruction as two FMAs) / kernel time / lane-op peak -- 0.49 at C2 and 0.62 at C3 in round 1; the kernel now needs 16182",
         },
         "frac_pipe_slots": units_per_s * max(t_pipe, t_mufu),
         "frac_survey_8d": units_per_s * t8,
+        "frac_round1_work_count": units_per_s * ROUND1_LANE_OPS.get(o_exec, 0) / fma_peak_ops if o_exec in ROUND1_LANE_OPS else None,
         "traffic": traffic, "kernel_ms": k_s * 1e3, "kernel_share_of_step": k_s * 1e3 / ms_per_step,
         "algorithmic_per_unit": dict(w, hbm_bytes=KSMOGN_HBM_BYTES_PER_UNIT, offset_bins_executed=o_exec),
         "peaks_measured_here": {"mufu_Tops": mufu_peak / 1e12, "fp32_TFLOPs": flop_peak / 1e12, "fp32_lane_Tops": fma_peak_ops / 1e12,
@@ -421,7 +424,8 @@ def run_native(args):
             subs[name] = {k: res[k] for k in keepk if k in res}
             r = res["roofline"]
             subs[name]["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "frac_pipe_slots",
-                                                        "frac_survey_8d", "kernel_ms", "kernel_share_of_step", "step_roofline_frac")}
+                                                        "frac_survey_8d", "frac_round1_work_count", "kernel_ms", "kernel_share_of_step",
+                                                        "step_roofline_frac")}
             m.engine.close()
             del m
             torch.cuda.empty_cache()
