@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(kFThreads, 4) cosmos_fused_kernel(const FusedA
 
             PatchOut<float, kM> out;
             out.zero();
-            if (pairs)
+            if (pairs && OC == 1)
+                sweep_patch_rows_single_bin(spx, sub, tab, s, fc, off_s[0], off_w2[0] * kLn2, W, out);
+            else if (pairs)
                 sweep_patch_pairs<OC>(spx, sub, tab, s, fc, off_s, off_w2, W, out);
             else if (__any_sync(kFull, small))
                 sweep_patch<OC, true, true, true>(spx, 14, 196, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);

@@ -312,6 +312,8 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
         out.zero();
         if (MANY && pairs)
             sweep_patch_pairs_many(spx, sub, tab, s, fc, O, bins, delta_ref, w2_ref, W, out);
+        else if (pairs && OC == 1)
+            sweep_patch_rows_single_bin(spx, sub, tab, s, fc, off_s[0], off_w2[0] * kLn2, W, out);
         else if (pairs)
             sweep_patch_pairs<OC>(spx, sub, tab, s, fc, off_s, off_w2, W, out);
         else if (__any_sync(kFull, small))

@@ -158,6 +158,37 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
     finish_pair(po, fc.rate, out);
 }
 
+// Single offset bin, ROW mapping: lane r < 7 of the patch's eight takes the row pair (r, r + 7) and walks the 14 columns.
+// Row factors and distances stay in registers for the whole patch, the column index is a compile-time constant (tables
+// and pixels at immediate offsets: no index arithmetic, no branch in the loop), and the y / dy^2 moments follow from the
+// height moment at the end of the row (single_bin_row_fixup).  14 trips of 75 packed + 18 other instructions against 13
+// trips of 79 + 41 in the (row, col) = (p / 14, p % 14) walk; the eighth lane idles through the sweep.
+__device__ __forceinline__ void sweep_patch_rows_single_bin(const float* __restrict__ pix, int sub, const float* __restrict__ tab,
+                                                            const PatchSpots<float>& s, const FastConst& fc, float off,
+                                                            float log_w, const float (&W)[kM], PatchOut<float, kM>& out) {
+    const SingleBinConst sc = single_bin_const(s.b, fc);
+    PairOut1 po;
+    po.zero();
+    int npix = 0;
+    if (sub < 7) {
+        const float4* col4 = reinterpret_cast<const float4*>(tab);
+        const float4* row4 = reinterpret_cast<const float4*>(tab + 14 * 8);
+        const float4 r0 = row4[sub * 2], r1 = row4[sub * 2 + 1];
+        const F2 gyk[kK] = {F2{r0.x, r0.y}, F2{r0.z, r0.w}}, dy[kK] = {F2{r1.x, r1.y}, F2{r1.z, r1.w}};
+        const float* p0 = pix + sub * 14;
+#pragma unroll
+        for (int c = 0; c < 14; ++c) {
+            const float4 c0 = col4[c * 2], c1 = col4[c * 2 + 1];
+            const float gxh[kK] = {c0.x, c0.y}, dx[kK] = {c0.z, c0.w}, dx2[kK] = {c1.x, c1.y};
+            const F2 D{p0[c], p0[c + 98]};
+            pixel_pair_single_bin<true>(D, gxh, gyk, dx, dx2, dy, s, fc, sc, off, W, po);
+        }
+        single_bin_row_fixup(po, dy);
+        npix = 28;
+    }
+    finish_single_bin(po, sc, fc, s.b, log_w, W[0], npix, out);
+}
+
 // the same pair mapping for O > 4 offset bins (ksmogn_fast.cuh: "many offset bins"); bins: per-bin constants in shared memory
 __device__ __forceinline__ void sweep_patch_pairs_many(const float* __restrict__ pix, int sub, const float* __restrict__ tab,
                                                        const PatchSpots<float>& s, const FastConst& fc, int O,
