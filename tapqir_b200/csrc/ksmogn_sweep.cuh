@@ -163,6 +163,10 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
 // and pixels at immediate offsets: no index arithmetic, no branch in the loop), and the y / dy^2 moments follow from the
 // height moment at the end of the row (single_bin_row_fixup).  14 trips of 75 packed + 18 other instructions against 13
 // trips of 79 + 41 in the (row, col) = (p / 14, p % 14) walk; the eighth lane idles through the sweep.
+#ifndef TQ_ROW_UNROLL
+#define TQ_ROW_UNROLL 7   // two trips of seven: the fully unrolled loop (21 KB) stalled on instruction fetch (C3 kernel 3.64 vs 3.58 ms)
+#endif
+constexpr int kRowUnroll = TQ_ROW_UNROLL;
 __device__ __forceinline__ void sweep_patch_rows_single_bin(const float* __restrict__ pix, int sub, const float* __restrict__ tab,
                                                             const PatchSpots<float>& s, const FastConst& fc, float off,
                                                             float log_w, const float (&W)[kM], PatchOut<float, kM>& out) {
@@ -176,7 +180,7 @@ __device__ __forceinline__ void sweep_patch_rows_single_bin(const float* __restr
         const float4 r0 = row4[sub * 2], r1 = row4[sub * 2 + 1];
         const F2 gyk[kK] = {F2{r0.x, r0.y}, F2{r0.z, r0.w}}, dy[kK] = {F2{r1.x, r1.y}, F2{r1.z, r1.w}};
         const float* p0 = pix + sub * 14;
-#pragma unroll
+#pragma unroll kRowUnroll
         for (int c = 0; c < 14; ++c) {
             const float4 c0 = col4[c * 2], c1 = col4[c * 2 + 1];
             const float gxh[kK] = {c0.x, c0.y}, dx[kK] = {c0.z, c0.w}, dx2[kK] = {c1.x, c1.y};
