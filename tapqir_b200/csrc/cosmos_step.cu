@@ -187,7 +187,10 @@ __host__ __device__ inline int post_upt(int nb, int fb, int C) {
 __host__ __device__ inline int post_chunks(int fb, int upt) { return (fb + kLocalBlock * upt - 1) / (kLocalBlock * upt); }
 
 template <typename T, int kPostUPT, bool HMM = false>
-__global__ void __launch_bounds__(kLocalBlock, 3) local_post_kernel(const LocalArgs<T> a, int chunks, unsigned int* __restrict__ tickets,
+#ifndef TQ_POST_MINB
+#define TQ_POST_MINB 3
+#endif
+__global__ void __launch_bounds__(kLocalBlock, TQ_POST_MINB) local_post_kernel(const LocalArgs<T> a, int chunks, unsigned int* __restrict__ tickets,
                                                                 double* __restrict__ acc_out) {
     __shared__ double red[kLocalBlock / 32][kPostRed];
     __shared__ GlobalTables<T> gt;
