@@ -1,8 +1,9 @@
-# A/B of local_post occupancy variants (csrc/build.py --variant=pbN -DTQ_POST_MINB=N): step time and per-kernel times
+# A/B of build variants by per-kernel times (torch profiler): bash profiles/r2_post_ab.sh "<workloads>" variant...
 mkdir -p gpurun_out
+WL=$1; shift
 for v in "$@"; do
   LIBV=""; [ "$v" != "default" ] && LIBV="$PWD/tapqir_b200/lib/libtapqir_b200.$v.so"
-  for w in c3 c2; do
-    echo "== $v $w"; TQ_LIB=$LIBV timeout 600 python profiles/kernel_times.py $w 10 2>&1 | grep -E "local_post|sum of kernels|adam_kernel<float"
+  for w in $WL; do
+    echo "== $v $w"; TQ_LIB=$LIBV timeout 600 python profiles/kernel_times.py $w 10 2>&1 | grep -E "local_post|site_fast|sum of kernels"
   done
 done

@@ -180,9 +180,12 @@ __global__ void __launch_bounds__(kLocalBlock) site_worklist_kernel(const LocalA
 // same for the channel accumulators.  Fixed summation order => run-to-run deterministic, whichever block is last.
 // `tickets`: (nb * C + 1) zero-initialised counters, left zeroed for the next launch.
 
+#ifndef TQ_POST_UPT_MIN
+#define TQ_POST_UPT_MIN 888   // two waves of 3 blocks per SM (B200: 125 AOIs x 5000 frames, one rank of 8: 105 -> 74 us)
+#endif
 // units per thread: 4 amortises the block reduction when there are enough blocks to fill the GPU, else 1
 __host__ __device__ inline int post_upt(int nb, int fb, int C) {
-    return (int64_t)nb * C * ((fb + kLocalBlock * 4 - 1) / (kLocalBlock * 4)) >= 2048 ? 4 : 1;
+    return (int64_t)nb * C * ((fb + kLocalBlock * 4 - 1) / (kLocalBlock * 4)) >= TQ_POST_UPT_MIN ? 4 : 1;
 }
 __host__ __device__ inline int post_chunks(int fb, int upt) { return (fb + kLocalBlock * upt - 1) / (kLocalBlock * upt); }
 
