@@ -172,10 +172,17 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     __syncthreads();
     int ref_bin = 0;
     float delta_ref = 0.0f, w2_ref = 0.0f;
+    bool many_ok = false;
     if (MANY) {
         ref_bin = many_bins_reference(O, off_s);
         delta_ref = off_s[ref_bin];
         w2_ref = off_w2[ref_bin];
+        // the one-pass form exponentiates v_j - v_ref without a running maximum: it is bounded by c_j = (w2_j - w2_ref) +
+        // rate2 (delta_j - delta_ref) (the other term is <= 0).  A histogram so wide, or a gain so small, that some c_j
+        // nears the fp32 exponent range (64 bins at gain 7: 13 bits) goes through the two-pass form instead.
+        float c_max = 0.0f;
+        for (int j = 0; j < O; ++j) c_max = fmaxf(c_max, many_bins_const(j, ref_bin, off_s, off_w2, fc.rate2).c);
+        many_ok = c_max < 100.0f;
         for (int j = threadIdx.x; j < O; j += blockDim.x) bins[j] = many_bins_const(j, ref_bin, off_s, off_w2, fc.rate2);
         __syncthreads();
     }
@@ -301,7 +308,7 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
             pairs = __all_sync(kFull, !small && pix_min > max_off);
         }
         // many bins: every pixel above the SMALLEST offset (bins at or above a pixel drop out by underflow)
-        if (MANY) pairs = __all_sync(kFull, !small && pix_min > delta_ref);
+        if (MANY) pairs = many_ok && __all_sync(kFull, !small && pix_min > delta_ref);
         // separable spot factors: 2*K*P exponentials per patch instead of K*P*P (ksmogn_sweep.cuh: table layouts)
         float norm[kK];
         if (pairs) build_tables_pairs(tab, sub, s);
