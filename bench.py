@@ -11,8 +11,8 @@ batch, at every N.  It fits one B200 (1.96 GB of pixels, 1.44 GB of parameters /
 same workload and the 1/2/4/8 curve is STRONG scaling: rank r holds AOIs [r * 1000/N, (r+1) * 1000/N) and all ranks
 exchange one (C, 18) vector of doubles per step over NVLink peer memory.  At N=1 the line also carries `sub_results`
 for the other single-GPU configurations (C2 full batch -- round 1's headline --, the reference-default 10 x 512 minibatch
-of C2, C2 with the simulator's three offset bins kept distinct and with a 64-bin offset histogram), each with its own
-roofline object.  Prints ONE JSON line (rank 0).
+of C2, C2 with the simulator's three offset bins kept distinct and with a 64-bin offset histogram, BASELINE configs 4
+(two channels) and 5 (cosmos+hmm)), each with its own roofline object.  Prints ONE JSON line (rank 0).
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) before each timed step outside
 the event pair, max over ranks; clocks sampled through NVML during the timed region.  `--impl reference` times the
@@ -50,6 +50,7 @@ WORKLOAD_MODEL = {"c5": "cosmos+hmm"}
 O_BINS = 3   # offset bins of the simulated data (simulate.py:92,103): three IDENTICAL bins, merged to one on upload
 SUBS = {     # sub-results of the N=1 line: name -> (workload, offset_hist, keep_offset_bins)
     "c2": ("c2", 0, False), "c2mb": ("c2mb", 0, False), "c2_o3": ("c2", 0, True), "c2_o64": ("c2", 64, False),
+    "c4": ("c4", 0, False), "c5": ("c5", 0, False),   # BASELINE configs 4 (two channels) and 5 (cosmos+hmm)
 }
 
 
