@@ -42,7 +42,13 @@ TQ_HD float pow_m32_m1(float g) {
     if (fabsf(g) <= 0.1f)
         return g * (-1.5f + g * (1.875f + g * (-2.1875f + g * (2.4609375f + g * (-2.70703125f + g * (2.9326171875f
                  + g * (-3.14208984375f + g * 3.338470458984375f)))))));
+    // |g| > 0.1: nothing cancels in (1 + g)^(-3/2) - 1 (its magnitude is >= 0.13); one rsqrt instead of log1p + expm1
+#ifdef __CUDA_ARCH__
+    const float r = rsqrtf(1.0f + g);
+    return fmaf(r * r, r, -1.0f);
+#else
     return expm1f(-1.5f * log1pf(g));
+#endif
 }
 
 // l = log1p(u), f = u - l, A = l/u - 1, F = 2 f / u^2 - 1, for u > -1; r = 1 + u rounded from its own
@@ -186,9 +192,10 @@ TQ_HD_NOINLINE bool beta_grad_tierb(double xd, double yd, float lx, float ly, fl
         const double f = -(double)dc, a = alpha, b = beta;
         double numer = 1.0, id = rcp_d(a);
         double series = id * (f + id);
-#pragma unroll 1
+        const double inv_i[11] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10};
+#pragma unroll
         for (int i = 1; i <= 10; ++i) {
-            numer *= ((double)i - b) * xd * rcp_d((double)i);
+            numer *= ((double)i - b) * xd * inv_i[i];
             id = rcp_d(a + (double)i);
             series = fma(numer * id, f + id, series);
         }
@@ -200,9 +207,10 @@ TQ_HD_NOINLINE bool beta_grad_tierb(double xd, double yd, float lx, float ly, fl
         // the mirrored series in y = 1 - x
         const double f = dpsi, a = alpha, b = beta;
         double numer = 1.0, betas = 1.0, dbetas = 0.0, series = f * rcp_d(b);
-#pragma unroll 1
+        const double inv_j[9] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8};
+#pragma unroll
         for (int i = 1; i <= 8; ++i) {
-            numer *= -yd * rcp_d((double)i);
+            numer *= -yd * inv_j[i];
             dbetas = dbetas * (a - (double)i) + betas;
             betas = betas * (a - (double)i);
             series = fma(numer * rcp_d(b + (double)i), dbetas + f * betas, series);
@@ -322,7 +330,17 @@ TQ_HD void gamma_density_fast(float conc, float lconc, float lrate, float rate, 
 // SITE_DEFER with `variate` and a regime class in `cls` otherwise; 2 = replay a deferred site (everything but the bulk
 // forms and the sampler compiled out); 0 = everything in one call.
 enum { SITE_DONE = 0, SITE_FALLBACK = 1, SITE_FALLBACK_DRAW = 2, SITE_DEFER = 3 };
-constexpr int kSiteClasses = 4;   // regime classes of deferred sites
+// Regime classes of deferred sites.  A class fixes every data-dependent branch of the replay (MODE 2), so that sites sorted
+// by class run side by side in one warp through the same code:
+//   Gamma (8 classes):  bit 0: x < 0.8,  bit 1: concentration > 8,  bit 2: concentration > 10
+//   Beta (64 classes):  density regime (S <= 16 / c1 <= 6 / c0 <= 6 / both > 6 with a tail draw) x the branch each of the
+//                       two beta_grad_tierb calls takes (series in x, series in 1 - x, Rice, rational correction)
+constexpr int kSiteClasses = 64;
+TQ_HD int beta_tierb_branch(float x, float boundary, float alpha, float beta) {
+    if (x <= 0.5f && boundary < 2.5f) return 0;
+    if (x >= 0.5f && boundary < 0.75f) return 1;
+    return (alpha > 6.0f && beta > 6.0f) ? 2 : 3;
+}
 template <int MODE>
 TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
                            Philox* rng, double& variate, float& sample, float* rec, float* extra, int& cls) {
@@ -342,7 +360,7 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
         if (x < 0.8f && conc > 30.0f) return SITE_FALLBACK;        // Taylor regime far in the tail: powers underflow in fp32
         const bool bulk = conc > 10.0f && x >= 0.8f;
         if (MODE == 1 && !bulk) {
-            cls = conc > 10.0f ? 2 : (x < 0.8f ? 0 : 1);
+            cls = (x < 0.8f ? 1 : 0) | (conc > 8.0f ? 2 : 0) | (conc > 10.0f ? 4 : 0);
             return SITE_DEFER;
         }
         const float ibeta = expf(-u1), beta = site_rcp(ibeta), loc = conc * ibeta;
@@ -403,7 +421,9 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
     const float ie = site_rcp(e), ub = -ua * ie;                  // -(x - m1) / m0
     const bool bulk = c1 > 6.0f && c0 > 6.0f && S * x * y >= 2.5f && ua > -1.0f && ub > -1.0f;
     if (MODE == 1 && !bulk) {
-        cls = S <= 16.0f ? 0 : (c1 <= 6.0f ? 1 : (c0 <= 6.0f ? 2 : 3));
+        const float boundary = S * x * y;
+        cls = (S <= 16.0f ? 0 : (c1 <= 6.0f ? 1 : (c0 <= 6.0f ? 2 : 3))) * 16 + beta_tierb_branch(x, boundary, c1, c0) * 4
+              + beta_tierb_branch(y, boundary, c0, c1);
         return SITE_DEFER;
     }
     if (MODE != 1 && (MODE == 2 || !bulk)) {

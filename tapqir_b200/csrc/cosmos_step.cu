@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
     __shared__ unsigned char t_cls[kSiteSpan];
     const int s = blockIdx.y;
     const uint32_t base = blockIdx.x * (uint32_t)kSiteSpan;
+    static_assert(kSiteClasses <= kLocalBlock, "one thread per class counter");
     if (threadIdx.x < kSiteClasses) { cnt[threadIdx.x] = 0u; fill[threadIdx.x] = 0u; }
     if (threadIdx.x == 0) n_def = 0u;
     __syncthreads();
@@ -111,7 +112,6 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
     if (!__syncthreads_or(deferred)) return;   // every site was in the bulk regime (always so at the initial point)
     if (threadIdx.x == 0) {
         unsigned int acc = 0u;
-#pragma unroll
         for (int c = 0; c < kSiteClasses; ++c) { off[c] = acc; acc += cnt[c]; }
         off[kSiteClasses] = acc;
     }
@@ -801,9 +801,12 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
             if (stm != TQ_OK) return stm;
         }
         // four units per thread once the grid still covers the GPU several times over (>= 4 waves of 8 blocks per SM)
-        const int64_t blocks4 = (a.U + 4 * kLocalBlock - 1) / (4 * kLocalBlock);
+#ifndef TQ_SITE_UPT_BIG
+#define TQ_SITE_UPT_BIG 8   // B200, one rank's C3 shard after 3000 iterations: 608 (1 x 128 sites, 4 classes) -> 588 (4 x, 64 classes) -> 550 us (8 x)
+#endif
+        const int64_t blocks4 = (a.U + TQ_SITE_UPT_BIG * kLocalBlock - 1) / (TQ_SITE_UPT_BIG * kLocalBlock);
         if (blocks4 * NSAMP >= (int64_t)sm_count() * 8 * 4)
-            site_fast_kernel<4><<<dim3((unsigned)blocks4, NSAMP), kLocalBlock, 0, st>>>(a);
+            site_fast_kernel<TQ_SITE_UPT_BIG><<<dim3((unsigned)blocks4, NSAMP), kLocalBlock, 0, st>>>(a);
         else
             site_fast_kernel<1><<<grid, kLocalBlock, 0, st>>>(a);
         TQ_LAUNCH_CHECK("site_fast_kernel launch");

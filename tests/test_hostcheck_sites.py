@@ -215,4 +215,9 @@ def test_two_pass_form_equals_the_one_call_form():
         if st1 == 0:
             assert list(a) == list(b), (i, s, cls.value, list(a), list(b))
         seen["gamma" if s < 3 else "beta"].add(cls.value)
-    assert seen["gamma"] >= {-1, 0, 1} and seen["beta"] >= {-1, 0, 1, 2, 3}, seen
+    # classes (cosmos_sites_fast.cuh): Gamma = bits (x < 0.8, conc > 8, conc > 10); Beta = density regime * 16 + the
+    # branches of the two beta_grad_tierb calls -- every density regime and every branch must have been replayed
+    assert seen["gamma"] >= {-1, 0, 1, 2}, seen   # (x < 0.8 at concentration > 8 is a far-tail draw: not in 6000 tries)
+    beta = {c for c in seen["beta"] if c >= 0}
+    assert {c // 16 for c in beta} == {0, 1, 2, 3} and {(c // 4) % 4 for c in beta} == {0, 1, 2, 3} and -1 in seen["beta"], seen
+    assert max(beta) < 64
