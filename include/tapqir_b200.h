@@ -182,6 +182,26 @@ int tq_cosmos_sites_ws(int dtype, const tq_patch_view* view, int64_t Nt, const v
                        const void* noise_in, void* samples, void* qm, void* rec, void* worklist,
                        void* work_count, void* stream);
 
+/* tq_cosmos_sites_ws for a FULL-BATCH float32 step (no ndx / fdx, nb == Nt, fb == F) with the previous step's dense Adam
+ * update of the AOI-local parameters folded in (the reference's optimiser step, models/model.py:168-171,212, moved from
+ * the end of step t to the first read of the parameters in step t + 1: the same values reach the same arithmetic).  The
+ * dense update is pure HBM traffic, this kernel is issue-bound with the memory system idle: when StepState says an update
+ * is pending (tq_step_advance_deferred) every site's thread applies it -- same formula, same constants, same bits as
+ * tq_adam_dense -- to the parameters it owns before reading them.  lparams is read AND written; lgrads / exp_avg /
+ * exp_avg_sq are the flat buffers tq_adam_dense would get.  Covered: the flat range [begin, end) of
+ * tq_local_deferred_range (b_loc, b_beta, m_probs, h_loc, h_beta, w_mean, w_size, x_mean, y_mean); the rest (per-AOI
+ * background parameters in front of it, `size` -- shared by the x and y sites -- behind it) stays with tq_adam_dense at
+ * the end of the step.  Call order of such a step:
+ *   ... -> tq_cosmos_sites_adam -> tq_ksmogn_fwd_bwd -> tq_cosmos_local_post -> ... -> tq_adam_dense ([0, begin) and
+ *   [end, numel)) -> tq_step_advance_deferred
+ * and tq_adam_deferred_flush before anything else reads the parameters or the moments. */
+int tq_cosmos_sites_adam(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc,
+                         void* lparams, int64_t aoi_offset, uint64_t seed, const void* state,
+                         const void* noise_in, void* samples, void* qm, void* rec, void* worklist,
+                         void* work_count, const void* lgrads, void* exp_avg, void* exp_avg_sq,
+                         double beta1, double beta2, double eps, void* stream);
+int tq_local_deferred_range(int64_t Nt, int64_t F, int64_t C, int64_t* begin, int64_t* end);
+
 /* Priors, (z, theta) log-sum-exp, q(m)-weighted ELBO summand and its reverse mode per unit
  * (TraceEnum_ELBO [third party] on cosmos.py:216-327).  Inputs: the buffers above plus L (4, U),
  * gs (9, U) and g_rate (U,) from tq_ksmogn_fwd_bwd with W = qm.  sN = Nt_total / nb_total and
@@ -310,6 +330,18 @@ int tq_adam_dense(int dtype, int64_t n, void* params, const void* grads, void* e
 
 /* *state += 1 */
 int tq_step_advance(void* state, void* stream);
+
+/* Device-resident step state: { uint64 step; uint32 pending; float step_size, inv_sqrt_bc2 } (tq_sizeof_step_state
+ * bytes, zero-initialised by the caller).  Entry points that only need the step count accept an 8-byte state.
+ * tq_step_advance_deferred: end of a step whose local update is deferred -- stores the bias-corrected constants of
+ * update number step + 1, sets `pending`, then step += 1.
+ * tq_adam_deferred_flush: applies a pending update now over n entries (the tq_local_deferred_range part of the flat
+ * buffers) and clears `pending`; a no-op when nothing is pending. */
+int tq_sizeof_step_state(void);
+int tq_step_advance_deferred(void* state, double lr, double beta1, double beta2, void* stream);
+int tq_adam_deferred_flush(int dtype, int64_t n, void* params, const void* grads, void* exp_avg,
+                           void* exp_avg_sq, double beta1, double beta2, double eps, void* state,
+                           void* stream);
 
 /* Measured-peak helpers for the roofline (register-resident FMA / MUFU loops); *ops receives the
  * operations issued by the launch (host pointer). */

@@ -57,6 +57,9 @@ SIGNATURES = {
                                  _VP, _VP]),
     "tq_cosmos_sites_ws": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,
                                  _VP, _VP, _VP, _VP]),
+    "tq_cosmos_sites_adam": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, c_int64, c_uint64, _VP, _VP, _VP, _VP,
+                                      _VP, _VP, _VP, _VP, _VP, _VP, c_double, c_double, c_double, _VP]),
+    "tq_local_deferred_range": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64), POINTER(c_int64)]),
     "tq_cosmos_local_post": (c_int, [c_int, POINTER(PatchView), c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                       c_double, c_double, _VP, _VP, _VP, _VP, _VP]),
     "tq_cosmos_fused_supported": (c_int, [c_int, POINTER(PatchView)]),
@@ -97,6 +100,9 @@ SIGNATURES = {
     "tq_snr_chi2": (c_int, [c_int64, c_int, c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, c_double, c_double, c_double, _VP, _VP, _VP]),
     "tq_adam_dense": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, c_double, _VP, _VP]),
     "tq_step_advance": (c_int, [_VP, _VP]),
+    "tq_sizeof_step_state": (c_int, []),
+    "tq_step_advance_deferred": (c_int, [_VP, c_double, c_double, c_double, _VP]),
+    "tq_adam_deferred_flush": (c_int, [c_int, c_int64, _VP, _VP, _VP, _VP, c_double, c_double, c_double, _VP, _VP]),
     "tq_peak_fma": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
     "tq_peak_mufu": (c_int, [c_int, c_int, _VP, POINTER(c_double), _VP]),
     "tq_subsample": (c_int, [c_int, c_int, c_uint64, _VP, c_uint64, _VP, _VP, _VP]),

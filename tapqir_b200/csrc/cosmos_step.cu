@@ -66,6 +66,32 @@ __device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int 
     else a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u32] = nanf("");   // marker for site_fallback_kernel
 }
 
+// Deferred Adam (tq_cosmos_sites_adam; full-batch steps).  The dense Adam over the AOI-local buffer is pure HBM traffic
+// (28 B per element, 0.39 ms at 1000 AOIs x 5000 frames) while this kernel is issue-bound with the memory system at 13 %:
+// the thread of site s applies the previous step's update to the parameters it is about to read -- its own two (x and y
+// share `size`, which therefore stays with tq_adam_dense at the end of the step, as do the per-AOI background
+// parameters) and, on the background site, the spot-presence logits it turns into q(m).  Same arithmetic, same constants
+// (StepState), hence the same bits as adam_kernel.
+__device__ __forceinline__ float deferred_adam_at(const LocalArgs<float>& a, int64_t i, float p, float ss, float isb) {
+    const float g = a.adam_g[i];
+    float m = a.adam_m[i], v = a.adam_v[i];
+    adam_update(p, g, m, v, ss, isb, a.adam_b1, a.adam_b2, a.adam_eps);
+    a.adam_p[i] = p; a.adam_m[i] = m; a.adam_v[i] = v;
+    return p;
+}
+__device__ __forceinline__ void site_deferred_adam(const LocalArgs<float>& a, int s, SiteInputs<float>& in) {
+    const float ss = a.state->step_size, isb = a.state->inv_sqrt_bc2;   // (re-read per unit: two registers less across the loop)
+    in.p0 = deferred_adam_at(a, a.lo.slab(site_param0(s)) + in.unit, in.p0, ss, isb);
+    if (s < S_X) in.p1 = deferred_adam_at(a, a.lo.slab(site_param1(s)) + in.unit, in.p1, ss, isb);
+    if (s == S_B) {
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            const int64_t i = a.lo.slab(LP_M_PROBS + k) + in.unit;
+            deferred_adam_at(a, i, a.adam_p[i], ss, isb);
+        }
+    }
+}
+
 // (8 resident blocks per SM = 64 registers, no spills: 5 us faster on a trained model than 6 blocks at 71 registers)
 // A block takes kSiteUPT x 128 consecutive units of one site: with 128 a trained model's deferred sites (a quarter of
 // them, four regime classes) left each class with a handful of sites per block -- partially filled warps in pass 2
@@ -86,12 +112,16 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
     if (threadIdx.x == 0) n_def = 0u;
     __syncthreads();
     const bool use_rng = a.noise_in == nullptr;
+    // the previous step's Adam update of the parameters this thread is about to read (pass 2 and the double-precision
+    // kernels behind this one re-read them from memory, updated)
+    const bool adam_pending = a.adam_p != nullptr && a.state->pending != 0u;
     bool deferred = false;
 #pragma unroll 1
     for (int j = 0; j < kSiteUPT; ++j) {
         const uint32_t local = (uint32_t)j * kLocalBlock + threadIdx.x, u32 = base + local;
         if (u32 >= (uint32_t)a.U) break;
-        const SiteInputs<float> in = site_gather(a, s, u32);
+        SiteInputs<float> in = site_gather(a, s, u32);
+        if (adam_pending) site_deferred_adam(a, s, in);
         Philox rng(a.seed, a.state->step, in.rng_offset);
         double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
         float v = 0.0f, rec[NSO], extra[NEX];
@@ -678,24 +708,30 @@ __global__ void globals_finish_kernel(int Q, bool hmm, ModelConst mc, const doub
 // dense over the whole tensor.  `state->step` is the number of completed steps.
 template <typename T> struct alignas(4 * sizeof(T)) Vec4 { T x, y, z, w; };
 
+// bias-corrected constants of update number t (1-based), rounded to T exactly once (shared by both evaluations)
 template <typename T>
-__device__ __forceinline__ void adam_update(T& p, T g, T& m, T& v, T step_size, T inv_sqrt_bc2, T tb1, T tb2, T teps) {
-    m = m + (g - m) * (T(1) - tb1);              // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * tb2 + (T(1) - tb2) * g * g;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-    const T denom = Real<T>::sqrt(v) * inv_sqrt_bc2 + teps;
-    p = p - step_size * (m / denom);
+__device__ __forceinline__ void adam_constants(double lr, double b1, double b2, double t, T& step_size, T& inv_sqrt_bc2) {
+    const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+    step_size = (T)(lr / bc1);
+    inv_sqrt_bc2 = (T)(1.0 / sqrt(bc2));
 }
 
 // 28 B of HBM traffic per element (p, g, m, v read; p, m, v written): four elements per thread through 16-byte
-// (float) / 32-byte (double) accesses, scalar tail
-template <typename T, bool VEC>
+// (float) / 32-byte (double) accesses, scalar tail.
+// DEFERRED: the constants come from StepState (written by step_advance_deferred_kernel with the update they belong to)
+// and nothing happens unless an update is pending -- tq_adam_deferred_flush.
+template <typename T, bool VEC, bool DEFERRED = false>
 __global__ void __launch_bounds__(256) adam_kernel(int64_t n, T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
                                                    T* __restrict__ v, double lr, double b1, double b2, double eps,
                                                    const StepState* __restrict__ state) {
-    const double t = (double)(state->step + 1ull);
-    const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
-    const T step_size = (T)(lr / bc1);
-    const T inv_sqrt_bc2 = (T)(1.0 / sqrt(bc2));
+    T step_size, inv_sqrt_bc2;
+    if (DEFERRED) {
+        if (state->pending == 0u) return;
+        step_size = (T)state->step_size;
+        inv_sqrt_bc2 = (T)state->inv_sqrt_bc2;
+    } else {
+        adam_constants<T>(lr, b1, b2, (double)(state->step + 1ull), step_size, inv_sqrt_bc2);
+    }
     const T tb1 = (T)b1, tb2 = (T)b2, teps = (T)eps;
     const int64_t n4 = VEC ? n / 4 : 0;
     Vec4<T>* p4 = reinterpret_cast<Vec4<T>*>(p);
@@ -717,6 +753,22 @@ __global__ void __launch_bounds__(256) adam_kernel(int64_t n, T* __restrict__ p,
 
 __global__ void step_advance_kernel(StepState* state) {
     if (blockIdx.x == 0 && threadIdx.x == 0) state->step += 1ull;
+}
+
+// End of a step whose AOI-local Adam update is deferred into the next step's site kernel: record the constants of THIS
+// update (number step + 1) with the pending flag, then count the step.
+__global__ void step_advance_deferred_kernel(StepState* state, double lr, double b1, double b2) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    float ss, isb;
+    adam_constants<float>(lr, b1, b2, (double)(state->step + 1ull), ss, isb);
+    state->step_size = ss;
+    state->inv_sqrt_bc2 = isb;
+    state->pending = 1u;
+    state->step += 1ull;
+}
+
+__global__ void step_clear_pending_kernel(StepState* state) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) state->pending = 0u;
 }
 
 static int local_blocks(int64_t U) { return (int)((U + kLocalBlock - 1) / kLocalBlock); }
@@ -779,12 +831,26 @@ extern "C" int tq_hmm_globals_sample(int dtype, int Q, const void* gparams, cons
     return globals_sample_impl(dtype, Q, true, gparams, mc, noise_in, seed, state, gstate, tables, gain_out, stream);
 }
 
+struct DeferredAdam {   // tq_cosmos_sites_adam
+    const void* grads;
+    void* exp_avg;
+    void* exp_avg_sq;
+    double beta1, beta2, eps;
+};
+
 template <typename T>
 static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams,
                      int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in, void* samples,
-                     void* qm, void* rec, void* worklist, void* work_count, cudaStream_t st) {
+                     void* qm, void* rec, void* worklist, void* work_count, cudaStream_t st, const DeferredAdam* adam = nullptr) {
     LocalArgs<T> a{};
     fill_common(a, view, Nt, mc, lparams, nullptr, aoi_offset, seed, state);
+    if (adam) {
+        a.adam_p = (T*)const_cast<void*>(lparams);
+        a.adam_g = (const T*)adam->grads;
+        a.adam_m = (T*)adam->exp_avg;
+        a.adam_v = (T*)adam->exp_avg_sq;
+        a.adam_b1 = (float)adam->beta1; a.adam_b2 = (float)adam->beta2; a.adam_eps = (float)adam->eps;
+    }
     a.noise_in = (const T*)noise_in;
     a.samples = (T*)samples;
     a.qm = (T*)qm;
@@ -826,11 +892,18 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
 
 static int sites_impl(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, const void* lparams,
                       int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
-                      void* samples, void* qm, void* rec, void* worklist, void* work_count, void* stream) {
+                      void* samples, void* qm, void* rec, void* worklist, void* work_count, void* stream,
+                      const DeferredAdam* adam = nullptr) {
     TQ_CHECK_ARG(view && mc && lparams && state && samples && qm && rec, "NULL pointer");
     TQ_CHECK_ARG(view->C >= 1 && view->C <= kMaxC, "C (channels) must be in [1, 4]");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TQ_F32) return run_sites<float>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, st);
+    if (adam) {
+        TQ_CHECK_ARG(dtype == TQ_F32, "the deferred Adam update lives in the fp32 site kernel");
+        TQ_CHECK_ARG(adam->grads && adam->exp_avg && adam->exp_avg_sq, "NULL pointer");
+        TQ_CHECK_ARG(view->ndx == nullptr && view->fdx == nullptr && view->nb == Nt && view->fb == view->F,
+                     "the deferred Adam update needs a full-batch step (a subsampled step visits only its minibatch, the update is dense)");
+    }
+    if (dtype == TQ_F32) return run_sites<float>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, st, adam);
     if (dtype == TQ_F64) return run_sites<double>(view, Nt, (const ModelConst*)mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, st);
     set_error("bad dtype %d", dtype);
     return TQ_ERR_ARG;
@@ -848,6 +921,30 @@ extern "C" int tq_cosmos_sites_ws(int dtype, const tq_patch_view* view, int64_t 
     TQ_CHECK_ARG(worklist && work_count, "NULL workspace");
     return sites_impl(dtype, view, Nt, mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, stream);
 }
+
+// tq_cosmos_sites_ws for a FULL-BATCH fp32 step, with the previous step's dense Adam update of the AOI-local parameters
+// folded in: if StepState says an update is pending (tq_step_advance_deferred), every site's thread applies it to the
+// parameters it owns before reading them.  Covers the flat range tq_local_deferred_range reports; the rest of the
+// buffer (per-AOI background parameters, `size`) is updated by tq_adam_dense at the end of the step as before.
+extern "C" int tq_cosmos_sites_adam(int dtype, const tq_patch_view* view, int64_t Nt, const void* mc, void* lparams,
+                                    int64_t aoi_offset, uint64_t seed, const void* state, const void* noise_in,
+                                    void* samples, void* qm, void* rec, void* worklist, void* work_count,
+                                    const void* lgrads, void* exp_avg, void* exp_avg_sq, double beta1, double beta2,
+                                    double eps, void* stream) {
+    TQ_CHECK_ARG(worklist && work_count, "NULL workspace");
+    const DeferredAdam adam{lgrads, exp_avg, exp_avg_sq, beta1, beta2, eps};
+    return sites_impl(dtype, view, Nt, mc, lparams, aoi_offset, seed, state, noise_in, samples, qm, rec, worklist, work_count, stream, &adam);
+}
+
+// [*begin, *end): the entries of the flat AOI-local buffer whose update tq_cosmos_sites_adam performs
+extern "C" int tq_local_deferred_range(int64_t Nt, int64_t F, int64_t C, int64_t* begin, int64_t* end) {
+    TQ_CHECK_ARG(begin && end && Nt >= 0 && F >= 0 && C >= 1, "bad arguments");
+    const LocalOffsets lo{Nt, F, C};
+    *begin = lo.index(LP_B_LOC, 0, 0, 0);
+    *end = lo.index(LP_SIZE, 0, 0, 0);
+    return TQ_OK;
+}
+extern "C" int tq_sizeof_step_state(void) { return (int)sizeof(StepState); }
 
 template <typename T>
 static int run_local_post(const tq_patch_view* view, int64_t Nt, const ModelConst* mc, const void* lparams, const void* tables,
@@ -1150,6 +1247,40 @@ extern "C" int tq_adam_dense(int dtype, int64_t n, void* params, const void* gra
         else adam_kernel<double, false><<<(int)grid, block, 0, st>>>(n, (double*)params, (const double*)grads, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, (const StepState*)state);
     } else { set_error("bad dtype %d", dtype); return TQ_ERR_ARG; }
     TQ_LAUNCH_CHECK("adam_kernel launch");
+    return TQ_OK;
+}
+
+// End of a step whose local update is deferred: StepState (tq_sizeof_step_state bytes) receives the constants of this
+// update and the pending flag, then the step count advances.
+extern "C" int tq_step_advance_deferred(void* state, double lr, double beta1, double beta2, void* stream) {
+    TQ_CHECK_ARG(state != nullptr, "NULL pointer");
+    step_advance_deferred_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((StepState*)state, lr, beta1, beta2);
+    TQ_LAUNCH_CHECK("step_advance_deferred_kernel launch");
+    return TQ_OK;
+}
+
+// Apply a pending deferred update NOW (before anything but tq_cosmos_sites_adam reads the parameters: checkpoints,
+// statistics, a subsampled step ...) over n entries -- the range of tq_local_deferred_range -- and clear the flag.
+// No-op when nothing is pending.
+extern "C" int tq_adam_deferred_flush(int dtype, int64_t n, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
+                                      double beta1, double beta2, double eps, void* state, void* stream) {
+    TQ_CHECK_ARG(dtype == TQ_F32, "the deferred Adam update is fp32");
+    TQ_CHECK_ARG(n >= 0 && state, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) {
+        TQ_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "NULL pointer");
+        const int block = 256;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        const bool vec = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0;
+        int64_t grid = ((vec ? n / 4 : n) + block - 1) / block;
+        if (grid < 1) grid = 1;
+        if (grid > cap) grid = cap;
+        if (vec) adam_kernel<float, true, true><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, 0.0, beta1, beta2, eps, (const StepState*)state);
+        else adam_kernel<float, false, true><<<(int)grid, block, 0, st>>>(n, (float*)params, (const float*)grads, (float*)exp_avg, (float*)exp_avg_sq, 0.0, beta1, beta2, eps, (const StepState*)state);
+        TQ_LAUNCH_CHECK("adam_kernel (deferred flush) launch");
+    }
+    step_clear_pending_kernel<<<1, 1, 0, st>>>((StepState*)state);
+    TQ_LAUNCH_CHECK("step_clear_pending_kernel launch");
     return TQ_OK;
 }
 

@@ -26,13 +26,21 @@ struct LocalOffsets {
         if (i < 2) return (int64_t)i * (Nt * C) + n * C + c;
         return 2 * (Nt * C) + (int64_t)(i - 2) * (Nt * F * C) + (n * F + f) * C + c;
     }
+    // the same for entries 2.. from the unit's store offset  unit = (n F + f) C + c
+    __host__ __device__ int64_t slab(int i) const { return 2 * (Nt * C) + (int64_t)(i - 2) * (Nt * F * C); }
     __host__ __device__ int64_t numel() const { return tensor_off(12); }
 };
 
 // per-step state kept on the device so that a captured CUDA graph can be replayed unchanged
 struct StepState {
     unsigned long long step;  // SVI iteration counter: Philox stream + Adam bias correction
+    // deferred AOI-local Adam (tq_cosmos_sites_adam): the gradients of the previous step are still to be applied, with
+    // these bias-corrected constants.  Callers that never defer may keep passing an 8-byte state.
+    unsigned int pending;
+    float step_size, inv_sqrt_bc2;
 };
+constexpr int kStepStateBytes = 24;
+static_assert(sizeof(StepState) == kStepStateBytes, "StepState layout is part of the C ABI (tq_sizeof_step_state)");
 
 constexpr int kLocalBlock = 128;
 
@@ -62,6 +70,12 @@ template <typename T> struct LocalArgs {
     // sites outside the fp32 forms: appended here by site_fast_kernel, redone in double by site_worklist_kernel
     uint32_t* worklist;          // (NSAMP * U) entries s * U + u, or NULL (block-local compaction instead)
     unsigned int* work_count;    // [0]: entries appended this launch
+    // deferred Adam of the parameters a site's thread owns (site_fast_kernel; NULL = parameters are read-only here)
+    T* adam_p;                   // == lparams, writable
+    const T* adam_g;             // lgrads of the previous step
+    T* adam_m;
+    T* adam_v;
+    float adam_b1, adam_b2, adam_eps;
     // hmm variant (cosmos_hmm.cuh): the extra local slabs live behind the cosmos layout in the same flat buffers --
     // m_probs[z = 1] (K slabs of (Nt, F, C)), then z_trans (Nt, F, C, 2, 2); m_probs[z = 0] are the cosmos m_probs slabs
     const double* hmm_a;         // (kZ, U) forward marginals of the guide's chain
@@ -83,25 +97,37 @@ template <typename T> struct LocalArgs {
 //   site_fallback_kernel     ... and is redone here in double (same Philox stream, so the same draw whichever
 //                            kernel makes it).  Keeping the two apart holds the hot kernel at 66 registers.
 template <typename T> struct SiteInputs {
-    UnitIndex ui;
-    int64_t f;
+    int64_t unit;                // (n F + f) C + c: offset of the unit in every (Nt, F, C) slab of the flat local buffers
     T p0, p1, pbm, pbs;
     unsigned long long rng_offset;
 };
 
+// A full-frame minibatch without index lists (every full-batch step; fb == F, AOIs 0 .. nb-1) has unit == u: no
+// division, no index lists; only the background site needs the AOI (its prior's two per-AOI parameters).
 template <typename T>
 __device__ __forceinline__ SiteInputs<T> site_gather(const LocalArgs<T>& a, int s, uint32_t u32) {
     SiteInputs<T> in;
-    in.ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
-    in.f = a.v.fdx ? a.v.fdx[in.ui.fi] : in.ui.fi;
-    in.p0 = a.lparams[a.lo.index(site_param0(s), in.ui.aoi, in.f, in.ui.c)];
-    in.p1 = a.lparams[a.lo.index(site_param1(s), in.ui.aoi, in.f, in.ui.c)];
+    int64_t aoi_c;               // n C + c (used by the background site only)
+    if (a.v.ndx == nullptr && a.v.fdx == nullptr && a.v.fb == a.v.F) {
+        in.unit = (int64_t)u32;
+        aoi_c = 0;
+        if (s == S_B) {
+            const uint32_t C = (uint32_t)a.v.C, n = u32 / ((uint32_t)a.v.F * C);
+            aoi_c = (int64_t)(n * C + (C == 1u ? 0u : u32 % C));
+        }
+    } else {
+        const UnitIndex ui = locate_unit32(u32, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        in.unit = ui.patch;
+        aoi_c = (int64_t)ui.aoi * a.v.C + ui.c;
+    }
+    in.p0 = a.lparams[a.lo.slab(site_param0(s)) + in.unit];
+    in.p1 = a.lparams[a.lo.slab(site_param1(s)) + in.unit];
     in.pbm = in.pbs = T(0);
     if (s == S_B) {
-        in.pbm = a.lparams[a.lo.index(LP_BM, in.ui.aoi, in.f, in.ui.c)];
-        in.pbs = a.lparams[a.lo.index(LP_BS, in.ui.aoi, in.f, in.ui.c)];
+        in.pbm = a.lparams[aoi_c];                      // LP_BM, LP_BS: (Nt, C) tables at the front
+        in.pbs = a.lparams[a.lo.Nt * a.lo.C + aoi_c];
     }
-    const unsigned long long gid = (((unsigned long long)(a.aoi_offset + in.ui.aoi)) * a.v.F + in.f) * a.v.C + in.ui.c;
+    const unsigned long long gid = (unsigned long long)a.aoi_offset * (unsigned long long)(a.v.F * a.v.C) + (unsigned long long)in.unit;
     in.rng_offset = ((gid + 1ull) << 12) + ((unsigned long long)s << 8);
     return in;
 }
@@ -136,7 +162,7 @@ __device__ __forceinline__ void write_presence_weights(const LocalArgs<T>& a, co
     T q1[kK], q0[kK], qm[kM];
 #pragma unroll
     for (int k = 0; k < kK; ++k) {
-        const SpotPresence<T> sp((T)a.lparams[a.lo.index(LP_M_PROBS + k, in.ui.aoi, in.f, in.ui.c)], a.mc);
+        const SpotPresence<T> sp((T)a.lparams[a.lo.slab(LP_M_PROBS + k) + in.unit], a.mc);
         q1[k] = sp.q1; q0[k] = sp.q0;
     }
     presence_weights<T>(q1, q0, qm);
@@ -158,6 +184,28 @@ __device__ __forceinline__ void site_double(const LocalArgs<T>& a, int s, uint32
 #pragma unroll
     for (int j = 0; j < NEX; ++j) extra[j] = (T)dextra[j];
     site_scatter(a, s, (int64_t)u32, v, rec, extra);
+}
+
+// Explicit fused multiply-adds: the update is evaluated in two kernels (adam_kernel, and site_fast_kernel for the
+// deferred update of the parameters a site owns) and both must round identically, whatever the compiler would contract.
+template <typename T>
+__device__ __forceinline__ void adam_update(T& p, T g, T& m, T& v, T step_size, T inv_sqrt_bc2, T tb1, T tb2, T teps) {
+    m = fma(g - m, T(1) - tb1, m);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = fma((T(1) - tb2) * g, g, v * tb2);               // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    const T denom = fma(Real<T>::sqrt(v), inv_sqrt_bc2, teps);
+    p = fma(-step_size, m / denom, p);
+}
+// float: the square root and the reciprocal on the MUFU (2 ulp; the update they scale is 1e-3 of the parameter).  IEEE
+// sqrt + division are ~20 instructions per element -- invisible in the bandwidth-bound adam_kernel, 6 % of the
+// issue-bound site kernel when the update is deferred into it.
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float step_size, float inv_sqrt_bc2, float tb1,
+                                            float tb2, float teps) {
+    m = fmaf(g - m, 1.0f - tb1, m);
+    v = fmaf((1.0f - tb2) * g, g, v * tb2);
+    float sq, r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(sq, inv_sqrt_bc2, teps)));
+    p = fmaf(-step_size * m, r, p);
 }
 
 constexpr int kPostRed = NACC + 2;

@@ -187,6 +187,8 @@ class cosmos(Model):
         n = 10 if eng.dtype == torch.float32 else 9
         if getattr(eng, "last_step_fused", False):
             n -= 3   # site_fast + site_worklist + ksmogn + local_post -> cosmos_fused_kernel
+        if getattr(eng, "_pending", False):
+            n += 1   # deferred local Adam: tq_adam_dense over the two ranges the site kernel does not own instead of one launch
         draws = (0 if eng.full_n else 1) + (0 if eng.full_f else 1)
         n += 1 if draws == 2 and eng.lib.tq_subsample_pair_supported(eng.Nt, eng.F) else draws
         return n

@@ -51,13 +51,17 @@ class CosmosEngine:
         dev, f64 = self.device, torch.float64
         z = lambda n, dt=dtype: torch.zeros(n, dtype=dt, device=dev)
         # parameters, gradients, Adam moments (flat; see layout.py)
+        # (lparams / lm / lv are properties: reading them first applies a deferred update, see flush_deferred)
+        self._pending = False
         self.lparams, self.lgrads, self.lm, self.lv = z(self.ll.numel), z(self.ll.numel), z(self.ll.numel), z(self.ll.numel)
         # the global parameters (4 + 5Q scalars), their gradients and moments are float64 whatever `dtype` is: the
         # global sites are evaluated in double anyway, and rounding gain_loc / gain_beta to fp32 alone moves the
         # gradient of gain_beta by 1e-4 of itself (it cancels ~1e3-fold in the base variate)
         self.gparams, self.ggrads, self.gm, self.gv = (z(self.gl.numel, f64) for _ in range(4))
         # small device-resident state
-        self.state = torch.zeros(1, dtype=torch.int64, device=dev)          # StepState.step
+        # StepState {uint64 step; uint32 pending; float step_size, inv_sqrt_bc2}: [0] is the iteration counter
+        assert self.lib.tq_sizeof_step_state() == 24, "StepState ABI mismatch"
+        self.state = torch.zeros(3, dtype=torch.int64, device=dev)
         self.tables = torch.zeros(self.lib.tq_sizeof_tables(), dtype=torch.uint8, device=dev)
         self.gstate = torch.zeros(self.lib.tq_sizeof_gstate() // 8, dtype=f64, device=dev)
         self.gain = z(1)
@@ -89,6 +93,21 @@ class CosmosEngine:
         # (128) for three very different phases leaves 16 warps per SM, and the site / post phases, which the
         # stand-alone kernels run at 32 / 12 warps per SM, are latency-bound at 4 warps per block
         self.fused = os.environ.get("TQ_FUSED", "0") == "1" and type(self).__name__ == "CosmosEngine"
+        # Deferred local Adam (default; TQ_DEFERRED_ADAM=0 turns it off): on full-batch float32 steps the dense Adam
+        # update of the AOI-local parameters -- 28 B of HBM traffic per element, 0.39 of 6.1 ms at 1000 AOIs x 5000
+        # frames -- is applied by the NEXT step's site kernel, which is issue-bound and leaves the memory system idle
+        # (tq_cosmos_sites_adam): each site's thread updates the parameters it owns just before it reads them.  Bit for
+        # bit the same parameters and moments as the separate kernel; anything else that reads them (checkpoints,
+        # statistics, a subsampled or gradient-only step) goes through flush_deferred first.
+        self.deferred_adam = (os.environ.get("TQ_DEFERRED_ADAM", "1") == "1" and type(self).__name__ == "CosmosEngine"
+                              and dtype == torch.float32)
+        # measured (B200, profiles/r2_deferred_ab.sh): 5 M units 6.09 -> 5.97 ms, 2 M (two channels) 2.52 -> 2.47 ms,
+        # 625 k and 100 k units: no gain (the dense update is a few us there and the split costs one more launch)
+        self.deferred_min_units = int(os.environ.get("TQ_DEFERRED_ADAM_MIN_UNITS", 1 << 20))
+        begin, end = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib.tq_local_deferred_range(self.Nt, self.F, self.C, ctypes.byref(begin), ctypes.byref(end)),
+                   "tq_local_deferred_range")
+        self._deferred_range = (int(begin.value), int(end.value))
         self.keep_intermediates = False   # fused path: also write samples / L back to HBM (tests, diagnostics)
         self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -97,8 +116,37 @@ class CosmosEngine:
         self.mcfg_arg = None  # NULL = built-in enumerated table -> fp32 production kernel; set to self.mcfg for the generic one
         self.set_batch(nbatch_size or self.Nt, fbatch_size or self.F)
 
+    # ---- deferred local Adam ------------------------------------------------------------------------------
+    def flush_deferred(self):
+        """Apply a deferred AOI-local Adam update now (no-op when none is pending)."""
+        if not self._pending:
+            return
+        self._pending = False
+        lo, hi = self._deferred_range
+        b1, b2 = self.betas
+        p = _lib.ptr
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tq_adam_deferred_flush(self.code, hi - lo, p(self._lparams[lo:hi]), p(self.lgrads[lo:hi]),
+                                                       p(self._lm[lo:hi]), p(self._lv[lo:hi]), b1, b2, self.adam_eps,
+                                                       p(self.state), _lib.stream_ptr(self.device)), "tq_adam_deferred_flush")
+
+    def _flat_property(name):
+        def get(self):
+            self.flush_deferred()
+            return getattr(self, name)
+
+        def set_(self, value):
+            self.flush_deferred()
+            setattr(self, name, value)
+
+        return property(get, set_)
+
+    lparams, lm, lv = _flat_property("_lparams"), _flat_property("_lm"), _flat_property("_lv")
+    del _flat_property
+
     # ---- buffers that depend on the minibatch shape ---------------------------------------------------
     def set_batch(self, nbatch_size, fbatch_size):
+        self.flush_deferred()
         self._graph, self._eager_default_steps = None, 0  # buffers below are re-allocated: drop any captured graph
         self.nb, self.fb = min(int(nbatch_size), self.Nt), min(int(fbatch_size), self.F)
         dev, dtype = self.device, self.dtype
@@ -164,6 +212,7 @@ class CosmosEngine:
             return self._enqueue(ndx, fdx, local_noise, global_noise, update, time_likelihood)
         if self._graph is not None:
             self._graph.replay()
+            self._pending = self._graph_defers
             return self.loss
         self._eager_default_steps += 1
         if self._eager_default_steps < 2:
@@ -172,7 +221,7 @@ class CosmosEngine:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._enqueue(None, None, None, None, True, None)
-        self._graph = graph
+        self._graph, self._graph_defers = graph, self._pending
         graph.replay()
         return self.loss
 
@@ -189,6 +238,11 @@ class CosmosEngine:
         lib, st, code = self.lib, _lib.stream_ptr(self.device), self.code
         p = _lib.ptr
         mc = ctypes.byref(self.mc)
+        # this step leaves its local Adam update to the next site kernel / applies the previous one in its own
+        defer = (self.deferred_adam and update and ndx is None and fdx is None and self.full_n and self.full_f
+                 and self.U >= max(self.deferred_min_units, 1) and not self.fused)
+        if not defer:
+            self.flush_deferred()
         with torch.cuda.device(self.device):
             if (ndx is None and not self.full_n and fdx is None and not self.full_f
                     and lib.tq_subsample_pair_supported(self.Nt, self.F)):
@@ -237,7 +291,7 @@ class CosmosEngine:
                 if time_likelihood is not None:
                     time_likelihood[1].record()
             else:
-                self._enqueue_stages(view, local_noise, main, time_likelihood, st)
+                self._enqueue_stages(view, local_noise, main, time_likelihood, st, defer)
             # the all-reduce of the (C, 18) accumulators (multi-GPU), finishing the global reverse pass (a few FMAs per
             # parameter) and the global Adam run on the side stream, beside the dense Adam over the AOI-local buffer,
             # which depends on none of them: the collective's latency hides under the local update
@@ -264,23 +318,37 @@ class CosmosEngine:
                 self._ev_join.record(self._side)
             if update:
                 b1, b2 = self.betas
-                _lib.check(lib.tq_adam_dense(code, self.ll.numel, p(self.lparams), p(self.lgrads), p(self.lm), p(self.lv),
-                                             self.lr, b1, b2, self.adam_eps, p(self.state), st), "tq_adam_dense")
+                lo, hi = self._deferred_range if defer else (0, 0)
+                for a, b in ((0, lo), (hi, self.ll.numel)):   # everything, or what the site kernel does not own
+                    if b > a:
+                        _lib.check(lib.tq_adam_dense(code, b - a, p(self._lparams[a:b]), p(self.lgrads[a:b]), p(self._lm[a:b]),
+                                                     p(self._lv[a:b]), self.lr, b1, b2, self.adam_eps, p(self.state), st),
+                                   "tq_adam_dense")
             main.wait_event(self._ev_join)
-            if update:
+            if update and defer:
+                _lib.check(lib.tq_step_advance_deferred(p(self.state), self.lr, b1, b2, st), "tq_step_advance_deferred")
+                self._pending = True
+            elif update:
                 _lib.check(lib.tq_step_advance(p(self.state), st), "tq_step_advance")
         return self.loss
 
-    def _enqueue_stages(self, view, local_noise, main, time_likelihood, st):
+    def _enqueue_stages(self, view, local_noise, main, time_likelihood, st, defer=False):
         """The AOI-local part of a step as three kernels with HBM scratch between them (dtype double, float pixels,
         P != 14, the operator-level mcfg table, TQ_FUSED=0)."""
         lib, code, p = self.lib, self.code, _lib.ptr
         mc = ctypes.byref(self.mc)
         # sites that leave the fp32 forms are collected in a worklist (the not-yet-written gradient buffer of the
         # likelihood kernel serves as its storage) and redone in double by dense warps
-        _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self.lparams), self.aoi_offset, self.seed,
-                                          p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
-                                          p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
+        if defer:
+            b1, b2 = self.betas
+            _lib.check(lib.tq_cosmos_sites_adam(code, view, self.Nt, mc, p(self._lparams), self.aoi_offset, self.seed,
+                                                p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
+                                                p(self.gs), p(self.work_count), p(self.lgrads), p(self._lm), p(self._lv),
+                                                b1, b2, self.adam_eps, st), "tq_cosmos_sites_adam")
+        else:
+            _lib.check(lib.tq_cosmos_sites_ws(code, view, self.Nt, mc, p(self._lparams), self.aoi_offset, self.seed,
+                                              p(self.state), p(local_noise), p(self.samples), p(self.qm), p(self.rec),
+                                              p(self.gs), p(self.work_count), st), "tq_cosmos_sites_ws")
         main.wait_event(self._ev_join0)
         S, G, K = self.samples, self.gs, L.K
         if time_likelihood is not None:
@@ -291,7 +359,7 @@ class CosmosEngine:
                                          p(G[1 + 3 * K:1 + 4 * K]), p(G[0]), p(self.g_rate), st), "tq_ksmogn_fwd_bwd")
         if time_likelihood is not None:
             time_likelihood[1].record()
-        _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self.lparams), p(self.tables), p(self.samples),
+        _lib.check(lib.tq_cosmos_local_post(code, view, self.Nt, mc, p(self._lparams), p(self.tables), p(self.samples),
                                             p(self.rec), p(self.Lm), p(self.gs), p(self.g_rate), self.sN, self.sF, p(self.lgrads),
                                             p(self.tickets), p(self.block_partial), p(self.acc), st),
                    "tq_cosmos_local_post")
@@ -362,7 +430,8 @@ class CosmosEngine:
 
     @property
     def iteration(self):
-        return int(self.state.item())
+        return int(self.state[0].item())
 
     def set_iteration(self, it):
-        self.state.fill_(int(it))
+        self.flush_deferred()   # a pending update belongs to the count it was recorded with
+        self.state[0] = int(it)
