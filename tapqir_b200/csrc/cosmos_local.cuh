@@ -261,7 +261,8 @@ TQ_HD double site_eval(int s, double u0, double u1, double ubm, double ubs, cons
     const AffBeta<A> d(mean.v, size.v, lo, hi);
     if (use_rng) {
         // the base draws are made in fp32 (their value is random); everything done with them is double
-        const A g1 = (A)sample_std_gamma_f32(*rng, (float)d.c1), g2 = (A)sample_std_gamma_f32(*rng, (float)d.c0);
+        GammaTrials trials;
+        const A g1 = (A)sample_std_gamma_f32(*rng, trials, (float)d.c1), g2 = (A)sample_std_gamma_f32(*rng, trials, (float)d.c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
     const A v = d.clamp(d.low + d.scale * variate, mc);

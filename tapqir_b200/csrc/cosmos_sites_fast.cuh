@@ -412,7 +412,8 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
     const float sz = expf(u1), S = 2.0f + sz;                     // size - 2 = d size / d u, size
     const float c1 = S * m1, c0 = S * m0;
     if (use_rng) {
-        const double g1 = sample_std_gamma_f32(*rng, c1), g2 = sample_std_gamma_f32(*rng, c0);
+        GammaTrials trials;
+        const double g1 = sample_std_gamma_f32(*rng, trials, c1), g2 = sample_std_gamma_f32(*rng, trials, c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
     const double x01d = variate;   // (v - low) / scale of the reference, to rounding

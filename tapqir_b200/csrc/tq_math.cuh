@@ -430,16 +430,21 @@ struct Philox {
         const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
         c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
     }
-    TQ_HD void refill() {
-        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    // the next block of four words; advances the counter
+    TQ_HD void block(uint32_t (&c)[4]) {
+        c[0] = ctr[0]; c[1] = ctr[1]; c[2] = ctr[2]; c[3] = ctr[3];
         uint32_t k[2] = {key[0], key[1]};
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
             round(c, k);
             k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
         }
-        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
         if (++ctr[0] == 0) ++ctr[1];
+    }
+    TQ_HD void refill() {
+        uint32_t c[4];
+        block(c);
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
         have = 4;
     }
     TQ_HD uint32_t next() {
@@ -450,7 +455,8 @@ struct Philox {
         return r;
     }
     // uniform in (0, 1]
-    TQ_HD float uniform() { return ((float)(next() >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+    static TQ_HD float to_uniform(uint32_t w) { return ((float)(w >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+    TQ_HD float uniform() { return to_uniform(next()); }
     TQ_HD double uniform_d() {
         const uint64_t hi = next(), lo = next();
         return ((double)(((hi << 32) | lo) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
@@ -466,6 +472,37 @@ struct Philox {
         return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
 #endif
     }
+    // One whole block as TWO (standard normal, uniform in (0, 1]) pairs: both branches of Box-Muller on words 0 and 1,
+    // the uniforms from words 2 and 3.  A Marsaglia-Tsang trial consumes exactly one such pair, so a block serves a Beta
+    // site's two gamma draws (or a draw and its retry): 9 blocks per unit instead of 15, and none of next()'s bookkeeping.
+    // Independent of the word buffer behind next().
+    TQ_HD void normal_uniform_pairs(float& n0, float& u0, float& n1, float& u1) {
+        uint32_t c[4];
+        block(c);
+        const float a = to_uniform(c[0]), b = to_uniform(c[1]);
+        float r, sn, cs;
+#ifdef __CUDA_ARCH__
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(a)));
+        __sincosf(6.283185307179586f * b, &sn, &cs);
+#else
+        r = sqrtf(-2.0f * logf(a));
+        sn = sinf(6.283185307179586f * b); cs = cosf(6.283185307179586f * b);
+#endif
+        n0 = r * cs; n1 = r * sn;
+        u0 = to_uniform(c[2]); u1 = to_uniform(c[3]);
+    }
+};
+
+// (normal, uniform) pairs for Marsaglia-Tsang trials, two per Philox block: the second waits here for the next trial --
+// of the same draw after a rejection, or of the next draw of the same site (a Beta variate is two gamma draws)
+struct GammaTrials {
+    float n1, u1;
+    bool spare = false;
+    TQ_HD void draw(Philox& rng, float& xn, float& u) {
+        if (spare) { xn = n1; u = u1; spare = false; return; }
+        rng.normal_uniform_pairs(xn, u, n1, u1);
+        spare = true;
+    }
 };
 
 // fp32 inline variant of the sampler below for the per-site kernels: inlining keeps the Philox state
@@ -474,7 +511,7 @@ struct Philox {
 // u^(1/alpha) spans hundreds of orders of magnitude and is applied in double -- in fp32 it underflows to an exact 0 with
 // probability ~(1e-38)^alpha, which puts the guide sample ON its clamp (seen after ~3000 SVI iterations on absent spots,
 // whose Beta concentrations drift below 1: x = -7.5 exactly -> log1p(-1) = -inf downstream).
-TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
+TQ_HD double sample_std_gamma_f32(Philox& rng, GammaTrials& trials, float alpha) {
 #ifdef __CUDA_ARCH__
     // MUFU forms: the accept/reject comparison tolerates their ~1e-6 absolute error (a borderline trial
     // flips with probability ~1e-6; the accepted value d*v itself is exact arithmetic)
@@ -493,13 +530,11 @@ TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
     const float d = alpha - 1.0f / 3.0f;
     const float c = TQ_SRSQRT(9.0f * d);
     for (int it = 0; it < 64; ++it) {
-        float xn, yv;
-        do {
-            xn = rng.normal();
-            yv = 1.0f + c * xn;
-        } while (yv <= 0.0f);
+        float xn, u;
+        trials.draw(rng, xn, u);
+        const float yv = 1.0f + c * xn;
+        if (yv <= 0.0f) continue;       // (the paper redraws the normal alone; discarding the independent uniform with it is the same law)
         const float v = yv * yv * yv;
-        const float u = rng.uniform();
         const float xx = xn * xn;
         if (u < 1.0f - 0.0331f * xx * xx) return scale * (double)(d * v);
         if (TQ_SLOG(u) < 0.5f * xx + d * (1.0f - v + TQ_SLOG(v))) return scale * (double)(d * v);
@@ -507,6 +542,10 @@ TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
     return scale * (double)d;
 #undef TQ_SLOG
 #undef TQ_SRSQRT
+}
+TQ_HD double sample_std_gamma_f32(Philox& rng, float alpha) {
+    GammaTrials trials;
+    return sample_std_gamma_f32(rng, trials, alpha);
 }
 
 // Marsaglia & Tsang (2000) standard gamma sampler (doi:10.1145/358407.358414), alpha > 0.

@@ -190,6 +190,20 @@ void hc_philox(uint64_t seed, uint64_t stream, uint64_t offset, int n, uint32_t*
     Philox rng(seed, stream, offset);
     for (int i = 0; i < n; ++i) out[i] = rng.next();
 }
+// n Philox blocks as (normal, uniform, normal, uniform) rows -- what the Marsaglia-Tsang trials of the guide sites consume
+void hc_normal_uniform_pairs(uint64_t seed, uint64_t stream, int n, float* out) {
+    Philox rng(seed, stream, 0);
+    for (int i = 0; i < n; ++i) rng.normal_uniform_pairs(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+// n Beta(c1, c0)-distributed pairs of gamma draws sharing their trials (the form the AffineBeta sites use): g1, g2 per row
+void hc_sample_gamma_pair_f32(uint64_t seed, uint64_t stream, float c1, float c0, int n, double* out) {
+    for (int i = 0; i < n; ++i) {
+        Philox rng(seed, stream, (uint64_t)i * 64);
+        GammaTrials trials;
+        out[2 * i] = sample_std_gamma_f32(rng, trials, c1);
+        out[2 * i + 1] = sample_std_gamma_f32(rng, trials, c0);
+    }
+}
 void hc_sample_gamma_f64(uint64_t seed, uint64_t stream, double alpha, int n, double* out) {
     for (int i = 0; i < n; ++i) { Philox rng(seed, stream, (uint64_t)i * 64); out[i] = sample_std_gamma<double>(rng, alpha); }
 }

@@ -186,3 +186,44 @@ def test_gamma_sampler_moments():
                                out.ctypes.data_as(ctypes.c_void_p))
         assert abs(out.mean() - alpha) < 5 * np.sqrt(alpha / n)
         assert abs(out.var() - alpha) < 0.1 * alpha
+
+
+def test_normal_uniform_pairs_of_a_philox_block():
+    """Both Box-Muller branches and the two uniforms of a block: standard moments, no correlation between any two of the
+    four, Kolmogorov-Smirnov against the normal / uniform laws."""
+    from scipy import stats
+
+    hc = hostcheck.load()
+    n = 200000
+    out = np.empty((n, 4), dtype=np.float32)
+    hc.hc_normal_uniform_pairs(ctypes.c_uint64(5), ctypes.c_uint64(9), n, out.ctypes.data_as(ctypes.c_void_p))
+    x = out.astype(np.float64)
+    for j in (0, 2):
+        assert abs(x[:, j].mean()) < 5 / np.sqrt(n) and abs(x[:, j].var() - 1) < 5 * np.sqrt(2 / n)
+        assert abs(stats.kurtosis(x[:, j])) < 0.05
+        assert stats.kstest(x[:, j], "norm").pvalue > 1e-3
+    for j in (1, 3):
+        assert x[:, j].min() > 0 and x[:, j].max() <= 1
+        assert stats.kstest(x[:, j], "uniform").pvalue > 1e-3
+    c = np.corrcoef(x.T)
+    assert np.abs(c - np.eye(4)).max() < 5 / np.sqrt(n)
+    # ... and of the squares (Box-Muller's two branches share their radius: independent only if the angle is uniform)
+    c2 = np.corrcoef((x[:, [0, 2]] ** 2).T)
+    assert abs(c2[0, 1]) < 5 / np.sqrt(n)
+
+
+def test_gamma_draws_that_share_their_trials():
+    """Two gamma draws fed from one GammaTrials (second draw starts on the first block's spare pair): right marginals
+    (KS against scipy), uncorrelated, and their ratio g1 / (g1 + g2) is Beta(c1, c0)."""
+    from scipy import stats
+
+    hc = hostcheck.load()
+    n = 100000
+    out = np.empty((n, 2))
+    for c1, c0 in ((50.0, 50.0), (100.0, 100.0), (2.5, 7.0), (0.6, 1.7), (12.0, 0.8)):
+        hc.hc_sample_gamma_pair_f32(ctypes.c_uint64(11), ctypes.c_uint64(2), ctypes.c_float(c1), ctypes.c_float(c0), n,
+                                    out.ctypes.data_as(ctypes.c_void_p))
+        assert stats.kstest(out[:, 0], "gamma", args=(c1,)).pvalue > 1e-3, (c1, c0)
+        assert stats.kstest(out[:, 1], "gamma", args=(c0,)).pvalue > 1e-3, (c1, c0)
+        assert abs(np.corrcoef(out.T)[0, 1]) < 5 / np.sqrt(n), (c1, c0)
+        assert stats.kstest(out[:, 0] / out.sum(1), "beta", args=(c1, c0)).pvalue > 1e-3, (c1, c0)

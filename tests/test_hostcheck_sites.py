@@ -201,7 +201,7 @@ def test_two_pass_form_equals_the_one_call_form():
     a, b = (ctypes.c_double * NOUT)(), (ctypes.c_double * NOUT)()
     va, vb, cls = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
     seen = {"gamma": set(), "beta": set()}
-    for i in range(6000):
+    for i in range(24000):
         s = int(g.integers(0, 9))
         if s < 3:
             lc = g.uniform(-1.0, 9.0); u1 = g.uniform(-7, 1); u0 = lc - u1
@@ -217,7 +217,7 @@ def test_two_pass_form_equals_the_one_call_form():
         seen["gamma" if s < 3 else "beta"].add(cls.value)
     # classes (cosmos_sites_fast.cuh): Gamma = bits (x < 0.8, conc > 8, conc > 10); Beta = density regime * 16 + the
     # branches of the two beta_grad_tierb calls -- every density regime and every branch must have been replayed
-    assert seen["gamma"] >= {-1, 0, 1, 2}, seen   # (x < 0.8 at concentration > 8 is a far-tail draw: not in 6000 tries)
+    assert seen["gamma"] >= {-1, 0, 1, 2}, seen   # (x < 0.8 at concentration > 8 is a far-tail draw: not in 24000 tries)
     beta = {c for c in seen["beta"] if c >= 0}
     assert {c // 16 for c in beta} == {0, 1, 2, 3} and {(c // 4) % 4 for c in beta} == {0, 1, 2, 3} and -1 in seen["beta"], seen
     assert max(beta) < 64
