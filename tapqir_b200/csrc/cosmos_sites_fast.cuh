@@ -341,9 +341,10 @@ TQ_HD int beta_tierb_branch(float x, float boundary, float alpha, float beta) {
     if (x >= 0.5f && boundary < 0.75f) return 1;
     return (alpha > 6.0f && beta > 6.0f) ? 2 : 3;
 }
+// `trials`: the site's Marsaglia-Tsang trial pairs (RNG mode); the caller may have preloaded its first block
 template <int MODE>
 TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
-                           Philox* rng, double& variate, float& sample, float* rec, float* extra, int& cls) {
+                           Philox* rng, GammaTrials& trials, double& variate, float& sample, float* rec, float* extra, int& cls) {
     if (!(mc.eps < 1e-12)) return SITE_FALLBACK_DRAW;   // fp32 reference conventions move the clamps into range
     if (site_is_gamma(s)) {
         // Gamma(loc * beta, beta): background cosmos.py:408-415, height cosmos.py:428-435
@@ -351,7 +352,7 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
         if (!(lconc > -4.0f && lconc < 13.0f) || fabsf(u1) > 40.0f) return SITE_FALLBACK_DRAW;
         const double ed = exp(-((double)u0 + (double)u1));         // 1 / conc
         const float ic = (float)ed, conc = site_rcp(ic);
-        if (use_rng) variate = fmax((double)sample_std_gamma_f32(*rng, conc), mc.tiny);
+        if (use_rng) variate = fmax((double)sample_std_gamma_f32(*rng, trials, conc), mc.tiny);
         const double xd = variate;
         if (!(xd > 1e-18) || !(xd < 1e18)) return SITE_FALLBACK;
         const double rd = xd * ed;                                 // x / conc
@@ -412,7 +413,6 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
     const float sz = expf(u1), S = 2.0f + sz;                     // size - 2 = d size / d u, size
     const float c1 = S * m1, c0 = S * m0;
     if (use_rng) {
-        GammaTrials trials;
         const double g1 = sample_std_gamma_f32(*rng, trials, c1), g2 = sample_std_gamma_f32(*rng, trials, c0);
         variate = beta01_from_gammas(g1, g2, mc);
     }
@@ -554,6 +554,12 @@ TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, cons
     return SITE_DONE;
 }
 
+template <int MODE>
+TQ_HD int site_eval_fast_t(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
+                           Philox* rng, double& variate, float& sample, float* rec, float* extra, int& cls) {
+    GammaTrials trials;
+    return site_eval_fast_t<MODE>(s, u0, u1, ubm, ubs, mc, use_rng, rng, trials, variate, sample, rec, extra, cls);
+}
 TQ_HD int site_eval_fast(int s, float u0, float u1, float ubm, float ubs, const ModelConst& mc, bool use_rng,
                          Philox* rng, double& variate, float& sample, float* rec, float* extra) {
     int cls = 0;

@@ -72,22 +72,36 @@ __device__ __forceinline__ void site_fast_finish(const LocalArgs<float>& a, int 
 // share `size`, which therefore stays with tq_adam_dense at the end of the step, as do the per-AOI background
 // parameters) and, on the background site, the spot-presence logits it turns into q(m).  Same arithmetic, same constants
 // (StepState), hence the same bits as adam_kernel.
-__device__ __forceinline__ float deferred_adam_at(const LocalArgs<float>& a, int64_t i, float p, float ss, float isb) {
-    const float g = a.adam_g[i];
-    float m = a.adam_m[i], v = a.adam_v[i];
+struct DeferredAdamLoads {   // gradient and moments of the (up to) two parameters a site owns
+    float g0, m0, v0, g1, m1, v1;
+};
+__device__ __forceinline__ float deferred_adam_at(const LocalArgs<float>& a, int64_t i, float p, float g, float m, float v, float ss, float isb) {
     adam_update(p, g, m, v, ss, isb, a.adam_b1, a.adam_b2, a.adam_eps);
     a.adam_p[i] = p; a.adam_m[i] = m; a.adam_v[i] = v;
     return p;
 }
-__device__ __forceinline__ void site_deferred_adam(const LocalArgs<float>& a, int s, SiteInputs<float>& in) {
+// issue the loads ...
+__device__ __forceinline__ DeferredAdamLoads site_deferred_adam_load(const LocalArgs<float>& a, int s, const SiteInputs<float>& in) {
+    DeferredAdamLoads l;
+    const int64_t i0 = a.lo.slab(site_param0(s)) + in.unit;
+    l.g0 = a.adam_g[i0]; l.m0 = a.adam_m[i0]; l.v0 = a.adam_v[i0];
+    l.g1 = l.m1 = l.v1 = 0.0f;
+    if (s < S_X) {
+        const int64_t i1 = a.lo.slab(site_param1(s)) + in.unit;
+        l.g1 = a.adam_g[i1]; l.m1 = a.adam_m[i1]; l.v1 = a.adam_v[i1];
+    }
+    return l;
+}
+// ... and use them after the (parameter-independent) Philox block of the site's first trials has been generated
+__device__ __forceinline__ void site_deferred_adam(const LocalArgs<float>& a, int s, SiteInputs<float>& in, const DeferredAdamLoads& l) {
     const float ss = a.state->step_size, isb = a.state->inv_sqrt_bc2;   // (re-read per unit: two registers less across the loop)
-    in.p0 = deferred_adam_at(a, a.lo.slab(site_param0(s)) + in.unit, in.p0, ss, isb);
-    if (s < S_X) in.p1 = deferred_adam_at(a, a.lo.slab(site_param1(s)) + in.unit, in.p1, ss, isb);
+    in.p0 = deferred_adam_at(a, a.lo.slab(site_param0(s)) + in.unit, in.p0, l.g0, l.m0, l.v0, ss, isb);
+    if (s < S_X) in.p1 = deferred_adam_at(a, a.lo.slab(site_param1(s)) + in.unit, in.p1, l.g1, l.m1, l.v1, ss, isb);
     if (s == S_B) {
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
             const int64_t i = a.lo.slab(LP_M_PROBS + k) + in.unit;
-            deferred_adam_at(a, i, a.adam_p[i], ss, isb);
+            deferred_adam_at(a, i, a.adam_p[i], a.adam_g[i], a.adam_m[i], a.adam_v[i], ss, isb);
         }
     }
 }
@@ -121,12 +135,18 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
         const uint32_t local = (uint32_t)j * kLocalBlock + threadIdx.x, u32 = base + local;
         if (u32 >= (uint32_t)a.U) break;
         SiteInputs<float> in = site_gather(a, s, u32);
-        if (adam_pending) site_deferred_adam(a, s, in);
+        DeferredAdamLoads al;
+        if (adam_pending) al = site_deferred_adam_load(a, s, in);
         Philox rng(a.seed, a.state->step, in.rng_offset);
+        GammaTrials trials;
+        // ~100 instructions that need no parameter: issued under the loads above (C3 on a B200: 1643 -> 1613 us; an explicit
+        // prefetch.global.L2 of the thread's next unit on top of it: 1670 us -- the kernel is issue-bound)
+        if (use_rng) trials.preload(rng);
+        if (adam_pending) site_deferred_adam(a, s, in, al);
         double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
         float v = 0.0f, rec[NSO], extra[NEX];
         int cls = 0;
-        const int status = site_eval_fast_t<1>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, variate, v, rec, extra, cls);
+        const int status = site_eval_fast_t<1>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, trials, variate, v, rec, extra, cls);
         if (status == SITE_DEFER) {
             deferred = true;
             const unsigned int pos = atomicAdd(&n_def, 1u);

@@ -496,12 +496,17 @@ struct Philox {
 // (normal, uniform) pairs for Marsaglia-Tsang trials, two per Philox block: the second waits here for the next trial --
 // of the same draw after a rejection, or of the next draw of the same site (a Beta variate is two gamma draws)
 struct GammaTrials {
-    float n1, u1;
-    bool spare = false;
+    float n0, u0, n1, u1;
+    int have = 0;
+    // fetch a block ahead of its use (it depends on nothing but the counter: a kernel issues it under the latency of its
+    // parameter loads); the pairs are consumed in the same order with or without it
+    TQ_HD void preload(Philox& rng) {
+        if (have == 0) { rng.normal_uniform_pairs(n0, u0, n1, u1); have = 2; }
+    }
     TQ_HD void draw(Philox& rng, float& xn, float& u) {
-        if (spare) { xn = n1; u = u1; spare = false; return; }
-        rng.normal_uniform_pairs(xn, u, n1, u1);
-        spare = true;
+        preload(rng);
+        if (have == 2) { xn = n0; u = u0; } else { xn = n1; u = u1; }
+        --have;
     }
 };
 
