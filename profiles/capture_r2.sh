@@ -6,7 +6,7 @@ for W in c3 c2; do
   CMD="python bench.py --workload $W --steps 3 --warmup 3 --no-cpu-baseline --no-subs --trained-iters 0"
   # (1) every launch of this library with its device time (cold-cache, serialised: compare SHARES)
   $CMD > gpurun_out/plain_r2_$W.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 27 -c 27 --csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 33 -c 33 --csv \
       --log-file gpurun_out/launches_r2_$W.csv $CMD > gpurun_out/ncu_launch_r2_$W.log 2>&1
   echo "$W launch list rc=$?"
   # (2) full capture of the likelihood, site and post kernels (one launch each, after warm-up)
