@@ -526,6 +526,9 @@ TQ_HD double sample_std_gamma_f32(Philox& rng, GammaTrials& trials, float alpha)
 #define TQ_SLOG(x) logf(x)
 #define TQ_SRSQRT(x) (1.0f / sqrtf(x))
 #endif
+    // the block of the first trial always comes first in the stream: a caller may have fetched it already (preload), and
+    // the draw must not depend on that
+    trials.preload(rng);
     double scale = 1.0;
     if (alpha < 1.0f) {
         // u^(1/alpha): the logarithm of a random number needs no more than fp32, the exponential needs double's range
