@@ -575,6 +575,110 @@ TQ_HD void finish_single_bin(const PairOut1& p, const SingleBinConst& sc, const 
     }
 }
 
+// ---- single offset bin, ROW form (sweep_patch_rows_single_bin): one row pair per lane, everything in units of a ----------
+// The lane's row factors arrive pre-multiplied by 1/gain (gyr = gy * rate), so mu' = gyr * gxh IS the spots' share of
+// a = image/gain and no pixel-configuration needs its own multiply; the spot moments are accumulated in the same units
+// (t' = S mu' = rate t: exactly the factor finish_single_bin applied afterwards).  d/d(1/gain) needs NO per-pixel work:
+// with W_m e_m = gi_m + W_m (gi = W (dL/da), the quantity the spot moments are made of)
+//   rate * sum_m W_m (a_m e_m - y/gain)  =  sumW dev + W_0 a_0 (ln(y/b) + q_0) + a_0 gsum + t'_0 + t'_1
+//                                           + (W_1 + W_3) mu'_0 + (W_2 + W_3) mu'_1,        dev = -(y - b)/gain
+// and every term's sum over the pixels is either accumulated anyway (sum dev, sum ln(y/b), sum gsum = g_b, sum t'_k =
+// the height moments) or separable (sum mu'_k = row factor x sum over columns of gxh_k).  60 packed operations per pixel
+// pair against 75 (B200, C3: kernel 3.57 -> see DESIGN 4.1).
+struct RowOut {
+    F2 logp[kM];                       // [0] unused
+    F2 g_b, g_h[kK], g_x[kK], g_w[kK];
+    F2 sum_dc, sum_dev;
+    float colsum[kK];                  // sum over the swept columns of gxh_k
+    TQ_HD void zero() {
+#pragma unroll
+        for (int m = 0; m < kM; ++m) logp[m] = f2(0.0f);
+        g_b = sum_dc = sum_dev = f2(0.0f);
+#pragma unroll
+        for (int k = 0; k < kK; ++k) { g_h[k] = g_x[k] = g_w[k] = f2(0.0f); colsum[k] = 0.0f; }
+    }
+};
+struct RowConst {
+    float off, off_rate, offb_rate, neg_rate;   // offset, offset / gain, (offset + b) / gain, -1 / gain
+};
+TQ_HD RowConst row_const(float off, float b, const FastConst& fc) {
+    return RowConst{off, off * fc.rate, (off + b) * fc.rate, -fc.rate};
+}
+
+// two pixels (rows r, r + 7) of one column; contract of pixel_pair_single_bin (every pixel above the offset, a >= 4)
+TQ_HD void row_pair_single_bin(F2 D, const float (&gxh)[kK], const F2 (&gyr)[kK], const float (&dx)[kK], const float (&dx2)[kK],
+                               const SingleBinConst& sc, const RowConst& rc, const float (&W)[kM], RowOut& out) {
+    F2 mu[kK], a[kM];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) mu[k] = mul2(gyr[k], f2(gxh[k]));
+    a[1] = add2(mu[0], f2(sc.a0));
+    a[2] = add2(mu[1], f2(sc.a0));
+    a[3] = add2(a[1], mu[1]);
+    const F2 y = sub2(D, f2(rc.off));
+    const F2 nry = fma2(D, f2(rc.neg_rate), f2(rc.off_rate));          // -y / gain
+    const F2 dev = fma2(D, f2(rc.neg_rate), f2(rc.offb_rate));         // -(y - b) / gain: small numbers, accurate sums
+    const F2 dc = fma2(lg2_2(y), f2(kLn2), f2(sc.neg_lnb));            // ln(y / b)
+    out.sum_dev = add2(out.sum_dev, dev);
+    out.sum_dc = add2(out.sum_dc, dc);
+    const F2 c1p1 = add2(dc, f2(sc.la0p1));                            // d/da [a log(rate) + lse] + 1
+    F2 gi[kM];
+#pragma unroll
+    for (int m = 1; m < kM; ++m) {
+        const F2 ia = rcp_2(a[m]), l2 = lg2_2(a[m]);
+        const F2 ia2 = mul2(ia, ia);
+        const F2 d = fma2(l2, f2(-kLn2), c1p1);                        // c1 + 1 - ln a
+        // a d - y/gain nearly cancels (a ~ y/gain): formed BEFORE it enters the running sum; ln(a)/2 and the Stirling
+        // remainder -r = ia (ia^2 / 360 - 1/12) go in directly (short tails for a >= 4: see pixel_pair_single_bin)
+        const F2 t1 = fma2(a[m], d, nry);
+        F2 lp = fma2(l2, f2(0.5f * kLn2), out.logp[m]);
+        lp = fma2(ia, fma2(ia2, f2(0.00277777778f), f2(-0.0833333333f)), lp);
+        out.logp[m] = add2(lp, t1);
+        // e = d + q,  q = ia (1/2 + ia (1/12 - ia^2 / 120)):  dL/da + 1
+        const F2 e = fma2(ia, fma2(ia, fma2(ia2, f2(-0.00833333333f), f2(0.0833333333f)), f2(0.5f)), d);
+        gi[m] = fma2(e, f2(W[m]), f2(-W[m]));                          // W dL/da
+    }
+    const F2 S[kK] = {add2(gi[1], gi[3]), add2(gi[2], gi[3])};
+    out.g_b = add2(out.g_b, add2(S[0], gi[2]));
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const F2 t = mul2(S[k], mu[k]);
+        out.g_h[k] = add2(out.g_h[k], t);
+        out.g_x[k] = fma2(t, f2(dx[k]), out.g_x[k]);
+        out.g_w[k] = fma2(t, f2(dx2[k]), out.g_w[k]);
+        out.colsum[k] += gxh[k];
+    }
+}
+
+// end of the lane's row pair: y- and dy^2-moments from the height moment (dy is fixed along a row), then the lane-level fold
+// into the scalar record (before the cross-lane reduction).  npix = pixels this lane swept (0 for the idle eighth lane)
+TQ_HD void finish_row_single_bin(const RowOut& p, const F2 (&gyr)[kK], const F2 (&dy)[kK], const SingleBinConst& sc,
+                                 const FastConst& fc, float log_w, const float (&W)[kM], int npix, PatchOut<float, kM>& out) {
+    const float n = float(npix);
+    const float sdc = p.sum_dc.x + p.sum_dc.y, sdev = p.sum_dev.x + p.sum_dev.y;
+    // terms shared by all configurations, -y/gain excepted: sum over pixels of  log w - ln y
+    const float common = n * (log_w + sc.neg_lnb) - sdc;
+    // spot-free configuration: a0 ln(y/b) + [a0 ln a0 - lgamma(a0)] - y/gain, with -y/gain = dev - a0
+    out.logp[0] = sc.a0 * sdc + n * (sc.K0 - sc.a0) + sdev + common;
+#pragma unroll
+    for (int m = 1; m < kM; ++m) out.logp[m] = (p.logp[m].x + p.logp[m].y) - n * kHalfLn2Pi + common;
+    const float gsum = p.g_b.x + p.g_b.y, w0 = W[0] * (sdc + n * sc.q0);
+    out.g_b = (gsum + w0) * fc.rate;
+    float grate = (W[0] + W[1] + W[2] + W[3]) * sdev + sc.a0 * (w0 + gsum);
+    const float Wk[kK] = {W[1] + W[3], W[2] + W[3]};
+#pragma unroll
+    for (int k = 0; k < kK; ++k) {
+        const F2 gy = fma2(mul2(dy[k], dy[k]), p.g_h[k], p.g_w[k]);    // sum t' (dx^2 + dy^2)
+        const F2 gyy = mul2(p.g_h[k], dy[k]);                          // sum t' dy
+        const float h = p.g_h[k].x + p.g_h[k].y;
+        out.g_h[k] = h;
+        out.g_x[k] = p.g_x[k].x + p.g_x[k].y;
+        out.g_y[k] = gyy.x + gyy.y;
+        out.g_w[k] = gy.x + gy.y;
+        grate += h + Wk[k] * ((gyr[k].x + gyr[k].y) * p.colsum[k]);
+    }
+    out.g_rate = grate * fc.gain;
+}
+
 // lane-level fold of the pair sums into the scalar record (before the cross-lane reduction)
 TQ_HD void finish_pair(const PairOut& p, float rate, PatchOut<float, kM>& out) {
 #pragma unroll

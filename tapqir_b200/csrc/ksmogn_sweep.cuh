@@ -161,8 +161,9 @@ __device__ __forceinline__ void sweep_patch_pairs(const float* __restrict__ pix,
 // Single offset bin, ROW mapping: lane r < 7 of the patch's eight takes the row pair (r, r + 7) and walks the 14 columns.
 // Row factors and distances stay in registers for the whole patch, the column index is a compile-time constant (tables
 // and pixels at immediate offsets: no index arithmetic, no branch in the loop), and the y / dy^2 moments follow from the
-// height moment at the end of the row (single_bin_row_fixup).  14 trips of 75 packed + 18 other instructions against 13
-// trips of 79 + 41 in the (row, col) = (p / 14, p % 14) walk; the eighth lane idles through the sweep.
+// height moment at the end of the row (finish_row_single_bin).  14 trips of 60 packed + ~20 other instructions (round 2:
+// 75 + 21 before the sweep moved to units of a = image / gain, ksmogn_fast.cuh "ROW form") against 13 trips of 79 + 41 in the
+// (row, col) = (p / 14, p % 14) walk; the eighth lane idles through the sweep.
 #ifndef TQ_ROW_UNROLL
 #define TQ_ROW_UNROLL 7   // two trips of seven: the fully unrolled loop (21 KB) stalled on instruction fetch (C3 kernel 3.64 vs 3.58 ms)
 #endif
@@ -171,26 +172,29 @@ __device__ __forceinline__ void sweep_patch_rows_single_bin(const float* __restr
                                                             const PatchSpots<float>& s, const FastConst& fc, float off,
                                                             float log_w, const float (&W)[kM], PatchOut<float, kM>& out) {
     const SingleBinConst sc = single_bin_const(s.b, fc);
-    PairOut1 po;
+    const RowConst rc = row_const(off, s.b, fc);
+    RowOut po;
     po.zero();
     int npix = 0;
+    F2 gyr[kK] = {f2(0.0f), f2(0.0f)}, dy[kK] = {f2(0.0f), f2(0.0f)};
     if (sub < 7) {
         const float4* col4 = reinterpret_cast<const float4*>(tab);
         const float4* row4 = reinterpret_cast<const float4*>(tab + 14 * 8);
         const float4 r0 = row4[sub * 2], r1 = row4[sub * 2 + 1];
-        const F2 gyk[kK] = {F2{r0.x, r0.y}, F2{r0.z, r0.w}}, dy[kK] = {F2{r1.x, r1.y}, F2{r1.z, r1.w}};
+        gyr[0] = mul2(F2{r0.x, r0.y}, f2(fc.rate)); gyr[1] = mul2(F2{r0.z, r0.w}, f2(fc.rate));
+        dy[0] = F2{r1.x, r1.y}; dy[1] = F2{r1.z, r1.w};
         const float* p0 = pix + sub * 14;
 #pragma unroll kRowUnroll
         for (int c = 0; c < 14; ++c) {
-            const float4 c0 = col4[c * 2], c1 = col4[c * 2 + 1];
+            const float4 c0 = col4[c * 2];
+            const float2 c1 = *reinterpret_cast<const float2*>(col4 + c * 2 + 1);
             const float gxh[kK] = {c0.x, c0.y}, dx[kK] = {c0.z, c0.w}, dx2[kK] = {c1.x, c1.y};
             const F2 D{p0[c], p0[c + 98]};
-            pixel_pair_single_bin<true>(D, gxh, gyk, dx, dx2, dy, s, fc, sc, off, W, po);
+            row_pair_single_bin(D, gxh, gyr, dx, dx2, sc, rc, W, po);
         }
-        single_bin_row_fixup(po, dy);
         npix = 28;
     }
-    finish_single_bin(po, sc, fc, s.b, log_w, W[0], npix, out);
+    finish_row_single_bin(po, gyr, dy, sc, fc, log_w, W, npix, out);
 }
 
 // the same pair mapping for O > 4 offset bins (ksmogn_fast.cuh: "many offset bins"); bins: per-bin constants in shared memory

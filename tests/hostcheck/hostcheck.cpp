@@ -107,14 +107,15 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
             finish_pair(po, fc.rate, out);
         } else if (pairs && OC == 1) {
             const SingleBinConst sc = single_bin_const(s.b, fc);
-            // the kernel's row mapping (sweep_patch_rows_single_bin): one row pair at a time, y / dy^2 moments from the
-            // height moment at the end of the row; the seven rows' partial sums are then added (the kernel: across lanes)
-            PairOut1 po; po.zero();
+            const RowConst rc = row_const(off_s[0], s.b, fc);
+            // the kernel's row mapping (sweep_patch_rows_single_bin): one row pair at a time in units of a = image / gain,
+            // folded per row (the kernel: per lane) into the scalar record; the seven rows' records are then added (the
+            // kernel: across lanes)
             for (int row = 0; row < 7; ++row) {
-                PairOut1 pr; pr.zero();
-                F2 gyk[kK], dy[kK];
+                RowOut pr; pr.zero();
+                F2 gyr[kK], dy[kK];
                 for (int k = 0; k < kK; ++k) {
-                    gyk[k] = F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])};
+                    gyr[k] = mul2(F2{axis_factor<float>(row, s.cy[k], s.w[k]), axis_factor<float>(row + 7, s.cy[k], s.w[k])}, f2(fc.rate));
                     dy[k] = F2{float(row) - s.cy[k], float(row + 7) - s.cy[k]};
                 }
                 for (int col = 0; col < 14; ++col) {
@@ -125,18 +126,16 @@ void hc_ksmogn_fast_f32(int64_t U, int P, int O, int OC, const float* height, co
                         dx2[k] = dx[k] * dx[k];
                     }
                     const F2 D{value[(u * P + row) * P + col], value[(u * P + row + 7) * P + col]};
-                    pixel_pair_single_bin<true>(D, gxh, gyk, dx, dx2, dy, s, fc, sc, off_s[0], Wm, pr);
+                    row_pair_single_bin(D, gxh, gyr, dx, dx2, sc, rc, Wm, pr);
                 }
-                single_bin_row_fixup(pr, dy);
-                for (int m = 0; m < kM; ++m) po.logp[m] = add2(po.logp[m], pr.logp[m]);
-                po.g_b = add2(po.g_b, pr.g_b); po.g_rate = add2(po.g_rate, pr.g_rate);
-                po.sum_dc = add2(po.sum_dc, pr.sum_dc); po.sum_yb = add2(po.sum_yb, pr.sum_yb);
+                PatchOut<float, kM> part; part.zero();
+                finish_row_single_bin(pr, gyr, dy, sc, fc, w2[0] * kLn2, Wm, 28, part);
+                for (int m = 0; m < kM; ++m) out.logp[m] += part.logp[m];
+                out.g_b += part.g_b; out.g_rate += part.g_rate;
                 for (int k = 0; k < kK; ++k) {
-                    po.g_h[k] = add2(po.g_h[k], pr.g_h[k]); po.g_w[k] = add2(po.g_w[k], pr.g_w[k]);
-                    po.g_x[k] = add2(po.g_x[k], pr.g_x[k]); po.g_y[k] = add2(po.g_y[k], pr.g_y[k]);
+                    out.g_h[k] += part.g_h[k]; out.g_w[k] += part.g_w[k]; out.g_x[k] += part.g_x[k]; out.g_y[k] += part.g_y[k];
                 }
             }
-            finish_single_bin(po, sc, fc, s.b, w2[0] * kLn2, Wm[0], P * P, out);
         } else if (pairs) {
             PairOut po; po.zero();
             auto run = [&](auto oc_tag) {
