@@ -61,7 +61,8 @@ def algorithmic_work(o_exec):
     * SURVEY.md 8(d)'s estimate: 980 O + 3276 MUFU ops, 8232 O + 63220 flops (an upper estimate written before the
       kernel existed: per-bin terms for every configuration, separate lgamma / digamma / log-sum evaluations);
     * the EXECUTED count of this repository's formulation, read off the SASS of the packed two-pixel sweep
-      (profiles/r2_sass_ksmogn_o1.txt: per pixel pair 37 FFMA2 + 24 FADD2 + 14 FMUL2 + 14 MUFU, 98 pairs per patch):
+      (profiles/r2_sass_ksmogn_o1.txt: per pixel pair 34 FFMA2 + 16 FADD2 + 7 FMUL2 + 2 FADD + 14 MUFU, 98 pairs per patch;
+      mid round 2: 37 + 24 + 14, round 1: 85 packed):
         MUFU:  P^2 O [lg2(D - delta)] + M P^2 (O + 3) [ex2 per bin, rcp, lg2 a, lg2 sum]   (O > 1)
                P^2   + (M - 1) P^2 2  [rcp a, lg2 a; the spot-free configuration is a closed form]   (O = 1)
                + 2 K P [separable render]
@@ -72,7 +73,7 @@ def algorithmic_work(o_exec):
     pairs = P2 // 2
     if o_exec == 1:
         mufu = P2 + (M - 1) * P2 * 2 + 2 * K * P
-        ffma2, fadd2, fmul2, fadd, fmul = 37, 24, 14, 0, 0
+        ffma2, fadd2, fmul2, fadd, fmul = 34, 16, 7, 2, 0
     elif o_exec <= 4:   # register-cached bins: per pair 35 + 53 O packed (of which ~55 % FMAs), 13 scalar
         mufu = P2 * o_exec + M * P2 * (o_exec + 3) + 2 * K * P
         packed = 35 + 53 * o_exec - 1

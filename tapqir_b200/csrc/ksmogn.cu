@@ -192,11 +192,15 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
     const unsigned U = (unsigned)a.U, n_wg = (U + 3u) >> 2;
     const unsigned stride = gridDim.x * kWarpsPerBlock;
 
+    const bool dense_units = a.v.ndx == nullptr && a.v.fdx == nullptr && a.v.fb == a.v.F;
     // issue the copies of group g: this lane's share of its slot's patch and two of the slot's 15 scalars
     unsigned pix_off = 0u, pix_off_next = 0u, phase = 0u;   // bulk staging: where the patch starts in its slot; mbarrier phase
     auto prefetch = [&](unsigned g) {
         const unsigned u_raw = g * 4u + wslot, u = u_raw < U ? u_raw : U - 1u;
-        const UnitIndex ui = locate_unit32(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
+        // whole frames of consecutive AOIs (every full-batch step): the unit index IS the patch index
+        UnitIndex ui;
+        if (dense_units) ui.patch = (int64_t)u;
+        else ui = locate_unit32(u, a.v.fb, a.v.C, a.v.F, a.v.ndx, a.v.fdx);
         if (PF && bulk) {
             // 392 B at an 8-byte stride: odd patches start 8 bytes off a 16-byte boundary.  The 384 aligned bytes go by
             // one bulk copy, the other 8 (head of an odd patch, tail of an even one) by one cp.async; the patch lands

@@ -460,14 +460,16 @@ struct SingleBinConst {
 TQ_HD SingleBinConst single_bin_const(float b, const FastConst& fc) {
     SingleBinConst c;
     c.a0 = b * fc.rate;
-    const float ia = rcp_newton(c.a0), la0 = logf(c.a0);
+    // MUFU logarithms (absolute error 2e-7): the same approximation every pixel's ln(y/b) goes through, and the
+    // library logf is ~20 instructions of a per-patch prologue that is a quarter of the kernel
+    const float ia = rcp_newton(c.a0), la0 = kLn2 * f_lg2(c.a0);
     float r, q;
     stirling(ia, r, q);
     c.la0p1 = la0 + 1.0f;
     c.q0 = q;
     c.q0p1 = q + 1.0f;
     c.K0 = 0.5f * la0 + c.a0 - kHalfLn2Pi - r;
-    c.neg_lnb = -logf(b);
+    c.neg_lnb = -kLn2 * f_lg2(b);
     return c;
 }
 
