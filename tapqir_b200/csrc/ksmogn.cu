@@ -164,6 +164,19 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
         off_s[j] = static_cast<const float*>(a.v.offset_samples)[j];
         off_w2[j] = static_cast<const float*>(a.v.offset_logits)[j] * kLog2e;
     }
+    // where each of a patch's eight lanes stores its two results (epilogue)
+    __shared__ float* out_ptr[kSub][2];
+    if (BWD && threadIdx.x < kSub) {
+        const int l = threadIdx.x;
+        const size_t Uz = (size_t)a.U;
+        float* p0 = nullptr;
+        float* p1 = nullptr;
+        if (l < 2) { if (a.logp) { p0 = a.logp + (size_t)(2 * l) * Uz; p1 = p0 + Uz; } }
+        else if (l == 2) { p0 = a.g_background; p1 = a.g_rate; }
+        else if (l < 7) { p0 = l == 3 ? a.g_height : l == 4 ? a.g_width : l == 5 ? a.g_x : a.g_y; p1 = p0 + Uz; }
+        out_ptr[l][0] = p0;
+        out_ptr[l][1] = p1;
+    }
     FastConst fc;
     fc.gain = a.gain[0];
     fc.rate = 1.0f / fc.gain;
@@ -332,35 +345,35 @@ ksmogn_stream_kernel(const KsmognArgs<float> a, unsigned int* __restrict__ count
         else
             sweep_patch<OC, P14, BWD, false>(spx, P, PP, sub, gx, gy, s, norm, fc, O, off_s, off_w2, W, Wr, out);
 
-#pragma unroll
-        for (int m = 0; m < kM; ++m) out.logp[m] = sub_sum(out.logp[m]);
         if (BWD) {
-            out.g_b = sub_sum(out.g_b);
-            out.g_rate = sub_sum(out.g_rate);
+            // the 14 sums of a patch, reduce-scattered: lane 0 of its eight ends with logp[0], logp[1]; 1: logp[2], logp[3];
+            // 2: d/d background, d/d (1/gain); 3: the height moments A0; 4: A3; 5: A1; 6: A2 (k = 0, 1 each); 7: nothing
+            const float v[16] = {out.logp[0], out.logp[1], out.logp[2], out.logp[3], out.g_b, out.g_rate, out.g_h[0], out.g_h[1],
+                                 out.g_w[0], out.g_w[1], out.g_x[0], out.g_x[1], out.g_y[0], out.g_y[1], 0.0f, 0.0f};
+            float y[kK];
+            sub_reduce_scatter16(v, sub, y[0], y[1]);
+            // moments -> gradients (finish_spot_moments, the same arithmetic on every lane's own pair; d/dw also needs A0)
+            PatchOut<float, kM> fin;
 #pragma unroll
             for (int k = 0; k < kK; ++k) {
-                out.g_h[k] = sub_sum(out.g_h[k]);
-                out.g_w[k] = sub_sum(out.g_w[k]);
-                out.g_x[k] = sub_sum(out.g_x[k]);
-                out.g_y[k] = sub_sum(out.g_y[k]);
+                fin.g_h[k] = __shfl_sync(kFull, y[k], (lane & ~7) | 3);
+                fin.g_w[k] = fin.g_x[k] = fin.g_y[k] = y[k];
             }
-            finish_spot_moments(s, out);
-        }
-        if (live && sub == 0) {
-            if (a.logp) {
+            finish_spot_moments(s, fin);
+#pragma unroll
+            for (int k = 0; k < kK; ++k) y[k] = sub == 3 ? fin.g_h[k] : sub == 4 ? fin.g_w[k] : sub >= 5 ? fin.g_x[k] : y[k];
+            if (live) {
+                float* const p0 = out_ptr[sub][0];
+                float* const p1 = out_ptr[sub][1];
+                if (p0) p0[u] = y[0];
+                if (p1) p1[u] = y[1];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < kM; ++m) out.logp[m] = sub_sum(out.logp[m]);
+            if (live && sub == 0 && a.logp) {
 #pragma unroll
                 for (int m = 0; m < kM; ++m) a.logp[(size_t)m * U + u] = out.logp[m];
-            }
-            if (BWD) {
-                a.g_background[u] = out.g_b;
-                a.g_rate[u] = out.g_rate;
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
-                    a.g_height[(size_t)k * U + u] = out.g_h[k];
-                    a.g_width[(size_t)k * U + u] = out.g_w[k];
-                    a.g_x[(size_t)k * U + u] = out.g_x[k];
-                    a.g_y[(size_t)k * U + u] = out.g_y[k];
-                }
             }
         }
         cur = nxt;

@@ -707,7 +707,7 @@ TQ_HD void finish_spot_moments(const PatchSpots<float>& s, PatchOut<float, kM>& 
         out.g_h[k] = A0 * rcp_newton(s.h[k]);
         out.g_x[k] *= iw2;
         out.g_y[k] *= iw2;
-        out.g_w[k] = iw * (iw2 * A3 - 2.0f * A0);
+        out.g_w[k] = iw * fmaf(iw2, A3, -2.0f * A0);   // (explicit: two kernels evaluate this and must round alike)
     }
 }
 
