@@ -313,7 +313,7 @@ def roofline_of(model, timer, peaks, hbm_peak, hbm_src, ms_per_step, steps, worl
                     if bound[1] == "fp32" else "executed ops of the binding unit / kernel time / its measured peak",
             "frac_pipe_slots": "FP32-pipe lane operations (FMA, add, mul each one slot) / kernel time / measured lane-op peak: how busy the binding pipe is",
             "frac_survey_8d": "SURVEY 8(d)'s per-unit estimate at the executed number of offset bins / kernel time / peak (estimate written before the kernel: > 1 possible, the kernel needs less work than it assumes)",
-            "frac_round1_work_count": "round 1's accounting kept for continuity: ITS executed count (18632 FP32 lane operations per unit at one bin, every packed instruction as two FMAs) / kernel time / lane-op peak -- 0.49 at C2 and 0.62 at C3 in round 1; the kernel now needs 16182",
+            "frac_round1_work_count": "round 1's accounting kept for continuity: ITS executed count (18632 FP32 lane operations per unit at one bin, every packed instruction as two FMAs) / kernel time / lane-op peak -- 0.49 at C2 and 0.62 at C3 in round 1; the kernel now needs 11968",
         },
         "frac_pipe_slots": units_per_s * max(t_pipe, t_mufu),
         "frac_survey_8d": units_per_s * t8,
@@ -327,6 +327,9 @@ def roofline_of(model, timer, peaks, hbm_peak, hbm_src, ms_per_step, steps, worl
         # the whole step against the same roofline (time the likelihood's executed work would take at peak / step time)
         "step_roofline_frac": (patches / (ms_per_step * 1e-3)) * (w["fp32_flop"] / flop_peak if bound[1] == "fp32" else bound[0]),
         "step_frac_pipe_slots": (patches / (ms_per_step * 1e-3)) * max(t_pipe, t_mufu),
+        # round 1's step-level figure (0.28 at C2): ITS work count of the likelihood sweep at peak / the whole step's time
+        "step_frac_round1_work_count": ((patches / (ms_per_step * 1e-3)) * ROUND1_LANE_OPS[o_exec] / fma_peak_ops
+                                        if o_exec in ROUND1_LANE_OPS else None),
     }
 
 
@@ -427,7 +430,7 @@ def run_native(args):
             r = res["roofline"]
             subs[name]["roofline"] = {k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "frac_pipe_slots",
                                                         "frac_survey_8d", "frac_round1_work_count", "kernel_ms", "kernel_share_of_step",
-                                                        "step_roofline_frac")}
+                                                        "step_roofline_frac", "step_frac_round1_work_count")}
             m.engine.close()
             del m
             torch.cuda.empty_cache()
