@@ -41,6 +41,8 @@ WORKLOADS = {
     "c2mb": (100, 1000, 10, 512, "cosmos C2: simulated N=100 AOIs x F=1000 frames, reference-default minibatch 10 AOIs x 512 frames (main.py:1428-1431)"),
     "c1": (5, 100, 5, 100, "cosmos C1: simulated N=5 AOIs x F=100 frames, full batch"),
     "c3s8": (125, 5000, 125, 5000, "one rank's shard of C3 at 8 GPUs (125 AOIs x 5000 frames) on its own: what the strong-scaling step costs without the exchange"),
+    "c3s4": (250, 5000, 250, 5000, "one rank's shard of C3 at 4 GPUs (250 AOIs x 5000 frames) on its own"),
+    "c3s2": (500, 5000, 500, 5000, "one rank's shard of C3 at 2 GPUs (500 AOIs x 5000 frames) on its own"),
     # BASELINE configs 4 and 5 (parity-test cases; here for per-config timings, not the headline line)
     "c4": (500, 2000, 500, 2000, "cosmos C4: two-channel (C=2) simulated N=500 AOIs x F=2000 frames, full batch"),
     "c5": (200, 2000, 200, 2000, "cosmos+hmm C5: simulated N=200 AOIs x F=2000 frames, all frames per step"),

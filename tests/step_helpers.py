@@ -10,8 +10,8 @@ from tapqir_b200.models import layout as L
 from tapqir_b200.utils.simulate import simulate
 
 
-def make_problem(N=4, F=6, C=1, nb=3, fb=4, seed=0, perturb=True, offsets="sim", dtype=torch.float64):
-    kw = {}
+def make_problem(N=4, F=6, C=1, nb=3, fb=4, seed=0, perturb=True, offsets="sim", dtype=torch.float64, P=14):
+    kw = {} if P == 14 else {"P": P}   # AOI size (the reference's `--aoi-size`; 14 is the default of glimpse and simulate)
     if offsets == "hist":
         s = torch.arange(80.0, 96.0)
         w = torch.exp(-0.5 * ((s - 90) / 3) ** 2) + 1e-3

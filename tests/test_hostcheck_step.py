@@ -18,6 +18,8 @@ from tests.step_helpers import check_global_grads, compare_grads, host_step, mak
     dict(N=4, F=5, C=2, nb=4, fb=3, seed=1),
     dict(N=3, F=4, C=1, nb=3, fb=4, seed=2, offsets="hist"),
     dict(N=4, F=6, C=1, nb=2, fb=6, seed=3, perturb=False),
+    dict(N=3, F=5, C=1, nb=3, fb=5, seed=5, P=10),   # another AOI size: the +-(P+1)/2 position range, the proximity constraint
+    dict(N=2, F=3, C=1, nb=1, fb=3, seed=6, P=17),
 ])
 def test_step_f64_matches_oracle(cfg):
     hc = hostcheck.load()

@@ -37,6 +37,11 @@ CONFIGS = [
     dict(N=3, F=4, C=1, nb=3, fb=4, seed=2, offsets="hist"),
     dict(N=5, F=100, C=1, nb=5, fb=100, seed=3, perturb=False),   # BASELINE config 1 shape, full batch
     dict(N=6, F=70, C=1, nb=4, fb=33, seed=4),
+    # AOI sizes other than 14 (generic sweep of the likelihood kernel, P-dependent ranges and constraints) with launch sizes
+    # that are not a multiple of a warp's four patches, and a single-AOI, single-frame minibatch
+    dict(N=3, F=5, C=1, nb=3, fb=5, seed=5, P=10),
+    dict(N=2, F=3, C=2, nb=1, fb=3, seed=6, P=17),
+    dict(N=3, F=4, C=1, nb=1, fb=1, seed=7, f64_only=True),
 ]
 
 
@@ -45,6 +50,13 @@ CONFIGS = [
 # ill-conditioned near x = mean, evaluation order moves it at the 1e-9 level; see test_hostcheck_math)
 @pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
 def test_step_loss_and_grads_match_oracle(cfg, dtype, ltol, gtol):
+    cfg = dict(cfg)
+    if cfg.pop("f64_only", False) and dtype == torch.float32:
+        # a single unit leaves each gradient tensor with one unit's entries as its scale: d loss / d m_probs is
+        # q1 q0 x (differences of the four log-likelihoods, |L| ~ 3e3), and fp32 rounding of L alone is 2e-4 absolute -- 3e-5
+        # to 1e-4 of a gradient of 20-70 (the host build of the same arithmetic shows the same); in a real minibatch the
+        # tensor's scale is ~1e3.  The launch-shape path this case is here for is dtype-independent
+        pytest.skip("single-unit minibatch: launch-shape case, checked in float64")
     ds, data, params, ndx, fdx, noise = make_problem(**cfg)
     if dtype == torch.float32:  # both sides see the same fp32-rounded parameters and variates
         params = {k: v.float().double() for k, v in params.items()}
