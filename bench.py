@@ -53,7 +53,25 @@ O_BINS = 3   # offset bins of the simulated data (simulate.py:92,103): three IDE
 SUBS = {     # sub-results of the N=1 line: name -> (workload, offset_hist, keep_offset_bins)
     "c2": ("c2", 0, False), "c2mb": ("c2mb", 0, False), "c2_o3": ("c2", 0, True), "c2_o64": ("c2", 64, False),
     "c4": ("c4", 0, False), "c5": ("c5", 0, False),   # BASELINE configs 4 (two channels) and 5 (cosmos+hmm)
+    "c3_o3": ("c3", 0, True),   # the headline workload with the simulator's three bins kept distinct: SURVEY 8(d)'s own case
 }
+
+
+def north_star_check(peaks, main_value, subs):
+    """The north-star target read literally: ">= 50 % of the compute-bound roofline on 1 B200" with SURVEY.md 8(d)'s
+    definition of that roofline -- time per unit = max(MUFU ops / MUFU peak, flops / FP32 peak) of ITS per-unit work
+    estimate at O = 3 distinct offset bins (6216 MUFU ops, 87916 flops), against the peaks measured on this GPU -- and the
+    whole step's throughput (not one kernel's) as the numerator."""
+    def roof(o):
+        w = algorithmic_work(o)["survey_8d"]
+        return 1.0 / max(w["mufu_ops"] / peaks["mufu"], w["fp32_flop"] / (2.0 * peaks["fma"]))   # FMA = 2 flops
+    out = {"target": ">= 0.5 of SURVEY 8(d)'s step roofline on 1 B200 (north_star)",
+           "survey_8d_step_roofline": {"o3_aoi_frames_per_s": roof(3), "o1_aoi_frames_per_s": roof(1), "peaks": "measured in this run"},
+           "c3_merged_bins_over_o3_roofline": main_value / roof(3),
+           "c3_merged_bins_over_o1_roofline": main_value / roof(1)}
+    if subs and "c3_o3" in subs:
+        out["c3_three_bins_kept_over_o3_roofline"] = subs["c3_o3"]["value"] / roof(3)
+    return out
 
 
 def algorithmic_work(o_exec):
@@ -449,6 +467,7 @@ def run_native(args):
             "config": config_of(args.workload, world, args.scaling, args.offset_hist, args.keep_offset_bins, args.train_iters),
             "roofline": main["roofline"], "cpu_baseline": cpu_baseline, "e2e": main["e2e"],
             "trained_state": main.get("trained_state"), "sub_results": subs,
+            "north_star": north_star_check(peaks, main["value"], subs) if world == 1 and args.workload == "c3" else None,
             "gpu_launches": launches, "clocks": main["clocks"],
             "wall_s_timed_region": main["wall_s_timed_region"], "final_loss": main["final_loss"],
         }
