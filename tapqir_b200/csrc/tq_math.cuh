@@ -412,6 +412,15 @@ template <typename T> TQ_HD_NOINLINE void beta_grad_pair(T x, T c1, T c0, T& g1,
 }
 
 // ---- Philox4x32-10 counter RNG -----------------------------------------------------------------
+#ifndef TQ_PHILOX_UNROLL
+// Rounds unrolled per trip.  Two, not ten: the guide-site kernel inlines the block generator half a dozen times inside 114 KB of
+// SASS, and on a trained model -- where its warps walk most of that code -- instruction fetch is its largest stall reason.
+// B200, one 8-GPU rank's C3 shard, site kernel at the initial point / after 1000 / 3000 iterations: 191 / 246 / 499 us
+// unrolled by ten, 190 / 236 / 438 by two, 194 / 242 / 444 by one, 190 / 239 / 449 as one out-of-line function
+// (profiles/r2s2_sites_icache.md).  Same arithmetic, same bits.
+#define TQ_PHILOX_UNROLL 2
+#endif
+constexpr int kPhiloxUnroll = TQ_PHILOX_UNROLL;
 struct Philox {
     uint32_t key[2];
     uint32_t ctr[4];
@@ -434,7 +443,7 @@ struct Philox {
     TQ_HD void block(uint32_t (&c)[4]) {
         c[0] = ctr[0]; c[1] = ctr[1]; c[2] = ctr[2]; c[3] = ctr[3];
         uint32_t k[2] = {key[0], key[1]};
-#pragma unroll
+#pragma unroll kPhiloxUnroll
         for (int r = 0; r < 10; ++r) {
             round(c, k);
             k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
