@@ -185,6 +185,124 @@ __global__ void __launch_bounds__(kLocalBlock, 8) site_fast_kernel(const LocalAr
     }
 }
 
+// ---- the two passes as two launches (TQ_SITE_SPLIT=1; profiles/r2s2_sites_icache.md) ------------------------------------------
+// On a trained model the kernel above is instruction-fetch bound: 106 KB of SASS, and an SM's eight blocks are spread over the
+// sampler, the bulk forms (pass 1) and the regime classes of the replay (pass 2).  Split, every SM runs pass-1 code OR pass-2 code.
+// A deferred site parks its base variate (8 bytes) and its class in its OWN, not yet written, rows of the record buffer
+// -- no list, no extra memory -- under a NaN marker with a payload; the second launch (a resident wave of blocks walking
+// the spans of the first) finds the parked sites of a span, sorts them by class in shared memory and replays them exactly as
+// pass 2 above does.  A launch with nothing deferred costs its blocks one read of a counter.
+constexpr unsigned int kParkMarker = 0x7FD00000u;          // quiet NaN, payload = regime class in the low byte
+__device__ unsigned int g_site_deferred[8];                 // sites deferred by the current launch, per stream slot
+
+template <int kSiteUPT>
+__global__ void __launch_bounds__(kLocalBlock, 8) site_pass1_kernel(const LocalArgs<float> a, unsigned int* __restrict__ n_deferred) {
+    constexpr int kSiteSpan = kLocalBlock * kSiteUPT;
+    const int s = blockIdx.y;
+    const uint32_t base = blockIdx.x * (uint32_t)kSiteSpan;
+    const bool use_rng = a.noise_in == nullptr;
+    const bool adam_pending = a.adam_p != nullptr && a.state->pending != 0u;
+    unsigned int parked = 0u;
+#pragma unroll 1
+    for (int j = 0; j < kSiteUPT; ++j) {
+        const uint32_t u32 = base + (uint32_t)j * kLocalBlock + threadIdx.x;
+        if (u32 >= (uint32_t)a.U) break;
+        SiteInputs<float> in = site_gather(a, s, u32);
+        DeferredAdamLoads al;
+        if (adam_pending) al = site_deferred_adam_load(a, s, in);
+        Philox rng(a.seed, a.state->step, in.rng_offset);
+        GammaTrials trials;
+        if (use_rng) trials.preload(rng);
+        if (adam_pending) site_deferred_adam(a, s, in, al);
+        double variate = use_rng ? 0.0 : (double)a.noise_in[(int64_t)s * a.U + u32];
+        float v = 0.0f, rec[NSO], extra[NEX];
+        int cls = 0;
+        const int status = site_eval_fast_t<1>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, use_rng, &rng, trials, variate, v, rec, extra, cls);
+        if (status == SITE_DEFER) {
+            const long long bits = __double_as_longlong(variate);
+            float* r = a.rec + (int64_t)s * NSO * a.U + u32;
+            r[(int64_t)SO_A0 * a.U] = __int_as_float((int)(bits & 0xffffffffll));
+            r[(int64_t)SO_B0 * a.U] = __int_as_float((int)(bits >> 32));
+            r[(int64_t)SO_LQ * a.U] = __uint_as_float(kParkMarker | (unsigned int)cls);
+            ++parked;
+        } else {
+            site_fast_finish(a, s, u32, status, v, rec, extra);
+        }
+        if (s == S_B) write_presence_weights(a, in, (int64_t)u32);
+    }
+    const unsigned int warp_parked = __reduce_add_sync(0xffffffffu, parked);
+    if ((threadIdx.x & 31) == 0 && warp_parked) atomicAdd(n_deferred, warp_parked);
+}
+
+template <int kSiteUPT>
+__global__ void __launch_bounds__(kLocalBlock, 8) site_pass2_kernel(const LocalArgs<float> a, const unsigned int* __restrict__ n_deferred,
+                                                                    unsigned int spans_per_site) {
+    constexpr int kSiteSpan = kLocalBlock * kSiteUPT;
+    if (*n_deferred == 0u) return;
+    __shared__ unsigned int cnt[kSiteClasses], off[kSiteClasses + 1], fill[kSiteClasses], n_def;
+    __shared__ double t_var[kSiteSpan], s_var[kSiteSpan];
+    __shared__ unsigned short t_idx[kSiteSpan], s_idx[kSiteSpan];
+    __shared__ unsigned char t_cls[kSiteSpan];
+    const unsigned int n_spans = spans_per_site * NSAMP;
+    for (unsigned int span = blockIdx.x; span < n_spans; span += gridDim.x) {
+        const int s = (int)(span / spans_per_site);
+        const uint32_t base = (span - (unsigned int)s * spans_per_site) * (uint32_t)kSiteSpan;
+        if (threadIdx.x < kSiteClasses) { cnt[threadIdx.x] = 0u; fill[threadIdx.x] = 0u; }
+        if (threadIdx.x == 0) n_def = 0u;
+        __syncthreads();
+        const float* r = a.rec + (int64_t)s * NSO * a.U;
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < kSiteUPT; ++j) {
+            const uint32_t local = (uint32_t)j * kLocalBlock + threadIdx.x, u32 = base + local;
+            if (u32 < (uint32_t)a.U) {
+                const unsigned int m = __float_as_uint(r[(int64_t)SO_LQ * a.U + u32]);
+                if ((m & 0xffffff00u) == kParkMarker) {
+                    const unsigned int lo = __float_as_uint(r[(int64_t)SO_A0 * a.U + u32]), hi = __float_as_uint(r[(int64_t)SO_B0 * a.U + u32]);
+                    const int cls = (int)(m & 0xffu) < kSiteClasses ? (int)(m & 0xffu) : 0;
+                    const unsigned int pos = atomicAdd(&n_def, 1u);
+                    atomicAdd(&cnt[cls], 1u);
+                    t_var[pos] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                    t_idx[pos] = (unsigned short)local;
+                    t_cls[pos] = (unsigned char)cls;
+                    any = true;
+                }
+            }
+        }
+        if (__syncthreads_or(any)) {
+            if (threadIdx.x == 0) {
+                unsigned int acc = 0u;
+                for (int c = 0; c < kSiteClasses; ++c) { off[c] = acc; acc += cnt[c]; }
+                off[kSiteClasses] = acc;
+            }
+            __syncthreads();
+            const unsigned int total = off[kSiteClasses];
+            for (unsigned int i = threadIdx.x; i < total; i += kLocalBlock) {   // counting sort by regime class
+                const int c = t_cls[i];
+                const unsigned int pos = off[c] + atomicAdd(&fill[c], 1u);
+                s_var[pos] = t_var[i];
+                s_idx[pos] = t_idx[i];
+            }
+            __syncthreads();
+            for (unsigned int i = threadIdx.x; i < total; i += kLocalBlock) {
+                const uint32_t u = base + s_idx[i];
+                const SiteInputs<float> in = site_gather(a, s, u);
+                double var = s_var[i];
+                float v = 0.0f, rec[NSO], extra[NEX];
+                int cls = 0;
+                const int status = site_eval_fast_t<2>(s, in.p0, in.p1, in.pbm, in.pbs, a.mc, false, nullptr, var, v, rec, extra, cls);
+                if (status == SITE_DONE) site_scatter(a, s, (int64_t)u, v, rec, extra);
+                else {
+                    // leaves the fp32 forms after all: to the double worklist, and the marker must not be found again
+                    a.rec[((int64_t)s * NSO + SO_LQ) * a.U + u] = 0.0f;
+                    a.worklist[atomicAdd(a.work_count, 1u)] = (uint32_t)s * (uint32_t)a.U + u;
+                }
+            }
+        }
+        __syncthreads();   // the shared lists are reused by the next span
+    }
+}
+
 // A block scans kFallbackUPT * 128 markers of one site, compacts the hits into shared memory and then works through
 // them with dense warps: a trained model leaves the fp32 forms at a percent or so of its sites (draws in the far tail,
 // Rice expansion at small concentrations), and scattered over the warps every one of them would drag 31 idle lanes
@@ -886,12 +1004,29 @@ static int run_sites(const tq_patch_view* view, int64_t Nt, const ModelConst* mc
             int stm = cuda_status(cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work_count)");
             if (stm != TQ_OK) return stm;
         }
-        // four units per thread once the grid still covers the GPU several times over (>= 4 waves of 8 blocks per SM)
+        // eight units per thread once the grid still covers the GPU several times over (>= 4 waves of 8 blocks per SM)
 #ifndef TQ_SITE_UPT_BIG
 #define TQ_SITE_UPT_BIG 8   // B200, one rank's C3 shard after 3000 iterations: 608 (1 x 128 sites, 4 classes) -> 588 (4 x, 64 classes) -> 550 us (8 x)
 #endif
         const int64_t blocks4 = (a.U + TQ_SITE_UPT_BIG * kLocalBlock - 1) / (TQ_SITE_UPT_BIG * kLocalBlock);
-        if (blocks4 * NSAMP >= (int64_t)sm_count() * 8 * 4)
+        // TQ_SITE_SPLIT=1: the two passes as two launches (same bits either way).  Opt-in: measured on a B200 (one 8-GPU rank's
+        // C3 shard, site kernels at the initial point / after 1000 / 3000 iterations) 216 / 241 / 396 us against 190 / 236 / 438
+        // in one launch -- it wins once most height / width sites are deferred (a fit beyond ~2000 iterations) and loses before,
+        // where the few replays of a block overlap with other blocks' first pass only in the one-launch form
+        static const bool split = [] { const char* e = getenv("TQ_SITE_SPLIT"); return e && e[0] == '1'; }();
+        if (blocks4 * NSAMP >= (int64_t)sm_count() * 8 * 4 && split && ws) {
+            void* sym = nullptr;
+            int stc = cuda_status(cudaGetSymbolAddress(&sym, g_site_deferred), "cudaGetSymbolAddress(g_site_deferred)");
+            if (stc != TQ_OK) return stc;
+            unsigned int* n_deferred = static_cast<unsigned int*>(sym) + (((uintptr_t)st >> 8) & 7u);
+            stc = cuda_status(cudaMemsetAsync(n_deferred, 0, sizeof(unsigned int), st), "cudaMemsetAsync(n_deferred)");
+            if (stc != TQ_OK) return stc;
+            site_pass1_kernel<TQ_SITE_UPT_BIG><<<dim3((unsigned)blocks4, NSAMP), kLocalBlock, 0, st>>>(a, n_deferred);
+            TQ_LAUNCH_CHECK("site_pass1_kernel launch");
+            // one block per span, as in pass 1 (a single resident wave walking the spans was latency-bound: 69 us for the
+            // scan alone at 625 k units)
+            site_pass2_kernel<TQ_SITE_UPT_BIG><<<(unsigned)(blocks4 * NSAMP), kLocalBlock, 0, st>>>(a, n_deferred, (unsigned)blocks4);
+        } else if (blocks4 * NSAMP >= (int64_t)sm_count() * 8 * 4)
             site_fast_kernel<TQ_SITE_UPT_BIG><<<dim3((unsigned)blocks4, NSAMP), kLocalBlock, 0, st>>>(a);
         else
             site_fast_kernel<1><<<grid, kLocalBlock, 0, st>>>(a);
