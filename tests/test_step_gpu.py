@@ -45,18 +45,21 @@ CONFIGS = [
 ]
 
 
-@pytest.mark.parametrize("cfg", CONFIGS)
 # fp64 gradients: 1e-8 (the paired Rice expansion of the Beta reparameterisation gradient is
 # ill-conditioned near x = mean, evaluation order moves it at the 1e-9 level; see test_hostcheck_math)
-@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)])
+PRECISIONS = [(torch.float64, 1e-11, 1e-8), (torch.float32, 1e-6, 1e-5)]
+# `f64_only`: a single-unit minibatch leaves each gradient tensor with one unit's entries as its scale: d loss / d m_probs is
+# q1 q0 x (differences of the four log-likelihoods, |L| ~ 3e3), and fp32 rounding of L alone is 2e-4 absolute -- 3e-5 to 1e-4
+# of a gradient of 20-70 (the host build of the same arithmetic shows the same); in a real minibatch the tensor's scale is
+# ~1e3.  The launch-shape path that case is here for does not depend on the dtype.
+STEP_CASES = [pytest.param({k: v for k, v in cfg.items() if k != "f64_only"}, dtype, ltol, gtol,
+                           id=f"cfg{i}-{'f64' if dtype == torch.float64 else 'f32'}")
+              for i, cfg in enumerate(CONFIGS) for dtype, ltol, gtol in PRECISIONS
+              if not (cfg.get("f64_only") and dtype == torch.float32)]
+
+
+@pytest.mark.parametrize("cfg,dtype,ltol,gtol", STEP_CASES)
 def test_step_loss_and_grads_match_oracle(cfg, dtype, ltol, gtol):
-    cfg = dict(cfg)
-    if cfg.pop("f64_only", False) and dtype == torch.float32:
-        # a single unit leaves each gradient tensor with one unit's entries as its scale: d loss / d m_probs is
-        # q1 q0 x (differences of the four log-likelihoods, |L| ~ 3e3), and fp32 rounding of L alone is 2e-4 absolute -- 3e-5
-        # to 1e-4 of a gradient of 20-70 (the host build of the same arithmetic shows the same); in a real minibatch the
-        # tensor's scale is ~1e3.  The launch-shape path this case is here for is dtype-independent
-        pytest.skip("single-unit minibatch: launch-shape case, checked in float64")
     ds, data, params, ndx, fdx, noise = make_problem(**cfg)
     if dtype == torch.float32:  # both sides see the same fp32-rounded parameters and variates
         params = {k: v.float().double() for k, v in params.items()}
